@@ -1,0 +1,252 @@
+// D1+D2+D3: heat-map sigmoid -> candidate threshold -> per-level radix-select top-k ->
+// box decode -> dense level-major candidate list.  One CTA per problem; the keys of
+// one level live in shared memory, so the heat-map is read from HBM exactly once.
+//
+// Selection: key = fp32 bits of p (positive floats order like their bit patterns),
+// 0 for non-candidates.  An MSB-first 8-bit radix select (warp-aggregated shared
+// atomics into per-warp histograms) finds the k-th largest key T and how many
+// elements equal to T are needed; one ordered block scan then emits the survivors
+// in ascending location order: all keys > T plus the first `need` keys == T.
+#include "common.cuh"
+
+namespace fod {
+
+constexpr int kDecThreads = 1024;
+constexpr int kDecWarps = kDecThreads / 32;
+constexpr int kMaxLevelPixels = 40960;  // 160 KB of keys
+
+struct DecodeParams {
+  const float* hm[FOD_MAX_LEVELS];
+  const float* reg[FOD_MAX_LEVELS];
+  int H[FOD_MAX_LEVELS], W[FOD_MAX_LEVELS], stride[FOD_MAX_LEVELS];
+  int num_levels;
+  int hm_is_logit, reg_channels_last;
+  float thresh;
+  int pre_topk, cand_cap;
+};
+
+__global__ void __launch_bounds__(kDecThreads, 1)
+decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restrict__ scores, int64_t* __restrict__ loc,
+                   int32_t* __restrict__ level_count, int32_t* __restrict__ cand_count, uint32_t* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);
+  __shared__ int hist[kDecWarps][256];
+  __shared__ int warp_sums[kDecWarps];
+  __shared__ int sh[8];
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int out_base = 0;
+  for (int l = 0; l < prm.num_levels; ++l) {
+    const int H = prm.H[l], W = prm.W[l], n = H * W, stride = prm.stride[l];
+    const float* hm = prm.hm[l] + (size_t)p * n;
+    // ---- pass 0: keys + candidate count
+    int local = 0;
+    for (int i = tid; i < n; i += kDecThreads) {
+      float v = __ldg(hm + i);
+      float pr = prm.hm_is_logit ? 1.0f / (1.0f + expf(-v)) : v;
+      uint32_t k = (pr > prm.thresh) ? __float_as_uint(pr) : 0u;
+      keys[i] = k;
+      local += (k != 0u);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0) warp_sums[warp] = local;
+    __syncthreads();
+    if (warp == 0) {
+      int v = warp_sums[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sh[0] = v;
+    }
+    __syncthreads();
+    const int cnt = sh[0];
+    uint32_t T = 0u;   // select keys > T plus the first `need` keys == T
+    int need = 0;
+    if (cnt > prm.pre_topk) {
+      uint32_t prefix = 0u, mask = 0u;
+      int remaining = prm.pre_topk;
+      for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = tid; i < kDecWarps * 256; i += kDecThreads) (&hist[0][0])[i] = 0;
+        __syncthreads();
+        for (int i0 = 0; i0 < n; i0 += kDecThreads) {
+          int i = i0 + tid;
+          bool act = false;
+          int bin = 0;
+          if (i < n) {
+            uint32_t k = keys[i];
+            act = (k & mask) == prefix;
+            bin = (k >> shift) & 255;
+          }
+          unsigned am = __ballot_sync(0xffffffffu, act);
+          if (act) {
+            unsigned peers = __match_any_sync(am, bin);
+            if (lane == __ffs(peers) - 1) hist[warp][bin] += __popc(peers);
+          }
+          __syncwarp();
+        }
+        __syncthreads();
+        // column sums over the per-warp histograms, then a top-down scan by warp 0
+        if (tid < 256) {
+          int sum = 0;
+#pragma unroll 8
+          for (int w = 0; w < kDecWarps; ++w) sum += hist[w][tid];
+          hist[0][tid] = sum;
+        }
+        __syncthreads();
+        if (warp == 0) {
+          // lane handles bins [lane*8, lane*8+8); suffix sums from the top
+          int c[8], tot = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            c[j] = hist[0][lane * 8 + j];
+            tot += c[j];
+          }
+          int above = 0;  // elements in lanes above this one
+          int x = tot;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_down_sync(0xffffffffu, x, o);
+            if (lane + o < 32) x += y;
+          }
+          above = x - tot;
+          // the digit d is the highest bin with (count of bins >= d) >= remaining
+          if (above < remaining && above + tot >= remaining) {
+            int acc = above;
+            for (int j = 7; j >= 0; --j) {
+              if (acc + c[j] >= remaining) {
+                sh[1] = lane * 8 + j;
+                sh[2] = remaining - acc;
+                break;
+              }
+              acc += c[j];
+            }
+          }
+        }
+        __syncthreads();
+        prefix |= (uint32_t)sh[1] << shift;
+        mask |= 255u << shift;
+        remaining = sh[2];
+        __syncthreads();
+      }
+      T = prefix;
+      need = remaining;
+    }
+    // ---- ordered emission
+    const int nsel = min(cnt, prm.pre_topk);
+    if (out_base + nsel > prm.cand_cap && tid == 0) atomicOr(status, FOD_STATUS_CAND_OVERFLOW);
+    const float half = (float)(stride / 2);
+    const float fstride = (float)stride;
+    int gt_before = 0, eq_before = 0;
+    for (int i0 = 0; i0 < n; i0 += kDecThreads) {
+      int i = i0 + tid;
+      uint32_t k = (i < n) ? keys[i] : 0u;
+      int is_gt = (k > T) ? 1 : 0;
+      int is_eq = (T != 0u && k == T) ? 1 : 0;
+      int v = is_gt | (is_eq << 16);
+      // inclusive warp scan, then block offsets
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) warp_sums[warp] = x;
+      __syncthreads();
+      if (warp == 0) {
+        int w = warp_sums[lane], xs = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int y = __shfl_up_sync(0xffffffffu, xs, o);
+          if (lane >= o) xs += y;
+        }
+        warp_sums[lane] = xs - w;
+        if (lane == 31) sh[3] = xs;
+      }
+      __syncthreads();
+      int excl = warp_sums[warp] + x - v;
+      int tot = sh[3];
+      int gt_pos = gt_before + (excl & 0xffff);
+      int eq_pos = eq_before + (excl >> 16);
+      bool sel = is_gt || (is_eq && eq_pos < need);
+      if (sel) {
+        int o = out_base + gt_pos + min(eq_pos, need);
+        if (o < prm.cand_cap) {
+          int y = i / W, xx = i - y * W;
+          float gx = __fadd_rn((float)(xx * stride), half);
+          float gy = __fadd_rn((float)(y * stride), half);
+          float r0, r1, r2, r3;
+          if (prm.reg_channels_last) {
+            float4 r = ldg4(prm.reg[l] + ((size_t)p * n + i) * 4);
+            r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
+          } else {
+            const float* rp = prm.reg[l] + (size_t)p * 4 * n + i;
+            r0 = __ldg(rp); r1 = __ldg(rp + n); r2 = __ldg(rp + 2 * (size_t)n); r3 = __ldg(rp + 3 * (size_t)n);
+          }
+          float x1 = __fsub_rn(gx, __fmul_rn(r0, fstride));
+          float y1 = __fsub_rn(gy, __fmul_rn(r1, fstride));
+          float x2 = __fadd_rn(gx, __fmul_rn(r2, fstride));
+          float y2 = __fadd_rn(gy, __fmul_rn(r3, fstride));
+          x2 = fmaxf(x2, __fadd_rn(x1, 0.01f));
+          y2 = fmaxf(y2, __fadd_rn(y1, 0.01f));
+          size_t ob = (size_t)p * prm.cand_cap + o;
+          *reinterpret_cast<float4*>(boxes + ob * 4) = make_float4(x1, y1, x2, y2);
+          scores[ob] = __fsqrt_rn(__uint_as_float(k));
+          loc[ob] = i;
+        }
+      }
+      gt_before += tot & 0xffff;
+      eq_before += tot >> 16;
+      __syncthreads();
+    }
+    if (tid == 0) level_count[p * prm.num_levels + l] = nsel;
+    out_base += nsel;
+    __syncthreads();
+  }
+  if (tid == 0) cand_count[p] = min(out_base, prm.cand_cap);
+}
+
+}  // namespace fod
+
+using namespace fod;
+
+extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_level_t* levels,
+                               int num_levels, int num_problems, int hm_is_logit, int reg_channels_last,
+                               float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores,
+                               int64_t* loc, int32_t* level_count, int32_t* cand_count, uint32_t* status,
+                               fod_stream_t stream) {
+  FOD_REQUIRE(hm && reg && levels && boxes && scores && loc && level_count && cand_count && status,
+              "fod_decode_topk: null pointer");
+  FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_decode_topk: num_levels %d out of range", num_levels);
+  FOD_REQUIRE(num_problems >= 0 && pre_topk > 0 && cand_cap >= num_levels * pre_topk,
+              "fod_decode_topk: cand_cap %d < num_levels*pre_topk %d", cand_cap, num_levels * pre_topk);
+  FOD_REQUIRE(score_thresh >= 0.f, "fod_decode_topk: score_thresh must be >= 0");
+  if (num_problems == 0) return FOD_OK;
+  DecodeParams prm;
+  int maxpix = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    FOD_REQUIRE(hm[l] && reg[l], "fod_decode_topk: null level pointer");
+    FOD_REQUIRE(levels[l].height > 0 && levels[l].width > 0 && levels[l].stride > 0, "fod_decode_topk: bad level %d", l);
+    prm.hm[l] = hm[l];
+    prm.reg[l] = reg[l];
+    prm.H[l] = levels[l].height;
+    prm.W[l] = levels[l].width;
+    prm.stride[l] = levels[l].stride;
+    int px = levels[l].height * levels[l].width;
+    if (px > maxpix) maxpix = px;
+  }
+  if (maxpix > kMaxLevelPixels) {
+    set_error("fod_decode_topk: level with %d pixels exceeds the in-smem limit %d", maxpix, kMaxLevelPixels);
+    return FOD_ERR_CAPACITY;
+  }
+  prm.num_levels = num_levels;
+  prm.hm_is_logit = hm_is_logit;
+  prm.reg_channels_last = reg_channels_last;
+  prm.thresh = score_thresh;
+  prm.pre_topk = pre_topk;
+  prm.cand_cap = cand_cap;
+  size_t smem = (size_t)maxpix * sizeof(uint32_t);
+  FOD_CUDA_CALL(cudaFuncSetAttribute(decode_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  decode_topk_kernel<<<num_problems, kDecThreads, smem, as_stream(stream)>>>(prm, boxes, scores, loc, level_count,
+                                                                             cand_count, status);
+  FOD_CUDA_LAUNCH_CHECK("fod_decode_topk");
+  return FOD_OK;
+}

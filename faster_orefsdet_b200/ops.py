@@ -1,0 +1,253 @@
+"""Operator-level host wrappers: torch CUDA tensors in, C-ABI kernels underneath.
+
+Every function here launches hand-written sm_100a kernels from ``libfod_b200.so``
+on torch's current stream.  There is no PyTorch / CPU fallback: a CPU tensor or a
+missing library is an error.
+
+Layout: feature maps are passed as ordinary NCHW-shaped tensors but must be (or
+are made) ``torch.channels_last`` in memory, which is the NHWC layout the kernels
+read (include/fod_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import fod_level_t
+
+Tensor = torch.Tensor
+_vp = ctypes.c_void_p
+
+
+def _stream() -> _vp:
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[Tensor]) -> _vp:
+    return _vp(0) if t is None else _vp(t.data_ptr())
+
+
+def _chk(t: Tensor, dtype, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise _lib.FodError(f"{name}: expected a CUDA tensor (the detection head has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.FodError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+def nhwc(t: Tensor, name: str = "map") -> Tensor:
+    """Return ``t`` ([N,C,H,W] logical) with NHWC memory (no copy if already channels_last)."""
+    _chk(t, torch.float32, name)
+    if t.dim() != 4:
+        raise _lib.FodError(f"{name}: expected [N,C,H,W]")
+    # channels_last contiguity test that also works for N==1 / C==1 corner cases
+    n, c, h, w = t.shape
+    if t.stride() != (h * w * c, 1, w * c, c):
+        t = t.contiguous(memory_format=torch.channels_last)
+        if t.stride() != (h * w * c, 1, w * c, c):   # ambiguous strides (size-1 dims): force
+            t = t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    return t
+
+
+def _levels(maps: Sequence[Tensor], strides: Sequence[int]):
+    arr = (fod_level_t * len(maps))()
+    for i, (m, s) in enumerate(zip(maps, strides)):
+        arr[i].height, arr[i].width, arr[i].stride = int(m.shape[-2]), int(m.shape[-1]), int(s)
+    return arr
+
+
+def _ptr_array(ts: Sequence[Tensor]):
+    return (_vp * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def new_status(device) -> Tensor:
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+def check_status(status: Tensor) -> None:
+    """Synchronising read of the device status word; raises on any overflow bit."""
+    v = int(status.item()) & 0xFFFFFFFF
+    if v:
+        names = [n for b, n in ((1, "candidate list overflow"), (2, "proposal capacity overflow (ties above roi_cap)"),
+                                (4, "final-NMS row overflow")) if v & b]
+        raise _lib.FodError("device status: " + ", ".join(names))
+
+
+# --------------------------------------------------------------------------- Q1
+def support_taps(proto: Tensor) -> Tensor:
+    """proto [C,128,h,w] (one level, all classes) -> taps [C,7,128] (fsod_cen.py:458-460)."""
+    proto = nhwc(proto, "proto")
+    C, ch, h, w = proto.shape
+    if ch != 128:
+        raise _lib.FodError("support_taps: 128 channels expected")
+    taps = torch.empty((C, 7, 128), dtype=torch.float32, device=proto.device)
+    _lib.check(_lib.lib().fod_support_taps(_ptr(proto), C, h, w, _ptr(taps), _stream()), "fod_support_taps")
+    return taps
+
+
+# --------------------------------------------------------------------------- Q2+Q3
+def correlate(q: Tensor, taps: Tensor, w3: Tensor, b3: Tensor) -> Tensor:
+    """q [B,128,H,W], taps [C,7,128], w3 [128,256(,1,1)], b3 [128] -> attn [B*C,128,H,W]
+    (channels_last), problem-major (fsod_cen.py:463-470)."""
+    q = nhwc(q, "q")
+    B, ch, H, W = q.shape
+    C = taps.shape[0]
+    if ch != 128 or tuple(taps.shape[1:]) != (7, 128):
+        raise _lib.FodError("correlate: bad shapes")
+    w3 = _chk(w3, torch.float32, "w3").reshape(128, 256).contiguous()
+    b3 = _chk(b3, torch.float32, "b3").contiguous()
+    taps = _chk(taps, torch.float32, "taps").contiguous()
+    attn = torch.empty((B * C, 128, H, W), dtype=torch.float32, device=q.device, memory_format=torch.channels_last)
+    if attn.stride() != (H * W * 128, 1, W * 128, 128):
+        attn = torch.empty((B * C, H, W, 128), dtype=torch.float32, device=q.device).permute(0, 3, 1, 2)
+    _lib.check(_lib.lib().fod_correlate(_ptr(q), _ptr(taps), _ptr(w3), _ptr(b3), _ptr(attn), B, C, H, W, _stream()),
+               "fod_correlate")
+    return attn
+
+
+# --------------------------------------------------------------------------- D1-D3
+def decode_topk(hm: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[int], score_thresh: float,
+                pre_topk: int, status: Tensor, hm_is_logit: bool = True, cand_cap: Optional[int] = None):
+    """hm[l] [P,1,H,W], reg[l] [P,4,H,W] (either memory format) ->
+    (boxes [P,cap,4], scores [P,cap], loc [P,cap] i64, level_count [P,L] i32, cand_count [P] i32)
+    (fsod_rpn.py:1071-1181)."""
+    L = len(hm)
+    P = hm[0].shape[0]
+    dev = hm[0].device
+    hm = [_chk(h, torch.float32, "hm").reshape(P, h.shape[-2], h.shape[-1]).contiguous() for h in hm]
+    regs, cl = [], None
+    for r in reg:
+        _chk(r, torch.float32, "reg")
+        n, c, h, w = r.shape
+        is_cl = r.stride() == (h * w * c, 1, w * c, c)
+        if cl is None:
+            cl = is_cl
+        if is_cl != cl:
+            r = nhwc(r) if cl else r.contiguous()
+        elif not is_cl:
+            r = r.contiguous()
+        regs.append(r)
+    cap = cand_cap if cand_cap is not None else L * pre_topk
+    boxes = torch.empty((P, cap, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((P, cap), dtype=torch.float32, device=dev)
+    loc = torch.empty((P, cap), dtype=torch.int64, device=dev)
+    level_count = torch.empty((P, L), dtype=torch.int32, device=dev)
+    cand_count = torch.empty((P,), dtype=torch.int32, device=dev)
+    lv = _levels(hm, strides)
+    _lib.check(_lib.lib().fod_decode_topk(_ptr_array(hm), _ptr_array(regs), lv, L, P, int(hm_is_logit), int(bool(cl)),
+                                          float(score_thresh), int(pre_topk), cap, _ptr(boxes), _ptr(scores), _ptr(loc),
+                                          _ptr(level_count), _ptr(cand_count), _ptr(status), _stream()),
+               "fod_decode_topk")
+    return boxes, scores, loc, level_count, cand_count
+
+
+# --------------------------------------------------------------------------- N0
+def nms_proposals(boxes: Tensor, scores: Tensor, count: Optional[Tensor], iou_thresh: float, post_topk: int,
+                  roi_cap: int, status: Tensor):
+    """-> (keep [P,roi_cap] i64, out_boxes [P,roi_cap,4], out_scores [P,roi_cap], out_count [P] i32)
+    (fsod_rpn.py:1184-1210)."""
+    _chk(boxes, torch.float32, "boxes"), _chk(scores, torch.float32, "scores")
+    P, cap = scores.shape
+    dev = boxes.device
+    boxes, scores = boxes.contiguous(), scores.contiguous()
+    keep = torch.zeros((P, roi_cap), dtype=torch.int64, device=dev)
+    ob = torch.zeros((P, roi_cap, 4), dtype=torch.float32, device=dev)
+    os_ = torch.zeros((P, roi_cap), dtype=torch.float32, device=dev)
+    oc = torch.empty((P,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().fod_nms_proposals(_ptr(boxes), _ptr(scores), _ptr(count), P, cap, float(iou_thresh),
+                                            int(post_topk), int(roi_cap), _ptr(keep), _ptr(ob), _ptr(os_), _ptr(oc),
+                                            _ptr(status), _stream()), "fod_nms_proposals")
+    return keep, ob, os_, oc
+
+
+# --------------------------------------------------------------------------- R1 / P1
+def roi_align(feats: Sequence[Tensor], strides: Sequence[int], rois: Tensor, roi_count: Optional[Tensor],
+              problems_per_image: int, resolution: int, out: Optional[Tensor] = None, want_levels: bool = False):
+    """feats[l] [B,128,H,W]; rois [P,cap,4] -> pooled [P,cap,R*R,128] (bin-major, channel innermost)
+    (d2 poolers.py:190-250)."""
+    feats = [nhwc(f, "feat") for f in feats]
+    B = feats[0].shape[0]
+    _chk(rois, torch.float32, "rois")
+    rois = rois.contiguous()
+    P, cap = rois.shape[0], rois.shape[1]
+    if P != B * problems_per_image:
+        raise _lib.FodError("roi_align: rois.shape[0] must be batch * problems_per_image")
+    dev = rois.device
+    if out is None:
+        out = torch.zeros((P, cap, resolution * resolution, 128), dtype=torch.float32, device=dev)
+    lvl = torch.zeros((P, cap), dtype=torch.int32, device=dev) if want_levels else None
+    lv = _levels(feats, strides)
+    _lib.check(_lib.lib().fod_roi_align(_ptr_array(feats), lv, len(feats), B, int(problems_per_image), _ptr(rois),
+                                        _ptr(roi_count), cap, int(resolution), _ptr(out), _ptr(lvl), _stream()),
+               "fod_roi_align")
+    return (out, lvl) if want_levels else out
+
+
+# --------------------------------------------------------------------------- R2+R3
+def relation_head(pooled: Tensor, w_fold: Tensor, bias_cls: Tensor, w_out: Tensor, b_out: Tensor, rois: Tensor,
+                  roi_count: Optional[Tensor], problems_per_image: int, reg_weights: Sequence[float],
+                  want_raw: bool = False):
+    """-> (det_boxes [P,cap,4] unclipped, det_scores [P,cap][, logits [P,cap,2], deltas [P,cap,4]])
+    (fsod_roi_heads.py:482-520, custom_fast_rcnn.py:160-170, d2 box_regression.py:77-115)."""
+    P, cap = rois.shape[0], rois.shape[1]
+    dev = rois.device
+    for t, n in ((pooled, "pooled"), (w_fold, "w_fold"), (bias_cls, "bias_cls"), (w_out, "w_out"), (b_out, "b_out"),
+                 (rois, "rois")):
+        _chk(t, torch.float32, n)
+        if not t.is_contiguous():
+            raise _lib.FodError(f"relation_head: {n} must be contiguous")
+    if tuple(w_fold.shape) != (128, 8192) or tuple(w_out.shape) != (6, 128) or bias_cls.shape[-1] != 128:
+        raise _lib.FodError("relation_head: bad weight shapes")
+    det_boxes = torch.zeros((P, cap, 4), dtype=torch.float32, device=dev)
+    det_scores = torch.zeros((P, cap), dtype=torch.float32, device=dev)
+    logits = torch.zeros((P, cap, 2), dtype=torch.float32, device=dev) if want_raw else None
+    deltas = torch.zeros((P, cap, 4), dtype=torch.float32, device=dev) if want_raw else None
+    rw = (ctypes.c_float * 4)(*[float(x) for x in reg_weights])
+    _lib.check(_lib.lib().fod_relation_head(_ptr(pooled), _ptr(w_fold), _ptr(bias_cls), _ptr(w_out), _ptr(b_out),
+                                            _ptr(rois), _ptr(roi_count), P, int(problems_per_image), cap, rw,
+                                            _ptr(det_boxes), _ptr(det_scores), _ptr(logits), _ptr(deltas), _stream()),
+               "fod_relation_head")
+    return (det_boxes, det_scores, logits, deltas) if want_raw else (det_boxes, det_scores)
+
+
+# --------------------------------------------------------------------------- R4 / N1 / O1
+def final_detect(det_boxes: Tensor, det_scores: Tensor, roi_count: Optional[Tensor], problems_per_image: int,
+                 score_thresh: float, iou_thresh: float, max_det: int, image_hw: Tensor, out_hw: Optional[Tensor],
+                 status: Tensor):
+    """-> (boxes [B,max_det,4], scores [B,max_det], classes [B,max_det] i64, rows [B,max_det] i64, count [B] i32)
+    (d2 fast_rcnn.py:118-171, fsod_fast_rcnn.py:84-145, d2 postprocessing.py:9-75)."""
+    P, cap = det_scores.shape
+    B = P // problems_per_image
+    dev = det_boxes.device
+    _chk(det_boxes, torch.float32, "det_boxes"), _chk(det_scores, torch.float32, "det_scores")
+    det_boxes, det_scores = det_boxes.contiguous(), det_scores.contiguous()
+    ob = torch.zeros((B, max_det, 4), dtype=torch.float32, device=dev)
+    os_ = torch.zeros((B, max_det), dtype=torch.float32, device=dev)
+    ocls = torch.zeros((B, max_det), dtype=torch.int64, device=dev)
+    orow = torch.zeros((B, max_det), dtype=torch.int64, device=dev)
+    oc = torch.empty((B,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().fod_final_detect(_ptr(det_boxes), _ptr(det_scores), _ptr(roi_count), B,
+                                           int(problems_per_image), cap, float(score_thresh), float(iou_thresh),
+                                           int(max_det), _ptr(image_hw), _ptr(out_hw), _ptr(ob), _ptr(os_), _ptr(ocls),
+                                           _ptr(orow), _ptr(oc), _ptr(status), _stream()), "fod_final_detect")
+    return ob, os_, ocls, orow, oc
+
+
+# --------------------------------------------------------------------------- operator boundary
+def batched_nms(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_threshold: float) -> Tensor:
+    """Drop-in for detectron2.layers.batched_nms (d2 nms.py:10-30): returns kept indices,
+    score-descending.  Synchronises once to size the result, like the reference op."""
+    _chk(boxes, torch.float32, "boxes"), _chk(scores, torch.float32, "scores")
+    n = boxes.shape[0]
+    dev = boxes.device
+    boxes, scores = boxes.contiguous(), scores.contiguous()
+    if idxs is not None:
+        idxs = _chk(idxs, torch.int64, "idxs").contiguous()
+    keep = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+    cnt = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().fod_batched_nms(_ptr(boxes), _ptr(scores), _ptr(idxs), n, float(iou_threshold), _ptr(keep),
+                                          _ptr(cnt), _stream()), "fod_batched_nms")
+    return keep[: int(cnt.item())]

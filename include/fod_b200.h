@@ -1,0 +1,193 @@
+/*
+ * fod_b200.h - C ABI of the B200-native support-guided detection head
+ *              (Faster-OreFSDet hot path: correlation -> CenterNet2 proposal
+ *              decode -> NMS -> relation ROI head -> class-wise NMS).
+ *
+ * The reference (MVME-HBUT/Faster-OreFSDet) has no native code of its own: every
+ * stage below is a chain of ATen / torchvision calls made from Python.  Each
+ * entry point names the reference lines it replaces (paths relative to the
+ * reference root; "d2!/" = inside the vendored detectron2.7z).
+ *
+ * Conventions
+ *   - plain C symbols, raw DEVICE pointers, explicit sizes; no torch types.
+ *   - fp32 everywhere; index outputs are int64 (reference dtype) or int32 counts.
+ *   - feature maps are NHWC ("channels-last": [N][H][W][128], channel innermost),
+ *     128 channels (MODEL.FPN.OUT_CHANNELS).  A PyTorch NCHW tensor in
+ *     torch.channels_last memory format has exactly this layout.
+ *   - a "problem" is one (query image b, support class c) pair, p = b*C + c.
+ *   - the caller owns every buffer; the library allocates nothing, keeps no
+ *     global state, never synchronises, never touches the default stream;
+ *     every call is stream-ordered and CUDA-graph capturable.
+ *   - return value: FOD_OK or a negative FOD_ERR_* (fod_last_error() gives text).
+ *     Data-dependent overflow of a fixed-capacity output is reported on the
+ *     device in the caller's `status` word (FOD_STATUS_* bits) and must be
+ *     checked after the caller's own final synchronisation.
+ */
+#ifndef FOD_B200_H
+#define FOD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* fod_stream_t; /* == cudaStream_t */
+
+#define FOD_CHANNELS 128
+#define FOD_MAX_LEVELS 3
+#define FOD_NMS_MAX_BOXES 8192 /* per problem, limit of the in-smem sort */
+
+enum {
+  FOD_OK = 0,
+  FOD_ERR_BAD_ARG = -1,
+  FOD_ERR_CAPACITY = -2,   /* a static capacity argument exceeds a kernel limit */
+  FOD_ERR_CUDA = -3,       /* a CUDA runtime call failed; see fod_last_error */
+  FOD_ERR_UNSUPPORTED = -4 /* device is not sm_100 */
+};
+
+/* bits of the device-side status word */
+#define FOD_STATUS_CAND_OVERFLOW 1u     /* fod_decode_topk: more candidates than cand_cap   */
+#define FOD_STATUS_PROPOSAL_OVERFLOW 2u /* fod_nms_proposals: ties pushed R above roi_cap   */
+#define FOD_STATUS_DET_OVERFLOW 4u      /* fod_final_detect: more rows than FOD_NMS_MAX_BOXES */
+
+int fod_version(void);
+/* copies the calling thread's last error text (NUL-terminated) into buf */
+int fod_last_error(char* buf, size_t len);
+
+/* One FPN level of a batch of NHWC maps. */
+typedef struct {
+  int height; /* H_l */
+  int width;  /* W_l */
+  int stride; /* 8, 16, 32 */
+} fod_level_t;
+
+/* ---------------------------------------------------------------------------
+ * Q1  support taps.  Replaces the three nn.AdaptiveAvgPool2d calls per level per
+ * class per image of fewx/modeling/fsod/fsod_cen.py:458-460, 476-479, 498-500.
+ *   proto : [C][h][w][128] NHWC dense-head prototype of one level
+ *   taps  : [C][7][128]  rows: k11, k13[0..2] (left, centre, right), k31[0..2] (up, centre, down)
+ */
+int fod_support_taps(const float* proto, int num_classes, int h, int w, float* taps, fod_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Q2+Q3  depthwise correlation + 1x1 relation conv on one FPN level, fused.
+ * Replaces fsod_cen.py:463-470 (p3), :482-491 (p4), :502-509 (p5): four depthwise
+ * F.conv2d + ReLUs + adds + torch.cat + self.conv3 + ReLU.
+ *   q     : [B][H][W][128]            query map of this level
+ *   taps  : [C][7][128]               from fod_support_taps
+ *   w3    : [128][256]                conv3.weight (out, in) ; in = [attn-sum | q]
+ *   b3    : [128]
+ *   attn  : [B*C][H][W][128]          problem-major output
+ */
+int fod_correlate(const float* q, const float* taps, const float* w3, const float* b3, float* attn, int batch,
+                  int num_classes, int height, int width, fod_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * D1+D2+D3  heat-map sigmoid, candidate threshold, per-level top-k, box decode,
+ * level concatenation.  Replaces CenterNet.inference / predict_instances /
+ * predict_single_level, fewx/modeling/fsod/fsod_rpn.py:1071-1074, 1100-1110,
+ * 1116-1181 and compute_grids :782-800.
+ *   hm[l]   : [P][H_l][W_l]           agn_hm output (logits if hm_is_logit, else sigmoid already applied)
+ *   reg[l]  : [P][H_l][W_l][4] if reg_channels_last else [P][4][H_l][W_l]; relu(scale*bbox_pred), NOT yet x stride
+ *   boxes   : [P][cand_cap][4]        candidates, level-major, ascending location inside a level
+ *   scores  : [P][cand_cap]           sqrt(p)
+ *   loc     : [P][cand_cap] int64     location index y*W+x inside its level
+ *   level_count : [P][num_levels] int32 ; cand_count : [P] int32
+ * Selection rule when a level has more than pre_topk candidates: every p above
+ * the k-th largest plus the lowest-location ties at it (oracle/head_oracle.py).
+ * cand_cap must be >= num_levels * pre_topk.
+ */
+int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_level_t* levels, int num_levels,
+                    int num_problems, int hm_is_logit, int reg_channels_last, float score_thresh, int pre_topk,
+                    int cand_cap, float* boxes, float* scores, int64_t* loc, int32_t* level_count,
+                    int32_t* cand_count, uint32_t* status, fod_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * N0  class-agnostic NMS + post-NMS top-k.  Replaces nms_and_topK -> ml_nms ->
+ * batched_nms -> torchvision nms and the CPU kthvalue, fsod_rpn.py:1184-1210,
+ * CenterNet2/centernet/modeling/layers/ml_nms.py:4-31, d2!/layers/nms.py:10-30.
+ *   boxes/scores/count : candidate lists as written by fod_decode_topk
+ *   keep      : [P][roi_cap] int64    indices into the candidate list, score-descending
+ *   out_boxes : [P][roi_cap][4], out_scores : [P][roi_cap], out_count : [P] int32
+ * Semantics: stable descending sort, greedy suppression when
+ * inter/(area_i+area_j-inter) > iou_thresh (fp32 ratio, compared as double like
+ * torchvision's CPU kernel), then if more than post_topk survive keep every
+ * survivor whose score >= the post_topk-th best (ties kept).  post_topk <= 0
+ * disables the second step.
+ */
+int fod_nms_proposals(const float* boxes, const float* scores, const int32_t* count, int num_problems, int cand_cap,
+                      double iou_thresh, int post_topk, int roi_cap, int64_t* keep, float* out_boxes,
+                      float* out_scores, int32_t* out_count, uint32_t* status, fod_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * R1 / P1  multi-level ROIAlign (aligned=True, sampling_ratio=0) with FPN level
+ * assignment.  Replaces ROIPooler.forward + assign_boxes_to_levels +
+ * torchvision.ops.roi_align, d2!/modeling/poolers.py:22-58,190-250,
+ * d2!/layers/roi_align.py:49-65; call sites fsod_roi_heads.py:470-472 and
+ * fsod_cen.py:355-357 (support boxes).
+ *   feat[l]  : [B][H_l][W_l][128]
+ *   rois     : [P][roi_cap][4] xyxy in image pixels, roi_count [P] (NULL = all roi_cap valid)
+ *   problems_per_image : C (ROI row p reads image p / C)
+ *   pooled   : [P][roi_cap][R*R][128] (bin-major, channel innermost); rows >= count untouched
+ *   out_level: [P][roi_cap] int32 assigned level (may be NULL)
+ */
+int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
+                  int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap, int resolution,
+                  float* pooled, int32_t* out_level, fod_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * R2+R3  relation head on pooled ROI features, softmax, box decoding.
+ * Replaces CustomCascadeROIHeads._run_stage fsod_roi_heads.py:482-483,509-511,520
+ * (conv3/conv1/conv2 1x1 + fc1 + cls_score/bbox_pred), predict_probs
+ * CenterNet2/centernet/modeling/roi_heads/custom_fast_rcnn.py:160-170,
+ * Box2BoxTransform.apply_deltas d2!/modeling/box_regression.py:77-115.
+ * The three 1x1 convs and fc1 have no non-linearity between them and are folded
+ * on the host into one [128][8192] matrix plus a per-class bias.
+ *   pooled   : [P][roi_cap][64][128]
+ *   w_fold   : [128][8192]   k index = bin*128 + channel
+ *   bias_cls : [C][128]      per-class folded bias (support term + fc1 bias)
+ *   w_out    : [6][128], b_out [6] : rows 0-1 cls_score, rows 2-5 bbox_pred
+ *   reg_weights : HOST pointer, 4 floats (wx, wy, ww, wh) = ROI_BOX_CASCADE_HEAD.BBOX_REG_WEIGHTS[0]
+ *   det_boxes: [P][roi_cap][4] (unclipped), det_scores [P][roi_cap] (foreground probability)
+ *   logits/deltas (optional, may be NULL): [P][roi_cap][2] / [P][roi_cap][4]
+ */
+int fod_relation_head(const float* pooled, const float* w_fold, const float* bias_cls, const float* w_out,
+                      const float* b_out, const float* rois, const int32_t* roi_count, int num_problems,
+                      int problems_per_image, int roi_cap, const float* reg_weights, float* det_boxes,
+                      float* det_scores, float* logits, float* deltas, fod_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * R4 / N1 / O1  final class-wise NMS, top-k, rescale to the output resolution.
+ * Replaces fast_rcnn_inference_single_image d2!/modeling/roi_heads/fast_rcnn.py:118-171
+ * (and its N-way sibling fewx/modeling/fsod/fsod_fast_rcnn.py:84-145) followed by
+ * detector_postprocess d2!/modeling/postprocessing.py:9-75.
+ *   det_boxes/det_scores/roi_count : per problem, as written by fod_relation_head
+ *   rows of image b = problems b*C .. b*C+C-1 in class-major order
+ *   out_hw : [B][2] int32 requested output (height, width); image_hw as above
+ *   out_boxes [B][max_det][4], out_scores [B][max_det], out_classes [B][max_det] int64 (class index 0..C-1),
+ *   out_rows [B][max_det] int64 (c*roi_cap + r of the source row), out_count [B] int32
+ * Non-finite rows are dropped, boxes clipped to the image (Boxes.clip
+ * d2!/structures/boxes.py:192-207), score > score_thresh kept, boxes offset by
+ * class*(max_coordinate+1) (torchvision 0.8.2 batched_nms), greedy NMS, first
+ * max_det; then scale/clip/drop-empty.
+ */
+int fod_final_detect(const float* det_boxes, const float* det_scores, const int32_t* roi_count, int batch,
+                     int problems_per_image, int roi_cap, float score_thresh, double iou_thresh, int max_det,
+                     const int32_t* image_hw, const int32_t* out_hw, float* out_boxes, float* out_scores,
+                     int64_t* out_classes, int64_t* out_rows, int32_t* out_count, uint32_t* status,
+                     fod_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Generic batched_nms (operator-level boundary, d2!/layers/nms.py:10-30):
+ * one problem, boxes [n][4], scores [n], idxs [n] int64 (NULL = single class).
+ * keep [n] int64 score-descending, keep_count [1] int32.
+ */
+int fod_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int n, double iou_thresh,
+                    int64_t* keep, int32_t* keep_count, fod_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOD_B200_H */

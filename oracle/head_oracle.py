@@ -128,13 +128,13 @@ def centernet_head_level(attn: Tensor, sd: Dict[str, Tensor], level: int,
 # --------------------------------------------------------------------------- #
 # D1/D2: sigmoid, threshold, top-k, box decode      fsod_rpn.py:782-800, 1071-1074, 1116-1181
 # --------------------------------------------------------------------------- #
-def decode_level(hm_logits: Tensor, reg: Tensor, stride: int, cfg: HeadConfig
+def decode_level(hm_logits: Tensor, reg: Tensor, stride: int, cfg: HeadConfig, is_logit: bool = True
                  ) -> Tuple[Tensor, Tensor, Tensor]:
     """One image, one level.  hm_logits [H,W] (pre-sigmoid), reg [4,H,W]
     (post relu*scale, NOT yet multiplied by stride; fsod_rpn.py:1107 does that).
     Returns (loc int64 [n] ascending, boxes [n,4], scores [n])."""
     H, W = hm_logits.shape
-    p = torch.sigmoid(hm_logits).reshape(-1)                     # :1073, :1126-1127
+    p = (torch.sigmoid(hm_logits) if is_logit else hm_logits).reshape(-1)   # :1073, :1126-1127
     cand = torch.nonzero(p > cfg.inference_th).squeeze(1)        # :1131, :1147
     k = min(int(cand.numel()), cfg.pre_nms_topk)                 # :1132-1134
     if cand.numel() > k:                                         # :1157
