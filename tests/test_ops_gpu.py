@@ -130,7 +130,11 @@ def test_decode_topk_bit_exact_on_probabilities(ties, channels_last):
             assert int(lc[p, l]) == n
             assert np.array_equal(loc[p, off:off + n].cpu().numpy(), ref_loc.numpy())
             assert np.array_equal(boxes[p, off:off + n].cpu().numpy(), ref_boxes.numpy())
-            assert np.array_equal(scores[p, off:off + n].cpu().numpy(), ref_scores.numpy())
+            # torch's CPU sqrt goes through MKL VML on large tensors and is not correctly rounded
+            # (about 0.6 % of elements are 1 ulp off); numpy's is, like CUDA's sqrt.rn.
+            exact = np.sqrt(prob[l][p, 0].reshape(-1).numpy()[ref_loc.numpy()])
+            assert np.array_equal(scores[p, off:off + n].cpu().numpy(), exact)
+            assert_close(scores[p, off:off + n].cpu(), ref_scores, rtol=2e-7, atol=0, what="scores vs oracle")
             off += n
         assert int(cc[p]) == off
 
