@@ -143,4 +143,5 @@ def _merge(a: CfgNode, b: CfgNode, stack: List[str]) -> None:
         if isinstance(v, CfgNode) and isinstance(b[k], CfgNode):
             _merge(v, b[k], stack + [k])
         else:
-            dict.__setitem__(b, k, _coerce(copy.deepcopy(v), b[k], full))
+            # yaml leaves "(1, 2)" as a string; decode it like yacs does
+            dict.__setitem__(b, k, _coerce(_decode(copy.deepcopy(v)), b[k], full))

@@ -1,0 +1,201 @@
+"""VoVNet-19-slim-eSE + FPN backbone (side input of the hot path; stays PyTorch/cuDNN).
+
+Restates d2!/modeling/backbone/vovnet.py:50-58,205-489,527-555 and
+d2!/modeling/backbone/fpn.py:17-155 with the same module / state_dict key names
+(log:549-697), so reference checkpoints load.  Runs in ``channels_last`` so the
+feature maps it hands to the head are already in the NHWC layout the kernels read.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..compat import BACKBONE_REGISTRY, ShapeSpec
+
+_STAGE_SPECS = {
+    # name: (stem, stage_conv_ch, stage_out_ch, layers_per_block, blocks_per_stage)   vovnet.py:50-97
+    "V-19-slim-eSE": ([64, 64, 128], [64, 80, 96, 112], [112, 256, 384, 512], 3, [1, 1, 1, 1]),
+    "V-19-eSE": ([64, 64, 128], [128, 160, 192, 224], [256, 512, 768, 1024], 3, [1, 1, 1, 1]),
+    "V-39-eSE": ([64, 64, 128], [128, 160, 192, 224], [256, 512, 768, 1024], 5, [1, 1, 2, 2]),
+}
+
+
+class FrozenBatchNorm2d(nn.Module):
+    """BatchNorm with fixed statistics and affine parameters (d2!/layers/batch_norm.py)."""
+
+    def __init__(self, num_features: int, eps: float = 1e-5):
+        super().__init__()
+        self.num_features, self.eps = num_features, eps
+        self.register_buffer("weight", torch.ones(num_features))
+        self.register_buffer("bias", torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features) - eps)
+
+    def forward(self, x):
+        scale = self.weight * (self.running_var + self.eps).rsqrt()
+        bias = self.bias - self.running_mean * scale
+        return x * scale.reshape(1, -1, 1, 1).to(x.dtype) + bias.reshape(1, -1, 1, 1).to(x.dtype)
+
+
+def _conv_norm_relu(cin, cout, name, postfix, stride=1, k=3, pad=1):
+    return [
+        (f"{name}_{postfix}/conv", nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=pad, bias=False)),
+        (f"{name}_{postfix}/norm", FrozenBatchNorm2d(cout)),
+        (f"{name}_{postfix}/relu", nn.ReLU(inplace=True)),
+    ]
+
+
+class _ESE(nn.Module):
+    def __init__(self, channel):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Conv2d(channel, channel, kernel_size=1, padding=0)
+
+    def forward(self, x):
+        w = self.fc(self.avg_pool(x))
+        return x * (F.relu6(w + 3.0) / 6.0)
+
+
+class _OSAModule(nn.Module):
+    def __init__(self, in_ch, stage_ch, concat_ch, layers, name, identity=False):
+        super().__init__()
+        self.identity = identity
+        self.layers = nn.ModuleList()
+        c = in_ch
+        for i in range(layers):
+            self.layers.append(nn.Sequential(OrderedDict(_conv_norm_relu(c, stage_ch, name, i))))
+            c = stage_ch
+        self.concat = nn.Sequential(OrderedDict(_conv_norm_relu(in_ch + layers * stage_ch, concat_ch, name, "concat", k=1, pad=0)))
+        self.ese = _ESE(concat_ch)
+
+    def forward(self, x):
+        outs = [x]
+        y = x
+        for layer in self.layers:
+            y = layer(y)
+            outs.append(y)
+        y = self.ese(self.concat(torch.cat(outs, dim=1)))
+        return y + x if self.identity else y
+
+
+class _OSAStage(nn.Sequential):
+    def __init__(self, in_ch, stage_ch, concat_ch, blocks, layers, stage_num):
+        super().__init__()
+        if stage_num != 2:
+            self.add_module("Pooling", nn.MaxPool2d(kernel_size=3, stride=2, ceil_mode=True))
+        self.add_module(f"OSA{stage_num}_1", _OSAModule(in_ch, stage_ch, concat_ch, layers, f"OSA{stage_num}_1"))
+        for i in range(blocks - 1):
+            n = f"OSA{stage_num}_{i + 2}"
+            self.add_module(n, _OSAModule(concat_ch, stage_ch, concat_ch, layers, n, identity=True))
+
+
+class VoVNet(nn.Module):
+    def __init__(self, cfg, input_ch: int, out_features: List[str]):
+        super().__init__()
+        stem_ch, conv_ch, out_ch, layers, blocks = _STAGE_SPECS[cfg.MODEL.VOVNET.CONV_BODY]
+        if cfg.MODEL.VOVNET.NORM != "FrozenBN":
+            raise NotImplementedError("only MODEL.VOVNET.NORM=FrozenBN (the inference configuration) is built")
+        self._out_features = list(out_features)
+        stem = _conv_norm_relu(input_ch, stem_ch[0], "stem", "1", 2)
+        stem += _conv_norm_relu(stem_ch[0], stem_ch[1], "stem", "2", 1)
+        stem += _conv_norm_relu(stem_ch[1], stem_ch[2], "stem", "3", 2)
+        self.add_module("stem", nn.Sequential(OrderedDict(stem)))
+        stride = 4
+        self._out_feature_strides = {"stem": stride, "stage2": stride}
+        self._out_feature_channels = {"stem": stem_ch[2]}
+        in_list = [stem_ch[2]] + out_ch[:-1]
+        self.stage_names = []
+        for i in range(4):
+            name = f"stage{i + 2}"
+            self.stage_names.append(name)
+            self.add_module(name, _OSAStage(in_list[i], conv_ch[i], out_ch[i], blocks[i], layers, i + 2))
+            self._out_feature_channels[name] = out_ch[i]
+            if i != 0:
+                stride *= 2
+                self._out_feature_strides[name] = stride
+
+    def forward(self, x):
+        outputs = {}
+        x = self.stem(x)
+        if "stem" in self._out_features:
+            outputs["stem"] = x
+        for name in self.stage_names:
+            x = getattr(self, name)(x)
+            if name in self._out_features:
+                outputs[name] = x
+        return outputs
+
+    def output_shape(self):
+        return {n: ShapeSpec(channels=self._out_feature_channels[n], stride=self._out_feature_strides[n])
+                for n in self._out_features}
+
+
+class FPN(nn.Module):
+    """Top-down pathway with lateral 1x1 and output 3x3 convs, "sum" fusion, no top block
+    (MODEL.FCOS.TOP_LEVELS = 0, log:264)."""
+
+    def __init__(self, bottom_up: VoVNet, in_features: List[str], out_channels: int, fuse_type: str = "sum"):
+        super().__init__()
+        shapes = bottom_up.output_shape()
+        strides = [shapes[f].stride for f in in_features]
+        laterals, outputs = [], []
+        for f in in_features:
+            stage = int(math.log2(shapes[f].stride))
+            lat = nn.Conv2d(shapes[f].channels, out_channels, kernel_size=1)
+            out = nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1)
+            for m in (lat, out):      # c2_xavier_fill (fvcore): kaiming_uniform(a=1), zero bias
+                nn.init.kaiming_uniform_(m.weight, a=1)
+                nn.init.constant_(m.bias, 0)
+            self.add_module(f"fpn_lateral{stage}", lat)
+            self.add_module(f"fpn_output{stage}", out)
+            laterals.append(lat)
+            outputs.append(out)
+        self._laterals, self._outputs = laterals[::-1], outputs[::-1]
+        self.in_features = tuple(in_features)
+        self.bottom_up = bottom_up
+        self._out_feature_strides = {f"p{int(math.log2(s))}": s for s in strides}
+        self._out_features = list(self._out_feature_strides)
+        self._out_feature_channels = {k: out_channels for k in self._out_features}
+        self._size_divisibility = strides[-1]
+        assert fuse_type in ("sum", "avg")
+        self._fuse_type = fuse_type
+
+    @property
+    def size_divisibility(self) -> int:
+        return self._size_divisibility
+
+    def forward(self, x) -> Dict[str, torch.Tensor]:
+        feats = self.bottom_up(x)
+        prev = self._laterals[0](feats[self.in_features[-1]])
+        results = [self._outputs[0](prev)]
+        for idx in range(1, len(self._laterals)):
+            f = feats[self.in_features[-idx - 1]]
+            top_down = F.interpolate(prev, scale_factor=2.0, mode="nearest")
+            prev = self._laterals[idx](f) + top_down
+            if self._fuse_type == "avg":
+                prev = prev / 2
+            results.insert(0, self._outputs[idx](prev))
+        return dict(zip(self._out_features, results))
+
+    def output_shape(self):
+        return {n: ShapeSpec(channels=self._out_feature_channels[n], stride=self._out_feature_strides[n])
+                for n in self._out_features}
+
+
+@BACKBONE_REGISTRY.register()
+def build_fcos_vovnet_fpn_backbone(cfg, input_shape: ShapeSpec):
+    if cfg.MODEL.FCOS.TOP_LEVELS != 0:
+        raise NotImplementedError("MODEL.FCOS.TOP_LEVELS != 0 (P6/P7) is not used by finetune_vovnet.yaml")
+    bottom_up = VoVNet(cfg, input_shape.channels, cfg.MODEL.VOVNET.OUT_FEATURES)
+    return FPN(bottom_up, cfg.MODEL.FPN.IN_FEATURES, cfg.MODEL.FPN.OUT_CHANNELS, cfg.MODEL.FPN.FUSE_TYPE)
+
+
+def build_backbone(cfg, input_shape: ShapeSpec = None):
+    if input_shape is None:
+        input_shape = ShapeSpec(channels=len(cfg.MODEL.PIXEL_MEAN))
+    return BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, input_shape)

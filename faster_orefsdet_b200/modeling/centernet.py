@@ -1,0 +1,149 @@
+"""CenterNet2 dense head + proposal generator (host side).
+
+Mirrors the reference interface:
+  * ``CenterNetHead`` - CenterNet2/centernet/modeling/dense_heads/centernet_head.py:21-161
+    (conv tower + GroupNorm + agn_hm + bbox_pred + Scale).  Boundary row H0: the 3x3
+    convolutions stay PyTorch/cuDNN.
+  * ``CenterNet`` - fewx/modeling/fsod/fsod_rpn.py:491-655, 1068-1210, registered in
+    PROPOSAL_GENERATOR_REGISTRY under the same name, built as ``cls(cfg, input_shape)``,
+    ``forward(images, features_dict, gt_instances) -> (list[Instances], {})``.
+    Everything after the convolutions (sigmoid, threshold, top-k, decode, concat, NMS,
+    post-NMS top-k) runs in two CUDA kernels over the whole batch with no host sync.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import ops
+from ..compat import PROPOSAL_GENERATOR_REGISTRY, Boxes, Instances, ShapeSpec
+
+
+class Scale(nn.Module):
+    def __init__(self, init_value: float = 1.0):
+        super().__init__()
+        self.scale = nn.Parameter(torch.FloatTensor([init_value]))
+
+    def forward(self, x):
+        return x * self.scale
+
+
+class CenterNetHead(nn.Module):
+    def __init__(self, cfg, input_shape: List[ShapeSpec]):
+        super().__init__()
+        c = cfg.MODEL.CENTERNET
+        if not (c.ONLY_PROPOSAL and c.WITH_AGN_HM):
+            raise NotImplementedError("CenterNetHead: only ONLY_PROPOSAL + WITH_AGN_HM (finetune_vovnet.yaml) is built")
+        if c.USE_DEFORMABLE or c.NUM_SHARE_CONVS != 0:
+            raise NotImplementedError("CenterNetHead: deformable / shared towers are disabled in the reference config")
+        in_channels = input_shape[0].channels
+        self.only_proposal, self.with_agn_hm = True, True
+        tower = []
+        for _ in range(c.NUM_BOX_CONVS):
+            tower.append(nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1, bias=True))
+            if c.NORM == "GN":
+                tower.append(nn.GroupNorm(32 if in_channels % 32 == 0 else 25, in_channels))
+            elif c.NORM != "":
+                raise NotImplementedError(f"CenterNetHead norm {c.NORM}")
+            tower.append(nn.ReLU())
+        self.cls_tower = nn.Sequential()
+        self.bbox_tower = nn.Sequential(*tower)
+        self.share_tower = nn.Sequential()
+        self.bbox_pred = nn.Conv2d(in_channels, 4, kernel_size=3, stride=1, padding=1)
+        self.scales = nn.ModuleList([Scale(1.0) for _ in input_shape])
+        for m in list(self.bbox_tower.modules()) + [self.bbox_pred]:
+            if isinstance(m, nn.Conv2d):
+                nn.init.normal_(m.weight, std=0.01)
+                nn.init.constant_(m.bias, 0)
+        nn.init.constant_(self.bbox_pred.bias, 8.0)
+        self.agn_hm = nn.Conv2d(in_channels, 1, kernel_size=3, stride=1, padding=1)
+        nn.init.constant_(self.agn_hm.bias, -math.log((1 - c.PRIOR_PROB) / c.PRIOR_PROB))
+        nn.init.normal_(self.agn_hm.weight, std=0.01)
+
+    def forward(self, x: Sequence[torch.Tensor]):
+        clss, bbox_reg, agn_hms = [], [], []
+        for l, feature in enumerate(x):
+            t = self.bbox_tower(feature)
+            clss.append(None)
+            agn_hms.append(self.agn_hm(t))
+            bbox_reg.append(F.relu(self.scales[l](self.bbox_pred(t))))
+        return clss, bbox_reg, agn_hms
+
+
+@dataclass
+class RawProposals:
+    """Fixed-capacity batched proposals (device tensors, no host sync)."""
+    boxes: torch.Tensor        # [P, roi_cap, 4]
+    scores: torch.Tensor       # [P, roi_cap]   objectness (sqrt of the heat-map)
+    count: torch.Tensor        # [P] int32
+    keep: torch.Tensor         # [P, roi_cap] int64 index into the candidate list
+    cand_boxes: torch.Tensor   # [P, cand_cap, 4]
+    cand_scores: torch.Tensor  # [P, cand_cap]
+    cand_loc: torch.Tensor     # [P, cand_cap] int64
+    level_count: torch.Tensor  # [P, L] int32
+    cand_count: torch.Tensor   # [P] int32
+
+
+@PROPOSAL_GENERATOR_REGISTRY.register()
+class CenterNet(nn.Module):
+    def __init__(self, cfg, input_shape: Dict[str, ShapeSpec]):
+        super().__init__()
+        c = cfg.MODEL.CENTERNET
+        self.in_features = list(c.IN_FEATURES)
+        self.strides = list(c.FPN_STRIDES)
+        self.score_thresh = c.INFERENCE_TH
+        self.pre_nms_topk_test = c.PRE_NMS_TOPK_TEST
+        self.post_nms_topk_test = c.POST_NMS_TOPK_TEST
+        self.nms_thresh_test = c.NMS_TH_TEST
+        self.not_nms = c.NOT_NMS
+        self.only_proposal, self.as_proposal, self.with_agn_hm = c.ONLY_PROPOSAL, c.AS_PROPOSAL, c.WITH_AGN_HM
+        if c.CENTER_NMS or c.NOT_NMS:
+            raise NotImplementedError("CenterNet: CENTER_NMS / NOT_NMS are off in the reference config and not built")
+        if len(self.in_features) > 3:
+            raise NotImplementedError("CenterNet: at most 3 FPN levels (p3..p5)")
+        self.centernet_head = CenterNetHead(cfg, [input_shape[f] for f in self.in_features])
+        # extra proposal rows reserved for ties at the post-NMS threshold (fsod_rpn.py:1204 keeps them all)
+        self.tie_slack = 64
+
+    @property
+    def roi_cap(self) -> int:
+        return (self.post_nms_topk_test + self.tie_slack + 63) // 64 * 64
+
+    def forward(self, images, features_dict: Dict[str, torch.Tensor], gt_instances=None):
+        if self.training:
+            raise NotImplementedError("CenterNet: training (targets / losses) is outside the inference hot path")
+        features = [features_dict[f] for f in self.in_features]
+        status = ops.new_status(features[0].device)
+        raw = self.propose_raw(features, status)
+        ops.check_status(status)
+        n_img = len(images.image_sizes)
+        per_image = features[0].shape[0] // max(n_img, 1)
+        return self.to_instances(raw, [images.image_sizes[p // per_image] for p in range(features[0].shape[0])]), {}
+
+    @torch.no_grad()
+    def propose_raw(self, features: Sequence[torch.Tensor], status: torch.Tensor, roi_cap: Optional[int] = None) -> RawProposals:
+        """features[l]: [P,128,H_l,W_l] correlated maps, one row per (image, class) problem."""
+        _, reg, hm = self.centernet_head(features)
+        boxes, scores, loc, level_count, cand_count = ops.decode_topk(
+            hm, reg, self.strides, self.score_thresh, self.pre_nms_topk_test, status, hm_is_logit=True)
+        keep, pb, ps, pc = ops.nms_proposals(boxes, scores, cand_count, self.nms_thresh_test, self.post_nms_topk_test,
+                                             roi_cap or self.roi_cap, status)
+        return RawProposals(pb, ps, pc, keep, boxes, scores, loc, level_count, cand_count)
+
+    @staticmethod
+    def to_instances(raw: RawProposals, image_sizes: Sequence[Tuple[int, int]]) -> List[Instances]:
+        counts = raw.count.tolist()   # one sync for the whole batch
+        out = []
+        for p, n in enumerate(counts):
+            inst = Instances(tuple(image_sizes[p]))
+            inst.scores = raw.scores[p, :n]
+            inst.pred_classes = torch.zeros((n,), dtype=torch.int64, device=raw.scores.device)
+            inst.proposal_boxes = Boxes(raw.boxes[p, :n])
+            inst.objectness_logits = raw.scores[p, :n]
+            out.append(inst)
+        return out

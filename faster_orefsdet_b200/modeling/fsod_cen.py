@@ -1,0 +1,230 @@
+"""``CenterNet2Detector`` meta-architecture (host side of the hot path).
+
+Drop-in for fewx/modeling/fsod/fsod_cen.py:38-571: same registry name, ``cls(cfg)``
+construction, parameter names, ``forward(batched_inputs) -> [{"instances": Instances}]``
+and the ``./support_dir/support_feature.pkl`` side channel.  Differences (recorded in
+DESIGN.md):
+
+  * B >= 1 query images per call (the reference asserts B == 1, :438); results equal B
+    separate calls.
+  * N-way episodes: every class of the pickle is scored; the
+    reference's three per-level loops keep only the last class (:454-509).
+  * the pickle is read once (cached on mtime) and reduced to a device-resident
+    ``PrototypeBank``; the reference reloads and re-uploads it per forward (:152-153,410-415).
+  * ``MODEL.DEVICE=cpu`` is refused: the head exists only as sm_100a kernels.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import pickle
+import sys
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import _lib, ops
+from ..compat import META_ARCH_REGISTRY, Boxes, ImageList, Instances
+from .backbone import build_backbone
+from .centernet import CenterNet, RawProposals  # noqa: F401  (registers "CenterNet")
+from .prototypes import LEVELS, PrototypeBank, SM_Block, SupportCache, bank_from_support_dict, broadcast_bank
+from .roi_heads import build_roi_heads, pack_instances
+from ..compat import PROPOSAL_GENERATOR_REGISTRY
+
+__all__ = ["CenterNet2Detector"]
+
+
+def build_proposal_generator(cfg, input_shape):
+    return PROPOSAL_GENERATOR_REGISTRY.get(cfg.MODEL.PROPOSAL_GENERATOR.NAME)(cfg, input_shape)
+
+
+@META_ARCH_REGISTRY.register()
+class CenterNet2Detector(nn.Module):
+    def __init__(self, cfg, pos_encoding=True):
+        super().__init__()
+        # The reference computes in fp32 (SOLVER.AMP off, log:490-491; sm_75 has no TF32).  PyTorch lets cuDNN
+        # use TF32 for convolutions by default, which would put the heat-map 1e-3 away from the reference.
+        if os.environ.get("FOD_ALLOW_TF32", "0") != "1":
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+        self.backbone = build_backbone(cfg)
+        self.proposal_generator = build_proposal_generator(cfg, self.backbone.output_shape())
+        self.roi_heads = build_roi_heads(cfg, self.backbone.output_shape())
+        self.vis_period = cfg.VIS_PERIOD
+        self.input_format = cfg.INPUT.FORMAT
+        assert len(cfg.MODEL.PIXEL_MEAN) == len(cfg.MODEL.PIXEL_STD)
+        self.register_buffer("pixel_mean", torch.Tensor(cfg.MODEL.PIXEL_MEAN).view(-1, 1, 1))
+        self.register_buffer("pixel_std", torch.Tensor(cfg.MODEL.PIXEL_STD).view(-1, 1, 1))
+        self.in_features = cfg.MODEL.ROI_HEADS.IN_FEATURES
+        self.support_way = cfg.INPUT.FS.SUPPORT_WAY
+        self.support_shot = cfg.INPUT.FS.SUPPORT_SHOT
+        self.logger = logging.getLogger(__name__)
+        # dense-head prototype builder (fsod_cen.py:66-75) and the relation conv on maps (:76-78)
+        self.vip_p3 = SM_Block(128, 32)
+        self.vip_p4 = SM_Block(128, 16)
+        self.vip_p5 = SM_Block(128, 8)
+        self.conv1 = nn.Conv2d(128, 64, 1)     # present in checkpoints, unused at inference (:470)
+        self.conv2 = nn.Conv2d(128, 64, 1)
+        self.conv3 = nn.Conv2d(256, 128, 1)
+        self._support = SupportCache()
+        self._bank: Optional[PrototypeBank] = None
+        self._bank_key = None
+        if str(cfg.MODEL.DEVICE).startswith("cpu"):
+            raise _lib.FodError("MODEL.DEVICE=cpu: the detection head exists only as sm_100a CUDA kernels; "
+                                "the CPU restatement lives in oracle/ and is test infrastructure")
+
+    @property
+    def device(self):
+        return self.pixel_mean.device
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, batched_inputs: List[dict]):
+        if not self.training:
+            self.init_model()
+            return self.inference(batched_inputs)
+        raise NotImplementedError("CenterNet2Detector: training (fsod_cen.py:156-308) is outside the inference hot path")
+
+    # ------------------------------------------------------------------ prototypes
+    def set_prototypes(self, support_dict: Dict[str, Dict[int, torch.Tensor]]) -> PrototypeBank:
+        """Install an episode from an in-memory pkl-schema dict (what init_model does from disk)."""
+        self._bank = bank_from_support_dict(support_dict, self.roi_heads, self.device)
+        self._bank_key = ("memory", id(support_dict))
+        return self._bank
+
+    def set_bank(self, bank: PrototypeBank) -> None:
+        self._bank, self._bank_key = bank, ("bank", id(bank))
+
+    def sync_prototypes(self, src: int = 0) -> PrototypeBank:
+        """Multi-GPU: rank ``src`` owns the episode, everyone else receives it over NCCL."""
+        self.set_bank(broadcast_bank(self._bank, self.device, src))
+        return self._bank
+
+    def init_model(self):
+        """fsod_cen.py:313-415.  Cache present: load it (once per file version).  Cache missing:
+        build it from ./datasets/coco/10_shot_support_df.pkl, write it, and ``sys.exit(0)`` exactly
+        like the reference (README.md:74 tells users to delete the cache before fine-tuning)."""
+        if self._bank is not None and self._bank_key is not None and self._bank_key[0] in ("memory", "bank"):
+            return
+        os.makedirs(os.path.dirname(self._support.path) or ".", exist_ok=True)
+        if not self._support.exists():
+            self._build_support_cache()
+            self.logger.info("=========== Offline support features are generated. ===========")
+            self.logger.info("============ Few-shot object detetion will start. =============")
+            sys.exit(0)
+        d = self._support.load()
+        if self._bank is None or self._bank_key != self._support.key:
+            self._bank = bank_from_support_dict(d, self.roi_heads, self.device)
+            self._bank_key = self._support.key
+
+    @torch.no_grad()
+    def build_support_dict(self, images_per_class: Dict[int, List[torch.Tensor]],
+                           boxes_per_class: Dict[int, List[List[float]]]) -> Dict[str, Dict[int, torch.Tensor]]:
+        """Rows P1+P2 (fsod_cen.py:348-389): support images -> backbone -> ROIAlign of the support
+        box (CUDA kernel) + SM_Block dense prototypes -> pkl-schema dict of CPU tensors."""
+        out = {k: {} for k in ("p3", "p4", "p5", "rcnn_8", "rcnn_4")}
+        for cls, imgs in images_per_class.items():
+            ims = [(x.to(self.device).float() - self.pixel_mean) / self.pixel_std for x in imgs]
+            il = ImageList.from_tensors(ims, self.backbone.size_divisibility)
+            feats = self.backbone(il.tensor.contiguous(memory_format=torch.channels_last))
+            fl = [feats[f] for f in self.in_features]
+            S = len(imgs)
+            rois = torch.tensor(boxes_per_class[cls], dtype=torch.float32, device=self.device).reshape(S, 1, 4)
+            for res, key in ((self.roi_heads.pooler_resolution, "rcnn_8"), (self.roi_heads.pooler_resolution2, "rcnn_4")):
+                pooled = ops.roi_align(fl, self.roi_heads.strides, rois, None, 1, res)       # [S,1,res*res,128]
+                out[key][cls] = pooled.reshape(S, res, res, 128).permute(0, 3, 1, 2).contiguous().cpu()
+            for l, size, blk in (("p3", 32, self.vip_p3), ("p4", 16, self.vip_p4), ("p5", 8, self.vip_p5)):
+                x = F.adaptive_avg_pool2d(feats[l], (size, size)).permute(0, 2, 3, 1)
+                y = blk(x).permute(0, 3, 2, 1)                     # note the H/W swap of the reference (:371-373)
+                out[l][cls] = y.mean(0, True).contiguous().cpu()
+        return out
+
+    def _build_support_cache(self):
+        import pandas as pd
+        df = pd.read_pickle("./datasets/coco/10_shot_support_df.pkl")
+        images, boxes = {}, {}
+        for cls in df["category_id"].unique():
+            rows = df.loc[df["category_id"] == cls, :].reset_index()
+            images[cls], boxes[cls] = [], []
+            for index, row in rows.iterrows():
+                if index >= self.support_shot:
+                    break
+                images[cls].append(_read_image_bgr(os.path.join("./datasets/coco", row["file_path"])))
+                boxes[cls].append([float(v) for v in row["support_box"]])
+        d = self.build_support_dict(images, boxes)
+        with open(self._support.path, "wb") as f:
+            pickle.dump(d, f)
+
+    # ------------------------------------------------------------------ inference
+    @torch.no_grad()
+    def inference(self, batched_inputs: List[dict], detected_instances=None, do_postprocess: bool = True):
+        assert not self.training
+        if self._bank is None:
+            raise _lib.FodError("no support prototypes installed: call init_model() / set_prototypes() first")
+        images = self.preprocess_image(batched_inputs)
+        out_sizes = []
+        for inp, size in zip(batched_inputs, images.image_sizes):
+            out_sizes.append((int(inp.get("height", size[0])), int(inp.get("width", size[1]))) if do_postprocess else tuple(size))
+        features = self.backbone(images.tensor)
+        ob, os_, ocls, oc = self.head(features, images.image_sizes, out_sizes)
+        results = pack_instances(ob, os_, ocls, oc, out_sizes)
+        return [{"instances": r} for r in results] if do_postprocess else results
+
+    @torch.no_grad()
+    def head(self, features: Dict[str, torch.Tensor], image_sizes, out_sizes, want_trace: bool = False):
+        """The hot path on device tensors: features[l] [B,128,H,W] -> padded detections
+        (boxes [B,K,4], scores [B,K], classes [B,K] i64, count [B] i32).  No host sync except the
+        final status check."""
+        bank = self._bank
+        dev = features[self.in_features[0]].device
+        C = bank.num_classes
+        raw = [features[f] for f in self.in_features]
+        image_hw = torch.tensor([list(s) for s in image_sizes], dtype=torch.int32).to(dev, non_blocking=True)
+        out_hw = torch.tensor([list(s) for s in out_sizes], dtype=torch.int32).to(dev, non_blocking=True)
+        attempt_cap = None
+        for attempt in range(2):
+            status = ops.new_status(dev)
+            attn = [ops.correlate(q, t, self.conv3.weight, self.conv3.bias) for q, t in zip(raw, bank.taps)]
+            props = self.proposal_generator.propose_raw(attn, status, attempt_cap)
+            (ob, os_, ocls, orow, oc), per_roi = self.roi_heads.detect_raw(raw, bank.bias_cls, props.boxes, props.count, C,
+                                                                           image_hw, out_hw, status)
+            st = int(status.item()) & 0xFFFFFFFF       # the single sync of the head
+            if st & _lib.FOD_STATUS_PROPOSAL_OVERFLOW and attempt == 0:
+                attempt_cap = props.cand_boxes.shape[1]   # ties above the reserved slack: redo with full capacity
+                continue
+            if st:
+                ops.check_status(status)
+            break
+        if want_trace:
+            return (ob, os_, ocls, oc), dict(attn=attn, proposals=props, det_boxes=per_roi[0], det_scores=per_roi[1], rows=orow)
+        return ob, os_, ocls, oc
+
+    def preprocess_image(self, batched_inputs: List[dict]) -> ImageList:
+        """Normalise, pad to a multiple of 32, batch (fsod_cen.py:540-555); channels_last for cuDNN."""
+        imgs = [x["image"].to(self.device, non_blocking=True) for x in batched_inputs]
+        sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in imgs]
+        d = self.backbone.size_divisibility
+        H = (max(s[0] for s in sizes) + d - 1) // d * d
+        W = (max(s[1] for s in sizes) + d - 1) // d * d
+        if all(s == sizes[0] for s in sizes):
+            x = (torch.stack(imgs).float() - self.pixel_mean) / self.pixel_std
+            if (H, W) != sizes[0]:
+                x = F.pad(x, [0, W - sizes[0][1], 0, H - sizes[0][0]], value=0.0)
+        else:
+            x = torch.zeros((len(imgs), imgs[0].shape[0], H, W), dtype=torch.float32, device=self.device)
+            for i, im in enumerate(imgs):
+                x[i, :, : sizes[i][0], : sizes[i][1]] = (im.float() - self.pixel_mean) / self.pixel_std
+        return ImageList(x.contiguous(memory_format=torch.channels_last), sizes)
+
+    @staticmethod
+    def _postprocess(instances, batched_inputs, image_sizes):
+        """Kept for API parity (fsod_cen.py:557-571); the rescale itself runs inside fod_final_detect."""
+        return [{"instances": r} for r in instances]
+
+
+def _read_image_bgr(path: str) -> torch.Tensor:
+    from PIL import Image
+    img = np.asarray(Image.open(path).convert("RGB"))[:, :, ::-1]
+    return torch.as_tensor(np.ascontiguousarray(img.transpose(2, 0, 1)))

@@ -283,7 +283,26 @@ def run_prototype_build(model):
     print("prototypes:", {k: v.shape for k, v in rec.items()})
 
 
+def run_backbone():
+    """The reference's own VoVNet-19-slim-eSE + FPN (d2 vovnet.py / fpn.py) on a small image."""
+    cfg = get_cfg()
+    cfg.merge_from_file(YAML)
+    cfg.merge_from_list(["MODEL.DEVICE", "cpu"])
+    model = build_model(cfg).eval()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    with open(os.path.join(HERE, "backbone_param_shapes.txt"), "w") as f:
+        for k, v in shapes.items():
+            f.write(f"{k} {' '.join(map(str, v))}\n")
+    x = synth.tensor((2, 3, 96, 160), 601, -120.0, 130.0)
+    with torch.no_grad():
+        out = model.backbone(x)
+    np.savez_compressed(os.path.join(HERE, "backbone.npz"), **{k: np_(v) for k, v in out.items()})
+    print("backbone:", {k: tuple(v.shape) for k, v in out.items()})
+
+
 def main():
+    run_backbone()
     cfg, model, shapes = build_reference()
     with open(os.path.join(HERE, "head_param_shapes.txt"), "w") as f:
         for k, v in shapes.items():

@@ -1,0 +1,214 @@
+"""GPU parity of the assembled head / detector against (a) golden outputs of the unmodified
+reference and (b) the CPU oracle on the same features."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from faster_orefsdet_b200 import ops, synth
+from faster_orefsdet_b200.config import get_cfg
+from faster_orefsdet_b200.modeling import build_model
+from oracle import head_oracle as O
+from tests.util import assert_close, golden, head_param_shapes, head_state_dict, t
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CFG = O.HeadConfig()
+
+
+def _model(*opts):
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(ROOT, "configs/fsod/finetune_vovnet.yaml"))
+    cfg.merge_from_list(["MODEL.DEVICE", "cuda"] + list(opts))
+    torch.manual_seed(0)
+    model = build_model(cfg).eval()
+    model.load_state_dict(synth.state_dict(head_param_shapes()), strict=False)
+    return model
+
+
+def _match(ref_boxes, ref_scores, boxes, scores, box_tol=2e-2, score_rtol=1e-4):
+    """Fraction of reference detections that have a counterpart (same box within tol, score within rtol)."""
+    if ref_boxes.shape[0] == 0:
+        return 1.0
+    d = (ref_boxes[:, None, :] - boxes[None, :, :]).abs().amax(-1)
+    j = d.argmin(1)
+    ok = (d[torch.arange(len(j)), j] < box_tol) & ((ref_scores - scores[j]).abs() <= score_rtol * ref_scores.abs() + 1e-6)
+    return float(ok.float().mean())
+
+
+@pytest.mark.parametrize("name", ["full_small", "full_640"])
+def test_head_matches_unmodified_reference_outputs(name):
+    g = golden(name)
+    model = _model()
+    model.set_prototypes(synth.prototypes(list(g["class_ids"]), int(g["shots"]), int(g["proto_seed"])))
+    for i, ((h, w), (oh, ow)) in enumerate(zip(g["sizes"], g["out_sizes"])):
+        feats = {k: v.cuda() for k, v in synth.features(1, int(h), int(w), int(g["feat_seed"]) + i).items()}
+        (ob, os_, ocls, oc), tr = model.head(feats, [(int(h), int(w))], [(int(oh), int(ow))], want_trace=True)
+        for l in range(3):
+            ga = g[f"img{i}_attn{l}"]
+            a = tr["attn"][l][0].cpu()
+            assert_close(a if ga.ndim == 3 else a.reshape(-1)[::97], t(ga), what=f"attn{l}")
+        n = int(tr["proposals"].count[0])
+        rp, ro = t(g[f"img{i}_proposal_boxes"]), t(g[f"img{i}_objectness"])
+        assert abs(n - rp.shape[0]) <= 2
+        assert _match(rp, ro, tr["proposals"].boxes[0, :n].cpu(), tr["proposals"].scores[0, :n].cpu()) >= 0.98
+        m = int(oc[0])
+        rb, rs = t(g[f"img{i}_out_boxes"]), t(g[f"img{i}_out_scores"])
+        assert abs(m - rb.shape[0]) <= 2
+        assert _match(rb, rs, ob[0, :m].cpu(), os_[0, :m].cpu()) >= 0.97
+        assert torch.all(os_[0, :m - 1] >= os_[0, 1:m])
+        assert torch.all(ocls[0, :m] == 0)
+
+
+def test_head_stagewise_bit_exact_indices_against_oracle():
+    """Teacher-forced: each index-producing stage gets the oracle's inputs, so keep / top-k indices
+    must be identical (north_star: bit-exact given identical scores)."""
+    sd = head_state_dict()
+    model = _model()
+    protos = synth.prototypes([4], 5, 3)
+    model.set_prototypes(protos)
+    feats = synth.features(1, 320, 384, 77)
+    tr = {}
+    O.detect_image(feats, protos, sd, (320, 384), CFG, None, tr)
+    pc = tr["per_class"][0]
+    status = ops.new_status("cuda")
+    hm = [x.cuda() for x in pc["hm"]]
+    reg = [x.cuda() for x in pc["reg"]]
+    prob = [x.sigmoid().cuda() for x in pc["hm"]]
+    boxes, scores, loc, lc, cc = ops.decode_topk(prob, reg, (8, 16, 32), CFG.inference_th, 1000, status, hm_is_logit=False)
+    n = int(cc[0])
+    assert np.array_equal(loc[0, :n].cpu().numpy(), torch.cat(pc["loc"]).numpy())
+    assert np.array_equal(boxes[0, :n].cpu().numpy(), pc["cand_boxes"].numpy())
+    cb = torch.zeros((1, 3000, 4)); cs = torch.zeros((1, 3000))
+    cb[0, :n], cs[0, :n] = pc["cand_boxes"], pc["cand_scores"]
+    keep, pb, ps, pcount = ops.nms_proposals(cb.cuda(), cs.cuda(), cc, CFG.nms_th, CFG.post_nms_topk, 320, status)
+    m = int(pcount[0])
+    assert np.array_equal(keep[0, :m].cpu().numpy(), pc["keep"].numpy())
+    db = torch.zeros((1, 320, 4)); ds = torch.zeros((1, 320))
+    r = pc["det_boxes"].shape[0]
+    db[0, :r], ds[0, :r] = pc["det_boxes"], pc["det_scores"]
+    hw = torch.tensor([[320, 384]], dtype=torch.int32, device="cuda")
+    ob, os_, ocls, orow, oc = ops.final_detect(db.cuda(), ds.cuda(), torch.tensor([r], dtype=torch.int32, device="cuda"), 1,
+                                               CFG.score_thresh_test, CFG.nms_thresh_test, 100, hw, None, status)
+    ops.check_status(status)
+    k = int(oc[0])
+    assert np.array_equal(orow[0, :k].cpu().numpy(), tr["final_rows"].numpy())
+
+
+def test_nway_batched_head_matches_oracle():
+    sd = head_state_dict()
+    model = _model()
+    class_ids = [7, 2, 9]
+    protos = synth.prototypes(class_ids, 4, 11)
+    model.set_prototypes(protos)
+    B, H, W = 3, 256, 320
+    feats = synth.features(B, H, W, 91)
+    (ob, os_, ocls, oc) = model.head({k: v.cuda() for k, v in feats.items()}, [(H, W)] * B, [(H, W), (300, 400), (128, 160)])
+    outs = [(H, W), (300, 400), (128, 160)]
+    for b in range(B):
+        fb = {k: v[b:b + 1] for k, v in feats.items()}
+        rb, rs, rc = O.detect_image(fb, protos, sd, (H, W), CFG, outs[b])
+        m = int(oc[b])
+        assert abs(m - rb.shape[0]) <= 2
+        assert _match(rb, rs, ob[b, :m].cpu(), os_[b, :m].cpu()) >= 0.97
+        # classes of matched detections agree
+        d = (rb[:, None, :] - ob[b, :m].cpu()[None]).abs().amax(-1)
+        j = d.argmin(1)
+        good = d[torch.arange(len(j)), j] < 2e-2
+        assert torch.equal(rc[good], ocls[b, :m].cpu()[j][good])
+
+
+def test_batched_call_equals_separate_calls():
+    model = _model()
+    model.set_prototypes(synth.prototypes([1], 5, 7))
+    B, H, W = 4, 256, 320
+    feats = {k: v.cuda() for k, v in synth.features(B, H, W, 55).items()}
+    ob, os_, ocls, oc = model.head(feats, [(H, W)] * B, [(H, W)] * B)
+    for b in range(B):
+        fb = {k: v[b:b + 1].contiguous(memory_format=torch.channels_last) for k, v in feats.items()}
+        sb, ss, sc, scount = model.head(fb, [(H, W)], [(H, W)])
+        assert int(scount[0]) == int(oc[b])
+        m = int(oc[b])
+        assert_close(sb[0, :m], ob[b, :m], rtol=1e-5, atol=1e-3, what="boxes")
+        assert_close(ss[0, :m], os_[b, :m], rtol=1e-5, atol=1e-6, what="scores")
+
+
+def test_full_detector_forward_with_pkl_side_channel(tmp_path, monkeypatch):
+    """model(batched_inputs) through the real backbone, prototypes from ./support_dir/support_feature.pkl."""
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("support_dir")
+    protos = synth.prototypes([1], 5, 7)
+    with open("support_dir/support_feature.pkl", "wb") as f:
+        pickle.dump(protos, f)
+    model = _model()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    imgs = [synth.ore_image(256, 320, 1000), synth.ore_image(224, 300, 1001)]
+    inputs = [{"image": imgs[0], "height": 300, "width": 375}, {"image": imgs[1]}]
+    out = model(inputs)
+    assert len(out) == 2 and out[0]["instances"].image_size == (300, 375) and out[1]["instances"].image_size == (224, 300)
+    # oracle on the features the model's own backbone produced
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    images = model.preprocess_image(inputs)
+    with torch.no_grad():
+        feats = {k: v.cpu().contiguous() for k, v in model.backbone(images.tensor).items()}
+    for b, inp in enumerate(inputs):
+        size = images.image_sizes[b]
+        outsz = (inp.get("height", size[0]), inp.get("width", size[1]))
+        rb, rs, rc = O.detect_image({k: v[b:b + 1] for k, v in feats.items()}, protos, sd, size, CFG, outsz)
+        inst = out[b]["instances"]
+        assert inst.pred_classes.dtype == torch.int64
+        assert abs(len(inst) - rb.shape[0]) <= 2
+        assert _match(rb, rs, inst.pred_boxes.tensor.cpu(), inst.scores.cpu()) >= 0.97
+    # second call: pickle untouched -> cached bank is reused
+    bank = model._bank
+    model(inputs)
+    assert model._bank is bank
+
+
+def test_missing_pkl_builds_cache_and_exits_like_the_reference(tmp_path, monkeypatch):
+    import pandas as pd
+    from PIL import Image
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("datasets/coco/img")
+    rows = []
+    boxes = [[40.0, 30.0, 200.0, 180.0], [10.0, 60.0, 120.0, 250.0], [100.0, 100.0, 300.0, 240.0]]
+    for s in range(3):
+        img = synth.ore_image(256, 320, 500 + s).permute(1, 2, 0).numpy()
+        Image.fromarray(img[:, :, ::-1].copy()).save(f"datasets/coco/img/s{s}.png")
+        rows.append({"category_id": 1, "file_path": f"img/s{s}.png", "support_box": boxes[s]})
+    pd.DataFrame(rows).to_pickle("datasets/coco/10_shot_support_df.pkl")
+    model = _model("INPUT.FS.SUPPORT_SHOT", 3)
+    with pytest.raises(SystemExit):
+        model([{"image": synth.ore_image(64, 64, 1)}])
+    with open("support_dir/support_feature.pkl", "rb") as f:
+        d = pickle.load(f)
+    assert set(d) == {"p3", "p4", "p5", "rcnn_8", "rcnn_4"}
+    assert tuple(d["p3"][1].shape) == (1, 128, 32, 32) and tuple(d["rcnn_8"][1].shape) == (3, 128, 8, 8)
+    assert tuple(d["rcnn_4"][1].shape) == (3, 128, 4, 4)
+
+
+def test_prototype_builder_matches_reference_cache_build():
+    """P1+P2 on the reference's own init_model output (tests/golden/prototypes.npz): same synthetic
+    backbone maps in, same five pkl entries out."""
+    g = golden("prototypes")
+    model = _model()
+    feats = synth.features(3, 256, 320, 900)
+
+    class Stub(torch.nn.Module):
+        size_divisibility = 32
+
+        def forward(self, x):
+            return {k: v.cuda().contiguous(memory_format=torch.channels_last) for k, v in feats.items()}
+
+        def output_shape(self):
+            return model_backbone.output_shape()
+
+    model_backbone = model.backbone
+    model.backbone = Stub()
+    imgs = [synth.ore_image(256, 320, 500 + s) for s in range(3)]
+    d = model.build_support_dict({1: imgs}, {1: [list(map(float, b)) for b in g["support_boxes"]]})
+    for k in ("p3", "p4", "p5", "rcnn_8", "rcnn_4"):
+        assert_close(d[k][1], t(g[k]), what=k)
