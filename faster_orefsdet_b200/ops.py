@@ -177,7 +177,7 @@ def roi_align(feats: Sequence[Tensor], strides: Sequence[int], rois: Tensor, roi
         raise _lib.FodError("roi_align: rois.shape[0] must be batch * problems_per_image")
     dev = rois.device
     if out is None:
-        out = torch.zeros((P, cap, resolution * resolution, 128), dtype=torch.float32, device=dev)
+        out = torch.empty((P, cap, resolution * resolution, 128), dtype=torch.float32, device=dev)
     lvl = torch.zeros((P, cap), dtype=torch.int32, device=dev) if want_levels else None
     lv = _levels(feats, strides)
     _lib.check(_lib.lib().fod_roi_align(_ptr_array(feats), lv, len(feats), B, int(problems_per_image), _ptr(rois),

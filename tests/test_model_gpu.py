@@ -112,12 +112,15 @@ def test_nway_batched_head_matches_oracle():
         rb, rs, rc = O.detect_image(fb, protos, sd, (H, W), CFG, outs[b])
         m = int(oc[b])
         assert abs(m - rb.shape[0]) <= 2
-        assert _match(rb, rs, ob[b, :m].cpu(), os_[b, :m].cpu()) >= 0.97
-        # classes of matched detections agree
-        d = (rb[:, None, :] - ob[b, :m].cpu()[None]).abs().amax(-1)
-        j = d.argmin(1)
-        good = d[torch.arange(len(j)), j] < 2e-2
-        assert torch.equal(rc[good], ocls[b, :m].cpu()[j][good])
+        gb, gs, gc = ob[b, :m].cpu(), os_[b, :m].cpu(), ocls[b, :m].cpu()
+        assert set(gc.tolist()) <= {0, 1, 2}
+        matched = 0.0
+        for c in range(3):       # match class by class: different classes may propose the same box
+            if int((rc == c).sum()) == 0:
+                continue
+            assert int((gc == c).sum()) > 0
+            matched += _match(rb[rc == c], rs[rc == c], gb[gc == c], gs[gc == c]) * int((rc == c).sum())
+        assert matched / rb.shape[0] >= 0.97
 
 
 def test_batched_call_equals_separate_calls():
