@@ -179,3 +179,19 @@ def test_full_forward_small_matches_reference():
 
 def test_full_forward_640_matches_reference():
     _run_full("full_640")
+
+
+def test_c_restatement_of_nms_equals_torchvision_and_reference():
+    from oracle import nms_c
+    g = golden("ops")
+    boxes, scores, idxs = _nms_inputs()
+    for thr in (0.6, 0.9):
+        assert np.array_equal(nms_c.batched_nms(boxes, scores, None, thr).numpy(), g[f"nms1_keep_{thr}"])
+        assert np.array_equal(nms_c.batched_nms(boxes, scores, idxs, thr).numpy(), g[f"nms3_keep_{thr}"])
+    for n, seed in ((0, 1), (1, 2), (3000, 3)):
+        ctr = synth.tensor((n, 2), seed, 20.0, 600.0)
+        wh = synth.tensor((n, 2), seed + 50, 8.0, 190.0)
+        b = torch.cat((ctr - wh / 2, ctr + wh / 2), 1)
+        s = torch.round(synth.tensor((n,), seed + 99, 0.0, 1.0) * 100) / 100
+        ref = O.batched_nms_coordinate_trick(b, s, torch.zeros(n, dtype=torch.long), 0.6)
+        assert np.array_equal(nms_c.batched_nms(b, s, None, 0.6).numpy(), ref.numpy())
