@@ -42,6 +42,41 @@ class FrozenBatchNorm2d(nn.Module):
         return x * scale.reshape(1, -1, 1, 1).to(x.dtype) + bias.reshape(1, -1, 1, 1).to(x.dtype)
 
 
+class ConvNormReLUSeq(nn.Sequential):
+    """Sequential of (conv, FrozenBN, ReLU) triples, named like the reference (``X/conv``, ``X/norm``,
+    ``X/relu``).  At inference the frozen BN is folded into the convolution (weight * scale, bias through
+    cuDNN's fused epilogue) and the ReLU is in place, so a triple costs one conv and one vectorised
+    elementwise pass instead of a broadcast multiply-add over the whole activation."""
+
+    def __init__(self, *args):
+        super().__init__(*args)
+        self._fold_cache = {}
+
+    def _folded(self, i, conv, norm):
+        key = (conv.weight.data_ptr(), conv.weight._version, norm.weight._version, norm.bias._version,
+               norm.running_mean._version, norm.running_var._version, conv.weight.device, conv.weight.stride())
+        hit = self._fold_cache.get(i)
+        if hit is None or hit[0] != key:
+            scale = norm.weight * (norm.running_var + norm.eps).rsqrt()
+            w = (conv.weight * scale.reshape(-1, 1, 1, 1)).contiguous(memory_format=torch.channels_last)
+            b = norm.bias - norm.running_mean * scale
+            hit = (key, w.detach(), b.detach())
+            self._fold_cache[i] = hit
+        return hit[1], hit[2]
+
+    def forward(self, x):
+        mods = list(self.children())
+        if self.training or len(mods) % 3 != 0:
+            for m in mods:
+                x = m(x)
+            return x
+        for i in range(0, len(mods), 3):
+            conv, norm, _ = mods[i:i + 3]
+            w, b = self._folded(i, conv, norm)
+            x = F.relu_(F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups))
+        return x
+
+
 def _conv_norm_relu(cin, cout, name, postfix, stride=1, k=3, pad=1):
     return [
         (f"{name}_{postfix}/conv", nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=pad, bias=False)),
@@ -68,9 +103,9 @@ class _OSAModule(nn.Module):
         self.layers = nn.ModuleList()
         c = in_ch
         for i in range(layers):
-            self.layers.append(nn.Sequential(OrderedDict(_conv_norm_relu(c, stage_ch, name, i))))
+            self.layers.append(ConvNormReLUSeq(OrderedDict(_conv_norm_relu(c, stage_ch, name, i))))
             c = stage_ch
-        self.concat = nn.Sequential(OrderedDict(_conv_norm_relu(in_ch + layers * stage_ch, concat_ch, name, "concat", k=1, pad=0)))
+        self.concat = ConvNormReLUSeq(OrderedDict(_conv_norm_relu(in_ch + layers * stage_ch, concat_ch, name, "concat", k=1, pad=0)))
         self.ese = _ESE(concat_ch)
 
     def forward(self, x):
@@ -104,7 +139,7 @@ class VoVNet(nn.Module):
         stem = _conv_norm_relu(input_ch, stem_ch[0], "stem", "1", 2)
         stem += _conv_norm_relu(stem_ch[0], stem_ch[1], "stem", "2", 1)
         stem += _conv_norm_relu(stem_ch[1], stem_ch[2], "stem", "3", 2)
-        self.add_module("stem", nn.Sequential(OrderedDict(stem)))
+        self.add_module("stem", ConvNormReLUSeq(OrderedDict(stem)))
         stride = 4
         self._out_feature_strides = {"stem": stride, "stage2": stride}
         self._out_feature_channels = {"stem": stem_ch[2]}

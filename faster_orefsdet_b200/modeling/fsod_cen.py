@@ -50,6 +50,10 @@ class CenterNet2Detector(nn.Module):
         if os.environ.get("FOD_ALLOW_TF32", "0") != "1":
             torch.backends.cudnn.allow_tf32 = False
             torch.backends.cuda.matmul.allow_tf32 = False
+        # cuDNN's heuristic picks FFT / legacy SIMT engines for the fp32 convolutions of the backbone on sm_100;
+        # letting it time the candidates once per shape is worth ~20 % of a step (profiles/r1_step_breakdown.md).
+        if os.environ.get("FOD_CUDNN_BENCHMARK", "1") == "1":
+            torch.backends.cudnn.benchmark = True
         self.backbone = build_backbone(cfg)
         self.proposal_generator = build_proposal_generator(cfg, self.backbone.output_shape())
         self.roi_heads = build_roi_heads(cfg, self.backbone.output_shape())
