@@ -1,0 +1,458 @@
+// Q2+Q3 on the 5th-generation tensor cores: depthwise support correlation fused with the 1x1 relation
+// conv (fsod_cen.py:463-470, 482-491, 502-509), all FPN levels and all (image, class) problems in ONE
+// persistent launch.
+//
+//   attn[p][y][x][:] = relu( W3 . [ s(y,x,:) | q(y,x,:) ] + b3 ),   s = a + b + q,
+//   a = relu(k11 * relu(k11 * q)),   b = relu(conv3x1_k31(relu(conv1x3_k13(q))))   (zero padding)
+//
+// Design (B200, sm_100a)
+//   * work unit = tile of 8 x 16 pixels of one problem (128 rows of the GEMM).  CTAs run as pairs (cluster of 2,
+//     tcgen05 cta_group::2): one MMA covers both CTAs' tiles (M = 256) against W3 (N = 128) whose rows are split
+//     between the two CTAs, so each CTA keeps only half of the weights resident in shared memory (hi + lo tf32
+//     parts of 64 x 256 fp32 = 128 KB) for the whole kernel.
+//   * fp32 accuracy on tf32 tensor cores by operand splitting (3xTF32): x = hi + lo, A.B ~ Ahi.Bhi + Alo.Bhi +
+//     Ahi.Blo, fp32 accumulation in tensor memory; measured error ~1e-6 relative (tools/tc_probe.cu).
+//   * the query tile (+1 pixel halo, zero-filled outside the image by TMA) is staged channel-chunk-wise
+//     (32 channels = one 128-byte swizzled row per pixel) into a 3-deep shared-memory ring by TMA.
+//   * 8 "stencil" warps build the A operand: one pixel per lane, they read the 3x3 neighbourhood from the ring,
+//     evaluate s, split s and q into hi/lo and write them straight into TENSOR MEMORY (tcgen05.st): the A operand
+//     never exists in shared or global memory, and the MMA reads only the weights from shared memory.
+//   * one thread of the leader CTA issues the MMAs (24 per chunk), completion is tracked with tcgen05.commit
+//     multicast to both CTAs; accumulators are double buffered in tensor memory (2 x 128 columns).
+//   * 4 epilogue warps: tcgen05.ld -> + bias, ReLU -> swizzled staging tile -> TMA store (clipped at the image
+//     border by the tensor map).
+//   HBM traffic = read q once + write attn once = 1024 B per pixel per problem.
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace fod {
+
+using namespace tc;
+
+namespace ctc {
+
+constexpr int kTileH = 8, kTileW = 16, kTilePx = 128;
+constexpr int kHaloH = kTileH + 2, kHaloW = kTileW + 2, kHaloPx = kHaloH * kHaloW;  // 10 x 18 = 180
+constexpr int kChunk = 32;                                                           // channels per chunk
+constexpr int kNumChunks = kC / kChunk;                                              // 4
+constexpr int kQStages = 3, kAStages = 2, kAccStages = 2;
+constexpr uint32_t kQStageBytes = kHaloPx * 128;         // 23040
+constexpr uint32_t kQStageStride = 23552;                // rounded up to 1024
+constexpr uint32_t kBHalfRows = 64;                      // W3 rows per CTA
+constexpr uint32_t kBChunkBytes = kBHalfRows * 128;      // 8192: one 32-wide K chunk
+constexpr uint32_t kBPartBytes = 8 * kBChunkBytes;       // 65536: K = 256
+constexpr uint32_t kStageOutBytes = kTilePx * 128;       // 16384
+
+// shared memory map (offsets from the 1024-aligned base)
+constexpr uint32_t kOffBHi = 0;
+constexpr uint32_t kOffBLo = kOffBHi + kBPartBytes;
+constexpr uint32_t kOffQ = kOffBLo + kBPartBytes;
+constexpr uint32_t kOffOut = kOffQ + kQStages * kQStageStride;
+constexpr uint32_t kOffTaps = kOffOut + kStageOutBytes;          // 2 x [7][128] fp32
+constexpr uint32_t kOffBias = kOffTaps + 2 * 7 * kC * 4;
+constexpr uint32_t kOffBars = kOffBias + kC * 4;
+constexpr uint32_t kNumBars = 2 * kQStages + 2 * kAStages + 2 * kAccStages;
+constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
+constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;
+
+constexpr int kThreads = 512;
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpEpi0 = 4, kWarpSten0 = 8;
+
+// tensor memory columns
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColA = 0;      // 2 stages x [s_hi 32 | s_lo 32 | q_hi 32 | q_lo 32]
+constexpr uint32_t kColAcc = 256;  // 2 stages x 128
+
+struct Level {
+  int H, W, tiles_x, tiles_per_problem, tile_begin;
+  const float* taps;  // [C][7][128]
+};
+
+struct Params {
+  CUtensorMap in_map[FOD_MAX_LEVELS];   // [B][H][W][128], box 32 x 18 x 10
+  CUtensorMap out_map[FOD_MAX_LEVELS];  // [P][H][W][128], box 32 x 16 x 8
+  Level lv[FOD_MAX_LEVELS];
+  const float* w3;
+  const float* b3;
+  int num_levels, num_classes, total_tiles, num_pairs;
+};
+
+struct TileCoord {
+  int level, p, y0, x0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const Params& P, int t) {
+  int l = 0;
+  if (P.num_levels > 1 && t >= P.lv[1].tile_begin) l = 1;
+  if (P.num_levels > 2 && t >= P.lv[2].tile_begin) l = 2;
+  const Level& L = P.lv[l];
+  int r = t - L.tile_begin;
+  int p = r / L.tiles_per_problem;
+  int tt = r - p * L.tiles_per_problem;
+  int ty = tt / L.tiles_x;
+  TileCoord tc;
+  tc.level = l;
+  tc.p = p;
+  tc.y0 = ty * kTileH;
+  tc.x0 = (tt - ty * L.tiles_x) * kTileW;
+  return tc;
+}
+
+__device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 f4_relu(float4 v) {
+  return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+}
+__device__ __forceinline__ float4 f4_mul(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) {
+  return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_constant__ Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+
+  // barrier addresses
+  const uint32_t bar0 = sbase + kOffBars;
+  auto q_full = [&](int s) { return bar0 + 8u * s; };
+  auto q_empty = [&](int s) { return bar0 + 8u * (kQStages + s); };
+  auto a_full = [&](int s) { return bar0 + 8u * (2 * kQStages + s); };
+  auto a_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + kAStages + s); };
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kAStages + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kAStages + kAccStages + s); };
+
+  if (tid == 0) {
+    for (int s = 0; s < kQStages; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 8);
+    }
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(a_full(s), 16);  // 8 stencil warps x 2 CTAs (used in the leader only)
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 8);  // 4 epilogue warps x 2 CTAs (leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == kWarpAlloc) {
+    tmem_alloc<2>(sbase + kOffTmemPtr, kTmemCols);
+    tmem_relinquish<2>();
+  }
+  if (warp == kWarpTma && lane == 0) {
+    for (int l = 0; l < P.num_levels; ++l) {
+      tma_prefetch_desc(&P.in_map[l]);
+      tma_prefetch_desc(&P.out_map[l]);
+    }
+  }
+  // resident weights: this CTA's 64 rows of W3, split into tf32 hi / lo, K-major SW128 chunks
+  {
+    const float* wsrc = P.w3 + (size_t)rank * kBHalfRows * 256;
+    for (int i = tid; i < (int)kBHalfRows * 64; i += kThreads) {  // float4 index: 64 per row
+      int r = i >> 6, c = (i & 63) << 2;
+      float4 v = ldg4(wsrc + (size_t)r * 256 + c);
+      float x[4] = {v.x, v.y, v.z, v.w};
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x[j]));
+        hi[j] = h;
+        lo[j] = __float_as_uint(x[j] - __uint_as_float(h));
+      }
+      uint32_t off = (uint32_t)(c >> 5) * kBChunkBytes + sw128_offset(r, c & 31);
+      *reinterpret_cast<uint4*>(smem + kOffBHi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(smem + kOffBLo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    if (tid < kC) reinterpret_cast<float*>(smem + kOffBias)[tid] = P.b3[tid];
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+
+  // static schedule: iteration i of pair k handles tiles 2*(i*num_pairs + k) + rank
+  const int T = P.total_tiles;
+  auto tile_of = [&](int i) { return 2 * (i * P.num_pairs + pair) + (int)rank; };
+  auto iter_valid = [&](int i) { return 2 * (i * P.num_pairs + pair) < T; };
+
+  if (warp == kWarpTma) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int i = 0; iter_valid(i); ++i) {
+        int t = min(tile_of(i), T - 1);
+        TileCoord tcd = decode_tile(P, t);
+        int b = tcd.p / P.num_classes;
+        for (int ch = 0; ch < kNumChunks; ++ch, ++g) {
+          int s = g % kQStages;
+          uint32_t ph = (g / kQStages) & 1;
+          mbar_wait(q_empty(s), ph ^ 1);
+          mbar_arrive_expect_tx(q_full(s), kQStageBytes);
+          tma_load_4d(sbase + kOffQ + s * kQStageStride, &P.in_map[tcd.level], q_full(s), ch * kChunk, tcd.x0 - 1,
+                      tcd.y0 - 1, b);
+        }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = idesc_tf32(256, 128);
+      const uint64_t bhi0 = smem_desc_k_sw128(sbase + kOffBHi);
+      const uint64_t blo0 = smem_desc_k_sw128(sbase + kOffBLo);
+      uint32_t g = 0;
+      for (int i = 0; iter_valid(i); ++i) {
+        int as_ = i % kAccStages;
+        uint32_t aph = (i / kAccStages) & 1;
+        mbar_wait_cluster(acc_empty(as_), aph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + kColAcc + as_ * 128;
+        for (int ch = 0; ch < kNumChunks; ++ch, ++g) {
+          int s = g % kAStages;
+          uint32_t ph = (g / kAStages) & 1;
+          mbar_wait_cluster(a_full(s), ph);
+          tc_fence_after();
+          const uint32_t a0 = tmem_base + kColA + s * 128;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              uint32_t ah = a0 + half * 64 + ks * 8, al = ah + 32;
+              uint64_t boff = (uint64_t)(((half * 4 + ch) * kBChunkBytes + ks * 32) >> 4);
+              uint32_t acc = (ch | half | ks) ? 1u : 0u;
+              mma_tf32_ts<2>(d, ah, bhi0 + boff, idesc, acc);
+              mma_tf32_ts<2>(d, al, bhi0 + boff, idesc, 1u);
+              mma_tf32_ts<2>(d, ah, blo0 + boff, idesc, 1u);
+            }
+          }
+          mma_commit_pair(a_empty(s), 3);
+        }
+        mma_commit_pair(acc_full(as_), 3);
+      }
+    }
+  } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int qd = warp & 3;
+    const int m = qd * 32 + lane;  // pixel row of the tile == TMEM lane
+    const uint32_t acc_empty_leader = map_to_cta(acc_empty(0), 0);
+    const float* bias = reinterpret_cast<const float*>(smem + kOffBias);
+    uint8_t* stage = smem + kOffOut;
+    const bool issuer = (warp == kWarpEpi0 && lane == 0);
+    for (int i = 0; iter_valid(i); ++i) {
+      int t = tile_of(i);
+      bool do_store = t < T;
+      TileCoord tcd = decode_tile(P, min(t, T - 1));
+      int as_ = i % kAccStages;
+      uint32_t aph = (i / kAccStages) & 1;
+      mbar_wait(acc_full(as_), aph);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColAcc + as_ * 128;
+#pragma unroll 1
+      for (int j = 0; j < 4; ++j) {
+        uint32_t v[32];
+        tmem_ld32(trow + j * 32, v);
+        tmem_wait_ld();
+        if (j == 3) {  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * as_);
+        }
+        if (issuer) tma_store_wait_read<0>();  // staging tile free again
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 bb = *reinterpret_cast<const float4*>(bias + j * 32 + c4 * 4);
+          float4 o;
+          o.x = fmaxf(__uint_as_float(v[c4 * 4 + 0]) + bb.x, 0.f);
+          o.y = fmaxf(__uint_as_float(v[c4 * 4 + 1]) + bb.y, 0.f);
+          o.z = fmaxf(__uint_as_float(v[c4 * 4 + 2]) + bb.z, 0.f);
+          o.w = fmaxf(__uint_as_float(v[c4 * 4 + 3]) + bb.w, 0.f);
+          *reinterpret_cast<float4*>(stage + (m >> 3) * 1024 + (m & 7) * 128 + ((c4 ^ (m & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer && do_store) {
+          tma_store_4d(&P.out_map[tcd.level], sbase + kOffOut, j * 32, tcd.x0, tcd.y0, tcd.p);
+          tma_store_commit();
+        }
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  } else if (warp >= kWarpSten0) {
+    // ------------------------------------------------------------------ stencil: build A in tensor memory
+    const int ws = warp - kWarpSten0;
+    const int qd = ws & 3, half = ws >> 2;  // TMEM lane quadrant, channel half of the chunk
+    const int m = qd * 32 + lane;
+    const int ty = m >> 4, tx = m & 15;
+    const int stid = tid - kWarpSten0 * 32;  // 0..255
+    const uint32_t a_full_leader = map_to_cta(a_full(0), 0);
+    const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColA;
+    // halo rows of the 3x3 neighbourhood: r = (ty+1+dy)*18 + tx+1+dx
+    int rr[3][3];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) rr[dy][dx] = (ty + dy) * kHaloW + tx + dx;
+
+    auto load_taps = [&](int i, int buf) {
+      if (stid < 7 * kC / 4) {
+        TileCoord tcd = decode_tile(P, min(tile_of(i), T - 1));
+        int c = tcd.p % P.num_classes;
+        cp_async16(sbase + kOffTaps + buf * 7 * kC * 4 + stid * 16, P.lv[tcd.level].taps + (size_t)c * 7 * kC + stid * 4);
+      }
+    };
+    if (iter_valid(0)) load_taps(0, 0);
+    cp_async_wait_all();
+    named_bar_sync(2, 256);
+
+    uint32_t g = 0;
+    for (int i = 0; iter_valid(i); ++i) {
+      if (iter_valid(i + 1)) load_taps(i + 1, (i + 1) & 1);
+      const uint8_t* taps = smem + kOffTaps + (i & 1) * 7 * kC * 4;
+      for (int ch = 0; ch < kNumChunks; ++ch, ++g) {
+        const int qs = g % kQStages, as_ = g % kAStages;
+        const uint32_t qph = (g / kQStages) & 1, aph = (g / kAStages) & 1;
+        mbar_wait(q_full(qs), qph);
+        mbar_wait(a_empty(as_), aph ^ 1);
+        tc_fence_after();
+        const uint8_t* qt = smem + kOffQ + qs * kQStageStride;
+        const uint32_t tcol = trow + as_ * 128 + half * 16;
+#pragma unroll
+        for (int grp = 0; grp < 2; ++grp) {  // 8 channels per group
+          uint32_t shi[8], slo[8], qhi[8], qlo[8];
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = half * 4 + grp * 2 + jj;              // 16-byte chunk inside the 128-byte row
+            const uint8_t* tp = taps + (ch * kChunk + j * 4) * 4;  // channel offset inside a tap row
+            const float4 k11 = lds4(tp), k13l = lds4(tp + 1 * kC * 4), k13c = lds4(tp + 2 * kC * 4),
+                         k13r = lds4(tp + 3 * kC * 4);
+            float4 trow3[3], qc;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const int r0 = rr[dy][0], r1 = rr[dy][1], r2 = rr[dy][2];
+              float4 ql = lds4(qt + r0 * 128 + ((j ^ (r0 & 7)) << 4));
+              float4 qm = lds4(qt + r1 * 128 + ((j ^ (r1 & 7)) << 4));
+              float4 qr = lds4(qt + r2 * 128 + ((j ^ (r2 & 7)) << 4));
+              if (dy == 1) qc = qm;
+              trow3[dy] = f4_relu(f4_fma(k13r, qr, f4_fma(k13l, ql, f4_mul(k13c, qm))));
+            }
+            const float4 k31u = lds4(tp + 4 * kC * 4), k31c = lds4(tp + 5 * kC * 4), k31d = lds4(tp + 6 * kC * 4);
+            float4 bv = f4_relu(f4_fma(k31d, trow3[2], f4_fma(k31u, trow3[0], f4_mul(k31c, trow3[1]))));
+            float4 av = f4_relu(f4_mul(k11, f4_relu(f4_mul(k11, qc))));
+            float4 sv = f4_add(f4_add(av, bv), qc);
+            split_tf32(sv.x, shi[jj * 4 + 0], slo[jj * 4 + 0]);
+            split_tf32(sv.y, shi[jj * 4 + 1], slo[jj * 4 + 1]);
+            split_tf32(sv.z, shi[jj * 4 + 2], slo[jj * 4 + 2]);
+            split_tf32(sv.w, shi[jj * 4 + 3], slo[jj * 4 + 3]);
+            split_tf32(qc.x, qhi[jj * 4 + 0], qlo[jj * 4 + 0]);
+            split_tf32(qc.y, qhi[jj * 4 + 1], qlo[jj * 4 + 1]);
+            split_tf32(qc.z, qhi[jj * 4 + 2], qlo[jj * 4 + 2]);
+            split_tf32(qc.w, qhi[jj * 4 + 3], qlo[jj * 4 + 3]);
+          }
+          tmem_st8(tcol + grp * 8, shi);
+          tmem_st8(tcol + 32 + grp * 8, slo);
+          tmem_st8(tcol + 64 + grp * 8, qhi);
+          tmem_st8(tcol + 96 + grp * 8, qlo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(q_empty(qs));
+          mbar_arrive_cluster(a_full_leader + 8u * as_);
+        }
+      }
+      cp_async_wait_all();
+      named_bar_sync(2, 256);
+    }
+  }
+  // ---------------------------------------------------------------------- teardown
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync();
+  if (warp == kWarpAlloc) tmem_dealloc<2>(tmem_base, kTmemCols);
+}
+
+}  // namespace ctc
+}  // namespace fod
+
+using namespace fod;
+
+extern "C" int fod_correlate_levels(const float* const* q, const float* const* taps, const fod_level_t* levels,
+                                    int num_levels, const float* w3, const float* b3, float* const* attn, int batch,
+                                    int num_classes, fod_stream_t stream) {
+  FOD_REQUIRE(q && taps && levels && w3 && b3 && attn, "fod_correlate_levels: null pointer");
+  FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_correlate_levels: 1..%d levels", FOD_MAX_LEVELS);
+  FOD_REQUIRE(batch >= 0 && num_classes >= 0, "fod_correlate_levels: bad sizes");
+  FOD_REQUIRE((((uintptr_t)w3 | (uintptr_t)b3) & 15) == 0, "fod_correlate_levels: weights must be 16-byte aligned");
+  const long Pn = (long)batch * num_classes;
+  if (Pn == 0) return FOD_OK;
+  ctc::Params prm;
+  memset(&prm, 0, sizeof(prm));
+  long tiles = 0;
+  for (int l = 0; l < num_levels; ++l) {
+    const int H = levels[l].height, W = levels[l].width;
+    FOD_REQUIRE(H > 0 && W > 0 && q[l] && attn[l] && taps[l], "fod_correlate_levels: level %d invalid", l);
+    FOD_REQUIRE((((uintptr_t)q[l] | (uintptr_t)attn[l] | (uintptr_t)taps[l]) & 15) == 0,
+                "fod_correlate_levels: level %d pointers must be 16-byte aligned", l);
+    ctc::Level& L = prm.lv[l];
+    L.H = H;
+    L.W = W;
+    L.tiles_x = (W + ctc::kTileW - 1) / ctc::kTileW;
+    L.tiles_per_problem = L.tiles_x * ((H + ctc::kTileH - 1) / ctc::kTileH);
+    L.tile_begin = (int)tiles;
+    L.taps = taps[l];
+    tiles += Pn * L.tiles_per_problem;
+    FOD_REQUIRE(tiles < (1L << 30), "fod_correlate_levels: too many tiles");
+    int rc = make_nhwc_map(&prm.in_map[l], q[l], batch, H, W, kC, ctc::kChunk, ctc::kHaloW, ctc::kHaloH);
+    if (rc != FOD_OK) return rc;
+    rc = make_nhwc_map(&prm.out_map[l], attn[l], (int)Pn, H, W, kC, ctc::kChunk, ctc::kTileW, ctc::kTileH);
+    if (rc != FOD_OK) return rc;
+  }
+  prm.w3 = w3;
+  prm.b3 = b3;
+  prm.num_levels = num_levels;
+  prm.num_classes = num_classes;
+  prm.total_tiles = (int)tiles;
+  int dev = 0, sms = 0;
+  FOD_CUDA_CALL(cudaGetDevice(&dev));
+  FOD_CUDA_CALL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int max_pairs = sms / 2 > 0 ? sms / 2 : 1;
+  const int need_pairs = (int)((tiles + 1) / 2);
+  prm.num_pairs = need_pairs < max_pairs ? need_pairs : max_pairs;
+  FOD_CUDA_CALL(cudaFuncSetAttribute(ctc::correlate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)ctc::kSmemAlloc));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * prm.num_pairs);
+  cfg.blockDim = dim3(ctc::kThreads);
+  cfg.dynamicSmemBytes = ctc::kSmemAlloc;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, ctc::correlate_tc_kernel, prm);
+  if (e != cudaSuccess) {
+    set_error("fod_correlate_levels: launch failed: %s", cudaGetErrorString(e));
+    return FOD_ERR_CUDA;
+  }
+  return FOD_OK;
+}

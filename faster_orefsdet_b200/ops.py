@@ -108,6 +108,33 @@ def correlate(q: Tensor, taps: Tensor, w3: Tensor, b3: Tensor) -> Tensor:
     return attn
 
 
+def _empty_nhwc(n: int, h: int, w: int, device) -> Tensor:
+    """[n,128,h,w] logical, NHWC memory (explicit strides also for size-1 dims)."""
+    return torch.empty((n, h, w, 128), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
+
+
+def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3: Tensor) -> List[Tensor]:
+    """All FPN levels in one persistent tensor-core launch.
+    q[l] [B,128,H_l,W_l], taps[l] [C,7,128] -> attn[l] [B*C,128,H_l,W_l] (NHWC memory), problem-major
+    (fsod_cen.py:463-470, 482-491, 502-509)."""
+    L = len(q)
+    if L < 1 or L > 3 or len(taps) != L:
+        raise _lib.FodError("correlate_levels: 1..3 levels with one taps tensor each")
+    q = [nhwc(t, f"q[{i}]") for i, t in enumerate(q)]
+    B, C = q[0].shape[0], taps[0].shape[0]
+    taps = [_chk(t, torch.float32, "taps").contiguous() for t in taps]
+    for t, qq in zip(taps, q):
+        if tuple(t.shape) != (C, 7, 128) or qq.shape[0] != B or qq.shape[1] != 128:
+            raise _lib.FodError("correlate_levels: bad shapes")
+    w3 = _chk(w3, torch.float32, "w3").reshape(128, 256).contiguous()
+    b3 = _chk(b3, torch.float32, "b3").contiguous()
+    attn = [_empty_nhwc(B * C, t.shape[2], t.shape[3], t.device) for t in q]
+    lv = _levels(q, [0] * L)
+    _lib.check(_lib.lib().fod_correlate_levels(_ptr_array(q), _ptr_array(taps), lv, L, _ptr(w3), _ptr(b3),
+                                               _ptr_array(attn), B, C, _stream()), "fod_correlate_levels")
+    return attn
+
+
 # --------------------------------------------------------------------------- D1-D3
 def decode_topk(hm: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[int], score_thresh: float,
                 pre_topk: int, status: Tensor, hm_is_logit: bool = True, cand_cap: Optional[int] = None):

@@ -84,6 +84,18 @@ int fod_support_taps(const float* proto, int num_classes, int h, int w, float* t
 int fod_correlate(const float* q, const float* taps, const float* w3, const float* b3, float* attn, int batch,
                   int num_classes, int height, int width, fod_stream_t stream);
 
+/* Q2+Q3 for ALL FPN levels and all (image, class) problems in one persistent launch
+ * (tcgen05 tensor cores, 3xTF32 operand splitting = fp32 accuracy, TMA in/out).
+ * Same arithmetic contract as fod_correlate.  q, taps, attn are HOST arrays of
+ * num_levels DEVICE pointers:
+ *   q[l]    : [B][H_l][W_l][128]
+ *   taps[l] : [C][7][128]              from fod_support_taps on the level-l prototype
+ *   attn[l] : [B*C][H_l][W_l][128]     problem-major output
+ */
+int fod_correlate_levels(const float* const* q, const float* const* taps, const fod_level_t* levels, int num_levels,
+                         const float* w3, const float* b3, float* const* attn, int batch, int num_classes,
+                         fod_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * D1+D2+D3  heat-map sigmoid, candidate threshold, per-level top-k, box decode,
  * level concatenation.  Replaces CenterNet.inference / predict_instances /

@@ -199,6 +199,26 @@ def test_correlate_matches_oracle(hw):
             assert_close(attn[b * C + c], ref[0], what=f"attn b{b} c{c}")
 
 
+@pytest.mark.parametrize("sizes,B,C", [(((80, 80), (40, 40), (20, 20)), 2, 1), (((25, 42), (13, 21), (7, 11)), 3, 2),
+                                       (((8, 16),), 1, 1), (((1, 1), (5, 3)), 1, 3), (((100, 168), (50, 84), (25, 42)), 1, 2)])
+def test_correlate_levels_tensor_core_matches_oracle(sizes, B, C):
+    """One persistent tcgen05 launch over all levels (3xTF32) against the fp32 CPU oracle."""
+    sd = head_state_dict()
+    qs = [synth.tensor((B, 128, h, w), 150 + h + 3 * i, -1.5, 1.5) for i, (h, w) in enumerate(sizes)]
+    protos = [synth.tensor((C, 128, 8 // (i + 1) + 1, 8 // (i + 1) + 2), 160 + i, -0.6, 0.8) for i in range(len(sizes))]
+    taps = [ops.support_taps(p.to(DEV)) for p in protos]
+    outs = ops.correlate_levels([q.to(DEV) for q in qs], taps, sd["conv3.weight"].to(DEV), sd["conv3.bias"].to(DEV))
+    torch.cuda.synchronize()
+    for l, (q, proto) in enumerate(zip(qs, protos)):
+        got = outs[l].cpu()
+        assert got.shape == (B * C, 128) + tuple(sizes[l])
+        for b in range(B):
+            for c in range(C):
+                k11, k13, k31 = O.support_taps(proto[c:c + 1])
+                ref = O.correlate_level(q[b:b + 1], k11, k13, k31, sd["conv3.weight"], sd["conv3.bias"])
+                assert_close(got[b * C + c], ref[0], what=f"attn level{l} b{b} c{c}")
+
+
 def test_correlate_golden_reference_maps():
     g = golden("full_small")
     sd = head_state_dict()
