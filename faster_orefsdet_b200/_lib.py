@@ -11,7 +11,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfod_b200.so")
+LIB_PATH = os.environ.get("FOD_B200_LIB_DEV") or os.path.join(_HERE, "libfod_b200.so")  # env: kernel A/B experiments only
 CSRC = os.path.join(_HERE, "csrc")
 
 FOD_STATUS_CAND_OVERFLOW = 1

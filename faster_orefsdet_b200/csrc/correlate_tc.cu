@@ -48,16 +48,16 @@ constexpr uint32_t kOffBHi = 0;
 constexpr uint32_t kOffBLo = kOffBHi + kBPartBytes;
 constexpr uint32_t kOffQ = kOffBLo + kBPartBytes;
 constexpr uint32_t kOffOut = kOffQ + kQStages * kQStageStride;
-constexpr uint32_t kOffTaps = kOffOut + kStageOutBytes;          // 2 x [7][128] fp32
-constexpr uint32_t kOffBias = kOffTaps + 2 * 7 * kC * 4;
+constexpr uint32_t kOffBias = kOffOut + kStageOutBytes;
 constexpr uint32_t kOffBars = kOffBias + kC * 4;
 constexpr uint32_t kNumBars = 2 * kQStages + 2 * kAStages + 2 * kAccStages;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
 constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 768;
 constexpr int kWarpTma = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpEpi0 = 4, kWarpSten0 = 8;
+constexpr int kStencilWarps = 16;
 
 // tensor memory columns
 constexpr uint32_t kTmemCols = 512;
@@ -65,8 +65,7 @@ constexpr uint32_t kColA = 0;      // 2 stages x [s_hi 32 | s_lo 32 | q_hi 32 | 
 constexpr uint32_t kColAcc = 256;  // 2 stages x 128
 
 struct Level {
-  int H, W, tiles_x, tiles_per_problem, tile_begin;
-  const float* taps;  // [C][7][128]
+  int H, W, tiles_x, tiles_per_problem, tiles_per_class, tile_begin;  // tiles_per_class = batch * tiles_per_problem
 };
 
 struct Params {
@@ -75,11 +74,13 @@ struct Params {
   Level lv[FOD_MAX_LEVELS];
   const float* w3;
   const float* b3;
-  int num_levels, num_classes, total_tiles, num_pairs;
+  // problems of this launch: images x classes [class_begin, class_begin + class_count) of num_classes
+  int num_levels, num_classes, class_begin, class_count, total_tiles, num_pairs;
 };
 
+// Tile order: level-major, then class, then image, then tile (all tiles that share one tap set are contiguous).
 struct TileCoord {
-  int level, p, y0, x0;
+  int level, b, cc, y0, x0;  // image, class index inside the launch's class group
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const Params& P, int t) {
@@ -88,12 +89,15 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int t) {
   if (P.num_levels > 2 && t >= P.lv[2].tile_begin) l = 2;
   const Level& L = P.lv[l];
   int r = t - L.tile_begin;
-  int p = r / L.tiles_per_problem;
-  int tt = r - p * L.tiles_per_problem;
+  int cc = r / L.tiles_per_class;
+  r -= cc * L.tiles_per_class;
+  int b = r / L.tiles_per_problem;
+  int tt = r - b * L.tiles_per_problem;
   int ty = tt / L.tiles_x;
   TileCoord tc;
   tc.level = l;
-  tc.p = p;
+  tc.b = b;
+  tc.cc = cc;
   tc.y0 = ty * kTileH;
   tc.x0 = (tt - ty * L.tiles_x) * kTileW;
   return tc;
@@ -117,12 +121,133 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Support taps of every (level, class) set of the launch, in the constant bank: a tap is warp-uniform, so it
+// reaches the FMA as a uniform / constant operand instead of costing shared-memory bandwidth per lane.
+#ifndef FOD_TAPS_MODE
+#define FOD_TAPS_MODE 0
+#endif
+constexpr int kMaxTapSets = 16;
+__constant__ float c_taps[kMaxTapSets][7][kC];
+
+struct StencilCtx {
+  uint8_t* smem;
+  uint32_t sbase, tmem_base, bar0;
+  int pair, rank;
+};
+
+__device__ __forceinline__ float2 relu2(float2 v) { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
+__device__ __forceinline__ void split2(float2 v, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
+  h0 = __float_as_uint(v.x) & 0xFFFFE000u;
+  h1 = __float_as_uint(v.y) & 0xFFFFE000u;
+  float2 lo = __ffma2_rn(make_float2(__uint_as_float(h0), __uint_as_float(h1)), make_float2(-1.f, -1.f), v);
+  l0 = __float_as_uint(lo.x);
+  l1 = __float_as_uint(lo.y);
+}
+
+// One stencil warp: TMEM lane quadrant qd = warp & 3, one pixel per lane.  The four warps of a quadrant share every
+// 32-channel chunk: warp k takes the 16-byte channel groups jj with (jj >> 1) == k.  The loops over chunks and
+// groups stay ROLLED with uniform counters (one small code copy for all 16 warps -> instruction cache; the tap
+// address set*3584 + ch*128 + jj*16 stays in uniform registers -> LDCU + uniform FFMA2 operands).
+__device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& cx, const int warp) {
+  const int lane = threadIdx.x & 31;
+  const int qd = warp & 3, myk = (warp - kWarpSten0) >> 2;
+  const int m = qd * 32 + lane;
+  const int ty = m >> 4, tx = m & 15;
+  const uint32_t bar0 = cx.bar0;
+  const uint32_t a_full_leader = map_to_cta(bar0 + 8u * (2 * kQStages), 0);
+  const uint32_t trow = cx.tmem_base + ((uint32_t)(qd * 32) << 16) + kColA;
+  // byte offset of 16-byte chunk 0 of each neighbour's 128-byte row (swizzled); chunk jj is this ^ (jj << 4)
+  uint32_t off[3][3];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      int r = (ty + dy) * kHaloW + tx + dx;
+      off[dy][dx] = (uint32_t)(r * 128 + ((r & 7) << 4));
+    }
+  const int T = P.total_tiles;
+  uint32_t g = 0;
+  int i = 0;
+  // Outer loops over the tap sets (level, class): `set` is a loop counter (uniform); this CTA's tiles arrive in
+  // set order because tiles are numbered set-major.
+  for (int l = 0; l < P.num_levels; ++l)
+    for (int cc = 0; cc < P.class_count; ++cc) {
+      const int set = l * P.class_count + cc;
+      const int set_end = P.lv[l].tile_begin + (cc + 1) * P.lv[l].tiles_per_class;
+      for (; 2 * (i * P.num_pairs + cx.pair) < T && min(2 * (i * P.num_pairs + cx.pair) + cx.rank, T - 1) < set_end;
+           ++i) {
+#pragma unroll 1
+        for (int ch = 0; ch < kNumChunks; ++ch, ++g) {
+          const int qs = g % kQStages, as_ = g % kAStages;
+          const uint32_t qph = (g / kQStages) & 1, aph = (g / kAStages) & 1;
+          mbar_wait(bar0 + 8u * qs, qph);                                   // q_full
+          mbar_wait(bar0 + 8u * (2 * kQStages + kAStages + as_), aph ^ 1);  // a_empty
+          tc_fence_after();
+          const uint8_t* qt = cx.smem + kOffQ + qs * kQStageStride;
+          const uint32_t tcol = trow + as_ * 128;
+#pragma unroll 1
+          for (int jj = 0; jj < 8; ++jj) {  // 4 channels per step
+            if ((jj >> 1) != myk) continue;
+            const float* tp = &c_taps[set][0][ch * kChunk + jj * 4];
+            const uint32_t jx = (uint32_t)jj << 4;
+            uint32_t shi[4], slo[4], qhi[4], qlo[4];
+            float4 qc4;
+            float2 t3[3][2];
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+              const float4 ql = lds4(qt + (off[dy][0] ^ jx));
+              const float4 qm = lds4(qt + (off[dy][1] ^ jx));
+              const float4 qr = lds4(qt + (off[dy][2] ^ jx));
+              if (dy == 1) qc4 = qm;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float2 kl = make_float2(tp[1 * kC + 2 * h], tp[1 * kC + 2 * h + 1]);
+                const float2 kc = make_float2(tp[2 * kC + 2 * h], tp[2 * kC + 2 * h + 1]);
+                const float2 kr = make_float2(tp[3 * kC + 2 * h], tp[3 * kC + 2 * h + 1]);
+                const float2 l2 = h ? make_float2(ql.z, ql.w) : make_float2(ql.x, ql.y);
+                const float2 m2 = h ? make_float2(qm.z, qm.w) : make_float2(qm.x, qm.y);
+                const float2 r2 = h ? make_float2(qr.z, qr.w) : make_float2(qr.x, qr.y);
+                t3[dy][h] = relu2(__ffma2_rn(kr, r2, __ffma2_rn(kl, l2, __fmul2_rn(kc, m2))));
+              }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const float2 k11 = make_float2(tp[2 * h], tp[2 * h + 1]);
+              const float2 ku = make_float2(tp[4 * kC + 2 * h], tp[4 * kC + 2 * h + 1]);
+              const float2 kc = make_float2(tp[5 * kC + 2 * h], tp[5 * kC + 2 * h + 1]);
+              const float2 kd = make_float2(tp[6 * kC + 2 * h], tp[6 * kC + 2 * h + 1]);
+              const float2 qc = h ? make_float2(qc4.z, qc4.w) : make_float2(qc4.x, qc4.y);
+              const float2 bv = relu2(__ffma2_rn(kd, t3[2][h], __ffma2_rn(ku, t3[0][h], __fmul2_rn(kc, t3[1][h]))));
+              const float2 av = relu2(__fmul2_rn(k11, relu2(__fmul2_rn(k11, qc))));
+              const float2 sv = __fadd2_rn(__fadd2_rn(av, bv), qc);
+              split2(sv, shi[2 * h], shi[2 * h + 1], slo[2 * h], slo[2 * h + 1]);
+              split2(qc, qhi[2 * h], qhi[2 * h + 1], qlo[2 * h], qlo[2 * h + 1]);
+            }
+            tmem_st4(tcol + jj * 4, shi);
+            tmem_st4(tcol + 32 + jj * 4, slo);
+            tmem_st4(tcol + 64 + jj * 4, qhi);
+            tmem_st4(tcol + 96 + jj * 4, qlo);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(bar0 + 8u * (kQStages + qs));       // q_empty
+            mbar_arrive_remote(a_full_leader + 8u * as_);   // a_full (leader CTA)
+          }
+        }
+      }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_constant__ Params P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  // rank inside the CTA pair; == %cluster_ctarank for cluster dims (2,1,1), but written from blockIdx so that ptxas
+  // can prove it warp-uniform (an inline-asm special-register read is opaque to its uniformity analysis)
+  const uint32_t rank = blockIdx.x & 1;
   const int pair = blockIdx.x >> 1;
 
   // barrier addresses
@@ -137,10 +262,10 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
   if (tid == 0) {
     for (int s = 0; s < kQStages; ++s) {
       mbar_init(q_full(s), 1);
-      mbar_init(q_empty(s), 8);
+      mbar_init(q_empty(s), kStencilWarps);
     }
     for (int s = 0; s < kAStages; ++s) {
-      mbar_init(a_full(s), 16);  // 8 stencil warps x 2 CTAs (used in the leader only)
+      mbar_init(a_full(s), 2 * kStencilWarps);  // stencil warps of both CTAs (used in the leader only)
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
@@ -198,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
       for (int i = 0; iter_valid(i); ++i) {
         int t = min(tile_of(i), T - 1);
         TileCoord tcd = decode_tile(P, t);
-        int b = tcd.p / P.num_classes;
+        int b = tcd.b;
         for (int ch = 0; ch < kNumChunks; ++ch, ++g) {
           int s = g % kQStages;
           uint32_t ph = (g / kQStages) & 1;
@@ -219,13 +344,13 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
       for (int i = 0; iter_valid(i); ++i) {
         int as_ = i % kAccStages;
         uint32_t aph = (i / kAccStages) & 1;
-        mbar_wait_cluster(acc_empty(as_), aph ^ 1);
+        mbar_wait(acc_empty(as_), aph ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + kColAcc + as_ * 128;
         for (int ch = 0; ch < kNumChunks; ++ch, ++g) {
           int s = g % kAStages;
           uint32_t ph = (g / kAStages) & 1;
-          mbar_wait_cluster(a_full(s), ph);
+          mbar_wait(a_full(s), ph);
           tc_fence_after();
           const uint32_t a0 = tmem_base + kColA + s * 128;
 #pragma unroll
@@ -257,6 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
       int t = tile_of(i);
       bool do_store = t < T;
       TileCoord tcd = decode_tile(P, min(t, T - 1));
+      const int pg = tcd.b * P.num_classes + P.class_begin + tcd.cc;
       int as_ = i % kAccStages;
       uint32_t aph = (i / kAccStages) & 1;
       mbar_wait(acc_full(as_), aph);
@@ -270,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
         if (j == 3) {  // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(acc_empty_leader + 8u * as_);
+          if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * as_);
         }
         if (issuer) tma_store_wait_read<0>();  // staging tile free again
         named_bar_sync(1, 128);
@@ -287,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (issuer && do_store) {
-          tma_store_4d(&P.out_map[tcd.level], sbase + kOffOut, j * 32, tcd.x0, tcd.y0, tcd.p);
+          tma_store_4d(&P.out_map[tcd.level], sbase + kOffOut, j * 32, tcd.x0, tcd.y0, pg);
           tma_store_commit();
         }
       }
@@ -295,91 +421,14 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
     if (issuer) tma_store_wait<0>();
   } else if (warp >= kWarpSten0) {
     // ------------------------------------------------------------------ stencil: build A in tensor memory
-    const int ws = warp - kWarpSten0;
-    const int qd = ws & 3, half = ws >> 2;  // TMEM lane quadrant, channel half of the chunk
-    const int m = qd * 32 + lane;
-    const int ty = m >> 4, tx = m & 15;
-    const int stid = tid - kWarpSten0 * 32;  // 0..255
-    const uint32_t a_full_leader = map_to_cta(a_full(0), 0);
-    const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColA;
-    // halo rows of the 3x3 neighbourhood: r = (ty+1+dy)*18 + tx+1+dx
-    int rr[3][3];
-#pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) rr[dy][dx] = (ty + dy) * kHaloW + tx + dx;
-
-    auto load_taps = [&](int i, int buf) {
-      if (stid < 7 * kC / 4) {
-        TileCoord tcd = decode_tile(P, min(tile_of(i), T - 1));
-        int c = tcd.p % P.num_classes;
-        cp_async16(sbase + kOffTaps + buf * 7 * kC * 4 + stid * 16, P.lv[tcd.level].taps + (size_t)c * 7 * kC + stid * 4);
-      }
-    };
-    if (iter_valid(0)) load_taps(0, 0);
-    cp_async_wait_all();
-    named_bar_sync(2, 256);
-
-    uint32_t g = 0;
-    for (int i = 0; iter_valid(i); ++i) {
-      if (iter_valid(i + 1)) load_taps(i + 1, (i + 1) & 1);
-      const uint8_t* taps = smem + kOffTaps + (i & 1) * 7 * kC * 4;
-      for (int ch = 0; ch < kNumChunks; ++ch, ++g) {
-        const int qs = g % kQStages, as_ = g % kAStages;
-        const uint32_t qph = (g / kQStages) & 1, aph = (g / kAStages) & 1;
-        mbar_wait(q_full(qs), qph);
-        mbar_wait(a_empty(as_), aph ^ 1);
-        tc_fence_after();
-        const uint8_t* qt = smem + kOffQ + qs * kQStageStride;
-        const uint32_t tcol = trow + as_ * 128 + half * 16;
-#pragma unroll
-        for (int grp = 0; grp < 2; ++grp) {  // 8 channels per group
-          uint32_t shi[8], slo[8], qhi[8], qlo[8];
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int j = half * 4 + grp * 2 + jj;              // 16-byte chunk inside the 128-byte row
-            const uint8_t* tp = taps + (ch * kChunk + j * 4) * 4;  // channel offset inside a tap row
-            const float4 k11 = lds4(tp), k13l = lds4(tp + 1 * kC * 4), k13c = lds4(tp + 2 * kC * 4),
-                         k13r = lds4(tp + 3 * kC * 4);
-            float4 trow3[3], qc;
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const int r0 = rr[dy][0], r1 = rr[dy][1], r2 = rr[dy][2];
-              float4 ql = lds4(qt + r0 * 128 + ((j ^ (r0 & 7)) << 4));
-              float4 qm = lds4(qt + r1 * 128 + ((j ^ (r1 & 7)) << 4));
-              float4 qr = lds4(qt + r2 * 128 + ((j ^ (r2 & 7)) << 4));
-              if (dy == 1) qc = qm;
-              trow3[dy] = f4_relu(f4_fma(k13r, qr, f4_fma(k13l, ql, f4_mul(k13c, qm))));
-            }
-            const float4 k31u = lds4(tp + 4 * kC * 4), k31c = lds4(tp + 5 * kC * 4), k31d = lds4(tp + 6 * kC * 4);
-            float4 bv = f4_relu(f4_fma(k31d, trow3[2], f4_fma(k31u, trow3[0], f4_mul(k31c, trow3[1]))));
-            float4 av = f4_relu(f4_mul(k11, f4_relu(f4_mul(k11, qc))));
-            float4 sv = f4_add(f4_add(av, bv), qc);
-            split_tf32(sv.x, shi[jj * 4 + 0], slo[jj * 4 + 0]);
-            split_tf32(sv.y, shi[jj * 4 + 1], slo[jj * 4 + 1]);
-            split_tf32(sv.z, shi[jj * 4 + 2], slo[jj * 4 + 2]);
-            split_tf32(sv.w, shi[jj * 4 + 3], slo[jj * 4 + 3]);
-            split_tf32(qc.x, qhi[jj * 4 + 0], qlo[jj * 4 + 0]);
-            split_tf32(qc.y, qhi[jj * 4 + 1], qlo[jj * 4 + 1]);
-            split_tf32(qc.z, qhi[jj * 4 + 2], qlo[jj * 4 + 2]);
-            split_tf32(qc.w, qhi[jj * 4 + 3], qlo[jj * 4 + 3]);
-          }
-          tmem_st8(tcol + grp * 8, shi);
-          tmem_st8(tcol + 32 + grp * 8, slo);
-          tmem_st8(tcol + 64 + grp * 8, qhi);
-          tmem_st8(tcol + 96 + grp * 8, qlo);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(q_empty(qs));
-          mbar_arrive_cluster(a_full_leader + 8u * as_);
-        }
-      }
-      cp_async_wait_all();
-      named_bar_sync(2, 256);
-    }
+    StencilCtx cx;
+    cx.smem = smem;
+    cx.sbase = sbase;
+    cx.tmem_base = tmem_base;
+    cx.bar0 = bar0;
+    cx.pair = pair;
+    cx.rank = (int)rank;
+    stencil_role(P, cx, warp);
   }
   // ---------------------------------------------------------------------- teardown
   __syncwarp();
@@ -400,59 +449,72 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* t
   FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_correlate_levels: 1..%d levels", FOD_MAX_LEVELS);
   FOD_REQUIRE(batch >= 0 && num_classes >= 0, "fod_correlate_levels: bad sizes");
   FOD_REQUIRE((((uintptr_t)w3 | (uintptr_t)b3) & 15) == 0, "fod_correlate_levels: weights must be 16-byte aligned");
-  const long Pn = (long)batch * num_classes;
-  if (Pn == 0) return FOD_OK;
+  if ((long)batch * num_classes == 0) return FOD_OK;
+  FOD_REQUIRE((long)batch * num_classes < (1L << 24), "fod_correlate_levels: too many problems");
   ctc::Params prm;
   memset(&prm, 0, sizeof(prm));
-  long tiles = 0;
   for (int l = 0; l < num_levels; ++l) {
     const int H = levels[l].height, W = levels[l].width;
     FOD_REQUIRE(H > 0 && W > 0 && q[l] && attn[l] && taps[l], "fod_correlate_levels: level %d invalid", l);
     FOD_REQUIRE((((uintptr_t)q[l] | (uintptr_t)attn[l] | (uintptr_t)taps[l]) & 15) == 0,
                 "fod_correlate_levels: level %d pointers must be 16-byte aligned", l);
-    ctc::Level& L = prm.lv[l];
-    L.H = H;
-    L.W = W;
-    L.tiles_x = (W + ctc::kTileW - 1) / ctc::kTileW;
-    L.tiles_per_problem = L.tiles_x * ((H + ctc::kTileH - 1) / ctc::kTileH);
-    L.tile_begin = (int)tiles;
-    L.taps = taps[l];
-    tiles += Pn * L.tiles_per_problem;
-    FOD_REQUIRE(tiles < (1L << 30), "fod_correlate_levels: too many tiles");
     int rc = make_nhwc_map(&prm.in_map[l], q[l], batch, H, W, kC, ctc::kChunk, ctc::kHaloW, ctc::kHaloH);
     if (rc != FOD_OK) return rc;
-    rc = make_nhwc_map(&prm.out_map[l], attn[l], (int)Pn, H, W, kC, ctc::kChunk, ctc::kTileW, ctc::kTileH);
+    rc = make_nhwc_map(&prm.out_map[l], attn[l], batch * num_classes, H, W, kC, ctc::kChunk, ctc::kTileW, ctc::kTileH);
     if (rc != FOD_OK) return rc;
   }
   prm.w3 = w3;
   prm.b3 = b3;
   prm.num_levels = num_levels;
   prm.num_classes = num_classes;
-  prm.total_tiles = (int)tiles;
   int dev = 0, sms = 0;
   FOD_CUDA_CALL(cudaGetDevice(&dev));
   FOD_CUDA_CALL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int max_pairs = sms / 2 > 0 ? sms / 2 : 1;
-  const int need_pairs = (int)((tiles + 1) / 2);
-  prm.num_pairs = need_pairs < max_pairs ? need_pairs : max_pairs;
   FOD_CUDA_CALL(cudaFuncSetAttribute(ctc::correlate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)ctc::kSmemAlloc));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * prm.num_pairs);
-  cfg.blockDim = dim3(ctc::kThreads);
-  cfg.dynamicSmemBytes = ctc::kSmemAlloc;
-  cfg.stream = as_stream(stream);
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension;
-  at[0].val.clusterDim.x = 2;
-  at[0].val.clusterDim.y = 1;
-  at[0].val.clusterDim.z = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, ctc::correlate_tc_kernel, prm);
-  if (e != cudaSuccess) {
-    set_error("fod_correlate_levels: launch failed: %s", cudaGetErrorString(e));
-    return FOD_ERR_CUDA;
+  // The taps live in the constant bank (ctc::c_taps, kMaxTapSets sets): classes are processed in groups that fit,
+  // each group = one stream-ordered symbol update + one persistent launch.
+  const int group = ctc::kMaxTapSets / num_levels;
+  for (int c0 = 0; c0 < num_classes; c0 += group) {
+    const int cn = num_classes - c0 < group ? num_classes - c0 : group;
+    long tiles = 0;
+    for (int l = 0; l < num_levels; ++l) {
+      ctc::Level& L = prm.lv[l];
+      L.H = levels[l].height;
+      L.W = levels[l].width;
+      L.tiles_x = (L.W + ctc::kTileW - 1) / ctc::kTileW;
+      L.tiles_per_problem = L.tiles_x * ((L.H + ctc::kTileH - 1) / ctc::kTileH);
+      L.tiles_per_class = batch * L.tiles_per_problem;
+      L.tile_begin = (int)tiles;
+      tiles += (long)cn * L.tiles_per_class;
+      FOD_REQUIRE(tiles < (1L << 30), "fod_correlate_levels: too many tiles");
+      FOD_CUDA_CALL(cudaMemcpyToSymbolAsync(ctc::c_taps, taps[l] + (size_t)c0 * 7 * kC, (size_t)cn * 7 * kC * sizeof(float),
+                                            (size_t)l * cn * 7 * kC * sizeof(float), cudaMemcpyDeviceToDevice,
+                                            as_stream(stream)));
+    }
+    prm.class_begin = c0;
+    prm.class_count = cn;
+    prm.total_tiles = (int)tiles;
+    const int need_pairs = (int)((tiles + 1) / 2);
+    prm.num_pairs = need_pairs < max_pairs ? need_pairs : max_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * prm.num_pairs);
+    cfg.blockDim = dim3(ctc::kThreads);
+    cfg.dynamicSmemBytes = ctc::kSmemAlloc;
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ctc::correlate_tc_kernel, prm);
+    if (e != cudaSuccess) {
+      set_error("fod_correlate_levels: launch failed: %s", cudaGetErrorString(e));
+      return FOD_ERR_CUDA;
+    }
   }
   return FOD_OK;
 }
