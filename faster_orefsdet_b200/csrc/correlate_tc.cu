@@ -104,6 +104,14 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int t) {
 }
 
 __device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 lds4s(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts4s(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ float4 f4_relu(float4 v) {
   return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
 }
@@ -126,8 +134,27 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #ifndef FOD_TAPS_MODE
 #define FOD_TAPS_MODE 0
 #endif
-constexpr int kMaxTapSets = 16;
-__constant__ float c_taps[kMaxTapSets][7][kC];
+constexpr int kMaxTapSets = 15;
+// rows 0..6: k11, k13 (left, centre, right), k31 (up, centre, down); row 7: c11 = k11 > 0 ? k11*k11 : 0
+constexpr int kTapRows = 8;
+__constant__ __align__(16) float c_taps[kMaxTapSets][kTapRows][kC];
+
+// Fills the constant-bank tap sets of one launch (set = level * class_count + class) from the [C][7][128] taps of
+// fod_support_taps and appends row 7.  Runs stream-ordered before the persistent kernel (the constant cache is
+// coherent at kernel boundaries).
+struct TapPack {
+  const float* src[FOD_MAX_LEVELS];
+  int class_count;
+};
+__global__ void pack_taps_kernel(const TapPack pk, float* __restrict__ dst) {
+  const int set = blockIdx.x, l = set / pk.class_count, cc = set - l * pk.class_count, ch = threadIdx.x;
+  const float* s = pk.src[l] + (size_t)cc * 7 * kC;
+  float* d = dst + (size_t)set * kTapRows * kC;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) d[k * kC + ch] = s[k * kC + ch];
+  const float k11 = s[ch];
+  d[7 * kC + ch] = k11 > 0.f ? k11 * k11 : 0.f;
+}
 
 struct StencilCtx {
   uint8_t* smem;
@@ -183,50 +210,55 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
           mbar_wait(bar0 + 8u * qs, qph);                                   // q_full
           mbar_wait(bar0 + 8u * (2 * kQStages + kAStages + as_), aph ^ 1);  // a_empty
           tc_fence_after();
-          const uint8_t* qt = cx.smem + kOffQ + qs * kQStageStride;
+          const uint32_t qt = cx.sbase + kOffQ + qs * kQStageStride;  // shared-window address: LDS, not generic LD
           const uint32_t tcol = trow + as_ * 128;
 #pragma unroll 1
-          for (int jj = 0; jj < 8; ++jj) {  // 4 channels per step
-            if ((jj >> 1) != myk) continue;
-            const float* tp = &c_taps[set][0][ch * kChunk + jj * 4];
-            const uint32_t jx = (uint32_t)jj << 4;
-            uint32_t shi[4], slo[4], qhi[4], qlo[4];
-            float4 qc4;
-            float2 t3[3][2];
+          for (int jj = 0; jj < 8; ++jj) {  // uniform counter (keeps the tap address uniform); 4 channels per step
+            {
+              if ((jj >> 1) != myk) continue;  // this warp's two channel groups
+              const float* tp = &c_taps[set][0][ch * kChunk + jj * 4];
+              const uint32_t jx = (uint32_t)jj << 4;
+              const float4 k13l = *reinterpret_cast<const float4*>(tp + 1 * kC);
+              const float4 k13c = *reinterpret_cast<const float4*>(tp + 2 * kC);
+              const float4 k13r = *reinterpret_cast<const float4*>(tp + 3 * kC);
+              uint32_t shi[4], slo[4], qhi[4], qlo[4];
+              float4 qc4;
+              float2 t3[3][2];
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              const float4 ql = lds4(qt + (off[dy][0] ^ jx));
-              const float4 qm = lds4(qt + (off[dy][1] ^ jx));
-              const float4 qr = lds4(qt + (off[dy][2] ^ jx));
-              if (dy == 1) qc4 = qm;
+              for (int dy = 0; dy < 3; ++dy) {
+                const float4 ql = lds4s(qt + (off[dy][0] ^ jx));
+                const float4 qm = lds4s(qt + (off[dy][1] ^ jx));
+                const float4 qr = lds4s(qt + (off[dy][2] ^ jx));
+                if (dy == 1) qc4 = qm;
+                t3[dy][0] = relu2(__ffma2_rn(make_float2(k13r.x, k13r.y), make_float2(qr.x, qr.y),
+                                             __ffma2_rn(make_float2(k13l.x, k13l.y), make_float2(ql.x, ql.y),
+                                                        __fmul2_rn(make_float2(k13c.x, k13c.y), make_float2(qm.x, qm.y)))));
+                t3[dy][1] = relu2(__ffma2_rn(make_float2(k13r.z, k13r.w), make_float2(qr.z, qr.w),
+                                             __ffma2_rn(make_float2(k13l.z, k13l.w), make_float2(ql.z, ql.w),
+                                                        __fmul2_rn(make_float2(k13c.z, k13c.w), make_float2(qm.z, qm.w)))));
+              }
+              const float4 c11 = *reinterpret_cast<const float4*>(tp + 7 * kC);
+              const float4 k31u = *reinterpret_cast<const float4*>(tp + 4 * kC);
+              const float4 k31c = *reinterpret_cast<const float4*>(tp + 5 * kC);
+              const float4 k31d = *reinterpret_cast<const float4*>(tp + 6 * kC);
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                const float2 kl = make_float2(tp[1 * kC + 2 * h], tp[1 * kC + 2 * h + 1]);
-                const float2 kc = make_float2(tp[2 * kC + 2 * h], tp[2 * kC + 2 * h + 1]);
-                const float2 kr = make_float2(tp[3 * kC + 2 * h], tp[3 * kC + 2 * h + 1]);
-                const float2 l2 = h ? make_float2(ql.z, ql.w) : make_float2(ql.x, ql.y);
-                const float2 m2 = h ? make_float2(qm.z, qm.w) : make_float2(qm.x, qm.y);
-                const float2 r2 = h ? make_float2(qr.z, qr.w) : make_float2(qr.x, qr.y);
-                t3[dy][h] = relu2(__ffma2_rn(kr, r2, __ffma2_rn(kl, l2, __fmul2_rn(kc, m2))));
+                const float2 k1 = h ? make_float2(c11.z, c11.w) : make_float2(c11.x, c11.y);
+                const float2 ku = h ? make_float2(k31u.z, k31u.w) : make_float2(k31u.x, k31u.y);
+                const float2 kc = h ? make_float2(k31c.z, k31c.w) : make_float2(k31c.x, k31c.y);
+                const float2 kd = h ? make_float2(k31d.z, k31d.w) : make_float2(k31d.x, k31d.y);
+                const float2 qc = h ? make_float2(qc4.z, qc4.w) : make_float2(qc4.x, qc4.y);
+                const float2 bv = relu2(__ffma2_rn(kd, t3[2][h], __ffma2_rn(ku, t3[0][h], __fmul2_rn(kc, t3[1][h]))));
+                // a = relu(k11 * relu(k11 * q)) == c11 * relu(q) with c11 = k11 > 0 ? k11^2 : 0 (row 7 of the set)
+                const float2 sv = __fadd2_rn(__ffma2_rn(k1, relu2(qc), bv), qc);
+                split2(sv, shi[2 * h], shi[2 * h + 1], slo[2 * h], slo[2 * h + 1]);
+                split2(qc, qhi[2 * h], qhi[2 * h + 1], qlo[2 * h], qlo[2 * h + 1]);
               }
+              tmem_st4(tcol + jj * 4, shi);
+              tmem_st4(tcol + 32 + jj * 4, slo);
+              tmem_st4(tcol + 64 + jj * 4, qhi);
+              tmem_st4(tcol + 96 + jj * 4, qlo);
             }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const float2 k11 = make_float2(tp[2 * h], tp[2 * h + 1]);
-              const float2 ku = make_float2(tp[4 * kC + 2 * h], tp[4 * kC + 2 * h + 1]);
-              const float2 kc = make_float2(tp[5 * kC + 2 * h], tp[5 * kC + 2 * h + 1]);
-              const float2 kd = make_float2(tp[6 * kC + 2 * h], tp[6 * kC + 2 * h + 1]);
-              const float2 qc = h ? make_float2(qc4.z, qc4.w) : make_float2(qc4.x, qc4.y);
-              const float2 bv = relu2(__ffma2_rn(kd, t3[2][h], __ffma2_rn(ku, t3[0][h], __fmul2_rn(kc, t3[1][h]))));
-              const float2 av = relu2(__fmul2_rn(k11, relu2(__fmul2_rn(k11, qc))));
-              const float2 sv = __fadd2_rn(__fadd2_rn(av, bv), qc);
-              split2(sv, shi[2 * h], shi[2 * h + 1], slo[2 * h], slo[2 * h + 1]);
-              split2(qc, qhi[2 * h], qhi[2 * h + 1], qlo[2 * h], qlo[2 * h + 1]);
-            }
-            tmem_st4(tcol + jj * 4, shi);
-            tmem_st4(tcol + 32 + jj * 4, slo);
-            tmem_st4(tcol + 64 + jj * 4, qhi);
-            tmem_st4(tcol + 96 + jj * 4, qlo);
           }
           tmem_wait_st();
           tc_fence_before();
@@ -375,8 +407,6 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
     const int qd = warp & 3;
     const int m = qd * 32 + lane;  // pixel row of the tile == TMEM lane
     const uint32_t acc_empty_leader = map_to_cta(acc_empty(0), 0);
-    const float* bias = reinterpret_cast<const float*>(smem + kOffBias);
-    uint8_t* stage = smem + kOffOut;
     const bool issuer = (warp == kWarpEpi0 && lane == 0);
     for (int i = 0; iter_valid(i); ++i) {
       int t = tile_of(i);
@@ -402,13 +432,13 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
         named_bar_sync(1, 128);
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4) {
-          float4 bb = *reinterpret_cast<const float4*>(bias + j * 32 + c4 * 4);
+          const float4 bb = lds4s(sbase + kOffBias + (j * 32 + c4 * 4) * 4);
           float4 o;
           o.x = fmaxf(__uint_as_float(v[c4 * 4 + 0]) + bb.x, 0.f);
           o.y = fmaxf(__uint_as_float(v[c4 * 4 + 1]) + bb.y, 0.f);
           o.z = fmaxf(__uint_as_float(v[c4 * 4 + 2]) + bb.z, 0.f);
           o.w = fmaxf(__uint_as_float(v[c4 * 4 + 3]) + bb.w, 0.f);
-          *reinterpret_cast<float4*>(stage + (m >> 3) * 1024 + (m & 7) * 128 + ((c4 ^ (m & 7)) << 4)) = o;
+          sts4s(sbase + kOffOut + (m >> 3) * 1024 + (m & 7) * 128 + ((c4 ^ (m & 7)) << 4), o);
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
@@ -476,6 +506,10 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* t
   // The taps live in the constant bank (ctc::c_taps, kMaxTapSets sets): classes are processed in groups that fit,
   // each group = one stream-ordered symbol update + one persistent launch.
   const int group = ctc::kMaxTapSets / num_levels;
+  float* ctaps_dev = nullptr;
+  FOD_CUDA_CALL(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctaps_dev), ctc::c_taps));
+  ctc::TapPack pk;
+  memset(&pk, 0, sizeof(pk));
   for (int c0 = 0; c0 < num_classes; c0 += group) {
     const int cn = num_classes - c0 < group ? num_classes - c0 : group;
     long tiles = 0;
@@ -489,10 +523,11 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* t
       L.tile_begin = (int)tiles;
       tiles += (long)cn * L.tiles_per_class;
       FOD_REQUIRE(tiles < (1L << 30), "fod_correlate_levels: too many tiles");
-      FOD_CUDA_CALL(cudaMemcpyToSymbolAsync(ctc::c_taps, taps[l] + (size_t)c0 * 7 * kC, (size_t)cn * 7 * kC * sizeof(float),
-                                            (size_t)l * cn * 7 * kC * sizeof(float), cudaMemcpyDeviceToDevice,
-                                            as_stream(stream)));
+      pk.src[l] = taps[l] + (size_t)c0 * 7 * kC;
     }
+    pk.class_count = cn;
+    ctc::pack_taps_kernel<<<num_levels * cn, kC, 0, as_stream(stream)>>>(pk, ctaps_dev);
+    FOD_CUDA_LAUNCH_CHECK("fod_correlate_levels (pack taps)");
     prm.class_begin = c0;
     prm.class_count = cn;
     prm.total_tiles = (int)tiles;
