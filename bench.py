@@ -216,7 +216,7 @@ def run_gpu_arm(args):
     dev_sets = [torch.stack(hs).to(dev) for hs in host_sets]
     sizes = [(IMG, IMG)] * B
     timer = KernelTimer()
-    timer.wrap(ops, ["correlate", "decode_topk", "nms_proposals", "roi_align", "relation_head", "final_detect"])
+    timer.wrap(ops, ["correlate_levels", "decode_topk", "nms_proposals", "roi_align", "relation_head", "final_detect"])
 
     def step_resident(i):
         x = dev_sets[i % NSETS]
@@ -287,7 +287,7 @@ def run_gpu_arm(args):
     # algorithmic bytes per launch (DESIGN.md "Measurement"), 1-way, B images of 640x640
     lvl_px = [6400, 1600, 400]
     alg = {
-        "correlate": 1024.0 * M_PIXELS * B / 3.0,            # average over the three per-level launches
+        "correlate_levels": 1024.0 * M_PIXELS * B,          # one persistent launch over the three levels
         "decode_topk": (20.0 * M_PIXELS + 28.0 * 2400) * B,
         "nms_proposals": (20.0 * 2400 + 8.0 * 256) * B,
         "roi_align": (512.0 * M_PIXELS + 16.0 * 256 + 256 * 32768.0) * B,   # + materialised pooled rows (v1)

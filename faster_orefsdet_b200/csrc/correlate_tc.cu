@@ -14,10 +14,14 @@
 //     Ahi.Blo, fp32 accumulation in tensor memory; measured error ~1e-6 relative (tools/tc_probe.cu).
 //   * the query tile (+1 pixel halo, zero-filled outside the image by TMA) is staged channel-chunk-wise
 //     (32 channels = one 128-byte swizzled row per pixel) into a 3-deep shared-memory ring by TMA.
-//   * 8 "stencil" warps build the A operand: one pixel per lane, they read the 3x3 neighbourhood from the ring,
-//     evaluate s, split s and q into hi/lo and write them straight into TENSOR MEMORY (tcgen05.st): the A operand
-//     never exists in shared or global memory, and the MMA reads only the weights from shared memory.
-//   * one thread of the leader CTA issues the MMAs (24 per chunk), completion is tracked with tcgen05.commit
+//   * 16 "stencil" warps build the A operand: one pixel per lane (TMEM lane = pixel), they read the 3x3
+//     neighbourhood from the ring (conflict-free LDS.128 thanks to the TMA swizzle), evaluate s with packed
+//     f32x2 math, split s and q into hi/lo and write them straight into TENSOR MEMORY (tcgen05.st): the A operand
+//     never exists in shared or global memory, and the MMA reads only the weights from shared memory.  The support
+//     taps are warp-uniform: they sit in the constant bank and reach the FMAs through uniform registers (LDCU),
+//     costing no shared-memory bandwidth.  A stages are 16 channels wide, 4 deep; warp k of a quadrant owns the
+//     sub-chunks with index % 4 == k, so the warps of one SM sub-partition sit in different pipeline phases.
+//   * one thread of the leader CTA issues the MMAs (12 per sub-chunk), completion is tracked with tcgen05.commit
 //     multicast to both CTAs; accumulators are double buffered in tensor memory (2 x 128 columns).
 //   * 4 epilogue warps: tcgen05.ld -> + bias, ReLU -> swizzled staging tile -> TMA store (clipped at the image
 //     border by the tensor map).
@@ -35,7 +39,10 @@ constexpr int kTileH = 8, kTileW = 16, kTilePx = 128;
 constexpr int kHaloH = kTileH + 2, kHaloW = kTileW + 2, kHaloPx = kHaloH * kHaloW;  // 10 x 18 = 180
 constexpr int kChunk = 32;                                                           // channels per chunk
 constexpr int kNumChunks = kC / kChunk;                                              // 4
-constexpr int kQStages = 3, kAStages = 2, kAccStages = 2;
+constexpr int kQStages = 3, kAStages = 4, kAccStages = 2;
+constexpr int kSub = 16;                      // channels per A stage (sub-chunk); 2 per 32-channel q box
+constexpr int kNumSubs = kC / kSub;           // 8 per tile
+constexpr uint32_t kAStageCols = 4 * kSub;    // [s_hi 16 | s_lo 16 | q_hi 16 | q_lo 16]
 constexpr uint32_t kQStageBytes = kHaloPx * 128;         // 23040
 constexpr uint32_t kQStageStride = 23552;                // rounded up to 1024
 constexpr uint32_t kBHalfRows = 64;                      // W3 rows per CTA
@@ -61,7 +68,7 @@ constexpr int kStencilWarps = 16;
 
 // tensor memory columns
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColA = 0;      // 2 stages x [s_hi 32 | s_lo 32 | q_hi 32 | q_lo 32]
+constexpr uint32_t kColA = 0;      // 4 stages x [s_hi 16 | s_lo 16 | q_hi 16 | q_lo 16]
 constexpr uint32_t kColAcc = 256;  // 2 stages x 128
 
 struct Level {
@@ -131,10 +138,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // Support taps of every (level, class) set of the launch, in the constant bank: a tap is warp-uniform, so it
 // reaches the FMA as a uniform / constant operand instead of costing shared-memory bandwidth per lane.
-#ifndef FOD_TAPS_MODE
-#define FOD_TAPS_MODE 0
-#endif
 constexpr int kMaxTapSets = 15;
+constexpr int kStencilUnroll = 1;  // measured: 1, 2 and 4 run at the same speed; 1 keeps the body inside the L0 I-cache
 // rows 0..6: k11, k13 (left, centre, right), k31 (up, centre, down); row 7: c11 = k11 > 0 ? k11*k11 : 0
 constexpr int kTapRows = 8;
 __constant__ __align__(16) float c_taps[kMaxTapSets][kTapRows][kC];
@@ -193,7 +198,6 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
       off[dy][dx] = (uint32_t)(r * 128 + ((r & 7) << 4));
     }
   const int T = P.total_tiles;
-  uint32_t g = 0;
   int i = 0;
   // Outer loops over the tap sets (level, class): `set` is a loop counter (uniform); this CTA's tiles arrive in
   // set order because tiles are numbered set-major.
@@ -204,19 +208,21 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
       for (; 2 * (i * P.num_pairs + cx.pair) < T && min(2 * (i * P.num_pairs + cx.pair) + cx.rank, T - 1) < set_end;
            ++i) {
 #pragma unroll 1
-        for (int ch = 0; ch < kNumChunks; ++ch, ++g) {
-          const int qs = g % kQStages, as_ = g % kAStages;
-          const uint32_t qph = (g / kQStages) & 1, aph = (g / kAStages) & 1;
+        for (int sub = 0; sub < kNumSubs; ++sub) {  // uniform counter; this warp takes sub % 4 == myk
+          if ((sub & 3) != myk) continue;
+          const uint32_t gq = (uint32_t)i * kNumChunks + (sub >> 1);  // q box (32 channels) of this sub-chunk
+          const int qs = gq % kQStages, as_ = sub & 3;                // kNumSubs % kAStages == 0
+          const uint32_t qph = (gq / kQStages) & 1, aph = ((uint32_t)i * 2 + (sub >> 2)) & 1;
           mbar_wait(bar0 + 8u * qs, qph);                                   // q_full
           mbar_wait(bar0 + 8u * (2 * kQStages + kAStages + as_), aph ^ 1);  // a_empty
           tc_fence_after();
           const uint32_t qt = cx.sbase + kOffQ + qs * kQStageStride;  // shared-window address: LDS, not generic LD
-          const uint32_t tcol = trow + as_ * 128;
-#pragma unroll 1
-          for (int jj = 0; jj < 8; ++jj) {  // uniform counter (keeps the tap address uniform); 4 channels per step
+          const uint32_t tcol = trow + as_ * kAStageCols;
+#pragma unroll(kStencilUnroll)
+          for (int j4 = 0; j4 < 4; ++j4) {  // 4 channels per step
             {
-              if ((jj >> 1) != myk) continue;  // this warp's two channel groups
-              const float* tp = &c_taps[set][0][ch * kChunk + jj * 4];
+              const int jj = (sub & 1) * 4 + j4;  // 16-byte channel group inside the q box
+              const float* tp = &c_taps[set][0][sub * kSub + j4 * 4];
               const uint32_t jx = (uint32_t)jj << 4;
               const float4 k13l = *reinterpret_cast<const float4*>(tp + 1 * kC);
               const float4 k13c = *reinterpret_cast<const float4*>(tp + 2 * kC);
@@ -254,10 +260,10 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
                 split2(sv, shi[2 * h], shi[2 * h + 1], slo[2 * h], slo[2 * h + 1]);
                 split2(qc, qhi[2 * h], qhi[2 * h + 1], qlo[2 * h], qlo[2 * h + 1]);
               }
-              tmem_st4(tcol + jj * 4, shi);
-              tmem_st4(tcol + 32 + jj * 4, slo);
-              tmem_st4(tcol + 64 + jj * 4, qhi);
-              tmem_st4(tcol + 96 + jj * 4, qlo);
+              tmem_st4(tcol + j4 * 4, shi);
+              tmem_st4(tcol + kSub + j4 * 4, slo);
+              tmem_st4(tcol + 2 * kSub + j4 * 4, qhi);
+              tmem_st4(tcol + 3 * kSub + j4 * 4, qlo);
             }
           }
           tmem_wait_st();
@@ -294,10 +300,10 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
   if (tid == 0) {
     for (int s = 0; s < kQStages; ++s) {
       mbar_init(q_full(s), 1);
-      mbar_init(q_empty(s), kStencilWarps);
+      mbar_init(q_empty(s), kStencilWarps / 2);  // the 8 warps that read a q box
     }
     for (int s = 0; s < kAStages; ++s) {
-      mbar_init(a_full(s), 2 * kStencilWarps);  // stencil warps of both CTAs (used in the leader only)
+      mbar_init(a_full(s), 2 * 4);  // one warp per TMEM quadrant, both CTAs (used in the leader only)
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
@@ -379,19 +385,20 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
         mbar_wait(acc_empty(as_), aph ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + kColAcc + as_ * 128;
-        for (int ch = 0; ch < kNumChunks; ++ch, ++g) {
-          int s = g % kAStages;
-          uint32_t ph = (g / kAStages) & 1;
+        for (int sub = 0; sub < kNumSubs; ++sub, ++g) {
+          const int s = g % kAStages;
+          const uint32_t ph = (g / kAStages) & 1;
           mbar_wait(a_full(s), ph);
           tc_fence_after();
-          const uint32_t a0 = tmem_base + kColA + s * 128;
+          const uint32_t a0 = tmem_base + kColA + s * kAStageCols;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              uint32_t ah = a0 + half * 64 + ks * 8, al = ah + 32;
-              uint64_t boff = (uint64_t)(((half * 4 + ch) * kBChunkBytes + ks * 32) >> 4);
-              uint32_t acc = (ch | half | ks) ? 1u : 0u;
+            for (int ks = 0; ks < kSub / 8; ++ks) {
+              const uint32_t ah = a0 + half * 2 * kSub + ks * 8, al = ah + kSub;
+              const uint64_t boff =
+                  (uint64_t)(((half * 4 + (sub >> 1)) * kBChunkBytes + (sub & 1) * kSub * 4 + ks * 32) >> 4);
+              const uint32_t acc = (sub | half | ks) ? 1u : 0u;
               mma_tf32_ts<2>(d, ah, bhi0 + boff, idesc, acc);
               mma_tf32_ts<2>(d, al, bhi0 + boff, idesc, 1u);
               mma_tf32_ts<2>(d, ah, blo0 + boff, idesc, 1u);

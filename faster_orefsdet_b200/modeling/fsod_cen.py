@@ -190,7 +190,7 @@ class CenterNet2Detector(nn.Module):
         attempt_cap = None
         for attempt in range(2):
             status = ops.new_status(dev)
-            attn = [ops.correlate(q, t, self.conv3.weight, self.conv3.bias) for q, t in zip(raw, bank.taps)]
+            attn = ops.correlate_levels(raw, bank.taps, self.conv3.weight, self.conv3.bias)   # one persistent launch
             props = self.proposal_generator.propose_raw(attn, status, attempt_cap)
             (ob, os_, ocls, orow, oc), per_roi = self.roi_heads.detect_raw(raw, bank.bias_cls, props.boxes, props.count, C,
                                                                            image_hw, out_hw, status)

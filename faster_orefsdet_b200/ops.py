@@ -90,22 +90,8 @@ def support_taps(proto: Tensor) -> Tensor:
 
 # --------------------------------------------------------------------------- Q2+Q3
 def correlate(q: Tensor, taps: Tensor, w3: Tensor, b3: Tensor) -> Tensor:
-    """q [B,128,H,W], taps [C,7,128], w3 [128,256(,1,1)], b3 [128] -> attn [B*C,128,H,W]
-    (channels_last), problem-major (fsod_cen.py:463-470)."""
-    q = nhwc(q, "q")
-    B, ch, H, W = q.shape
-    C = taps.shape[0]
-    if ch != 128 or tuple(taps.shape[1:]) != (7, 128):
-        raise _lib.FodError("correlate: bad shapes")
-    w3 = _chk(w3, torch.float32, "w3").reshape(128, 256).contiguous()
-    b3 = _chk(b3, torch.float32, "b3").contiguous()
-    taps = _chk(taps, torch.float32, "taps").contiguous()
-    attn = torch.empty((B * C, 128, H, W), dtype=torch.float32, device=q.device, memory_format=torch.channels_last)
-    if attn.stride() != (H * W * 128, 1, W * 128, 128):
-        attn = torch.empty((B * C, H, W, 128), dtype=torch.float32, device=q.device).permute(0, 3, 1, 2)
-    _lib.check(_lib.lib().fod_correlate(_ptr(q), _ptr(taps), _ptr(w3), _ptr(b3), _ptr(attn), B, C, H, W, _stream()),
-               "fod_correlate")
-    return attn
+    """One level: q [B,128,H,W], taps [C,7,128] -> attn [B*C,128,H,W] (see correlate_levels)."""
+    return correlate_levels([q], [taps], w3, b3)[0]
 
 
 def _empty_nhwc(n: int, h: int, w: int, device) -> Tensor:
