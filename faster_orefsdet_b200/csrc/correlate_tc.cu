@@ -111,14 +111,6 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& P, int t) {
 }
 
 __device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float4 lds4s(uint32_t saddr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-  return v;
-}
-__device__ __forceinline__ void sts4s(uint32_t saddr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 __device__ __forceinline__ float4 f4_relu(float4 v) {
   return make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
 }
@@ -128,9 +120,6 @@ __device__ __forceinline__ float4 f4_fma(float4 a, float4 b, float4 c) {
 }
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -169,8 +158,8 @@ struct StencilCtx {
 
 __device__ __forceinline__ float2 relu2(float2 v) { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
 __device__ __forceinline__ void split2(float2 v, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
-  h0 = __float_as_uint(v.x) & 0xFFFFE000u;
-  h1 = __float_as_uint(v.y) & 0xFFFFE000u;
+  h0 = (__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u;  // round to nearest tf32 (see tc05.cuh split_tf32)
+  h1 = (__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u;
   float2 lo = __ffma2_rn(make_float2(__uint_as_float(h0), __uint_as_float(h1)), make_float2(-1.f, -1.f), v);
   l0 = __float_as_uint(lo.x);
   l1 = __float_as_uint(lo.y);

@@ -1,4 +1,4 @@
-// R1/P1: multi-level ROIAlign (NHWC), R2+R3: folded relation head + scoring + box decode.
+// R1/P1: multi-level ROIAlign (NHWC).  R2+R3 (relation head) live in relation_tc.cu.
 #include "common.cuh"
 
 namespace fod {
@@ -99,115 +99,6 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Relation head, v1 (fp32 CUDA-core contraction).
-//   D[rows][128] = pooled[rows][8192] . w_fold[128][8192]^T ; f = relu(D + bias_cls[c])
-//   logits = w_out[0:2] f + b ; deltas = w_out[2:6] f + b ; softmax ; apply_deltas
-// tile: 64 ROI rows x 128 columns per CTA, 256 threads, 4x8 register tile, K chunks of 16
-// with register double buffering.
-// ------------------------------------------------------------------------------------------------
-constexpr int kRM = 64, kRN = 128, kRK = 16, kRelThreads = 256;
-constexpr int kK = 64 * kC;  // 8192
-constexpr float kScaleClamp = 4.135166556742356f;  // log(1000/16), d2 box_regression.py:13
-
-__global__ void __launch_bounds__(kRelThreads, 2)
-relation_head_kernel(const float* __restrict__ pooled, const float* __restrict__ w_fold, const float* __restrict__ bias_cls,
-                     const float* __restrict__ w_out, const float* __restrict__ b_out, const float* __restrict__ rois,
-                     const int32_t* __restrict__ roi_count, int C, int roi_cap, float4 reg_w,
-                     float* __restrict__ det_boxes, float* __restrict__ det_scores,
-                     float* __restrict__ logits_out, float* __restrict__ deltas_out) {
-  __shared__ __align__(16) float As[kRK][kRM + 4];
-  __shared__ __align__(16) float Ws[kRK][kRN + 4];
-  __shared__ __align__(16) float Wo[6][kRN];
-  const int p = blockIdx.y, r0 = blockIdx.x * kRM;
-  const int cnt = roi_count ? min(roi_count[p], roi_cap) : roi_cap;
-  if (r0 >= cnt) return;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int lr = tid >> 2, lk = (tid & 3) * 4;
-  for (int i = tid; i < 6 * kRN; i += kRelThreads) (&Wo[0][0])[i] = w_out[i];
-  const bool rvalid = (r0 + lr) < cnt;
-  const float* arow = pooled + ((size_t)p * roi_cap + r0 + lr) * kK + lk;
-  const float* wrow0 = w_fold + (size_t)lr * kK + lk;
-  const float* wrow1 = w_fold + (size_t)(lr + 64) * kK + lk;
-  float acc[4][8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  float4 an = rvalid ? ldg4(arow) : make_float4(0, 0, 0, 0);
-  float4 wn0 = ldg4(wrow0), wn1 = ldg4(wrow1);
-  for (int k0 = 0; k0 < kK; k0 += kRK) {
-    __syncthreads();
-    As[lk + 0][lr] = an.x; As[lk + 1][lr] = an.y; As[lk + 2][lr] = an.z; As[lk + 3][lr] = an.w;
-    Ws[lk + 0][lr] = wn0.x; Ws[lk + 1][lr] = wn0.y; Ws[lk + 2][lr] = wn0.z; Ws[lk + 3][lr] = wn0.w;
-    Ws[lk + 0][lr + 64] = wn1.x; Ws[lk + 1][lr + 64] = wn1.y; Ws[lk + 2][lr + 64] = wn1.z; Ws[lk + 3][lr + 64] = wn1.w;
-    __syncthreads();
-    if (k0 + kRK < kK) {
-      an = rvalid ? ldg4(arow + k0 + kRK) : make_float4(0, 0, 0, 0);
-      wn0 = ldg4(wrow0 + k0 + kRK);
-      wn1 = ldg4(wrow1 + k0 + kRK);
-    }
-#pragma unroll
-    for (int k = 0; k < kRK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[k][tx * 8]);
-      const float4 w1 = *reinterpret_cast<const float4*>(&Ws[k][tx * 8 + 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
-    }
-  }
-  // epilogue
-  const int c = p % C;
-  const float4 bb0 = ldg4(bias_cls + (size_t)c * kRN + tx * 8), bb1 = ldg4(bias_cls + (size_t)c * kRN + tx * 8 + 4);
-  const float bv[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float fj = fmaxf(acc[i][j] + bv[j], 0.f);
-#pragma unroll
-      for (int o = 0; o < 6; ++o) part[o] = fmaf(fj, Wo[o][tx * 8 + j], part[o]);
-    }
-#pragma unroll
-    for (int o = 0; o < 6; ++o) {
-#pragma unroll
-      for (int s = 8; s > 0; s >>= 1) part[o] += __shfl_xor_sync(0xffffffffu, part[o], s);
-    }
-    const int r = r0 + ty * 4 + i;
-    if (tx == 0 && r < cnt) {
-      const size_t row = (size_t)p * roi_cap + r;
-      const float l0 = part[0] + b_out[0], l1 = part[1] + b_out[1];
-      const float d0 = part[2] + b_out[2], d1 = part[3] + b_out[3], d2 = part[4] + b_out[4], d3 = part[5] + b_out[5];
-      if (logits_out) {
-        logits_out[row * 2] = l0;
-        logits_out[row * 2 + 1] = l1;
-      }
-      if (deltas_out) *reinterpret_cast<float4*>(deltas_out + row * 4) = make_float4(d0, d1, d2, d3);
-      // softmax over (fg, bg) -> fg probability (custom_fast_rcnn.py:169)
-      const float m = fmaxf(l0, l1);
-      const float e0 = expf(l0 - m), e1 = expf(l1 - m);
-      det_scores[row] = e0 / (e0 + e1);
-      // apply_deltas (box_regression.py:87-115); clipping happens in fod_final_detect, after the
-      // reference's isfinite filter (d2 fast_rcnn.py:137-147)
-      const float4 bx = *reinterpret_cast<const float4*>(rois + row * 4);
-      const float w = bx.z - bx.x, h = bx.w - bx.y;
-      const float cx = bx.x + 0.5f * w, cy = bx.y + 0.5f * h;
-      const float dx = d0 / reg_w.x, dy = d1 / reg_w.y;
-      const float dw = fminf(d2 / reg_w.z, kScaleClamp), dh = fminf(d3 / reg_w.w, kScaleClamp);
-      const float pcx = __fadd_rn(__fmul_rn(dx, w), cx), pcy = __fadd_rn(__fmul_rn(dy, h), cy);
-      const float pw = __fmul_rn(expf(dw), w), ph = __fmul_rn(expf(dh), h);
-      const float x1 = __fsub_rn(pcx, __fmul_rn(0.5f, pw)), y1 = __fsub_rn(pcy, __fmul_rn(0.5f, ph));
-      const float x2 = __fadd_rn(pcx, __fmul_rn(0.5f, pw)), y2 = __fadd_rn(pcy, __fmul_rn(0.5f, ph));
-      *reinterpret_cast<float4*>(det_boxes + row * 4) = make_float4(x1, y1, x2, y2);
-    }
-  }
-}
-
 }  // namespace fod
 
 using namespace fod;
@@ -243,21 +134,3 @@ extern "C" int fod_roi_align(const float* const* feat, const fod_level_t* levels
   return FOD_OK;
 }
 
-extern "C" int fod_relation_head(const float* pooled, const float* w_fold, const float* bias_cls, const float* w_out,
-                                 const float* b_out, const float* rois, const int32_t* roi_count, int num_problems,
-                                 int problems_per_image, int roi_cap, const float* reg_weights, float* det_boxes,
-                                 float* det_scores, float* logits, float* deltas, fod_stream_t stream) {
-  FOD_REQUIRE(pooled && w_fold && bias_cls && w_out && b_out && rois && reg_weights && det_boxes && det_scores,
-              "fod_relation_head: null pointer");
-  FOD_REQUIRE(num_problems >= 0 && problems_per_image > 0 && roi_cap > 0, "fod_relation_head: bad sizes");
-  FOD_REQUIRE(num_problems % problems_per_image == 0, "fod_relation_head: num_problems not a multiple of classes");
-  if (num_problems == 0) return FOD_OK;
-  FOD_REQUIRE(num_problems <= 65535, "fod_relation_head: num_problems %d > 65535", num_problems);
-  dim3 grid((roi_cap + kRM - 1) / kRM, num_problems);
-  float4 rw = make_float4(reg_weights[0], reg_weights[1], reg_weights[2], reg_weights[3]);
-  relation_head_kernel<<<grid, kRelThreads, 0, as_stream(stream)>>>(pooled, w_fold, bias_cls, w_out, b_out, rois,
-                                                                    roi_count, problems_per_image, roi_cap, rw,
-                                                                    det_boxes, det_scores, logits, deltas);
-  FOD_CUDA_LAUNCH_CHECK("fod_relation_head");
-  return FOD_OK;
-}

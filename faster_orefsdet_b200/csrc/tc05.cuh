@@ -120,6 +120,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// cta_group::2 form: the bytes complete on an mbarrier of the PEER (leader) CTA; `bar` is a shared::cluster address
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -275,13 +282,28 @@ __device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t mask) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3xTF32 operand split: x = hi + lo with hi = x truncated to tf32 (the tensor core reads only the top 19
-// bits of each 32-bit operand), lo = x - hi (exact in fp32; its own truncation to tf32 leaves a relative
-// error of 2^-21 on x).  A*B ~= Ahi*Bhi + Alo*Bhi + Ahi*Blo.
+// 3xTF32 operand split: x = hi + lo, hi = x rounded to nearest tf32 (integer add of half an ulp, then mask;
+// the tensor core reads only the top 19 bits of each 32-bit operand), lo = x - hi (exact in fp32, |lo| <=
+// 2^-11 |x|, sign random).  The hardware truncates lo to tf32: error <= 2^-21 |x| with random sign, so it does
+// not accumulate coherently along K (a truncated hi would make every lo positive and the error a bias that
+// grows linearly with K: measured 1e-4 absolute at K = 8192).  A*B ~= Ahi*Bhi + Alo*Bhi + Ahi*Blo.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xFFFFE000u;
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// explicit shared-window accesses (a generic pointer would compile to LD/ST with address-space resolution)
+__device__ __forceinline__ float4 lds4s(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts4s(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // byte offset of fp32 element (row r, column c) inside a K-major SW128 tile (c in [0,32))
@@ -302,5 +324,8 @@ PFN_encodeTiled get_encode_tiled();
 // fp32 NHWC map [N][H][W][C] -> 4-D tensor map (dims innermost first: C, W, H, N), box (bc, bw, bh, 1),
 // 128-byte swizzle (bc * 4 must be 128), out-of-bounds elements read as zero / are not written.
 int make_nhwc_map(CUtensorMap* out, const float* base, int N, int H, int W, int C, int bc, int bw, int bh);
+// fp32 row-major matrix [rows][cols] -> 2-D tensor map, box (box_cols, box_rows), 128-byte swizzle
+// (box_cols * 4 must be 128), rows beyond the matrix read as zero.
+int make_matrix_map(CUtensorMap* out, const float* base, long rows, long cols, int box_cols, int box_rows);
 
 }  // namespace fod

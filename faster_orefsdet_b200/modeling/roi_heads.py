@@ -103,7 +103,10 @@ class CustomCascadeROIHeads(nn.Module):
     def folded(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         key = tuple((p.data_ptr(), p._version, p.device) for p in self._fold_params())
         if self._fold_cache is None or self._fold_cache[0] != key:
-            self._fold_cache = (key, fold.fold_relation_weights(self._state()))
+            w_fold, w_out, b_out = fold.fold_relation_weights(self._state())
+            if w_fold.is_cuda:       # tf32 hi / lo planes for the tensor-core kernel, once per weight load
+                w_fold = ops.split_tf32(w_fold)
+            self._fold_cache = (key, (w_fold, w_out, b_out))
         return self._fold_cache[1]
 
     def class_bias(self, support_mean: torch.Tensor) -> torch.Tensor:

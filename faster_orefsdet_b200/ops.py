@@ -200,19 +200,31 @@ def roi_align(feats: Sequence[Tensor], strides: Sequence[int], rois: Tensor, roi
 
 
 # --------------------------------------------------------------------------- R2+R3
+def split_tf32(w: Tensor) -> Tensor:
+    """fp32 tensor -> [2, *w.shape]: plane 0 = tf32-rounded value, plane 1 = exact remainder (the B operand planes
+    of the 3xTF32 tensor-core contraction; done once per weight load)."""
+    w = _chk(w, torch.float32, "w").contiguous()
+    out = torch.empty((2,) + tuple(w.shape), dtype=torch.float32, device=w.device)
+    _lib.check(_lib.lib().fod_split_tf32(_ptr(w), _ptr(out), ctypes.c_size_t(w.numel()), _stream()), "fod_split_tf32")
+    return out
+
+
 def relation_head(pooled: Tensor, w_fold: Tensor, bias_cls: Tensor, w_out: Tensor, b_out: Tensor, rois: Tensor,
                   roi_count: Optional[Tensor], problems_per_image: int, reg_weights: Sequence[float],
                   want_raw: bool = False):
     """-> (det_boxes [P,cap,4] unclipped, det_scores [P,cap][, logits [P,cap,2], deltas [P,cap,4]])
-    (fsod_roi_heads.py:482-520, custom_fast_rcnn.py:160-170, d2 box_regression.py:77-115)."""
+    (fsod_roi_heads.py:482-520, custom_fast_rcnn.py:160-170, d2 box_regression.py:77-115).
+    w_fold: the folded matrix [128,8192] or, preferably, its pre-split planes [2,128,8192] (split_tf32)."""
     P, cap = rois.shape[0], rois.shape[1]
     dev = rois.device
+    if w_fold.dim() == 2:
+        w_fold = split_tf32(w_fold)
     for t, n in ((pooled, "pooled"), (w_fold, "w_fold"), (bias_cls, "bias_cls"), (w_out, "w_out"), (b_out, "b_out"),
                  (rois, "rois")):
         _chk(t, torch.float32, n)
         if not t.is_contiguous():
             raise _lib.FodError(f"relation_head: {n} must be contiguous")
-    if tuple(w_fold.shape) != (128, 8192) or tuple(w_out.shape) != (6, 128) or bias_cls.shape[-1] != 128:
+    if tuple(w_fold.shape) != (2, 128, 8192) or tuple(w_out.shape) != (6, 128) or bias_cls.shape[-1] != 128:
         raise _lib.FodError("relation_head: bad weight shapes")
     det_boxes = torch.zeros((P, cap, 4), dtype=torch.float32, device=dev)
     det_scores = torch.zeros((P, cap), dtype=torch.float32, device=dev)

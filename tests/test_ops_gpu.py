@@ -284,6 +284,36 @@ def test_relation_head_matches_reference_and_oracle():
         assert float(ds[p, n:].abs().max()) == 0.0 if n < 96 else True
 
 
+def test_relation_head_tensor_core_multi_class_ragged_counts():
+    """tcgen05 3xTF32 contraction: several classes, roi_cap not a multiple of 128, empty / 1-row / full problems."""
+    sd = head_state_dict()
+    B, C, cap = 3, 2, 320
+    P = B * C
+    counts = torch.tensor([320, 0, 1, 129, 256, 37], dtype=torch.int32)
+    pooled = synth.tensor((P, cap, 64, 128), 71, -1.0, 1.5)
+    bx = _boxes(P * cap, 72, 30.0, 280.0, 8.0, 150.0).reshape(P, cap, 4)
+    sup = synth.tensor((C, 128, 8, 8), 73, -1.0, 1.0)
+    w_fold, w_out, b_out = fold.fold_relation_weights(sd)
+    bias = fold.fold_class_bias(sd, sup)
+    db, ds, logits, deltas = ops.relation_head(pooled.to(DEV), ops.split_tf32(w_fold.to(DEV)), bias.to(DEV), w_out.to(DEV),
+                                               b_out.to(DEV), bx.to(DEV), counts.to(DEV), C, CFG.bbox_reg_weights,
+                                               want_raw=True)
+    torch.cuda.synchronize()
+    for p in range(P):
+        n = int(counts[p])
+        if n == 0:
+            continue
+        x = pooled[p, :n].reshape(n, 8, 8, 128).permute(0, 3, 1, 2).contiguous()
+        ref_logits, ref_deltas = O.relation_head(x, sup[p % C:p % C + 1], sd)
+        assert_close(logits[p, :n].cpu(), ref_logits, what=f"logits p{p}")
+        assert_close(deltas[p, :n].cpu(), ref_deltas, atol=2e-5, what=f"deltas p{p}")
+        sc, bb = O.score_and_decode(ref_logits, ref_deltas, bx[p, :n], CFG)
+        assert_close(ds[p, :n].cpu(), sc, what=f"scores p{p}")
+        assert_close(db[p, :n].cpu(), bb, atol=2e-3, what=f"boxes p{p}")
+        if n < cap:
+            assert float(ds[p, n:].abs().max()) == 0.0
+
+
 # ----------------------------------------------------------------------------------------- final detect
 @pytest.mark.parametrize("C", [1, 3])
 def test_final_detect_bit_exact(C):

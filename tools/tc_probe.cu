@@ -29,7 +29,7 @@ constexpr int NT = 128;  // total N
 // G = cta group (1 or 2), TS = A from tensor memory (else shared memory), NPROD = 1 (plain tf32) or 3 (3xTF32)
 template <int G, bool TS, int NPROD>
 __global__ void __launch_bounds__(128, 1) gemm_probe(const float* __restrict__ X, const float* __restrict__ W,
-                                                     float* __restrict__ out) {
+                                                     float* __restrict__ out, int repeat) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(128, 1) gemm_probe(const float* __restrict__ X
     const uint32_t idesc = idesc_tf32(128 * G, NT);
     const uint32_t d = tmem_base + 128;
     uint32_t acc = 0;
+    for (int rep = 0; rep < repeat; ++rep)  // repeat > 1: accumulate the same product again (accumulator rounding probe)
     for (int kc = 0; kc < 2; ++kc)
       for (int ks = 0; ks < 4; ++ks) {
         uint64_t bh = smem_desc_k_sw128(smem_u32(b_hi) + kc * NB * 128 + ks * 32);
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(128, 1) gemm_probe(const float* __restrict__ X
 }
 
 template <int G, bool TS, int NPROD>
-static int run_gemm(const char* name) {
+static int run_gemm(const char* name, int repeat = 1) {
   const int M = 128 * G;
   std::vector<float> X((size_t)M * K), W((size_t)NT * K), out((size_t)M * NT);
   srand(1234);
@@ -165,7 +166,7 @@ static int run_gemm(const char* name) {
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, kern, (const float*)dX, (const float*)dW, dO));
+  CK(cudaLaunchKernelEx(&cfg, kern, (const float*)dX, (const float*)dW, dO, repeat));
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out.data(), dO, out.size() * 4, cudaMemcpyDeviceToHost));
   double maxerr = 0, maxref = 0;
@@ -173,9 +174,30 @@ static int run_gemm(const char* name) {
     for (int n = 0; n < NT; ++n) {
       double r = 0;
       for (int k = 0; k < K; ++k) r += (double)X[(size_t)m * K + k] * W[(size_t)n * K + k];
+      r *= repeat;
       maxerr = fmax(maxerr, fabs(r - out[(size_t)m * NT + n]));
       maxref = fmax(maxref, fabs(r));
     }
+  double sum_signed = 0;
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < NT; ++n) {
+      double r = 0;
+      for (int k = 0; k < K; ++k) r += (double)X[(size_t)m * K + k] * W[(size_t)n * K + k];
+      r *= repeat;
+      sum_signed += (out[(size_t)m * NT + n] - r) / (fabs(r) + 1e-3);
+    }
+  printf("repeat=%d mean signed rel err (sign-normalised: err*sign(ref)) ", repeat);
+  {
+    double s2 = 0;
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < NT; ++n) {
+        double r = 0;
+        for (int k = 0; k < K; ++k) r += (double)X[(size_t)m * K + k] * W[(size_t)n * K + k];
+        r *= repeat;
+        s2 += (out[(size_t)m * NT + n] - r) * (r > 0 ? 1 : -1) / (fabs(r) + 1e-3);
+      }
+    printf("%.3e\n", s2 / (M * NT));
+  }
   printf("%s G=%d %s prod=%d: max abs err %.3e (max |ref| %.3f) rel %.3e -> %s\n", name, G, TS ? "TS" : "SS", NPROD,
          maxerr, maxref, maxerr / maxref, (maxerr / maxref < (NPROD == 3 ? 2e-6 : 2e-3)) ? "OK" : "FAIL");
   return 0;
@@ -277,6 +299,10 @@ int main(int argc, char** argv) {
   if (!strcmp(mode, "g1ss")) { run_gemm<1, false, 1>(mode); return run_gemm<1, false, 3>(mode); }
   if (!strcmp(mode, "g2ts")) { run_gemm<2, true, 1>(mode); return run_gemm<2, true, 3>(mode); }
   if (!strcmp(mode, "g2ss")) { run_gemm<2, false, 1>(mode); return run_gemm<2, false, 3>(mode); }
+  if (!strcmp(mode, "acc")) {  // accumulator rounding: error growth with the number of accumulations
+    for (int r : {1, 16, 128, 1024}) run_gemm<1, true, 3>(mode, r);
+    return 0;
+  }
   if (!strcmp(mode, "tma")) return run_tma();
   printf("unknown mode\n");
   return 1;
