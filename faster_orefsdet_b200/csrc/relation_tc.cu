@@ -28,10 +28,11 @@ constexpr int kStages = 4;           // A ring, B ring and TMEM A ring
 constexpr int kAccStages = 2;
 // The tensor core adds into its fp32 accumulator with round-toward-zero (measured, tools/tc_probe.cu acc: the
 // relative bias grows by ~1.7e-8 per accumulated MMA).  3072 MMAs per output (K = 8192, 3 products) would leave a
-// 5e-5 bias, so the K loop is cut into kParts partial sums of 384 MMAs each (bias ~6e-6); the partials are added in
-// IEEE fp32 by the epilogue warps into a running sum held in shared memory.
-constexpr int kParts = 8;
-constexpr int kChunksPerPart = kNumChunks / kParts;  // 32
+// 5e-5 bias, so the K loop is cut into kParts partial sums of 96 MMAs each (bias ~1.6e-6, the chain length of the
+// correlation kernel); the partials are added in IEEE fp32 by the epilogue warps into a running sum held in
+// shared memory.
+constexpr int kParts = 32;
+constexpr int kChunksPerPart = kNumChunks / kParts;  // 8
 constexpr uint32_t kABytes = 128 * 128;       // 128 rows x 32 fp32
 constexpr uint32_t kBHalfRows = 64;
 constexpr uint32_t kBPlaneBytes = kBHalfRows * 128;  // 8192: hi or lo plane of one chunk
@@ -61,7 +62,7 @@ constexpr uint32_t kColAcc = 256;    // 2 stages x 128
 constexpr float kScaleClamp = 4.135166556742356f;  // log(1000/16), d2 box_regression.py:13
 
 struct Params {
-  CUtensorMap a_map;    // pooled  [P*roi_cap][8192], box 32 x 128
+  CUtensorMap a_map;    // pooled, tiled [P*units*256*128][32], box 32 x 128 (one contiguous 16 KB A tile)
   CUtensorMap whi_map;  // w_fold hi plane [128][8192], box 32 x 64
   CUtensorMap wlo_map;  // w_fold lo plane
   const float* bias_cls;  // [C][128]
@@ -181,13 +182,13 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
       uint32_t g = 0;
       for (int i = 0; in_range(i); ++i) {
         const Slot me = decode_unit(P, pref, slot_of(i, rank));
-        const int row0 = me.p * P.roi_cap + me.r0;
+        const int tile0 = (me.p * P.tiles_per_problem + (me.r0 >> 7)) * kNumChunks;  // first A tile of this unit
         for (int kc = 0; kc < kNumChunks; ++kc, ++g) {
           const int s = g % kStages;
           const uint32_t ph = (g / kStages) & 1;
           mbar_wait(a_empty(s), ph ^ 1);
           mbar_arrive_expect_tx(a_full(s), kABytes);
-          tma_load_2d(sbase + kOffA + s * kABytes, &P.a_map, a_full(s), kc * kChunk, row0);
+          tma_load_2d(sbase + kOffA + s * kABytes, &P.a_map, a_full(s), 0, (tile0 + kc) * 128);
           // weights: each CTA loads its 64 rows; both CTAs' bytes complete on the LEADER's barrier
           mbar_wait(st_free(s), ph ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(b_full(s), 2 * kBBytes);
@@ -403,8 +404,9 @@ extern "C" int fod_relation_head(const float* pooled, const float* w_fold_split,
   if (num_problems == 0) return FOD_OK;
   rtc::Params prm;
   memset(&prm, 0, sizeof(prm));
-  const long rows = (long)num_problems * roi_cap;
-  int rc = make_matrix_map(&prm.a_map, pooled, rows, rtc::kK, rtc::kChunk, 128);
+  const long units = (long)num_problems * ((roi_cap + 127) / 128);
+  FOD_REQUIRE(units * rtc::kNumChunks * 128 < (1L << 31), "fod_relation_head: pooled buffer too large for one call");
+  int rc = make_matrix_map(&prm.a_map, pooled, units * rtc::kNumChunks * 128, rtc::kChunk, rtc::kChunk, 128);
   if (rc != FOD_OK) return rc;
   rc = make_matrix_map(&prm.whi_map, w_fold_split, kC, rtc::kK, rtc::kChunk, rtc::kBHalfRows);
   if (rc != FOD_OK) return rc;

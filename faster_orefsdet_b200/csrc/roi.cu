@@ -16,6 +16,7 @@ struct RoiParams {
   int C;        // problems per image
   int roi_cap;
   int R;        // output resolution
+  int tiled;    // output layout, see roi_align_kernel
 };
 
 // d2 poolers.py:50-58, fp32 like torch: floor(4 + log2(sqrt(area)/224 + 1e-8)) clamped to the
@@ -53,7 +54,19 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
   const int grid_h = (int)ceilf(__fdiv_rn(roi_h, (float)R));
   const int grid_w = (int)ceilf(__fdiv_rn(roi_w, (float)R));
   const float count = fmaxf((float)(grid_h * grid_w), 1.0f);
-  float* out = pooled + ((size_t)p * prm.roi_cap + r) * R * R * kC + lane * 4;
+  // Output layout.  tiled == 0: [P][roi_cap][R*R][128] (row-major ROI rows).  tiled == 1 (R == 8, consumed by
+  // fod_relation_head): [P][units][256 k-chunks][128 rows][32], units = ceil(roi_cap / 128): the 16 KB A tile of
+  // one 32-wide K chunk of 128 ROI rows is contiguous, so one TMA box fetches it as a linear stream.
+  float* out;
+  size_t bin_stride;
+  if (prm.tiled) {
+    const int units = (prm.roi_cap + 127) >> 7;
+    out = pooled + ((((size_t)p * units + (r >> 7)) * 256 + (lane >> 3)) * 128 + (r & 127)) * 32 + (lane & 7) * 4;
+    bin_stride = (size_t)4 * 128 * 32;  // next bin = 4 k-chunks further
+  } else {
+    out = pooled + ((size_t)p * prm.roi_cap + r) * R * R * kC + lane * 4;
+    bin_stride = kC;
+  }
   for (int bin = warp; bin < R * R; bin += nwarps) {
     const int ph = bin / R, pw = bin - ph * R;
     float4 acc = make_float4(0, 0, 0, 0);
@@ -95,7 +108,7 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
       }
     }
     acc.x /= count; acc.y /= count; acc.z /= count; acc.w /= count;
-    *reinterpret_cast<float4*>(out + (size_t)bin * kC) = acc;
+    *reinterpret_cast<float4*>(out + (size_t)bin * bin_stride) = acc;
   }
 }
 
@@ -105,7 +118,7 @@ using namespace fod;
 
 extern "C" int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
                              int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap,
-                             int resolution, float* pooled, int32_t* out_level, fod_stream_t stream) {
+                             int resolution, int tiled, float* pooled, int32_t* out_level, fod_stream_t stream) {
   FOD_REQUIRE(feat && levels && rois && pooled, "fod_roi_align: null pointer");
   FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_roi_align: num_levels %d out of range", num_levels);
   FOD_REQUIRE(batch >= 0 && problems_per_image > 0 && roi_cap > 0 && resolution > 0 && resolution <= 16,
@@ -128,6 +141,8 @@ extern "C" int fod_roi_align(const float* const* feat, const fod_level_t* levels
   prm.C = problems_per_image;
   prm.roi_cap = roi_cap;
   prm.R = resolution;
+  FOD_REQUIRE(!tiled || resolution == 8, "fod_roi_align: the tiled layout needs resolution 8");
+  prm.tiled = tiled ? 1 : 0;
   dim3 grid(roi_cap, (unsigned)P);
   roi_align_kernel<<<grid, 256, 0, as_stream(stream)>>>(prm, rois, roi_count, pooled, out_level);
   FOD_CUDA_LAUNCH_CHECK("fod_roi_align");

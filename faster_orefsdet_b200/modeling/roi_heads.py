@@ -121,7 +121,7 @@ class CustomCascadeROIHeads(nn.Module):
         """features[l] [B,128,H,W] raw backbone maps; rois [B*C,cap,4]; returns the padded
         outputs of ops.final_detect plus the per-ROI (boxes, scores)."""
         w_fold, w_out, b_out = self.folded()
-        pooled = ops.roi_align(features, self.strides, rois, roi_count, num_classes, self.pooler_resolution)
+        pooled = ops.roi_align(features, self.strides, rois, roi_count, num_classes, self.pooler_resolution, tiled=True)
         det_boxes, det_scores = ops.relation_head(pooled, w_fold, bias_cls, w_out, b_out, rois, roi_count, num_classes,
                                                   self.bbox_reg_weights)
         p = self.box_predictor[0]

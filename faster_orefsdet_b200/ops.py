@@ -177,9 +177,27 @@ def nms_proposals(boxes: Tensor, scores: Tensor, count: Optional[Tensor], iou_th
 
 
 # --------------------------------------------------------------------------- R1 / P1
+def tile_pooled(x: Tensor) -> Tensor:
+    """[P,cap,64,128] ROI rows -> the tiled operand layout [P,U,256,128,32] of relation_head (U = ceil(cap/128);
+    unit u = rows 128u..128u+127, k-chunk = bin*4 + channel//32).  Test / interop helper (torch ops)."""
+    P, cap = x.shape[0], x.shape[1]
+    U = (cap + 127) // 128
+    rows = torch.zeros((P, U * 128, 8192), dtype=x.dtype, device=x.device)
+    rows[:, :cap] = x.reshape(P, cap, 8192)
+    return rows.reshape(P, U, 128, 256, 32).permute(0, 1, 3, 2, 4).contiguous()
+
+
+def untile_pooled(t: Tensor, cap: int) -> Tensor:
+    """Inverse of tile_pooled: [P,U,256,128,32] -> [P,cap,64,128]."""
+    P, U = t.shape[0], t.shape[1]
+    return t.permute(0, 1, 3, 2, 4).reshape(P, U * 128, 64, 128)[:, :cap]
+
+
 def roi_align(feats: Sequence[Tensor], strides: Sequence[int], rois: Tensor, roi_count: Optional[Tensor],
-              problems_per_image: int, resolution: int, out: Optional[Tensor] = None, want_levels: bool = False):
-    """feats[l] [B,128,H,W]; rois [P,cap,4] -> pooled [P,cap,R*R,128] (bin-major, channel innermost)
+              problems_per_image: int, resolution: int, out: Optional[Tensor] = None, want_levels: bool = False,
+              tiled: bool = False):
+    """feats[l] [B,128,H,W]; rois [P,cap,4] -> pooled [P,cap,R*R,128] (bin-major, channel innermost), or with
+    tiled=True (R == 8) the relation-head operand layout [P,U,256,128,32] (see tile_pooled)
     (d2 poolers.py:190-250)."""
     feats = [nhwc(f, "feat") for f in feats]
     B = feats[0].shape[0]
@@ -190,12 +208,13 @@ def roi_align(feats: Sequence[Tensor], strides: Sequence[int], rois: Tensor, roi
         raise _lib.FodError("roi_align: rois.shape[0] must be batch * problems_per_image")
     dev = rois.device
     if out is None:
-        out = torch.empty((P, cap, resolution * resolution, 128), dtype=torch.float32, device=dev)
+        shape = (P, (cap + 127) // 128, 256, 128, 32) if tiled else (P, cap, resolution * resolution, 128)
+        out = torch.empty(shape, dtype=torch.float32, device=dev)
     lvl = torch.zeros((P, cap), dtype=torch.int32, device=dev) if want_levels else None
     lv = _levels(feats, strides)
     _lib.check(_lib.lib().fod_roi_align(_ptr_array(feats), lv, len(feats), B, int(problems_per_image), _ptr(rois),
-                                        _ptr(roi_count), cap, int(resolution), _ptr(out), _ptr(lvl), _stream()),
-               "fod_roi_align")
+                                        _ptr(roi_count), cap, int(resolution), int(bool(tiled)), _ptr(out), _ptr(lvl),
+                                        _stream()), "fod_roi_align")
     return (out, lvl) if want_levels else out
 
 
@@ -214,11 +233,16 @@ def relation_head(pooled: Tensor, w_fold: Tensor, bias_cls: Tensor, w_out: Tenso
                   want_raw: bool = False):
     """-> (det_boxes [P,cap,4] unclipped, det_scores [P,cap][, logits [P,cap,2], deltas [P,cap,4]])
     (fsod_roi_heads.py:482-520, custom_fast_rcnn.py:160-170, d2 box_regression.py:77-115).
-    w_fold: the folded matrix [128,8192] or, preferably, its pre-split planes [2,128,8192] (split_tf32)."""
+    pooled: the tiled layout [P,U,256,128,32] written by roi_align(tiled=True) (a [P,cap,64,128] tensor is
+    re-tiled with torch ops first - tests only).  w_fold: the folded matrix [128,8192] or, preferably, its pre-split planes [2,128,8192] (split_tf32)."""
     P, cap = rois.shape[0], rois.shape[1]
     dev = rois.device
     if w_fold.dim() == 2:
         w_fold = split_tf32(w_fold)
+    if pooled.dim() == 4:
+        pooled = tile_pooled(pooled)
+    if tuple(pooled.shape) != (P, (cap + 127) // 128, 256, 128, 32):
+        raise _lib.FodError("relation_head: pooled must be [P,U,256,128,32]")
     for t, n in ((pooled, "pooled"), (w_fold, "w_fold"), (bias_cls, "bias_cls"), (w_out, "w_out"), (b_out, "b_out"),
                  (rois, "rois")):
         _chk(t, torch.float32, n)

@@ -142,12 +142,15 @@ int fod_nms_proposals(const float* boxes, const float* scores, const int32_t* co
  *   feat[l]  : [B][H_l][W_l][128]
  *   rois     : [P][roi_cap][4] xyxy in image pixels, roi_count [P] (NULL = all roi_cap valid)
  *   problems_per_image : C (ROI row p reads image p / C)
- *   pooled   : [P][roi_cap][R*R][128] (bin-major, channel innermost); rows >= count untouched
+ *   pooled   : tiled == 0: [P][roi_cap][R*R][128] (bin-major, channel innermost); rows >= count untouched.
+ *              tiled == 1 (R == 8; the input format of fod_relation_head): [P][U][256][128][32] with
+ *              U = ceil(roi_cap/128): unit u = ROI rows 128u..128u+127, k-chunk kc = bin*4 + channel/32, so every
+ *              [128 rows x 32 k] operand tile is 16 KB of contiguous memory (one linear TMA box).
  *   out_level: [P][roi_cap] int32 assigned level (may be NULL)
  */
 int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
                   int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap, int resolution,
-                  float* pooled, int32_t* out_level, fod_stream_t stream);
+                  int tiled, float* pooled, int32_t* out_level, fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * R2+R3  relation head on pooled ROI features, softmax, box decoding.
@@ -158,7 +161,7 @@ int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_l
  * The three 1x1 convs and fc1 have no non-linearity between them and are folded
  * on the host into one [128][8192] matrix plus a per-class bias.
  * Tensor cores (tcgen05, 3xTF32 operand splitting = fp32 accuracy), TMA-fed.
- *   pooled   : [P][roi_cap][64][128]
+ *   pooled   : [P][U][256][128][32], the tiled layout of fod_roi_align (tiled = 1)
  *   w_fold_split : [2][128][8192]   k index = bin*128 + channel; plane 0 = tf32-rounded folded weights, plane 1 =
  *                  exact remainder, as written by fod_split_tf32 (once per weight load)
  *   bias_cls : [C][128]      per-class folded bias (support term + fc1 bias)

@@ -259,6 +259,12 @@ def test_roi_align_respects_counts_and_classes():
         ref = O.roi_pool([f[img:img + 1] for f in fl], [bx[p, :n]], 8) if n else torch.zeros((0, 128, 8, 8))
         got = pooled[p, :n].reshape(n, 8, 8, 128).permute(0, 3, 1, 2)
         assert_close(got, ref, what=f"problem {p}")
+    # the tiled operand layout of the relation head holds the same rows
+    tiled = ops.roi_align([f.to(DEV) for f in fl], (8, 16, 32), bx.to(DEV), counts.to(DEV), C, 8, tiled=True)
+    back = ops.untile_pooled(tiled, cap).cpu()
+    for p in range(2 * C):
+        n = int(counts[p])
+        assert torch.equal(back[p, :n], pooled[p, :n])
 
 
 def test_relation_head_matches_reference_and_oracle():

@@ -33,8 +33,8 @@ def timeit(fn, iters=10, warm=3):
     return e0.elapsed_time(e1) / iters
 
 
-pooled = ops.roi_align(feats, (8, 16, 32), rois, counts, C, 8)
-t_roi = timeit(lambda: ops.roi_align(feats, (8, 16, 32), rois, counts, C, 8))
+pooled = ops.roi_align(feats, (8, 16, 32), rois, counts, C, 8, tiled=True)
+t_roi = timeit(lambda: ops.roi_align(feats, (8, 16, 32), rois, counts, C, 8, tiled=True))
 t_rel = timeit(lambda: ops.relation_head(pooled, w_fold, bias, w_out, b_out, rois, counts, C, (10., 10., 5., 5.)))
 flops = 2.0 * P * n * 8192 * 128
 print(f"B={B} C={C}: roi_align {t_roi*1e3:.1f} us   relation_head {t_rel*1e3:.1f} us ({flops/t_rel/1e9:.1f} fp32-equivalent TFLOP/s, "
