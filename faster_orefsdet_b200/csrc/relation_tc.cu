@@ -20,6 +20,9 @@ namespace fod {
 using namespace tc;
 
 namespace rtc {
+#ifndef FOD_EXP
+#define FOD_EXP 0
+#endif
 
 constexpr int kK = 64 * kC;          // 8192
 constexpr int kChunk = 32;           // K per pipeline stage
@@ -48,11 +51,12 @@ constexpr uint32_t kOffPref = kOffWout + (6 * kC + 8) * 4;  // int32[P + 1]: exc
 constexpr uint32_t kOffBars = kOffPref + (kMaxProblems + 1) * 4;
 constexpr uint32_t kNumBars = 5 * kStages + 2 * kAccStages;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr uint32_t kOffFlag = kOffTmemPtr + 8;   // chunks released to the MMA thread by its barrier watcher
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
 constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;
 
 constexpr int kConvWarps = 8;
-constexpr int kWarpTma = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpEpi0 = 4, kWarpConv0 = 8;
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpTmaB = 3, kWarpEpi0 = 4, kWarpConv0 = 8;
 constexpr int kThreads = (kWarpConv0 + kConvWarps) * 32;  // 512
 
 constexpr uint32_t kTmemCols = 512;
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
       mbar_init(acc_full(s), 1);
       mbar_init(acc_empty(s), 8);  // 4 epilogue warps x 2 CTAs
     }
+    *reinterpret_cast<volatile uint32_t*>(smem + kOffFlag) = 0;
     fence_barrier_init();
   }
   if (warp == kWarpAlloc) {
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
   for (int i = tid; i < 6 * kC + 6; i += kThreads)
     reinterpret_cast<float*>(smem + kOffWout)[i] = i < 6 * kC ? P.w_out[i] : P.b_out[i - 6 * kC];
   int* pref = reinterpret_cast<int*>(smem + kOffPref);
-  if (warp == 3) {  // exclusive prefix sum of the unit counts, one warp, 32 problems per step
+  if (warp == kWarpTmaB) {  // exclusive prefix sum of the unit counts, one warp, 32 problems per step
     int carry = 0;
     for (int base = 0; base < P.num_problems; base += 32) {
       const int p = base + lane;
@@ -177,8 +182,8 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
   auto in_range = [&](int i) { return slot_of(i, 0) < total_units; };
 
   if (warp == kWarpTma) {
+    // ------------------------------------------------------------------ TMA producer, A operand (pooled rows)
     if (lane == 0) {
-      const uint32_t b_full_leader = map_to_cta(b_full(0), 0);
       uint32_t g = 0;
       for (int i = 0; in_range(i); ++i) {
         const Slot me = decode_unit(P, pref, slot_of(i, rank));
@@ -187,10 +192,29 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
           const int s = g % kStages;
           const uint32_t ph = (g / kStages) & 1;
           mbar_wait(a_empty(s), ph ^ 1);
+#if FOD_EXP == 1
+          if (g >= (uint32_t)kStages) { mbar_arrive(a_full(s)); continue; }
+#endif
           mbar_arrive_expect_tx(a_full(s), kABytes);
           tma_load_2d(sbase + kOffA + s * kABytes, &P.a_map, a_full(s), 0, (tile0 + kc) * 128);
-          // weights: each CTA loads its 64 rows; both CTAs' bytes complete on the LEADER's barrier
+        }
+      }
+    }
+  } else if (warp == kWarpTmaB) {
+    // ------------------------------------------------------------------ TMA producer, B operand (weights); its own
+    // thread so that a late st_free never delays the A stream and vice versa
+    if (lane == 0) {
+      const uint32_t b_full_leader = map_to_cta(b_full(0), 0);
+      uint32_t g = 0;
+      for (int i = 0; in_range(i); ++i) {
+        for (int kc = 0; kc < kNumChunks; ++kc, ++g) {
+          const int s = g % kStages;
+          const uint32_t ph = (g / kStages) & 1;
+          // each CTA loads its 64 rows; both CTAs' bytes complete on the LEADER's barrier
           mbar_wait(st_free(s), ph ^ 1);
+#if FOD_EXP == 2
+          if (g >= (uint32_t)kStages) { if (rank == 0) mbar_arrive(b_full(s)); continue; }
+#endif
           if (rank == 0) mbar_arrive_expect_tx(b_full(s), 2 * kBBytes);
           tma_load_2d_2sm(sbase + kOffB + s * kBBytes, &P.whi_map, b_full_leader + 8u * s, kc * kChunk, rank * kBHalfRows);
           tma_load_2d_2sm(sbase + kOffB + s * kBBytes + kBPlaneBytes, &P.wlo_map, b_full_leader + 8u * s, kc * kChunk,
@@ -201,35 +225,68 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
   } else if (warp == kWarpMma) {
     if (rank == 0 && lane == 0) {
       const uint32_t idesc = idesc_tf32(256, 128);
-      uint32_t g = 0, gp = 0;
-      for (int i = 0; in_range(i); ++i) {
-        for (int part = 0; part < kParts; ++part, ++gp) {
-          const int as_ = gp % kAccStages;
-          const uint32_t aph = (gp / kAccStages) & 1;
-          mbar_wait(acc_empty(as_), aph ^ 1);
-          tc_fence_after();
-          const uint32_t d = tmem_base + kColAcc + as_ * 128;
-          for (int kc = part * kChunksPerPart; kc < (part + 1) * kChunksPerPart; ++kc, ++g) {
-            const int s = g % kStages;
-            const uint32_t ph = (g / kStages) & 1;
-            mbar_wait(b_full(s), ph);   // weight chunks of both CTAs have landed
-            mbar_wait(ready(s), ph);    // A chunk of both CTAs is in tensor memory
-            tc_fence_after();
-            const uint32_t a0 = tmem_base + kColA + s * 64;
-            const uint64_t bhi = smem_desc_k_sw128(sbase + kOffB + s * kBBytes);
-            const uint64_t blo = smem_desc_k_sw128(sbase + kOffB + s * kBBytes + kBPlaneBytes);
+      // The issuing thread is throttled to the tensor pipe's rate (its queue is only an MMA or two deep), and an
+      // mbarrier wait costs a few hundred cycles even when the phase has long completed: waiting here would starve
+      // the pipe between chunks.  A helper thread (warp kWarpAlloc) does all the waiting and publishes the number of
+      // chunks whose operands are in place through one shared-memory word; this thread only polls that word.
+      int n_iter = 0;
+      for (int i = 0; in_range(i); ++i) ++n_iter;
+      const uint32_t total = (uint32_t)n_iter * kNumChunks;
+      const uint32_t flag = sbase + kOffFlag;
+      uint32_t upto = 0;
+      for (uint32_t g = 0; g < total; ++g) {
+#if FOD_EXP == 3
+        long long t0 = clock64();
+#endif
+        while (upto <= g) asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(upto) : "r"(flag) : "memory");
+        tc_fence_after();
+#if FOD_EXP == 3
+        long long t2 = clock64();
+#endif
+        const int s = g % kStages;
+        const uint32_t gp = g / kChunksPerPart;
+        const int as_ = gp % kAccStages;
+        const bool first = (g % kChunksPerPart) == 0, last = (g % kChunksPerPart) == kChunksPerPart - 1;
+        const uint32_t d = tmem_base + kColAcc + as_ * 128;
+        const uint32_t a0 = tmem_base + kColA + s * 64;
+        const uint64_t bhi = smem_desc_k_sw128(sbase + kOffB + s * kBBytes);
+        const uint64_t blo = smem_desc_k_sw128(sbase + kOffB + s * kBBytes + kBPlaneBytes);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t ah = a0 + ks * 8, al = ah + 32;
-              const uint64_t boff = (uint64_t)((ks * 32) >> 4);
-              mma_tf32_ts<2>(d, ah, bhi + boff, idesc, (kc != part * kChunksPerPart || ks) ? 1u : 0u);
-              mma_tf32_ts<2>(d, al, bhi + boff, idesc, 1u);
-              mma_tf32_ts<2>(d, ah, blo + boff, idesc, 1u);
-            }
-            mma_commit_pair(st_free(s), 3);
-          }
-          mma_commit_pair(acc_full(as_), 3);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t ah = a0 + ks * 8, al = ah + 32;
+          const uint64_t boff = (uint64_t)((ks * 32) >> 4);
+          mma_tf32_ts<2>(d, ah, bhi + boff, idesc, (!first || ks) ? 1u : 0u);
+          mma_tf32_ts<2>(d, al, bhi + boff, idesc, 1u);
+          mma_tf32_ts<2>(d, ah, blo + boff, idesc, 1u);
         }
+        mma_commit_pair(st_free(s), 3);
+        if (last) mma_commit_pair(acc_full(as_), 3);
+#if FOD_EXP == 3
+        if (pair == 0 && g >= 128 && g < 128 + 32 && P.deltas) {
+          long long t3 = clock64();
+          long long* dbg = reinterpret_cast<long long*>(P.deltas + 256 * 4) + (g - 128) * 4;  // unused rows 256..319
+          dbg[0] = t0; dbg[1] = t2 - t0; dbg[2] = upto - g; dbg[3] = t3 - t2;
+        }
+#endif
+      }
+    }
+  } else if (warp == kWarpAlloc) {
+    // ------------------------------------------------------------------ barrier watcher of the MMA thread (leader)
+    if (rank == 0 && lane == 0) {
+      int n_iter = 0;
+      for (int i = 0; in_range(i); ++i) ++n_iter;
+      const uint32_t total = (uint32_t)n_iter * kNumChunks;
+      const uint32_t flag = sbase + kOffFlag;
+      for (uint32_t g = 0; g < total; ++g) {
+        const int s = g % kStages;
+        const uint32_t ph = (g / kStages) & 1;
+        mbar_wait(b_full(s), ph);   // weight chunks of both CTAs have landed
+        mbar_wait(ready(s), ph);    // A chunk of both CTAs is in tensor memory
+        if (g % kChunksPerPart == 0) {  // first chunk of a partial sum: its accumulator must have been drained
+          const uint32_t gp = g / kChunksPerPart;
+          mbar_wait(acc_empty(gp % kAccStages), ((gp / kAccStages) & 1) ^ 1);
+        }
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(flag), "r"(g + 1) : "memory");
       }
     }
   } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 4) {

@@ -92,11 +92,12 @@ __global__ void __launch_bounds__(128, 1) gemm_probe(const float* __restrict__ X
   if (G == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
 
+  long long t_start = clock64();
   if (rank == 0 && tid == 0) {
     const uint32_t idesc = idesc_tf32(128 * G, NT);
     const uint32_t d = tmem_base + 128;
     uint32_t acc = 0;
-    for (int rep = 0; rep < repeat; ++rep)  // repeat > 1: accumulate the same product again (accumulator rounding probe)
+    for (int rep = 0; rep < (repeat < 0 ? -repeat : repeat); ++rep)  // repeat > 1: accumulate the same product again (accumulator rounding probe)
     for (int kc = 0; kc < 2; ++kc)
       for (int ks = 0; ks < 4; ++ks) {
         uint64_t bh = smem_desc_k_sw128(smem_u32(b_hi) + kc * NB * 128 + ks * 32);
@@ -122,8 +123,26 @@ __global__ void __launch_bounds__(128, 1) gemm_probe(const float* __restrict__ X
       }
     if (G == 2) mma_commit_pair(smem_u32(&bar), 3); else mma_commit(smem_u32(&bar));
   }
+  if (repeat < 0 && warp > 0) {  // contention probe: keep storing to unused TMEM columns while the MMAs run
+    uint32_t z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = j;
+    long long t0 = clock64();
+    const int nst = 2000;
+    for (int it = 0; it < nst; ++it) {
+      tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + 256 - 64 + (it & 3) * 16, z);
+      tmem_wait_st();
+    }
+    if (lane == 0 && rank == 0)
+      printf("  warp %d: %d x (tcgen05.st.x16 + wait::st) in %lld cycles = %.1f cycles each\n", warp, nst, clock64() - t0,
+             double(clock64() - t0) / nst);
+  }
   mbar_wait(smem_u32(&bar), 0);
   tc_fence_after();
+  if (repeat < 0) repeat = -repeat;
+  if (rank == 0 && tid == 0 && repeat > 1)
+    printf("  G=%d %s prod=%d: %d MMAs (M=%d N=%d K=8) in %lld cycles = %.1f cycles/MMA\n", G, TS ? "TS" : "SS", NPROD,
+           repeat * 8 * NPROD, 128 * G, NT, clock64() - t_start, double(clock64() - t_start) / (repeat * 8 * NPROD));
   float* orow = out + (size_t)(rank * 128 + tid) * NT;
 #pragma unroll
   for (int c0 = 0; c0 < NT; c0 += 32) {
@@ -174,7 +193,7 @@ static int run_gemm(const char* name, int repeat = 1) {
     for (int n = 0; n < NT; ++n) {
       double r = 0;
       for (int k = 0; k < K; ++k) r += (double)X[(size_t)m * K + k] * W[(size_t)n * K + k];
-      r *= repeat;
+      r *= abs(repeat);
       maxerr = fmax(maxerr, fabs(r - out[(size_t)m * NT + n]));
       maxref = fmax(maxref, fabs(r));
     }
@@ -301,6 +320,20 @@ int main(int argc, char** argv) {
   if (!strcmp(mode, "g2ss")) { run_gemm<2, false, 1>(mode); return run_gemm<2, false, 3>(mode); }
   if (!strcmp(mode, "acc")) {  // accumulator rounding: error growth with the number of accumulations
     for (int r : {1, 16, 128, 1024}) run_gemm<1, true, 3>(mode, r);
+    return 0;
+  }
+  if (!strcmp(mode, "contend")) {  // MMA chain while other warps store to tensor memory
+    run_gemm<1, true, 3>(mode, -512);
+    run_gemm<2, true, 3>(mode, -512);
+    run_gemm<2, true, 3>(mode, -16);
+    return 0;
+  }
+  if (!strcmp(mode, "rate")) {  // MMA issue rate
+    run_gemm<1, true, 3>(mode, 512);
+    run_gemm<1, false, 3>(mode, 512);
+    run_gemm<2, true, 3>(mode, 512);
+    run_gemm<2, false, 3>(mode, 512);
+    run_gemm<2, true, 1>(mode, 512);
     return 0;
   }
   if (!strcmp(mode, "tma")) return run_tma();
