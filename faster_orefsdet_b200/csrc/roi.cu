@@ -30,21 +30,98 @@ __device__ __forceinline__ int assign_level(float4 b, int min_level, int num_lev
   return (int)v - min_level;   // NaN area (negative) -> (int)NaN = 0 on CUDA; torch gives INT64_MIN: never valid input
 }
 
-__global__ void __launch_bounds__(256)
+// One bilinear sample coordinate along one axis (torchvision roi_align_common.h pre_calc_for_bilinear_interpolate):
+// the two neighbouring rows / columns and their weights; w_low = w_high = 0 for a sample outside [-1, size].
+struct AxisSample {
+  int lo, hi;
+  float w_hi, w_lo;  // weight of index `hi` (l) and of index `lo` (h = 1 - l)
+};
+
+__device__ __forceinline__ AxisSample axis_sample(float start, float bin, int p, int i, int grid, int size) {
+  // coordinate = start + p*bin + (i+.5)*bin/grid     (left-to-right like the C++ expression)
+  float v = __fadd_rn(__fadd_rn(start, __fmul_rn((float)p, bin)),
+                      __fdiv_rn(__fmul_rn(__fadd_rn((float)i, 0.5f), bin), (float)grid));
+  AxisSample s;
+  if (v < -1.0f || v > (float)size) {
+    s.lo = s.hi = 0;
+    s.w_hi = s.w_lo = 0.f;
+    return s;
+  }
+  if (v <= 0.f) v = 0.f;
+  int lo = (int)v, hi;
+  if (lo >= size - 1) {
+    hi = lo = size - 1;
+    v = (float)lo;
+  } else {
+    hi = lo + 1;
+  }
+  s.lo = lo;
+  s.hi = hi;
+  s.w_hi = __fsub_rn(v, (float)lo);
+  s.w_lo = __fsub_rn(1.f, s.w_hi);
+  return s;
+}
+
+constexpr int kMaxGrid = 8;             // sampling grid per bin handled by the shared-memory tables
+constexpr int kMaxTaps = 2 * kMaxGrid;  // distinct rows / columns one bin can touch
+
+// Per ROI and axis: for every bin the list of DISTINCT map rows (columns) its samples touch, with the summed
+// interpolation weight of each.  Consecutive samples of a bin share a row (the upper neighbour of one is the lower
+// neighbour of the next), so a bin with a g x g grid reads (g+1)^2 pixels instead of 4 g^2 taps.
+struct AxisTaps {
+  int idx[8][kMaxTaps];
+  float w[8][kMaxTaps];
+  int n[8];
+};
+
+__device__ __forceinline__ void build_axis_taps(AxisTaps& t, int bin, float start, float bin_size, int grid, int size) {
+  int n = 0;
+  for (int i = 0; i < grid; ++i) {
+    const AxisSample s = axis_sample(start, bin_size, bin, i, grid, size);
+    if (s.w_lo == 0.f && s.w_hi == 0.f) continue;  // outside the map: contributes nothing
+    // lower neighbour
+    if (n > 0 && t.idx[bin][n - 1] == s.lo) {
+      t.w[bin][n - 1] += s.w_lo;
+    } else if (n > 1 && t.idx[bin][n - 2] == s.lo) {
+      t.w[bin][n - 2] += s.w_lo;
+    } else {
+      t.idx[bin][n] = s.lo;
+      t.w[bin][n] = s.w_lo;
+      ++n;
+    }
+    // upper neighbour (lo == hi at the last row: both weights go to the same pixel, w_hi is 0 there)
+    if (t.idx[bin][n - 1] == s.hi) {
+      t.w[bin][n - 1] += s.w_hi;
+    } else {
+      t.idx[bin][n] = s.hi;
+      t.w[bin][n] = s.w_hi;
+      ++n;
+    }
+  }
+  t.n[bin] = n;
+}
+
+// One CTA per ROI; warp = (bin row, half of the bin columns), lane = 4 channels: every tap is one fully coalesced
+// 512-byte row of the NHWC map, 4 accumulators per lane keep the register count low enough for full occupancy.
+template <int R>
+__global__ void __launch_bounds__(R * 64)
 roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* __restrict__ roi_count,
                  float* __restrict__ pooled, int32_t* __restrict__ out_level) {
+  __shared__ AxisTaps xt, yt;
   const int r = blockIdx.x, p = blockIdx.y;
   const int cnt = roi_count ? min(roi_count[p], prm.roi_cap) : prm.roi_cap;
   if (r >= cnt) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float4 box = *reinterpret_cast<const float4*>(rois + ((size_t)p * prm.roi_cap + r) * 4);
   int min_level = 31 - __clz(prm.stride[0]);
   const int lvl = assign_level(box, min_level, prm.num_levels);
   if (out_level && threadIdx.x == 0) out_level[(size_t)p * prm.roi_cap + r] = lvl;
-  const int H = prm.H[lvl], W = prm.W[lvl];
-  const float scale = 1.0f / (float)prm.stride[lvl];
-  const float* f = prm.feat[lvl] + (size_t)(p / prm.C) * H * W * kC + lane * 4;
-  const int R = prm.R;
+  int H = prm.H[0], W = prm.W[0], stride = prm.stride[0];
+  const float* fbase = prm.feat[0];
+  if (lvl == 1) { H = prm.H[1]; W = prm.W[1]; stride = prm.stride[1]; fbase = prm.feat[1]; }
+  if (lvl == 2) { H = prm.H[2]; W = prm.W[2]; stride = prm.stride[2]; fbase = prm.feat[2]; }
+  const float scale = 1.0f / (float)stride;
+  const float* f = fbase + (size_t)(p / prm.C) * H * W * kC + lane * 4;
   const float start_w = __fsub_rn(__fmul_rn(box.x, scale), 0.5f);
   const float start_h = __fsub_rn(__fmul_rn(box.y, scale), 0.5f);
   const float end_w = __fsub_rn(__fmul_rn(box.z, scale), 0.5f);
@@ -53,7 +130,7 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
   const float bin_h = __fdiv_rn(roi_h, (float)R), bin_w = __fdiv_rn(roi_w, (float)R);
   const int grid_h = (int)ceilf(__fdiv_rn(roi_h, (float)R));
   const int grid_w = (int)ceilf(__fdiv_rn(roi_w, (float)R));
-  const float count = fmaxf((float)(grid_h * grid_w), 1.0f);
+  const float inv_count = 1.0f / fmaxf((float)(grid_h * grid_w), 1.0f);
   // Output layout.  tiled == 0: [P][roi_cap][R*R][128] (row-major ROI rows).  tiled == 1 (R == 8, consumed by
   // fod_relation_head): [P][units][256 k-chunks][128 rows][32], units = ceil(roi_cap / 128): the 16 KB A tile of
   // one 32-wide K chunk of 128 ROI rows is contiguous, so one TMA box fetches it as a linear stream.
@@ -67,48 +144,60 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
     out = pooled + ((size_t)p * prm.roi_cap + r) * R * R * kC + lane * 4;
     bin_stride = kC;
   }
-  for (int bin = warp; bin < R * R; bin += nwarps) {
-    const int ph = bin / R, pw = bin - ph * R;
-    float4 acc = make_float4(0, 0, 0, 0);
-    for (int iy = 0; iy < grid_h; ++iy) {
-      // y = start_h + ph*bin_h + (iy+.5)*bin_h/grid_h     (left-to-right like the C++ expression)
-      float yy = __fadd_rn(__fadd_rn(start_h, __fmul_rn((float)ph, bin_h)),
-                           __fdiv_rn(__fmul_rn(__fadd_rn((float)iy, 0.5f), bin_h), (float)grid_h));
-      for (int ix = 0; ix < grid_w; ++ix) {
-        float xx = __fadd_rn(__fadd_rn(start_w, __fmul_rn((float)pw, bin_w)),
-                             __fdiv_rn(__fmul_rn(__fadd_rn((float)ix, 0.5f), bin_w), (float)grid_w));
-        float y = yy, x = xx;
-        if (y < -1.0f || y > (float)H || x < -1.0f || x > (float)W) continue;
-        if (y <= 0.f) y = 0.f;
-        if (x <= 0.f) x = 0.f;
-        int y_low = (int)y, x_low = (int)x, y_high, x_high;
-        if (y_low >= H - 1) {
-          y_high = y_low = H - 1;
-          y = (float)y_low;
-        } else {
-          y_high = y_low + 1;
+  const bool tables = grid_h <= kMaxGrid && grid_w <= kMaxGrid;
+  if (tables) {
+    if (threadIdx.x < R) build_axis_taps(xt, threadIdx.x, start_w, bin_w, grid_w, W);
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + R) build_axis_taps(yt, threadIdx.x - 32, start_h, bin_h, grid_h, H);
+  }
+  __syncthreads();
+  const int ph = warp >> 1, pw0 = (warp & 1) * (R / 2);
+  float4 acc[R / 2];
+#pragma unroll
+  for (int j = 0; j < R / 2; ++j) acc[j] = make_float4(0, 0, 0, 0);
+  if (tables) {
+    const int ny = yt.n[ph];
+    for (int kr = 0; kr < ny; ++kr) {
+      const float wy = yt.w[ph][kr];
+      const float* rowp = f + (size_t)yt.idx[ph][kr] * W * kC;
+#pragma unroll
+      for (int j = 0; j < R / 2; ++j) {
+        const int nx = xt.n[pw0 + j];
+#pragma unroll 3
+        for (int kx = 0; kx < nx; ++kx) {
+          const float4 v = ldg4(rowp + (size_t)xt.idx[pw0 + j][kx] * kC);
+          const float w = wy * xt.w[pw0 + j][kx];
+          acc[j].x = fmaf(w, v.x, acc[j].x);
+          acc[j].y = fmaf(w, v.y, acc[j].y);
+          acc[j].z = fmaf(w, v.z, acc[j].z);
+          acc[j].w = fmaf(w, v.w, acc[j].w);
         }
-        if (x_low >= W - 1) {
-          x_high = x_low = W - 1;
-          x = (float)x_low;
-        } else {
-          x_high = x_low + 1;
-        }
-        const float ly = __fsub_rn(y, (float)y_low), lx = __fsub_rn(x, (float)x_low);
-        const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
-        const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
-        const float4 v1 = ldg4(f + ((size_t)y_low * W + x_low) * kC);
-        const float4 v2 = ldg4(f + ((size_t)y_low * W + x_high) * kC);
-        const float4 v3 = ldg4(f + ((size_t)y_high * W + x_low) * kC);
-        const float4 v4 = ldg4(f + ((size_t)y_high * W + x_high) * kC);
-        acc.x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-        acc.y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
-        acc.z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
-        acc.w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
       }
     }
-    acc.x /= count; acc.y /= count; acc.z /= count; acc.w /= count;
-    *reinterpret_cast<float4*>(out + (size_t)bin * bin_stride) = acc;
+  } else {  // sampling grid beyond the tables (box much larger than the pyramid level expects): sample by sample
+    for (int iy = 0; iy < grid_h; ++iy) {
+      const AxisSample ys = axis_sample(start_h, bin_h, ph, iy, grid_h, H);
+      if (ys.w_lo == 0.f && ys.w_hi == 0.f) continue;
+      const float* row_lo = f + (size_t)ys.lo * W * kC;
+      const float* row_hi = f + (size_t)ys.hi * W * kC;
+#pragma unroll
+      for (int j = 0; j < R / 2; ++j) {
+        for (int ix = 0; ix < grid_w; ++ix) {
+          const AxisSample xs = axis_sample(start_w, bin_w, pw0 + j, ix, grid_w, W);
+          const float4 v1 = ldg4(row_lo + (size_t)xs.lo * kC), v2 = ldg4(row_lo + (size_t)xs.hi * kC);
+          const float4 v3 = ldg4(row_hi + (size_t)xs.lo * kC), v4 = ldg4(row_hi + (size_t)xs.hi * kC);
+          const float w1 = ys.w_lo * xs.w_lo, w2 = ys.w_lo * xs.w_hi, w3 = ys.w_hi * xs.w_lo, w4 = ys.w_hi * xs.w_hi;
+          acc[j].x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+          acc[j].y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+          acc[j].z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+          acc[j].w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < R / 2; ++j) {
+    float4 o = make_float4(acc[j].x * inv_count, acc[j].y * inv_count, acc[j].z * inv_count, acc[j].w * inv_count);
+    *reinterpret_cast<float4*>(out + (size_t)(ph * R + pw0 + j) * bin_stride) = o;
   }
 }
 
@@ -121,8 +210,8 @@ extern "C" int fod_roi_align(const float* const* feat, const fod_level_t* levels
                              int resolution, int tiled, float* pooled, int32_t* out_level, fod_stream_t stream) {
   FOD_REQUIRE(feat && levels && rois && pooled, "fod_roi_align: null pointer");
   FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_roi_align: num_levels %d out of range", num_levels);
-  FOD_REQUIRE(batch >= 0 && problems_per_image > 0 && roi_cap > 0 && resolution > 0 && resolution <= 16,
-              "fod_roi_align: bad sizes");
+  FOD_REQUIRE(batch >= 0 && problems_per_image > 0 && roi_cap > 0, "fod_roi_align: bad sizes");
+  FOD_REQUIRE(resolution == 8 || resolution == 4, "fod_roi_align: pooler resolution must be 8 or 4 (POOLER_RESOLUTION / _2)");
   long P = (long)batch * problems_per_image;
   if (P == 0) return FOD_OK;
   FOD_REQUIRE(P <= 65535, "fod_roi_align: batch*classes %ld > 65535", P);
@@ -144,7 +233,10 @@ extern "C" int fod_roi_align(const float* const* feat, const fod_level_t* levels
   FOD_REQUIRE(!tiled || resolution == 8, "fod_roi_align: the tiled layout needs resolution 8");
   prm.tiled = tiled ? 1 : 0;
   dim3 grid(roi_cap, (unsigned)P);
-  roi_align_kernel<<<grid, 256, 0, as_stream(stream)>>>(prm, rois, roi_count, pooled, out_level);
+  if (resolution == 8)
+    roi_align_kernel<8><<<grid, 512, 0, as_stream(stream)>>>(prm, rois, roi_count, pooled, out_level);
+  else
+    roi_align_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(prm, rois, roi_count, pooled, out_level);
   FOD_CUDA_LAUNCH_CHECK("fod_roi_align");
   return FOD_OK;
 }
