@@ -60,7 +60,16 @@ __device__ __forceinline__ bool iou_exceeds(const float4 a, float area_a, const 
   float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
   float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
   float inter = __fmul_rn(w, h);
-  float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  // Same decision as the exact quotient below, without the division in the clear cases: for uni > 0 and thr > 0
+  // the rounded quotient is >= thr iff inter/uni is, up to half an ulp; a 1e-6 relative margin around thr*uni is
+  // hundreds of ulps wide, everything inside it takes the exact path.  (Most pairs do not overlap at all.)
+  if (uni > 0.f && thr_f > 0.f) {
+    const float t = __fmul_rn(thr_f, uni);
+    if (inter > __fmul_rn(t, 1.000001f)) return true;
+    if (inter < __fmul_rn(t, 0.999999f)) return false;
+  }
+  float ovr = __fdiv_rn(inter, uni);
   return ovr >= thr_f;  // false for NaN, like `ovr > thr`
 }
 
