@@ -161,6 +161,8 @@ class KernelTimer:
         self.launches = 0
         self.enabled = False
 
+    kernels_per_call = {"correlate_levels": 2}   # tap packing + the persistent correlation kernel
+
     def wrap(self, ops_mod, names):
         for n in names:
             fn = getattr(ops_mod, n)
@@ -173,7 +175,7 @@ class KernelTimer:
                 r = __fn(*a, **k)
                 e.record()
                 self.records.setdefault(__n, []).append((s, e))
-                self.launches += 1
+                self.launches += self.kernels_per_call.get(__n, 1)
                 return r
             setattr(ops_mod, n, timed)
 
@@ -290,8 +292,8 @@ def run_gpu_arm(args):
         "correlate_levels": 1024.0 * M_PIXELS * B,          # one persistent launch over the three levels
         "decode_topk": (20.0 * M_PIXELS + 28.0 * 2400) * B,
         "nms_proposals": (20.0 * 2400 + 8.0 * 256) * B,
-        "roi_align": (512.0 * M_PIXELS + 16.0 * 256 + 256 * 32768.0) * B,   # + materialised pooled rows (v1)
-        "relation_head": (256 * 32768.0 + 40.0 * 256) * B + 4.36e6,
+        "roi_align": (512.0 * M_PIXELS + 16.0 * 256 + 256 * 32768.0) * B,   # + pooled rows, materialised while R1/R2 are two kernels
+        "relation_head": (256 * 32768.0 + 40.0 * 256) * B + 2 * 4.19e6,    # pooled rows + tf32 hi/lo weight planes
         "final_detect": 20.0 * 256 * B,
     }
     kernels = {}
@@ -300,6 +302,9 @@ def run_gpu_arm(args):
         gbs = alg[n] / (per_launch_ms * 1e-3) / 1e9
         kernels[n] = {"ms_per_step": tot_ms / args.steps, "launches_per_step": cnt / args.steps,
                       "achieved_gbs": gbs, "frac": gbs / peak}
+    # DRAM traffic per launch of the same kernels from the committed `ncu --set full` captures
+    # (dram__bytes_read.sum + dram__bytes_write.sum, batch 64, 1-way; profiles/r1_ncu_v2_summary.md)
+    ncu_traffic = {"correlate_levels": 504.9e6, "relation_head": 550.6e6, "roi_align": 686.9e6} if B == BATCH else {}
     dom = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
     head_ms = sum(k["ms_per_step"] for k in kernels.values())
     head_alg_bytes = 13.2e6 * B
@@ -323,7 +328,8 @@ def run_gpu_arm(args):
                 "d2h_bytes_per_step": d2h_bytes, "api": "model(batched_inputs) with pinned host uint8 images; Instances.to('cpu')"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src},
+                     "frac": kernels[dom]["frac"], "traffic": ncu_traffic.get(dom), "algorithmic_bytes": alg[dom],
+                     "peak_source": peak_src},
         "head": {"ms_per_step": head_ms, "images_per_s": B / (head_ms * 1e-3),
                  "achieved_gbs": head_alg_bytes / (head_ms * 1e-3) / 1e9, "frac": head_alg_bytes / (head_ms * 1e-3) / 1e9 / peak,
                  "share_of_step": head_ms / (ms / args.steps), "kernels": kernels},
