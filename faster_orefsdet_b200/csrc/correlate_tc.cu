@@ -59,6 +59,7 @@ constexpr uint32_t kOffBias = kOffOut + kStageOutBytes;
 constexpr uint32_t kOffBars = kOffBias + kC * 4;
 constexpr uint32_t kNumBars = 2 * kQStages + 2 * kAStages + 2 * kAccStages;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr uint32_t kOffFlag = kOffTmemPtr + 8;  // sub-chunks released to the MMA thread by its barrier watcher
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
 constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;
 
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
       mbar_init(acc_full(s), 1);
       mbar_init(acc_empty(s), 8);  // 4 epilogue warps x 2 CTAs (leader only)
     }
+    *reinterpret_cast<volatile uint32_t*>(smem + kOffFlag) = 0;
     fence_barrier_init();
   }
   if (warp == kWarpAlloc) {
@@ -367,35 +369,53 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
       const uint32_t idesc = idesc_tf32(256, 128);
       const uint64_t bhi0 = smem_desc_k_sw128(sbase + kOffBHi);
       const uint64_t blo0 = smem_desc_k_sw128(sbase + kOffBLo);
-      uint32_t g = 0;
-      for (int i = 0; iter_valid(i); ++i) {
-        int as_ = i % kAccStages;
-        uint32_t aph = (i / kAccStages) & 1;
-        mbar_wait(acc_empty(as_), aph ^ 1);
+      // The issuing thread is throttled to the tensor pipe's rate (its queue is only an MMA or two deep) and an
+      // mbarrier wait costs a few hundred cycles even when the phase completed long ago, so waiting here would
+      // starve the pipe between sub-chunks.  A watcher thread (warp kWarpAlloc) does all the waiting and publishes
+      // the number of sub-chunks whose operands are in place through one shared-memory word.
+      int n_iter = 0;
+      for (int i = 0; iter_valid(i); ++i) ++n_iter;
+      const uint32_t total = (uint32_t)n_iter * kNumSubs;
+      const uint32_t flag = sbase + kOffFlag;
+      uint32_t upto = 0;
+      for (uint32_t g = 0; g < total; ++g) {
+        while (upto <= g) asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(upto) : "r"(flag) : "memory");
         tc_fence_after();
+        const int sub = g % kNumSubs, s = g % kAStages;
+        const int as_ = (g / kNumSubs) % kAccStages;
         const uint32_t d = tmem_base + kColAcc + as_ * 128;
-        for (int sub = 0; sub < kNumSubs; ++sub, ++g) {
-          const int s = g % kAStages;
-          const uint32_t ph = (g / kAStages) & 1;
-          mbar_wait(a_full(s), ph);
-          tc_fence_after();
-          const uint32_t a0 = tmem_base + kColA + s * kAStageCols;
+        const uint32_t a0 = tmem_base + kColA + s * kAStageCols;
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int ks = 0; ks < kSub / 8; ++ks) {
-              const uint32_t ah = a0 + half * 2 * kSub + ks * 8, al = ah + kSub;
-              const uint64_t boff =
-                  (uint64_t)(((half * 4 + (sub >> 1)) * kBChunkBytes + (sub & 1) * kSub * 4 + ks * 32) >> 4);
-              const uint32_t acc = (sub | half | ks) ? 1u : 0u;
-              mma_tf32_ts<2>(d, ah, bhi0 + boff, idesc, acc);
-              mma_tf32_ts<2>(d, al, bhi0 + boff, idesc, 1u);
-              mma_tf32_ts<2>(d, ah, blo0 + boff, idesc, 1u);
-            }
+          for (int ks = 0; ks < kSub / 8; ++ks) {
+            const uint32_t ah = a0 + half * 2 * kSub + ks * 8, al = ah + kSub;
+            const uint64_t boff =
+                (uint64_t)(((half * 4 + (sub >> 1)) * kBChunkBytes + (sub & 1) * kSub * 4 + ks * 32) >> 4);
+            const uint32_t acc = (sub | half | ks) ? 1u : 0u;
+            mma_tf32_ts<2>(d, ah, bhi0 + boff, idesc, acc);
+            mma_tf32_ts<2>(d, al, bhi0 + boff, idesc, 1u);
+            mma_tf32_ts<2>(d, ah, blo0 + boff, idesc, 1u);
           }
-          mma_commit_pair(a_empty(s), 3);
         }
-        mma_commit_pair(acc_full(as_), 3);
+        mma_commit_pair(a_empty(s), 3);
+        if (sub == kNumSubs - 1) mma_commit_pair(acc_full(as_), 3);
+      }
+    }
+  } else if (warp == kWarpAlloc) {
+    // ------------------------------------------------------------------ barrier watcher of the MMA thread (leader)
+    if (rank == 0 && lane == 0) {
+      int n_iter = 0;
+      for (int i = 0; iter_valid(i); ++i) ++n_iter;
+      const uint32_t total = (uint32_t)n_iter * kNumSubs;
+      const uint32_t flag = sbase + kOffFlag;
+      for (uint32_t g = 0; g < total; ++g) {
+        if (g % kNumSubs == 0) {  // first sub-chunk of a tile: its accumulator must have been drained
+          const uint32_t it = g / kNumSubs;
+          mbar_wait(acc_empty(it % kAccStages), ((it / kAccStages) & 1) ^ 1);
+        }
+        mbar_wait(a_full(g % kAStages), (g / kAStages) & 1);
+        asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(flag), "r"(g + 1) : "memory");
       }
     }
   } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 4) {

@@ -62,75 +62,184 @@ __device__ __forceinline__ AxisSample axis_sample(float start, float bin, int p,
   return s;
 }
 
-constexpr int kMaxGrid = 8;             // sampling grid per bin handled by the shared-memory tables
-constexpr int kMaxTaps = 2 * kMaxGrid;  // distinct rows / columns one bin can touch
+constexpr int kMaxGrid = 7;             // sampling grid per bin handled by the shared-memory tables
+constexpr int kMaxTaps = 8;             // distinct rows / columns one bin can touch (grid + 1)
 
 // Per ROI and axis: for every bin the list of DISTINCT map rows (columns) its samples touch, with the summed
 // interpolation weight of each.  Consecutive samples of a bin share a row (the upper neighbour of one is the lower
-// neighbour of the next), so a bin with a g x g grid reads (g+1)^2 pixels instead of 4 g^2 taps.
+// neighbour of the next), so a bin with a g x g grid reads (g+1)^2 pixels instead of 4 g^2 taps.  Lists are padded
+// to the ROI-wide maximum length with zero-weight entries so that the hot loop has a compile-time trip count.
 struct AxisTaps {
-  int idx[8][kMaxTaps];
+  int off[8][kMaxTaps];   // element offset of the row / column inside the map (index * row pitch or * 128)
   float w[8][kMaxTaps];
   int n[8];
 };
 
-__device__ __forceinline__ void build_axis_taps(AxisTaps& t, int bin, float start, float bin_size, int grid, int size) {
+__device__ __forceinline__ void build_axis_taps(AxisTaps& t, int bin, float start, float bin_size, int grid, int size,
+                                                int pitch) {
+  int idx[kMaxTaps];
+  float w[kMaxTaps];
   int n = 0;
   for (int i = 0; i < grid; ++i) {
     const AxisSample s = axis_sample(start, bin_size, bin, i, grid, size);
     if (s.w_lo == 0.f && s.w_hi == 0.f) continue;  // outside the map: contributes nothing
     // lower neighbour
-    if (n > 0 && t.idx[bin][n - 1] == s.lo) {
-      t.w[bin][n - 1] += s.w_lo;
-    } else if (n > 1 && t.idx[bin][n - 2] == s.lo) {
-      t.w[bin][n - 2] += s.w_lo;
+    if (n > 0 && idx[n - 1] == s.lo) {
+      w[n - 1] += s.w_lo;
+    } else if (n > 1 && idx[n - 2] == s.lo) {
+      w[n - 2] += s.w_lo;
     } else {
-      t.idx[bin][n] = s.lo;
-      t.w[bin][n] = s.w_lo;
+      idx[n] = s.lo;
+      w[n] = s.w_lo;
       ++n;
     }
     // upper neighbour (lo == hi at the last row: both weights go to the same pixel, w_hi is 0 there)
-    if (t.idx[bin][n - 1] == s.hi) {
-      t.w[bin][n - 1] += s.w_hi;
+    if (idx[n - 1] == s.hi) {
+      w[n - 1] += s.w_hi;
     } else {
-      t.idx[bin][n] = s.hi;
-      t.w[bin][n] = s.w_hi;
+      idx[n] = s.hi;
+      w[n] = s.w_hi;
       ++n;
     }
   }
+#pragma unroll
+  for (int k = 0; k < kMaxTaps; ++k) {
+    t.off[bin][k] = (k < n ? idx[k] : 0) * pitch;
+    t.w[bin][k] = k < n ? w[k] : 0.f;
+  }
   t.n[bin] = n;
+}
+
+struct RoiGeom {  // computed once per ROI by one thread
+  const float* f;
+  int W, nx, ny, tables, pad;
+  float inv_count;
+};
+
+// NX = padded number of column taps per bin (compile time): the inner loop is 2 LDS.128 per bin and row plus
+// LDG.128 + FMUL + 4 FFMA per tap.
+template <int R, int NX>
+__device__ __forceinline__ void roi_accumulate(const AxisTaps& xt, const AxisTaps& yt, const float* __restrict__ f, int ph,
+                                               int pw0, int ny, float4 (&acc)[R / 2]) {
+  for (int kr = 0; kr < ny; ++kr) {
+    const float wy = yt.w[ph][kr];
+    const float* rowp = f + yt.off[ph][kr];
+#pragma unroll
+    for (int j = 0; j < R / 2; ++j) {
+      int off[kMaxTaps];
+      float w[kMaxTaps];
+      *reinterpret_cast<int4*>(off) = *reinterpret_cast<const int4*>(&xt.off[pw0 + j][0]);
+      *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(&xt.w[pw0 + j][0]);
+      if (NX > 4) {
+        *reinterpret_cast<int4*>(off + 4) = *reinterpret_cast<const int4*>(&xt.off[pw0 + j][4]);
+        *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(&xt.w[pw0 + j][4]);
+      }
+      float4 v[NX];
+#pragma unroll
+      for (int k = 0; k < NX; ++k) v[k] = ldg4(rowp + off[k]);
+#pragma unroll
+      for (int k = 0; k < NX; ++k) {
+        const float ww = wy * w[k];
+        acc[j].x = fmaf(ww, v[k].x, acc[j].x);
+        acc[j].y = fmaf(ww, v[k].y, acc[j].y);
+        acc[j].z = fmaf(ww, v[k].z, acc[j].z);
+        acc[j].w = fmaf(ww, v[k].w, acc[j].w);
+      }
+    }
+  }
 }
 
 // One CTA per ROI; warp = (bin row, half of the bin columns), lane = 4 channels: every tap is one fully coalesced
 // 512-byte row of the NHWC map, 4 accumulators per lane keep the register count low enough for full occupancy.
 template <int R>
-__global__ void __launch_bounds__(R * 64)
+__global__ void __launch_bounds__(R * 64, 2)
 roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* __restrict__ roi_count,
                  float* __restrict__ pooled, int32_t* __restrict__ out_level) {
-  __shared__ AxisTaps xt, yt;
+  __shared__ __align__(16) AxisTaps xt, yt;
+  __shared__ RoiGeom geom;
+  __shared__ float gbox[8];  // start_w, start_h, bin_w, bin_h, grid_w, grid_h (as float bits), W, H
   const int r = blockIdx.x, p = blockIdx.y;
   const int cnt = roi_count ? min(roi_count[p], prm.roi_cap) : prm.roi_cap;
   if (r >= cnt) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float4 box = *reinterpret_cast<const float4*>(rois + ((size_t)p * prm.roi_cap + r) * 4);
-  int min_level = 31 - __clz(prm.stride[0]);
-  const int lvl = assign_level(box, min_level, prm.num_levels);
-  if (out_level && threadIdx.x == 0) out_level[(size_t)p * prm.roi_cap + r] = lvl;
-  int H = prm.H[0], W = prm.W[0], stride = prm.stride[0];
-  const float* fbase = prm.feat[0];
-  if (lvl == 1) { H = prm.H[1]; W = prm.W[1]; stride = prm.stride[1]; fbase = prm.feat[1]; }
-  if (lvl == 2) { H = prm.H[2]; W = prm.W[2]; stride = prm.stride[2]; fbase = prm.feat[2]; }
-  const float scale = 1.0f / (float)stride;
-  const float* f = fbase + (size_t)(p / prm.C) * H * W * kC + lane * 4;
-  const float start_w = __fsub_rn(__fmul_rn(box.x, scale), 0.5f);
-  const float start_h = __fsub_rn(__fmul_rn(box.y, scale), 0.5f);
-  const float end_w = __fsub_rn(__fmul_rn(box.z, scale), 0.5f);
-  const float end_h = __fsub_rn(__fmul_rn(box.w, scale), 0.5f);
-  const float roi_w = __fsub_rn(end_w, start_w), roi_h = __fsub_rn(end_h, start_h);
-  const float bin_h = __fdiv_rn(roi_h, (float)R), bin_w = __fdiv_rn(roi_w, (float)R);
-  const int grid_h = (int)ceilf(__fdiv_rn(roi_h, (float)R));
-  const int grid_w = (int)ceilf(__fdiv_rn(roi_w, (float)R));
-  const float inv_count = 1.0f / fmaxf((float)(grid_h * grid_w), 1.0f);
+  if (threadIdx.x == 0) {
+    const float4 box = *reinterpret_cast<const float4*>(rois + ((size_t)p * prm.roi_cap + r) * 4);
+    int min_level = 31 - __clz(prm.stride[0]);
+    const int lvl = assign_level(box, min_level, prm.num_levels);
+    if (out_level) out_level[(size_t)p * prm.roi_cap + r] = lvl;
+    int H = prm.H[0], W = prm.W[0], stride = prm.stride[0];
+    const float* fbase = prm.feat[0];
+    if (lvl == 1) { H = prm.H[1]; W = prm.W[1]; stride = prm.stride[1]; fbase = prm.feat[1]; }
+    if (lvl == 2) { H = prm.H[2]; W = prm.W[2]; stride = prm.stride[2]; fbase = prm.feat[2]; }
+    const float scale = 1.0f / (float)stride;
+    const float start_w = __fsub_rn(__fmul_rn(box.x, scale), 0.5f);
+    const float start_h = __fsub_rn(__fmul_rn(box.y, scale), 0.5f);
+    const float end_w = __fsub_rn(__fmul_rn(box.z, scale), 0.5f);
+    const float end_h = __fsub_rn(__fmul_rn(box.w, scale), 0.5f);
+    const float roi_w = __fsub_rn(end_w, start_w), roi_h = __fsub_rn(end_h, start_h);
+    const int grid_h = (int)ceilf(__fdiv_rn(roi_h, (float)R));
+    const int grid_w = (int)ceilf(__fdiv_rn(roi_w, (float)R));
+    geom.f = fbase + (size_t)(p / prm.C) * H * W * kC;
+    geom.W = W;
+    geom.inv_count = 1.0f / fmaxf((float)(grid_h * grid_w), 1.0f);
+    geom.tables = grid_h <= kMaxGrid && grid_w <= kMaxGrid;
+    gbox[0] = start_w;
+    gbox[1] = start_h;
+    gbox[2] = __fdiv_rn(roi_w, (float)R);
+    gbox[3] = __fdiv_rn(roi_h, (float)R);
+    gbox[4] = __int_as_float(grid_w);
+    gbox[5] = __int_as_float(grid_h);
+    gbox[6] = __int_as_float(W);
+    gbox[7] = __int_as_float(H);
+  }
+  __syncthreads();
+  const bool tables = geom.tables;
+  const int W = __float_as_int(gbox[6]), H = __float_as_int(gbox[7]);
+  const int grid_w = __float_as_int(gbox[4]), grid_h = __float_as_int(gbox[5]);
+  if (tables) {
+    if (threadIdx.x < R) build_axis_taps(xt, threadIdx.x, gbox[0], gbox[2], grid_w, W, kC);
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + R) build_axis_taps(yt, threadIdx.x - 32, gbox[1], gbox[3], grid_h, H, W * kC);
+  }
+  __syncthreads();
+  const float* f = geom.f + lane * 4;
+  const int ph = warp >> 1, pw0 = (warp & 1) * (R / 2);
+  float4 acc[R / 2];
+#pragma unroll
+  for (int j = 0; j < R / 2; ++j) acc[j] = make_float4(0, 0, 0, 0);
+  if (tables) {
+    int nx = 0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) nx = max(nx, xt.n[j]);
+    const int ny = yt.n[ph];
+    switch (nx) {
+      case 0: break;
+      case 1: case 2: roi_accumulate<R, 2>(xt, yt, f, ph, pw0, ny, acc); break;
+      case 3: roi_accumulate<R, 3>(xt, yt, f, ph, pw0, ny, acc); break;
+      case 4: roi_accumulate<R, 4>(xt, yt, f, ph, pw0, ny, acc); break;
+      case 5: case 6: roi_accumulate<R, 6>(xt, yt, f, ph, pw0, ny, acc); break;
+      default: roi_accumulate<R, 8>(xt, yt, f, ph, pw0, ny, acc); break;
+    }
+  } else {  // sampling grid beyond the tables (box much larger than the pyramid level expects): sample by sample
+    for (int iy = 0; iy < grid_h; ++iy) {
+      const AxisSample ys = axis_sample(gbox[1], gbox[3], ph, iy, grid_h, H);
+      if (ys.w_lo == 0.f && ys.w_hi == 0.f) continue;
+      const float* row_lo = f + (size_t)ys.lo * W * kC;
+      const float* row_hi = f + (size_t)ys.hi * W * kC;
+#pragma unroll
+      for (int j = 0; j < R / 2; ++j) {
+        for (int ix = 0; ix < grid_w; ++ix) {
+          const AxisSample xs = axis_sample(gbox[0], gbox[2], pw0 + j, ix, grid_w, W);
+          const float4 v1 = ldg4(row_lo + (size_t)xs.lo * kC), v2 = ldg4(row_lo + (size_t)xs.hi * kC);
+          const float4 v3 = ldg4(row_hi + (size_t)xs.lo * kC), v4 = ldg4(row_hi + (size_t)xs.hi * kC);
+          const float w1 = ys.w_lo * xs.w_lo, w2 = ys.w_lo * xs.w_hi, w3 = ys.w_hi * xs.w_lo, w4 = ys.w_hi * xs.w_hi;
+          acc[j].x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
+          acc[j].y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
+          acc[j].z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
+          acc[j].w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
+        }
+      }
+    }
+  }
   // Output layout.  tiled == 0: [P][roi_cap][R*R][128] (row-major ROI rows).  tiled == 1 (R == 8, consumed by
   // fod_relation_head): [P][units][256 k-chunks][128 rows][32], units = ceil(roi_cap / 128): the 16 KB A tile of
   // one 32-wide K chunk of 128 ROI rows is contiguous, so one TMA box fetches it as a linear stream.
@@ -144,56 +253,7 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
     out = pooled + ((size_t)p * prm.roi_cap + r) * R * R * kC + lane * 4;
     bin_stride = kC;
   }
-  const bool tables = grid_h <= kMaxGrid && grid_w <= kMaxGrid;
-  if (tables) {
-    if (threadIdx.x < R) build_axis_taps(xt, threadIdx.x, start_w, bin_w, grid_w, W);
-    else if (threadIdx.x >= 32 && threadIdx.x < 32 + R) build_axis_taps(yt, threadIdx.x - 32, start_h, bin_h, grid_h, H);
-  }
-  __syncthreads();
-  const int ph = warp >> 1, pw0 = (warp & 1) * (R / 2);
-  float4 acc[R / 2];
-#pragma unroll
-  for (int j = 0; j < R / 2; ++j) acc[j] = make_float4(0, 0, 0, 0);
-  if (tables) {
-    const int ny = yt.n[ph];
-    for (int kr = 0; kr < ny; ++kr) {
-      const float wy = yt.w[ph][kr];
-      const float* rowp = f + (size_t)yt.idx[ph][kr] * W * kC;
-#pragma unroll
-      for (int j = 0; j < R / 2; ++j) {
-        const int nx = xt.n[pw0 + j];
-#pragma unroll 3
-        for (int kx = 0; kx < nx; ++kx) {
-          const float4 v = ldg4(rowp + (size_t)xt.idx[pw0 + j][kx] * kC);
-          const float w = wy * xt.w[pw0 + j][kx];
-          acc[j].x = fmaf(w, v.x, acc[j].x);
-          acc[j].y = fmaf(w, v.y, acc[j].y);
-          acc[j].z = fmaf(w, v.z, acc[j].z);
-          acc[j].w = fmaf(w, v.w, acc[j].w);
-        }
-      }
-    }
-  } else {  // sampling grid beyond the tables (box much larger than the pyramid level expects): sample by sample
-    for (int iy = 0; iy < grid_h; ++iy) {
-      const AxisSample ys = axis_sample(start_h, bin_h, ph, iy, grid_h, H);
-      if (ys.w_lo == 0.f && ys.w_hi == 0.f) continue;
-      const float* row_lo = f + (size_t)ys.lo * W * kC;
-      const float* row_hi = f + (size_t)ys.hi * W * kC;
-#pragma unroll
-      for (int j = 0; j < R / 2; ++j) {
-        for (int ix = 0; ix < grid_w; ++ix) {
-          const AxisSample xs = axis_sample(start_w, bin_w, pw0 + j, ix, grid_w, W);
-          const float4 v1 = ldg4(row_lo + (size_t)xs.lo * kC), v2 = ldg4(row_lo + (size_t)xs.hi * kC);
-          const float4 v3 = ldg4(row_hi + (size_t)xs.lo * kC), v4 = ldg4(row_hi + (size_t)xs.hi * kC);
-          const float w1 = ys.w_lo * xs.w_lo, w2 = ys.w_lo * xs.w_hi, w3 = ys.w_hi * xs.w_lo, w4 = ys.w_hi * xs.w_hi;
-          acc[j].x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
-          acc[j].y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
-          acc[j].z += w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
-          acc[j].w += w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
-        }
-      }
-    }
-  }
+  const float inv_count = geom.inv_count;
 #pragma unroll
   for (int j = 0; j < R / 2; ++j) {
     float4 o = make_float4(acc[j].x * inv_count, acc[j].y * inv_count, acc[j].z * inv_count, acc[j].w * inv_count);
