@@ -49,6 +49,9 @@ _PROTOTYPES = {
     "fod_split_tf32": ([_vp, _vp, ctypes.c_size_t, _vp], _i),
     "fod_final_detect": ([_vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_batched_nms": ([_vp, _vp, _vp, _i, _d, _vp, _vp, _vp], _i),
+    "fod_conv2d_packed_floats": ([_i, _i, _i], ctypes.c_size_t),
+    "fod_conv2d_pack_weights": ([_vp, _i, _i, _i, _vp, _vp], _i),
+    "fod_conv2d_nhwc": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_long, _vp], _i),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)

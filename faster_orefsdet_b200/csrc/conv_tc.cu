@@ -1,0 +1,543 @@
+// H0 (and the convolutions either side of the head): 3x3 / 1x1 convolution over NHWC fp32 maps as an implicit GEMM on
+// the 5th-generation tensor cores, fp32 accuracy by 3xTF32 operand splitting, bias + ReLU epilogue.
+// Replaces the F.conv2d -> cuDNN calls of CenterNetHead (CenterNet2/centernet/modeling/dense_heads/centernet_head.py:
+// 141-161) and of the VoVNet/FPN modules that feed the head (d2!/modeling/backbone/vovnet.py, fpn.py), which cuDNN
+// serves on sm_100 with fp32 SIMT / FFT engines when TF32 is off.
+//
+//   y[n][oy][ox][co] = act( bias[co] + sum_{ky,kx,ci} w[co][ky][kx][ci] * x[n][oy*s + ky - pad][ox*s + kx - pad][ci] )
+//   (stride s in {1, 2}, pad = ksize / 2, zero padding)
+//
+// Design (B200, sm_100a) - the skeleton of correlate_tc.cu / relation_tc.cu:
+//   * work unit = tile of 8 x 16 output pixels of one image (128 GEMM rows) x one group of <= 128 output channels.
+//     CTAs run as pairs (cluster of 2, tcgen05 cta_group::2): one MMA covers both CTAs' tiles (M = 256) against the
+//     weight group whose rows are split between the two CTAs (each CTA stages only half of every weight chunk).
+//   * K = taps x Cin is streamed in 32-channel chunks.  The input tile plus its halo (zero-filled outside the image
+//     by TMA, which is the convolution's zero padding) is staged ONCE per 32-channel chunk into a 3-deep shared-memory
+//     ring and serves all ksize^2 taps: the shifted A operands are read from it, never re-fetched from L2.
+//   * 16 converter warps (one output pixel per lane = TMEM lane) read the tap-shifted 128-byte row of their pixel
+//     (conflict-free LDS.128 thanks to the TMA swizzle), split it into tf32 hi / lo and write it into TENSOR MEMORY;
+//     the MMA (Ahi.Bhi + Alo.Bhi + Ahi.Blo) reads A from tensor memory and only the weights from shared memory.
+//     Two sets of 8 warps alternate over the chunks so that their latencies overlap.
+//   * weights: pre-split tf32 hi / lo planes [Cout][taps][Cin_pad] (fod_conv2d_pack_weights), TMA-streamed per chunk
+//     into a 4-stage ring (they are L2 resident: <= 1.2 MB per layer).
+//   * the tensor core accumulates with round-toward-zero (tools/tc_probe.cu), so the K loop is cut into partial sums
+//     of <= 8 chunks (96 MMAs) that the 4 epilogue warps add in IEEE fp32 into a running tile in shared memory; the
+//     last part adds the bias, applies ReLU and the tile leaves through TMA stores (clipped at the image border and at
+//     Cout by the tensor map, so the output may be a channel slice of a wider NHWC buffer: concatenation is free).
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace fod {
+
+using namespace tc;
+
+namespace cvt {
+
+constexpr int kTileH = 8, kTileW = 16;
+constexpr int kChunk = 32;
+constexpr int kQStages = 3, kStages = 4, kAccStages = 2;
+constexpr int kPartChunks = 8;
+constexpr int kMaxHaloPx = (2 * kTileH + 1) * (2 * kTileW + 1);            // stride 2, 3x3: 17 x 33
+constexpr uint32_t kQStageStrideS1 = ((kTileH + 2) * (kTileW + 2) * 128 + 1023) / 1024 * 1024;   // 23552
+constexpr uint32_t kBPlaneMax = 64 * 128;                                   // 64 rows (half of a 128 group) x 128 B
+constexpr uint32_t kBStageBytes = 2 * kBPlaneMax;                           // hi + lo
+constexpr uint32_t kSlabBytes = 128 * 128;                                  // 128 pixels x 32 channels
+
+constexpr uint32_t kOffQ = 0;
+constexpr uint32_t kOffB = kOffQ + kQStages * kQStageStrideS1;              // 70656
+constexpr uint32_t kOffSum = kOffB + kStages * kBStageBytes;                // running tile / store staging, 4 slabs
+constexpr uint32_t kOffBias = kOffSum + 4 * kSlabBytes;
+constexpr uint32_t kOffBars = kOffBias + 128 * 4;
+constexpr uint32_t kNumBars = 2 * kQStages + 3 * kStages + 2 * kAccStages;
+constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr uint32_t kOffFlag = kOffTmemPtr + 8;
+constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
+constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;
+
+constexpr int kConvWarps = 16;
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpTmaB = 3, kWarpEpi0 = 4, kWarpConv0 = 8;
+constexpr int kThreads = (kWarpConv0 + kConvWarps) * 32;  // 768
+
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColA = 0;      // 4 stages x [hi 32 | lo 32]
+constexpr uint32_t kColAcc = 256;  // 2 stages x 128
+
+#ifdef FOD_DBG
+__device__ long long* g_dbg = nullptr;   // [role][g][4] clock64 stamps of pair 0 / rank 0, chunks kDbg0 .. kDbg0 + kDbgN
+constexpr uint32_t kDbg0 = 400, kDbgN = 64;
+#define DBG_STAMP(role, g, slot)                                                                   \
+  do {                                                                                             \
+    if (dbg_buf && lane == 0 && (g) >= kDbg0 && (g) < kDbg0 + kDbgN)                               \
+      dbg_buf[((role) * kDbgN + ((g) - kDbg0)) * 4 + (slot)] = clock64();                          \
+  } while (0)
+#else
+#define DBG_STAMP(role, g, slot)
+#endif
+
+struct Params {
+  CUtensorMap in_map;   // [N][H][W][Cin] (pixel stride may exceed Cin), box 32 x halo_w x halo_h
+  CUtensorMap out_map;  // [N][Ho][Wo][Cout], box 32 x 16 x 8
+  CUtensorMap whi_map;  // [Cout][taps*Cin_pad], box 32 x nhalf
+  CUtensorMap wlo_map;
+  const float* bias;    // [Cout] or null
+  int tiles_x, tiles_per_img, tiles_total;
+  int ksize, taps, stride, halo_w;
+  int cin_chunks, chunks, parts, chunks_per_part;
+  int n_groups, n_group, nhalf, ncol32, cout;
+  int relu, num_pairs, pair_units;
+  uint32_t q_stage_bytes, q_stage_stride;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  const uint32_t rank = blockIdx.x & 1;  // == %cluster_ctarank for cluster dims (2,1,1)
+  const int pair = blockIdx.x >> 1;
+
+#ifdef FOD_DBG
+  long long* const dbg_buf = (pair == 0 && rank == 0) ? g_dbg : nullptr;
+#endif
+  const uint32_t bar0 = sbase + kOffBars;
+  auto q_full = [&](int s) { return bar0 + 8u * s; };                                  // TMA -> converters
+  auto q_empty = [&](int s) { return bar0 + 8u * (kQStages + s); };                    // converters -> TMA
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * kQStages + s); };                 // TMA of both CTAs -> MMA (leader)
+  auto ready = [&](int s) { return bar0 + 8u * (2 * kQStages + kStages + s); };        // converters of both CTAs -> MMA
+  auto st_free = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kStages + s); };  // MMA commit -> A + B stage free
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + kAccStages + s); };
+
+  if (tid == 0) {
+    for (int s = 0; s < kQStages; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), kConvWarps);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(b_full(s), 1);
+      mbar_init(ready(s), kConvWarps);  // one set of 8 warps per CTA, both CTAs
+      mbar_init(st_free(s), 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      mbar_init(acc_full(s), 1);
+      mbar_init(acc_empty(s), 8);  // 4 epilogue warps x 2 CTAs
+    }
+    *reinterpret_cast<volatile uint32_t*>(smem + kOffFlag) = 0;
+    fence_barrier_init();
+  }
+  if (warp == kWarpAlloc) {
+    tmem_alloc<2>(sbase + kOffTmemPtr, kTmemCols);
+    tmem_relinquish<2>();
+  }
+  if (warp == kWarpTma && lane == 0) {
+    tma_prefetch_desc(&P.in_map);
+    tma_prefetch_desc(&P.out_map);
+    tma_prefetch_desc(&P.whi_map);
+    tma_prefetch_desc(&P.wlo_map);
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+
+  // Static schedule: iteration i of pair k owns pair-unit pu = i * num_pairs + k = (tile pair tp, channel group grp),
+  // grp innermost so that the pairs working on the same input tile run at the same time (L2 reuse of the halo).
+  auto in_range = [&](int i) { return i * P.num_pairs + pair < P.pair_units; };
+  auto unit_tile = [&](int i) { return 2 * ((i * P.num_pairs + pair) / P.n_groups) + (int)rank; };
+  auto unit_grp = [&](int i) { return (i * P.num_pairs + pair) % P.n_groups; };
+  const int chunks = P.chunks, taps = P.taps, cin_chunks = P.cin_chunks;
+
+  if (warp == kWarpTma) {
+    // ------------------------------------------------------------------ TMA producer: input tile + halo, per 32 channels
+    if (lane == 0) {
+      uint32_t g = 0;
+      const int pad = P.ksize >> 1;
+      for (int i = 0; in_range(i); ++i) {
+        const int t = min(unit_tile(i), P.tiles_total - 1);
+        const int n = t / P.tiles_per_img, tt = t - n * P.tiles_per_img;
+        const int ty = tt / P.tiles_x, tx = tt - ty * P.tiles_x;
+        const int x0 = tx * kTileW * P.stride - pad, y0 = ty * kTileH * P.stride - pad;
+        for (int cc = 0; cc < cin_chunks; ++cc, ++g) {
+          const int s = g % kQStages;
+          const uint32_t ph = (g / kQStages) & 1;
+          mbar_wait(q_empty(s), ph ^ 1);
+          mbar_arrive_expect_tx(q_full(s), P.q_stage_bytes);
+          tma_load_4d(sbase + kOffQ + s * P.q_stage_stride, &P.in_map, q_full(s), cc * kChunk, x0, y0, n);
+        }
+      }
+    }
+  } else if (warp == kWarpTmaB) {
+    // ------------------------------------------------------------------ TMA producer: weight chunk (hi + lo planes)
+    if (lane == 0) {
+      const uint32_t b_full_leader = map_to_cta(b_full(0), 0);
+      const uint32_t plane = (uint32_t)P.nhalf * 128u;
+      uint32_t g = 0;
+      for (int i = 0; in_range(i); ++i) {
+        const int row0 = unit_grp(i) * P.n_group + (int)rank * P.nhalf;
+        for (int cc = 0; cc < cin_chunks; ++cc)
+          for (int tap = 0; tap < taps; ++tap, ++g) {
+            const int s = g % kStages;
+            const uint32_t ph = (g / kStages) & 1;
+            DBG_STAMP(0, g, 0);
+            mbar_wait(st_free(s), ph ^ 1);
+            DBG_STAMP(0, g, 1);
+            if (rank == 0) mbar_arrive_expect_tx(b_full(s), 4 * plane);
+            const int k0 = (tap * cin_chunks + cc) * kChunk;
+            tma_load_2d_2sm(sbase + kOffB + s * kBStageBytes, &P.whi_map, b_full_leader + 8u * s, k0, row0);
+            tma_load_2d_2sm(sbase + kOffB + s * kBStageBytes + plane, &P.wlo_map, b_full_leader + 8u * s, k0, row0);
+          }
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    // The whole warp runs the loop converged and one elected lane issues: every operand of tcgen05.mma is then a
+    // warp-uniform value that ptxas keeps in uniform registers.  (Inside an `if (lane == 0)` region the same code
+    // compiles to a broadcast-and-retry loop around each MMA whose latency exceeds the 64 cycles of the MMA itself.)
+    if (rank == 0) {
+      const uint32_t idesc = idesc_tf32(256, P.n_group);
+      const uint32_t plane = (uint32_t)P.nhalf * 128u;
+      const uint32_t flag = sbase + kOffFlag;
+      const int cpp = P.chunks_per_part;
+      uint32_t upto = 0, g = 0, gp = 0;
+      for (int i = 0; in_range(i); ++i) {
+        int pc = 0;
+        for (int lc = 0; lc < chunks; ++lc, ++g) {
+          DBG_STAMP(1, g, 0);
+          while (upto <= g) {
+            uint32_t v;
+            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(flag) : "memory");
+            upto = __shfl_sync(0xffffffffu, v, 0);
+          }
+          tc_fence_after();
+          DBG_STAMP(1, g, 1);
+          const int s = g % kStages;
+          const bool first = pc == 0, last = (pc == cpp - 1) || (lc == chunks - 1);
+          const int as_ = gp % kAccStages;
+          const uint32_t d = tmem_base + kColAcc + as_ * 128;
+          const uint32_t a0 = tmem_base + kColA + s * 64;
+          const uint64_t bhi = smem_desc_k_sw128(sbase + kOffB + s * kBStageBytes);
+          const uint64_t blo = smem_desc_k_sw128(sbase + kOffB + s * kBStageBytes + plane);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t ah = a0 + ks * 8, al = ah + 32;
+              const uint64_t boff = (uint64_t)((ks * 32) >> 4);
+              mma_tf32_ts<2>(d, ah, bhi + boff, idesc, (!first || ks) ? 1u : 0u);
+              mma_tf32_ts<2>(d, al, bhi + boff, idesc, 1u);
+              mma_tf32_ts<2>(d, ah, blo + boff, idesc, 1u);
+            }
+            mma_commit_pair(st_free(s), 3);
+            if (last) mma_commit_pair(acc_full(as_), 3);
+          }
+          __syncwarp();
+          DBG_STAMP(1, g, 2);
+          if (last) {
+            ++gp;
+            pc = 0;
+          } else {
+            ++pc;
+          }
+        }
+      }
+    }
+  } else if (warp == kWarpAlloc) {
+    // ------------------------------------------------------------------ barrier watcher of the MMA thread (leader)
+    if (rank == 0 && lane == 0) {
+      const uint32_t flag = sbase + kOffFlag;
+      uint32_t g = 0, gp = 0;
+      const int cpp = P.chunks_per_part;
+      for (int i = 0; in_range(i); ++i) {
+        int pc = 0;
+        for (int lc = 0; lc < chunks; ++lc, ++g) {
+          const int s = g % kStages;
+          const uint32_t ph = (g / kStages) & 1;
+          DBG_STAMP(2, g, 0);
+          if (pc == 0) mbar_wait(acc_empty(gp % kAccStages), ((gp / kAccStages) & 1) ^ 1);
+          DBG_STAMP(2, g, 1);
+          mbar_wait(b_full(s), ph);
+          DBG_STAMP(2, g, 2);
+          mbar_wait(ready(s), ph);
+          DBG_STAMP(2, g, 3);
+          asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(flag), "r"(g + 1) : "memory");
+          if (pc == cpp - 1 || lc == chunks - 1) {
+            ++gp;
+            pc = 0;
+          } else {
+            ++pc;
+          }
+        }
+      }
+    }
+  } else if (warp >= kWarpEpi0 && warp < kWarpEpi0 + 4) {
+    // ------------------------------------------------------------------ epilogue: one output pixel per lane
+    const int qd = warp & 3;
+    const int m = qd * 32 + lane;
+    const uint32_t acc_empty_leader = map_to_cta(acc_empty(0), 0);
+    const bool issuer = (warp == kWarpEpi0 && lane == 0);
+    const uint32_t row_s = sbase + kOffSum + (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
+    const uint32_t bias_s = sbase + kOffBias;
+    const int ncol32 = P.ncol32, parts = P.parts;
+    uint32_t gp = 0;
+    for (int i = 0; in_range(i); ++i) {
+      const int t = unit_tile(i);
+      const bool do_store = t < P.tiles_total;
+      const int tc_ = min(t, P.tiles_total - 1);
+      const int n = tc_ / P.tiles_per_img, tt = tc_ - n * P.tiles_per_img;
+      const int ty = tt / P.tiles_x, tx = tt - ty * P.tiles_x;
+      const int ch0 = unit_grp(i) * P.n_group;
+      if (issuer) tma_store_wait_read<0>();  // the previous tile has left the staging slabs
+      named_bar_sync(1, 128);
+      {
+        const int ch = ch0 + m;
+        reinterpret_cast<float*>(smem + kOffBias)[m] = (P.bias && ch < P.cout) ? __ldg(P.bias + ch) : 0.f;
+      }
+      named_bar_sync(1, 128);
+#pragma unroll 1
+      for (int part = 0; part < parts; ++part, ++gp) {
+        const int as_ = gp % kAccStages;
+        const uint32_t aph = (gp / kAccStages) & 1;
+        mbar_wait(acc_full(as_), aph);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColAcc + as_ * 128;
+#pragma unroll 1
+        for (int j = 0; j < ncol32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(trow + j * 32, v);
+          tmem_wait_ld();
+          if (j == ncol32 - 1) {  // accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * as_);
+          }
+          const uint32_t slab = row_s + (uint32_t)j * kSlabBytes;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            const uint32_t sa = slab + (uint32_t)((c4 ^ (m & 7)) << 4);
+            float4 x = make_float4(__uint_as_float(v[c4 * 4 + 0]), __uint_as_float(v[c4 * 4 + 1]),
+                                   __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+            if (part > 0) {
+              const float4 r = lds4s(sa);
+              x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+            }
+            if (part == parts - 1) {
+              const float4 bb = lds4s(bias_s + (j * 32 + c4 * 4) * 4);
+              x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+              if (P.relu) {
+                x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+              }
+            }
+            sts4s(sa, x);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (issuer && do_store) {
+        for (int j = 0; j < ncol32 && ch0 + j * 32 < P.cout; ++j)
+          tma_store_4d(&P.out_map, sbase + kOffSum + j * kSlabBytes, ch0 + j * 32, tx * kTileW, ty * kTileH, n);
+        tma_store_commit();
+      }
+    }
+    if (issuer) tma_store_wait<0>();
+  } else if (warp >= kWarpConv0) {
+    // ------------------------------------------------------------------ converters: shifted A chunk -> tf32 hi/lo in TMEM
+    const int cw = warp - kWarpConv0;
+    const int qd = cw & 3, half = (cw >> 2) & 1, set = cw >> 3;
+    const int m = qd * 32 + lane;
+    const int py = (m >> 4) * P.stride, px = (m & 15) * P.stride;  // position of this pixel's tap (0,0) in the halo tile
+    const uint32_t ready_leader = map_to_cta(ready(0), 0);
+    const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColA + half * 16;
+    const int ksz = P.ksize, hw = P.halo_w;
+    uint32_t g = 0, gq = 0;
+    for (int i = 0; in_range(i); ++i) {
+      for (int cc = 0; cc < cin_chunks; ++cc, ++gq) {
+        const int qs = gq % kQStages;
+        mbar_wait(q_full(qs), (gq / kQStages) & 1);
+        const uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
+        int dy = 0, dx = 0;
+        for (int tap = 0; tap < taps; ++tap, ++g) {
+          if ((int)(g & 1) == set) {
+            if (cw == 0 || cw == 8) DBG_STAMP(3, g, 0);
+            const int r = (py + dy) * hw + px + dx;
+            const uint32_t at = qt + (uint32_t)r * 128u;
+            const uint32_t key = (uint32_t)(r & 7);
+            float4 x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = lds4s(at + ((((uint32_t)(half * 4 + j)) ^ key) << 4));
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              split_tf32(x[j].x, hi[4 * j + 0], lo[4 * j + 0]);
+              split_tf32(x[j].y, hi[4 * j + 1], lo[4 * j + 1]);
+              split_tf32(x[j].z, hi[4 * j + 2], lo[4 * j + 2]);
+              split_tf32(x[j].w, hi[4 * j + 3], lo[4 * j + 3]);
+            }
+            const int s = g % kStages;
+            if (cw == 0 || cw == 8) DBG_STAMP(3, g, 1);
+            mbar_wait(st_free(s), ((g / kStages) & 1) ^ 1);  // the MMAs that read this TMEM stage have completed
+            tc_fence_after();
+            if (cw == 0 || cw == 8) DBG_STAMP(3, g, 2);
+            tmem_st16(trow + s * 64, hi);
+            tmem_st16(trow + s * 64 + 32, lo);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(ready_leader + 8u * s);
+            if (cw == 0 || cw == 8) DBG_STAMP(3, g, 3);
+          }
+          if (++dx == ksz) { dx = 0; ++dy; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(q_empty(qs));
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync();
+  if (warp == kWarpAlloc) tmem_dealloc<2>(tmem_base, kTmemCols);
+}
+
+// OIHW fp32 weights -> tf32 hi / lo planes [Cout][ky][kx][Cin_pad] (Cin_pad = Cin rounded up to 32, zero filled)
+__global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int ksize, int cin_pad,
+                                    float* __restrict__ hi, float* __restrict__ lo) {
+  const int taps = ksize * ksize;
+  const size_t total = (size_t)cout * taps * cin_pad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % cin_pad);
+    const size_t r = i / cin_pad;
+    const int tap = (int)(r % taps), co = (int)(r / taps);
+    float x = 0.f;
+    if (ci < cin) x = w[((size_t)co * cin + ci) * taps + tap];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi[i] = __uint_as_float(h);
+    lo[i] = x - __uint_as_float(h);
+  }
+}
+
+int make_nhwc_map_strided(CUtensorMap* out, const float* base, int N, int H, int W, int C, long pixel_stride, int bc, int bw,
+                          int bh, int estride) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return FOD_ERR_CUDA;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)pixel_stride * 4, (cuuint64_t)W * pixel_stride * 4, (cuuint64_t)H * W * pixel_stride * 4};
+  cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for map [%d,%d,%d,%d] pixel stride %ld box [%d,%d,%d]", (int)r, N, H, W, C,
+              pixel_stride, bc, bw, bh);
+    return FOD_ERR_CUDA;
+  }
+  return FOD_OK;
+}
+
+}  // namespace cvt
+}  // namespace fod
+
+using namespace fod;
+
+#ifdef FOD_DBG
+extern "C" int fod_conv2d_debug(long long* buf) {
+  cudaMemcpyToSymbol(cvt::g_dbg, &buf, sizeof(buf));
+  return 0;
+}
+#endif
+
+extern "C" size_t fod_conv2d_packed_floats(int cout, int cin, int ksize) {
+  const size_t cin_pad = (size_t)(cin + 31) / 32 * 32;
+  return 2 * (size_t)cout * ksize * ksize * cin_pad;
+}
+
+extern "C" int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, float* packed, fod_stream_t stream) {
+  FOD_REQUIRE(w_oihw && packed, "fod_conv2d_pack_weights: null pointer");
+  FOD_REQUIRE(cout > 0 && cin > 0 && (ksize == 1 || ksize == 3), "fod_conv2d_pack_weights: bad sizes");
+  const int cin_pad = (cin + 31) / 32 * 32;
+  const size_t plane = (size_t)cout * ksize * ksize * cin_pad;
+  const unsigned blocks = (unsigned)((plane + 255) / 256 < 4096 ? (plane + 255) / 256 : 4096);
+  cvt::pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize, cin_pad, packed, packed + plane);
+  FOD_CUDA_LAUNCH_CHECK("fod_conv2d_pack_weights");
+  return FOD_OK;
+}
+
+extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* packed,
+                               const float* bias, int cout, int ksize, int stride, int relu, float* y,
+                               long y_pixel_stride, fod_stream_t stream) {
+  FOD_REQUIRE(x && packed && y, "fod_conv2d_nhwc: null pointer");
+  FOD_REQUIRE(n >= 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "fod_conv2d_nhwc: bad sizes");
+  FOD_REQUIRE(ksize == 1 || ksize == 3, "fod_conv2d_nhwc: ksize must be 1 or 3");
+  FOD_REQUIRE(stride == 1, "fod_conv2d_nhwc: only stride 1 is built");
+  FOD_REQUIRE(cin % 4 == 0 && cout % 4 == 0 && x_pixel_stride % 4 == 0 && y_pixel_stride % 4 == 0 &&
+                  x_pixel_stride >= cin && y_pixel_stride >= cout,
+              "fod_conv2d_nhwc: channel counts and pixel strides must be multiples of 4 (16-byte TMA granularity)");
+  FOD_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)packed) & 15) == 0, "fod_conv2d_nhwc: pointers must be 16-byte aligned");
+  if (n == 0) return FOD_OK;
+  const int pad = ksize / 2;
+  const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (w + 2 * pad - ksize) / stride + 1;
+  cvt::Params prm;
+  memset(&prm, 0, sizeof(prm));
+  const int halo_w = (cvt::kTileW - 1) * stride + ksize, halo_h = (cvt::kTileH - 1) * stride + ksize;
+  prm.halo_w = halo_w;
+  prm.q_stage_bytes = (uint32_t)(halo_w * halo_h * 128);
+  prm.q_stage_stride = (prm.q_stage_bytes + 1023) / 1024 * 1024;
+  FOD_REQUIRE(cvt::kQStages * prm.q_stage_stride <= cvt::kOffB, "fod_conv2d_nhwc: halo tile does not fit the input ring");
+  const int cin_pad = (cin + 31) / 32 * 32;
+  prm.ksize = ksize;
+  prm.taps = ksize * ksize;
+  prm.stride = stride;
+  prm.cin_chunks = cin_pad / 32;
+  prm.chunks = prm.taps * prm.cin_chunks;
+  prm.parts = (prm.chunks + cvt::kPartChunks - 1) / cvt::kPartChunks;
+  prm.chunks_per_part = (prm.chunks + prm.parts - 1) / prm.parts;
+  prm.parts = (prm.chunks + prm.chunks_per_part - 1) / prm.chunks_per_part;
+  const int n16 = (cout + 15) / 16 * 16;
+  prm.n_group = n16 < 128 ? n16 : 128;
+  prm.n_groups = (cout + prm.n_group - 1) / prm.n_group;
+  prm.nhalf = prm.n_group / 2;
+  prm.ncol32 = (prm.n_group + 31) / 32;
+  prm.cout = cout;
+  prm.relu = relu;
+  prm.bias = bias;
+  prm.tiles_x = (wo + cvt::kTileW - 1) / cvt::kTileW;
+  prm.tiles_per_img = prm.tiles_x * ((ho + cvt::kTileH - 1) / cvt::kTileH);
+  const long tiles = (long)n * prm.tiles_per_img;
+  FOD_REQUIRE(tiles * prm.n_groups < (1L << 30), "fod_conv2d_nhwc: too many tiles");
+  prm.tiles_total = (int)tiles;
+  prm.pair_units = (int)((tiles + 1) / 2) * prm.n_groups;
+  int rc = cvt::make_nhwc_map_strided(&prm.in_map, x, n, h, w, cin, x_pixel_stride, cvt::kChunk, halo_w, halo_h, 1);
+  if (rc != FOD_OK) return rc;
+  rc = cvt::make_nhwc_map_strided(&prm.out_map, y, n, ho, wo, cout, y_pixel_stride, cvt::kChunk, cvt::kTileW, cvt::kTileH, 1);
+  if (rc != FOD_OK) return rc;
+  const long ktot = (long)prm.taps * cin_pad;
+  rc = make_matrix_map(&prm.whi_map, packed, cout, ktot, cvt::kChunk, prm.nhalf);
+  if (rc != FOD_OK) return rc;
+  rc = make_matrix_map(&prm.wlo_map, packed + (size_t)cout * ktot, cout, ktot, cvt::kChunk, prm.nhalf);
+  if (rc != FOD_OK) return rc;
+  int dev = 0, sms = 0;
+  FOD_CUDA_CALL(cudaGetDevice(&dev));
+  FOD_CUDA_CALL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int max_pairs = sms / 2 > 0 ? sms / 2 : 1;
+  prm.num_pairs = prm.pair_units < max_pairs ? prm.pair_units : max_pairs;
+  FOD_CUDA_CALL(cudaFuncSetAttribute(cvt::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cvt::kSmemAlloc));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * prm.num_pairs);
+  cfg.blockDim = dim3(cvt::kThreads);
+  cfg.dynamicSmemBytes = cvt::kSmemAlloc;
+  cfg.stream = as_stream(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, cvt::conv_tc_kernel, prm);
+  if (e != cudaSuccess) {
+    set_error("fod_conv2d_nhwc: launch failed: %s", cudaGetErrorString(e));
+    return FOD_ERR_CUDA;
+  }
+  return FOD_OK;
+}

@@ -365,41 +365,49 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
     }
   } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
       const uint32_t idesc = idesc_tf32(256, 128);
       const uint64_t bhi0 = smem_desc_k_sw128(sbase + kOffBHi);
       const uint64_t blo0 = smem_desc_k_sw128(sbase + kOffBLo);
-      // The issuing thread is throttled to the tensor pipe's rate (its queue is only an MMA or two deep) and an
-      // mbarrier wait costs a few hundred cycles even when the phase completed long ago, so waiting here would
-      // starve the pipe between sub-chunks.  A watcher thread (warp kWarpAlloc) does all the waiting and publishes
-      // the number of sub-chunks whose operands are in place through one shared-memory word.
+      // A watcher thread (warp kWarpAlloc) does all the barrier waiting and publishes the number of sub-chunks whose
+      // operands are in place through one shared-memory word; this warp only polls that word.  The whole warp runs
+      // the loop converged and one elected lane issues, so that every tcgen05.mma operand is a warp-uniform value
+      // in a uniform register (inside an `if (lane == 0)` region ptxas wraps each MMA in a broadcast-and-retry loop
+      // whose latency exceeds the 64 cycles of the MMA itself).
       int n_iter = 0;
       for (int i = 0; iter_valid(i); ++i) ++n_iter;
       const uint32_t total = (uint32_t)n_iter * kNumSubs;
       const uint32_t flag = sbase + kOffFlag;
       uint32_t upto = 0;
       for (uint32_t g = 0; g < total; ++g) {
-        while (upto <= g) asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(upto) : "r"(flag) : "memory");
+        while (upto <= g) {
+          uint32_t v;
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(flag) : "memory");
+          upto = __shfl_sync(0xffffffffu, v, 0);
+        }
         tc_fence_after();
         const int sub = g % kNumSubs, s = g % kAStages;
         const int as_ = (g / kNumSubs) % kAccStages;
         const uint32_t d = tmem_base + kColAcc + as_ * 128;
         const uint32_t a0 = tmem_base + kColA + s * kAStageCols;
+        if (elect_one()) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+          for (int half = 0; half < 2; ++half) {
 #pragma unroll
-          for (int ks = 0; ks < kSub / 8; ++ks) {
-            const uint32_t ah = a0 + half * 2 * kSub + ks * 8, al = ah + kSub;
-            const uint64_t boff =
-                (uint64_t)(((half * 4 + (sub >> 1)) * kBChunkBytes + (sub & 1) * kSub * 4 + ks * 32) >> 4);
-            const uint32_t acc = (sub | half | ks) ? 1u : 0u;
-            mma_tf32_ts<2>(d, ah, bhi0 + boff, idesc, acc);
-            mma_tf32_ts<2>(d, al, bhi0 + boff, idesc, 1u);
-            mma_tf32_ts<2>(d, ah, blo0 + boff, idesc, 1u);
+            for (int ks = 0; ks < kSub / 8; ++ks) {
+              const uint32_t ah = a0 + half * 2 * kSub + ks * 8, al = ah + kSub;
+              const uint64_t boff =
+                  (uint64_t)(((half * 4 + (sub >> 1)) * kBChunkBytes + (sub & 1) * kSub * 4 + ks * 32) >> 4);
+              const uint32_t acc = (sub | half | ks) ? 1u : 0u;
+              mma_tf32_ts<2>(d, ah, bhi0 + boff, idesc, acc);
+              mma_tf32_ts<2>(d, al, bhi0 + boff, idesc, 1u);
+              mma_tf32_ts<2>(d, ah, blo0 + boff, idesc, 1u);
+            }
           }
+          mma_commit_pair(a_empty(s), 3);
+          if (sub == kNumSubs - 1) mma_commit_pair(acc_full(as_), 3);
         }
-        mma_commit_pair(a_empty(s), 3);
-        if (sub == kNumSubs - 1) mma_commit_pair(acc_full(as_), 3);
+        __syncwarp();
       }
     }
   } else if (warp == kWarpAlloc) {

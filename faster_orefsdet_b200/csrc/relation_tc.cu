@@ -223,26 +223,25 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
       }
     }
   } else if (warp == kWarpMma) {
-    if (rank == 0 && lane == 0) {
+    if (rank == 0) {
       const uint32_t idesc = idesc_tf32(256, 128);
-      // The issuing thread is throttled to the tensor pipe's rate (its queue is only an MMA or two deep), and an
-      // mbarrier wait costs a few hundred cycles even when the phase has long completed: waiting here would starve
-      // the pipe between chunks.  A helper thread (warp kWarpAlloc) does all the waiting and publishes the number of
-      // chunks whose operands are in place through one shared-memory word; this thread only polls that word.
+      // A helper thread (warp kWarpAlloc) does all the barrier waiting and publishes the number of chunks whose
+      // operands are in place through one shared-memory word; this warp only polls that word.  The whole warp runs
+      // the loop converged and one elected lane issues, so that every tcgen05.mma operand is a warp-uniform value
+      // in a uniform register (inside an `if (lane == 0)` region ptxas wraps each MMA in a broadcast-and-retry loop
+      // whose latency exceeds the 64 cycles of the MMA itself).
       int n_iter = 0;
       for (int i = 0; in_range(i); ++i) ++n_iter;
       const uint32_t total = (uint32_t)n_iter * kNumChunks;
       const uint32_t flag = sbase + kOffFlag;
       uint32_t upto = 0;
       for (uint32_t g = 0; g < total; ++g) {
-#if FOD_EXP == 3
-        long long t0 = clock64();
-#endif
-        while (upto <= g) asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(upto) : "r"(flag) : "memory");
+        while (upto <= g) {
+          uint32_t v;
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(flag) : "memory");
+          upto = __shfl_sync(0xffffffffu, v, 0);
+        }
         tc_fence_after();
-#if FOD_EXP == 3
-        long long t2 = clock64();
-#endif
         const int s = g % kStages;
         const uint32_t gp = g / kChunksPerPart;
         const int as_ = gp % kAccStages;
@@ -251,23 +250,19 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
         const uint32_t a0 = tmem_base + kColA + s * 64;
         const uint64_t bhi = smem_desc_k_sw128(sbase + kOffB + s * kBBytes);
         const uint64_t blo = smem_desc_k_sw128(sbase + kOffB + s * kBBytes + kBPlaneBytes);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t ah = a0 + ks * 8, al = ah + 32;
-          const uint64_t boff = (uint64_t)((ks * 32) >> 4);
-          mma_tf32_ts<2>(d, ah, bhi + boff, idesc, (!first || ks) ? 1u : 0u);
-          mma_tf32_ts<2>(d, al, bhi + boff, idesc, 1u);
-          mma_tf32_ts<2>(d, ah, blo + boff, idesc, 1u);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t ah = a0 + ks * 8, al = ah + 32;
+            const uint64_t boff = (uint64_t)((ks * 32) >> 4);
+            mma_tf32_ts<2>(d, ah, bhi + boff, idesc, (!first || ks) ? 1u : 0u);
+            mma_tf32_ts<2>(d, al, bhi + boff, idesc, 1u);
+            mma_tf32_ts<2>(d, ah, blo + boff, idesc, 1u);
+          }
+          mma_commit_pair(st_free(s), 3);
+          if (last) mma_commit_pair(acc_full(as_), 3);
         }
-        mma_commit_pair(st_free(s), 3);
-        if (last) mma_commit_pair(acc_full(as_), 3);
-#if FOD_EXP == 3
-        if (pair == 0 && g >= 128 && g < 128 + 32 && P.deltas) {
-          long long t3 = clock64();
-          long long* dbg = reinterpret_cast<long long*>(P.deltas + 256 * 4) + (g - 128) * 4;  // unused rows 256..319
-          dbg[0] = t0; dbg[1] = t2 - t0; dbg[2] = upto - g; dbg[3] = t3 - t2;
-        }
-#endif
+        __syncwarp();
       }
     }
   } else if (warp == kWarpAlloc) {

@@ -300,3 +300,48 @@ def batched_nms(boxes: Tensor, scores: Tensor, idxs: Optional[Tensor], iou_thres
     _lib.check(_lib.lib().fod_batched_nms(_ptr(boxes), _ptr(scores), _ptr(idxs), n, float(iou_threshold), _ptr(keep),
                                           _ptr(cnt), _stream()), "fod_batched_nms")
     return keep[: int(cnt.item())]
+
+
+# --------------------------------------------------------------------------- H0 (convolutions)
+def _pixel_stride(t: Tensor, name: str) -> int:
+    """Pixel stride (in floats) of an [N,C,H,W]-shaped NHWC view; C may be a slice of a wider buffer."""
+    _chk(t, torch.float32, name)
+    if t.dim() != 4:
+        raise _lib.FodError(f"{name}: expected [N,C,H,W]")
+    n, c, h, w = t.shape
+    sn, sc, sh, sw = t.stride()
+    ps = sw if w > 1 else (sh if h > 1 else c)
+    ok = (c == 1 or sc == 1) and (w == 1 or sw == ps) and (h == 1 or sh == w * ps) and (n == 1 or sn == h * w * ps) and ps >= c
+    if not ok:
+        raise _lib.FodError(f"{name}: not an NHWC (channels_last) view: shape {tuple(t.shape)} stride {t.stride()}")
+    return int(ps)
+
+
+def conv2d_pack(weight: Tensor) -> Tensor:
+    """PyTorch conv weight [Cout,Cin,k,k] -> tf32 hi/lo planes for conv2d_nhwc (fod_conv2d_pack_weights)."""
+    weight = _chk(weight, torch.float32, "weight").contiguous()
+    cout, cin, k, k2 = weight.shape
+    if k != k2 or k not in (1, 3):
+        raise _lib.FodError("conv2d_pack: 1x1 or 3x3 kernels")
+    L = _lib.lib()
+    packed = torch.empty((L.fod_conv2d_packed_floats(cout, cin, k),), dtype=torch.float32, device=weight.device)
+    _lib.check(L.fod_conv2d_pack_weights(_ptr(weight), cout, cin, k, _ptr(packed), _stream()), "fod_conv2d_pack_weights")
+    return packed
+
+
+def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ksize: int, relu: bool = False,
+                out: Optional[Tensor] = None) -> Tensor:
+    """Stride-1 'same' convolution on the tensor cores (3xTF32), bias + optional ReLU fused.
+    x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise."""
+    ps_x = _pixel_stride(x, "x")
+    n, cin, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+    ps_y = _pixel_stride(out, "out")
+    if tuple(out.shape) != (n, cout, h, w):
+        raise _lib.FodError("conv2d_nhwc: bad output shape")
+    if bias is not None:
+        bias = _chk(bias, torch.float32, "bias").contiguous()
+    _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(packed), _ptr(bias), cout, ksize, 1, int(relu),
+                                          _ptr(out), ps_y, _stream()), "fod_conv2d_nhwc")
+    return out

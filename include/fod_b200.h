@@ -205,6 +205,28 @@ int fod_final_detect(const float* det_boxes, const float* det_scores, const int3
 int fod_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int n, double iou_thresh,
                     int64_t* keep, int32_t* keep_count, fod_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * H0  3x3 / 1x1 stride-1 convolution over NHWC fp32 maps (zero padding ksize/2),
+ * bias and optional ReLU fused; tcgen05 tensor cores with 3xTF32 operand splitting
+ * (fp32 accuracy, ~1e-6 relative).  Replaces the F.conv2d -> cuDNN calls of
+ * CenterNetHead.forward (CenterNet2/centernet/modeling/dense_heads/centernet_head.py:
+ * 141-161: bbox_tower conv, agn_hm, bbox_pred) and of the modules that hand maps to
+ * the head (d2!/modeling/backbone/vovnet.py:205-489 conv3x3/conv1x1 + FrozenBN folded,
+ * d2!/modeling/backbone/fpn.py:113-155 lateral / output convs).
+ *   x      : [N][H][W] pixels of x_pixel_stride floats, the first cin of them are read
+ *            (a channel slice of a wider NHWC buffer is a valid input)
+ *   packed : fod_conv2d_pack_weights output (fod_conv2d_packed_floats floats)
+ *   bias   : [cout] or NULL
+ *   y      : [N][H][W] pixels of y_pixel_stride floats, the first cout are written
+ * cin, cout and both pixel strides must be multiples of 4; pointers 16-byte aligned.
+ */
+size_t fod_conv2d_packed_floats(int cout, int cin, int ksize);
+/* w_oihw : [cout][cin][ksize][ksize] (PyTorch conv weight) -> tf32 hi / lo planes [cout][ky][kx][cin_pad] */
+int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, float* packed, fod_stream_t stream);
+int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* packed,
+                    const float* bias, int cout, int ksize, int stride, int relu, float* y, long y_pixel_stride,
+                    fod_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,80 @@
+"""GPU parity of the tensor-core convolution (fod_conv2d_nhwc) against PyTorch's fp32 CPU convolution
+(a floating-point kernel: the fp32 torch op is the reference; tolerance 2e-5 relative to the output scale,
+well inside the 1e-4 of north_star)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from faster_orefsdet_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ref(x, w, b, relu):
+    y = F.conv2d(x.double(), w.double(), None if b is None else b.double(), padding=w.shape[-1] // 2)
+    return (y.relu() if relu else y).float()
+
+
+def _check(y, ref, what):
+    scale = float(ref.abs().max()) + 1e-12
+    err = float((y.cpu() - ref).abs().max())
+    assert err <= 2e-5 * scale, f"{what}: max abs err {err:.3e} vs output scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,relu", [
+    (2, 20, 20, 128, 128, 3, True),     # tower conv on p5 (partial tiles in both directions)
+    (1, 40, 40, 128, 128, 3, False),
+    (2, 16, 32, 64, 64, 3, True),       # stem-like
+    (1, 24, 40, 128, 64, 3, True),
+    (2, 20, 24, 112, 80, 3, True),      # stage 3: Cin not a multiple of 32, Cout not a multiple of 32
+    (1, 20, 20, 256, 96, 3, True),
+    (1, 10, 10, 384, 112, 3, True),
+    (1, 40, 40, 320, 112, 1, True),     # OSA concat 1x1
+    (1, 20, 20, 352, 256, 1, True),     # two output-channel groups
+    (1, 10, 12, 720, 512, 1, True),     # four groups, K tail chunk
+    (3, 8, 16, 128, 128, 1, False),     # exactly one tile per image, odd tile count
+    (1, 3, 5, 64, 128, 3, True),        # map smaller than a tile
+    (1, 20, 20, 128, 8, 3, False),      # narrow output (agn_hm + bbox_pred padded to 8)
+])
+def test_conv2d_nhwc_matches_fp32(n, h, w, cin, cout, k, relu):
+    x = synth.tensor((n, cin, h, w), 100 + cin + cout, -1.0, 1.0)
+    wt = synth.tensor((cout, cin, k, k), 200 + cin + cout, -1.0, 1.0) / (cin * k * k) ** 0.5
+    b = synth.tensor((cout,), 300 + cout, -0.5, 0.5)
+    ref = _ref(x, wt, b, relu)
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    packed = ops.conv2d_pack(wt.to(DEV))
+    y = ops.conv2d_nhwc(xg, packed, b.to(DEV), cout, k, relu)
+    torch.cuda.synchronize()
+    assert y.shape == ref.shape
+    _check(y, ref, f"conv {cin}->{cout} k{k} {h}x{w}")
+
+
+def test_conv2d_nhwc_channel_slices_concat_in_place():
+    """Input and output as channel slices of wider NHWC buffers (the OSA concat is never materialised by a copy)."""
+    n, h, w = 2, 24, 20
+    buf = torch.zeros((n, h, w, 64 + 80 + 80), device=DEV).permute(0, 3, 1, 2)
+    x = synth.tensor((n, 64, h, w), 7, -1.0, 1.0)
+    w1 = synth.tensor((80, 64, 3, 3), 8, -0.05, 0.05)
+    w2 = synth.tensor((80, 80, 3, 3), 9, -0.05, 0.05)
+    buf[:, :64] = x.to(DEV)
+    ops.conv2d_nhwc(buf[:, :64], ops.conv2d_pack(w1.to(DEV)), None, 80, 3, True, out=buf[:, 64:144])
+    ops.conv2d_nhwc(buf[:, 64:144], ops.conv2d_pack(w2.to(DEV)), None, 80, 3, True, out=buf[:, 144:224])
+    torch.cuda.synchronize()
+    r1 = _ref(x, w1, None, True)
+    r2 = _ref(r1, w2, None, True)
+    _check(buf[:, :64], x, "input slice untouched")
+    _check(buf[:, 64:144], r1, "first slice")
+    _check(buf[:, 144:224], r2, "second slice")
+
+
+def test_conv2d_nhwc_no_bias_accumulation_bias_free():
+    """Long K (3x3, 384 channels = 108 chunks = 14 partial sums) with same-sign products: the tensor core's
+    round-toward-zero accumulation would show as a one-sided error without the partial-sum scheme."""
+    x = synth.tensor((1, 384, 16, 16), 21, 0.5, 1.0)
+    wt = synth.tensor((112, 384, 3, 3), 22, 0.5, 1.0) / 3456.0
+    ref = _ref(x, wt, None, False)
+    y = ops.conv2d_nhwc(x.to(DEV).contiguous(memory_format=torch.channels_last), ops.conv2d_pack(wt.to(DEV)), None, 112, 3)
+    rel = ((y.cpu() - ref) / ref)[:, :, 2:-2, 2:-2]
+    assert float(rel.abs().max()) < 5e-6, float(rel.abs().max())
+    assert abs(float(rel.mean())) < 4e-6, float(rel.mean())
