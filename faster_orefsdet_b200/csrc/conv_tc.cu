@@ -14,6 +14,8 @@
 //   * K = taps x Cin is streamed in 32-channel chunks.  The input tile plus its halo (zero-filled outside the image
 //     by TMA, which is the convolution's zero padding) is staged ONCE per 32-channel chunk into a 3-deep shared-memory
 //     ring and serves all ksize^2 taps: the shifted A operands are read from it, never re-fetched from L2.
+//     (Stride 2: a halo tile would be 17 x 33 pixels, so each tap's 8 x 16 pixels are fetched by their own TMA load
+//     with element strides (2, 2) instead: one ring stage per tap.)
 //   * 16 converter warps (one output pixel per lane = TMEM lane) read the tap-shifted 128-byte row of their pixel
 //     (conflict-free LDS.128 thanks to the TMA swizzle), split it into tf32 hi / lo and write it into TENSOR MEMORY;
 //     the MMA (Ahi.Bhi + Alo.Bhi + Ahi.Blo) reads A from tensor memory and only the weights from shared memory.
@@ -37,7 +39,6 @@ constexpr int kTileH = 8, kTileW = 16;
 constexpr int kChunk = 32;
 constexpr int kQStages = 3, kStages = 4, kAccStages = 2;
 constexpr int kPartChunks = 8;
-constexpr int kMaxHaloPx = (2 * kTileH + 1) * (2 * kTileW + 1);            // stride 2, 3x3: 17 x 33
 constexpr uint32_t kQStageStrideS1 = ((kTileH + 2) * (kTileW + 2) * 128 + 1023) / 1024 * 1024;   // 23552
 constexpr uint32_t kBPlaneMax = 64 * 128;                                   // 64 rows (half of a 128 group) x 128 B
 constexpr uint32_t kBStageBytes = 2 * kBPlaneMax;                           // hi + lo
@@ -81,7 +82,7 @@ struct Params {
   CUtensorMap wlo_map;
   const float* bias;    // [Cout] or null
   int tiles_x, tiles_per_img, tiles_total;
-  int ksize, taps, stride, halo_w;
+  int ksize, taps, stride, halo_w, per_tap;  // per_tap: one input-ring stage per (channel chunk, tap) (stride 2)
   int cin_chunks, chunks, parts, chunks_per_part;
   int n_groups, n_group, nhalf, ncol32, cout;
   int relu, num_pairs, pair_units;
@@ -157,13 +158,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int n = t / P.tiles_per_img, tt = t - n * P.tiles_per_img;
         const int ty = tt / P.tiles_x, tx = tt - ty * P.tiles_x;
         const int x0 = tx * kTileW * P.stride - pad, y0 = ty * kTileH * P.stride - pad;
-        for (int cc = 0; cc < cin_chunks; ++cc, ++g) {
-          const int s = g % kQStages;
-          const uint32_t ph = (g / kQStages) & 1;
-          mbar_wait(q_empty(s), ph ^ 1);
-          mbar_arrive_expect_tx(q_full(s), P.q_stage_bytes);
-          tma_load_4d(sbase + kOffQ + s * P.q_stage_stride, &P.in_map, q_full(s), cc * kChunk, x0, y0, n);
-        }
+        const int loads = P.per_tap ? taps : 1;
+        for (int cc = 0; cc < cin_chunks; ++cc)
+          for (int tap = 0; tap < loads; ++tap, ++g) {
+            const int s = g % kQStages;
+            const uint32_t ph = (g / kQStages) & 1;
+            const int dy = tap / P.ksize, dx = tap - dy * P.ksize;   // (0, 0) when the halo tile serves every tap
+            mbar_wait(q_empty(s), ph ^ 1);
+            mbar_arrive_expect_tx(q_full(s), P.q_stage_bytes);
+            tma_load_4d(sbase + kOffQ + s * P.q_stage_stride, &P.in_map, q_full(s), cc * kChunk, x0 + dx, y0 + dy, n);
+          }
       }
     }
   } else if (warp == kWarpTmaB) {
@@ -344,21 +348,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int cw = warp - kWarpConv0;
     const int qd = cw & 3, half = (cw >> 2) & 1, set = cw >> 3;
     const int m = qd * 32 + lane;
-    const int py = (m >> 4) * P.stride, px = (m & 15) * P.stride;  // position of this pixel's tap (0,0) in the halo tile
+    const int py = m >> 4, px = m & 15;  // position of this pixel's tap (0,0) in the halo tile
+    const bool per_tap = P.per_tap != 0;
     const uint32_t ready_leader = map_to_cta(ready(0), 0);
     const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColA + half * 16;
     const int ksz = P.ksize, hw = P.halo_w;
     uint32_t g = 0, gq = 0;
     for (int i = 0; in_range(i); ++i) {
-      for (int cc = 0; cc < cin_chunks; ++cc, ++gq) {
-        const int qs = gq % kQStages;
-        mbar_wait(q_full(qs), (gq / kQStages) & 1);
-        const uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
+      for (int cc = 0; cc < cin_chunks; ++cc) {
+        int qs = gq % kQStages;
+        if (!per_tap) mbar_wait(q_full(qs), (gq / kQStages) & 1);
+        uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
         int dy = 0, dx = 0;
         for (int tap = 0; tap < taps; ++tap, ++g) {
+          if (per_tap) {  // this tap's own 8 x 16 tile: every warp passes the barrier pair, the owner set reads
+            qs = gq % kQStages;
+            mbar_wait(q_full(qs), (gq / kQStages) & 1);
+            qt = sbase + kOffQ + qs * P.q_stage_stride;
+          }
           if ((int)(g & 1) == set) {
             if (cw == 0 || cw == 8) DBG_STAMP(3, g, 0);
-            const int r = (py + dy) * hw + px + dx;
+            const int r = per_tap ? m : (py + dy) * hw + px + dx;
             const uint32_t at = qt + (uint32_t)r * 128u;
             const uint32_t key = (uint32_t)(r & 7);
             float4 x[4];
@@ -386,9 +396,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (cw == 0 || cw == 8) DBG_STAMP(3, g, 3);
           }
           if (++dx == ksz) { dx = 0; ++dy; }
+          if (per_tap) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_empty(qs));
+            ++gq;
+          }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(q_empty(qs));
+        if (!per_tap) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(q_empty(qs));
+          ++gq;
+        }
       }
     }
   }
@@ -469,7 +487,7 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   FOD_REQUIRE(x && packed && y, "fod_conv2d_nhwc: null pointer");
   FOD_REQUIRE(n >= 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "fod_conv2d_nhwc: bad sizes");
   FOD_REQUIRE(ksize == 1 || ksize == 3, "fod_conv2d_nhwc: ksize must be 1 or 3");
-  FOD_REQUIRE(stride == 1, "fod_conv2d_nhwc: only stride 1 is built");
+  FOD_REQUIRE(stride == 1 || (stride == 2 && ksize == 3), "fod_conv2d_nhwc: stride 1, or stride 2 with a 3x3 kernel");
   FOD_REQUIRE(cin % 4 == 0 && cout % 4 == 0 && x_pixel_stride % 4 == 0 && y_pixel_stride % 4 == 0 &&
                   x_pixel_stride >= cin && y_pixel_stride >= cout,
               "fod_conv2d_nhwc: channel counts and pixel strides must be multiples of 4 (16-byte TMA granularity)");
@@ -479,9 +497,13 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   const int ho = (h + 2 * pad - ksize) / stride + 1, wo = (w + 2 * pad - ksize) / stride + 1;
   cvt::Params prm;
   memset(&prm, 0, sizeof(prm));
-  const int halo_w = (cvt::kTileW - 1) * stride + ksize, halo_h = (cvt::kTileH - 1) * stride + ksize;
-  prm.halo_w = halo_w;
-  prm.q_stage_bytes = (uint32_t)(halo_w * halo_h * 128);
+  const int per_tap = stride != 1;
+  // stride 1: tile + halo; stride 2: every second pixel of a (2*16-1) x (2*8-1) window = the 16 x 8 pixels of one tap
+  const int halo_w = per_tap ? (cvt::kTileW - 1) * stride + 1 : cvt::kTileW + ksize - 1;
+  const int halo_h = per_tap ? (cvt::kTileH - 1) * stride + 1 : cvt::kTileH + ksize - 1;
+  prm.per_tap = per_tap;
+  prm.halo_w = per_tap ? cvt::kTileW : halo_w;
+  prm.q_stage_bytes = per_tap ? (uint32_t)(cvt::kTileW * cvt::kTileH * 128) : (uint32_t)(halo_w * halo_h * 128);
   prm.q_stage_stride = (prm.q_stage_bytes + 1023) / 1024 * 1024;
   FOD_REQUIRE(cvt::kQStages * prm.q_stage_stride <= cvt::kOffB, "fod_conv2d_nhwc: halo tile does not fit the input ring");
   const int cin_pad = (cin + 31) / 32 * 32;
@@ -507,7 +529,7 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   FOD_REQUIRE(tiles * prm.n_groups < (1L << 30), "fod_conv2d_nhwc: too many tiles");
   prm.tiles_total = (int)tiles;
   prm.pair_units = (int)((tiles + 1) / 2) * prm.n_groups;
-  int rc = cvt::make_nhwc_map_strided(&prm.in_map, x, n, h, w, cin, x_pixel_stride, cvt::kChunk, halo_w, halo_h, 1);
+  int rc = cvt::make_nhwc_map_strided(&prm.in_map, x, n, h, w, cin, x_pixel_stride, cvt::kChunk, halo_w, halo_h, stride);
   if (rc != FOD_OK) return rc;
   rc = cvt::make_nhwc_map_strided(&prm.out_map, y, n, ho, wo, cout, y_pixel_stride, cvt::kChunk, cvt::kTileW, cvt::kTileH, 1);
   if (rc != FOD_OK) return rc;

@@ -1,0 +1,110 @@
+// Memory-bound glue between the tensor-core convolutions of the feature extractor (d2!/modeling/backbone/vovnet.py):
+//   * fod_stem_patches   - im2col of the 3-channel stem convolution (3x3, stride 2, pad 1, vovnet.py stem_1): each output
+//                          pixel gets its 27 input values (+5 zeros) as one 128-byte row, so stem_1 runs as a 1x1
+//                          tensor-core convolution with K = 32 instead of a 3-channel cuDNN kernel.
+//   * fod_maxpool3x3s2   - nn.MaxPool2d(3, stride 2, ceil_mode=True) of the OSA stages (vovnet.py _OSA_stage) over NHWC
+//                          maps, optionally multiplied by the eSE gate of the producing stage (x * hsigmoid(fc(avg(x))),
+//                          vovnet.py eSEModule; the gate is >= 0, so it commutes with the max), written straight into a
+//                          channel slice of the next stage's concat buffer.
+// One float4 (4 channels) per thread, coalesced 128-bit accesses; the 9-fold window overlap is served by L1/L2.
+#include "common.cuh"
+
+namespace fod {
+namespace glue {
+
+constexpr int kThreads = 256;
+
+// x: [N][H][W][3] fp32 (normalised image, NHWC) -> p: [N][Ho][Wo][32], k = (ky*3 + kx)*3 + c, rows 27..31 zero
+__global__ void __launch_bounds__(kThreads) stem_patches_kernel(const float* __restrict__ x, int H, int W, int Ho, int Wo,
+                                                                float* __restrict__ p, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+    const int q = (int)(i & 7);  // float4 index inside the 32-wide row
+    const size_t pix = i >> 3;
+    const int ox = (int)(pix % Wo);
+    const size_t r = pix / Wo;
+    const int oy = (int)(r % Ho);
+    const size_t n = r / Ho;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = q * 4 + j;
+      float val = 0.f;
+      if (k < 27) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(x + ((n * H + iy) * (size_t)W + ix) * 3 + c);
+      }
+      v[j] = val;
+    }
+    *reinterpret_cast<float4*>(p + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// x: [N][H][W] pixels of xs floats (first C used), gate: [N][C] or null -> y: [N][Ho][Wo] pixels of ys floats
+__global__ void __launch_bounds__(kThreads) maxpool_kernel(const float* __restrict__ x, long xs, int H, int W, int C,
+                                                           const float* __restrict__ gate, float* __restrict__ y, long ys,
+                                                           int Ho, int Wo, size_t total) {
+  const int c4n = C >> 2;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+    const int c4 = (int)(i % c4n);
+    const size_t pix = i / c4n;
+    const int ox = (int)(pix % Wo);
+    const size_t r = pix / Wo;
+    const int oy = (int)(r % Ho);
+    const size_t n = r / Ho;
+    const int y0 = 2 * oy, x0 = 2 * ox;
+    const int y1 = min(y0 + 3, H), x1 = min(x0 + 3, W);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int iy = y0; iy < y1; ++iy)
+      for (int ix = x0; ix < x1; ++ix) {
+        const float4 v = ldg4(x + ((n * H + iy) * (size_t)W + ix) * xs + c4 * 4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    if (gate) {
+      const float4 g = ldg4(gate + n * C + c4 * 4);
+      m.x *= g.x; m.y *= g.y; m.z *= g.z; m.w *= g.w;
+    }
+    *reinterpret_cast<float4*>(y + pix * ys + c4 * 4) = m;
+  }
+}
+
+}  // namespace glue
+}  // namespace fod
+
+using namespace fod;
+
+static unsigned grid_for(size_t total, int threads) {
+  size_t b = (total + threads - 1) / threads;
+  const size_t cap = 148 * 32;
+  return (unsigned)(b < cap ? (b ? b : 1) : cap);
+}
+
+extern "C" int fod_stem_patches(const float* x, int n, int h, int w, float* patches, fod_stream_t stream) {
+  FOD_REQUIRE(x && patches, "fod_stem_patches: null pointer");
+  FOD_REQUIRE(n >= 0 && h > 0 && w > 0, "fod_stem_patches: bad sizes");
+  FOD_REQUIRE(((uintptr_t)patches & 15) == 0, "fod_stem_patches: output must be 16-byte aligned");
+  if (n == 0) return FOD_OK;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const size_t total = (size_t)n * ho * wo * 8;
+  glue::stem_patches_kernel<<<grid_for(total, glue::kThreads), glue::kThreads, 0, as_stream(stream)>>>(x, h, w, ho, wo, patches,
+                                                                                                    total);
+  FOD_CUDA_LAUNCH_CHECK("fod_stem_patches");
+  return FOD_OK;
+}
+
+extern "C" int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate,
+                                     float* y, long y_pixel_stride, fod_stream_t stream) {
+  FOD_REQUIRE(x && y, "fod_maxpool3x3s2_nhwc: null pointer");
+  FOD_REQUIRE(n >= 0 && h >= 3 && w >= 3 && c > 0 && c % 4 == 0 && x_pixel_stride % 4 == 0 && y_pixel_stride % 4 == 0 &&
+                  x_pixel_stride >= c && y_pixel_stride >= c, "fod_maxpool3x3s2_nhwc: bad sizes (channels / strides multiples of 4)");
+  FOD_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gate) & 15) == 0, "fod_maxpool3x3s2_nhwc: pointers must be 16-byte aligned");
+  if (n == 0) return FOD_OK;
+  // ceil_mode output size of nn.MaxPool2d(3, 2): ceil((H - 3) / 2) + 1 (the last window always starts inside the map)
+  const int ho = (h - 3 + 1) / 2 + 1, wo = (w - 3 + 1) / 2 + 1;
+  const size_t total = (size_t)n * ho * wo * (c / 4);
+  glue::maxpool_kernel<<<grid_for(total, glue::kThreads), glue::kThreads, 0, as_stream(stream)>>>(
+      x, x_pixel_stride, h, w, c, gate, y, y_pixel_stride, ho, wo, total);
+  FOD_CUDA_LAUNCH_CHECK("fod_maxpool3x3s2_nhwc");
+  return FOD_OK;
+}

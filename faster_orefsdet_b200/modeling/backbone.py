@@ -15,7 +15,9 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import ops
 from ..compat import BACKBONE_REGISTRY, ShapeSpec
+from . import tcconv
 
 _STAGE_SPECS = {
     # name: (stem, stage_conv_ch, stage_out_ch, layers_per_block, blocks_per_stage)   vovnet.py:50-97
@@ -72,7 +74,10 @@ class ConvNormReLUSeq(nn.Sequential):
             return x
         for i in range(0, len(mods), 3):
             conv, norm, _ = mods[i:i + 3]
-            w, b = self._folded(i, conv, norm)
+            if tcconv.supported(conv, x):          # tcgen05 3xTF32 kernel (csrc/conv_tc.cu)
+                x = tcconv.conv(x, conv, norm, relu=True)
+                continue
+            w, b = self._folded(i, conv, norm)     # stride-2 / 3-channel stem convolutions, CPU tensors: cuDNN / ATen
             x = F.relu_(F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups))
         return x
 
@@ -91,9 +96,12 @@ class _ESE(nn.Module):
         self.avg_pool = nn.AdaptiveAvgPool2d(1)
         self.fc = nn.Conv2d(channel, channel, kernel_size=1, padding=0)
 
+    def gate(self, x):
+        """hsigmoid(fc(avg(x))) as [N, C, 1, 1]"""
+        return F.relu6(self.fc(self.avg_pool(x)) + 3.0) / 6.0
+
     def forward(self, x):
-        w = self.fc(self.avg_pool(x))
-        return x * (F.relu6(w + 3.0) / 6.0)
+        return x * self.gate(x)
 
 
 class _OSAModule(nn.Module):
@@ -109,6 +117,9 @@ class _OSAModule(nn.Module):
         self.ese = _ESE(concat_ch)
 
     def forward(self, x):
+        if not self.training and all(tcconv.supported(layer[0], x) for layer in self.layers):
+            y = self.ese(self.concat(self._layers_in_place(x)))
+            return y + x if self.identity else y
         outs = [x]
         y = x
         for layer in self.layers:
@@ -116,6 +127,37 @@ class _OSAModule(nn.Module):
             outs.append(y)
         y = self.ese(self.concat(torch.cat(outs, dim=1)))
         return y + x if self.identity else y
+
+    @property
+    def concat_channels(self) -> int:
+        return self.layers[0][0].in_channels + sum(layer[0].out_channels for layer in self.layers)
+
+    def new_buffer(self, n, h, w, device):
+        """NHWC buffer [x | y0 | y1 | y2] of this module; the producer of x writes its first slice."""
+        buf = torch.empty((n, h, w, self.concat_channels), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
+        return buf, buf[:, :self.layers[0][0].in_channels]
+
+    def _layers_in_place(self, x, buf=None):
+        """The 3x3 layers write their outputs straight into channel slices of one NHWC buffer
+        [x | y0 | y1 | y2] and read their inputs from it: torch.cat never runs."""
+        n, c, h, w = x.shape
+        if buf is None:
+            buf, first = self.new_buffer(n, h, w, x.device)
+            first.copy_(x)
+        src, off = buf[:, :c], c
+        for layer in self.layers:
+            cw = layer[0].out_channels
+            dst = buf[:, off:off + cw]
+            tcconv.conv(src, layer[0], layer[1], relu=True, out=dst)
+            src, off = dst, off + cw
+        return buf
+
+    def forward_buffer(self, buf):
+        """Tensor-core path with x already sitting in the first slice of ``buf``: returns the concat-conv output
+        BEFORE the eSE gate and the gate [N,C,1,1] (the consumer fuses the multiplication)."""
+        c = self.layers[0][0].in_channels
+        y = self.concat(self._layers_in_place(buf[:, :c], buf))
+        return y, self.ese.gate(y)
 
 
 class _OSAStage(nn.Sequential):
@@ -154,7 +196,54 @@ class VoVNet(nn.Module):
                 stride *= 2
                 self._out_feature_strides[name] = stride
 
+    def _tc_path(self, x) -> bool:
+        return (tcconv.ENABLED and x.is_cuda and x.dtype == torch.float32 and not self.training and x.shape[1] == 3
+                and all(len([m for m in getattr(self, n) if isinstance(m, _OSAModule)]) == 1 for n in self.stage_names))
+
+    def _stem1_packed(self):
+        """stem_1 (3x3, stride 2, 3 input channels) as a 1x1 convolution over 32-wide im2col rows (ops.stem_patches)."""
+        conv, norm = self.stem[0], self.stem[1]
+        key = tcconv._versions(conv.weight, *norm.buffers())
+        hit = getattr(self, "_stem1_cache", None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                w, b = tcconv.folded(conv, norm)
+                w = w.permute(0, 2, 3, 1).reshape(w.shape[0], 27)                      # k = (ky*3 + kx)*3 + c
+                w = torch.cat((w, w.new_zeros(w.shape[0], 5)), 1).reshape(-1, 32, 1, 1).contiguous()
+                hit = (key, ops.conv2d_pack(w), b.detach().float().contiguous())
+            self._stem1_cache = hit
+        return hit[1], hit[2]
+
+    def _forward_tc(self, x):
+        """Inference on CUDA: every convolution on the tensor cores (csrc/conv_tc.cu), no torch.cat, no layout copies.
+        stem_3 and the stage poolings write straight into the first slice of the next stage's concat buffer; the eSE
+        gate of a stage is applied inside the pooling that consumes it (and materialised only for FPN inputs)."""
+        outputs = {}
+        n = x.shape[0]
+        pk, b = self._stem1_packed()
+        y = ops.conv2d_nhwc(ops.stem_patches(x), pk, b, self.stem[0].out_channels, 1, relu=True)
+        y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True)
+        mods = [[m for m in getattr(self, name) if isinstance(m, _OSAModule)][0] for name in self.stage_names]
+        h, w = (y.shape[2] - 1) // 2 + 1, (y.shape[3] - 1) // 2 + 1
+        buf, first = mods[0].new_buffer(n, h, w, x.device)
+        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=first)
+        if "stem" in self._out_features:
+            outputs["stem"] = first
+        for i, (name, mod) in enumerate(zip(self.stage_names, mods)):
+            y, gate = mod.forward_buffer(buf)
+            if name in self._out_features:
+                y = y.mul_(gate)
+                outputs[name] = y
+                gate = None
+            if i + 1 < len(mods):
+                h, w = (y.shape[2] - 2) // 2 + 1, (y.shape[3] - 2) // 2 + 1
+                buf, first = mods[i + 1].new_buffer(n, h, w, x.device)
+                ops.maxpool3x3s2_nhwc(y, gate, out=first)
+        return outputs
+
     def forward(self, x):
+        if self._tc_path(x):
+            return self._forward_tc(x)
         outputs = {}
         x = self.stem(x)
         if "stem" in self._out_features:
@@ -206,15 +295,19 @@ class FPN(nn.Module):
 
     def forward(self, x) -> Dict[str, torch.Tensor]:
         feats = self.bottom_up(x)
-        prev = self._laterals[0](feats[self.in_features[-1]])
-        results = [self._outputs[0](prev)]
+
+        def run(m, t):
+            return tcconv.conv(t, m) if tcconv.supported(m, t) else m(t)
+
+        prev = run(self._laterals[0], feats[self.in_features[-1]])
+        results = [run(self._outputs[0], prev)]
         for idx in range(1, len(self._laterals)):
             f = feats[self.in_features[-idx - 1]]
             top_down = F.interpolate(prev, scale_factor=2.0, mode="nearest")
-            prev = self._laterals[idx](f) + top_down
+            prev = run(self._laterals[idx], f) + top_down
             if self._fuse_type == "avg":
                 prev = prev / 2
-            results.insert(0, self._outputs[idx](prev))
+            results.insert(0, run(self._outputs[idx], prev))
         return dict(zip(self._out_features, results))
 
     def output_shape(self):

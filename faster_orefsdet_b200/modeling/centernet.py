@@ -22,6 +22,7 @@ from torch.nn import functional as F
 
 from .. import ops
 from ..compat import PROPOSAL_GENERATOR_REGISTRY, Boxes, Instances, ShapeSpec
+from . import tcconv
 
 
 class Scale(nn.Module):
@@ -68,11 +69,36 @@ class CenterNetHead(nn.Module):
     def forward(self, x: Sequence[torch.Tensor]):
         clss, bbox_reg, agn_hms = [], [], []
         for l, feature in enumerate(x):
-            t = self.bbox_tower(feature)
+            if tcconv.supported(self.agn_hm, feature):
+                hm, reg = self._level_tc(feature)
+            else:
+                t = self.bbox_tower(feature)
+                hm, reg = self.agn_hm(t), self.bbox_pred(t)
             clss.append(None)
-            agn_hms.append(self.agn_hm(t))
-            bbox_reg.append(F.relu(self.scales[l](self.bbox_pred(t))))
+            agn_hms.append(hm)
+            bbox_reg.append(F.relu(self.scales[l](reg)))
         return clss, bbox_reg, agn_hms
+
+    def _level_tc(self, t: torch.Tensor):
+        """Tower and output convolutions on the tensor cores (csrc/conv_tc.cu); agn_hm and bbox_pred read the same
+        tower output, so they run as ONE convolution with 1 + 4 (+3 zero) output channels."""
+        mods = list(self.bbox_tower)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Conv2d):
+                t = tcconv.conv(t, m)
+            elif isinstance(m, nn.GroupNorm) and m.num_channels % (4 * m.num_groups) == 0:
+                fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)      # GN + ReLU in one pass, in place
+                t = ops.group_norm_nhwc(t, m.num_groups, m.weight, m.bias, m.eps, relu=fuse, inplace=True)
+                i += int(fuse)
+            elif isinstance(m, nn.ReLU):
+                t = F.relu_(t)
+            else:
+                t = m(t).contiguous(memory_format=torch.channels_last)
+            i += 1
+        y = tcconv.conv(t, self.agn_hm, extra=self.bbox_pred)      # [P, 8, H, W]: hm | l t r b | 0 0 0
+        return y[:, 0:1], y[:, 1:5]
 
 
 @dataclass

@@ -330,18 +330,67 @@ def conv2d_pack(weight: Tensor) -> Tensor:
 
 
 def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ksize: int, relu: bool = False,
-                out: Optional[Tensor] = None) -> Tensor:
-    """Stride-1 'same' convolution on the tensor cores (3xTF32), bias + optional ReLU fused.
+                out: Optional[Tensor] = None, stride: int = 1) -> Tensor:
+    """Convolution with padding ksize//2 on the tensor cores (3xTF32), bias + optional ReLU fused.
     x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise."""
     ps_x = _pixel_stride(x, "x")
     n, cin, h, w = x.shape
+    pad = ksize // 2
+    ho, wo = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
     if out is None:
-        out = torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+        out = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
     ps_y = _pixel_stride(out, "out")
-    if tuple(out.shape) != (n, cout, h, w):
+    if tuple(out.shape) != (n, cout, ho, wo):
         raise _lib.FodError("conv2d_nhwc: bad output shape")
     if bias is not None:
         bias = _chk(bias, torch.float32, "bias").contiguous()
-    _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(packed), _ptr(bias), cout, ksize, 1, int(relu),
-                                          _ptr(out), ps_y, _stream()), "fod_conv2d_nhwc")
+    _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(packed), _ptr(bias), cout, ksize, int(stride),
+                                          int(relu), _ptr(out), ps_y, _stream()), "fod_conv2d_nhwc")
+    return out
+
+
+def group_norm_nhwc(x: Tensor, groups: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
+                    relu: bool = False, inplace: bool = False) -> Tensor:
+    """GroupNorm (+ ReLU) of a dense NHWC map [N,C,H,W] (centernet_head.py:61-72); output NHWC."""
+    x = nhwc(x, "x")
+    n, c, h, w = x.shape
+    y = x if inplace else torch.empty((n, h, w, c), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+    L = _lib.lib()
+    ws = torch.empty((L.fod_group_norm_workspace_bytes(n, groups) // 8,), dtype=torch.float64, device=x.device)
+    g = None if gamma is None else _chk(gamma, torch.float32, "gamma").contiguous()
+    b = None if beta is None else _chk(beta, torch.float32, "beta").contiguous()
+    _lib.check(L.fod_group_norm_nhwc(_ptr(x), n, h * w, c, groups, _ptr(g), _ptr(b), float(eps), int(relu), _ptr(y), _ptr(ws),
+                                     _stream()), "fod_group_norm_nhwc")
+    return y
+
+
+# --------------------------------------------------------------------------- feature-extractor glue
+def stem_patches(x: Tensor) -> Tensor:
+    """x [N,3,H,W] NHWC normalised image -> [N,32,ceil(H/2),ceil(W/2)] NHWC rows of the 27 values a 3x3 / stride-2 /
+    pad-1 convolution reads (k = (ky*3+kx)*3 + c, 5 zeros)."""
+    x = nhwc(x, "x")
+    n, c, h, w = x.shape
+    if c != 3:
+        raise _lib.FodError("stem_patches: 3 input channels")
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty((n, ho, wo, 32), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+    _lib.check(_lib.lib().fod_stem_patches(_ptr(x), n, h, w, _ptr(out), _stream()), "fod_stem_patches")
+    return out
+
+
+def maxpool3x3s2_nhwc(x: Tensor, gate: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """nn.MaxPool2d(3, 2, ceil_mode=True) of an NHWC view, times an optional per-(image, channel) gate [N,C];
+    ``out`` may be a channel slice of a wider NHWC buffer."""
+    ps_x = _pixel_stride(x, "x")
+    n, c, h, w = x.shape
+    ho, wo = (h - 2) // 2 + 1, (w - 2) // 2 + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+    if tuple(out.shape) != (n, c, ho, wo):
+        raise _lib.FodError("maxpool3x3s2_nhwc: bad output shape")
+    ps_y = _pixel_stride(out, "out")
+    if gate is not None:
+        gate = _chk(gate, torch.float32, "gate").reshape(n, c).contiguous()
+    _lib.check(_lib.lib().fod_maxpool3x3s2_nhwc(_ptr(x), n, h, w, c, ps_x, _ptr(gate), _ptr(out), ps_y, _stream()),
+               "fod_maxpool3x3s2_nhwc")
     return out

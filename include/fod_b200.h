@@ -227,6 +227,33 @@ int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_s
                     const float* bias, int cout, int ksize, int stride, int relu, float* y, long y_pixel_stride,
                     fod_stream_t stream);
 
+/* ---------------------------------------------------------------------------
+ * H0  GroupNorm (+ ReLU) over NHWC maps: the normalisation of CenterNetHead's tower
+ * (CenterNet2/centernet/modeling/dense_heads/centernet_head.py:61-72, 145-150,
+ * nn.GroupNorm(32, 128) then nn.ReLU).  Statistics per (map, group) over H*W and the
+ * group's channels, biased variance, fp64 accumulation across threads.
+ *   x, y      : [maps][hw][channels] (y may alias x)
+ *   gamma/beta: [channels] or NULL
+ *   workspace : fod_group_norm_workspace_bytes(maps, groups) bytes, 16-byte aligned
+ * channels / groups must be a multiple of 4.
+ */
+size_t fod_group_norm_workspace_bytes(int maps, int groups);
+int fod_group_norm_nhwc(const float* x, int maps, long hw, int channels, int groups, const float* gamma,
+                        const float* beta, float eps, int relu, float* y, void* workspace, fod_stream_t stream);
+
+/* ---------------------------------------------------------------------------
+ * Glue of the feature extractor (d2!/modeling/backbone/vovnet.py), memory bound.
+ * fod_stem_patches: im2col of stem_1 (3x3, stride 2, pad 1 over the 3-channel normalised image):
+ *   x [N][H][W][3] NHWC  ->  patches [N][ceil(H/2)][ceil(W/2)][32], k = (ky*3+kx)*3 + c, k >= 27 zero;
+ *   stem_1 then is fod_conv2d_nhwc(ksize 1, cin 32) with the weight rows in the same order.
+ * fod_maxpool3x3s2_nhwc: nn.MaxPool2d(kernel 3, stride 2, ceil_mode=True) of the OSA stages; `gate` (NULL or
+ *   [N][C] >= 0) multiplies the result per (image, channel): the eSE gate of the producing stage.  x / y may be
+ *   channel slices of wider NHWC buffers (pixel strides in floats).  Output size ceil((H-3)/2)+1.
+ */
+int fod_stem_patches(const float* x, int n, int h, int w, float* patches, fod_stream_t stream);
+int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate, float* y,
+                          long y_pixel_stride, fod_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

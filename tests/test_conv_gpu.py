@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _ref(x, w, b, relu):
-    y = F.conv2d(x.double(), w.double(), None if b is None else b.double(), padding=w.shape[-1] // 2)
+def _ref(x, w, b, relu, stride=1):
+    y = F.conv2d(x.double(), w.double(), None if b is None else b.double(), stride=stride, padding=w.shape[-1] // 2)
     return (y.relu() if relu else y).float()
 
 
@@ -50,6 +50,18 @@ def test_conv2d_nhwc_matches_fp32(n, h, w, cin, cout, k, relu):
     _check(y, ref, f"conv {cin}->{cout} k{k} {h}x{w}")
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 64, 64, 64, 128), (1, 40, 56, 64, 128), (2, 17, 23, 32, 64), (1, 16, 32, 128, 96)])
+def test_conv2d_nhwc_stride2_matches_fp32(n, h, w, cin, cout):
+    x = synth.tensor((n, cin, h, w), 500 + h, -1.0, 1.0)
+    wt = synth.tensor((cout, cin, 3, 3), 501 + h, -1.0, 1.0) / (cin * 9) ** 0.5
+    b = synth.tensor((cout,), 502, -0.5, 0.5)
+    ref = _ref(x, wt, b, True, stride=2)
+    y = ops.conv2d_nhwc(x.to(DEV).contiguous(memory_format=torch.channels_last), ops.conv2d_pack(wt.to(DEV)), b.to(DEV), cout, 3,
+                        True, stride=2)
+    assert y.shape == ref.shape
+    _check(y, ref, f"stride-2 conv {cin}->{cout} {h}x{w}")
+
+
 def test_conv2d_nhwc_channel_slices_concat_in_place():
     """Input and output as channel slices of wider NHWC buffers (the OSA concat is never materialised by a copy)."""
     n, h, w = 2, 24, 20
@@ -78,3 +90,31 @@ def test_conv2d_nhwc_no_bias_accumulation_bias_free():
     rel = ((y.cpu() - ref) / ref)[:, :, 2:-2, 2:-2]
     assert float(rel.abs().max()) < 5e-6, float(rel.abs().max())
     assert abs(float(rel.mean())) < 4e-6, float(rel.mean())
+
+
+@pytest.mark.parametrize("n,h,w,relu", [(3, 20, 20, True), (2, 37, 53, False), (1, 80, 80, True)])
+def test_group_norm_nhwc_matches_fp32(n, h, w, relu):
+    x = synth.tensor((n, 128, h, w), 41 + h, -2.0, 3.0)
+    gamma, beta = synth.tensor((128,), 42, 0.5, 1.5), synth.tensor((128,), 43, -0.5, 0.5)
+    ref = F.group_norm(x.double(), 32, gamma.double(), beta.double(), 1e-5)
+    ref = (ref.relu() if relu else ref).float()
+    y = ops.group_norm_nhwc(x.to(DEV).contiguous(memory_format=torch.channels_last), 32, gamma.to(DEV), beta.to(DEV), 1e-5, relu)
+    _check(y, ref, "group_norm")
+
+
+def test_stem_patches_and_gated_maxpool_match_torch():
+    x = synth.tensor((2, 3, 37, 50), 61, -2.0, 2.0)
+    w = synth.tensor((64, 3, 3, 3), 62, -0.3, 0.3)
+    ref = F.conv2d(x.double(), w.double(), stride=2, padding=1).float()
+    p = ops.stem_patches(x.to(DEV).contiguous(memory_format=torch.channels_last))
+    assert tuple(p.shape) == (2, 32, 19, 25)
+    wk = torch.cat((w.permute(0, 2, 3, 1).reshape(64, 27), torch.zeros(64, 5)), 1).reshape(64, 32, 1, 1)
+    y = ops.conv2d_nhwc(p, ops.conv2d_pack(wk.to(DEV)), None, 64, 1)
+    _check(y, ref, "stem_1 through im2col rows")
+
+    t = synth.tensor((2, 24, 21, 30), 63, -1.0, 1.0)
+    gate = synth.tensor((2, 24), 64, 0.0, 1.0)
+    ref = F.max_pool2d(t, 3, 2, ceil_mode=True) * gate[:, :, None, None]
+    buf = torch.zeros((2, 10, 15, 40), device=DEV).permute(0, 3, 1, 2)
+    ops.maxpool3x3s2_nhwc(t.to(DEV).contiguous(memory_format=torch.channels_last), gate.to(DEV), out=buf[:, 8:32])
+    assert torch.equal(buf[:, 8:32].cpu(), ref) and float(buf[:, :8].abs().max()) == 0 and float(buf[:, 32:].abs().max()) == 0

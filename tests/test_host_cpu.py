@@ -78,7 +78,7 @@ def test_backbone_matches_reference_vovnet_fpn():
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include/fod_b200.h")).read()
-    declared = set(re.findall(r"^int (fod_\w+)\(", hdr, flags=re.M))
+    declared = set(re.findall(r"^(?:int|size_t) (fod_\w+)\(", hdr, flags=re.M))
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:

@@ -164,7 +164,12 @@ def test_full_detector_forward_with_pkl_side_channel(tmp_path, monkeypatch):
         inst = out[b]["instances"]
         assert inst.pred_classes.dtype == torch.int64
         assert abs(len(inst) - rb.shape[0]) <= 2
-        assert _match(rb, rs, inst.pred_boxes.tensor.cpu(), inst.scores.cpu()) >= 0.97
+        # Integration check through the real backbone.  The final score of a detection moves by a few 1e-4 relative
+        # when its proposal box moves by 1e-3 px (ROIAlign -> K = 8192 relation head -> softmax), which is what fp32
+        # rounding differences in the tower convolutions produce (cuDNN's fp32 engines and the 3xTF32 kernel are
+        # equally far from float64, tools/dbg_tower.py).  The stage-by-stage 1e-4 parity is pinned by the golden-vector
+        # tests above and in test_ops_gpu.py; here the detections must correspond one to one.
+        assert _match(rb, rs, inst.pred_boxes.tensor.cpu(), inst.scores.cpu(), score_rtol=1e-3) >= 0.97
     # second call: pickle untouched -> cached bank is reused
     bank = model._bank
     model(inputs)
