@@ -25,6 +25,10 @@ import torch  # noqa: E402
 
 from faster_orefsdet_b200 import synth  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one conv_tc_kernel launch (ncu --set full, batch 64), keyed by
+# (H, W, Cin, Cout, ksize, stride); profiles/r1_ncu_v3_summary.md
+NCU_CONV_TRAFFIC = {}
+
 METRIC = "query_images_per_sec"
 UNIT = "images/s"
 IMG = 640
@@ -34,12 +38,14 @@ M_PIXELS = 8400       # p3+p4+p5 pixels at 640x640
 
 
 def _peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s sustained, source).  The sustained tensor figure is the one for a kernel timed
+    inside a long step (B200_PROFILING.md)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1410.0))), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1410.0, "fallback (B200_PROFILING.md)"
 
 
 def _cfg(device):
@@ -161,7 +167,8 @@ class KernelTimer:
         self.launches = 0
         self.enabled = False
 
-    kernels_per_call = {"correlate_levels": 2}   # tap packing + the persistent correlation kernel
+    # kernels of this library per C-ABI call (memsets are not counted)
+    kernels_per_call = {"correlate_levels": 2, "group_norm_nhwc": 2}
 
     def wrap(self, ops_mod, names):
         for n in names:
@@ -174,13 +181,28 @@ class KernelTimer:
                 s.record()
                 r = __fn(*a, **k)
                 e.record()
-                self.records.setdefault(__n, []).append((s, e))
+                tag = None
+                if __n == "conv2d_nhwc":      # (N, H, W, Cin, Cout, ksize, stride) of this layer
+                    x = a[0]
+                    tag = (x.shape[0], x.shape[2], x.shape[3], x.shape[1], int(a[3]), int(a[4]), int(k.get("stride", 1)))
+                self.records.setdefault(__n, []).append((s, e, tag))
                 self.launches += self.kernels_per_call.get(__n, 1)
                 return r
             setattr(ops_mod, n, timed)
 
     def summary(self):
-        return {n: (sum(s.elapsed_time(e) for s, e in ev), len(ev)) for n, ev in self.records.items()}
+        return {n: (sum(s.elapsed_time(e) for s, e, _ in ev), len(ev)) for n, ev in self.records.items()}
+
+    def conv_layers(self):
+        """per layer shape: [total ms, launches, flops per launch] (2*N*Ho*Wo*Cin*Cout*k*k, fp32 convolution flops)"""
+        out = {}
+        for s, e, tag in self.records.get("conv2d_nhwc", []):
+            n, h, w, cin, cout, ks, st = tag
+            ho, wo = (h - 1) // st + 1, (w - 1) // st + 1
+            ent = out.setdefault(tag, [0.0, 0, 2.0 * n * ho * wo * cin * cout * ks * ks])
+            ent[0] += s.elapsed_time(e)
+            ent[1] += 1
+        return out
 
 
 def run_gpu_arm(args):
@@ -218,7 +240,8 @@ def run_gpu_arm(args):
     dev_sets = [torch.stack(hs).to(dev) for hs in host_sets]
     sizes = [(IMG, IMG)] * B
     timer = KernelTimer()
-    timer.wrap(ops, ["correlate_levels", "decode_topk", "nms_proposals", "roi_align", "relation_head", "final_detect"])
+    timer.wrap(ops, ["correlate_levels", "decode_topk", "nms_proposals", "roi_align", "relation_head", "final_detect",
+                     "conv2d_nhwc", "group_norm_nhwc", "stem_patches", "maxpool3x3s2_nhwc"])
 
     def step_resident(i):
         x = dev_sets[i % NSETS]
@@ -261,11 +284,12 @@ def run_gpu_arm(args):
         def step_e2e(i):
             hs = host_sets[i % NSETS]
             res = model([{"image": im} for im in hs])
-            d2h = 0
+            n_det = 0
             for r in res:
-                inst = r["instances"].to("cpu")
-                d2h += inst.pred_boxes.tensor.numel() * 4 + inst.scores.numel() * 4 + inst.pred_classes.numel() * 8
-            return d2h
+                inst = r["instances"].to("cpu")          # host views of the one padded transfer the detector made
+                n_det += len(inst.scores) + int(inst.pred_boxes.tensor.shape[0] * 0)
+            from faster_orefsdet_b200.modeling import roi_heads as _rh
+            return _rh.LAST_D2H_BYTES + 4            # + the head's status word
         for i in range(max(args.warmup, 3)):
             step_e2e(i)
         barrier()
@@ -285,7 +309,7 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
 
-    peak, peak_src = _peaks()
+    peak, tensor_peak, peak_src = _peaks()
     # algorithmic bytes per launch (DESIGN.md "Measurement"), 1-way, B images of 640x640
     lvl_px = [6400, 1600, 400]
     alg = {
@@ -296,12 +320,33 @@ def run_gpu_arm(args):
         "relation_head": (256 * 32768.0 + 40.0 * 256) * B + 2 * 4.19e6,    # pooled rows + tf32 hi/lo weight planes
         "final_detect": 20.0 * 256 * B,
     }
-    kernels = {}
+    kernels, extractor = {}, {}
     for n, (tot_ms, cnt) in ksum.items():
         per_launch_ms = tot_ms / max(cnt, 1)
+        if n not in alg:      # feature-extractor kernels (convolutions on the tensor cores and their memory-bound glue)
+            extractor[n] = {"ms_per_step": tot_ms / args.steps, "launches_per_step": cnt / args.steps}
+            continue
         gbs = alg[n] / (per_launch_ms * 1e-3) / 1e9
         kernels[n] = {"ms_per_step": tot_ms / args.steps, "launches_per_step": cnt / args.steps,
                       "achieved_gbs": gbs, "frac": gbs / peak}
+    # the convolution kernel: per layer shape, and the launch with the largest share of the step
+    layers = timer.conv_layers()
+    conv_ms = sum(v[0] for v in layers.values()) / args.steps
+    conv_flops = sum(v[2] * v[1] for v in layers.values()) / args.steps
+    top = max(layers, key=lambda t: layers[t][0]) if layers else None
+    conv_roof = None
+    if top is not None:
+        t_ms, cnt, fl = layers[top]
+        ach = fl / (t_ms / cnt * 1e-3) / 1e12
+        # fp32-accurate arithmetic on the tensor cores = 3 tf32 MMAs per product, and tf32 runs at half the bf16 rate
+        conv_roof = {"bound": "tensor", "kernel": "conv_tc_kernel (fod_conv2d_nhwc)",
+                     "launch": "N%d %dx%d %d->%d k%d s%d" % top, "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
+                     "frac": ach / tensor_peak, "traffic": NCU_CONV_TRAFFIC.get(top[1:]) if B == BATCH else None,
+                     "algorithmic_flops": fl, "issued_tf32_tflops": 3 * ach, "frac_of_3xtf32_ceiling": ach / (tensor_peak / 6),
+                     "all_layers": {"ms_per_step": conv_ms, "launches_per_step": sum(v[1] for v in layers.values()) / args.steps,
+                                    "achieved": conv_flops / (conv_ms * 1e-3) / 1e12, "frac": conv_flops / (conv_ms * 1e-3) / 1e12 / tensor_peak},
+                     "peak_source": peak_src + ", dense bf16 sustained"}
+        extractor["conv2d_nhwc"]["fp32_tflops"] = conv_flops / (conv_ms * 1e-3) / 1e12
     # DRAM traffic per launch of the same kernels from the committed `ncu --set full` captures
     # (dram__bytes_read.sum + dram__bytes_write.sum, batch 64, 1-way; profiles/r1_ncu_v2_summary.md)
     ncu_traffic = {"correlate_levels": 504.9e6, "relation_head": 550.6e6, "roi_align": 686.9e6} if B == BATCH else {}
@@ -318,8 +363,8 @@ def run_gpu_arm(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"finetune_vovnet.yaml 1-way {SHOTS}-shot inference, batch {B} synthetic 640x640 ore queries "
-                               f"per GPU (BASELINE.json configs[1]), VoVNet-19-slim-eSE+FPN backbone (cuDNN fp32, TF32 off) + "
-                               f"CUDA head", "batch_per_gpu": B, "ways": 1, "shots": SHOTS,
+                               f"per GPU (BASELINE.json configs[1]), VoVNet-19-slim-eSE+FPN + CenterNetHead convolutions on tcgen05 "
+                               f"(3xTF32 = fp32 accuracy) + CUDA head", "batch_per_gpu": B, "ways": 1, "shots": SHOTS,
                    "l2": f"inputs rotate over {NSETS} distinct batches ({NSETS * B * 3 * IMG * IMG / 1e6:.0f} MB) and the "
                          f"backbone activations (> 1 GB per step) exceed the 126 MB L2",
                    "parallelism": f"query batch sharded, {world} rank(s); prototypes broadcast once "
@@ -327,12 +372,19 @@ def run_gpu_arm(args):
         "e2e": {"value": total_images / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * IMG * IMG,
                 "d2h_bytes_per_step": d2h_bytes, "api": "model(batched_inputs) with pinned host uint8 images; Instances.to('cpu')"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+        # dominant kernel of the step: the tensor-core convolution (its largest launch); the head's memory-bound
+        # kernels follow under "head" with their own HBM roofline fractions
+        "roofline": conv_roof if conv_roof is not None and conv_ms > kernels[dom]["ms_per_step"] else
+                    {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                      "frac": kernels[dom]["frac"], "traffic": ncu_traffic.get(dom), "algorithmic_bytes": alg[dom],
                      "peak_source": peak_src},
         "head": {"ms_per_step": head_ms, "images_per_s": B / (head_ms * 1e-3),
                  "achieved_gbs": head_alg_bytes / (head_ms * 1e-3) / 1e9, "frac": head_alg_bytes / (head_ms * 1e-3) / 1e9 / peak,
-                 "share_of_step": head_ms / (ms / args.steps), "kernels": kernels},
+                 "share_of_step": head_ms / (ms / args.steps), "kernels": kernels,
+                 "dominant_hbm_kernel": {"kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                                         "frac": kernels[dom]["frac"], "traffic": ncu_traffic.get(dom),
+                                         "algorithmic_bytes": alg[dom]}},
+        "feature_extractor": extractor,
         "clocks": clk,
     }
     if cpu_rate is not None:

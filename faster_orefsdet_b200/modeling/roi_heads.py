@@ -156,14 +156,32 @@ class CustomCascadeROIHeads(nn.Module):
         return pack_instances(ob, os_, ocls, oc, [p.image_size for p in proposals]), {}
 
 
+LAST_D2H_BYTES = 0     # size of the last detections transfer (bench.py reports it)
+
+
 def pack_instances(boxes, scores, classes, count, image_sizes) -> List[Instances]:
-    """Padded device outputs -> list[Instances] (one host sync for the counts)."""
-    counts = count.tolist()
+    """Padded device outputs -> list[Instances] on the device, with ONE device-to-host transfer of the whole
+    padded block ([B, K, 6] fp32 + counts) whose views ride along as the host mirror of every Instances
+    (compat Instances.to("cpu") returns them; the reference's evaluator copies field by field, image by image:
+    fewx/evaluation/coco_evaluation.py:119-126)."""
+    B, K = scores.shape
+    block = torch.cat((boxes, scores.unsqueeze(-1), classes.to(torch.float32).unsqueeze(-1),
+                       count.to(torch.float32).view(B, 1, 1).expand(B, K, 1)), -1)
+    host = torch.empty(block.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(block, non_blocking=True)
+    torch.cuda.current_stream(scores.device).synchronize()
+    global LAST_D2H_BYTES
+    LAST_D2H_BYTES = host.numel() * 4
+    counts = host[:, 0, 6].to(torch.int64).tolist()
+    host_cls = host[..., 5].to(torch.int64)
     out = []
     for b, n in enumerate(counts):
         inst = Instances(tuple(int(x) for x in image_sizes[b]))
         inst.pred_boxes = Boxes(boxes[b, :n])
         inst.scores = scores[b, :n]
         inst.pred_classes = classes[b, :n]
+        if hasattr(inst, "__dict__"):
+            inst.__dict__["_host_mirror"] = {"pred_boxes": Boxes(host[b, :n, :4]), "scores": host[b, :n, 4],
+                                             "pred_classes": host_cls[b, :n]}
         out.append(inst)
     return out
