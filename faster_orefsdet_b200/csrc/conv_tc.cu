@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(q_empty(s), kConvWarps);
     }
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(b_full(s), 1);
-      mbar_init(ready(s), kConvWarps);  // one set of 8 warps per CTA, both CTAs
+      mbar_init(b_full(s), 1);              // unused (the weight bytes complete `ready`)
+      mbar_init(ready(s), kConvWarps + 1);  // one set of 8 warps per CTA, both CTAs, + the weight producer's expect_tx
       mbar_init(st_free(s), 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   } else if (warp == kWarpTmaB) {
     // ------------------------------------------------------------------ TMA producer: weight chunk (hi + lo planes)
     if (lane == 0) {
-      const uint32_t b_full_leader = map_to_cta(b_full(0), 0);
+      const uint32_t b_full_leader = map_to_cta(ready(0), 0);   // the weight bytes complete the `ready` barrier
       const uint32_t plane = (uint32_t)P.nhalf * 128u;
       uint32_t g = 0;
       for (int i = 0; in_range(i); ++i) {
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             DBG_STAMP(0, g, 0);
             mbar_wait(st_free(s), ph ^ 1);
             DBG_STAMP(0, g, 1);
-            if (rank == 0) mbar_arrive_expect_tx(b_full(s), 4 * plane);
+            if (rank == 0) mbar_arrive_expect_tx(ready(s), 4 * plane);
             const int k0 = (tap * cin_chunks + cc) * kChunk;
             tma_load_2d_2sm(sbase + kOffB + s * kBStageBytes, &P.whi_map, b_full_leader + 8u * s, k0, row0);
             tma_load_2d_2sm(sbase + kOffB + s * kBStageBytes + plane, &P.wlo_map, b_full_leader + 8u * s, k0, row0);
@@ -245,7 +245,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else if (warp == kWarpAlloc) {
-    // ------------------------------------------------------------------ barrier watcher of the MMA thread (leader)
+    // ------------------------------------------------------------------ barrier watcher of the MMA warp (leader)
+    // An mbarrier wait costs ~200 cycles even when the phase completed long ago, and this thread is the only one that
+    // waits per chunk: the weight bytes of both CTAs and the converter warps of both CTAs therefore complete ONE
+    // barrier per stage (ready: 16 warp arrivals + the producer's expect_tx arrival + the TMA bytes).
     if (rank == 0 && lane == 0) {
       const uint32_t flag = sbase + kOffFlag;
       uint32_t g = 0, gp = 0;
@@ -258,8 +261,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           DBG_STAMP(2, g, 0);
           if (pc == 0) mbar_wait(acc_empty(gp % kAccStages), ((gp / kAccStages) & 1) ^ 1);
           DBG_STAMP(2, g, 1);
-          mbar_wait(b_full(s), ph);
-          DBG_STAMP(2, g, 2);
           mbar_wait(ready(s), ph);
           DBG_STAMP(2, g, 3);
           asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(flag), "r"(g + 1) : "memory");
