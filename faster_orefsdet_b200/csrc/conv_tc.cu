@@ -37,7 +37,7 @@ namespace cvt {
 
 constexpr int kTileH = 8, kTileW = 16;
 constexpr int kChunk = 32;
-constexpr int kQStages = 3, kStages = 4, kAccStages = 2;
+constexpr int kQStages = 3, kStages = 4, kMaxStages = 6, kAccStages = 2;
 constexpr int kPartChunks = 8;
 constexpr uint32_t kQStageStrideS1 = ((kTileH + 2) * (kTileW + 2) * 128 + 1023) / 1024 * 1024;   // 23552
 constexpr uint32_t kBPlaneMax = 64 * 128;                                   // 64 rows (half of a 128 group) x 128 B
@@ -49,7 +49,7 @@ constexpr uint32_t kOffB = kOffQ + kQStages * kQStageStrideS1;              // 7
 constexpr uint32_t kOffSum = kOffB + kStages * kBStageBytes;                // running tile / store staging, 4 slabs
 constexpr uint32_t kOffBias = kOffSum + 4 * kSlabBytes;
 constexpr uint32_t kOffBars = kOffBias + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kQStages + 3 * kStages + 2 * kAccStages;
+constexpr uint32_t kNumBars = 2 * kQStages + 3 * kMaxStages + 2 * kAccStages;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr uint32_t kOffFlag = kOffTmemPtr + 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
@@ -61,7 +61,8 @@ constexpr int kThreads = (kWarpConv0 + kConvWarps) * 32;  // 768
 
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColA = 0;      // 4 stages x [hi 32 | lo 32]
-constexpr uint32_t kColAcc = 256;  // 2 stages x 128
+// accumulators (2 stages) follow the A ring: 4 stages + 2 x 128 columns, or 6 stages + 2 x 64 when Cout <= 64
+// (the deeper ring hides the weight-load latency behind the shorter MMAs of a narrow layer)
 
 #ifdef FOD_DBG
 __device__ long long* g_dbg = nullptr;   // [role][g][4] clock64 stamps of pair 0 / rank 0, chunks kDbg0 .. kDbg0 + kDbgN
@@ -75,6 +76,18 @@ constexpr uint32_t kDbg0 = 400, kDbgN = 64;
 #define DBG_STAMP(role, g, slot)
 #endif
 
+// ring stage and phase parity of chunk g (constant divisors: no runtime integer division in the hot loops)
+__device__ __forceinline__ void stage_of(uint32_t g, int stages, int& s, uint32_t& ph) {
+  if (stages == kStages) {
+    s = (int)(g & (kStages - 1));
+    ph = (g / kStages) & 1;
+  } else {
+    const uint32_t q = g / (uint32_t)kMaxStages;
+    s = (int)(g - q * kMaxStages);
+    ph = q & 1;
+  }
+}
+
 struct Params {
   CUtensorMap in_map;   // [N][H][W][Cin] (pixel stride may exceed Cin), box 32 x halo_w x halo_h
   CUtensorMap out_map;  // [N][Ho][Wo][Cout], box 32 x 16 x 8
@@ -85,7 +98,7 @@ struct Params {
   int ksize, taps, stride, halo_w, per_tap;  // per_tap: one input-ring stage per (channel chunk, tap) (stride 2)
   int cin_chunks, chunks, parts, chunks_per_part;
   int n_groups, n_group, nhalf, ncol32, cout;
-  int relu, num_pairs, pair_units;
+  int relu, num_pairs, pair_units, stages;
   uint32_t q_stage_bytes, q_stage_stride;
 };
 
@@ -104,17 +117,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto q_full = [&](int s) { return bar0 + 8u * s; };                                  // TMA -> converters
   auto q_empty = [&](int s) { return bar0 + 8u * (kQStages + s); };                    // converters -> TMA
   auto b_full = [&](int s) { return bar0 + 8u * (2 * kQStages + s); };                 // TMA of both CTAs -> MMA (leader)
-  auto ready = [&](int s) { return bar0 + 8u * (2 * kQStages + kStages + s); };        // converters of both CTAs -> MMA
-  auto st_free = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kStages + s); };  // MMA commit -> A + B stage free
-  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + s); };
-  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + kAccStages + s); };
+  auto ready = [&](int s) { return bar0 + 8u * (2 * kQStages + kMaxStages + s); };        // converters of both CTAs -> MMA
+  auto st_free = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kMaxStages + s); };  // MMA commit -> A + B stage free
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kMaxStages + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kMaxStages + kAccStages + s); };
+  const int stages = P.stages;                               // depth of the TMEM A ring == weight ring
+  const uint32_t acc_w = stages == kStages ? 128u : 64u;     // accumulator stage width (columns)
+  const uint32_t col_acc = (uint32_t)stages * 64u;
+  const uint32_t b_stage = stages == kStages ? kBStageBytes : kBStageBytes / 2;   // weight ring stride (<= 64 KB in total)
 
   if (tid == 0) {
     for (int s = 0; s < kQStages; ++s) {
       mbar_init(q_full(s), 1);
       mbar_init(q_empty(s), kConvWarps);
     }
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(b_full(s), 1);              // unused (the weight bytes complete `ready`)
       mbar_init(ready(s), kConvWarps + 1);  // one set of 8 warps per CTA, both CTAs, + the weight producer's expect_tx
       mbar_init(st_free(s), 1);
@@ -180,15 +197,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int row0 = unit_grp(i) * P.n_group + (int)rank * P.nhalf;
         for (int cc = 0; cc < cin_chunks; ++cc)
           for (int tap = 0; tap < taps; ++tap, ++g) {
-            const int s = g % kStages;
-            const uint32_t ph = (g / kStages) & 1;
+            int s;
+            uint32_t ph;
+            stage_of(g, stages, s, ph);
             DBG_STAMP(0, g, 0);
             mbar_wait(st_free(s), ph ^ 1);
             DBG_STAMP(0, g, 1);
             if (rank == 0) mbar_arrive_expect_tx(ready(s), 4 * plane);
             const int k0 = (tap * cin_chunks + cc) * kChunk;
-            tma_load_2d_2sm(sbase + kOffB + s * kBStageBytes, &P.whi_map, b_full_leader + 8u * s, k0, row0);
-            tma_load_2d_2sm(sbase + kOffB + s * kBStageBytes + plane, &P.wlo_map, b_full_leader + 8u * s, k0, row0);
+            tma_load_2d_2sm(sbase + kOffB + s * b_stage, &P.whi_map, b_full_leader + 8u * s, k0, row0);
+            tma_load_2d_2sm(sbase + kOffB + s * b_stage + plane, &P.wlo_map, b_full_leader + 8u * s, k0, row0);
           }
       }
     }
@@ -199,12 +217,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // compiles to a broadcast-and-retry loop around each MMA whose latency exceeds the 64 cycles of the MMA itself.)
     if (rank == 0) {
       const uint32_t idesc = idesc_tf32(256, P.n_group);
-      const uint32_t plane = (uint32_t)P.nhalf * 128u;
+      const uint32_t plane16 = ((uint32_t)P.nhalf * 128u) >> 4, bstep16 = b_stage >> 4;
       const uint32_t flag = sbase + kOffFlag;
       const int cpp = P.chunks_per_part;
-      uint32_t upto = 0, g = 0, gp = 0;
+      // Everything a chunk's MMAs need is carried in (uniform) registers and advanced AFTER the chunk has been issued,
+      // so nothing but the flag test sits between the last MMA of one chunk and the first MMA of the next: the
+      // tensor pipe's queue is only an MMA or two deep and a 64-channel layer's MMA lasts 32 cycles.
+      const uint64_t bhi0 = smem_desc_k_sw128(sbase + kOffB);
+      const uint32_t a00 = tmem_base + kColA, d0 = tmem_base + col_acc;
+      uint64_t bhi = bhi0;
+      uint32_t a0 = a00, d = d0, sf = st_free(0), af = acc_full(0);
+      uint32_t upto = 0, g = 0;
+      int s = 0, pc = 0, as_ = 0;
       for (int i = 0; in_range(i); ++i) {
-        int pc = 0;
         for (int lc = 0; lc < chunks; ++lc, ++g) {
           DBG_STAMP(1, g, 0);
           while (upto <= g) {
@@ -214,30 +239,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           tc_fence_after();
           DBG_STAMP(1, g, 1);
-          const int s = g % kStages;
-          const bool first = pc == 0, last = (pc == cpp - 1) || (lc == chunks - 1);
-          const int as_ = gp % kAccStages;
-          const uint32_t d = tmem_base + kColAcc + as_ * 128;
-          const uint32_t a0 = tmem_base + kColA + s * 64;
-          const uint64_t bhi = smem_desc_k_sw128(sbase + kOffB + s * kBStageBytes);
-          const uint64_t blo = smem_desc_k_sw128(sbase + kOffB + s * kBStageBytes + plane);
+          const bool last = (pc == cpp - 1) || (lc == chunks - 1);
           if (elect_one()) {
+            const uint64_t blo = bhi + plane16;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t ah = a0 + ks * 8, al = ah + 32;
               const uint64_t boff = (uint64_t)((ks * 32) >> 4);
-              mma_tf32_ts<2>(d, ah, bhi + boff, idesc, (!first || ks) ? 1u : 0u);
+              mma_tf32_ts<2>(d, ah, bhi + boff, idesc, (pc | ks) ? 1u : 0u);
               mma_tf32_ts<2>(d, al, bhi + boff, idesc, 1u);
               mma_tf32_ts<2>(d, ah, blo + boff, idesc, 1u);
             }
-            mma_commit_pair(st_free(s), 3);
-            if (last) mma_commit_pair(acc_full(as_), 3);
+            mma_commit_pair(sf, 3);
+            if (last) mma_commit_pair(af, 3);
           }
           __syncwarp();
           DBG_STAMP(1, g, 2);
+          if (++s == stages) {
+            s = 0;
+            a0 = a00;
+            bhi = bhi0;
+            sf = st_free(0);
+          } else {
+            a0 += 64;
+            bhi += bstep16;
+            sf += 8;
+          }
           if (last) {
-            ++gp;
             pc = 0;
+            as_ ^= 1;
+            d = d0 + (uint32_t)as_ * acc_w;
+            af = acc_full(as_);
           } else {
             ++pc;
           }
@@ -256,8 +288,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int i = 0; in_range(i); ++i) {
         int pc = 0;
         for (int lc = 0; lc < chunks; ++lc, ++g) {
-          const int s = g % kStages;
-          const uint32_t ph = (g / kStages) & 1;
+          int s;
+          uint32_t ph;
+          stage_of(g, stages, s, ph);
           DBG_STAMP(2, g, 0);
           if (pc == 0) mbar_wait(acc_empty(gp % kAccStages), ((gp / kAccStages) & 1) ^ 1);
           DBG_STAMP(2, g, 1);
@@ -303,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t aph = (gp / kAccStages) & 1;
         mbar_wait(acc_full(as_), aph);
         tc_fence_after();
-        const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColAcc + as_ * 128;
+        const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + col_acc + as_ * acc_w;
 #pragma unroll 1
         for (int j = 0; j < ncol32; ++j) {
           uint32_t v[32];
@@ -383,9 +416,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               split_tf32(x[j].z, hi[4 * j + 2], lo[4 * j + 2]);
               split_tf32(x[j].w, hi[4 * j + 3], lo[4 * j + 3]);
             }
-            const int s = g % kStages;
+            int s;
+            uint32_t sph;
+            stage_of(g, stages, s, sph);
             if (cw == 0 || cw == 8) DBG_STAMP(3, g, 1);
-            mbar_wait(st_free(s), ((g / kStages) & 1) ^ 1);  // the MMAs that read this TMEM stage have completed
+            mbar_wait(st_free(s), sph ^ 1);  // the MMAs that read this TMEM stage have completed
             tc_fence_after();
             if (cw == 0 || cw == 8) DBG_STAMP(3, g, 2);
             tmem_st16(trow + s * 64, hi);
@@ -521,6 +556,7 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.n_groups = (cout + prm.n_group - 1) / prm.n_group;
   prm.nhalf = prm.n_group / 2;
   prm.ncol32 = (prm.n_group + 31) / 32;
+  prm.stages = prm.n_group <= 64 ? cvt::kMaxStages : cvt::kStages;   // 6 x (8 KB weights, 64 TMEM columns) or 4 x (16 KB, 64)
   prm.cout = cout;
   prm.relu = relu;
   prm.bias = bias;

@@ -41,6 +41,39 @@ __global__ void __launch_bounds__(kThreads) stem_patches_kernel(const float* __r
   }
 }
 
+// Same rows straight from the raw image: x [N][3][H][W] uint8 planar (the dataset mapper's CHW tensors, stacked),
+// normalised on the fly as (x - mean[c]) / std[c] (fsod_cen.py:540-555; IEEE division, identical to the torch ops).
+__global__ void __launch_bounds__(kThreads) stem_patches_u8_kernel(const uint8_t* __restrict__ x, int H, int W, int Ho, int Wo,
+                                                                   float m0, float m1, float m2, float s0, float s1, float s2,
+                                                                   float* __restrict__ p, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
+    const int q = (int)(i & 7);
+    const size_t pix = i >> 3;
+    const int ox = (int)(pix % Wo);
+    const size_t r = pix / Wo;
+    const int oy = (int)(r % Ho);
+    const size_t n = r / Ho;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = q * 4 + j;
+      float val = 0.f;
+      if (k < 27) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const int iy = 2 * oy + ky - 1, ix = 2 * ox + kx - 1;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+          const float raw = (float)__ldg(x + ((n * 3 + c) * (size_t)H + iy) * W + ix);
+          const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+          val = __fdiv_rn(__fsub_rn(raw, mean), sd);
+        }
+      }
+      v[j] = val;
+    }
+    *reinterpret_cast<float4*>(p + i * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // x: [N][H][W] pixels of xs floats (first C used), gate: [N][C] or null -> y: [N][Ho][Wo] pixels of ys floats
 __global__ void __launch_bounds__(kThreads) maxpool_kernel(const float* __restrict__ x, long xs, int H, int W, int C,
                                                            const float* __restrict__ gate, float* __restrict__ y, long ys,
@@ -90,6 +123,20 @@ extern "C" int fod_stem_patches(const float* x, int n, int h, int w, float* patc
   glue::stem_patches_kernel<<<grid_for(total, glue::kThreads), glue::kThreads, 0, as_stream(stream)>>>(x, h, w, ho, wo, patches,
                                                                                                     total);
   FOD_CUDA_LAUNCH_CHECK("fod_stem_patches");
+  return FOD_OK;
+}
+
+extern "C" int fod_stem_patches_u8(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, float* patches,
+                                   fod_stream_t stream) {
+  FOD_REQUIRE(x && patches && mean3 && std3, "fod_stem_patches_u8: null pointer");
+  FOD_REQUIRE(n >= 0 && h > 0 && w > 0, "fod_stem_patches_u8: bad sizes");
+  FOD_REQUIRE(((uintptr_t)patches & 15) == 0, "fod_stem_patches_u8: output must be 16-byte aligned");
+  if (n == 0) return FOD_OK;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const size_t total = (size_t)n * ho * wo * 8;
+  glue::stem_patches_u8_kernel<<<grid_for(total, glue::kThreads), glue::kThreads, 0, as_stream(stream)>>>(
+      x, h, w, ho, wo, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], patches, total);
+  FOD_CUDA_LAUNCH_CHECK("fod_stem_patches_u8");
   return FOD_OK;
 }
 

@@ -214,21 +214,33 @@ class VoVNet(nn.Module):
             self._stem1_cache = hit
         return hit[1], hit[2]
 
-    def _forward_tc(self, x):
-        """Inference on CUDA: every convolution on the tensor cores (csrc/conv_tc.cu), no torch.cat, no layout copies.
-        stem_3 and the stage poolings write straight into the first slice of the next stage's concat buffer; the eSE
-        gate of a stage is applied inside the pooling that consumes it (and materialised only for FPN inputs)."""
-        outputs = {}
-        n = x.shape[0]
+    def _tc_modules(self):
+        return [[m for m in getattr(self, name) if isinstance(m, _OSAModule)][0] for name in self.stage_names]
+
+    def tc_new_input_buffer(self, n, h, w, device):
+        """Concat buffer of the first OSA stage for n images of h x w pixels, and its first slice (where stem_3 writes)."""
+        h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1       # stem_1
+        h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1       # stem_3
+        return self._tc_modules()[0].new_buffer(n, h, w, device)
+
+    def tc_stem(self, patches, out):
+        """stem_1 (as a 1x1 convolution over im2col rows) -> stem_2 -> stem_3 into ``out`` (a batch slice of the first
+        slice of the stage-2 concat buffer).  Works on any sub-batch, so a caller can overlap host-to-device copies of
+        later images with the stem of earlier ones."""
         pk, b = self._stem1_packed()
-        y = ops.conv2d_nhwc(ops.stem_patches(x), pk, b, self.stem[0].out_channels, 1, relu=True)
+        y = ops.conv2d_nhwc(patches, pk, b, self.stem[0].out_channels, 1, relu=True)
         y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True)
-        mods = [[m for m in getattr(self, name) if isinstance(m, _OSAModule)][0] for name in self.stage_names]
-        h, w = (y.shape[2] - 1) // 2 + 1, (y.shape[3] - 1) // 2 + 1
-        buf, first = mods[0].new_buffer(n, h, w, x.device)
-        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=first)
+        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out)
+
+    def tc_body(self, buf):
+        """OSA stages from a filled stage-2 concat buffer.  The stage poolings write straight into the first slice of
+        the next stage's buffer; the eSE gate of a stage is applied inside the pooling that consumes it (and
+        materialised only for the stages that are FPN inputs)."""
+        outputs = {}
+        mods = self._tc_modules()
+        n = buf.shape[0]
         if "stem" in self._out_features:
-            outputs["stem"] = first
+            outputs["stem"] = buf[:, :mods[0].layers[0][0].in_channels]
         for i, (name, mod) in enumerate(zip(self.stage_names, mods)):
             y, gate = mod.forward_buffer(buf)
             if name in self._out_features:
@@ -237,9 +249,15 @@ class VoVNet(nn.Module):
                 gate = None
             if i + 1 < len(mods):
                 h, w = (y.shape[2] - 2) // 2 + 1, (y.shape[3] - 2) // 2 + 1
-                buf, first = mods[i + 1].new_buffer(n, h, w, x.device)
+                buf, first = mods[i + 1].new_buffer(n, h, w, y.device)
                 ops.maxpool3x3s2_nhwc(y, gate, out=first)
         return outputs
+
+    def _forward_tc(self, x):
+        """Inference on CUDA: every convolution on the tensor cores (csrc/conv_tc.cu), no torch.cat, no layout copies."""
+        buf, first = self.tc_new_input_buffer(x.shape[0], x.shape[2], x.shape[3], x.device)
+        self.tc_stem(ops.stem_patches(x), first)
+        return self.tc_body(buf)
 
     def forward(self, x):
         if self._tc_path(x):
@@ -294,8 +312,9 @@ class FPN(nn.Module):
         return self._size_divisibility
 
     def forward(self, x) -> Dict[str, torch.Tensor]:
-        feats = self.bottom_up(x)
+        return self.top_down(self.bottom_up(x))
 
+    def top_down(self, feats) -> Dict[str, torch.Tensor]:
         def run(m, t):
             return tcconv.conv(t, m) if tcconv.supported(m, t) else m(t)
 

@@ -167,14 +167,77 @@ class CenterNet2Detector(nn.Module):
         assert not self.training
         if self._bank is None:
             raise _lib.FodError("no support prototypes installed: call init_model() / set_prototypes() first")
-        images = self.preprocess_image(batched_inputs)
+        features, image_sizes = self._features_pipelined(batched_inputs)
+        if features is None:
+            images = self.preprocess_image(batched_inputs)
+            image_sizes = images.image_sizes
+            features = self.backbone(images.tensor)
         out_sizes = []
-        for inp, size in zip(batched_inputs, images.image_sizes):
+        for inp, size in zip(batched_inputs, image_sizes):
             out_sizes.append((int(inp.get("height", size[0])), int(inp.get("width", size[1]))) if do_postprocess else tuple(size))
-        features = self.backbone(images.tensor)
-        ob, os_, ocls, oc = self.head(features, images.image_sizes, out_sizes)
+        ob, os_, ocls, oc = self.head(features, image_sizes, out_sizes)
         results = pack_instances(ob, os_, ocls, oc, out_sizes)
         return [{"instances": r} for r in results] if do_postprocess else results
+
+    # ------------------------------------------------------------------ input staging
+    PIPELINE_CHUNK = 16      # images per host-to-device chunk
+
+    def features_from_uint8(self, x_u8: torch.Tensor, events=None, chunk: int = 0) -> Dict[str, torch.Tensor]:
+        """Raw uint8 image batch [N,3,H,W] already on the device (H, W multiples of the backbone's size divisibility)
+        -> FPN maps.  Normalisation is fused into the im2col kernel of stem_1.  With ``events`` (one CUDA event per
+        chunk of ``chunk`` images, recorded by the stream that fills ``x_u8``) the stem of chunk k starts as soon as
+        chunk k has landed, overlapping the copies of the later chunks."""
+        vov = self.backbone.bottom_up
+        n, _, h, w = x_u8.shape
+        buf, first = vov.tc_new_input_buffer(n, h, w, x_u8.device)
+        mean, std = self._mean_std_host()
+        chunk = chunk or n
+        main = torch.cuda.current_stream(x_u8.device)
+        for k, c0 in enumerate(range(0, n, chunk)):
+            c1 = min(c0 + chunk, n)
+            if events is not None:
+                main.wait_event(events[k])
+            vov.tc_stem(ops.stem_patches_u8(x_u8[c0:c1], mean, std), first[c0:c1])
+        return self.backbone.top_down(vov.tc_body(buf))
+
+    def _mean_std_host(self):
+        key = (self.pixel_mean._version, self.pixel_std._version, self.pixel_mean.data_ptr())
+        hit = getattr(self, "_mean_std_cache", None)
+        if hit is None or hit[0] != key:
+            hit = (key, [float(v) for v in self.pixel_mean.flatten().tolist()], [float(v) for v in self.pixel_std.flatten().tolist()])
+            self._mean_std_cache = hit
+        return hit[1], hit[2]
+
+    def _features_pipelined(self, batched_inputs: List[dict]):
+        """Fast path of preprocess_image + backbone for the common serving case: equally sized uint8 CHW images whose
+        size needs no padding.  The images are copied chunk by chunk on a side stream into one device batch while the
+        main stream already runs the stem of the chunks that have landed.  Returns (None, None) when it does not apply."""
+        from . import tcconv
+        imgs = [x["image"] for x in batched_inputs]
+        d = self.backbone.size_divisibility
+        vov = getattr(self.backbone, "bottom_up", None)
+        if (not tcconv.ENABLED or vov is None or not imgs or any(im.dtype != torch.uint8 or im.dim() != 3 or im.shape != imgs[0].shape
+                                                                 for im in imgs)
+                or imgs[0].shape[0] != 3 or imgs[0].shape[1] % d or imgs[0].shape[2] % d or self.device.type != "cuda"
+                or not vov._tc_path(torch.empty((1, 3, 1, 1), device=self.device))):
+            return None, None
+        n, (c, h, w) = len(imgs), imgs[0].shape
+        main = torch.cuda.current_stream(self.device)
+        x_u8 = torch.empty((n, c, h, w), dtype=torch.uint8, device=self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        side = self._copy_stream
+        side.wait_stream(main)                 # x_u8 was allocated on the main stream
+        events, chunk = [], self.PIPELINE_CHUNK
+        with torch.cuda.stream(side):
+            for c0 in range(0, n, chunk):
+                for i in range(c0, min(c0 + chunk, n)):
+                    x_u8[i].copy_(imgs[i], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                events.append(ev)
+        feats = self.features_from_uint8(x_u8, events, chunk)
+        return feats, [(int(h), int(w))] * n
 
     @torch.no_grad()
     def head(self, features: Dict[str, torch.Tensor], image_sizes, out_sizes, want_trace: bool = False):

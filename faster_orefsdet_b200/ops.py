@@ -378,6 +378,22 @@ def stem_patches(x: Tensor) -> Tensor:
     return out
 
 
+def stem_patches_u8(x: Tensor, mean: Sequence[float], std: Sequence[float], out: Optional[Tensor] = None) -> Tensor:
+    """x [N,3,H,W] uint8 (planar, contiguous) -> normalised im2col rows [N,32,ceil(H/2),ceil(W/2)] (NHWC memory)."""
+    _chk(x, torch.uint8, "x")
+    if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+        raise _lib.FodError("stem_patches_u8: contiguous [N,3,H,W] uint8 expected")
+    n, _, h, w = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, 32), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+    if tuple(out.shape) != (n, 32, ho, wo) or _pixel_stride(out, "out") != 32:
+        raise _lib.FodError("stem_patches_u8: bad output")
+    m3, s3 = (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.check(_lib.lib().fod_stem_patches_u8(_ptr(x), n, h, w, m3, s3, _ptr(out), _stream()), "fod_stem_patches_u8")
+    return out
+
+
 def maxpool3x3s2_nhwc(x: Tensor, gate: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
     """nn.MaxPool2d(3, 2, ceil_mode=True) of an NHWC view, times an optional per-(image, channel) gate [N,C];
     ``out`` may be a channel slice of a wider NHWC buffer."""

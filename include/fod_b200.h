@@ -251,6 +251,10 @@ int fod_group_norm_nhwc(const float* x, int maps, long hw, int channels, int gro
  *   channel slices of wider NHWC buffers (pixel strides in floats).  Output size ceil((H-3)/2)+1.
  */
 int fod_stem_patches(const float* x, int n, int h, int w, float* patches, fod_stream_t stream);
+/* the same rows from the raw uint8 planar image batch x [N][3][H][W], normalised on the fly as (x - mean[c]) / std[c]
+ * (CenterNet2Detector.preprocess_image, fewx/modeling/fsod/fsod_cen.py:540-555); mean3 / std3 are HOST arrays of 3 floats */
+int fod_stem_patches_u8(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, float* patches,
+                        fod_stream_t stream);
 int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate, float* y,
                           long y_pixel_stride, fod_stream_t stream);
 

@@ -220,3 +220,23 @@ def test_prototype_builder_matches_reference_cache_build():
     d = model.build_support_dict({1: imgs}, {1: [list(map(float, b)) for b in g["support_boxes"]]})
     for k in ("p3", "p4", "p5", "rcnn_8", "rcnn_4"):
         assert_close(d[k][1], t(g[k]), what=k)
+
+
+def test_pipelined_uint8_input_path_equals_generic_path():
+    """model(batched_inputs) with equally sized uint8 images (chunked host-to-device copies, normalisation fused into
+    the stem kernel) must give the features of preprocess_image + backbone bit for bit."""
+    model = _model()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    imgs = [synth.ore_image(128, 160, 3000 + i) for i in range(5)]
+    inputs = [{"image": im} for im in imgs]
+    model.PIPELINE_CHUNK = 2
+    feats, sizes = model._features_pipelined(inputs)
+    assert feats is not None and sizes == [(128, 160)] * 5
+    ref = model.backbone(model.preprocess_image(inputs).tensor)
+    torch.cuda.synchronize()
+    for k in ref:
+        assert torch.equal(feats[k], ref[k]), k
+    # float images or a size that needs padding fall back to the generic path
+    assert model._features_pipelined([{"image": imgs[0].float()}])[0] is None
+    assert model._features_pipelined([{"image": synth.ore_image(100, 160, 1)}])[0] is None

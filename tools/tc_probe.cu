@@ -24,7 +24,10 @@ using namespace fod::tc;
   } while (0)
 
 constexpr int K = 64;    // two 32-wide K chunks
-constexpr int NT = 128;  // total N
+#ifndef PROBE_NT
+#define PROBE_NT 128
+#endif
+constexpr int NT = PROBE_NT;  // total N
 
 // G = cta group (1 or 2), TS = A from tensor memory (else shared memory), NPROD = 1 (plain tf32) or 3 (3xTF32)
 template <int G, bool TS, int NPROD>
