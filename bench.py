@@ -244,8 +244,7 @@ def run_gpu_arm(args):
                      "conv2d_nhwc", "group_norm_nhwc", "stem_patches", "stem_patches_u8", "maxpool3x3s2_nhwc"])
 
     def step_resident(i):      # raw uint8 images resident in HBM -> padded detections on the device
-        feats = model.features_from_uint8(dev_sets[i % NSETS])
-        return model.head(feats, sizes, sizes)
+        return model.detect_from_uint8(dev_sets[i % NSETS], sizes, sizes)
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,9 +259,7 @@ def run_gpu_arm(args):
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
-        timer.enabled = True
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        head_ev = []
         ev0.record()
         for i in range(args.steps):
             out = step_resident(args.warmup + i)
@@ -272,9 +269,20 @@ def run_gpu_arm(args):
             dist.all_gather(gathered, packed)
         ev1.record()
         barrier()
-        timer.enabled = False
         clk = clocks.stop() if rank == 0 else None
         ms = ev0.elapsed_time(ev1)
+        # Per-kernel durations: the timed region replays one CUDA graph per step, inside which events cannot be read,
+        # so the same K steps are re-run eagerly right here (same inputs, same kernels, same launch parameters) with
+        # CUDA events around every C-ABI call on torch's current stream.
+        graph_mode = model.USE_CUDA_GRAPH
+        model.USE_CUDA_GRAPH = False
+        step_resident(0)
+        timer.enabled = True
+        for i in range(args.steps):
+            step_resident(args.warmup + i)
+        torch.cuda.synchronize()
+        timer.enabled = False
+        model.USE_CUDA_GRAPH = graph_mode
         ksum = timer.summary()
         launches = timer.launches
 
@@ -365,6 +373,8 @@ def run_gpu_arm(args):
                                f"(3xTF32 = fp32 accuracy) + CUDA head", "batch_per_gpu": B, "ways": 1, "shots": SHOTS,
                    "l2": f"inputs rotate over {NSETS} distinct batches ({NSETS * B * 3 * IMG * IMG / 1e6:.0f} MB) and the "
                          f"backbone activations (> 1 GB per step) exceed the 126 MB L2",
+                   "execution": ("stem eager, everything behind it one CUDA-graph replay per step" if graph_mode else "eager") +
+                                "; per-kernel durations from an eager re-run of the same steps inside this process",
                    "parallelism": f"query batch sharded, {world} rank(s); prototypes broadcast once "
                                   f"({bcast_ms:.2f} ms, outside the timed region), detections all-gathered once at the end"},
         "e2e": {"value": total_images / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * 3 * IMG * IMG,

@@ -167,15 +167,20 @@ class CenterNet2Detector(nn.Module):
         assert not self.training
         if self._bank is None:
             raise _lib.FodError("no support prototypes installed: call init_model() / set_prototypes() first")
-        features, image_sizes = self._features_pipelined(batched_inputs)
-        if features is None:
+        staged = self._stage_uint8(batched_inputs)
+        if staged is not None:
+            x_u8, events, chunk = staged
+            image_sizes = [(int(x_u8.shape[2]), int(x_u8.shape[3]))] * x_u8.shape[0]
+        else:
             images = self.preprocess_image(batched_inputs)
             image_sizes = images.image_sizes
-            features = self.backbone(images.tensor)
         out_sizes = []
         for inp, size in zip(batched_inputs, image_sizes):
             out_sizes.append((int(inp.get("height", size[0])), int(inp.get("width", size[1]))) if do_postprocess else tuple(size))
-        ob, os_, ocls, oc = self.head(features, image_sizes, out_sizes)
+        if staged is not None:
+            ob, os_, ocls, oc = self.detect_from_uint8(x_u8, image_sizes, out_sizes, events, chunk)
+        else:
+            ob, os_, ocls, oc = self.head(self.backbone(images.tensor), image_sizes, out_sizes)
         results = pack_instances(ob, os_, ocls, oc, out_sizes)
         return [{"instances": r} for r in results] if do_postprocess else results
 
@@ -187,9 +192,15 @@ class CenterNet2Detector(nn.Module):
         -> FPN maps.  Normalisation is fused into the im2col kernel of stem_1.  With ``events`` (one CUDA event per
         chunk of ``chunk`` images, recorded by the stream that fills ``x_u8``) the stem of chunk k starts as soon as
         chunk k has landed, overlapping the copies of the later chunks."""
+        buf = self._stem_from_uint8(x_u8, events, chunk)
+        return self.backbone.top_down(self.backbone.bottom_up.tc_body(buf))
+
+    def _stem_from_uint8(self, x_u8, events=None, chunk: int = 0, into=None):
+        """stem_1..3 of a raw uint8 batch into the first slice of a stage-2 concat buffer (``into`` = (buf, first) of a
+        captured graph, or a fresh one); returns the buffer."""
         vov = self.backbone.bottom_up
         n, _, h, w = x_u8.shape
-        buf, first = vov.tc_new_input_buffer(n, h, w, x_u8.device)
+        buf, first = into if into is not None else vov.tc_new_input_buffer(n, h, w, x_u8.device)
         mean, std = self._mean_std_host()
         chunk = chunk or n
         main = torch.cuda.current_stream(x_u8.device)
@@ -198,7 +209,17 @@ class CenterNet2Detector(nn.Module):
             if events is not None:
                 main.wait_event(events[k])
             vov.tc_stem(ops.stem_patches_u8(x_u8[c0:c1], mean, std), first[c0:c1])
-        return self.backbone.top_down(vov.tc_body(buf))
+        return buf
+
+    def detect_from_uint8(self, x_u8: torch.Tensor, image_sizes, out_sizes, events=None, chunk: int = 0):
+        """Raw uint8 batch on the device -> padded detections (boxes, scores, classes, count): the stem eagerly (chunk by
+        chunk behind the copy events), everything else as one CUDA-graph replay."""
+        n, _, h, w = x_u8.shape
+        if not self.USE_CUDA_GRAPH:
+            return self.head(self.features_from_uint8(x_u8, events, chunk), image_sizes, out_sizes)
+        g = self._graph_for(n, h, w)
+        self._stem_from_uint8(x_u8, events, chunk, into=(g["buf"], g["first"]))
+        return self._graph_replay(g, image_sizes, out_sizes)
 
     def _mean_std_host(self):
         key = (self.pixel_mean._version, self.pixel_std._version, self.pixel_mean.data_ptr())
@@ -209,9 +230,17 @@ class CenterNet2Detector(nn.Module):
         return hit[1], hit[2]
 
     def _features_pipelined(self, batched_inputs: List[dict]):
-        """Fast path of preprocess_image + backbone for the common serving case: equally sized uint8 CHW images whose
-        size needs no padding.  The images are copied chunk by chunk on a side stream into one device batch while the
-        main stream already runs the stem of the chunks that have landed.  Returns (None, None) when it does not apply."""
+        """(features, image sizes) through the staged uint8 path, or (None, None) when it does not apply."""
+        staged = self._stage_uint8(batched_inputs)
+        if staged is None:
+            return None, None
+        x_u8, events, chunk = staged
+        return self.features_from_uint8(x_u8, events, chunk), [(int(x_u8.shape[2]), int(x_u8.shape[3]))] * x_u8.shape[0]
+
+    def _stage_uint8(self, batched_inputs: List[dict]):
+        """Fast path of preprocess_image for the common serving case: equally sized uint8 CHW images whose size needs no
+        padding.  The images are copied chunk by chunk on a side stream into one device batch; the caller runs the stem
+        of chunk k behind event k while the later chunks are still in flight.  Returns (x_u8, events, chunk) or None."""
         from . import tcconv
         imgs = [x["image"] for x in batched_inputs]
         d = self.backbone.size_divisibility
@@ -220,7 +249,7 @@ class CenterNet2Detector(nn.Module):
                                                                  for im in imgs)
                 or imgs[0].shape[0] != 3 or imgs[0].shape[1] % d or imgs[0].shape[2] % d or self.device.type != "cuda"
                 or not vov._tc_path(torch.empty((1, 3, 1, 1), device=self.device))):
-            return None, None
+            return None
         n, (c, h, w) = len(imgs), imgs[0].shape
         main = torch.cuda.current_stream(self.device)
         x_u8 = torch.empty((n, c, h, w), dtype=torch.uint8, device=self.device)
@@ -236,37 +265,97 @@ class CenterNet2Detector(nn.Module):
                 ev = torch.cuda.Event()
                 ev.record(side)
                 events.append(ev)
-        feats = self.features_from_uint8(x_u8, events, chunk)
-        return feats, [(int(h), int(w))] * n
+        return x_u8, events, chunk
 
     @torch.no_grad()
     def head(self, features: Dict[str, torch.Tensor], image_sizes, out_sizes, want_trace: bool = False):
         """The hot path on device tensors: features[l] [B,128,H,W] -> padded detections
         (boxes [B,K,4], scores [B,K], classes [B,K] i64, count [B] i32).  No host sync except the
         final status check."""
-        bank = self._bank
         dev = features[self.in_features[0]].device
-        C = bank.num_classes
-        raw = [features[f] for f in self.in_features]
         image_hw = torch.tensor([list(s) for s in image_sizes], dtype=torch.int32).to(dev, non_blocking=True)
         out_hw = torch.tensor([list(s) for s in out_sizes], dtype=torch.int32).to(dev, non_blocking=True)
-        attempt_cap = None
-        for attempt in range(2):
-            status = ops.new_status(dev)
-            attn = ops.correlate_levels(raw, bank.taps, self.conv3.weight, self.conv3.bias)   # one persistent launch
-            props = self.proposal_generator.propose_raw(attn, status, attempt_cap)
-            (ob, os_, ocls, orow, oc), per_roi = self.roi_heads.detect_raw(raw, bank.bias_cls, props.boxes, props.count, C,
-                                                                           image_hw, out_hw, status)
-            st = int(status.item()) & 0xFFFFFFFF       # the single sync of the head
-            if st & _lib.FOD_STATUS_PROPOSAL_OVERFLOW and attempt == 0:
-                attempt_cap = props.cand_boxes.shape[1]   # ties above the reserved slack: redo with full capacity
-                continue
-            if st:
-                ops.check_status(status)
-            break
+        res = self._head_launch(features, image_hw, out_hw, None)
+        return self._head_finish(res, features, image_hw, out_hw, want_trace)
+
+    def _head_launch(self, features, image_hw, out_hw, cap):
+        """Kernel launches of the head only (stream-ordered, no host sync: CUDA-graph capturable)."""
+        bank = self._bank
+        raw = [features[f] for f in self.in_features]
+        status = ops.new_status(raw[0].device)
+        attn = ops.correlate_levels(raw, bank.taps, self.conv3.weight, self.conv3.bias)   # one persistent launch
+        props = self.proposal_generator.propose_raw(attn, status, cap)
+        out, per_roi = self.roi_heads.detect_raw(raw, bank.bias_cls, props.boxes, props.count, bank.num_classes, image_hw, out_hw,
+                                                 status)
+        return out, per_roi, props, attn, status
+
+    def _head_finish(self, res, features, image_hw, out_hw, want_trace: bool = False):
+        """The single sync of the head: read the status word; ties above the reserved proposal slack redo the head
+        once with full capacity."""
+        (ob, os_, ocls, orow, oc), per_roi, props, attn, status = res
+        st = int(status.item()) & 0xFFFFFFFF
+        if st & _lib.FOD_STATUS_PROPOSAL_OVERFLOW:
+            res = self._head_launch(features, image_hw, out_hw, props.cand_boxes.shape[1])
+            (ob, os_, ocls, orow, oc), per_roi, props, attn, status = res
+            st = int(status.item()) & 0xFFFFFFFF
+        if st:
+            ops.check_status(status)
         if want_trace:
             return (ob, os_, ocls, oc), dict(attn=attn, proposals=props, det_boxes=per_roi[0], det_scores=per_roi[1], rows=orow)
         return ob, os_, ocls, oc
+
+    # ------------------------------------------------------------------ CUDA graph of everything behind the stem
+    USE_CUDA_GRAPH = os.environ.get("FOD_CUDA_GRAPH", "1") == "1"
+
+    def _graph_key(self, n, h, w):
+        ver = sum(int(p._version) for p in self.parameters()) + sum(int(b._version) for b in self.buffers())
+        return (n, h, w, self._bank_key, id(self._bank), ver, str(self.device))
+
+    def _graph_for(self, n, h, w):
+        """Captured once per (batch, image size, episode, weights): OSA stages + FPN + CenterNetHead + the head kernels
+        (~140 launches, many of them a few microseconds long) replay as one graph launch.  The stem stays outside so
+        that it can start on the first images while the later ones are still being copied."""
+        key = self._graph_key(n, h, w)
+        hit = getattr(self, "_graph", None)
+        if hit is not None and hit["key"] == key:
+            return hit
+        dev = self.device
+        vov = self.backbone.bottom_up
+        buf, first = vov.tc_new_input_buffer(n, h, w, dev)
+        g = {"key": key, "buf": buf, "first": first,
+             "image_hw": torch.zeros((n, 2), dtype=torch.int32, device=dev), "out_hw": torch.zeros((n, 2), dtype=torch.int32, device=dev),
+             "sizes_host": torch.zeros((2, n, 2), dtype=torch.int32).pin_memory()}
+        g["image_hw"][:] = torch.tensor([h, w], dtype=torch.int32, device=dev)
+        g["out_hw"][:] = g["image_hw"]
+        first.zero_()
+
+        def run():
+            feats = self.backbone.top_down(vov.tc_body(buf))
+            return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None)
+
+        main = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):          # warm-up outside capture: weight packing, cuDNN/cuBLAS handles and plans
+            for _ in range(2):
+                run()
+        main.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g["feats"], g["res"] = run()
+        g["graph"] = graph
+        self._graph = g
+        return g
+
+    def _graph_replay(self, g, image_sizes, out_sizes, want_trace: bool = False):
+        sh = g["sizes_host"]
+        sh[0] = torch.tensor([list(s) for s in image_sizes], dtype=torch.int32)
+        sh[1] = torch.tensor([list(s) for s in out_sizes], dtype=torch.int32)
+        g["image_hw"].copy_(sh[0], non_blocking=True)
+        g["out_hw"].copy_(sh[1], non_blocking=True)
+        g["graph"].replay()
+        return self._head_finish(g["res"], g["feats"], g["image_hw"], g["out_hw"], want_trace)
 
     def preprocess_image(self, batched_inputs: List[dict]) -> ImageList:
         """Normalise, pad to a multiple of 32, batch (fsod_cen.py:540-555); channels_last for cuDNN."""

@@ -161,9 +161,10 @@ LAST_D2H_BYTES = 0     # size of the last detections transfer (bench.py reports 
 
 def pack_instances(boxes, scores, classes, count, image_sizes) -> List[Instances]:
     """Padded device outputs -> list[Instances] on the device, with ONE device-to-host transfer of the whole
-    padded block ([B, K, 6] fp32 + counts) whose views ride along as the host mirror of every Instances
+    padded block ([B, K, 7] fp32) whose views ride along as the host mirror of every Instances
     (compat Instances.to("cpu") returns them; the reference's evaluator copies field by field, image by image:
-    fewx/evaluation/coco_evaluation.py:119-126)."""
+    fewx/evaluation/coco_evaluation.py:119-126).  The valid rows are compacted once and split per image with
+    split_with_sizes, so the per-image Python cost is the construction of the containers only."""
     B, K = scores.shape
     block = torch.cat((boxes, scores.unsqueeze(-1), classes.to(torch.float32).unsqueeze(-1),
                        count.to(torch.float32).view(B, 1, 1).expand(B, K, 1)), -1)
@@ -172,16 +173,23 @@ def pack_instances(boxes, scores, classes, count, image_sizes) -> List[Instances
     torch.cuda.current_stream(scores.device).synchronize()
     global LAST_D2H_BYTES
     LAST_D2H_BYTES = host.numel() * 4
-    counts = host[:, 0, 6].to(torch.int64).tolist()
-    host_cls = host[..., 5].to(torch.int64)
+    counts_t = host[:, 0, 6].to(torch.int64)
+    counts = counts_t.tolist()
+    idx = torch.nonzero((torch.arange(K)[None, :] < counts_t[:, None]).flatten()).squeeze(1)
+    flat_h = host.view(B * K, 7).index_select(0, idx)
+    flat_d = block.view(B * K, 7).index_select(0, idx.to(scores.device, non_blocking=True))
+    parts = []
+    for flat in (flat_d, flat_h):
+        parts.append((torch.split(flat[:, :4], counts), torch.split(flat[:, 4], counts),
+                      torch.split(flat[:, 5].to(torch.int64), counts)))
+    (db, ds, dc), (hb, hs, hc) = parts
     out = []
-    for b, n in enumerate(counts):
+    for b in range(B):
         inst = Instances(tuple(int(x) for x in image_sizes[b]))
-        inst.pred_boxes = Boxes(boxes[b, :n])
-        inst.scores = scores[b, :n]
-        inst.pred_classes = classes[b, :n]
+        inst.pred_boxes = Boxes(db[b])
+        inst.scores = ds[b]
+        inst.pred_classes = dc[b]
         if hasattr(inst, "__dict__"):
-            inst.__dict__["_host_mirror"] = {"pred_boxes": Boxes(host[b, :n, :4]), "scores": host[b, :n, 4],
-                                             "pred_classes": host_cls[b, :n]}
+            inst.__dict__["_host_mirror"] = {"pred_boxes": Boxes(hb[b]), "scores": hs[b], "pred_classes": hc[b]}
         out.append(inst)
     return out

@@ -240,3 +240,22 @@ def test_pipelined_uint8_input_path_equals_generic_path():
     # float images or a size that needs padding fall back to the generic path
     assert model._features_pipelined([{"image": imgs[0].float()}])[0] is None
     assert model._features_pipelined([{"image": synth.ore_image(100, 160, 1)}])[0] is None
+
+
+def test_cuda_graph_replay_equals_eager_launches():
+    """detect_from_uint8: stem eager + one graph replay must equal the eager path bit for bit, also when the requested
+    output sizes change between replays and when the batch content changes."""
+    model = _model()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    model.set_prototypes(synth.prototypes([1], 5, 7))
+    sizes = [(128, 160)] * 3
+    for rnd, outs in enumerate(([(128, 160)] * 3, [(256, 320), (128, 160), (64, 80)])):
+        x = torch.stack([synth.ore_image(128, 160, 4000 + 10 * rnd + i) for i in range(3)]).cuda()
+        model.USE_CUDA_GRAPH = True
+        got = [t.clone() for t in model.detect_from_uint8(x, sizes, outs)]
+        model.USE_CUDA_GRAPH = False
+        ref = model.detect_from_uint8(x, sizes, outs)
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+    assert model._graph["graph"] is not None

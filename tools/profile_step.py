@@ -21,8 +21,7 @@ sizes = [(640, 640)] * B
 
 
 def step():
-    x = ((x8.float() - model.pixel_mean) / model.pixel_std).contiguous(memory_format=torch.channels_last)
-    return model.head(model.backbone(x), sizes, sizes)
+    return model.head(model.features_from_uint8(x8), sizes, sizes)
 
 
 with torch.no_grad():
