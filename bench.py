@@ -344,11 +344,12 @@ def run_gpu_arm(args):
     if top is not None:
         t_ms, cnt, fl = layers[top]
         ach = fl / (t_ms / cnt * 1e-3) / 1e12
-        # fp32-accurate arithmetic on the tensor cores = 3 tf32 MMAs per product, and tf32 runs at half the bf16 rate
+        # fp32-accurate arithmetic on the tensor cores = 3 fp16 MMAs per product (hi.hi + lo.hi + hi.lo), fp16 runs at the
+        # bf16 rate: the ceiling of this arithmetic is peak / 3
         conv_roof = {"bound": "tensor", "kernel": "conv_tc_kernel (fod_conv2d_nhwc)",
                      "launch": "N%d %dx%d %d->%d k%d s%d" % top, "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
                      "frac": ach / tensor_peak, "traffic": NCU_CONV_TRAFFIC.get(top[1:]) if B == BATCH else None,
-                     "algorithmic_flops": fl, "issued_tf32_tflops": 3 * ach, "frac_of_3xtf32_ceiling": ach / (tensor_peak / 6),
+                     "algorithmic_flops": fl, "issued_f16_tflops": 3 * ach, "frac_of_split_ceiling": ach / (tensor_peak / 3),
                      "all_layers": {"ms_per_step": conv_ms, "launches_per_step": sum(v[1] for v in layers.values()) / args.steps,
                                     "achieved": conv_flops / (conv_ms * 1e-3) / 1e12, "frac": conv_flops / (conv_ms * 1e-3) / 1e12 / tensor_peak},
                      "peak_source": peak_src + ", dense bf16 sustained"}
@@ -370,7 +371,7 @@ def run_gpu_arm(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"finetune_vovnet.yaml 1-way {SHOTS}-shot inference, batch {B} synthetic 640x640 ore queries "
                                f"per GPU (BASELINE.json configs[1]), VoVNet-19-slim-eSE+FPN + CenterNetHead convolutions on tcgen05 "
-                               f"(3xTF32 = fp32 accuracy) + CUDA head", "batch_per_gpu": B, "ways": 1, "shots": SHOTS,
+                               f"(fp16-split operands, 3 MMAs per product = fp32 accuracy) + CUDA head", "batch_per_gpu": B, "ways": 1, "shots": SHOTS,
                    "l2": f"inputs rotate over {NSETS} distinct batches ({NSETS * B * 3 * IMG * IMG / 1e6:.0f} MB) and the "
                          f"backbone activations (> 1 GB per step) exceed the 126 MB L2",
                    "execution": ("stem eager, everything behind it one CUDA-graph replay per step" if graph_mode else "eager") +

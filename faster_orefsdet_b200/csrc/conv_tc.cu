@@ -1,11 +1,20 @@
 // H0 (and the convolutions either side of the head): 3x3 / 1x1 convolution over NHWC fp32 maps as an implicit GEMM on
-// the 5th-generation tensor cores, fp32 accuracy by 3xTF32 operand splitting, bias + ReLU epilogue.
+// the 5th-generation tensor cores with fp32 accuracy, bias + ReLU epilogue.
 // Replaces the F.conv2d -> cuDNN calls of CenterNetHead (CenterNet2/centernet/modeling/dense_heads/centernet_head.py:
 // 141-161) and of the VoVNet/FPN modules that feed the head (d2!/modeling/backbone/vovnet.py, fpn.py), which cuDNN
 // serves on sm_100 with fp32 SIMT / FFT engines when TF32 is off.
 //
 //   y[n][oy][ox][co] = act( bias[co] + sum_{ky,kx,ci} w[co][ky][kx][ci] * x[n][oy*s + ky - pad][ox*s + kx - pad][ci] )
 //   (stride s in {1, 2}, pad = ksize / 2, zero padding)
+//
+// Arithmetic: every fp32 operand is split as x * 2^e = hi + lo with hi = fp16(x * 2^e), lo = fp16(x * 2^e - hi)
+// (22 significant bits, the same as a tf32 hi/lo split) and the product is hi.hi + lo.hi + hi.lo on kind::f16 MMAs with
+// fp32 accumulation.  The power-of-two scale 2^e puts the largest magnitude of the tensor into [2^13, 2^14), so nothing
+// overflows fp16 and what underflows is below 2^-38 of that maximum; it is exact and is undone in the epilogue.  The
+// caller passes an upper bound of max|x| (device scalar, normally written by the kernel that produced x: this kernel's
+// own epilogue reports max|y|); the weights' scale is fixed when they are packed.  Against the 3xTF32 version of this
+// kernel (K = 8 per MMA, one MMA per 45 cycles at best) kind::f16 moves K = 16 per MMA in 64 cycles at N = 128 and in
+// 32 cycles at N = 64 (tools/f16_probe.cu): half the tensor time for the same accuracy (measured 4e-7 relative).
 //
 // Design (B200, sm_100a) - the skeleton of correlate_tc.cu / relation_tc.cu:
 //   * work unit = tile of 8 x 16 output pixels of one image (128 GEMM rows) x one group of <= 128 output channels.
@@ -17,15 +26,18 @@
 //     (Stride 2: a halo tile would be 17 x 33 pixels, so each tap's 8 x 16 pixels are fetched by their own TMA load
 //     with element strides (2, 2) instead: one ring stage per tap.)
 //   * 16 converter warps (one output pixel per lane = TMEM lane) read the tap-shifted 128-byte row of their pixel
-//     (conflict-free LDS.128 thanks to the TMA swizzle), split it into tf32 hi / lo and write it into TENSOR MEMORY;
-//     the MMA (Ahi.Bhi + Alo.Bhi + Ahi.Blo) reads A from tensor memory and only the weights from shared memory.
+//     (conflict-free LDS.128 thanks to the TMA swizzle), scale and split it into fp16 hi / lo pairs and write them into
+//     TENSOR MEMORY; the MMA reads A from tensor memory and only the weights from shared memory.
 //     Two sets of 8 warps alternate over the chunks so that their latencies overlap.
-//   * weights: pre-split tf32 hi / lo planes [Cout][taps][Cin_pad] (fod_conv2d_pack_weights), TMA-streamed per chunk
-//     into a 4-stage ring (they are L2 resident: <= 1.2 MB per layer).
+//   * weights: pre-split fp16 hi / lo planes [Cout][taps][Cin_pad] (fod_conv2d_pack_weights), TMA-streamed per chunk
+//     into a 6-stage ring (they are L2 resident: <= 0.6 MB per layer).
 //   * the tensor core accumulates with round-toward-zero (tools/tc_probe.cu), so the K loop is cut into partial sums
-//     of <= 8 chunks (96 MMAs) that the 4 epilogue warps add in IEEE fp32 into a running tile in shared memory; the
-//     last part adds the bias, applies ReLU and the tile leaves through TMA stores (clipped at the image border and at
-//     Cout by the tensor map, so the output may be a channel slice of a wider NHWC buffer: concatenation is free).
+//     of <= 16 chunks (96 MMAs) that the 4 epilogue warps add in IEEE fp32 into a running tile in shared memory; the
+//     last part rescales, adds the bias, applies ReLU and the tile leaves through TMA stores (clipped at the image
+//     border and at Cout by the tensor map, so the output may be a channel slice of a wider NHWC buffer: concatenation
+//     is free).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -37,10 +49,10 @@ namespace cvt {
 
 constexpr int kTileH = 8, kTileW = 16;
 constexpr int kChunk = 32;
-constexpr int kQStages = 3, kStages = 4, kMaxStages = 6, kAccStages = 2;
-constexpr int kPartChunks = 8;
+constexpr int kQStages = 3, kStages = 6, kAccStages = 2;
+constexpr int kPartChunks = 16;
 constexpr uint32_t kQStageStrideS1 = ((kTileH + 2) * (kTileW + 2) * 128 + 1023) / 1024 * 1024;   // 23552
-constexpr uint32_t kBPlaneMax = 64 * 128;                                   // 64 rows (half of a 128 group) x 128 B
+constexpr uint32_t kBPlaneMax = 64 * 64;                                    // 64 rows (half of a 128 group) x 32 fp16
 constexpr uint32_t kBStageBytes = 2 * kBPlaneMax;                           // hi + lo
 constexpr uint32_t kSlabBytes = 128 * 128;                                  // 128 pixels x 32 channels
 
@@ -49,7 +61,7 @@ constexpr uint32_t kOffB = kOffQ + kQStages * kQStageStrideS1;              // 7
 constexpr uint32_t kOffSum = kOffB + kStages * kBStageBytes;                // running tile / store staging, 4 slabs
 constexpr uint32_t kOffBias = kOffSum + 4 * kSlabBytes;
 constexpr uint32_t kOffBars = kOffBias + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kQStages + 3 * kMaxStages + 2 * kAccStages;
+constexpr uint32_t kNumBars = 2 * kQStages + 3 * kStages + 2 * kAccStages;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr uint32_t kOffFlag = kOffTmemPtr + 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
@@ -60,9 +72,21 @@ constexpr int kWarpTma = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpTmaB = 3, kWarpEp
 constexpr int kThreads = (kWarpConv0 + kConvWarps) * 32;  // 768
 
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColA = 0;      // 4 stages x [hi 32 | lo 32]
-// accumulators (2 stages) follow the A ring: 4 stages + 2 x 128 columns, or 6 stages + 2 x 64 when Cout <= 64
-// (the deeper ring hides the weight-load latency behind the shorter MMAs of a narrow layer)
+constexpr uint32_t kAStageCols = 32;                // [hi: 16 columns of packed fp16 pairs | lo: 16]
+constexpr uint32_t kColA = 0;                       // 6 stages x 32
+constexpr uint32_t kColAcc = kStages * kAStageCols; // 2 stages x 128
+
+// 2^e with amax * 2^e in [2^13, 2^14) (and its inverse); 1 for zero / denormal-range / non-finite bounds
+__device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
+  const int E = (int)((__float_as_uint(amax) >> 23) & 0xFF);
+  if (E < 32 || E > 240) {
+    scale = 1.f;
+    inv = 1.f;
+  } else {
+    scale = __uint_as_float((uint32_t)(267 - E) << 23);  // 2^(13 - (E - 127))
+    inv = __uint_as_float((uint32_t)(E - 13) << 23);
+  }
+}
 
 #ifdef FOD_DBG
 __device__ long long* g_dbg = nullptr;   // [role][g][4] clock64 stamps of pair 0 / rank 0, chunks kDbg0 .. kDbg0 + kDbgN
@@ -76,29 +100,29 @@ constexpr uint32_t kDbg0 = 400, kDbgN = 64;
 #define DBG_STAMP(role, g, slot)
 #endif
 
-// ring stage and phase parity of chunk g (constant divisors: no runtime integer division in the hot loops)
-__device__ __forceinline__ void stage_of(uint32_t g, int stages, int& s, uint32_t& ph) {
-  if (stages == kStages) {
-    s = (int)(g & (kStages - 1));
-    ph = (g / kStages) & 1;
-  } else {
-    const uint32_t q = g / (uint32_t)kMaxStages;
-    s = (int)(g - q * kMaxStages);
-    ph = q & 1;
-  }
+// (a, b) -> packed fp16 pair of the rounded values (a in the low half) and of the exact remainders
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 struct Params {
   CUtensorMap in_map;   // [N][H][W][Cin] (pixel stride may exceed Cin), box 32 x halo_w x halo_h
   CUtensorMap out_map;  // [N][Ho][Wo][Cout], box 32 x 16 x 8
-  CUtensorMap whi_map;  // [Cout][taps*Cin_pad], box 32 x nhalf
+  CUtensorMap whi_map;  // fp16 [Cout][taps*Cin_pad], box 32 x nhalf
   CUtensorMap wlo_map;
   const float* bias;    // [Cout] or null
+  const float* x_amax;  // [n_amax] upper bounds of max|x| (their maximum is used)
+  const float* w_inv;   // 1 / weight scale (tail of the packed buffer)
+  float* y_amax;        // null or: atomically raised to max|y|
   int tiles_x, tiles_per_img, tiles_total;
   int ksize, taps, stride, halo_w, per_tap;  // per_tap: one input-ring stage per (channel chunk, tap) (stride 2)
   int cin_chunks, chunks, parts, chunks_per_part;
   int n_groups, n_group, nhalf, ncol32, cout;
-  int relu, num_pairs, pair_units, stages;
+  int relu, num_pairs, pair_units, n_amax, ho, wo;
   uint32_t q_stage_bytes, q_stage_stride;
 };
 
@@ -117,21 +141,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto q_full = [&](int s) { return bar0 + 8u * s; };                                  // TMA -> converters
   auto q_empty = [&](int s) { return bar0 + 8u * (kQStages + s); };                    // converters -> TMA
   auto b_full = [&](int s) { return bar0 + 8u * (2 * kQStages + s); };                 // TMA of both CTAs -> MMA (leader)
-  auto ready = [&](int s) { return bar0 + 8u * (2 * kQStages + kMaxStages + s); };        // converters of both CTAs -> MMA
-  auto st_free = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kMaxStages + s); };  // MMA commit -> A + B stage free
-  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kMaxStages + s); };
-  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kMaxStages + kAccStages + s); };
-  const int stages = P.stages;                               // depth of the TMEM A ring == weight ring
-  const uint32_t acc_w = stages == kStages ? 128u : 64u;     // accumulator stage width (columns)
-  const uint32_t col_acc = (uint32_t)stages * 64u;
-  const uint32_t b_stage = stages == kStages ? kBStageBytes : kBStageBytes / 2;   // weight ring stride (<= 64 KB in total)
+  auto ready = [&](int s) { return bar0 + 8u * (2 * kQStages + kStages + s); };        // converters + weight bytes -> MMA
+  auto st_free = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kStages + s); };  // MMA commit -> A + B stage free
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + kAccStages + s); };
+  constexpr int stages = kStages;
+  constexpr uint32_t acc_w = 128u, col_acc = kColAcc, b_stage = kBStageBytes;
+  float xs = 1.f, xs_inv = 1.f;   // input scale 2^e (converters) and its inverse (epilogue)
+  {
+    float amax = 0.f;
+    for (int i = 0; i < P.n_amax; ++i) amax = fmaxf(amax, __ldg(P.x_amax + i));
+    pow2_scale(amax, xs, xs_inv);
+  }
 
   if (tid == 0) {
     for (int s = 0; s < kQStages; ++s) {
       mbar_init(q_full(s), 1);
       mbar_init(q_empty(s), kConvWarps);
     }
-    for (int s = 0; s < kMaxStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(b_full(s), 1);              // unused (the weight bytes complete `ready`)
       mbar_init(ready(s), kConvWarps + 1);  // one set of 8 warps per CTA, both CTAs, + the weight producer's expect_tx
       mbar_init(st_free(s), 1);
@@ -191,15 +219,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ------------------------------------------------------------------ TMA producer: weight chunk (hi + lo planes)
     if (lane == 0) {
       const uint32_t b_full_leader = map_to_cta(ready(0), 0);   // the weight bytes complete the `ready` barrier
-      const uint32_t plane = (uint32_t)P.nhalf * 128u;
+      const uint32_t plane = (uint32_t)P.nhalf * 64u;
       uint32_t g = 0;
       for (int i = 0; in_range(i); ++i) {
         const int row0 = unit_grp(i) * P.n_group + (int)rank * P.nhalf;
         for (int cc = 0; cc < cin_chunks; ++cc)
           for (int tap = 0; tap < taps; ++tap, ++g) {
-            int s;
-            uint32_t ph;
-            stage_of(g, stages, s, ph);
+            const int s = (int)(g % stages);
+            const uint32_t ph = (g / stages) & 1;
             DBG_STAMP(0, g, 0);
             mbar_wait(st_free(s), ph ^ 1);
             DBG_STAMP(0, g, 1);
@@ -216,14 +243,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // warp-uniform value that ptxas keeps in uniform registers.  (Inside an `if (lane == 0)` region the same code
     // compiles to a broadcast-and-retry loop around each MMA whose latency exceeds the 64 cycles of the MMA itself.)
     if (rank == 0) {
-      const uint32_t idesc = idesc_tf32(256, P.n_group);
-      const uint32_t plane16 = ((uint32_t)P.nhalf * 128u) >> 4, bstep16 = b_stage >> 4;
+      const uint32_t idesc = idesc_f16(256, P.n_group);
+      const uint32_t plane16 = ((uint32_t)P.nhalf * 64u) >> 4, bstep16 = b_stage >> 4;
       const uint32_t flag = sbase + kOffFlag;
       const int cpp = P.chunks_per_part;
       // Everything a chunk's MMAs need is carried in (uniform) registers and advanced AFTER the chunk has been issued,
       // so nothing but the flag test sits between the last MMA of one chunk and the first MMA of the next: the
       // tensor pipe's queue is only an MMA or two deep and a 64-channel layer's MMA lasts 32 cycles.
-      const uint64_t bhi0 = smem_desc_k_sw128(sbase + kOffB);
+      const uint64_t bhi0 = smem_desc_k_sw64(sbase + kOffB);
       const uint32_t a00 = tmem_base + kColA, d0 = tmem_base + col_acc;
       uint64_t bhi = bhi0;
       uint32_t a0 = a00, d = d0, sf = st_free(0), af = acc_full(0);
@@ -243,12 +270,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (elect_one()) {
             const uint64_t blo = bhi + plane16;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t ah = a0 + ks * 8, al = ah + 32;
+            for (int ks = 0; ks < 2; ++ks) {  // K = 16 fp16 per MMA: 8 packed columns of A, 32 bytes of a B row
+              const uint32_t ah = a0 + ks * 8, al = ah + 16;
               const uint64_t boff = (uint64_t)((ks * 32) >> 4);
-              mma_tf32_ts<2>(d, ah, bhi + boff, idesc, (pc | ks) ? 1u : 0u);
-              mma_tf32_ts<2>(d, al, bhi + boff, idesc, 1u);
-              mma_tf32_ts<2>(d, ah, blo + boff, idesc, 1u);
+              mma_f16_ts<2>(d, ah, bhi + boff, idesc, (pc | ks) ? 1u : 0u);
+              mma_f16_ts<2>(d, al, bhi + boff, idesc, 1u);
+              mma_f16_ts<2>(d, ah, blo + boff, idesc, 1u);
             }
             mma_commit_pair(sf, 3);
             if (last) mma_commit_pair(af, 3);
@@ -261,7 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             bhi = bhi0;
             sf = st_free(0);
           } else {
-            a0 += 64;
+            a0 += kAStageCols;
             bhi += bstep16;
             sf += 8;
           }
@@ -288,9 +315,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int i = 0; in_range(i); ++i) {
         int pc = 0;
         for (int lc = 0; lc < chunks; ++lc, ++g) {
-          int s;
-          uint32_t ph;
-          stage_of(g, stages, s, ph);
+          const int s = (int)(g % stages);
+          const uint32_t ph = (g / stages) & 1;
           DBG_STAMP(2, g, 0);
           if (pc == 0) mbar_wait(acc_empty(gp % kAccStages), ((gp / kAccStages) & 1) ^ 1);
           DBG_STAMP(2, g, 1);
@@ -315,6 +341,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t row_s = sbase + kOffSum + (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
     const uint32_t bias_s = sbase + kOffBias;
     const int ncol32 = P.ncol32, parts = P.parts;
+    const float rescale = xs_inv * __ldg(P.w_inv);   // undoes the two power-of-two operand scales (exact)
+    float vmax = 0.f;                                // max |y| over the valid outputs this lane produced
     uint32_t gp = 0;
     for (int i = 0; in_range(i); ++i) {
       const int t = unit_tile(i);
@@ -323,6 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int n = tc_ / P.tiles_per_img, tt = tc_ - n * P.tiles_per_img;
       const int ty = tt / P.tiles_x, tx = tt - ty * P.tiles_x;
       const int ch0 = unit_grp(i) * P.n_group;
+      const bool px_valid = do_store && ty * kTileH + (m >> 4) < P.ho && tx * kTileW + (m & 15) < P.wo;
       if (issuer) tma_store_wait_read<0>();  // the previous tile has left the staging slabs
       named_bar_sync(1, 128);
       {
@@ -359,9 +388,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             }
             if (part == parts - 1) {
               const float4 bb = lds4s(bias_s + (j * 32 + c4 * 4) * 4);
-              x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+              x.x = fmaf(x.x, rescale, bb.x); x.y = fmaf(x.y, rescale, bb.y);
+              x.z = fmaf(x.z, rescale, bb.z); x.w = fmaf(x.w, rescale, bb.w);
               if (P.relu) {
                 x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+              }
+              if (P.y_amax && px_valid) {   // columns beyond Cout hold whatever the accumulator columns held
+                const int cb = ch0 + j * 32 + c4 * 4;
+                if (cb + 0 < P.cout) vmax = fmaxf(vmax, fabsf(x.x));
+                if (cb + 1 < P.cout) vmax = fmaxf(vmax, fabsf(x.y));
+                if (cb + 2 < P.cout) vmax = fmaxf(vmax, fabsf(x.z));
+                if (cb + 3 < P.cout) vmax = fmaxf(vmax, fabsf(x.w));
               }
             }
             sts4s(sa, x);
@@ -377,15 +414,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     if (issuer) tma_store_wait<0>();
+    if (P.y_amax) {   // non-negative floats order like their bit patterns; a NaN becomes a huge bound (scale 1 downstream)
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+      if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(P.y_amax), wmax);
+    }
   } else if (warp >= kWarpConv0) {
-    // ------------------------------------------------------------------ converters: shifted A chunk -> tf32 hi/lo in TMEM
+    // ------------------------------------------------------------------ converters: shifted A chunk -> scaled fp16 hi/lo in TMEM
     const int cw = warp - kWarpConv0;
     const int qd = cw & 3, half = (cw >> 2) & 1, set = cw >> 3;
     const int m = qd * 32 + lane;
     const int py = m >> 4, px = m & 15;  // position of this pixel's tap (0,0) in the halo tile
     const bool per_tap = P.per_tap != 0;
     const uint32_t ready_leader = map_to_cta(ready(0), 0);
-    const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColA + half * 16;
+    const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColA + half * 8;
     const int ksz = P.ksize, hw = P.halo_w;
     uint32_t g = 0, gq = 0;
     for (int i = 0; in_range(i); ++i) {
@@ -408,23 +449,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             float4 x[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) x[j] = lds4s(at + ((((uint32_t)(half * 4 + j)) ^ key) << 4));
-            uint32_t hi[16], lo[16];
+            uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              split_tf32(x[j].x, hi[4 * j + 0], lo[4 * j + 0]);
-              split_tf32(x[j].y, hi[4 * j + 1], lo[4 * j + 1]);
-              split_tf32(x[j].z, hi[4 * j + 2], lo[4 * j + 2]);
-              split_tf32(x[j].w, hi[4 * j + 3], lo[4 * j + 3]);
+              split_f16x2(x[j].x * xs, x[j].y * xs, hi[2 * j + 0], lo[2 * j + 0]);
+              split_f16x2(x[j].z * xs, x[j].w * xs, hi[2 * j + 1], lo[2 * j + 1]);
             }
-            int s;
-            uint32_t sph;
-            stage_of(g, stages, s, sph);
+            const int s = (int)(g % stages);
+            const uint32_t sph = (g / stages) & 1;
             if (cw == 0 || cw == 8) DBG_STAMP(3, g, 1);
             mbar_wait(st_free(s), sph ^ 1);  // the MMAs that read this TMEM stage have completed
             tc_fence_after();
             if (cw == 0 || cw == 8) DBG_STAMP(3, g, 2);
-            tmem_st16(trow + s * 64, hi);
-            tmem_st16(trow + s * 64 + 32, lo);
+            tmem_st8(trow + s * kAStageCols, hi);
+            tmem_st8(trow + s * kAStageCols + 16, lo);
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -452,21 +490,41 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == kWarpAlloc) tmem_dealloc<2>(tmem_base, kTmemCols);
 }
 
-// OIHW fp32 weights -> tf32 hi / lo planes [Cout][ky][kx][Cin_pad] (Cin_pad = Cin rounded up to 32, zero filled)
+// max |x| of a dense fp32 array into *out (non-negative floats order like their bit patterns); *out must start at 0
+__global__ void absmax_kernel(const float* __restrict__ x, size_t n, float* __restrict__ out) {
+  float m = 0.f;
+  const size_t n4 = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = ldg4(x + i * 4);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (blockIdx.x == 0)
+    for (size_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0 && w) atomicMax(reinterpret_cast<unsigned int*>(out), w);
+}
+
+// OIHW fp32 weights -> scaled fp16 hi / lo planes [Cout][ky][kx][Cin_pad] (Cin_pad = Cin rounded up to 32, zero filled);
+// tail[0] = 1 / scale, tail[1] = scale, tail[2] = max |w| (written by absmax_kernel before this kernel runs)
 __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int ksize, int cin_pad,
-                                    float* __restrict__ hi, float* __restrict__ lo) {
+                                    __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ tail) {
   const int taps = ksize * ksize;
   const size_t total = (size_t)cout * taps * cin_pad;
+  float scale, inv;
+  pow2_scale(tail[2], scale, inv);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int ci = (int)(i % cin_pad);
     const size_t r = i / cin_pad;
     const int tap = (int)(r % taps), co = (int)(r / taps);
     float x = 0.f;
-    if (ci < cin) x = w[((size_t)co * cin + ci) * taps + tap];
-    uint32_t h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi[i] = __uint_as_float(h);
-    lo[i] = x - __uint_as_float(h);
+    if (ci < cin) x = w[((size_t)co * cin + ci) * taps + tap] * scale;
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    lo[i] = __float2half_rn(x - __half2float(h));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    tail[0] = inv;
+    tail[1] = scale;
   }
 }
 
@@ -503,24 +561,41 @@ extern "C" int fod_conv2d_debug(long long* buf) {
 
 extern "C" size_t fod_conv2d_packed_floats(int cout, int cin, int ksize) {
   const size_t cin_pad = (size_t)(cin + 31) / 32 * 32;
-  return 2 * (size_t)cout * ksize * ksize * cin_pad;
+  return (size_t)cout * ksize * ksize * cin_pad + 4;   // two fp16 planes + {1/scale, scale, max|w|, 0}
+}
+
+extern "C" int fod_absmax(const float* x, size_t n, float* out, fod_stream_t stream) {
+  FOD_REQUIRE(x && out, "fod_absmax: null pointer");
+  FOD_REQUIRE(((uintptr_t)x & 15) == 0, "fod_absmax: input must be 16-byte aligned");
+  FOD_CUDA_CALL(cudaMemsetAsync(out, 0, sizeof(float), as_stream(stream)));
+  if (n == 0) return FOD_OK;
+  const size_t blocks = (n / 4 + 255) / 256;
+  cvt::absmax_kernel<<<(unsigned)(blocks < 148 * 8 ? (blocks ? blocks : 1) : 148 * 8), 256, 0, as_stream(stream)>>>(x, n, out);
+  FOD_CUDA_LAUNCH_CHECK("fod_absmax");
+  return FOD_OK;
 }
 
 extern "C" int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, float* packed, fod_stream_t stream) {
   FOD_REQUIRE(w_oihw && packed, "fod_conv2d_pack_weights: null pointer");
   FOD_REQUIRE(cout > 0 && cin > 0 && (ksize == 1 || ksize == 3), "fod_conv2d_pack_weights: bad sizes");
+  FOD_REQUIRE((((uintptr_t)w_oihw | (uintptr_t)packed) & 15) == 0, "fod_conv2d_pack_weights: pointers must be 16-byte aligned");
   const int cin_pad = (cin + 31) / 32 * 32;
   const size_t plane = (size_t)cout * ksize * ksize * cin_pad;
+  __half* hi = reinterpret_cast<__half*>(packed);
+  float* tail = packed + plane;
+  int rc = fod_absmax(w_oihw, (size_t)cout * cin * ksize * ksize, tail + 2, stream);
+  if (rc != FOD_OK) return rc;
   const unsigned blocks = (unsigned)((plane + 255) / 256 < 4096 ? (plane + 255) / 256 : 4096);
-  cvt::pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize, cin_pad, packed, packed + plane);
+  cvt::pack_weights_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_oihw, cout, cin, ksize, cin_pad, hi, hi + plane, tail);
   FOD_CUDA_LAUNCH_CHECK("fod_conv2d_pack_weights");
   return FOD_OK;
 }
 
-extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* packed,
-                               const float* bias, int cout, int ksize, int stride, int relu, float* y,
-                               long y_pixel_stride, fod_stream_t stream) {
-  FOD_REQUIRE(x && packed && y, "fod_conv2d_nhwc: null pointer");
+extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax,
+                               int n_amax, const float* packed, const float* bias, int cout, int ksize, int stride,
+                               int relu, float* y, long y_pixel_stride, float* y_amax, fod_stream_t stream) {
+  FOD_REQUIRE(x && packed && y && x_amax, "fod_conv2d_nhwc: null pointer");
+  FOD_REQUIRE(n_amax >= 1 && n_amax <= 8, "fod_conv2d_nhwc: 1..8 input bounds");
   FOD_REQUIRE(n >= 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "fod_conv2d_nhwc: bad sizes");
   FOD_REQUIRE(ksize == 1 || ksize == 3, "fod_conv2d_nhwc: ksize must be 1 or 3");
   FOD_REQUIRE(stride == 1 || (stride == 2 && ksize == 3), "fod_conv2d_nhwc: stride 1, or stride 2 with a 3x3 kernel");
@@ -556,10 +631,14 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.n_groups = (cout + prm.n_group - 1) / prm.n_group;
   prm.nhalf = prm.n_group / 2;
   prm.ncol32 = (prm.n_group + 31) / 32;
-  prm.stages = prm.n_group <= 64 ? cvt::kMaxStages : cvt::kStages;   // 6 x (8 KB weights, 64 TMEM columns) or 4 x (16 KB, 64)
   prm.cout = cout;
   prm.relu = relu;
   prm.bias = bias;
+  prm.x_amax = x_amax;
+  prm.n_amax = n_amax;
+  prm.y_amax = y_amax;
+  prm.ho = ho;
+  prm.wo = wo;
   prm.tiles_x = (wo + cvt::kTileW - 1) / cvt::kTileW;
   prm.tiles_per_img = prm.tiles_x * ((ho + cvt::kTileH - 1) / cvt::kTileH);
   const long tiles = (long)n * prm.tiles_per_img;
@@ -571,10 +650,12 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   rc = cvt::make_nhwc_map_strided(&prm.out_map, y, n, ho, wo, cout, y_pixel_stride, cvt::kChunk, cvt::kTileW, cvt::kTileH, 1);
   if (rc != FOD_OK) return rc;
   const long ktot = (long)prm.taps * cin_pad;
-  rc = make_matrix_map(&prm.whi_map, packed, cout, ktot, cvt::kChunk, prm.nhalf);
+  const __half* whi = reinterpret_cast<const __half*>(packed);
+  rc = make_matrix_map_f16(&prm.whi_map, whi, cout, ktot, cvt::kChunk, prm.nhalf);
   if (rc != FOD_OK) return rc;
-  rc = make_matrix_map(&prm.wlo_map, packed + (size_t)cout * ktot, cout, ktot, cvt::kChunk, prm.nhalf);
+  rc = make_matrix_map_f16(&prm.wlo_map, whi + (size_t)cout * ktot, cout, ktot, cvt::kChunk, prm.nhalf);
   if (rc != FOD_OK) return rc;
+  prm.w_inv = packed + (size_t)cout * ktot;   // tail[0] = 1 / weight scale
   int dev = 0, sms = 0;
   FOD_CUDA_CALL(cudaGetDevice(&dev));
   FOD_CUDA_CALL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

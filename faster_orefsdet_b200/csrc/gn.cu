@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(kThreads) stats_kernel(const float* __restrict
 __global__ void __launch_bounds__(kThreads) apply_kernel(const float* __restrict__ x, float* __restrict__ y, long hw,
                                                          int channels, int cpg, int groups, const double* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         float eps, int relu, size_t total4) {
+                                                         float eps, int relu, size_t total4, float* __restrict__ y_amax) {
   const int c4n = channels >> 2;
+  float vmax = 0.f;
   const double inv_n = 1.0 / ((double)hw * cpg);
   for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total4; i += (size_t)gridDim.x * kThreads) {
     const int c4 = (int)(i % c4n);
@@ -67,6 +68,11 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const float* __restrict
       o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
     }
     *reinterpret_cast<float4*>(y + i * 4) = o;
+    vmax = fmaxf(fmaxf(vmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+  }
+  if (y_amax) {
+    const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+    if ((threadIdx.x & 31) == 0 && w) atomicMax(reinterpret_cast<unsigned int*>(y_amax), w);
   }
 }
 
@@ -78,7 +84,8 @@ using namespace fod;
 extern "C" size_t fod_group_norm_workspace_bytes(int maps, int groups) { return (size_t)maps * groups * 2 * sizeof(double); }
 
 extern "C" int fod_group_norm_nhwc(const float* x, int maps, long hw, int channels, int groups, const float* gamma,
-                                   const float* beta, float eps, int relu, float* y, void* workspace, fod_stream_t stream) {
+                                   const float* beta, float eps, int relu, float* y, float* y_amax, void* workspace,
+                                   fod_stream_t stream) {
   FOD_REQUIRE(x && y && workspace, "fod_group_norm_nhwc: null pointer");
   FOD_REQUIRE(maps >= 0 && hw > 0 && channels > 0 && groups > 0 && channels % groups == 0, "fod_group_norm_nhwc: bad sizes");
   const int cpg = channels / groups;
@@ -101,7 +108,7 @@ extern "C" int fod_group_norm_nhwc(const float* x, int maps, long hw, int channe
   if (blocks > 148 * 16) blocks = 148 * 16;
   gn::apply_kernel<<<(unsigned)blocks, gn::kThreads, 0, as_stream(stream)>>>(x, y, hw, channels, cpg, groups,
                                                                             static_cast<const double*>(workspace), gamma, beta,
-                                                                            eps, relu, total4);
+                                                                            eps, relu, total4, y_amax);
   FOD_CUDA_LAUNCH_CHECK("fod_group_norm_nhwc (apply)");
   return FOD_OK;
 }

@@ -236,6 +236,41 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
          | ((uint32_t)(N >> 3) << 17)    // N / 8
          | ((uint32_t)(M >> 4) << 24);   // M / 16
 }
+// ---- kind::f16 (fp16 operands, fp32 accumulation): K = 16 per instruction.  Measured (tools/f16_probe.cu): 64 cycles
+// at N = 128 and 32 cycles at N = 64, where kind::tf32 (K = 8) needs 64 and 45.
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4)                       // D format  F32
+         | (0u << 7) | (0u << 10)        // A, B format F16
+         | (0u << 15) | (0u << 16)       // A, B K-major
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// Shared-memory operand descriptor, K-major, 64-byte swizzle: rows of 64 bytes (32 fp16 of K), 8 rows per 512-byte atom.
+__device__ __forceinline__ uint64_t smem_desc_k_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                // SWIZZLE_64B
+  return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, A: lane = row, each 32-bit column holds two consecutive fp16 of K (low half first)
+template <int kCtaGroup>
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kCtaGroup == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T
 template <int kCtaGroup>
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -327,5 +362,7 @@ int make_nhwc_map(CUtensorMap* out, const float* base, int N, int H, int W, int 
 // fp32 row-major matrix [rows][cols] -> 2-D tensor map, box (box_cols, box_rows), 128-byte swizzle
 // (box_cols * 4 must be 128), rows beyond the matrix read as zero.
 int make_matrix_map(CUtensorMap* out, const float* base, long rows, long cols, int box_cols, int box_rows);
+// fp16 row-major matrix [rows][cols] -> 2-D tensor map, box (box_cols, box_rows), 64-byte swizzle (box_cols * 2 must be 64)
+int make_matrix_map_f16(CUtensorMap* out, const void* base, long rows, long cols, int box_cols, int box_rows);
 
 }  // namespace fod

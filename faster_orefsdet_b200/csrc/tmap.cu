@@ -52,4 +52,21 @@ int make_matrix_map(CUtensorMap* out, const float* base, long rows, long cols, i
   return FOD_OK;
 }
 
+int make_matrix_map_f16(CUtensorMap* out, const void* base, long rows, long cols, int box_cols, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return FOD_ERR_CUDA;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for fp16 matrix [%ld,%ld] box [%d,%d]", (int)r, rows, cols, box_cols, box_rows);
+    return FOD_ERR_CUDA;
+  }
+  return FOD_OK;
+}
+
 }  // namespace fod

@@ -118,7 +118,8 @@ class _OSAModule(nn.Module):
 
     def forward(self, x):
         if not self.training and all(tcconv.supported(layer[0], x) for layer in self.layers):
-            y = self.ese(self.concat(self._layers_in_place(x)))
+            buf, amax = self._layers_in_place(x)
+            y = self.ese(tcconv.conv(buf, self.concat[0], self.concat[1], relu=True, x_amax=amax))
             return y + x if self.identity else y
         outs = [x]
         y = x
@@ -133,31 +134,37 @@ class _OSAModule(nn.Module):
         return self.layers[0][0].in_channels + sum(layer[0].out_channels for layer in self.layers)
 
     def new_buffer(self, n, h, w, device):
-        """NHWC buffer [x | y0 | y1 | y2] of this module; the producer of x writes its first slice."""
+        """NHWC buffer [x | y0 | y1 | y2] of this module, its first slice (written by the producer of x) and one
+        max|.| scalar per slice (the operand bounds of the tensor-core convolutions, ops.conv2d_nhwc)."""
         buf = torch.empty((n, h, w, self.concat_channels), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
-        return buf, buf[:, :self.layers[0][0].in_channels]
+        return buf, buf[:, :self.layers[0][0].in_channels], ops.new_amax(device, len(self.layers) + 1)
 
-    def _layers_in_place(self, x, buf=None):
+    def _layers_in_place(self, x, buf=None, amax=None):
         """The 3x3 layers write their outputs straight into channel slices of one NHWC buffer
         [x | y0 | y1 | y2] and read their inputs from it: torch.cat never runs."""
         n, c, h, w = x.shape
         if buf is None:
-            buf, first = self.new_buffer(n, h, w, x.device)
+            buf, first, amax = self.new_buffer(n, h, w, x.device)
             first.copy_(x)
+            amax[0:1].copy_(ops.absmax(x if x.is_contiguous(memory_format=torch.channels_last) else first.contiguous(memory_format=torch.channels_last)))
         src, off = buf[:, :c], c
-        for layer in self.layers:
+        for i, layer in enumerate(self.layers):
             cw = layer[0].out_channels
             dst = buf[:, off:off + cw]
-            tcconv.conv(src, layer[0], layer[1], relu=True, out=dst)
+            tcconv.conv(src, layer[0], layer[1], relu=True, out=dst, x_amax=amax[i:i + 1], y_amax=amax[i + 1:i + 2])
             src, off = dst, off + cw
-        return buf
+        return buf, amax
 
-    def forward_buffer(self, buf):
-        """Tensor-core path with x already sitting in the first slice of ``buf``: returns the concat-conv output
-        BEFORE the eSE gate and the gate [N,C,1,1] (the consumer fuses the multiplication)."""
+    def forward_buffer(self, buf, amax):
+        """Tensor-core path with x already sitting in the first slice of ``buf`` (and its bound in amax[0]): returns the
+        concat-conv output BEFORE the eSE gate, the gate [N,C,1,1] (the consumer fuses the multiplication) and the
+        bound of the output."""
         c = self.layers[0][0].in_channels
-        y = self.concat(self._layers_in_place(buf[:, :c], buf))
-        return y, self.ese.gate(y)
+        amax[1:].zero_()
+        self._layers_in_place(buf[:, :c], buf, amax)
+        a_y = ops.new_amax(buf.device)
+        y = tcconv.conv(buf, self.concat[0], self.concat[1], relu=True, x_amax=amax, y_amax=a_y)
+        return y, self.ese.gate(y), a_y
 
 
 class _OSAStage(nn.Sequential):
@@ -218,46 +225,50 @@ class VoVNet(nn.Module):
         return [[m for m in getattr(self, name) if isinstance(m, _OSAModule)][0] for name in self.stage_names]
 
     def tc_new_input_buffer(self, n, h, w, device):
-        """Concat buffer of the first OSA stage for n images of h x w pixels, and its first slice (where stem_3 writes)."""
+        """Concat buffer of the first OSA stage for n images of h x w pixels, its first slice (where stem_3 writes) and
+        its per-slice bounds."""
         h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1       # stem_1
         h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1       # stem_3
         return self._tc_modules()[0].new_buffer(n, h, w, device)
 
-    def tc_stem(self, patches, out):
+    def tc_stem(self, patches, patches_amax, out, out_amax):
         """stem_1 (as a 1x1 convolution over im2col rows) -> stem_2 -> stem_3 into ``out`` (a batch slice of the first
-        slice of the stage-2 concat buffer).  Works on any sub-batch, so a caller can overlap host-to-device copies of
-        later images with the stem of earlier ones."""
+        slice of the stage-2 concat buffer; ``out_amax`` is only ever raised).  Works on any sub-batch, so a caller can
+        overlap host-to-device copies of later images with the stem of earlier ones."""
         pk, b = self._stem1_packed()
-        y = ops.conv2d_nhwc(patches, pk, b, self.stem[0].out_channels, 1, relu=True)
-        y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True)
-        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out)
+        a1, a2 = ops.new_amax(patches.device), ops.new_amax(patches.device)
+        y = ops.conv2d_nhwc(patches, pk, b, self.stem[0].out_channels, 1, relu=True, x_amax=patches_amax, y_amax=a1)
+        y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1, y_amax=a2)
+        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2, y_amax=out_amax)
 
-    def tc_body(self, buf):
+    def tc_body(self, buf, amax, want_amax: bool = False):
         """OSA stages from a filled stage-2 concat buffer.  The stage poolings write straight into the first slice of
-        the next stage's buffer; the eSE gate of a stage is applied inside the pooling that consumes it (and
-        materialised only for the stages that are FPN inputs)."""
-        outputs = {}
+        the next stage's buffer; the eSE gate of a stage (<= 1, so the bound of the ungated map still holds) is applied
+        inside the pooling that consumes it (and materialised only for the stages that are FPN inputs)."""
+        outputs, bounds = {}, {}
         mods = self._tc_modules()
         n = buf.shape[0]
         if "stem" in self._out_features:
-            outputs["stem"] = buf[:, :mods[0].layers[0][0].in_channels]
+            outputs["stem"], bounds["stem"] = buf[:, :mods[0].layers[0][0].in_channels], amax[0:1]
         for i, (name, mod) in enumerate(zip(self.stage_names, mods)):
-            y, gate = mod.forward_buffer(buf)
+            y, gate, a_y = mod.forward_buffer(buf, amax)
             if name in self._out_features:
                 y = y.mul_(gate)
-                outputs[name] = y
+                outputs[name], bounds[name] = y, a_y
                 gate = None
             if i + 1 < len(mods):
                 h, w = (y.shape[2] - 2) // 2 + 1, (y.shape[3] - 2) // 2 + 1
-                buf, first = mods[i + 1].new_buffer(n, h, w, y.device)
+                buf, first, amax = mods[i + 1].new_buffer(n, h, w, y.device)
                 ops.maxpool3x3s2_nhwc(y, gate, out=first)
-        return outputs
+                amax[0:1].copy_(a_y)
+        return (outputs, bounds) if want_amax else outputs
 
     def _forward_tc(self, x):
         """Inference on CUDA: every convolution on the tensor cores (csrc/conv_tc.cu), no torch.cat, no layout copies."""
-        buf, first = self.tc_new_input_buffer(x.shape[0], x.shape[2], x.shape[3], x.device)
-        self.tc_stem(ops.stem_patches(x), first)
-        return self.tc_body(buf)
+        buf, first, amax = self.tc_new_input_buffer(x.shape[0], x.shape[2], x.shape[3], x.device)
+        patches = ops.stem_patches(x)
+        self.tc_stem(patches, ops.absmax(patches), first, amax[0:1])
+        return self.tc_body(buf, amax)
 
     def forward(self, x):
         if self._tc_path(x):
@@ -314,19 +325,32 @@ class FPN(nn.Module):
     def forward(self, x) -> Dict[str, torch.Tensor]:
         return self.top_down(self.bottom_up(x))
 
-    def top_down(self, feats) -> Dict[str, torch.Tensor]:
-        def run(m, t):
-            return tcconv.conv(t, m) if tcconv.supported(m, t) else m(t)
+    def top_down(self, feats, bounds=None) -> Dict[str, torch.Tensor]:
+        """Lateral 1x1 + nearest 2x upsampling + sum + output 3x3.  ``bounds[name]``: device scalar bounding
+        max|feats[name]| when the producer knows it (the tensor-core convolutions need one; computed otherwise)."""
+        bounds = bounds or {}
 
-        prev = run(self._laterals[0], feats[self.in_features[-1]])
-        results = [run(self._outputs[0], prev)]
+        def run(m, t, a_in=None, a_out=None):
+            return tcconv.conv(t, m, x_amax=a_in, y_amax=a_out) if tcconv.supported(m, t) else m(t)
+
+        def bound(t):
+            return ops.new_amax(t.device) if t.is_cuda else None
+
+        top = self.in_features[-1]
+        a_prev = bound(feats[top])
+        prev = run(self._laterals[0], feats[top], bounds.get(top), a_prev)
+        results = [run(self._outputs[0], prev, a_prev)]
         for idx in range(1, len(self._laterals)):
-            f = feats[self.in_features[-idx - 1]]
+            name = self.in_features[-idx - 1]
+            f = feats[name]
             top_down = F.interpolate(prev, scale_factor=2.0, mode="nearest")
-            prev = run(self._laterals[idx], f) + top_down
+            a_lat = bound(f)
+            prev = run(self._laterals[idx], f, bounds.get(name), a_lat) + top_down
+            if a_lat is not None:
+                a_prev = a_lat + a_prev            # |lateral + upsampled| <= bound + bound
             if self._fuse_type == "avg":
                 prev = prev / 2
-            results.insert(0, run(self._outputs[idx], prev))
+            results.insert(0, run(self._outputs[idx], prev, a_prev))
         return dict(zip(self._out_features, results))
 
     def output_shape(self):

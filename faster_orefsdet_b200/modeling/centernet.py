@@ -83,21 +83,23 @@ class CenterNetHead(nn.Module):
         """Tower and output convolutions on the tensor cores (csrc/conv_tc.cu); agn_hm and bbox_pred read the same
         tower output, so they run as ONE convolution with 1 + 4 (+3 zero) output channels."""
         mods = list(self.bbox_tower)
+        bound = None          # device scalar bounding max|t| when the producing kernel reported it
         i = 0
         while i < len(mods):
             m = mods[i]
             if isinstance(m, nn.Conv2d):
-                t = tcconv.conv(t, m)
+                t, bound = tcconv.conv(t, m, x_amax=bound), None
             elif isinstance(m, nn.GroupNorm) and m.num_channels % (4 * m.num_groups) == 0:
                 fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)      # GN + ReLU in one pass, in place
-                t = ops.group_norm_nhwc(t, m.num_groups, m.weight, m.bias, m.eps, relu=fuse, inplace=True)
+                bound = ops.new_amax(t.device)
+                t = ops.group_norm_nhwc(t, m.num_groups, m.weight, m.bias, m.eps, relu=fuse, inplace=True, y_amax=bound)
                 i += int(fuse)
             elif isinstance(m, nn.ReLU):
-                t = F.relu_(t)
+                t = F.relu_(t)          # a bound stays a bound
             else:
-                t = m(t).contiguous(memory_format=torch.channels_last)
+                t, bound = m(t).contiguous(memory_format=torch.channels_last), None
             i += 1
-        y = tcconv.conv(t, self.agn_hm, extra=self.bbox_pred)      # [P, 8, H, W]: hm | l t r b | 0 0 0
+        y = tcconv.conv(t, self.agn_hm, extra=self.bbox_pred, x_amax=bound)      # [P, 8, H, W]: hm | l t r b | 0 0 0
         return y[:, 0:1], y[:, 1:5]
 
 

@@ -192,24 +192,32 @@ class CenterNet2Detector(nn.Module):
         -> FPN maps.  Normalisation is fused into the im2col kernel of stem_1.  With ``events`` (one CUDA event per
         chunk of ``chunk`` images, recorded by the stream that fills ``x_u8``) the stem of chunk k starts as soon as
         chunk k has landed, overlapping the copies of the later chunks."""
-        buf = self._stem_from_uint8(x_u8, events, chunk)
-        return self.backbone.top_down(self.backbone.bottom_up.tc_body(buf))
+        buf, amax = self._stem_from_uint8(x_u8, events, chunk)
+        return self.backbone.top_down(*self.backbone.bottom_up.tc_body(buf, amax, want_amax=True))
 
     def _stem_from_uint8(self, x_u8, events=None, chunk: int = 0, into=None):
         """stem_1..3 of a raw uint8 batch into the first slice of a stage-2 concat buffer (``into`` = (buf, first) of a
         captured graph, or a fresh one); returns the buffer."""
         vov = self.backbone.bottom_up
         n, _, h, w = x_u8.shape
-        buf, first = into if into is not None else vov.tc_new_input_buffer(n, h, w, x_u8.device)
+        buf, first, amax = into if into is not None else vov.tc_new_input_buffer(n, h, w, x_u8.device)
         mean, std = self._mean_std_host()
+        # bound of the normalised image (and of its im2col rows): the extreme raw values 0 and 255
+        key = (tuple(mean), tuple(std), str(x_u8.device))
+        hit = getattr(self, "_patch_bound", None)
+        if hit is None or hit[0] != key:
+            b = max(max(abs(0.0 - m), abs(255.0 - m)) / s for m, s in zip(mean, std))
+            hit = (key, torch.tensor([b], dtype=torch.float32, device=x_u8.device))
+            self._patch_bound = hit
+        amax[0:1].zero_()
         chunk = chunk or n
         main = torch.cuda.current_stream(x_u8.device)
         for k, c0 in enumerate(range(0, n, chunk)):
             c1 = min(c0 + chunk, n)
             if events is not None:
                 main.wait_event(events[k])
-            vov.tc_stem(ops.stem_patches_u8(x_u8[c0:c1], mean, std), first[c0:c1])
-        return buf
+            vov.tc_stem(ops.stem_patches_u8(x_u8[c0:c1], mean, std), hit[1], first[c0:c1], amax[0:1])
+        return buf, amax
 
     def detect_from_uint8(self, x_u8: torch.Tensor, image_sizes, out_sizes, events=None, chunk: int = 0):
         """Raw uint8 batch on the device -> padded detections (boxes, scores, classes, count): the stem eagerly (chunk by
@@ -218,7 +226,7 @@ class CenterNet2Detector(nn.Module):
         if not self.USE_CUDA_GRAPH:
             return self.head(self.features_from_uint8(x_u8, events, chunk), image_sizes, out_sizes)
         g = self._graph_for(n, h, w)
-        self._stem_from_uint8(x_u8, events, chunk, into=(g["buf"], g["first"]))
+        self._stem_from_uint8(x_u8, events, chunk, into=(g["buf"], g["first"], g["amax"]))
         return self._graph_replay(g, image_sizes, out_sizes)
 
     def _mean_std_host(self):
@@ -321,8 +329,8 @@ class CenterNet2Detector(nn.Module):
             return hit
         dev = self.device
         vov = self.backbone.bottom_up
-        buf, first = vov.tc_new_input_buffer(n, h, w, dev)
-        g = {"key": key, "buf": buf, "first": first,
+        buf, first, amax = vov.tc_new_input_buffer(n, h, w, dev)
+        g = {"key": key, "buf": buf, "first": first, "amax": amax,
              "image_hw": torch.zeros((n, 2), dtype=torch.int32, device=dev), "out_hw": torch.zeros((n, 2), dtype=torch.int32, device=dev),
              "sizes_host": torch.zeros((2, n, 2), dtype=torch.int32).pin_memory()}
         g["image_hw"][:] = torch.tensor([h, w], dtype=torch.int32, device=dev)
@@ -330,7 +338,7 @@ class CenterNet2Detector(nn.Module):
         first.zero_()
 
         def run():
-            feats = self.backbone.top_down(vov.tc_body(buf))
+            feats = self.backbone.top_down(*vov.tc_body(buf, amax, want_amax=True))
             return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None)
 
         main = torch.cuda.current_stream(dev)

@@ -1,7 +1,7 @@
 """Host glue for the tensor-core convolution (``fod_conv2d_nhwc``, csrc/conv_tc.cu).
 
 A ``torch.nn.Conv2d`` (optionally followed by a frozen BatchNorm that is folded into it) is
-run on CUDA tensors through the C-ABI kernel: 3xTF32 on tcgen05 = fp32 accuracy, bias and
+run on CUDA tensors through the C-ABI kernel: fp16-split operands on tcgen05 = fp32 accuracy, bias and
 ReLU fused, NHWC in and out, input and output allowed to be channel slices of wider NHWC
 buffers (so an OSA concat is written in place).  CPU tensors take PyTorch's own convolution:
 the backbone module is also what the CPU baseline of bench.py runs on the host cores.
@@ -73,10 +73,12 @@ def packed(conv: nn.Conv2d, norm: Optional[nn.Module] = None, extra: Optional[nn
 
 
 def conv(x: torch.Tensor, m: nn.Conv2d, norm: Optional[nn.Module] = None, relu: bool = False,
-         out: Optional[torch.Tensor] = None, extra: Optional[nn.Conv2d] = None) -> torch.Tensor:
-    """conv (+ folded frozen BN) (+ ReLU) of an NHWC CUDA view; returns [N, Cout_padded_to_4, H, W] (NHWC memory)."""
+         out: Optional[torch.Tensor] = None, extra: Optional[nn.Conv2d] = None, x_amax: Optional[torch.Tensor] = None,
+         y_amax: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """conv (+ folded frozen BN) (+ ReLU) of an NHWC CUDA view; returns [N, Cout_padded_to_4, H, W] (NHWC memory).
+    ``x_amax`` / ``y_amax``: device scalars bounding max|x| (computed when omitted) / receiving max|y| (ops.conv2d_nhwc)."""
     pk, b, cout = packed(m, norm, extra)
-    return ops.conv2d_nhwc(x, pk, b, cout, m.kernel_size[0], relu, out=out, stride=m.stride[0])
+    return ops.conv2d_nhwc(x, pk, b, cout, m.kernel_size[0], relu, out=out, stride=m.stride[0], x_amax=x_amax, y_amax=y_amax)
 
 
 def conv_reference(x: torch.Tensor, m: nn.Conv2d, norm: Optional[nn.Module] = None, relu: bool = False) -> torch.Tensor:

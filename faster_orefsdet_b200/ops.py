@@ -329,10 +329,27 @@ def conv2d_pack(weight: Tensor) -> Tensor:
     return packed
 
 
+def absmax(x: Tensor) -> Tensor:
+    """max |x| of a dense fp32 tensor as a device float[1] (no host sync): the operand bound conv2d_nhwc needs."""
+    _chk(x, torch.float32, "x")
+    if not (x.is_contiguous() or x.is_contiguous(memory_format=torch.channels_last)):
+        raise _lib.FodError("absmax: dense tensor expected")
+    out = torch.empty((1,), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().fod_absmax(_ptr(x), x.numel(), _ptr(out), _stream()), "fod_absmax")
+    return out
+
+
+def new_amax(device, n: int = 1) -> Tensor:
+    return torch.zeros((n,), dtype=torch.float32, device=device)
+
+
 def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ksize: int, relu: bool = False,
-                out: Optional[Tensor] = None, stride: int = 1) -> Tensor:
-    """Convolution with padding ksize//2 on the tensor cores (3xTF32), bias + optional ReLU fused.
-    x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise."""
+                out: Optional[Tensor] = None, stride: int = 1, x_amax: Optional[Tensor] = None,
+                y_amax: Optional[Tensor] = None) -> Tensor:
+    """Convolution with padding ksize//2 on the tensor cores (fp16-split operands, fp32 accuracy), bias + optional
+    ReLU fused.  x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise.
+    ``x_amax``: device float tensor (1..8 values) bounding max|x| (computed with ``absmax`` when omitted, which needs a
+    dense x); ``y_amax``: zeroed device float[1] that receives max|y|."""
     ps_x = _pixel_stride(x, "x")
     n, cin, h, w = x.shape
     pad = ksize // 2
@@ -344,13 +361,21 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
         raise _lib.FodError("conv2d_nhwc: bad output shape")
     if bias is not None:
         bias = _chk(bias, torch.float32, "bias").contiguous()
-    _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(packed), _ptr(bias), cout, ksize, int(stride),
-                                          int(relu), _ptr(out), ps_y, _stream()), "fod_conv2d_nhwc")
+    if x_amax is None:
+        if ps_x != cin:
+            raise _lib.FodError("conv2d_nhwc: x_amax is required for a channel-slice input")
+        x_amax = absmax(x)
+    _chk(x_amax, torch.float32, "x_amax")
+    if y_amax is not None:
+        _chk(y_amax, torch.float32, "y_amax")
+    _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(x_amax), int(x_amax.numel()), _ptr(packed), _ptr(bias),
+                                          cout, ksize, int(stride), int(relu), _ptr(out), ps_y, _ptr(y_amax), _stream()),
+               "fod_conv2d_nhwc")
     return out
 
 
 def group_norm_nhwc(x: Tensor, groups: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,
-                    relu: bool = False, inplace: bool = False) -> Tensor:
+                    relu: bool = False, inplace: bool = False, y_amax: Optional[Tensor] = None) -> Tensor:
     """GroupNorm (+ ReLU) of a dense NHWC map [N,C,H,W] (centernet_head.py:61-72); output NHWC."""
     x = nhwc(x, "x")
     n, c, h, w = x.shape
@@ -359,8 +384,8 @@ def group_norm_nhwc(x: Tensor, groups: int, gamma: Optional[Tensor], beta: Optio
     ws = torch.empty((L.fod_group_norm_workspace_bytes(n, groups) // 8,), dtype=torch.float64, device=x.device)
     g = None if gamma is None else _chk(gamma, torch.float32, "gamma").contiguous()
     b = None if beta is None else _chk(beta, torch.float32, "beta").contiguous()
-    _lib.check(L.fod_group_norm_nhwc(_ptr(x), n, h * w, c, groups, _ptr(g), _ptr(b), float(eps), int(relu), _ptr(y), _ptr(ws),
-                                     _stream()), "fod_group_norm_nhwc")
+    _lib.check(L.fod_group_norm_nhwc(_ptr(x), n, h * w, c, groups, _ptr(g), _ptr(b), float(eps), int(relu), _ptr(y),
+                                     _ptr(y_amax), _ptr(ws), _stream()), "fod_group_norm_nhwc")
     return y
 
 

@@ -206,26 +206,33 @@ int fod_batched_nms(const float* boxes, const float* scores, const int64_t* idxs
                     int64_t* keep, int32_t* keep_count, fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
- * H0  3x3 / 1x1 stride-1 convolution over NHWC fp32 maps (zero padding ksize/2),
- * bias and optional ReLU fused; tcgen05 tensor cores with 3xTF32 operand splitting
- * (fp32 accuracy, ~1e-6 relative).  Replaces the F.conv2d -> cuDNN calls of
- * CenterNetHead.forward (CenterNet2/centernet/modeling/dense_heads/centernet_head.py:
- * 141-161: bbox_tower conv, agn_hm, bbox_pred) and of the modules that hand maps to
- * the head (d2!/modeling/backbone/vovnet.py:205-489 conv3x3/conv1x1 + FrozenBN folded,
+ * H0  3x3 / 1x1 convolution (stride 1, or stride 2 for 3x3) over NHWC fp32 maps, zero padding ksize/2, bias and
+ * optional ReLU fused; tcgen05 tensor cores with fp32 accuracy (~4e-7 relative): every operand is scaled by a power
+ * of two and split into two fp16 values, three kind::f16 MMAs per product, fp32 accumulation.
+ * Replaces the F.conv2d -> cuDNN calls of CenterNetHead.forward
+ * (CenterNet2/centernet/modeling/dense_heads/centernet_head.py:141-161: bbox_tower conv, agn_hm, bbox_pred) and of the
+ * modules that hand maps to the head (d2!/modeling/backbone/vovnet.py:205-489 conv3x3/conv1x1 + FrozenBN folded,
  * d2!/modeling/backbone/fpn.py:113-155 lateral / output convs).
- *   x      : [N][H][W] pixels of x_pixel_stride floats, the first cin of them are read
- *            (a channel slice of a wider NHWC buffer is a valid input)
- *   packed : fod_conv2d_pack_weights output (fod_conv2d_packed_floats floats)
- *   bias   : [cout] or NULL
- *   y      : [N][H][W] pixels of y_pixel_stride floats, the first cout are written
+ *   x       : [N][H][W] pixels of x_pixel_stride floats, the first cin of them are read
+ *             (a channel slice of a wider NHWC buffer is a valid input)
+ *   x_amax  : n_amax (1..8) DEVICE floats, each an upper bound of max|x| over (part of) the input view; their maximum
+ *             fixes the power-of-two operand scale.  Any bound >= the true maximum gives the same result up to 2^-38 of
+ *             the bound; a bound below the true maximum may overflow fp16.  fod_absmax computes it; the kernel that
+ *             produced x normally reports it (y_amax below).
+ *   packed  : fod_conv2d_pack_weights output (fod_conv2d_packed_floats floats)
+ *   bias    : [cout] or NULL
+ *   y       : [N][Ho][Wo] pixels of y_pixel_stride floats, the first cout are written
+ *   y_amax  : NULL, or a DEVICE float (zeroed by the caller) that is atomically raised to max|y|
  * cin, cout and both pixel strides must be multiples of 4; pointers 16-byte aligned.
  */
 size_t fod_conv2d_packed_floats(int cout, int cin, int ksize);
-/* w_oihw : [cout][cin][ksize][ksize] (PyTorch conv weight) -> tf32 hi / lo planes [cout][ky][kx][cin_pad] */
+/* w_oihw : [cout][cin][ksize][ksize] (PyTorch conv weight) -> scaled fp16 hi / lo planes [cout][ky][kx][cin_pad] + scale */
 int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, float* packed, fod_stream_t stream);
-int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* packed,
-                    const float* bias, int cout, int ksize, int stride, int relu, float* y, long y_pixel_stride,
-                    fod_stream_t stream);
+int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax, int n_amax,
+                    const float* packed, const float* bias, int cout, int ksize, int stride, int relu, float* y,
+                    long y_pixel_stride, float* y_amax, fod_stream_t stream);
+/* max |x| of a dense fp32 array -> *out (device float; zeroed inside) */
+int fod_absmax(const float* x, size_t n, float* out, fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * H0  GroupNorm (+ ReLU) over NHWC maps: the normalisation of CenterNetHead's tower
@@ -234,12 +241,14 @@ int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_s
  * group's channels, biased variance, fp64 accumulation across threads.
  *   x, y      : [maps][hw][channels] (y may alias x)
  *   gamma/beta: [channels] or NULL
+ *   y_amax    : NULL, or a DEVICE float (zeroed by the caller) raised to max|y| (the bound fod_conv2d_nhwc needs)
  *   workspace : fod_group_norm_workspace_bytes(maps, groups) bytes, 16-byte aligned
  * channels / groups must be a multiple of 4.
  */
 size_t fod_group_norm_workspace_bytes(int maps, int groups);
 int fod_group_norm_nhwc(const float* x, int maps, long hw, int channels, int groups, const float* gamma,
-                        const float* beta, float eps, int relu, float* y, void* workspace, fod_stream_t stream);
+                        const float* beta, float eps, int relu, float* y, float* y_amax, void* workspace,
+                        fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * Glue of the feature extractor (d2!/modeling/backbone/vovnet.py), memory bound.

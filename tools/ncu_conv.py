@@ -9,7 +9,8 @@ st = a[5] if len(a) > 5 else 1
 x = torch.randn(64, H, W, cin, device="cuda").permute(0, 3, 1, 2)
 packed = ops.conv2d_pack(torch.randn(cout, cin, k, k, device="cuda") * 0.05)
 b = torch.randn(cout, device="cuda")
+ax = ops.absmax(x)
 for _ in range(3):
-    ops.conv2d_nhwc(x, packed, b, cout, k, True, stride=st)
+    ops.conv2d_nhwc(x, packed, b, cout, k, True, stride=st, x_amax=ax)
 torch.cuda.synchronize()
 print("ok")
