@@ -25,10 +25,10 @@
 //     ring and serves all ksize^2 taps: the shifted A operands are read from it, never re-fetched from L2.
 //     (Stride 2: a halo tile would be 17 x 33 pixels, so each tap's 8 x 16 pixels are fetched by their own TMA load
 //     with element strides (2, 2) instead: one ring stage per tap.)
-//   * 16 converter warps (one output pixel per lane = TMEM lane) read the tap-shifted 128-byte row of their pixel
-//     (conflict-free LDS.128 thanks to the TMA swizzle), scale and split it into fp16 hi / lo pairs and write them into
-//     TENSOR MEMORY; the MMA reads A from tensor memory and only the weights from shared memory.
-//     Two sets of 8 warps alternate over the chunks so that their latencies overlap.
+//   * 16 converter warps first convert the staged tile IN PLACE to scaled fp16 hi / lo (once per 32 channels, not once
+//     per tap), then, per tap, one output pixel per lane (= TMEM lane), move the tap-shifted 128-byte row of their pixel
+//     (conflict-free LDS.128 thanks to the TMA swizzle) into TENSOR MEMORY; the MMA reads A from tensor memory and only
+//     the weights from shared memory.  Two sets of 8 warps alternate over the taps so that their latencies overlap.
 //   * weights: pre-split fp16 hi / lo planes [Cout][taps][Cin_pad] (fod_conv2d_pack_weights), TMA-streamed per chunk
 //     into a 6-stage ring (they are L2 resident: <= 0.6 MB per layer).
 //   * the tensor core accumulates with round-toward-zero (tools/tc_probe.cu), so the K loop is cut into partial sums
@@ -419,41 +419,102 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(P.y_amax), wmax);
     }
   } else if (warp >= kWarpConv0) {
-    // ------------------------------------------------------------------ converters: shifted A chunk -> scaled fp16 hi/lo in TMEM
+    // ------------------------------------------------------------------ converters
+    // Phase A, once per staged tile (i.e. once per 32 input channels, not once per tap): all 16 warps convert the tile
+    // IN PLACE from fp32 to scaled fp16 hi / lo: a 128-byte pixel row of 32 floats becomes [32 x hi | 32 x lo], the
+    // 16-byte chunks keep the position swizzle of the TMA (chunk c of row r at c ^ (r & 7)).  A row is shared by two
+    // adjacent lanes (16 channels each) that read it completely before either writes.
+    // Phase B, per tap: one set of 8 warps (the sets alternate over the chunks) moves the tap-shifted row of each
+    // output pixel (one pixel per lane = TMEM lane; conflict-free LDS.128) into TENSOR MEMORY: no arithmetic.
     const int cw = warp - kWarpConv0;
     const int qd = cw & 3, half = (cw >> 2) & 1, set = cw >> 3;
     const int m = qd * 32 + lane;
     const int py = m >> 4, px = m & 15;  // position of this pixel's tap (0,0) in the halo tile
     const bool per_tap = P.per_tap != 0;
+    // a tile that serves a single tap (1x1 kernels, stride 2) is converted on the way to tensor memory instead: no
+    // shared-memory round trip and no barrier between the two warp sets
+    const bool direct = per_tap || taps == 1;
     const uint32_t ready_leader = map_to_cta(ready(0), 0);
     const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColA + half * 8;
     const int ksz = P.ksize, hw = P.halo_w;
+    const int stage_rows = (int)(P.q_stage_bytes >> 7);
+    const int crow = (cw * 32 + lane) >> 1, chalf = lane & 1;   // phase A: (row, 16-channel half) of this lane
     uint32_t g = 0, gq = 0;
+
+    auto convert_stage = [&](uint32_t qt) {
+      const uint32_t at = qt + (uint32_t)crow * 128u;
+      const uint32_t key = (uint32_t)(crow & 7);
+      float4 x[4];
+      if (crow < stage_rows) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = lds4s(at + ((((uint32_t)(chalf * 4 + j)) ^ key) << 4));
+      }
+      __syncwarp();   // both lanes of a row have read it
+      if (crow < stage_rows) {
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          split_f16x2(x[j].x * xs, x[j].y * xs, hi[2 * j + 0], lo[2 * j + 0]);
+          split_f16x2(x[j].z * xs, x[j].w * xs, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        // logical chunks: hi of channels [8c, 8c+8) at c, lo at 4 + c; this lane owns c = 2*chalf, 2*chalf + 1.  The two
+        // lanes of a row write in opposite orders (hi first / lo first) so that a quarter warp never hits a bank twice.
+        const uint32_t c0 = (uint32_t)(2 * chalf);
+        const uint4 h0 = make_uint4(hi[0], hi[1], hi[2], hi[3]), h1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+        const uint4 l0 = make_uint4(lo[0], lo[1], lo[2], lo[3]), l1 = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+        auto put = [&](uint32_t c, const uint4& v) {
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(at + ((c ^ key) << 4)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                       : "memory");
+        };
+        if (chalf == 0) {
+          put(c0, h0); put(c0 + 1, h1); put(4 + c0, l0); put(5 + c0, l1);
+        } else {
+          put(4 + c0, l0); put(5 + c0, l1); put(c0, h0); put(c0 + 1, h1);
+        }
+      }
+      named_bar_sync(2, kConvWarps * 32);   // the whole tile is converted before any warp copies a tap out of it
+    };
+
     for (int i = 0; in_range(i); ++i) {
       for (int cc = 0; cc < cin_chunks; ++cc) {
         int qs = gq % kQStages;
-        if (!per_tap) mbar_wait(q_full(qs), (gq / kQStages) & 1);
         uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
+        if (!per_tap) {
+          mbar_wait(q_full(qs), (gq / kQStages) & 1);
+          if (!direct) convert_stage(qt);
+        }
         int dy = 0, dx = 0;
         for (int tap = 0; tap < taps; ++tap, ++g) {
-          if (per_tap) {  // this tap's own 8 x 16 tile: every warp passes the barrier pair, the owner set reads
+          if (per_tap) {  // this tap's own 8 x 16 tile
             qs = gq % kQStages;
-            mbar_wait(q_full(qs), (gq / kQStages) & 1);
             qt = sbase + kOffQ + qs * P.q_stage_stride;
+            mbar_wait(q_full(qs), (gq / kQStages) & 1);
           }
           if ((int)(g & 1) == set) {
             if (cw == 0 || cw == 8) DBG_STAMP(3, g, 0);
             const int r = per_tap ? m : (py + dy) * hw + px + dx;
             const uint32_t at = qt + (uint32_t)r * 128u;
             const uint32_t key = (uint32_t)(r & 7);
-            float4 x[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = lds4s(at + ((((uint32_t)(half * 4 + j)) ^ key) << 4));
             uint32_t hi[8], lo[8];
+            if (direct) {
+              float4 x[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              split_f16x2(x[j].x * xs, x[j].y * xs, hi[2 * j + 0], lo[2 * j + 0]);
-              split_f16x2(x[j].z * xs, x[j].w * xs, hi[2 * j + 1], lo[2 * j + 1]);
+              for (int j = 0; j < 4; ++j) x[j] = lds4s(at + ((((uint32_t)(half * 4 + j)) ^ key) << 4));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                split_f16x2(x[j].x * xs, x[j].y * xs, hi[2 * j + 0], lo[2 * j + 0]);
+                split_f16x2(x[j].z * xs, x[j].w * xs, hi[2 * j + 1], lo[2 * j + 1]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(hi[4 * j]), "=r"(hi[4 * j + 1]), "=r"(hi[4 * j + 2]), "=r"(hi[4 * j + 3])
+                             : "r"(at + ((((uint32_t)(2 * half + j)) ^ key) << 4)));
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(lo[4 * j]), "=r"(lo[4 * j + 1]), "=r"(lo[4 * j + 2]), "=r"(lo[4 * j + 3])
+                             : "r"(at + ((((uint32_t)(4 + 2 * half + j)) ^ key) << 4)));
+              }
             }
             const int s = (int)(g % stages);
             const uint32_t sph = (g / stages) & 1;
