@@ -37,6 +37,7 @@
 //     border and at Cout by the tensor map, so the output may be a channel slice of a wider NHWC buffer: concatenation
 //     is free).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc05.cuh"
@@ -51,6 +52,7 @@ constexpr int kTileH = 8, kTileW = 16;
 constexpr int kChunk = 32;
 constexpr int kQStages = 3, kStages = 6, kAccStages = 2;
 constexpr int kPartChunks = 16;
+constexpr float kRzKappa = 0.f;  // a scalar compensation of the truncation bias (8.8e-8 per MMA for same-sign sums, tools/rz_calib.py) over-corrects real, mixed-sign layers: off
 constexpr uint32_t kQStageStrideS1 = ((kTileH + 2) * (kTileW + 2) * 128 + 1023) / 1024 * 1024;   // 23552
 constexpr uint32_t kBPlaneMax = 64 * 64;                                    // 64 rows (half of a 128 group) x 32 fp16
 constexpr uint32_t kBStageBytes = 2 * kBPlaneMax;                           // hi + lo
@@ -118,6 +120,9 @@ struct Params {
   const float* x_amax;  // [n_amax] upper bounds of max|x| (their maximum is used)
   const float* w_inv;   // 1 / weight scale (tail of the packed buffer)
   float* y_amax;        // null or: atomically raised to max|y|
+  float rz_kappa;       // first-order compensation of the accumulator's round-toward-zero bias, per MMA of a part
+  const float* res;     // null or: residual [N][res_h][res_w][cout] (dense NHWC) added before the activation;
+  int res_h, res_w, res_shift;   // read at (oy >> res_shift, ox >> res_shift): 0 = same size, 1 = nearest 2x upsampling
   int tiles_x, tiles_per_img, tiles_total;
   int ksize, taps, stride, halo_w, per_tap;  // per_tap: one input-ring stage per (channel chunk, tap) (stride 2)
   int cin_chunks, chunks, parts, chunks_per_part;
@@ -342,6 +347,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t bias_s = sbase + kOffBias;
     const int ncol32 = P.ncol32, parts = P.parts;
     const float rescale = xs_inv * __ldg(P.w_inv);   // undoes the two power-of-two operand scales (exact)
+    // The tensor core truncates its fp32 accumulator toward zero after every MMA: a part that accumulated n MMAs
+    // comes out smaller by ~kappa * n / 2 of its value in expectation (calibrated on the hardware, tools/rz_calib.py).
+    // Each part is scaled back by that factor before it is added; what remains is the unbiased part of the rounding.
+    const int mma_per_chunk = 6;
     float vmax = 0.f;                                // max |y| over the valid outputs this lane produced
     uint32_t gp = 0;
     for (int i = 0; in_range(i); ++i) {
@@ -351,7 +360,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int n = tc_ / P.tiles_per_img, tt = tc_ - n * P.tiles_per_img;
       const int ty = tt / P.tiles_x, tx = tt - ty * P.tiles_x;
       const int ch0 = unit_grp(i) * P.n_group;
-      const bool px_valid = do_store && ty * kTileH + (m >> 4) < P.ho && tx * kTileW + (m & 15) < P.wo;
+      const int oy = ty * kTileH + (m >> 4), ox = tx * kTileW + (m & 15);
+      const bool px_valid = do_store && oy < P.ho && ox < P.wo;
+      const float* res_px = nullptr;   // this pixel's row of the residual map
+      if (P.res && px_valid)
+        res_px = P.res + (((size_t)n * P.res_h + (oy >> P.res_shift)) * P.res_w + (ox >> P.res_shift)) * P.cout;
       if (issuer) tma_store_wait_read<0>();  // the previous tile has left the staging slabs
       named_bar_sync(1, 128);
       {
@@ -366,6 +379,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(acc_full(as_), aph);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + col_acc + as_ * acc_w;
+        const int part_chunks = min(P.chunks_per_part, P.chunks - part * P.chunks_per_part);
+        const float comp = 1.f + P.rz_kappa * 0.5f * (float)(part_chunks * mma_per_chunk);
 #pragma unroll 1
         for (int j = 0; j < ncol32; ++j) {
           uint32_t v[32];
@@ -380,8 +395,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const uint32_t sa = slab + (uint32_t)((c4 ^ (m & 7)) << 4);
-            float4 x = make_float4(__uint_as_float(v[c4 * 4 + 0]), __uint_as_float(v[c4 * 4 + 1]),
-                                   __uint_as_float(v[c4 * 4 + 2]), __uint_as_float(v[c4 * 4 + 3]));
+            float4 x = make_float4(__uint_as_float(v[c4 * 4 + 0]) * comp, __uint_as_float(v[c4 * 4 + 1]) * comp,
+                                   __uint_as_float(v[c4 * 4 + 2]) * comp, __uint_as_float(v[c4 * 4 + 3]) * comp);
             if (part > 0) {
               const float4 r = lds4s(sa);
               x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
@@ -390,6 +405,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const float4 bb = lds4s(bias_s + (j * 32 + c4 * 4) * 4);
               x.x = fmaf(x.x, rescale, bb.x); x.y = fmaf(x.y, rescale, bb.y);
               x.z = fmaf(x.z, rescale, bb.z); x.w = fmaf(x.w, rescale, bb.w);
+              if (res_px && ch0 + j * 32 + c4 * 4 < P.cout) {
+                const float4 rv = ldg4(res_px + ch0 + j * 32 + c4 * 4);
+                x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+              }
               if (P.relu) {
                 x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
               }
@@ -654,8 +673,10 @@ extern "C" int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, i
 
 extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax,
                                int n_amax, const float* packed, const float* bias, int cout, int ksize, int stride,
-                               int relu, float* y, long y_pixel_stride, float* y_amax, fod_stream_t stream) {
+                               int relu, float* y, long y_pixel_stride, float* y_amax, const float* residual,
+                               int residual_upsample2, fod_stream_t stream) {
   FOD_REQUIRE(x && packed && y && x_amax, "fod_conv2d_nhwc: null pointer");
+  FOD_REQUIRE(((uintptr_t)residual & 15) == 0, "fod_conv2d_nhwc: residual must be 16-byte aligned");
   FOD_REQUIRE(n_amax >= 1 && n_amax <= 8, "fod_conv2d_nhwc: 1..8 input bounds");
   FOD_REQUIRE(n >= 0 && h > 0 && w > 0 && cin > 0 && cout > 0, "fod_conv2d_nhwc: bad sizes");
   FOD_REQUIRE(ksize == 1 || ksize == 3, "fod_conv2d_nhwc: ksize must be 1 or 3");
@@ -684,7 +705,13 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.stride = stride;
   prm.cin_chunks = cin_pad / 32;
   prm.chunks = prm.taps * prm.cin_chunks;
-  prm.parts = (prm.chunks + cvt::kPartChunks - 1) / cvt::kPartChunks;
+  // development knobs (tools/rz_calib.py): chunks per partial sum and the bias compensation per MMA
+  int part_chunks = cvt::kPartChunks;
+  float kappa = cvt::kRzKappa;
+  if (const char* e = getenv("FOD_CONV_PART_CHUNKS")) part_chunks = atoi(e) > 0 ? atoi(e) : part_chunks;
+  if (const char* e = getenv("FOD_CONV_RZ_KAPPA")) kappa = (float)atof(e);
+  prm.rz_kappa = kappa;
+  prm.parts = (prm.chunks + part_chunks - 1) / part_chunks;
   prm.chunks_per_part = (prm.chunks + prm.parts - 1) / prm.parts;
   prm.parts = (prm.chunks + prm.chunks_per_part - 1) / prm.chunks_per_part;
   const int n16 = (cout + 15) / 16 * 16;
@@ -700,6 +727,10 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.y_amax = y_amax;
   prm.ho = ho;
   prm.wo = wo;
+  prm.res = residual;
+  prm.res_shift = residual_upsample2 ? 1 : 0;
+  prm.res_h = residual_upsample2 ? (ho + 1) / 2 : ho;
+  prm.res_w = residual_upsample2 ? (wo + 1) / 2 : wo;
   prm.tiles_x = (wo + cvt::kTileW - 1) / cvt::kTileW;
   prm.tiles_per_img = prm.tiles_x * ((ho + cvt::kTileH - 1) / cvt::kTileH);
   const long tiles = (long)n * prm.tiles_per_img;

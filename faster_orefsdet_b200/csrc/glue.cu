@@ -74,6 +74,94 @@ __global__ void __launch_bounds__(kThreads) stem_patches_u8_kernel(const uint8_t
   }
 }
 
+// stem_1 in one pass on the CUDA cores: raw uint8 planar image -> normalise -> 3x3 / stride 2 / pad 1 convolution with 64
+// output channels (BN folded) -> ReLU -> NHWC fp32.  27 x 64 FMAs per output pixel are too few for the tensor-core
+// pipeline to pay (the im2col rows alone are 2.5x the bytes of the result), and the layer is bound by writing its
+// 1.7 GB result.  Four adjacent lanes share a pixel; lane j owns channels {16 i + 4 j .. + 3 : i = 0..3}, so every
+// store instruction of a warp writes 8 x 64 contiguous bytes; the weights sit in shared memory as [27][64].
+constexpr int kStemC = 64;
+__global__ void __launch_bounds__(kThreads) stem1_u8_kernel(const uint8_t* __restrict__ x, int H, int W, int Ho, int Wo,
+                                                            float m0, float m1, float m2, float s0, float s1, float s2,
+                                                            const float* __restrict__ w /*[64][27] = OIHW*/,
+                                                            const float* __restrict__ bias, float* __restrict__ y,
+                                                            float* __restrict__ y_amax, size_t total_pairs, int pairs_per_row) {
+  __shared__ __align__(16) float ws[27][kStemC];
+  __shared__ __align__(16) float bs[kStemC];
+  __shared__ float lut[3][257];   // (v - mean[c]) / std[c] for the 256 raw values (IEEE division, as torch); [256] = padding
+  for (int i = threadIdx.x; i < 27 * kStemC; i += kThreads) {
+    const int co = i % kStemC, k = i / kStemC;         // k = (ky*3 + kx)*3 + c  <-  OIHW index (c*3 + ky)*3 + kx
+    const int tap = k / 3, c = k - tap * 3;
+    ws[k][co] = w[co * 27 + c * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < kStemC; i += kThreads) bs[i] = bias ? bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 3 * 257; i += kThreads) {
+    const int c = i / 257, v = i - c * 257;
+    lut[c][v] = v == 256 ? 0.f : __fdiv_rn(__fsub_rn((float)v, c == 0 ? m0 : (c == 1 ? m1 : m2)), c == 0 ? s0 : (c == 1 ? s1 : s2));
+  }
+  __syncthreads();
+  const int j = threadIdx.x & 3;
+  const size_t plane = (size_t)H * W;
+  float vmax = 0.f;
+  // a group of four lanes computes two horizontally adjacent output pixels (their windows share an input column)
+  for (size_t pr = ((size_t)blockIdx.x * kThreads + threadIdx.x) >> 2; pr < total_pairs; pr += ((size_t)gridDim.x * kThreads) >> 2) {
+    const int px = (int)(pr % pairs_per_row);
+    const size_t r = pr / pairs_per_row;
+    const int oy = (int)(r % Ho);
+    const size_t n = r / Ho;
+    const int ox = 2 * px;
+    const bool second = ox + 1 < Wo;
+    float4 acc[2][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[0][i] = acc[1][i] = *reinterpret_cast<const float4*>(&bs[16 * i + 4 * j]);
+    const uint8_t* img = x + n * 3 * plane;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy + ky - 1;
+      const bool rowin = iy >= 0 && iy < H;
+      const uint8_t* rowp = img + (size_t)(rowin ? iy : 0) * W;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v[5];   // input columns 2*ox - 1 .. 2*ox + 3 of this row and channel
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int ix = 2 * ox - 1 + q;
+          const bool in = rowin && ix >= 0 && ix < W;
+          const int raw = in ? (int)__ldg(rowp + c * plane + ix) : 256;
+          v[q] = lut[c][raw];
+        }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int k = (ky * 3 + kx) * 3 + c;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 wv = *reinterpret_cast<const float4*>(&ws[k][16 * i + 4 * j]);
+            acc[0][i].x = fmaf(v[kx], wv.x, acc[0][i].x); acc[0][i].y = fmaf(v[kx], wv.y, acc[0][i].y);
+            acc[0][i].z = fmaf(v[kx], wv.z, acc[0][i].z); acc[0][i].w = fmaf(v[kx], wv.w, acc[0][i].w);
+            acc[1][i].x = fmaf(v[kx + 2], wv.x, acc[1][i].x); acc[1][i].y = fmaf(v[kx + 2], wv.y, acc[1][i].y);
+            acc[1][i].z = fmaf(v[kx + 2], wv.z, acc[1][i].z); acc[1][i].w = fmaf(v[kx + 2], wv.w, acc[1][i].w);
+          }
+        }
+      }
+    }
+    const size_t pix = (n * Ho + oy) * (size_t)Wo + ox;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (p == 1 && !second) break;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 a = acc[p][i];
+        const float4 o = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+        vmax = fmaxf(fmaxf(vmax, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
+        *reinterpret_cast<float4*>(y + (pix + p) * kStemC + 16 * i + 4 * j) = o;
+      }
+    }
+  }
+  if (y_amax) {
+    const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+    if ((threadIdx.x & 31) == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(y_amax), wm);
+  }
+}
+
 // x: [N][H][W] pixels of xs floats (first C used), gate: [N][C] or null -> y: [N][Ho][Wo] pixels of ys floats
 __global__ void __launch_bounds__(kThreads) maxpool_kernel(const float* __restrict__ x, long xs, int H, int W, int C,
                                                            const float* __restrict__ gate, float* __restrict__ y, long ys,
@@ -137,6 +225,22 @@ extern "C" int fod_stem_patches_u8(const uint8_t* x, int n, int h, int w, const 
   glue::stem_patches_u8_kernel<<<grid_for(total, glue::kThreads), glue::kThreads, 0, as_stream(stream)>>>(
       x, h, w, ho, wo, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], patches, total);
   FOD_CUDA_LAUNCH_CHECK("fod_stem_patches_u8");
+  return FOD_OK;
+}
+
+extern "C" int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, const float* weight,
+                            const float* bias, float* y, float* y_amax, fod_stream_t stream) {
+  FOD_REQUIRE(x && y && mean3 && std3 && weight, "fod_stem1_u8: null pointer");
+  FOD_REQUIRE(n >= 0 && h > 0 && w > 0, "fod_stem1_u8: bad sizes");
+  FOD_REQUIRE(((uintptr_t)y & 15) == 0, "fod_stem1_u8: output must be 16-byte aligned");
+  if (n == 0) return FOD_OK;
+  const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
+  const int pairs_per_row = (wo + 1) / 2;
+  const size_t total_pairs = (size_t)n * ho * pairs_per_row;
+  glue::stem1_u8_kernel<<<grid_for(total_pairs * 4, glue::kThreads), glue::kThreads, 0, as_stream(stream)>>>(
+      x, h, w, ho, wo, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], weight, bias, y, y_amax, total_pairs,
+      pairs_per_row);
+  FOD_CUDA_LAUNCH_CHECK("fod_stem1_u8");
   return FOD_OK;
 }
 

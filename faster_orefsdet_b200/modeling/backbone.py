@@ -231,11 +231,35 @@ class VoVNet(nn.Module):
         h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1       # stem_3
         return self._tc_modules()[0].new_buffer(n, h, w, device)
 
+    def _stem1_folded(self):
+        conv, norm = self.stem[0], self.stem[1]
+        key = tcconv._versions(conv.weight, *norm.buffers())
+        hit = getattr(self, "_stem1_folded_cache", None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                w, b = tcconv.folded(conv, norm)
+                hit = (key, w.detach().float().contiguous(), b.detach().float().contiguous())
+            self._stem1_folded_cache = hit
+        return hit[1], hit[2]
+
+    def tc_stem_u8(self, x_u8, mean, std, out, out_amax):
+        """Raw uint8 images -> stem_1 on the CUDA cores (normalisation fused, ops.stem1_u8) -> stem_2 -> stem_3 into
+        ``out``; same contract as tc_stem."""
+        if self.stem[0].out_channels != 64 or tuple(self.stem[0].weight.shape[1:]) != (3, 3, 3):
+            return self.tc_stem(ops.stem_patches_u8(x_u8, mean, std), None, out, out_amax)
+        w, b = self._stem1_folded()
+        a1, a2 = ops.new_amax(x_u8.device), ops.new_amax(x_u8.device)
+        y = ops.stem1_u8(x_u8, mean, std, w, b, y_amax=a1)
+        y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1, y_amax=a2)
+        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2, y_amax=out_amax)
+
     def tc_stem(self, patches, patches_amax, out, out_amax):
         """stem_1 (as a 1x1 convolution over im2col rows) -> stem_2 -> stem_3 into ``out`` (a batch slice of the first
         slice of the stage-2 concat buffer; ``out_amax`` is only ever raised).  Works on any sub-batch, so a caller can
         overlap host-to-device copies of later images with the stem of earlier ones."""
         pk, b = self._stem1_packed()
+        if patches_amax is None:
+            patches_amax = ops.absmax(patches)
         a1, a2 = ops.new_amax(patches.device), ops.new_amax(patches.device)
         y = ops.conv2d_nhwc(patches, pk, b, self.stem[0].out_channels, 1, relu=True, x_amax=patches_amax, y_amax=a1)
         y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1, y_amax=a2)
@@ -342,14 +366,20 @@ class FPN(nn.Module):
         results = [run(self._outputs[0], prev, a_prev)]
         for idx in range(1, len(self._laterals)):
             name = self.in_features[-idx - 1]
-            f = feats[name]
-            top_down = F.interpolate(prev, scale_factor=2.0, mode="nearest")
-            a_lat = bound(f)
-            prev = run(self._laterals[idx], f, bounds.get(name), a_lat) + top_down
-            if a_lat is not None:
-                a_prev = a_lat + a_prev            # |lateral + upsampled| <= bound + bound
-            if self._fuse_type == "avg":
-                prev = prev / 2
+            f, lat = feats[name], self._laterals[idx]
+            if (tcconv.supported(lat, f) and self._fuse_type == "sum" and lat.out_channels % 4 == 0
+                    and tuple(prev.shape[2:]) == ((f.shape[2] + 1) // 2, (f.shape[3] + 1) // 2)):
+                # nearest 2x upsampling + sum inside the lateral convolution's epilogue; its bound is that of the sum
+                a_prev = bound(f)
+                prev = tcconv.conv(f, lat, x_amax=bounds.get(name), y_amax=a_prev, residual=prev, residual_upsample2=True)
+            else:
+                top_down = F.interpolate(prev, scale_factor=2.0, mode="nearest")
+                a_lat = bound(f)
+                prev = run(lat, f, bounds.get(name), a_lat) + top_down
+                if a_lat is not None:
+                    a_prev = a_lat + a_prev            # |lateral + upsampled| <= bound + bound
+                if self._fuse_type == "avg":
+                    prev = prev / 2
             results.insert(0, run(self._outputs[idx], prev, a_prev))
         return dict(zip(self._out_features, results))
 

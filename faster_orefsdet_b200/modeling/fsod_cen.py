@@ -202,13 +202,6 @@ class CenterNet2Detector(nn.Module):
         n, _, h, w = x_u8.shape
         buf, first, amax = into if into is not None else vov.tc_new_input_buffer(n, h, w, x_u8.device)
         mean, std = self._mean_std_host()
-        # bound of the normalised image (and of its im2col rows): the extreme raw values 0 and 255
-        key = (tuple(mean), tuple(std), str(x_u8.device))
-        hit = getattr(self, "_patch_bound", None)
-        if hit is None or hit[0] != key:
-            b = max(max(abs(0.0 - m), abs(255.0 - m)) / s for m, s in zip(mean, std))
-            hit = (key, torch.tensor([b], dtype=torch.float32, device=x_u8.device))
-            self._patch_bound = hit
         amax[0:1].zero_()
         chunk = chunk or n
         main = torch.cuda.current_stream(x_u8.device)
@@ -216,7 +209,7 @@ class CenterNet2Detector(nn.Module):
             c1 = min(c0 + chunk, n)
             if events is not None:
                 main.wait_event(events[k])
-            vov.tc_stem(ops.stem_patches_u8(x_u8[c0:c1], mean, std), hit[1], first[c0:c1], amax[0:1])
+            vov.tc_stem_u8(x_u8[c0:c1], mean, std, first[c0:c1], amax[0:1])
         return buf, amax
 
     def detect_from_uint8(self, x_u8: torch.Tensor, image_sizes, out_sizes, events=None, chunk: int = 0):

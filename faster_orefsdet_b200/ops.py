@@ -345,7 +345,7 @@ def new_amax(device, n: int = 1) -> Tensor:
 
 def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ksize: int, relu: bool = False,
                 out: Optional[Tensor] = None, stride: int = 1, x_amax: Optional[Tensor] = None,
-                y_amax: Optional[Tensor] = None) -> Tensor:
+                y_amax: Optional[Tensor] = None, residual: Optional[Tensor] = None, residual_upsample2: bool = False) -> Tensor:
     """Convolution with padding ksize//2 on the tensor cores (fp16-split operands, fp32 accuracy), bias + optional
     ReLU fused.  x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise.
     ``x_amax``: device float tensor (1..8 values) bounding max|x| (computed with ``absmax`` when omitted, which needs a
@@ -368,9 +368,14 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
     _chk(x_amax, torch.float32, "x_amax")
     if y_amax is not None:
         _chk(y_amax, torch.float32, "y_amax")
+    if residual is not None:     # added before the activation; with residual_upsample2 read at (oy // 2, ox // 2)
+        residual = nhwc(residual, "residual")
+        rh, rw = ((ho + 1) // 2, (wo + 1) // 2) if residual_upsample2 else (ho, wo)
+        if tuple(residual.shape) != (n, cout, rh, rw):
+            raise _lib.FodError(f"conv2d_nhwc: residual shape {tuple(residual.shape)}, expected {(n, cout, rh, rw)}")
     _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(x_amax), int(x_amax.numel()), _ptr(packed), _ptr(bias),
-                                          cout, ksize, int(stride), int(relu), _ptr(out), ps_y, _ptr(y_amax), _stream()),
-               "fod_conv2d_nhwc")
+                                          cout, ksize, int(stride), int(relu), _ptr(out), ps_y, _ptr(y_amax), _ptr(residual),
+                                          int(residual_upsample2), _stream()), "fod_conv2d_nhwc")
     return out
 
 
@@ -416,6 +421,27 @@ def stem_patches_u8(x: Tensor, mean: Sequence[float], std: Sequence[float], out:
         raise _lib.FodError("stem_patches_u8: bad output")
     m3, s3 = (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std])
     _lib.check(_lib.lib().fod_stem_patches_u8(_ptr(x), n, h, w, m3, s3, _ptr(out), _stream()), "fod_stem_patches_u8")
+    return out
+
+
+def stem1_u8(x: Tensor, mean: Sequence[float], std: Sequence[float], weight: Tensor, bias: Optional[Tensor],
+             y_amax: Optional[Tensor] = None) -> Tensor:
+    """Raw uint8 batch [N,3,H,W] -> normalise -> stem_1 (3x3 / 2, 64 channels, BN folded into weight / bias) -> ReLU,
+    one CUDA-core pass; returns [N,64,ceil(H/2),ceil(W/2)] (NHWC memory)."""
+    _chk(x, torch.uint8, "x")
+    if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+        raise _lib.FodError("stem1_u8: contiguous [N,3,H,W] uint8 expected")
+    weight = _chk(weight, torch.float32, "weight").contiguous()
+    if tuple(weight.shape) != (64, 3, 3, 3):
+        raise _lib.FodError("stem1_u8: weight [64,3,3,3] expected")
+    if bias is not None:
+        bias = _chk(bias, torch.float32, "bias").contiguous()
+    n, _, h, w = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty((n, ho, wo, 64), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+    m3, s3 = (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std])
+    _lib.check(_lib.lib().fod_stem1_u8(_ptr(x), n, h, w, m3, s3, _ptr(weight), _ptr(bias), _ptr(out), _ptr(y_amax), _stream()),
+               "fod_stem1_u8")
     return out
 
 

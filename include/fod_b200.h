@@ -223,6 +223,9 @@ int fod_batched_nms(const float* boxes, const float* scores, const int64_t* idxs
  *   bias    : [cout] or NULL
  *   y       : [N][Ho][Wo] pixels of y_pixel_stride floats, the first cout are written
  *   y_amax  : NULL, or a DEVICE float (zeroed by the caller) that is atomically raised to max|y|
+ *   residual: NULL, or a dense NHWC map with cout channels added to the convolution (+ bias) before the activation:
+ *             [N][Ho][Wo][cout], or with residual_upsample2 [N][ceil(Ho/2)][ceil(Wo/2)][cout] read at (oy/2, ox/2) -
+ *             the nearest-neighbour 2x upsampling + sum of the FPN top-down path (d2!/modeling/backbone/fpn.py:139-147)
  * cin, cout and both pixel strides must be multiples of 4; pointers 16-byte aligned.
  */
 size_t fod_conv2d_packed_floats(int cout, int cin, int ksize);
@@ -230,7 +233,7 @@ size_t fod_conv2d_packed_floats(int cout, int cin, int ksize);
 int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, float* packed, fod_stream_t stream);
 int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax, int n_amax,
                     const float* packed, const float* bias, int cout, int ksize, int stride, int relu, float* y,
-                    long y_pixel_stride, float* y_amax, fod_stream_t stream);
+                    long y_pixel_stride, float* y_amax, const float* residual, int residual_upsample2, fod_stream_t stream);
 /* max |x| of a dense fp32 array -> *out (device float; zeroed inside) */
 int fod_absmax(const float* x, size_t n, float* out, fod_stream_t stream);
 
@@ -264,6 +267,12 @@ int fod_stem_patches(const float* x, int n, int h, int w, float* patches, fod_st
  * (CenterNet2Detector.preprocess_image, fewx/modeling/fsod/fsod_cen.py:540-555); mean3 / std3 are HOST arrays of 3 floats */
 int fod_stem_patches_u8(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, float* patches,
                         fod_stream_t stream);
+/* stem_1 in one pass (CUDA cores, fp32 FMA): raw uint8 planar batch x [N][3][H][W] -> (x - mean)/std -> 3x3 / stride 2 /
+ * pad 1 convolution, 64 output channels, weight [64][3][3][3] (OIHW, FrozenBN folded), bias [64] or NULL -> ReLU ->
+ * y [N][ceil(H/2)][ceil(W/2)][64] NHWC; y_amax as in fod_conv2d_nhwc.  (d2!/modeling/backbone/vovnet.py stem_1 +
+ * fsod_cen.py:540-555) */
+int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, const float* weight,
+                 const float* bias, float* y, float* y_amax, fod_stream_t stream);
 int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate, float* y,
                           long y_pixel_stride, fod_stream_t stream);
 

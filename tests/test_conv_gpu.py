@@ -138,3 +138,33 @@ def test_stem_patches_and_gated_maxpool_match_torch():
     buf = torch.zeros((2, 10, 15, 40), device=DEV).permute(0, 3, 1, 2)
     ops.maxpool3x3s2_nhwc(t.to(DEV).contiguous(memory_format=torch.channels_last), gate.to(DEV), out=buf[:, 8:32])
     assert torch.equal(buf[:, 8:32].cpu(), ref) and float(buf[:, :8].abs().max()) == 0 and float(buf[:, 32:].abs().max()) == 0
+
+
+def test_stem1_u8_matches_normalise_then_conv():
+    x = (synth.tensor((2, 3, 38, 52), 81, 0.0, 255.99)).to(torch.uint8)
+    mean, std = [103.53, 116.28, 123.675], [1.0, 57.4, 58.4]
+    w = synth.tensor((64, 3, 3, 3), 82, -0.3, 0.3)
+    b = synth.tensor((64,), 83, -1.0, 1.0)
+    xn = (x.double() - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    ref = F.conv2d(xn, w.double(), b.double(), stride=2, padding=1).relu().float()
+    bound = ops.new_amax(DEV)
+    y = ops.stem1_u8(x.to(DEV), mean, std, w.to(DEV), b.to(DEV), y_amax=bound)
+    assert tuple(y.shape) == (2, 64, 19, 26) and y.stride(1) == 1
+    _check(y, ref, "stem_1")
+    assert abs(float(bound) - float(ref.max())) <= 1e-5 * float(ref.max())
+
+
+@pytest.mark.parametrize("up2", [False, True])
+def test_conv2d_nhwc_residual_in_epilogue(up2):
+    """FPN top-down step: lateral 1x1 + (nearest 2x upsampled) coarser map, fused into the convolution's epilogue."""
+    n, h, w, cin, cout = 2, 20, 28, 96, 128
+    x = synth.tensor((n, cin, h, w), 91, -1.0, 1.0)
+    wt = synth.tensor((cout, cin, 1, 1), 92, -0.1, 0.1)
+    b = synth.tensor((cout,), 93, -0.5, 0.5)
+    r = synth.tensor((n, cout, h // 2, w // 2) if up2 else (n, cout, h, w), 94, -2.0, 2.0)
+    ref = _ref(x, wt, b, False) + (F.interpolate(r, scale_factor=2.0, mode="nearest") if up2 else r)
+    bound = ops.new_amax(DEV)
+    y = ops.conv2d_nhwc(x.to(DEV).contiguous(memory_format=torch.channels_last), ops.conv2d_pack(wt.to(DEV)), b.to(DEV), cout, 1,
+                        residual=r.to(DEV).contiguous(memory_format=torch.channels_last), residual_upsample2=up2, y_amax=bound)
+    _check(y, ref, "conv + residual")
+    assert abs(float(bound) - float(ref.abs().max())) <= 1e-5 * float(ref.abs().max())

@@ -224,7 +224,7 @@ def test_prototype_builder_matches_reference_cache_build():
 
 def test_pipelined_uint8_input_path_equals_generic_path():
     """model(batched_inputs) with equally sized uint8 images (chunked host-to-device copies, normalisation fused into
-    the stem kernel) must give the features of preprocess_image + backbone bit for bit."""
+    the stem kernel) must give the features of preprocess_image + backbone."""
     model = _model()
     shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
     model.load_state_dict(synth.state_dict(shapes), strict=False)
@@ -235,8 +235,12 @@ def test_pipelined_uint8_input_path_equals_generic_path():
     assert feats is not None and sizes == [(128, 160)] * 5
     ref = model.backbone(model.preprocess_image(inputs).tensor)
     torch.cuda.synchronize()
+    # stem_1 runs as fp32 FMAs on this path and as a tensor-core convolution over im2col rows on the other.  The
+    # synthetic (hash) weights make the 20-layer extractor ill-conditioned: per-layer differences of 5e-7 of the output
+    # scale grow to ~1e-4 of the map's maximum at p5 (tools/dbg_backbone.py; cuDNN's own fp32 engines end 3e-5 away from
+    # float64 on the same network).
     for k in ref:
-        assert torch.equal(feats[k], ref[k]), k
+        assert_close(feats[k], ref[k], rtol=1e-3, atol=4e-4 * float(ref[k].abs().max()), what=k)
     # float images or a size that needs padding fall back to the generic path
     assert model._features_pipelined([{"image": imgs[0].float()}])[0] is None
     assert model._features_pipelined([{"image": synth.ore_image(100, 160, 1)}])[0] is None
@@ -259,3 +263,20 @@ def test_cuda_graph_replay_equals_eager_launches():
         for a, b in zip(got, ref):
             assert torch.equal(a, b)
     assert model._graph["graph"] is not None
+
+
+def test_tensor_core_backbone_matches_reference_vovnet_fpn():
+    """The feature extractor on the tensor-core path against the outputs recorded from the reference's own
+    VoVNet-19-slim-eSE + FPN (tests/golden/backbone.npz; the CPU test_host_cpu.py checks the same vectors through ATen).
+    Tolerance: 4e-4 of each map's maximum (see the note in the test above)."""
+    from tests.util import golden, t
+    model = _model()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    g = golden("backbone")
+    x = synth.tensor((2, 3, 96, 160), 601, -120.0, 130.0).cuda().contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        out = model.backbone(x)
+    for k in ("p3", "p4", "p5"):
+        ref = t(g[k])
+        assert_close(out[k], ref, rtol=1e-3, atol=4e-4 * float(ref.abs().max()), what=k)
