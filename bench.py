@@ -27,7 +27,8 @@ from faster_orefsdet_b200 import synth  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one conv_tc_kernel launch (ncu --set full, batch 64), keyed by
 # (H, W, Cin, Cout, ksize, stride); profiles/r1_ncu_v3_summary.md
-NCU_CONV_TRAFFIC = {}
+NCU_CONV_TRAFFIC = {(320, 320, 64, 64, 3, 1): 1.678e9 + 1.633e9,      # stem_2: algorithmic 2 x 1.678 GB (read x, write y)
+                    (80, 80, 128, 128, 3, 1): 210.4e6 + 162.2e6}
 
 METRIC = "query_images_per_sec"
 UNIT = "images/s"

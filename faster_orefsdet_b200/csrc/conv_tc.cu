@@ -121,13 +121,15 @@ struct Params {
   const float* w_inv;   // 1 / weight scale (tail of the packed buffer)
   float* y_amax;        // null or: atomically raised to max|y|
   float rz_kappa;       // first-order compensation of the accumulator's round-toward-zero bias, per MMA of a part
+  const float* a_gate;  // null or: [N][Cin] factors multiplied into the input (the eSE gate of the producing stage)
+  float* colsum;        // null or: [N][tiles_per_img][Cout] per-tile channel sums of the output (for the eSE average)
   const float* res;     // null or: residual [N][res_h][res_w][cout] (dense NHWC) added before the activation;
   int res_h, res_w, res_shift;   // read at (oy >> res_shift, ox >> res_shift): 0 = same size, 1 = nearest 2x upsampling
   int tiles_x, tiles_per_img, tiles_total;
   int ksize, taps, stride, halo_w, per_tap;  // per_tap: one input-ring stage per (channel chunk, tap) (stride 2)
   int cin_chunks, chunks, parts, chunks_per_part;
   int n_groups, n_group, nhalf, ncol32, cout;
-  int relu, num_pairs, pair_units, n_amax, ho, wo;
+  int relu, num_pairs, pair_units, n_amax, ho, wo, cin;
   uint32_t q_stage_bytes, q_stage_stride;
 };
 
@@ -431,6 +433,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           tma_store_4d(&P.out_map, sbase + kOffSum + j * kSlabBytes, ch0 + j * 32, tx * kTileW, ty * kTileH, n);
         tma_store_commit();
       }
+      if (P.colsum && do_store && qd < ncol32) {
+        // Channel sums over the tile's pixels that lie inside the image, in a fixed order (deterministic, independent of
+        // the batch).  Warp = 32-channel slab; lane = (row offset 0..3, 4-channel group): a warp reads four consecutive
+        // 128-byte rows per step (conflict-free), 32 steps cover the tile; the four row offsets meet in two shuffles.
+        const int vy = min(kTileH, P.ho - ty * kTileH), vx = min(kTileW, P.wo - tx * kTileW);
+        const uint32_t c4 = (uint32_t)(lane & 7), ro = (uint32_t)(lane >> 3);
+        const uint32_t sb = sbase + kOffSum + (uint32_t)qd * kSlabBytes;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (uint32_t r0 = 0; r0 < 128; r0 += 4) {
+          const uint32_t r = r0 + ro;
+          if ((int)(r >> 4) < vy && (int)(r & 15) < vx) {
+            const float4 v = lds4s(sb + (r >> 3) * 1024 + (r & 7) * 128 + ((c4 ^ (r & 7)) << 4));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+        }
+#pragma unroll
+        for (int sh = 8; sh <= 16; sh <<= 1) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sh); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sh);
+          acc.z += __shfl_xor_sync(0xffffffffu, acc.z, sh); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, sh);
+        }
+        const int ch = ch0 + qd * 32 + (int)c4 * 4;
+        if (ro == 0 && ch < P.cout)
+          *reinterpret_cast<float4*>(P.colsum + ((size_t)n * P.tiles_per_img + tt) * P.cout + ch) = acc;
+      }
     }
     if (issuer) tma_store_wait<0>();
     if (P.y_amax) {   // non-negative floats order like their bit patterns; a NaN becomes a huge bound (scale 1 downstream)
@@ -460,13 +487,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int crow = (cw * 32 + lane) >> 1, chalf = lane & 1;   // phase A: (row, 16-channel half) of this lane
     uint32_t g = 0, gq = 0;
 
+    const float* gate_row = nullptr;   // a_gate row of this unit's image, at this chunk's first channel
+    auto gated = [&](float4 v, int c4) {   // c4: index of the 4-channel group inside the 32-channel chunk
+      if (gate_row) {
+        const float4 gv = ldg4(gate_row + c4 * 4);
+        v.x *= gv.x; v.y *= gv.y; v.z *= gv.z; v.w *= gv.w;
+      }
+      return v;
+    };
     auto convert_stage = [&](uint32_t qt) {
       const uint32_t at = qt + (uint32_t)crow * 128u;
       const uint32_t key = (uint32_t)(crow & 7);
       float4 x[4];
       if (crow < stage_rows) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) x[j] = lds4s(at + ((((uint32_t)(chalf * 4 + j)) ^ key) << 4));
+        for (int j = 0; j < 4; ++j) x[j] = gated(lds4s(at + ((((uint32_t)(chalf * 4 + j)) ^ key) << 4)), chalf * 4 + j);
       }
       __syncwarp();   // both lanes of a row have read it
       if (crow < stage_rows) {
@@ -495,7 +530,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     };
 
     for (int i = 0; in_range(i); ++i) {
+      const int unit_n = min(unit_tile(i), P.tiles_total - 1) / P.tiles_per_img;
       for (int cc = 0; cc < cin_chunks; ++cc) {
+        if (P.a_gate) gate_row = P.a_gate + (size_t)unit_n * P.cin + cc * kChunk;
         int qs = gq % kQStages;
         uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
         if (!per_tap) {
@@ -518,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (direct) {
               float4 x[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) x[j] = lds4s(at + ((((uint32_t)(half * 4 + j)) ^ key) << 4));
+              for (int j = 0; j < 4; ++j) x[j] = gated(lds4s(at + ((((uint32_t)(half * 4 + j)) ^ key) << 4)), half * 4 + j);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 split_f16x2(x[j].x * xs, x[j].y * xs, hi[2 * j + 0], lo[2 * j + 0]);
@@ -584,6 +621,37 @@ __global__ void absmax_kernel(const float* __restrict__ x, size_t n, float* __re
   if ((threadIdx.x & 31) == 0 && w) atomicMax(reinterpret_cast<unsigned int*>(out), w);
 }
 
+// eSE gate from the per-tile channel sums of a convolution (vovnet.py eSEModule: x * hsigmoid(fc(avg_pool(x)))):
+// gate[n][o] = relu6(b[o] + sum_i W[o][i] * mean[n][i] + 3) / 6, mean = sum over tiles / hw.  One CTA per image.
+__global__ void __launch_bounds__(256) ese_gate_kernel(const float* __restrict__ colsum, int tiles, int c, float inv_hw,
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       float* __restrict__ gate) {
+  extern __shared__ float mean[];   // [c] means, then [8][c] partial sums
+  float* part = mean + c;
+  const float* cs = colsum + (size_t)blockIdx.x * tiles * c;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  // warp w sums the tiles t = w, w + 8, ... (coalesced rows of c floats), the 8 partials are added in a fixed order
+  for (int i = lane; i < c; i += 32) {
+    float acc = 0.f;
+    for (int t = warp; t < tiles; t += nw) acc += __ldg(cs + (size_t)t * c + i);
+    part[warp * c + i] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    float acc = 0.f;
+    for (int w8 = 0; w8 < nw; ++w8) acc += part[w8 * c + i];
+    mean[i] = acc * inv_hw;
+  }
+  __syncthreads();
+  for (int o = warp; o < c; o += nw) {
+    float acc = 0.f;
+    for (int i = lane; i < c; i += 32) acc = fmaf(__ldg(w + (size_t)o * c + i), mean[i], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) gate[(size_t)blockIdx.x * c + o] = fminf(fmaxf(acc + b[o] + 3.f, 0.f), 6.f) / 6.f;
+  }
+}
+
 // OIHW fp32 weights -> scaled fp16 hi / lo planes [Cout][ky][kx][Cin_pad] (Cin_pad = Cin rounded up to 32, zero filled);
 // tail[0] = 1 / scale, tail[1] = scale, tail[2] = max |w| (written by absmax_kernel before this kernel runs)
 __global__ void pack_weights_kernel(const float* __restrict__ w, int cout, int cin, int ksize, int cin_pad,
@@ -644,6 +712,21 @@ extern "C" size_t fod_conv2d_packed_floats(int cout, int cin, int ksize) {
   return (size_t)cout * ksize * ksize * cin_pad + 4;   // two fp16 planes + {1/scale, scale, max|w|, 0}
 }
 
+extern "C" int fod_conv2d_tiles_per_image(int ho, int wo) {
+  return ((wo + cvt::kTileW - 1) / cvt::kTileW) * ((ho + cvt::kTileH - 1) / cvt::kTileH);
+}
+
+extern "C" int fod_ese_gate(const float* colsum, int n, int tiles_per_img, int channels, long hw, const float* fc_weight,
+                            const float* fc_bias, float* gate, fod_stream_t stream) {
+  FOD_REQUIRE(colsum && fc_weight && fc_bias && gate, "fod_ese_gate: null pointer");
+  FOD_REQUIRE(n >= 0 && tiles_per_img > 0 && channels > 0 && channels <= 1024 && hw > 0, "fod_ese_gate: bad sizes");
+  if (n == 0) return FOD_OK;
+  cvt::ese_gate_kernel<<<n, 256, 9 * channels * sizeof(float), as_stream(stream)>>>(colsum, tiles_per_img, channels, 1.f / (float)hw,
+                                                                              fc_weight, fc_bias, gate);
+  FOD_CUDA_LAUNCH_CHECK("fod_ese_gate");
+  return FOD_OK;
+}
+
 extern "C" int fod_absmax(const float* x, size_t n, float* out, fod_stream_t stream) {
   FOD_REQUIRE(x && out, "fod_absmax: null pointer");
   FOD_REQUIRE(((uintptr_t)x & 15) == 0, "fod_absmax: input must be 16-byte aligned");
@@ -674,7 +757,9 @@ extern "C" int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, i
 extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax,
                                int n_amax, const float* packed, const float* bias, int cout, int ksize, int stride,
                                int relu, float* y, long y_pixel_stride, float* y_amax, const float* residual,
-                               int residual_upsample2, fod_stream_t stream) {
+                               int residual_upsample2, const float* a_gate, float* colsum, fod_stream_t stream) {
+  FOD_REQUIRE((((uintptr_t)a_gate | (uintptr_t)colsum) & 15) == 0, "fod_conv2d_nhwc: a_gate / colsum must be 16-byte aligned");
+  FOD_REQUIRE(!a_gate || cin % 32 == 0, "fod_conv2d_nhwc: a_gate needs cin to be a multiple of 32");
   FOD_REQUIRE(x && packed && y && x_amax, "fod_conv2d_nhwc: null pointer");
   FOD_REQUIRE(((uintptr_t)residual & 15) == 0, "fod_conv2d_nhwc: residual must be 16-byte aligned");
   FOD_REQUIRE(n_amax >= 1 && n_amax <= 8, "fod_conv2d_nhwc: 1..8 input bounds");
@@ -727,6 +812,9 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.y_amax = y_amax;
   prm.ho = ho;
   prm.wo = wo;
+  prm.a_gate = a_gate;
+  prm.colsum = colsum;
+  prm.cin = cin;
   prm.res = residual;
   prm.res_shift = residual_upsample2 ? 1 : 0;
   prm.res_h = residual_upsample2 ? (ho + 1) / 2 : ho;

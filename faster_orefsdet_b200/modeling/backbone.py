@@ -168,8 +168,13 @@ class _OSAModule(nn.Module):
         amax[1:].zero_()
         self._layers_in_place(buf[:, :c], buf, amax)
         a_y = ops.new_amax(buf.device)
-        y = tcconv.conv(buf, self.concat[0], self.concat[1], relu=True, x_amax=amax, y_amax=a_y)
-        return y, self.ese.gate(y), a_y
+        n, _, h, w = buf.shape
+        cout = self.concat[0].out_channels
+        # the eSE average comes out of the concat convolution's epilogue as per-tile channel sums: no pass over y
+        colsum = torch.empty((n, ops.conv2d_tiles_per_image(h, w), cout), dtype=torch.float32, device=buf.device)
+        y = tcconv.conv(buf, self.concat[0], self.concat[1], relu=True, x_amax=amax, y_amax=a_y, colsum=colsum)
+        gate = ops.ese_gate(colsum, h * w, self.ese.fc.weight, self.ese.fc.bias)
+        return y, gate.view(n, cout, 1, 1), a_y
 
 
 class _OSAStage(nn.Sequential):
@@ -270,11 +275,13 @@ class VoVNet(nn.Module):
         y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1, y_amax=a2)
         tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2, y_amax=out_amax)
 
-    def tc_body(self, buf, amax, want_amax: bool = False):
+    def tc_body(self, buf, amax, want_amax: bool = False, fuse_gates: bool = False):
         """OSA stages from a filled stage-2 concat buffer.  The stage poolings write straight into the first slice of
         the next stage's buffer; the eSE gate of a stage (<= 1, so the bound of the ungated map still holds) is applied
-        inside the pooling that consumes it (and materialised only for the stages that are FPN inputs)."""
-        outputs, bounds = {}, {}
+        inside the pooling that consumes it.  For the stages that are FPN inputs the gated map is materialised, unless
+        ``fuse_gates``: then the UNGATED map is returned together with its gate (third result, {name: [N,C,1,1]}) and the
+        consumer multiplies it in (FPN.top_down passes it to the lateral convolution)."""
+        outputs, bounds, gates = {}, {}, {}
         mods = self._tc_modules()
         n = buf.shape[0]
         if "stem" in self._out_features:
@@ -282,14 +289,19 @@ class VoVNet(nn.Module):
         for i, (name, mod) in enumerate(zip(self.stage_names, mods)):
             y, gate, a_y = mod.forward_buffer(buf, amax)
             if name in self._out_features:
-                y = y.mul_(gate)
-                outputs[name], bounds[name] = y, a_y
-                gate = None
+                if fuse_gates:
+                    outputs[name], bounds[name], gates[name] = y, a_y, gate
+                else:
+                    y = y.mul_(gate)
+                    outputs[name], bounds[name] = y, a_y
+                    gate = None
             if i + 1 < len(mods):
                 h, w = (y.shape[2] - 2) // 2 + 1, (y.shape[3] - 2) // 2 + 1
                 buf, first, amax = mods[i + 1].new_buffer(n, h, w, y.device)
                 ops.maxpool3x3s2_nhwc(y, gate, out=first)
                 amax[0:1].copy_(a_y)
+        if fuse_gates:
+            return outputs, bounds, gates
         return (outputs, bounds) if want_amax else outputs
 
     def _forward_tc(self, x):
@@ -354,33 +366,39 @@ class FPN(nn.Module):
     def forward(self, x) -> Dict[str, torch.Tensor]:
         return self.top_down(self.bottom_up(x))
 
-    def top_down(self, feats, bounds=None) -> Dict[str, torch.Tensor]:
+    def top_down(self, feats, bounds=None, gates=None) -> Dict[str, torch.Tensor]:
         """Lateral 1x1 + nearest 2x upsampling + sum + output 3x3.  ``bounds[name]``: device scalar bounding
-        max|feats[name]| when the producer knows it (the tensor-core convolutions need one; computed otherwise)."""
-        bounds = bounds or {}
+        max|feats[name]| when the producer knows it (the tensor-core convolutions need one; computed otherwise).
+        ``gates[name]``: [N,C,1,1] factor still to be multiplied into feats[name] (the eSE gate, VoVNet.tc_body)."""
+        bounds, gates = bounds or {}, gates or {}
 
-        def run(m, t, a_in=None, a_out=None):
-            return tcconv.conv(t, m, x_amax=a_in, y_amax=a_out) if tcconv.supported(m, t) else m(t)
+        def run(m, t, a_in=None, a_out=None, gate=None):
+            if tcconv.supported(m, t) and (gate is None or m.in_channels % 32 == 0):
+                return tcconv.conv(t, m, x_amax=a_in, y_amax=a_out, a_gate=gate)
+            return m(t if gate is None else t * gate)
 
         def bound(t):
             return ops.new_amax(t.device) if t.is_cuda else None
 
         top = self.in_features[-1]
         a_prev = bound(feats[top])
-        prev = run(self._laterals[0], feats[top], bounds.get(top), a_prev)
+        prev = run(self._laterals[0], feats[top], bounds.get(top), a_prev, gates.get(top))
         results = [run(self._outputs[0], prev, a_prev)]
         for idx in range(1, len(self._laterals)):
             name = self.in_features[-idx - 1]
             f, lat = feats[name], self._laterals[idx]
+            gate = gates.get(name)
             if (tcconv.supported(lat, f) and self._fuse_type == "sum" and lat.out_channels % 4 == 0
+                    and (gate is None or lat.in_channels % 32 == 0)
                     and tuple(prev.shape[2:]) == ((f.shape[2] + 1) // 2, (f.shape[3] + 1) // 2)):
                 # nearest 2x upsampling + sum inside the lateral convolution's epilogue; its bound is that of the sum
                 a_prev = bound(f)
-                prev = tcconv.conv(f, lat, x_amax=bounds.get(name), y_amax=a_prev, residual=prev, residual_upsample2=True)
+                prev = tcconv.conv(f, lat, x_amax=bounds.get(name), y_amax=a_prev, residual=prev, residual_upsample2=True,
+                                   a_gate=gate)
             else:
                 top_down = F.interpolate(prev, scale_factor=2.0, mode="nearest")
                 a_lat = bound(f)
-                prev = run(lat, f, bounds.get(name), a_lat) + top_down
+                prev = run(lat, f, bounds.get(name), a_lat, gate) + top_down
                 if a_lat is not None:
                     a_prev = a_lat + a_prev            # |lateral + upsampled| <= bound + bound
                 if self._fuse_type == "avg":

@@ -193,7 +193,7 @@ class CenterNet2Detector(nn.Module):
         chunk of ``chunk`` images, recorded by the stream that fills ``x_u8``) the stem of chunk k starts as soon as
         chunk k has landed, overlapping the copies of the later chunks."""
         buf, amax = self._stem_from_uint8(x_u8, events, chunk)
-        return self.backbone.top_down(*self.backbone.bottom_up.tc_body(buf, amax, want_amax=True))
+        return self.backbone.top_down(*self.backbone.bottom_up.tc_body(buf, amax, fuse_gates=True))
 
     def _stem_from_uint8(self, x_u8, events=None, chunk: int = 0, into=None):
         """stem_1..3 of a raw uint8 batch into the first slice of a stage-2 concat buffer (``into`` = (buf, first) of a
@@ -331,7 +331,7 @@ class CenterNet2Detector(nn.Module):
         first.zero_()
 
         def run():
-            feats = self.backbone.top_down(*vov.tc_body(buf, amax, want_amax=True))
+            feats = self.backbone.top_down(*vov.tc_body(buf, amax, fuse_gates=True))
             return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None)
 
         main = torch.cuda.current_stream(dev)

@@ -345,7 +345,8 @@ def new_amax(device, n: int = 1) -> Tensor:
 
 def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ksize: int, relu: bool = False,
                 out: Optional[Tensor] = None, stride: int = 1, x_amax: Optional[Tensor] = None,
-                y_amax: Optional[Tensor] = None, residual: Optional[Tensor] = None, residual_upsample2: bool = False) -> Tensor:
+                y_amax: Optional[Tensor] = None, residual: Optional[Tensor] = None, residual_upsample2: bool = False,
+                a_gate: Optional[Tensor] = None, colsum: Optional[Tensor] = None) -> Tensor:
     """Convolution with padding ksize//2 on the tensor cores (fp16-split operands, fp32 accuracy), bias + optional
     ReLU fused.  x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise.
     ``x_amax``: device float tensor (1..8 values) bounding max|x| (computed with ``absmax`` when omitted, which needs a
@@ -373,10 +374,31 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
         rh, rw = ((ho + 1) // 2, (wo + 1) // 2) if residual_upsample2 else (ho, wo)
         if tuple(residual.shape) != (n, cout, rh, rw):
             raise _lib.FodError(f"conv2d_nhwc: residual shape {tuple(residual.shape)}, expected {(n, cout, rh, rw)}")
+    if a_gate is not None:       # [N, Cin] factors multiplied into x (the eSE gate of the stage that produced x)
+        a_gate = _chk(a_gate, torch.float32, "a_gate").reshape(n, cin).contiguous()
+    if colsum is not None:       # [N, tiles per image, Cout] per-tile channel sums of the output (ese_gate)
+        _chk(colsum, torch.float32, "colsum")
+        if tuple(colsum.shape) != (n, conv2d_tiles_per_image(ho, wo), cout) or not colsum.is_contiguous():
+            raise _lib.FodError("conv2d_nhwc: bad colsum buffer")
     _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(x_amax), int(x_amax.numel()), _ptr(packed), _ptr(bias),
                                           cout, ksize, int(stride), int(relu), _ptr(out), ps_y, _ptr(y_amax), _ptr(residual),
-                                          int(residual_upsample2), _stream()), "fod_conv2d_nhwc")
+                                          int(residual_upsample2), _ptr(a_gate), _ptr(colsum), _stream()), "fod_conv2d_nhwc")
     return out
+
+
+def conv2d_tiles_per_image(ho: int, wo: int) -> int:
+    return int(_lib.lib().fod_conv2d_tiles_per_image(int(ho), int(wo)))
+
+
+def ese_gate(colsum: Tensor, hw: int, fc_weight: Tensor, fc_bias: Tensor) -> Tensor:
+    """Per-tile channel sums of a convolution output (conv2d_nhwc colsum) -> eSE gate [N, C]
+    = relu6(fc(mean over H*W) + 3) / 6  (vovnet.py eSEModule)."""
+    n, tiles, c = colsum.shape
+    w = _chk(fc_weight, torch.float32, "fc_weight").reshape(c, c).contiguous()
+    b = _chk(fc_bias, torch.float32, "fc_bias").contiguous()
+    gate = torch.empty((n, c), dtype=torch.float32, device=colsum.device)
+    _lib.check(_lib.lib().fod_ese_gate(_ptr(colsum), n, tiles, c, int(hw), _ptr(w), _ptr(b), _ptr(gate), _stream()), "fod_ese_gate")
+    return gate
 
 
 def group_norm_nhwc(x: Tensor, groups: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,

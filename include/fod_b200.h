@@ -226,6 +226,8 @@ int fod_batched_nms(const float* boxes, const float* scores, const int64_t* idxs
  *   residual: NULL, or a dense NHWC map with cout channels added to the convolution (+ bias) before the activation:
  *             [N][Ho][Wo][cout], or with residual_upsample2 [N][ceil(Ho/2)][ceil(Wo/2)][cout] read at (oy/2, ox/2) -
  *             the nearest-neighbour 2x upsampling + sum of the FPN top-down path (d2!/modeling/backbone/fpn.py:139-147)
+ *   a_gate  : NULL, or [N][cin] factors multiplied into x before the convolution (cin a multiple of 32)
+ *   colsum  : NULL, or [N][tiles per image][cout]: receives the sum of y over each 8 x 16 output tile, per channel
  * cin, cout and both pixel strides must be multiples of 4; pointers 16-byte aligned.
  */
 size_t fod_conv2d_packed_floats(int cout, int cin, int ksize);
@@ -233,7 +235,15 @@ size_t fod_conv2d_packed_floats(int cout, int cin, int ksize);
 int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, float* packed, fod_stream_t stream);
 int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax, int n_amax,
                     const float* packed, const float* bias, int cout, int ksize, int stride, int relu, float* y,
-                    long y_pixel_stride, float* y_amax, const float* residual, int residual_upsample2, fod_stream_t stream);
+                    long y_pixel_stride, float* y_amax, const float* residual, int residual_upsample2, const float* a_gate,
+                    float* colsum, fod_stream_t stream);
+/* eSE attention of the OSA stages (d2!/modeling/backbone/vovnet.py eSEModule: x * hsigmoid(fc(avg_pool(x)))) without a
+ * pass over x: the convolution that produces x writes per-tile channel sums (colsum), fod_ese_gate turns them into
+ * gate [N][C] = relu6(fc(mean) + 3) / 6, and the consumers multiply it in (fod_conv2d_nhwc a_gate, fod_maxpool3x3s2_nhwc gate).
+ *   colsum : [N][fod_conv2d_tiles_per_image(Ho, Wo)][C]   fc_weight [C][C], fc_bias [C]   hw = Ho * Wo */
+int fod_conv2d_tiles_per_image(int ho, int wo);
+int fod_ese_gate(const float* colsum, int n, int tiles_per_img, int channels, long hw, const float* fc_weight,
+                 const float* fc_bias, float* gate, fod_stream_t stream);
 /* max |x| of a dense fp32 array -> *out (device float; zeroed inside) */
 int fod_absmax(const float* x, size_t n, float* out, fod_stream_t stream);
 

@@ -168,3 +168,25 @@ def test_conv2d_nhwc_residual_in_epilogue(up2):
                         residual=r.to(DEV).contiguous(memory_format=torch.channels_last), residual_upsample2=up2, y_amax=bound)
     _check(y, ref, "conv + residual")
     assert abs(float(bound) - float(ref.abs().max())) <= 1e-5 * float(ref.abs().max())
+
+
+def test_conv2d_nhwc_ese_gate_pieces():
+    """eSE without a pass over the map: per-tile channel sums out of the epilogue -> gate kernel; gate multiplied into the
+    consumer's input (vovnet.py eSEModule)."""
+    n, h, w, cin, c = 3, 20, 28, 64, 96
+    x = synth.tensor((n, cin, h, w), 95, -1.0, 1.0)
+    wt = synth.tensor((c, cin, 3, 3), 96, -0.1, 0.1)
+    fw, fb = synth.tensor((c, c, 1, 1), 97, -0.2, 0.2), synth.tensor((c,), 98, -1.0, 1.0)
+    y_ref = _ref(x, wt, None, True)
+    g_ref = (F.relu6(F.conv2d(y_ref.double().mean((2, 3), keepdim=True), fw.double(), fb.double()) + 3.0) / 6.0).float()
+    colsum = torch.zeros((n, ops.conv2d_tiles_per_image(h, w), c), device=DEV)
+    y = ops.conv2d_nhwc(x.to(DEV).contiguous(memory_format=torch.channels_last), ops.conv2d_pack(wt.to(DEV)), None, c, 3, True,
+                        colsum=colsum)
+    gate = ops.ese_gate(colsum, h * w, fw.to(DEV), fb.to(DEV))
+    _check(y, y_ref, "conv")
+    _check(gate.view(n, c, 1, 1), g_ref, "gate")
+    # consumer: 1x1 convolution of the gated map, gate applied to the A operand
+    w2 = synth.tensor((128, c, 1, 1), 99, -0.1, 0.1)
+    ref2 = _ref(y_ref * g_ref, w2, None, False)
+    out = ops.conv2d_nhwc(y, ops.conv2d_pack(w2.to(DEV)), None, 128, 1, a_gate=gate)
+    _check(out, ref2, "gated consumer")
