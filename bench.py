@@ -143,7 +143,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = len(os.sched_getaffinity(0))
-    per_step = 4                                  # bounded sample: images per step
+    per_step = 16                                 # bounded sample: images per step (~1 s of host work per step)
     rate, dt = cpu_reference_rate(per_step * args.steps, min(args.warmup, 2), threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -413,7 +413,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--cpu-images", type=int, default=12)
+    ap.add_argument("--cpu-images", type=int, default=200)      # ~12 s of host work on 16 cores
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

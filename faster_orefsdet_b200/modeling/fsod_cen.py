@@ -309,8 +309,22 @@ class CenterNet2Detector(nn.Module):
     USE_CUDA_GRAPH = os.environ.get("FOD_CUDA_GRAPH", "1") == "1"
 
     def _graph_key(self, n, h, w):
-        ver = sum(int(p._version) for p in self.parameters()) + sum(int(b._version) for b in self.buffers())
-        return (n, h, w, self._bank_key, id(self._bank), ver, str(self.device))
+        # weights enter the captured graph as packed copies: any path that replaces or rewrites them bumps the epoch
+        # (load_state_dict, .to() / .cuda() / .float() through _apply)
+        return (n, h, w, self._bank_key, id(self._bank), getattr(self, "_weights_epoch", 0), str(self.device))
+
+    def _bump_weights_epoch(self, *args, **kwargs):
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._bump_weights_epoch()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._bump_weights_epoch()
+        return out
 
     def _graph_for(self, n, h, w):
         """Captured once per (batch, image size, episode, weights): OSA stages + FPN + CenterNetHead + the head kernels

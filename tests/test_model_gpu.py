@@ -263,6 +263,16 @@ def test_cuda_graph_replay_equals_eager_launches():
         for a, b in zip(got, ref):
             assert torch.equal(a, b)
     assert model._graph["graph"] is not None
+    # new weights invalidate the captured graph (it holds packed copies of the old ones)
+    old_graph = model._graph["graph"]
+    sd = {k: (v * 1.25 if k.endswith("fpn_output3.weight") else v) for k, v in model.state_dict().items()}
+    model.load_state_dict(sd)
+    model.USE_CUDA_GRAPH = True
+    got = [t.clone() for t in model.detect_from_uint8(x, sizes, outs)]
+    assert model._graph["graph"] is not old_graph
+    model.USE_CUDA_GRAPH = False
+    for a, b in zip(got, model.detect_from_uint8(x, sizes, outs)):
+        assert torch.equal(a, b)
 
 
 def test_tensor_core_backbone_matches_reference_vovnet_fpn():
