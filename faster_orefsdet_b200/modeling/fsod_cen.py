@@ -30,7 +30,8 @@ from .. import _lib, ops
 from ..compat import META_ARCH_REGISTRY, Boxes, ImageList, Instances
 from .backbone import build_backbone
 from .centernet import CenterNet, RawProposals  # noqa: F401  (registers "CenterNet")
-from .prototypes import LEVELS, PrototypeBank, SM_Block, SupportCache, bank_from_support_dict, broadcast_bank
+from .prototypes import (LEVELS, PrototypeBank, SM_Block, SupportCache, bank_from_support_dict, broadcast_bank, load_bank,
+                         save_bank)
 from .roi_heads import build_roi_heads, pack_instances
 from ..compat import PROPOSAL_GENERATOR_REGISTRY
 
@@ -118,10 +119,25 @@ class CenterNet2Detector(nn.Module):
             self.logger.info("=========== Offline support features are generated. ===========")
             self.logger.info("============ Few-shot object detetion will start. =============")
             sys.exit(0)
-        d = self._support.load()
-        if self._bank is None or self._bank_key != self._support.key:
-            self._bank = bank_from_support_dict(d, self.roi_heads, self.device)
-            self._bank_key = self._support.key
+        # The pickle stays the source of truth (README.md:74: users delete it to rebuild), but it is only unpickled when it
+        # changed: its (mtime, size) is checked per call, and the reduced episode (taps, support mean, folded bias) is kept
+        # next to it as a binary, mmap-able file that a fresh process uploads with one copy.
+        src = self._support.stat_key()
+        key = (os.path.abspath(self._support.path),) + tuple(src) + (getattr(self, "_weights_epoch", 0),)
+        if self._bank is not None and self._bank_key == key:
+            return
+        bank = None
+        if os.environ.get("FOD_BINARY_PROTOTYPES", "1") == "1":
+            bank = load_bank(self._support.binary_path, self.device, src)
+            if bank is not None:     # taps and support mean depend on the pickle only; the folded bias on this model's weights
+                bank.bias_cls = self.roi_heads.class_bias(bank.support_mean)
+        if bank is None:
+            bank = bank_from_support_dict(self._support.load(), self.roi_heads, self.device)
+            try:
+                save_bank(bank, self._support.binary_path, src)
+            except OSError:
+                pass
+        self._bank, self._bank_key = bank, key
 
     @torch.no_grad()
     def build_support_dict(self, images_per_class: Dict[int, List[torch.Tensor]],

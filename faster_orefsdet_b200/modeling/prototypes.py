@@ -100,6 +100,54 @@ class PrototypeBank:
         return PrototypeBank(list(class_ids), taps, sm, bias)
 
 
+# ---- binary, mmap-able episode file: what the kernels need, nothing to unpickle
+#   bytes 0..63   header: magic "FODB", u32 version, u32 num_classes, u32 num_levels, u64 source mtime_ns, u64 source size,
+#                 zero padding
+#   then          int64 class_ids[num_classes], padded to a multiple of 64 bytes
+#   then          fp32 payload = PrototypeBank.pack() (taps per level, support mean, folded bias): the NCCL broadcast buffer
+_FODB_MAGIC = b"FODB"
+_FODB_VERSION = 1
+
+
+def save_bank(bank: PrototypeBank, path: str, source_key=(0, 0)) -> None:
+    import struct
+    import numpy as np
+    ids = np.asarray(bank.class_ids, dtype=np.int64)
+    pad = (-ids.nbytes) % 64
+    header = _FODB_MAGIC + struct.pack("<IIIQQ", _FODB_VERSION, bank.num_classes, len(bank.taps), int(source_key[0]), int(source_key[1]))
+    payload = bank.pack().detach().to("cpu", torch.float32).contiguous().numpy()
+    tmp = path + ".tmp"
+    with open(tmp, "wb") as f:
+        f.write(header.ljust(64, b"\0"))
+        f.write(ids.tobytes() + b"\0" * pad)
+        f.write(payload.tobytes())
+    os.replace(tmp, path)      # atomic: readers never see a half-written file
+
+
+def load_bank(path: str, device, expect_source_key=None) -> Optional[PrototypeBank]:
+    """Memory-maps the episode file and uploads its payload with one copy; None if the file is missing, of another
+    version, truncated, or (when ``expect_source_key`` = (mtime_ns, size) is given) derived from another pickle."""
+    import struct
+    import numpy as np
+    if not os.path.exists(path):
+        return None
+    with open(path, "rb") as f:
+        head = f.read(64)
+    if len(head) < 64 or head[:4] != _FODB_MAGIC:
+        return None
+    version, C, L, mtime_ns, size = struct.unpack("<IIIQQ", head[4:32])
+    if version != _FODB_VERSION or (expect_source_key is not None and (mtime_ns, size) != tuple(int(v) for v in expect_source_key)):
+        return None
+    ids_bytes = C * 8 + ((-C * 8) % 64)
+    n = PrototypeBank.packed_numel(C, L)
+    if os.path.getsize(path) != 64 + ids_bytes + 4 * n:
+        return None
+    ids = np.memmap(path, dtype=np.int64, mode="r", offset=64, shape=(C,))
+    payload = np.memmap(path, dtype=np.float32, mode="r", offset=64 + ids_bytes, shape=(n,))
+    buf = torch.from_numpy(np.array(payload)).to(device)      # one copy out of the page cache (a memmap is not writable)
+    return PrototypeBank.unpack(buf, [int(v) for v in ids], L)
+
+
 def bank_from_support_dict(support_dict: Dict[str, Dict[int, torch.Tensor]], roi_heads, device) -> PrototypeBank:
     """pkl-schema dict -> PrototypeBank on ``device``.  Taps come from the CUDA kernel (row Q1)."""
     class_ids = list(support_dict["p3"].keys())
@@ -158,3 +206,12 @@ class SupportCache:
     @property
     def key(self):
         return self._key
+
+    def stat_key(self):
+        """(mtime_ns, size) of the pickle without reading it."""
+        st = os.stat(self.path)
+        return (st.st_mtime_ns, st.st_size)
+
+    @property
+    def binary_path(self) -> str:
+        return os.path.splitext(self.path)[0] + ".fodb"

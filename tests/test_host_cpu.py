@@ -110,3 +110,23 @@ def test_prototype_bank_pack_roundtrip():
     for a, b in zip(bank.taps, back.taps):
         assert torch.equal(a, b)
     assert torch.equal(bank.support_mean, back.support_mean) and torch.equal(bank.bias_cls, back.bias_cls)
+
+
+def test_binary_prototype_file_round_trip(tmp_path):
+    """SURVEY 8f#2: the reduced episode as a binary, mmap-able file (header + class ids + the NCCL broadcast payload)."""
+    from faster_orefsdet_b200.modeling.prototypes import PrototypeBank, load_bank, save_bank
+    C = 3
+    bank = PrototypeBank([7, 2, 9], [synth.tensor((C, 7, 128), 10 + l, -1, 1) for l in range(3)],
+                         synth.tensor((C, 128, 8, 8), 20, -1, 1), synth.tensor((C, 128), 21, -1, 1))
+    path = str(tmp_path / "support_feature.fodb")
+    save_bank(bank, path, (123456789, 4242))
+    assert os.path.getsize(path) == 64 + 64 + 4 * PrototypeBank.packed_numel(C)
+    got = load_bank(path, "cpu", (123456789, 4242))
+    assert got.class_ids == [7, 2, 9]
+    for a, b in zip(got.taps + [got.support_mean, got.bias_cls], bank.taps + [bank.support_mean, bank.bias_cls]):
+        assert torch.equal(a, b)
+    assert load_bank(path, "cpu", (123456789, 4243)) is None          # derived from another pickle
+    assert load_bank(str(tmp_path / "missing.fodb"), "cpu") is None
+    with open(path, "r+b") as f:                                       # truncated file is refused
+        f.truncate(1000)
+    assert load_bank(path, "cpu") is None

@@ -174,6 +174,18 @@ def test_full_detector_forward_with_pkl_side_channel(tmp_path, monkeypatch):
     bank = model._bank
     model(inputs)
     assert model._bank is bank
+    # the reduced episode was written next to the pickle as a binary file; a fresh process-like model loads that
+    assert os.path.exists("support_dir/support_feature.fodb")
+    model2 = _model()
+    model2.load_state_dict(model.state_dict())
+    import faster_orefsdet_b200.modeling.prototypes as P
+    calls = []
+    monkeypatch.setattr(P.SupportCache, "load", lambda self: calls.append(1) or (_ for _ in ()).throw(AssertionError("unpickled")))
+    out2 = model2(inputs)
+    assert not calls
+    for a, b in zip(out, out2):
+        assert torch.equal(a["instances"].scores, b["instances"].scores)
+        assert torch.equal(a["instances"].pred_boxes.tensor, b["instances"].pred_boxes.tensor)
 
 
 def test_missing_pkl_builds_cache_and_exits_like_the_reference(tmp_path, monkeypatch):
