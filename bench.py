@@ -179,6 +179,9 @@ class KernelTimer:
                 if not self.enabled:
                     return __fn(*a, **k)
                 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                # keep the GPU busy (~0.2 ms spin) while the host enqueues this call's launches, so that the two events
+                # bracket kernel time and not the host's launch latency (this pass is eager; the timed region is a graph)
+                torch.cuda._sleep(400_000)
                 s.record()
                 r = __fn(*a, **k)
                 e.record()
