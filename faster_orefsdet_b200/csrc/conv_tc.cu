@@ -78,6 +78,18 @@ constexpr uint32_t kAStageCols = 32;                // [hi: 16 columns of packed
 constexpr uint32_t kColA = 0;                       // 6 stages x 32
 constexpr uint32_t kColAcc = kStages * kAStageCols; // 2 stages x 128
 
+// 2^e with amax * 2^e in [2^13, 2^14) (and its inverse); 1 for zero / denormal-range / non-finite bounds
+__device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
+  const int E = (int)((__float_as_uint(amax) >> 23) & 0xFF);
+  if (E < 32 || E > 240) {
+    scale = 1.f;
+    inv = 1.f;
+  } else {
+    scale = __uint_as_float((uint32_t)(267 - E) << 23);  // 2^(13 - (E - 127))
+    inv = __uint_as_float((uint32_t)(E - 13) << 23);
+  }
+}
+
 #ifdef FOD_DBG
 __device__ long long* g_dbg = nullptr;   // [role][g][4] clock64 stamps of pair 0 / rank 0, chunks kDbg0 .. kDbg0 + kDbgN
 constexpr uint32_t kDbg0 = 400, kDbgN = 64;
@@ -89,6 +101,15 @@ constexpr uint32_t kDbg0 = 400, kDbgN = 64;
 #else
 #define DBG_STAMP(role, g, slot)
 #endif
+
+// (a, b) -> packed fp16 pair of the rounded values (a in the low half) and of the exact remainders
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 struct Params {
   CUtensorMap in_map;   // [N][H][W][Cin] (pixel stride may exceed Cin), box 32 x halo_w x halo_h

@@ -10,10 +10,8 @@
 //     tcgen05 cta_group::2): one MMA covers both CTAs' tiles (M = 256) against W3 (N = 128) whose rows are split
 //     between the two CTAs, so each CTA keeps only half of the weights resident in shared memory (hi + lo tf32
 //     parts of 64 x 256 fp32 = 128 KB) for the whole kernel.
-//   * fp32 accuracy on the tensor cores by operand splitting: x * 2^e = hi + lo in fp16 (22 significant bits),
-//     A.B ~ Ahi.Bhi + Alo.Bhi + Ahi.Blo on kind::f16 MMAs (K = 16 per instruction: half the tensor time of the 3xTF32
-//     version this kernel started with), fp32 accumulation in tensor memory.  One power-of-two scale per (level, class)
-//     covers s and q: |q| <= max|q| (device scalar from the producer of q), |s| <= (1 + c11 + sum|k31| sum|k13|) max|q|.
+//   * fp32 accuracy on tf32 tensor cores by operand splitting (3xTF32): x = hi + lo, A.B ~ Ahi.Bhi + Alo.Bhi +
+//     Ahi.Blo, fp32 accumulation in tensor memory; measured error ~1e-6 relative (tools/tc_probe.cu).
 //   * the query tile (+1 pixel halo, zero-filled outside the image by TMA) is staged channel-chunk-wise
 //     (32 channels = one 128-byte swizzled row per pixel) into a 3-deep shared-memory ring by TMA.
 //   * 16 "stencil" warps build the A operand: one pixel per lane (TMEM lane = pixel), they read the 3x3
@@ -44,12 +42,12 @@ constexpr int kNumChunks = kC / kChunk;                                         
 constexpr int kQStages = 3, kAStages = 4, kAccStages = 2;
 constexpr int kSub = 16;                      // channels per A stage (sub-chunk); 2 per 32-channel q box
 constexpr int kNumSubs = kC / kSub;           // 8 per tile
-constexpr uint32_t kAStageCols = 2 * kSub;    // packed fp16 pairs: [s_hi 8 | s_lo 8 | q_hi 8 | q_lo 8]
+constexpr uint32_t kAStageCols = 4 * kSub;    // [s_hi 16 | s_lo 16 | q_hi 16 | q_lo 16]
 constexpr uint32_t kQStageBytes = kHaloPx * 128;         // 23040
 constexpr uint32_t kQStageStride = 23552;                // rounded up to 1024
 constexpr uint32_t kBHalfRows = 64;                      // W3 rows per CTA
-constexpr uint32_t kBChunkBytes = kBHalfRows * 64;       // 4096: one 32-wide K chunk of fp16 (64-byte swizzled rows)
-constexpr uint32_t kBPartBytes = 8 * kBChunkBytes;       // 32768: K = 256
+constexpr uint32_t kBChunkBytes = kBHalfRows * 128;      // 8192: one 32-wide K chunk
+constexpr uint32_t kBPartBytes = 8 * kBChunkBytes;       // 65536: K = 256
 constexpr uint32_t kStageOutBytes = kTilePx * 128;       // 16384
 
 // shared memory map (offsets from the 1024-aligned base)
@@ -59,7 +57,7 @@ constexpr uint32_t kOffQ = kOffBLo + kBPartBytes;
 constexpr uint32_t kOffOut = kOffQ + kQStages * kQStageStride;
 constexpr uint32_t kOffBias = kOffOut + kStageOutBytes;
 constexpr uint32_t kOffBars = kOffBias + kC * 4;
-constexpr uint32_t kNumBars = 2 * kQStages + 2 * kAStages + 2 * kAccStages + 1;   // + w_full (resident weights landed)
+constexpr uint32_t kNumBars = 2 * kQStages + 2 * kAStages + 2 * kAccStages;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr uint32_t kOffFlag = kOffTmemPtr + 8;  // sub-chunks released to the MMA thread by its barrier watcher
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
@@ -71,7 +69,7 @@ constexpr int kStencilWarps = 16;
 
 // tensor memory columns
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColA = 0;      // 4 stages x [s_hi 8 | s_lo 8 | q_hi 8 | q_lo 8] (packed fp16 pairs)
+constexpr uint32_t kColA = 0;      // 4 stages x [s_hi 16 | s_lo 16 | q_hi 16 | q_lo 16]
 constexpr uint32_t kColAcc = 256;  // 2 stages x 128
 
 struct Level {
@@ -82,10 +80,7 @@ struct Params {
   CUtensorMap in_map[FOD_MAX_LEVELS];   // [B][H][W][128], box 32 x 18 x 10
   CUtensorMap out_map[FOD_MAX_LEVELS];  // [P][H][W][128], box 32 x 16 x 8
   Level lv[FOD_MAX_LEVELS];
-  CUtensorMap w_hi_map, w_lo_map;       // fp16 planes of W3 [128][256] (fod_conv2d_pack_weights), box 32 x 64
-  const float* w_inv;                   // 1 / weight scale (tail of the packed buffer)
-  const float* q_amax[FOD_MAX_LEVELS];  // device scalar per level: upper bound of max|q|
-  float* attn_amax[FOD_MAX_LEVELS];     // null or device scalar per level (zeroed by the caller): raised to max(attn)
+  const float* w3;
   const float* b3;
   // problems of this launch: images x classes [class_begin, class_begin + class_count) of num_classes
   int num_levels, num_classes, class_begin, class_count, total_tiles, num_pairs;
@@ -138,8 +133,6 @@ constexpr int kStencilUnroll = 1;  // measured: 1, 2 and 4 run at the same speed
 // rows 0..6: k11, k13 (left, centre, right), k31 (up, centre, down); row 7: c11 = k11 > 0 ? k11*k11 : 0
 constexpr int kTapRows = 8;
 __constant__ __align__(16) float c_taps[kMaxTapSets][kTapRows][kC];
-// |s| <= c_sfactor[set] * max|q| with s = a + b + q: per channel 1 + c11 + (sum |k31|) (sum |k13|), maximum over channels
-__constant__ float c_sfactor[kMaxTapSets + 1];
 
 // Fills the constant-bank tap sets of one launch (set = level * class_count + class) from the [C][7][128] taps of
 // fod_support_taps and appends row 7.  Runs stream-ordered before the persistent kernel (the constant cache is
@@ -148,23 +141,14 @@ struct TapPack {
   const float* src[FOD_MAX_LEVELS];
   int class_count;
 };
-__global__ void pack_taps_kernel(const TapPack pk, float* __restrict__ dst, float* __restrict__ sfactor) {
+__global__ void pack_taps_kernel(const TapPack pk, float* __restrict__ dst) {
   const int set = blockIdx.x, l = set / pk.class_count, cc = set - l * pk.class_count, ch = threadIdx.x;
   const float* s = pk.src[l] + (size_t)cc * 7 * kC;
   float* d = dst + (size_t)set * kTapRows * kC;
 #pragma unroll
   for (int k = 0; k < 7; ++k) d[k * kC + ch] = s[k * kC + ch];
   const float k11 = s[ch];
-  const float c11 = k11 > 0.f ? k11 * k11 : 0.f;
-  d[7 * kC + ch] = c11;
-  // bound of |s| / max|q| for this channel, then the maximum over the 128 channels of the set
-  float f = 1.f + c11 + (fabsf(s[1 * kC + ch]) + fabsf(s[2 * kC + ch]) + fabsf(s[3 * kC + ch])) *
-                           (fabsf(s[4 * kC + ch]) + fabsf(s[5 * kC + ch]) + fabsf(s[6 * kC + ch]));
-  __shared__ float red[4];
-  uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(f));
-  if ((ch & 31) == 0) red[ch >> 5] = __uint_as_float(w);
-  __syncthreads();
-  if (ch == 0) sfactor[set] = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * 1.0001f;
+  d[7 * kC + ch] = k11 > 0.f ? k11 * k11 : 0.f;
 }
 
 struct StencilCtx {
@@ -174,6 +158,14 @@ struct StencilCtx {
 };
 
 __device__ __forceinline__ float2 relu2(float2 v) { return make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)); }
+__device__ __forceinline__ void split2(float2 v, uint32_t& h0, uint32_t& h1, uint32_t& l0, uint32_t& l1) {
+  h0 = (__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u;  // round to nearest tf32 (see tc05.cuh split_tf32)
+  h1 = (__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u;
+  float2 lo = __ffma2_rn(make_float2(__uint_as_float(h0), __uint_as_float(h1)), make_float2(-1.f, -1.f), v);
+  l0 = __float_as_uint(lo.x);
+  l1 = __float_as_uint(lo.y);
+}
+
 // One stencil warp: TMEM lane quadrant qd = warp & 3, one pixel per lane.  The four warps of a quadrant share every
 // 32-channel chunk: warp k takes the 16-byte channel groups jj with (jj >> 1) == k.  The loops over chunks and
 // groups stay ROLLED with uniform counters (one small code copy for all 16 warps -> instruction cache; the tap
@@ -203,10 +195,6 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
     for (int cc = 0; cc < P.class_count; ++cc) {
       const int set = l * P.class_count + cc;
       const int set_end = P.lv[l].tile_begin + (cc + 1) * P.lv[l].tiles_per_class;
-      // one power-of-two scale for s and q of this (level, class): |q| <= max|q|, |s| <= c_sfactor * max|q|
-      float xs, xs_inv;
-      pow2_scale(__ldg(P.q_amax[l]) * c_sfactor[set], xs, xs_inv);
-      const float2 xs2 = make_float2(xs, xs);
       for (; 2 * (i * P.num_pairs + cx.pair) < T && min(2 * (i * P.num_pairs + cx.pair) + cx.rank, T - 1) < set_end;
            ++i) {
 #pragma unroll 1
@@ -229,7 +217,7 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
               const float4 k13l = *reinterpret_cast<const float4*>(tp + 1 * kC);
               const float4 k13c = *reinterpret_cast<const float4*>(tp + 2 * kC);
               const float4 k13r = *reinterpret_cast<const float4*>(tp + 3 * kC);
-              uint32_t shi[2], slo[2], qhi[2], qlo[2];   // packed fp16 pairs of the 4 channels of this step
+              uint32_t shi[4], slo[4], qhi[4], qlo[4];
               float4 qc4;
               float2 t3[3][2];
 #pragma unroll
@@ -259,14 +247,13 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
                 const float2 bv = relu2(__ffma2_rn(kd, t3[2][h], __ffma2_rn(ku, t3[0][h], __fmul2_rn(kc, t3[1][h]))));
                 // a = relu(k11 * relu(k11 * q)) == c11 * relu(q) with c11 = k11 > 0 ? k11^2 : 0 (row 7 of the set)
                 const float2 sv = __fadd2_rn(__ffma2_rn(k1, relu2(qc), bv), qc);
-                const float2 svs = __fmul2_rn(sv, xs2), qcs = __fmul2_rn(qc, xs2);   // exact: power-of-two scale
-                split_f16x2(svs.x, svs.y, shi[h], slo[h]);
-                split_f16x2(qcs.x, qcs.y, qhi[h], qlo[h]);
+                split2(sv, shi[2 * h], shi[2 * h + 1], slo[2 * h], slo[2 * h + 1]);
+                split2(qc, qhi[2 * h], qhi[2 * h + 1], qlo[2 * h], qlo[2 * h + 1]);
               }
-              tmem_st2(tcol + j4 * 2, shi[0], shi[1]);
-              tmem_st2(tcol + 8 + j4 * 2, slo[0], slo[1]);
-              tmem_st2(tcol + 16 + j4 * 2, qhi[0], qhi[1]);
-              tmem_st2(tcol + 24 + j4 * 2, qlo[0], qlo[1]);
+              tmem_st4(tcol + j4 * 4, shi);
+              tmem_st4(tcol + kSub + j4 * 4, slo);
+              tmem_st4(tcol + 2 * kSub + j4 * 4, qhi);
+              tmem_st4(tcol + 3 * kSub + j4 * 4, qlo);
             }
           }
           tmem_wait_st();
@@ -299,7 +286,6 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
   auto a_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + kAStages + s); };
   auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kAStages + s); };
   auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kAStages + kAccStages + s); };
-  const uint32_t w_full = bar0 + 8u * (2 * kQStages + 2 * kAStages + 2 * kAccStages);
 
   if (tid == 0) {
     for (int s = 0; s < kQStages; ++s) {
@@ -314,7 +300,6 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
       mbar_init(acc_full(s), 1);
       mbar_init(acc_empty(s), 8);  // 4 epilogue warps x 2 CTAs (leader only)
     }
-    mbar_init(w_full, 1);
     *reinterpret_cast<volatile uint32_t*>(smem + kOffFlag) = 0;
     fence_barrier_init();
   }
@@ -328,24 +313,31 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
       tma_prefetch_desc(&P.out_map[l]);
     }
   }
-  // resident weights: this CTA's 64 rows of W3 as scaled fp16 hi / lo planes (packed once by fod_conv2d_pack_weights),
-  // eight 32-wide K chunks per plane, 64-byte swizzled rows, fetched by TMA
-  if (tid == 0) {
-    tma_prefetch_desc(&P.w_hi_map);
-    tma_prefetch_desc(&P.w_lo_map);
-    mbar_arrive_expect_tx(w_full, 2 * kBPartBytes);
-    for (int c = 0; c < 8; ++c) {
-      tma_load_2d(sbase + kOffBHi + c * kBChunkBytes, &P.w_hi_map, w_full, c * 32, (int)rank * (int)kBHalfRows);
-      tma_load_2d(sbase + kOffBLo + c * kBChunkBytes, &P.w_lo_map, w_full, c * 32, (int)rank * (int)kBHalfRows);
+  // resident weights: this CTA's 64 rows of W3, split into tf32 hi / lo, K-major SW128 chunks
+  {
+    const float* wsrc = P.w3 + (size_t)rank * kBHalfRows * 256;
+    for (int i = tid; i < (int)kBHalfRows * 64; i += kThreads) {  // float4 index: 64 per row
+      int r = i >> 6, c = (i & 63) << 2;
+      float4 v = ldg4(wsrc + (size_t)r * 256 + c);
+      float x[4] = {v.x, v.y, v.z, v.w};
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x[j]));
+        hi[j] = h;
+        lo[j] = __float_as_uint(x[j] - __uint_as_float(h));
+      }
+      uint32_t off = (uint32_t)(c >> 5) * kBChunkBytes + sw128_offset(r, c & 31);
+      *reinterpret_cast<uint4*>(smem + kOffBHi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(smem + kOffBLo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
+    if (tid < kC) reinterpret_cast<float*>(smem + kOffBias)[tid] = P.b3[tid];
   }
-  if (tid < kC) reinterpret_cast<float*>(smem + kOffBias)[tid] = P.b3[tid];
   fence_proxy_async_smem();
   tc_fence_before();
   cluster_sync();
   tc_fence_after();
-  mbar_wait(w_full, 0);   // the weights of this CTA have landed (the peer's are awaited by the peer; the MMA is issued
-                          // only after both CTAs' stencil warps have delivered their first operands)
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
 
   // static schedule: iteration i of pair k handles tiles 2*(i*num_pairs + k) + rank
@@ -374,9 +366,9 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
   } else if (warp == kWarpMma) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
     if (rank == 0) {
-      const uint32_t idesc = idesc_f16(256, 128);
-      const uint64_t bhi0 = smem_desc_k_sw64(sbase + kOffBHi);
-      const uint64_t blo0 = smem_desc_k_sw64(sbase + kOffBLo);
+      const uint32_t idesc = idesc_tf32(256, 128);
+      const uint64_t bhi0 = smem_desc_k_sw128(sbase + kOffBHi);
+      const uint64_t blo0 = smem_desc_k_sw128(sbase + kOffBLo);
       // A watcher thread (warp kWarpAlloc) does all the barrier waiting and publishes the number of sub-chunks whose
       // operands are in place through one shared-memory word; this warp only polls that word.  The whole warp runs
       // the loop converged and one elected lane issues, so that every tcgen05.mma operand is a warp-uniform value
@@ -400,13 +392,17 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
         const uint32_t a0 = tmem_base + kColA + s * kAStageCols;
         if (elect_one()) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {   // s part (K 0..127 of W3), then q part (K 128..255): K = 16 each
-            const uint32_t ah = a0 + half * 16, al = ah + 8;
-            const uint64_t boff = (uint64_t)(((half * 4 + (sub >> 1)) * kBChunkBytes + (sub & 1) * kSub * 2) >> 4);
-            const uint32_t acc = (sub | half) ? 1u : 0u;
-            mma_f16_ts<2>(d, ah, bhi0 + boff, idesc, acc);
-            mma_f16_ts<2>(d, al, bhi0 + boff, idesc, 1u);
-            mma_f16_ts<2>(d, ah, blo0 + boff, idesc, 1u);
+          for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int ks = 0; ks < kSub / 8; ++ks) {
+              const uint32_t ah = a0 + half * 2 * kSub + ks * 8, al = ah + kSub;
+              const uint64_t boff =
+                  (uint64_t)(((half * 4 + (sub >> 1)) * kBChunkBytes + (sub & 1) * kSub * 4 + ks * 32) >> 4);
+              const uint32_t acc = (sub | half | ks) ? 1u : 0u;
+              mma_tf32_ts<2>(d, ah, bhi0 + boff, idesc, acc);
+              mma_tf32_ts<2>(d, al, bhi0 + boff, idesc, 1u);
+              mma_tf32_ts<2>(d, ah, blo0 + boff, idesc, 1u);
+            }
           }
           mma_commit_pair(a_empty(s), 3);
           if (sub == kNumSubs - 1) mma_commit_pair(acc_full(as_), 3);
@@ -446,12 +442,6 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
       mbar_wait(acc_full(as_), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColAcc + as_ * 128;
-      // undo the two power-of-two operand scales (exact)
-      float xs_t, xs_inv_t;
-      pow2_scale(__ldg(P.q_amax[tcd.level]) * c_sfactor[tcd.level * P.class_count + tcd.cc], xs_t, xs_inv_t);
-      const float rescale = xs_inv_t * __ldg(P.w_inv);
-      const bool px_valid = do_store && tcd.y0 + (m >> 4) < P.lv[tcd.level].H && tcd.x0 + (m & 15) < P.lv[tcd.level].W;
-      float vmax = 0.f;
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         uint32_t v[32];
@@ -468,11 +458,10 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
         for (int c4 = 0; c4 < 8; ++c4) {
           const float4 bb = lds4s(sbase + kOffBias + (j * 32 + c4 * 4) * 4);
           float4 o;
-          o.x = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 0]), rescale, bb.x), 0.f);
-          o.y = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 1]), rescale, bb.y), 0.f);
-          o.z = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 2]), rescale, bb.z), 0.f);
-          o.w = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 3]), rescale, bb.w), 0.f);
-          vmax = fmaxf(fmaxf(vmax, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
+          o.x = fmaxf(__uint_as_float(v[c4 * 4 + 0]) + bb.x, 0.f);
+          o.y = fmaxf(__uint_as_float(v[c4 * 4 + 1]) + bb.y, 0.f);
+          o.z = fmaxf(__uint_as_float(v[c4 * 4 + 2]) + bb.z, 0.f);
+          o.w = fmaxf(__uint_as_float(v[c4 * 4 + 3]) + bb.w, 0.f);
           sts4s(sbase + kOffOut + (m >> 3) * 1024 + (m & 7) * 128 + ((c4 ^ (m & 7)) << 4), o);
         }
         fence_proxy_async_smem();
@@ -481,10 +470,6 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
           tma_store_4d(&P.out_map[tcd.level], sbase + kOffOut, j * 32, tcd.x0, tcd.y0, pg);
           tma_store_commit();
         }
-      }
-      if (P.attn_amax[tcd.level]) {   // max of the level's output (>= 0 after the ReLU): the operand bound its consumer needs
-        const uint32_t wmax = __reduce_max_sync(0xffffffffu, px_valid ? __float_as_uint(vmax) : 0u);
-        if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(P.attn_amax[tcd.level]), wmax);
       }
     }
     if (issuer) tma_store_wait<0>();
@@ -511,11 +496,10 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
 
 using namespace fod;
 
-extern "C" int fod_correlate_levels(const float* const* q, const float* const* q_amax, const float* const* taps,
-                                    const fod_level_t* levels, int num_levels, const float* w3, const float* b3,
-                                    float* const* attn, float* const* attn_amax, int batch, int num_classes,
-                                    fod_stream_t stream) {
-  FOD_REQUIRE(q && q_amax && taps && levels && w3 && b3 && attn, "fod_correlate_levels: null pointer");
+extern "C" int fod_correlate_levels(const float* const* q, const float* const* taps, const fod_level_t* levels,
+                                    int num_levels, const float* w3, const float* b3, float* const* attn, int batch,
+                                    int num_classes, fod_stream_t stream) {
+  FOD_REQUIRE(q && taps && levels && w3 && b3 && attn, "fod_correlate_levels: null pointer");
   FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_correlate_levels: 1..%d levels", FOD_MAX_LEVELS);
   FOD_REQUIRE(batch >= 0 && num_classes >= 0, "fod_correlate_levels: bad sizes");
   FOD_REQUIRE((((uintptr_t)w3 | (uintptr_t)b3) & 15) == 0, "fod_correlate_levels: weights must be 16-byte aligned");
@@ -525,9 +509,7 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* q
   memset(&prm, 0, sizeof(prm));
   for (int l = 0; l < num_levels; ++l) {
     const int H = levels[l].height, W = levels[l].width;
-    FOD_REQUIRE(H > 0 && W > 0 && q[l] && q_amax[l] && attn[l] && taps[l], "fod_correlate_levels: level %d invalid", l);
-    prm.q_amax[l] = q_amax[l];
-    prm.attn_amax[l] = attn_amax ? attn_amax[l] : nullptr;
+    FOD_REQUIRE(H > 0 && W > 0 && q[l] && attn[l] && taps[l], "fod_correlate_levels: level %d invalid", l);
     FOD_REQUIRE((((uintptr_t)q[l] | (uintptr_t)attn[l] | (uintptr_t)taps[l]) & 15) == 0,
                 "fod_correlate_levels: level %d pointers must be 16-byte aligned", l);
     int rc = make_nhwc_map(&prm.in_map[l], q[l], batch, H, W, kC, ctc::kChunk, ctc::kHaloW, ctc::kHaloH);
@@ -535,14 +517,7 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* q
     rc = make_nhwc_map(&prm.out_map[l], attn[l], batch * num_classes, H, W, kC, ctc::kChunk, ctc::kTileW, ctc::kTileH);
     if (rc != FOD_OK) return rc;
   }
-  {   // w3 = fod_conv2d_pack_weights(conv3.weight [128][256][1][1]): fp16 hi plane, lo plane, {1/scale, scale, max|w|, 0}
-    const __half* whi = reinterpret_cast<const __half*>(w3);
-    int rc = make_matrix_map_f16(&prm.w_hi_map, whi, kC, 2 * kC, 32, ctc::kBHalfRows);
-    if (rc != FOD_OK) return rc;
-    rc = make_matrix_map_f16(&prm.w_lo_map, whi + (size_t)kC * 2 * kC, kC, 2 * kC, 32, ctc::kBHalfRows);
-    if (rc != FOD_OK) return rc;
-    prm.w_inv = w3 + (size_t)kC * 2 * kC;
-  }
+  prm.w3 = w3;
   prm.b3 = b3;
   prm.num_levels = num_levels;
   prm.num_classes = num_classes;
@@ -556,9 +531,7 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* q
   // each group = one stream-ordered symbol update + one persistent launch.
   const int group = ctc::kMaxTapSets / num_levels;
   float* ctaps_dev = nullptr;
-  float* sfactor_dev = nullptr;
   FOD_CUDA_CALL(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctaps_dev), ctc::c_taps));
-  FOD_CUDA_CALL(cudaGetSymbolAddress(reinterpret_cast<void**>(&sfactor_dev), ctc::c_sfactor));
   ctc::TapPack pk;
   memset(&pk, 0, sizeof(pk));
   for (int c0 = 0; c0 < num_classes; c0 += group) {
@@ -577,7 +550,7 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* q
       pk.src[l] = taps[l] + (size_t)c0 * 7 * kC;
     }
     pk.class_count = cn;
-    ctc::pack_taps_kernel<<<num_levels * cn, kC, 0, as_stream(stream)>>>(pk, ctaps_dev, sfactor_dev);
+    ctc::pack_taps_kernel<<<num_levels * cn, kC, 0, as_stream(stream)>>>(pk, ctaps_dev);
     FOD_CUDA_LAUNCH_CHECK("fod_correlate_levels (pack taps)");
     prm.class_begin = c0;
     prm.class_count = cn;

@@ -6,7 +6,6 @@
 // through cudaGetDriverEntryPoint.
 #pragma once
 #include <cuda.h>
-#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -327,30 +326,6 @@ __device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
-}
-
-// fp16 operand split for kind::f16: (a, b) already scaled by 2^e -> packed fp16 pair of the rounded values (a in the low
-// half) and of the exact remainders (22 significant bits per value, like a tf32 hi/lo split)
-__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-// 2^e with amax * 2^e in [2^13, 2^14) (and its inverse); 1 for zero / denormal-range / non-finite bounds
-__device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
-  const int E = (int)((__float_as_uint(amax) >> 23) & 0xFF);
-  if (E < 32 || E > 240) {
-    scale = 1.f;
-    inv = 1.f;
-  } else {
-    scale = __uint_as_float((uint32_t)(267 - E) << 23);  // 2^(13 - (E - 127))
-    inv = __uint_as_float((uint32_t)(E - 13) << 23);
-  }
-}
-__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t v0, uint32_t v1) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(v0), "r"(v1) : "memory");
 }
 
 // explicit shared-window accesses (a generic pointer would compile to LD/ST with address-space resolution)

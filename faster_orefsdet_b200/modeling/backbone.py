@@ -366,7 +366,7 @@ class FPN(nn.Module):
     def forward(self, x) -> Dict[str, torch.Tensor]:
         return self.top_down(self.bottom_up(x))
 
-    def top_down(self, feats, bounds=None, gates=None, want_bounds: bool = False):
+    def top_down(self, feats, bounds=None, gates=None) -> Dict[str, torch.Tensor]:
         """Lateral 1x1 + nearest 2x upsampling + sum + output 3x3.  ``bounds[name]``: device scalar bounding
         max|feats[name]| when the producer knows it (the tensor-core convolutions need one; computed otherwise).
         ``gates[name]``: [N,C,1,1] factor still to be multiplied into feats[name] (the eSE gate, VoVNet.tc_body)."""
@@ -380,18 +380,10 @@ class FPN(nn.Module):
         def bound(t):
             return ops.new_amax(t.device) if t.is_cuda else None
 
-        out_bounds = []
-
-        def out_conv(m, t, a_in):
-            """FPN output convolution; records max|p_l| for the kernels that consume the map (correlation)."""
-            a_out = bound(t) if tcconv.supported(m, t) else None
-            out_bounds.insert(0, a_out)
-            return run(m, t, a_in, a_out)
-
         top = self.in_features[-1]
         a_prev = bound(feats[top])
         prev = run(self._laterals[0], feats[top], bounds.get(top), a_prev, gates.get(top))
-        results = [out_conv(self._outputs[0], prev, a_prev)]
+        results = [run(self._outputs[0], prev, a_prev)]
         for idx in range(1, len(self._laterals)):
             name = self.in_features[-idx - 1]
             f, lat = feats[name], self._laterals[idx]
@@ -411,11 +403,8 @@ class FPN(nn.Module):
                     a_prev = a_lat + a_prev            # |lateral + upsampled| <= bound + bound
                 if self._fuse_type == "avg":
                     prev = prev / 2
-            results.insert(0, out_conv(self._outputs[idx], prev, a_prev))
-        feats_out = dict(zip(self._out_features, results))
-        if want_bounds:
-            return feats_out, dict(zip(self._out_features, out_bounds))
-        return feats_out
+            results.insert(0, run(self._outputs[idx], prev, a_prev))
+        return dict(zip(self._out_features, results))
 
     def output_shape(self):
         return {n: ShapeSpec(channels=self._out_feature_channels[n], stride=self._out_feature_strides[n])

@@ -295,18 +295,13 @@ class CenterNet2Detector(nn.Module):
         res = self._head_launch(features, image_hw, out_hw, None)
         return self._head_finish(res, features, image_hw, out_hw, want_trace)
 
-    def _head_launch(self, features, image_hw, out_hw, cap, bounds=None):
-        """Kernel launches of the head only (stream-ordered, no host sync: CUDA-graph capturable).  ``bounds[name]``:
-        device scalar bounding max|features[name]| when the producer reported it (computed otherwise)."""
+    def _head_launch(self, features, image_hw, out_hw, cap):
+        """Kernel launches of the head only (stream-ordered, no host sync: CUDA-graph capturable)."""
         bank = self._bank
         raw = [features[f] for f in self.in_features]
-        q_amax = None
-        if bounds is not None and all(bounds.get(f) is not None for f in self.in_features):
-            q_amax = [bounds[f] for f in self.in_features]
         status = ops.new_status(raw[0].device)
-        attn, attn_amax = ops.correlate_levels(raw, bank.taps, self.conv3.weight, self.conv3.bias, q_amax=q_amax,
-                                               want_amax=True)                              # one persistent launch
-        props = self.proposal_generator.propose_raw(attn, status, cap, bounds=attn_amax)
+        attn = ops.correlate_levels(raw, bank.taps, self.conv3.weight, self.conv3.bias)   # one persistent launch
+        props = self.proposal_generator.propose_raw(attn, status, cap)
         out, per_roi = self.roi_heads.detect_raw(raw, bank.bias_cls, props.boxes, props.count, bank.num_classes, image_hw, out_hw,
                                                  status)
         return out, per_roi, props, attn, status
@@ -366,8 +361,8 @@ class CenterNet2Detector(nn.Module):
         first.zero_()
 
         def run():
-            feats, fb = self.backbone.top_down(*vov.tc_body(buf, amax, fuse_gates=True), want_bounds=True)
-            return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None, fb)
+            feats = self.backbone.top_down(*vov.tc_body(buf, amax, fuse_gates=True))
+            return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None)
 
         main = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)

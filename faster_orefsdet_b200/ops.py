@@ -99,26 +99,10 @@ def _empty_nhwc(n: int, h: int, w: int, device) -> Tensor:
     return torch.empty((n, h, w, 128), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
 
 
-_w3_cache: dict = {}
-
-
-def _packed_w3(w3: Tensor) -> Tensor:
-    """conv3.weight [128,256(,1,1)] -> scaled fp16 hi/lo planes (conv2d_pack), cached per (storage, version)."""
-    key = (w3.data_ptr(), w3._version, str(w3.device))
-    hit = _w3_cache.get("w3")
-    if hit is None or hit[0] != key:
-        with torch.no_grad():
-            hit = (key, conv2d_pack(_chk(w3, torch.float32, "w3").detach().reshape(128, 256, 1, 1).contiguous()))
-        _w3_cache["w3"] = hit
-    return hit[1]
-
-
-def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3: Tensor,
-                     q_amax: Optional[Sequence[Tensor]] = None, want_amax: bool = False):
+def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3: Tensor) -> List[Tensor]:
     """All FPN levels in one persistent tensor-core launch.
     q[l] [B,128,H_l,W_l], taps[l] [C,7,128] -> attn[l] [B*C,128,H_l,W_l] (NHWC memory), problem-major
-    (fsod_cen.py:463-470, 482-491, 502-509).  ``q_amax[l]``: device float bounding max|q[l]| (computed with absmax when
-    omitted); with ``want_amax`` also returns the per-level max of attn (device floats) for the next convolution."""
+    (fsod_cen.py:463-470, 482-491, 502-509)."""
     L = len(q)
     if L < 1 or L > 3 or len(taps) != L:
         raise _lib.FodError("correlate_levels: 1..3 levels with one taps tensor each")
@@ -128,19 +112,12 @@ def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3
     for t, qq in zip(taps, q):
         if tuple(t.shape) != (C, 7, 128) or qq.shape[0] != B or qq.shape[1] != 128:
             raise _lib.FodError("correlate_levels: bad shapes")
-    packed = _packed_w3(w3)
+    w3 = _chk(w3, torch.float32, "w3").reshape(128, 256).contiguous()
     b3 = _chk(b3, torch.float32, "b3").contiguous()
-    if q_amax is None:
-        q_amax = [absmax(t) for t in q]
-    q_amax = [_chk(a, torch.float32, "q_amax") for a in q_amax]
     attn = [_empty_nhwc(B * C, t.shape[2], t.shape[3], t.device) for t in q]
-    out_amax = new_amax(q[0].device, L) if want_amax else None
     lv = _levels(q, [0] * L)
-    am_ptrs = (_vp * L)(*[out_amax[i:i + 1].data_ptr() for i in range(L)]) if want_amax else None
-    _lib.check(_lib.lib().fod_correlate_levels(_ptr_array(q), _ptr_array(q_amax), _ptr_array(taps), lv, L, _ptr(packed), _ptr(b3),
-                                               _ptr_array(attn), am_ptrs, B, C, _stream()), "fod_correlate_levels")
-    if want_amax:
-        return attn, [out_amax[i:i + 1] for i in range(L)]
+    _lib.check(_lib.lib().fod_correlate_levels(_ptr_array(q), _ptr_array(taps), lv, L, _ptr(w3), _ptr(b3),
+                                               _ptr_array(attn), B, C, _stream()), "fod_correlate_levels")
     return attn
 
 

@@ -72,26 +72,29 @@ typedef struct {
 int fod_support_taps(const float* proto, int num_classes, int h, int w, float* taps, fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
- * Q2+Q3  depthwise correlation + 1x1 relation conv, fused, for ALL FPN levels and all (image, class) problems in one
- * persistent launch (tcgen05 tensor cores, fp16-split operands = fp32 accuracy, TMA in/out).
- * Replaces fsod_cen.py:463-470 (p3), :482-491 (p4), :502-509 (p5): four depthwise F.conv2d + ReLUs + adds +
- * torch.cat + self.conv3 + ReLU per level per class per image.
- * q, q_amax, taps, attn, attn_amax are HOST arrays of num_levels DEVICE pointers:
- *   q[l]         : [B][H_l][W_l][128]      query map of level l
- *   q_amax[l]    : device float, an upper bound of max|q[l]| (fod_absmax, or the y_amax of the convolution that made q)
- *   taps[l]      : [C][7][128]             from fod_support_taps on the level-l prototype
- *   w3           : fod_conv2d_pack_weights(conv3.weight as [128][256][1][1], cout 128, cin 256, ksize 1);
- *                  input channels = [attn-sum | q]
- *   b3           : [128]
- *   attn[l]      : [B*C][H_l][W_l][128]    problem-major output
- *   attn_amax    : NULL, or per level NULL / a device float (zeroed by the caller) raised to max(attn[l])
- * fod_correlate is the one-level form.
+ * Q2+Q3  depthwise correlation + 1x1 relation conv on one FPN level, fused.
+ * Replaces fsod_cen.py:463-470 (p3), :482-491 (p4), :502-509 (p5): four depthwise
+ * F.conv2d + ReLUs + adds + torch.cat + self.conv3 + ReLU.
+ *   q     : [B][H][W][128]            query map of this level
+ *   taps  : [C][7][128]               from fod_support_taps
+ *   w3    : [128][256]                conv3.weight (out, in) ; in = [attn-sum | q]
+ *   b3    : [128]
+ *   attn  : [B*C][H][W][128]          problem-major output
  */
-int fod_correlate(const float* q, const float* q_amax, const float* taps, const float* w3_packed, const float* b3, float* attn,
-                  float* attn_amax, int batch, int num_classes, int height, int width, fod_stream_t stream);
-int fod_correlate_levels(const float* const* q, const float* const* q_amax, const float* const* taps,
-                         const fod_level_t* levels, int num_levels, const float* w3_packed, const float* b3,
-                         float* const* attn, float* const* attn_amax, int batch, int num_classes, fod_stream_t stream);
+int fod_correlate(const float* q, const float* taps, const float* w3, const float* b3, float* attn, int batch,
+                  int num_classes, int height, int width, fod_stream_t stream);
+
+/* Q2+Q3 for ALL FPN levels and all (image, class) problems in one persistent launch
+ * (tcgen05 tensor cores, 3xTF32 operand splitting = fp32 accuracy, TMA in/out).
+ * Same arithmetic contract as fod_correlate.  q, taps, attn are HOST arrays of
+ * num_levels DEVICE pointers:
+ *   q[l]    : [B][H_l][W_l][128]
+ *   taps[l] : [C][7][128]              from fod_support_taps on the level-l prototype
+ *   attn[l] : [B*C][H_l][W_l][128]     problem-major output
+ */
+int fod_correlate_levels(const float* const* q, const float* const* taps, const fod_level_t* levels, int num_levels,
+                         const float* w3, const float* b3, float* const* attn, int batch, int num_classes,
+                         fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * D1+D2+D3  heat-map sigmoid, candidate threshold, per-level top-k, box decode,

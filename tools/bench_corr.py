@@ -31,9 +31,8 @@ def timeit(fn, iters=20, warm=5):
     return e0.elapsed_time(e1) / iters
 
 
-qa = [[ops.absmax(q) for q in qq] for qq in qs]       # operand bounds (normally reported by the producer of q)
-old = lambda i: [ops.correlate_levels([q], [t], w3, b3, q_amax=[a])[0] for q, t, a in zip(qs[i % NB], taps, qa[i % NB])]
-new = lambda i: ops.correlate_levels(qs[i % NB], taps, w3, b3, q_amax=qa[i % NB])
+old = lambda i: [ops.correlate(q, t, w3, b3) for q, t in zip(qs[i % NB], taps)]
+new = lambda i: ops.correlate_levels(qs[i % NB], taps, w3, b3)
 a = old(0)
 b = new(0)
 torch.cuda.synchronize()
