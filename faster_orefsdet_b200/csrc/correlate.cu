@@ -58,5 +58,5 @@ extern "C" int fod_correlate(const float* q, const float* taps, const float* w3,
   lv.height = height;
   lv.width = width;
   lv.stride = 0;
-  return fod_correlate_levels(&q, &taps, &lv, 1, w3, b3, &attn, batch, num_classes, stream);
+  return fod_correlate_levels(&q, &taps, &lv, 1, w3, b3, &attn, nullptr, batch, num_classes, stream);
 }

@@ -82,6 +82,7 @@ struct Params {
   Level lv[FOD_MAX_LEVELS];
   const float* w3;
   const float* b3;
+  float* attn_amax[FOD_MAX_LEVELS];   // null or device scalar per level (zeroed by the caller): raised to max(attn)
   // problems of this launch: images x classes [class_begin, class_begin + class_count) of num_classes
   int num_levels, num_classes, class_begin, class_count, total_tiles, num_pairs;
 };
@@ -432,6 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
     const int m = qd * 32 + lane;  // pixel row of the tile == TMEM lane
     const uint32_t acc_empty_leader = map_to_cta(acc_empty(0), 0);
     const bool issuer = (warp == kWarpEpi0 && lane == 0);
+    float lmax0 = 0.f, lmax1 = 0.f, lmax2 = 0.f;   // running max of each level's output over this lane's pixels
     for (int i = 0; iter_valid(i); ++i) {
       int t = tile_of(i);
       bool do_store = t < T;
@@ -442,6 +444,8 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
       mbar_wait(acc_full(as_), aph);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColAcc + as_ * 128;
+      const bool px_valid = do_store && tcd.y0 + (m >> 4) < P.lv[tcd.level].H && tcd.x0 + (m & 15) < P.lv[tcd.level].W;
+      float vmax = 0.f;
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         uint32_t v[32];
@@ -462,6 +466,7 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
           o.y = fmaxf(__uint_as_float(v[c4 * 4 + 1]) + bb.y, 0.f);
           o.z = fmaxf(__uint_as_float(v[c4 * 4 + 2]) + bb.z, 0.f);
           o.w = fmaxf(__uint_as_float(v[c4 * 4 + 3]) + bb.w, 0.f);
+          vmax = fmaxf(fmaxf(vmax, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
           sts4s(sbase + kOffOut + (m >> 3) * 1024 + (m & 7) * 128 + ((c4 ^ (m & 7)) << 4), o);
         }
         fence_proxy_async_smem();
@@ -471,8 +476,21 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
           tma_store_commit();
         }
       }
+      if (px_valid) {
+        if (tcd.level == 0) lmax0 = fmaxf(lmax0, vmax);
+        else if (tcd.level == 1) lmax1 = fmaxf(lmax1, vmax);
+        else lmax2 = fmaxf(lmax2, vmax);
+      }
     }
     if (issuer) tma_store_wait<0>();
+    // max of each level's output (>= 0 after the ReLU) = the operand bound the tower convolution needs (fod_conv2d_nhwc
+    // x_amax): one atomic per warp and level for the whole launch, no extra pass over the maps
+#pragma unroll
+    for (int l = 0; l < FOD_MAX_LEVELS; ++l) {
+      const float lm = l == 0 ? lmax0 : (l == 1 ? lmax1 : lmax2);
+      const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(lm));
+      if (lane == 0 && wmax && l < P.num_levels && P.attn_amax[l]) atomicMax(reinterpret_cast<unsigned int*>(P.attn_amax[l]), wmax);
+    }
   } else if (warp >= kWarpSten0) {
     // ------------------------------------------------------------------ stencil: build A in tensor memory
     StencilCtx cx;
@@ -497,8 +515,8 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
 using namespace fod;
 
 extern "C" int fod_correlate_levels(const float* const* q, const float* const* taps, const fod_level_t* levels,
-                                    int num_levels, const float* w3, const float* b3, float* const* attn, int batch,
-                                    int num_classes, fod_stream_t stream) {
+                                    int num_levels, const float* w3, const float* b3, float* const* attn,
+                                    float* const* attn_amax, int batch, int num_classes, fod_stream_t stream) {
   FOD_REQUIRE(q && taps && levels && w3 && b3 && attn, "fod_correlate_levels: null pointer");
   FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_correlate_levels: 1..%d levels", FOD_MAX_LEVELS);
   FOD_REQUIRE(batch >= 0 && num_classes >= 0, "fod_correlate_levels: bad sizes");
@@ -510,6 +528,7 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* t
   for (int l = 0; l < num_levels; ++l) {
     const int H = levels[l].height, W = levels[l].width;
     FOD_REQUIRE(H > 0 && W > 0 && q[l] && attn[l] && taps[l], "fod_correlate_levels: level %d invalid", l);
+    prm.attn_amax[l] = attn_amax ? attn_amax[l] : nullptr;
     FOD_REQUIRE((((uintptr_t)q[l] | (uintptr_t)attn[l] | (uintptr_t)taps[l]) & 15) == 0,
                 "fod_correlate_levels: level %d pointers must be 16-byte aligned", l);
     int rc = make_nhwc_map(&prm.in_map[l], q[l], batch, H, W, kC, ctc::kChunk, ctc::kHaloW, ctc::kHaloH);

@@ -66,11 +66,12 @@ class CenterNetHead(nn.Module):
         nn.init.constant_(self.agn_hm.bias, -math.log((1 - c.PRIOR_PROB) / c.PRIOR_PROB))
         nn.init.normal_(self.agn_hm.weight, std=0.01)
 
-    def forward(self, x: Sequence[torch.Tensor]):
+    def forward(self, x: Sequence[torch.Tensor], bounds: Optional[Sequence[torch.Tensor]] = None):
+        """``bounds[l]``: device scalar bounding max|x[l]| when the producer reported it (ops.correlate_levels)."""
         clss, bbox_reg, agn_hms = [], [], []
         for l, feature in enumerate(x):
             if tcconv.supported(self.agn_hm, feature):
-                hm, reg = self._level_tc(feature)
+                hm, reg = self._level_tc(feature, bounds[l] if bounds is not None else None)
             else:
                 t = self.bbox_tower(feature)
                 hm, reg = self.agn_hm(t), self.bbox_pred(t)
@@ -79,11 +80,10 @@ class CenterNetHead(nn.Module):
             bbox_reg.append(F.relu(self.scales[l](reg)))
         return clss, bbox_reg, agn_hms
 
-    def _level_tc(self, t: torch.Tensor):
+    def _level_tc(self, t: torch.Tensor, bound: Optional[torch.Tensor] = None):
         """Tower and output convolutions on the tensor cores (csrc/conv_tc.cu); agn_hm and bbox_pred read the same
         tower output, so they run as ONE convolution with 1 + 4 (+3 zero) output channels."""
-        mods = list(self.bbox_tower)
-        bound = None          # device scalar bounding max|t| when the producing kernel reported it
+        mods = list(self.bbox_tower)     # ``bound``: device scalar bounding max|t| when the producing kernel reported it
         i = 0
         while i < len(mods):
             m = mods[i]
@@ -154,9 +154,10 @@ class CenterNet(nn.Module):
         return self.to_instances(raw, [images.image_sizes[p // per_image] for p in range(features[0].shape[0])]), {}
 
     @torch.no_grad()
-    def propose_raw(self, features: Sequence[torch.Tensor], status: torch.Tensor, roi_cap: Optional[int] = None) -> RawProposals:
+    def propose_raw(self, features: Sequence[torch.Tensor], status: torch.Tensor, roi_cap: Optional[int] = None,
+                    bounds: Optional[Sequence[torch.Tensor]] = None) -> RawProposals:
         """features[l]: [P,128,H_l,W_l] correlated maps, one row per (image, class) problem."""
-        _, reg, hm = self.centernet_head(features)
+        _, reg, hm = self.centernet_head(features, bounds)
         boxes, scores, loc, level_count, cand_count = ops.decode_topk(
             hm, reg, self.strides, self.score_thresh, self.pre_nms_topk_test, status, hm_is_logit=True)
         keep, pb, ps, pc = ops.nms_proposals(boxes, scores, cand_count, self.nms_thresh_test, self.post_nms_topk_test,

@@ -300,8 +300,8 @@ class CenterNet2Detector(nn.Module):
         bank = self._bank
         raw = [features[f] for f in self.in_features]
         status = ops.new_status(raw[0].device)
-        attn = ops.correlate_levels(raw, bank.taps, self.conv3.weight, self.conv3.bias)   # one persistent launch
-        props = self.proposal_generator.propose_raw(attn, status, cap)
+        attn, attn_amax = ops.correlate_levels(raw, bank.taps, self.conv3.weight, self.conv3.bias, want_amax=True)
+        props = self.proposal_generator.propose_raw(attn, status, cap, bounds=attn_amax)
         out, per_roi = self.roi_heads.detect_raw(raw, bank.bias_cls, props.boxes, props.count, bank.num_classes, image_hw, out_hw,
                                                  status)
         return out, per_roi, props, attn, status

@@ -183,13 +183,16 @@ def pack_instances(boxes, scores, classes, count, image_sizes) -> List[Instances
         parts.append((torch.split(flat[:, :4], counts), torch.split(flat[:, 4], counts),
                       torch.split(flat[:, 5].to(torch.int64), counts)))
     (db, ds, dc), (hb, hs, hc) = parts
+    def boxes_of(t):          # the fields are already [n, 4] fp32: skip the constructor's conversions and checks
+        bx = Boxes.__new__(Boxes)
+        bx.tensor = t
+        return bx
+
     out = []
     for b in range(B):
-        inst = Instances(tuple(int(x) for x in image_sizes[b]))
-        inst.pred_boxes = Boxes(db[b])
-        inst.scores = ds[b]
-        inst.pred_classes = dc[b]
-        if hasattr(inst, "__dict__"):
-            inst.__dict__["_host_mirror"] = {"pred_boxes": Boxes(hb[b]), "scores": hs[b], "pred_classes": hc[b]}
+        inst = Instances.__new__(Instances)           # the three fields have equal lengths by construction
+        inst.__dict__["_image_size"] = (int(image_sizes[b][0]), int(image_sizes[b][1]))
+        inst.__dict__["_fields"] = {"pred_boxes": boxes_of(db[b]), "scores": ds[b], "pred_classes": dc[b]}
+        inst.__dict__["_host_mirror"] = {"pred_boxes": boxes_of(hb[b]), "scores": hs[b], "pred_classes": hc[b]}
         out.append(inst)
     return out

@@ -99,10 +99,11 @@ def _empty_nhwc(n: int, h: int, w: int, device) -> Tensor:
     return torch.empty((n, h, w, 128), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
 
 
-def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3: Tensor) -> List[Tensor]:
+def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3: Tensor, want_amax: bool = False):
     """All FPN levels in one persistent tensor-core launch.
     q[l] [B,128,H_l,W_l], taps[l] [C,7,128] -> attn[l] [B*C,128,H_l,W_l] (NHWC memory), problem-major
-    (fsod_cen.py:463-470, 482-491, 502-509)."""
+    (fsod_cen.py:463-470, 482-491, 502-509).  With ``want_amax`` also returns max(attn[l]) per level as device floats
+    (the operand bounds of the tower convolutions), tracked in the kernel's epilogue."""
     L = len(q)
     if L < 1 or L > 3 or len(taps) != L:
         raise _lib.FodError("correlate_levels: 1..3 levels with one taps tensor each")
@@ -116,8 +117,12 @@ def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3
     b3 = _chk(b3, torch.float32, "b3").contiguous()
     attn = [_empty_nhwc(B * C, t.shape[2], t.shape[3], t.device) for t in q]
     lv = _levels(q, [0] * L)
+    out_amax = torch.zeros((L,), dtype=torch.float32, device=q[0].device) if want_amax else None
+    am_ptrs = (_vp * L)(*[out_amax[i:i + 1].data_ptr() for i in range(L)]) if want_amax else None
     _lib.check(_lib.lib().fod_correlate_levels(_ptr_array(q), _ptr_array(taps), lv, L, _ptr(w3), _ptr(b3),
-                                               _ptr_array(attn), B, C, _stream()), "fod_correlate_levels")
+                                               _ptr_array(attn), am_ptrs, B, C, _stream()), "fod_correlate_levels")
+    if want_amax:
+        return attn, [out_amax[i:i + 1] for i in range(L)]
     return attn
 
 

@@ -91,10 +91,12 @@ int fod_correlate(const float* q, const float* taps, const float* w3, const floa
  *   q[l]    : [B][H_l][W_l][128]
  *   taps[l] : [C][7][128]              from fod_support_taps on the level-l prototype
  *   attn[l] : [B*C][H_l][W_l][128]     problem-major output
+ *   attn_amax : NULL, or per level NULL / a DEVICE float (zeroed by the caller) that is raised to max(attn[l]): the
+ *               operand bound of the convolution that consumes the map (fod_conv2d_nhwc x_amax), without a pass over it
  */
 int fod_correlate_levels(const float* const* q, const float* const* taps, const fod_level_t* levels, int num_levels,
-                         const float* w3, const float* b3, float* const* attn, int batch, int num_classes,
-                         fod_stream_t stream);
+                         const float* w3, const float* b3, float* const* attn, float* const* attn_amax, int batch,
+                         int num_classes, fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * D1+D2+D3  heat-map sigmoid, candidate threshold, per-level top-k, box decode,
