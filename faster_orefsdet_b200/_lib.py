@@ -59,7 +59,8 @@ _PROTOTYPES = {
     "fod_conv2d_packed_floats": ([_i, _i, _i], ctypes.c_size_t),
     "fod_conv2d_pack_weights": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "fod_conv2d_nhwc": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_long, _vp, _vp,
-                         _i, _vp, _vp, _vp], _i),
+                         _i, _vp, _vp, _i, _vp, _vp, _vp], _i),
+    "fod_group_norm_affine": ([_vp, _vp, _i, _i, _i, _i, ctypes.c_long, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_conv2d_tiles_per_image": ([_i, _i], _i),
     "fod_ese_gate": ([_vp, _i, _i, _i, ctypes.c_long, _vp, _vp, _vp, _vp], _i),
 }

@@ -121,8 +121,13 @@ struct Params {
   const float* w_inv;   // 1 / weight scale (tail of the packed buffer)
   float* y_amax;        // null or: atomically raised to max|y|
   float rz_kappa;       // first-order compensation of the accumulator's round-toward-zero bias, per MMA of a part
-  const float* a_gate;  // null or: [N][Cin] factors multiplied into the input (the eSE gate of the producing stage)
+  const float* a_gate;  // null or: [N][Cin] factors multiplied into the input (the eSE gate of the producing stage, or the
+                        // per-(image, channel) scale of a normalisation)
+  const float* a_shift; // null or: [N][Cin] added after the factor, followed by ReLU if a_relu: x' = act(x * a_gate + a_shift)
+                        // for pixels inside the image (the zero padding stays zero): GroupNorm + ReLU of the producer's map
+  int a_relu, in_h, in_w;
   float* colsum;        // null or: [N][tiles_per_img][Cout] per-tile channel sums of the output (for the eSE average)
+  float* colsumsq;      // null or: same shape, sums of squares (GroupNorm statistics of the output)
   const float* res;     // null or: residual [N][res_h][res_w][cout] (dense NHWC) added before the activation;
   int res_h, res_w, res_shift;   // read at (oy >> res_shift, ox >> res_shift): 0 = same size, 1 = nearest 2x upsampling
   int tiles_x, tiles_per_img, tiles_total;
@@ -440,23 +445,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int vy = min(kTileH, P.ho - ty * kTileH), vx = min(kTileW, P.wo - tx * kTileW);
         const uint32_t c4 = (uint32_t)(lane & 7), ro = (uint32_t)(lane >> 3);
         const uint32_t sb = sbase + kOffSum + (uint32_t)qd * kSlabBytes;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acq = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
         for (uint32_t r0 = 0; r0 < 128; r0 += 4) {
           const uint32_t r = r0 + ro;
           if ((int)(r >> 4) < vy && (int)(r & 15) < vx) {
             const float4 v = lds4s(sb + (r >> 3) * 1024 + (r & 7) * 128 + ((c4 ^ (r & 7)) << 4));
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            acq.x = fmaf(v.x, v.x, acq.x); acq.y = fmaf(v.y, v.y, acq.y);
+            acq.z = fmaf(v.z, v.z, acq.z); acq.w = fmaf(v.w, v.w, acq.w);
           }
         }
 #pragma unroll
         for (int sh = 8; sh <= 16; sh <<= 1) {
           acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sh); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sh);
           acc.z += __shfl_xor_sync(0xffffffffu, acc.z, sh); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, sh);
+          acq.x += __shfl_xor_sync(0xffffffffu, acq.x, sh); acq.y += __shfl_xor_sync(0xffffffffu, acq.y, sh);
+          acq.z += __shfl_xor_sync(0xffffffffu, acq.z, sh); acq.w += __shfl_xor_sync(0xffffffffu, acq.w, sh);
         }
         const int ch = ch0 + qd * 32 + (int)c4 * 4;
-        if (ro == 0 && ch < P.cout)
-          *reinterpret_cast<float4*>(P.colsum + ((size_t)n * P.tiles_per_img + tt) * P.cout + ch) = acc;
+        if (ro == 0 && ch < P.cout) {
+          const size_t o = ((size_t)n * P.tiles_per_img + tt) * P.cout + ch;
+          *reinterpret_cast<float4*>(P.colsum + o) = acc;
+          if (P.colsumsq) *reinterpret_cast<float4*>(P.colsumsq + o) = acq;
+        }
       }
     }
     if (issuer) tma_store_wait<0>();
@@ -487,17 +499,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int crow = (cw * 32 + lane) >> 1, chalf = lane & 1;   // phase A: (row, 16-channel half) of this lane
     uint32_t g = 0, gq = 0;
 
-    const float* gate_row = nullptr;   // a_gate row of this unit's image, at this chunk's first channel
+    const float* gate_row = nullptr;    // a_gate row of this unit's image, at this chunk's first channel
+    const float* shift_row = nullptr;   // a_shift likewise
+    bool row_in = true;                 // the row being transformed lies inside the image (set by the caller)
     auto gated = [&](float4 v, int c4) {   // c4: index of the 4-channel group inside the 32-channel chunk
       if (gate_row) {
         const float4 gv = ldg4(gate_row + c4 * 4);
         v.x *= gv.x; v.y *= gv.y; v.z *= gv.z; v.w *= gv.w;
       }
+      if (shift_row) {   // affine normalisation (+ ReLU) of the producer's map; the padding ring stays zero
+        const float4 sv = ldg4(shift_row + c4 * 4);
+        v.x += sv.x; v.y += sv.y; v.z += sv.z; v.w += sv.w;
+        if (P.a_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        if (!row_in) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       return v;
     };
+    int in_y0 = 0, in_x0 = 0;   // image coordinates of row 0 of the staged tile (tile origin - padding)
     auto convert_stage = [&](uint32_t qt) {
       const uint32_t at = qt + (uint32_t)crow * 128u;
       const uint32_t key = (uint32_t)(crow & 7);
+      {
+        const int ry = crow / hw, rx = crow - ry * hw;
+        row_in = in_y0 + ry >= 0 && in_y0 + ry < P.in_h && in_x0 + rx >= 0 && in_x0 + rx < P.in_w;
+      }
       float4 x[4];
       if (crow < stage_rows) {
 #pragma unroll
@@ -530,9 +555,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     };
 
     for (int i = 0; in_range(i); ++i) {
-      const int unit_n = min(unit_tile(i), P.tiles_total - 1) / P.tiles_per_img;
+      const int unit_t = min(unit_tile(i), P.tiles_total - 1);
+      const int unit_n = unit_t / P.tiles_per_img;
+      {
+        const int tt = unit_t - unit_n * P.tiles_per_img, ty = tt / P.tiles_x, tx = tt - ty * P.tiles_x;
+        in_y0 = ty * kTileH * P.stride - (ksz >> 1);
+        in_x0 = tx * kTileW * P.stride - (ksz >> 1);
+      }
       for (int cc = 0; cc < cin_chunks; ++cc) {
         if (P.a_gate) gate_row = P.a_gate + (size_t)unit_n * P.cin + cc * kChunk;
+        if (P.a_shift) shift_row = P.a_shift + (size_t)unit_n * P.cin + cc * kChunk;
         int qs = gq % kQStages;
         uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
         if (!per_tap) {
@@ -553,6 +585,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t key = (uint32_t)(r & 7);
             uint32_t hi[8], lo[8];
             if (direct) {
+              {   // image position of this pixel's input for this tap (a per-tap tile holds every stride-th pixel)
+                const int iy = in_y0 + (per_tap ? py * P.stride + dy : py), ix = in_x0 + (per_tap ? px * P.stride + dx : px);
+                row_in = iy >= 0 && iy < P.in_h && ix >= 0 && ix < P.in_w;
+              }
               float4 x[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) x[j] = gated(lds4s(at + ((((uint32_t)(half * 4 + j)) ^ key) << 4)), half * 4 + j);
@@ -757,9 +793,12 @@ extern "C" int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, i
 extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax,
                                int n_amax, const float* packed, const float* bias, int cout, int ksize, int stride,
                                int relu, float* y, long y_pixel_stride, float* y_amax, const float* residual,
-                               int residual_upsample2, const float* a_gate, float* colsum, fod_stream_t stream) {
-  FOD_REQUIRE((((uintptr_t)a_gate | (uintptr_t)colsum) & 15) == 0, "fod_conv2d_nhwc: a_gate / colsum must be 16-byte aligned");
-  FOD_REQUIRE(!a_gate || cin % 32 == 0, "fod_conv2d_nhwc: a_gate needs cin to be a multiple of 32");
+                               int residual_upsample2, const float* a_gate, const float* a_shift, int a_relu, float* colsum,
+                               float* colsumsq, fod_stream_t stream) {
+  FOD_REQUIRE((((uintptr_t)a_gate | (uintptr_t)a_shift | (uintptr_t)colsum | (uintptr_t)colsumsq) & 15) == 0,
+              "fod_conv2d_nhwc: a_gate / a_shift / colsum / colsumsq must be 16-byte aligned");
+  FOD_REQUIRE((!a_gate && !a_shift) || cin % 32 == 0, "fod_conv2d_nhwc: a_gate / a_shift need cin to be a multiple of 32");
+  FOD_REQUIRE(!colsumsq || colsum, "fod_conv2d_nhwc: colsumsq needs colsum");
   FOD_REQUIRE(x && packed && y && x_amax, "fod_conv2d_nhwc: null pointer");
   FOD_REQUIRE(((uintptr_t)residual & 15) == 0, "fod_conv2d_nhwc: residual must be 16-byte aligned");
   FOD_REQUIRE(n_amax >= 1 && n_amax <= 8, "fod_conv2d_nhwc: 1..8 input bounds");
@@ -813,7 +852,12 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.ho = ho;
   prm.wo = wo;
   prm.a_gate = a_gate;
+  prm.a_shift = a_shift;
+  prm.a_relu = a_relu;
+  prm.in_h = h;
+  prm.in_w = w;
   prm.colsum = colsum;
+  prm.colsumsq = colsumsq;
   prm.cin = cin;
   prm.res = residual;
   prm.res_shift = residual_upsample2 ? 1 : 0;

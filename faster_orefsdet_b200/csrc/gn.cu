@@ -76,6 +76,54 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const float* __restrict
   }
 }
 
+// GroupNorm as a per-(map, channel) affine map from the per-tile channel sums / sums of squares that the producing
+// convolution wrote (fod_conv2d_nhwc colsum / colsumsq): scale = rstd * gamma, shift = beta - mean * scale.  The consumer
+// applies x * scale + shift (+ ReLU) to its input operand, so the normalised map never exists in memory.
+// One CTA per map; fp64 across tiles and channels of a group; bound = max_c(|scale_c| * x_amax + |shift_c|).
+__global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ colsum, const float* __restrict__ colsumsq,
+                                                     int tiles, int channels, int cpg, double inv_n,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                     const float* __restrict__ x_amax, float* __restrict__ scale,
+                                                     float* __restrict__ shift, float* __restrict__ y_amax) {
+  extern __shared__ double sm[];   // [channels] sums, [channels] sums of squares
+  double* s1 = sm;
+  double* s2 = sm + channels;
+  const size_t base = (size_t)blockIdx.x * tiles * channels;
+  for (int c = threadIdx.x; c < channels; c += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    for (int t = 0; t < tiles; ++t) {
+      a += (double)colsum[base + (size_t)t * channels + c];
+      b += (double)colsumsq[base + (size_t)t * channels + c];
+    }
+    s1[c] = a;
+    s2[c] = b;
+  }
+  __syncthreads();
+  float vmax = 0.f;
+  const float xa = x_amax ? __ldg(x_amax) : 0.f;
+  for (int c = threadIdx.x; c < channels; c += blockDim.x) {
+    const int g0 = (c / cpg) * cpg;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < cpg; ++k) {
+      a += s1[g0 + k];
+      b += s2[g0 + k];
+    }
+    const double mean = a * inv_n;
+    double var = b * inv_n - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = rstd * (gamma ? gamma[c] : 1.f);
+    const float sh = (beta ? beta[c] : 0.f) - (float)mean * sc;
+    scale[(size_t)blockIdx.x * channels + c] = sc;
+    shift[(size_t)blockIdx.x * channels + c] = sh;
+    vmax = fmaxf(vmax, fabsf(sc) * xa + fabsf(sh));
+  }
+  if (y_amax) {
+    const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+    if ((threadIdx.x & 31) == 0 && w) atomicMax(reinterpret_cast<unsigned int*>(y_amax), w);
+  }
+}
+
 }  // namespace gn
 }  // namespace fod
 
@@ -110,5 +158,19 @@ extern "C" int fod_group_norm_nhwc(const float* x, int maps, long hw, int channe
                                                                             static_cast<const double*>(workspace), gamma, beta,
                                                                             eps, relu, total4, y_amax);
   FOD_CUDA_LAUNCH_CHECK("fod_group_norm_nhwc (apply)");
+  return FOD_OK;
+}
+
+extern "C" int fod_group_norm_affine(const float* colsum, const float* colsumsq, int maps, int tiles_per_map, int channels,
+                                     int groups, long hw, const float* gamma, const float* beta, float eps,
+                                     const float* x_amax, float* scale, float* shift, float* y_amax, fod_stream_t stream) {
+  FOD_REQUIRE(colsum && colsumsq && scale && shift, "fod_group_norm_affine: null pointer");
+  FOD_REQUIRE(maps >= 0 && tiles_per_map > 0 && channels > 0 && groups > 0 && channels % groups == 0 && hw > 0 &&
+                  channels <= 2048, "fod_group_norm_affine: bad sizes");
+  if (maps == 0) return FOD_OK;
+  const int cpg = channels / groups;
+  gn::affine_kernel<<<maps, 256, 2 * channels * sizeof(double), as_stream(stream)>>>(
+      colsum, colsumsq, tiles_per_map, channels, cpg, 1.0 / ((double)hw * cpg), gamma, beta, eps, x_amax, scale, shift, y_amax);
+  FOD_CUDA_LAUNCH_CHECK("fod_group_norm_affine");
   return FOD_OK;
 }

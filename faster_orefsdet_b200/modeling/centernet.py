@@ -80,10 +80,31 @@ class CenterNetHead(nn.Module):
             bbox_reg.append(F.relu(self.scales[l](reg)))
         return clss, bbox_reg, agn_hms
 
+    # conv -> GroupNorm -> ReLU -> conv without writing the normalised map (statistics from the first convolution's
+    # epilogue, affine + ReLU on the second one's operand): correct (tests/test_conv_gpu.py) but 0.37 ms per step SLOWER
+    # than the separate GroupNorm kernel at batch 64: the narrow output convolution (N = 16) is bound by its operand
+    # conversion, which now also waits for two global loads per 4 channels.  Off until those rows are staged in smem.
+    FUSE_GROUP_NORM = False
+
     def _level_tc(self, t: torch.Tensor, bound: Optional[torch.Tensor] = None):
         """Tower and output convolutions on the tensor cores (csrc/conv_tc.cu); agn_hm and bbox_pred read the same
         tower output, so they run as ONE convolution with 1 + 4 (+3 zero) output channels."""
         mods = list(self.bbox_tower)     # ``bound``: device scalar bounding max|t| when the producing kernel reported it
+        if (self.FUSE_GROUP_NORM and len(mods) == 3 and isinstance(mods[0], nn.Conv2d) and isinstance(mods[1], nn.GroupNorm)
+                and isinstance(mods[2], nn.ReLU) and mods[1].num_channels % 32 == 0 and tcconv.supported(mods[0], t)):
+            # conv -> GroupNorm -> ReLU -> conv with the normalised map never written: the tower convolution's epilogue
+            # emits per-tile channel sums and sums of squares, a tiny kernel turns them into a per-(problem, channel) scale
+            # and shift, and the output convolution applies relu(x * scale + shift) to its input operand
+            conv, gn = mods[0], mods[1]
+            n, _, h, w = t.shape
+            tiles = ops.conv2d_tiles_per_image(h, w)
+            cs = torch.empty((n, tiles, conv.out_channels), dtype=torch.float32, device=t.device)
+            cq = torch.empty_like(cs)
+            a_t = ops.new_amax(t.device)
+            t = tcconv.conv(t, conv, x_amax=bound, y_amax=a_t, colsum=cs, colsumsq=cq)
+            scale, shift, a_g = ops.group_norm_affine(cs, cq, h * w, gn.num_groups, gn.weight, gn.bias, gn.eps, x_amax=a_t)
+            y = tcconv.conv(t, self.agn_hm, extra=self.bbox_pred, x_amax=a_g, a_gate=scale, a_shift=shift, a_relu=True)
+            return y[:, 0:1], y[:, 1:5]
         i = 0
         while i < len(mods):
             m = mods[i]

@@ -351,7 +351,8 @@ def new_amax(device, n: int = 1) -> Tensor:
 def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ksize: int, relu: bool = False,
                 out: Optional[Tensor] = None, stride: int = 1, x_amax: Optional[Tensor] = None,
                 y_amax: Optional[Tensor] = None, residual: Optional[Tensor] = None, residual_upsample2: bool = False,
-                a_gate: Optional[Tensor] = None, colsum: Optional[Tensor] = None) -> Tensor:
+                a_gate: Optional[Tensor] = None, colsum: Optional[Tensor] = None, a_shift: Optional[Tensor] = None,
+                a_relu: bool = False, colsumsq: Optional[Tensor] = None) -> Tensor:
     """Convolution with padding ksize//2 on the tensor cores (fp16-split operands, fp32 accuracy), bias + optional
     ReLU fused.  x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise.
     ``x_amax``: device float tensor (1..8 values) bounding max|x| (computed with ``absmax`` when omitted, which needs a
@@ -381,13 +382,17 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
             raise _lib.FodError(f"conv2d_nhwc: residual shape {tuple(residual.shape)}, expected {(n, cout, rh, rw)}")
     if a_gate is not None:       # [N, Cin] factors multiplied into x (the eSE gate of the stage that produced x)
         a_gate = _chk(a_gate, torch.float32, "a_gate").reshape(n, cin).contiguous()
-    if colsum is not None:       # [N, tiles per image, Cout] per-tile channel sums of the output (ese_gate)
-        _chk(colsum, torch.float32, "colsum")
-        if tuple(colsum.shape) != (n, conv2d_tiles_per_image(ho, wo), cout) or not colsum.is_contiguous():
-            raise _lib.FodError("conv2d_nhwc: bad colsum buffer")
+    if a_shift is not None:      # x' = act(x * a_gate + a_shift) inside the image (group_norm_affine)
+        a_shift = _chk(a_shift, torch.float32, "a_shift").reshape(n, cin).contiguous()
+    for name, cs in (("colsum", colsum), ("colsumsq", colsumsq)):   # [N, tiles per image, Cout] per-tile channel sums
+        if cs is not None:
+            _chk(cs, torch.float32, name)
+            if tuple(cs.shape) != (n, conv2d_tiles_per_image(ho, wo), cout) or not cs.is_contiguous():
+                raise _lib.FodError(f"conv2d_nhwc: bad {name} buffer")
     _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(x_amax), int(x_amax.numel()), _ptr(packed), _ptr(bias),
                                           cout, ksize, int(stride), int(relu), _ptr(out), ps_y, _ptr(y_amax), _ptr(residual),
-                                          int(residual_upsample2), _ptr(a_gate), _ptr(colsum), _stream()), "fod_conv2d_nhwc")
+                                          int(residual_upsample2), _ptr(a_gate), _ptr(a_shift), int(a_relu), _ptr(colsum),
+                                          _ptr(colsumsq), _stream()), "fod_conv2d_nhwc")
     return out
 
 
@@ -404,6 +409,24 @@ def ese_gate(colsum: Tensor, hw: int, fc_weight: Tensor, fc_bias: Tensor) -> Ten
     gate = torch.empty((n, c), dtype=torch.float32, device=colsum.device)
     _lib.check(_lib.lib().fod_ese_gate(_ptr(colsum), n, tiles, c, int(hw), _ptr(w), _ptr(b), _ptr(gate), _stream()), "fod_ese_gate")
     return gate
+
+
+def group_norm_affine(colsum: Tensor, colsumsq: Tensor, hw: int, groups: int, gamma: Optional[Tensor], beta: Optional[Tensor],
+                      eps: float, x_amax: Optional[Tensor] = None):
+    """GroupNorm statistics from the per-tile channel sums of the producing convolution -> (scale [N,C], shift [N,C],
+    bound of the normalised map as a device float): the consumer applies act(x * scale + shift) to its operand
+    (conv2d_nhwc a_gate / a_shift / a_relu)."""
+    n, tiles, c = colsum.shape
+    dev = colsum.device
+    scale = torch.empty((n, c), dtype=torch.float32, device=dev)
+    shift = torch.empty((n, c), dtype=torch.float32, device=dev)
+    bound = torch.zeros((1,), dtype=torch.float32, device=dev)
+    g = None if gamma is None else _chk(gamma, torch.float32, "gamma").contiguous()
+    b = None if beta is None else _chk(beta, torch.float32, "beta").contiguous()
+    _lib.check(_lib.lib().fod_group_norm_affine(_ptr(colsum), _ptr(colsumsq), n, tiles, c, groups, int(hw), _ptr(g), _ptr(b),
+                                                float(eps), _ptr(x_amax), _ptr(scale), _ptr(shift), _ptr(bound), _stream()),
+               "fod_group_norm_affine")
+    return scale, shift, bound
 
 
 def group_norm_nhwc(x: Tensor, groups: int, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float,

@@ -229,7 +229,10 @@ int fod_batched_nms(const float* boxes, const float* scores, const int64_t* idxs
  *             [N][Ho][Wo][cout], or with residual_upsample2 [N][ceil(Ho/2)][ceil(Wo/2)][cout] read at (oy/2, ox/2) -
  *             the nearest-neighbour 2x upsampling + sum of the FPN top-down path (d2!/modeling/backbone/fpn.py:139-147)
  *   a_gate  : NULL, or [N][cin] factors multiplied into x before the convolution (cin a multiple of 32)
+ *   a_shift : NULL, or [N][cin] added after the factor, then ReLU if a_relu; applied to pixels inside the image only (the
+ *             zero padding stays zero)
  *   colsum  : NULL, or [N][tiles per image][cout]: receives the sum of y over each 8 x 16 output tile, per channel
+ *   colsumsq: NULL, or the same for y^2 (needs colsum)
  * cin, cout and both pixel strides must be multiples of 4; pointers 16-byte aligned.
  */
 size_t fod_conv2d_packed_floats(int cout, int cin, int ksize);
@@ -238,7 +241,14 @@ int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, f
 int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax, int n_amax,
                     const float* packed, const float* bias, int cout, int ksize, int stride, int relu, float* y,
                     long y_pixel_stride, float* y_amax, const float* residual, int residual_upsample2, const float* a_gate,
-                    float* colsum, fod_stream_t stream);
+                    const float* a_shift, int a_relu, float* colsum, float* colsumsq, fod_stream_t stream);
+/* GroupNorm (+ ReLU) between two convolutions without materialising the normalised map (CenterNetHead tower,
+ * centernet_head.py:61-72, 145-150): the first convolution writes colsum / colsumsq, fod_group_norm_affine turns them
+ * into scale / shift [maps][channels] (and the bound max|normalised map| from the bound x_amax of the raw map), the
+ * second convolution applies act(x * a_gate + a_shift) to its input operand (a_gate = scale, a_shift = shift, a_relu). */
+int fod_group_norm_affine(const float* colsum, const float* colsumsq, int maps, int tiles_per_map, int channels, int groups,
+                          long hw, const float* gamma, const float* beta, float eps, const float* x_amax, float* scale,
+                          float* shift, float* y_amax, fod_stream_t stream);
 /* eSE attention of the OSA stages (d2!/modeling/backbone/vovnet.py eSEModule: x * hsigmoid(fc(avg_pool(x)))) without a
  * pass over x: the convolution that produces x writes per-tile channel sums (colsum), fod_ese_gate turns them into
  * gate [N][C] = relu6(fc(mean) + 3) / 6, and the consumers multiply it in (fod_conv2d_nhwc a_gate, fod_maxpool3x3s2_nhwc gate).

@@ -190,3 +190,27 @@ def test_conv2d_nhwc_ese_gate_pieces():
     ref2 = _ref(y_ref * g_ref, w2, None, False)
     out = ops.conv2d_nhwc(y, ops.conv2d_pack(w2.to(DEV)), None, 128, 1, a_gate=gate)
     _check(out, ref2, "gated consumer")
+
+
+def test_conv_groupnorm_relu_conv_without_materialising_the_normalised_map():
+    """CenterNetHead tower: conv -> GroupNorm(32) -> ReLU -> conv; statistics from the first convolution's epilogue,
+    normalisation applied to the second convolution's input operand (zero padding must stay zero)."""
+    n, h, w, c = 3, 20, 28, 128
+    x = synth.tensor((n, c, h, w), 111, -1.0, 1.0)
+    w1 = synth.tensor((c, c, 3, 3), 112, -0.05, 0.05)
+    b1 = synth.tensor((c,), 113, -0.5, 0.5)
+    gamma, beta = synth.tensor((c,), 114, 0.5, 1.5), synth.tensor((c,), 115, -0.5, 0.5)
+    w2 = synth.tensor((8, c, 3, 3), 116, -0.05, 0.05)
+    b2 = synth.tensor((8,), 117, -1.0, 1.0)
+    t_ref = F.conv2d(x.double(), w1.double(), b1.double(), padding=1)
+    g_ref = F.group_norm(t_ref, 32, gamma.double(), beta.double(), 1e-5).relu()
+    y_ref = F.conv2d(g_ref, w2.double(), b2.double(), padding=1).float()
+    tiles = ops.conv2d_tiles_per_image(h, w)
+    cs, cq = torch.zeros((n, tiles, c), device=DEV), torch.zeros((n, tiles, c), device=DEV)
+    a_t = ops.new_amax(DEV)
+    t = ops.conv2d_nhwc(x.to(DEV).contiguous(memory_format=torch.channels_last), ops.conv2d_pack(w1.to(DEV)), b1.to(DEV), c, 3,
+                        y_amax=a_t, colsum=cs, colsumsq=cq)
+    scale, shift, a_g = ops.group_norm_affine(cs, cq, h * w, 32, gamma.to(DEV), beta.to(DEV), 1e-5, x_amax=a_t)
+    y = ops.conv2d_nhwc(t, ops.conv2d_pack(w2.to(DEV)), b2.to(DEV), 8, 3, x_amax=a_g, a_gate=scale, a_shift=shift, a_relu=True)
+    _check(y, y_ref, "conv-GN-ReLU-conv")
+    assert float(a_g) >= float(g_ref.max()) * (1 - 1e-5)
