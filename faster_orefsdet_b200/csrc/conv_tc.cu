@@ -658,19 +658,28 @@ __global__ void absmax_kernel(const float* __restrict__ x, size_t n, float* __re
 }
 
 // eSE gate from the per-tile channel sums of a convolution (vovnet.py eSEModule: x * hsigmoid(fc(avg_pool(x)))):
-// gate[n][o] = relu6(b[o] + sum_i W[o][i] * mean[n][i] + 3) / 6, mean = sum over tiles / hw.  One CTA per image.
+// gate[n][o] = relu6(b[o] + sum_i W[o][i] * mean[n][i] + 3) / 6, mean = sum over tiles / hw.
+// Grid (image, group of kEseOuts outputs): every CTA rebuilds the image's mean vector (a few KB out of L2) and then
+// computes its own outputs, one warp per output - 64 x c/32 CTAs instead of 64, so the fc weights (1 MB at c = 512) are
+// read by 16 CTAs per image in parallel instead of by one.  The summation orders are fixed (tiles w, w+8, ... per warp,
+// then the 8 partials; lanes i, i+32, ... then the shuffle tree): results do not depend on the grid.
+constexpr int kEseOuts = 32;
 __global__ void __launch_bounds__(256) ese_gate_kernel(const float* __restrict__ colsum, int tiles, int c, float inv_hw,
                                                        const float* __restrict__ w, const float* __restrict__ b,
                                                        float* __restrict__ gate) {
-  extern __shared__ float mean[];   // [c] means, then [8][c] partial sums
+  extern __shared__ __align__(16) float mean[];   // [c] means, then [8][c] partial sums
   float* part = mean + c;
   const float* cs = colsum + (size_t)blockIdx.x * tiles * c;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  // warp w sums the tiles t = w, w + 8, ... (coalesced rows of c floats), the 8 partials are added in a fixed order
-  for (int i = lane; i < c; i += 32) {
-    float acc = 0.f;
-    for (int t = warp; t < tiles; t += nw) acc += __ldg(cs + (size_t)t * c + i);
-    part[warp * c + i] = acc;
+  const int c4 = c >> 2;
+  for (int i = lane; i < c4; i += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int t = warp; t < tiles; t += nw) {
+      const float4 v = ldg4(cs + (size_t)t * c + i * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(part + warp * c + i * 4) = acc;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
@@ -679,7 +688,8 @@ __global__ void __launch_bounds__(256) ese_gate_kernel(const float* __restrict__
     mean[i] = acc * inv_hw;
   }
   __syncthreads();
-  for (int o = warp; o < c; o += nw) {
+  const int o1 = min(c, ((int)blockIdx.y + 1) * kEseOuts);
+  for (int o = (int)blockIdx.y * kEseOuts + warp; o < o1; o += nw) {
     float acc = 0.f;
     for (int i = lane; i < c; i += 32) acc = fmaf(__ldg(w + (size_t)o * c + i), mean[i], acc);
 #pragma unroll
@@ -757,8 +767,10 @@ extern "C" int fod_ese_gate(const float* colsum, int n, int tiles_per_img, int c
   FOD_REQUIRE(colsum && fc_weight && fc_bias && gate, "fod_ese_gate: null pointer");
   FOD_REQUIRE(n >= 0 && tiles_per_img > 0 && channels > 0 && channels <= 1024 && hw > 0, "fod_ese_gate: bad sizes");
   if (n == 0) return FOD_OK;
-  cvt::ese_gate_kernel<<<n, 256, 9 * channels * sizeof(float), as_stream(stream)>>>(colsum, tiles_per_img, channels, 1.f / (float)hw,
-                                                                              fc_weight, fc_bias, gate);
+  FOD_REQUIRE(channels % 4 == 0 && ((uintptr_t)colsum & 15) == 0, "fod_ese_gate: channels must be a multiple of 4, colsum 16-byte aligned");
+  const dim3 grid((unsigned)n, (unsigned)((channels + cvt::kEseOuts - 1) / cvt::kEseOuts));
+  cvt::ese_gate_kernel<<<grid, 256, 9 * channels * sizeof(float), as_stream(stream)>>>(colsum, tiles_per_img, channels,
+                                                                                 1.f / (float)hw, fc_weight, fc_bias, gate);
   FOD_CUDA_LAUNCH_CHECK("fod_ese_gate");
   return FOD_OK;
 }

@@ -162,6 +162,185 @@ __global__ void __launch_bounds__(kThreads) stem1_u8_kernel(const uint8_t* __res
   }
 }
 
+// The same layer, tiled (the version fod_stem1_u8 launches).  The kernel above is bound by the shared-memory pipe (128
+// bytes per cycle and SM delivered into registers): every lane re-reads the weights per two pixels and looks its inputs
+// up one by one, ~580 LSU cycles per 1024 outputs against 216 FMA cycles, and its scalar FFMAs run at half of the FP32
+// peak, which Blackwell only reaches with the packed FFMA2.  Here a CTA stages the normalised inputs of an 8 x 32 output
+// tile ONCE (17 input rows x 3 channels), de-interleaved per input row into three 32-float arrays - column 2p-1, 2p and
+// 2p+1 of output pixel p, i.e. the operand of kx = 0, 1, 2 - so that one LDS.128 yields the operands of four adjacent
+// pixels as two aligned register pairs.  A warp owns one output row of the tile, a quarter warp 8 adjacent pixels, a
+// lane 8 output channels {4l..4l+3, 32+4l..32+4l+3} of those pixels: per tap 4 LDS.128 (8 inputs, 8 weights) feed 32
+// FFMA2 (accumulators are pixel pairs of one channel, the weight is duplicated into a register pair), which balances the
+// two pipes, and the 8 lanes of a quarter write 128 contiguous bytes per store.  The summation order (bias, then ky, c,
+// kx) is the order of the kernel above: identical results.
+constexpr int kS1TileY = 8, kS1TileX = 32, kS1Rows = 2 * kS1TileY + 1;
+__global__ void __launch_bounds__(kThreads, 2) stem1_u8_tile_kernel(const uint8_t* __restrict__ x, int H, int W, int Ho, int Wo,
+                                                                    float m0, float m1, float m2, float s0, float s1, float s2,
+                                                                    const float* __restrict__ w /*[64][27] = OIHW*/,
+                                                                    const float* __restrict__ bias, float* __restrict__ y,
+                                                                    float* __restrict__ y_amax, int tiles_x, int tiles_y,
+                                                                    long total_tiles) {
+  __shared__ __align__(16) float vs[kS1Rows][3][3 * kS1TileX];   // [input row][channel][kx][pixel]
+  __shared__ __align__(16) float ws[27][kStemC];
+  __shared__ __align__(16) float bs[kStemC];
+  __shared__ float lut[3][257];
+  for (int i = threadIdx.x; i < 27 * kStemC; i += kThreads) {
+    const int co = i % kStemC, k = i / kStemC;         // k = (ky*3 + kx)*3 + c  <-  OIHW index (c*3 + ky)*3 + kx
+    const int tap = k / 3, c = k - tap * 3;
+    ws[k][co] = w[co * 27 + c * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < kStemC; i += kThreads) bs[i] = bias ? bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 3 * 257; i += kThreads) {
+    const int c = i / 257, v = i - c * 257;
+    lut[c][v] = v == 256 ? 0.f : __fdiv_rn(__fsub_rn((float)v, c == 0 ? m0 : (c == 1 ? m1 : m2)), c == 0 ? s0 : (c == 1 ? s1 : s2));
+  }
+  const int lane = threadIdx.x & 31, wr = threadIdx.x >> 5;
+  const int q = lane >> 3, cl = lane & 7;   // pixels 8q .. 8q+7 of the warp's row; channels 4cl .. +3 and 32 + 4cl .. +3
+  const size_t plane = (size_t)H * W;
+  float vmax = 0.f;
+  // Staging item = (input row r, channel c, group t of four input columns 2*ox0 + 4t .. + 3), t = -1 .. 15 (t = -1 only
+  // supplies column 2*ox0 - 1, the kx = 0 operand of the tile's first pixel): 17 x 3 x 17 = 867 items, <= 4 per thread.
+  // The raw bytes of the NEXT tile are fetched into registers before the current tile is computed (the loads fly during
+  // the FMAs); after the barrier they go through the normalisation table into shared memory.
+  constexpr int kItems = kS1Rows * 3 * 17, kPerThread = (kItems + kThreads - 1) / kThreads;
+  uint32_t raw[kPerThread];
+  uint32_t okmask = 0;   // 4 validity bits per item (a byte outside the image is the zero padding)
+  auto tile_origin = [&](int tile, int& oy0, int& ox0, size_t& n) {
+    const int tx = tile % tiles_x, tr = tile / tiles_x;
+    const int ty = tr % tiles_y;
+    n = (size_t)(tr / tiles_y);
+    oy0 = ty * kS1TileY;
+    ox0 = tx * kS1TileX;
+  };
+  auto fetch = [&](int tile) {
+    int oy0, ox0;
+    size_t n;
+    tile_origin(tile, oy0, ox0, n);
+    const uint8_t* img = x + n * 3 * plane;
+    okmask = 0;
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+      const int idx = (int)threadIdx.x + k * kThreads;
+      raw[k] = 0;
+      if (idx < kItems) {
+        const int t = idx % 17 - 1, rc = idx / 17;
+        const int c = rc % 3, r = rc / 3;
+        const int iy = 2 * oy0 - 1 + r, col0 = 2 * ox0 + 4 * t;
+        if (iy >= 0 && iy < H) {
+          const uint8_t* src = img + c * plane + (size_t)iy * W + col0;
+          if (col0 >= 0 && col0 + 3 < W && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+            raw[k] = __ldg(reinterpret_cast<const uint32_t*>(src));
+            okmask |= 0xFu << (4 * k);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col0 + j >= 0 && col0 + j < W) {
+                raw[k] |= (uint32_t)__ldg(src + j) << (8 * j);
+                okmask |= 1u << (4 * k + j);
+              }
+          }
+        }
+      }
+    }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+      const int idx = (int)threadIdx.x + k * kThreads;
+      if (idx < kItems) {
+        const int t = idx % 17 - 1, rc = idx / 17;
+        const int c = rc % 3, r = rc / 3;
+        float* row = &vs[r][c][0];
+        const float* lc = lut[c];
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = lc[((okmask >> (4 * k + j)) & 1u) ? (int)((raw[k] >> (8 * j)) & 255u) : 256];
+        if (t < 0) {
+          row[0] = v[3];
+        } else {
+          const int p = 2 * t;
+          *reinterpret_cast<float2*>(row + kS1TileX + p) = make_float2(v[0], v[2]);       // kx = 1: columns 2p, 2p + 2
+          *reinterpret_cast<float2*>(row + 2 * kS1TileX + p) = make_float2(v[1], v[3]);   // kx = 2: columns 2p + 1, 2p + 3
+          row[p + 1] = v[1];                                                              // kx = 0 of pixel p + 1
+          if (p + 2 < kS1TileX) row[p + 2] = v[3];                                        // kx = 0 of pixel p + 2
+        }
+      }
+    }
+  };
+  const int total = (int)total_tiles;
+  int tile = (int)blockIdx.x;
+  if (tile < total) fetch(tile);
+  for (; tile < total; tile += (int)gridDim.x) {
+    int oy0, ox0;
+    size_t n;
+    tile_origin(tile, oy0, ox0, n);
+    __syncthreads();   // the previous tile has been consumed (and, the first time, the tables above are written)
+    stage();
+    __syncthreads();
+    if (tile + (int)gridDim.x < total) fetch(tile + (int)gridDim.x);
+    const int oy = oy0 + wr;
+    if (oy >= Ho) continue;   // (uniform per warp; the barriers are at the top of the loop and every warp reaches them)
+    float2 acc[4][8];         // [pixel pair m: pixels 8q + 2m, + 1][channel j]
+    {
+      const float4 b0 = *reinterpret_cast<const float4*>(&bs[4 * cl]), b1 = *reinterpret_cast<const float4*>(&bs[32 + 4 * cl]);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[m][j] = make_float2(bb[j], bb[j]);
+    }
+#pragma unroll 1
+    for (int ky = 0; ky < 3; ++ky) {
+      const int r = 2 * wr + ky;
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int k = (ky * 3 + kx) * 3 + c;
+          const float4 w0 = *reinterpret_cast<const float4*>(&ws[k][4 * cl]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&ws[k][32 + 4 * cl]);
+          const float* arr = &vs[r][c][kx * kS1TileX + 8 * q];
+          const float4 va = *reinterpret_cast<const float4*>(arr), vb = *reinterpret_cast<const float4*>(arr + 4);
+          const float2 vp[4] = {make_float2(va.x, va.y), make_float2(va.z, va.w), make_float2(vb.x, vb.y), make_float2(vb.z, vb.w)};
+          const float wj[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+          // m outer: consecutive FFMA2s share the 64-bit input pair (operand-reuse cache), the weight is the 32-bit
+          // scalar-broadcast operand: fewer register-file reads per instruction
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[m][j] = __ffma2_rn(vp[m], make_float2(wj[j], wj[j]), acc[m][j]);
+        }
+      }
+    }
+    float* out = y + ((n * Ho + oy) * (size_t)Wo + ox0 + 8 * q) * kStemC + 4 * cl;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {   // pixel 8q + 2m + h
+        if (ox0 + 8 * q + 2 * m + h >= Wo) continue;
+        float4 lo, hi;
+        if (h == 0) {
+          lo = make_float4(acc[m][0].x, acc[m][1].x, acc[m][2].x, acc[m][3].x);
+          hi = make_float4(acc[m][4].x, acc[m][5].x, acc[m][6].x, acc[m][7].x);
+        } else {
+          lo = make_float4(acc[m][0].y, acc[m][1].y, acc[m][2].y, acc[m][3].y);
+          hi = make_float4(acc[m][4].y, acc[m][5].y, acc[m][6].y, acc[m][7].y);
+        }
+        lo = make_float4(fmaxf(lo.x, 0.f), fmaxf(lo.y, 0.f), fmaxf(lo.z, 0.f), fmaxf(lo.w, 0.f));
+        hi = make_float4(fmaxf(hi.x, 0.f), fmaxf(hi.y, 0.f), fmaxf(hi.z, 0.f), fmaxf(hi.w, 0.f));
+        vmax = fmaxf(vmax, fmaxf(fmaxf(fmaxf(lo.x, lo.y), fmaxf(lo.z, lo.w)), fmaxf(fmaxf(hi.x, hi.y), fmaxf(hi.z, hi.w))));
+        float* o = out + (size_t)(2 * m + h) * kStemC;
+        *reinterpret_cast<float4*>(o) = lo;
+        *reinterpret_cast<float4*>(o + 32) = hi;
+      }
+    }
+  }
+  if (y_amax) {
+    const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+    if ((threadIdx.x & 31) == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(y_amax), wm);
+  }
+}
+
 // x: [N][H][W] pixels of xs floats (first C used), gate: [N][C] or null -> y: [N][Ho][Wo] pixels of ys floats
 __global__ void __launch_bounds__(kThreads) maxpool_kernel(const float* __restrict__ x, long xs, int H, int W, int C,
                                                            const float* __restrict__ gate, float* __restrict__ y, long ys,
@@ -235,11 +414,16 @@ extern "C" int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* 
   FOD_REQUIRE(((uintptr_t)y & 15) == 0, "fod_stem1_u8: output must be 16-byte aligned");
   if (n == 0) return FOD_OK;
   const int ho = (h - 1) / 2 + 1, wo = (w - 1) / 2 + 1;
-  const int pairs_per_row = (wo + 1) / 2;
-  const size_t total_pairs = (size_t)n * ho * pairs_per_row;
-  glue::stem1_u8_kernel<<<grid_for(total_pairs * 4, glue::kThreads), glue::kThreads, 0, as_stream(stream)>>>(
-      x, h, w, ho, wo, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], weight, bias, y, y_amax, total_pairs,
-      pairs_per_row);
+  const int tiles_x = (wo + glue::kS1TileX - 1) / glue::kS1TileX, tiles_y = (ho + glue::kS1TileY - 1) / glue::kS1TileY;
+  const long total_tiles = (long)n * tiles_x * tiles_y;
+  FOD_REQUIRE(total_tiles < (1L << 31), "fod_stem1_u8: too many tiles");
+  int dev = 0, sms = 0;
+  FOD_CUDA_CALL(cudaGetDevice(&dev));
+  FOD_CUDA_CALL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long resident = 2L * (sms > 0 ? sms : 148);   // two CTAs per SM (__launch_bounds__), each loops over tiles
+  glue::stem1_u8_tile_kernel<<<(unsigned)(total_tiles < resident ? total_tiles : resident), glue::kThreads, 0, as_stream(stream)>>>(
+      x, h, w, ho, wo, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], weight, bias, y, y_amax, tiles_x, tiles_y,
+      total_tiles);
   FOD_CUDA_LAUNCH_CHECK("fod_stem1_u8");
   return FOD_OK;
 }
