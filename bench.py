@@ -57,6 +57,12 @@ def _cfg(device):
     return cfg
 
 
+def _workload(batch):
+    """The workload both arms are measured on (BASELINE.json configs[1])."""
+    return (f"finetune_vovnet.yaml 1-way {SHOTS}-shot inference, batch {batch} synthetic 640x640 ore queries per GPU "
+            f"(BASELINE.json configs[1])")
+
+
 def _images(batch, seed0, n_distinct=8):
     base = [synth.ore_image(IMG, IMG, seed0 + i) for i in range(n_distinct)]
     out = []
@@ -149,8 +155,10 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "finetune_vovnet.yaml 1-way 25-shot, 640x640 synthetic ore queries, batch-1 loop on host cores",
-                   "sample": f"{per_step} images per step"},
+        "config": {"workload": _workload(BATCH), "batch_per_gpu": BATCH, "ways": 1, "shots": SHOTS,
+                   "execution": "reference CPU path (MODEL.DEVICE=cpu semantics): batch-1 loop on the host cores, oracle head + "
+                                "PyTorch-CPU VoVNet/FPN",
+                   "sample": f"{per_step} images of the workload per step"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{per_step * args.steps} images 640x640, batch-1 loop, oracle head + PyTorch-CPU VoVNet/FPN"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -373,9 +381,9 @@ def run_gpu_arm(args):
         "metric": METRIC, "value": total_images / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"finetune_vovnet.yaml 1-way {SHOTS}-shot inference, batch {B} synthetic 640x640 ore queries "
-                               f"per GPU (BASELINE.json configs[1]), VoVNet-19-slim-eSE+FPN + CenterNetHead convolutions on tcgen05 "
-                               f"(fp16-split operands, 3 MMAs per product = fp32 accuracy) + CUDA head", "batch_per_gpu": B, "ways": 1, "shots": SHOTS,
+        "config": {"workload": _workload(B), "batch_per_gpu": B, "ways": 1, "shots": SHOTS,
+                   "implementation": "VoVNet-19-slim-eSE+FPN + CenterNetHead convolutions on tcgen05 (fp16-split operands, 3 MMAs "
+                                     "per product = fp32 accuracy) + CUDA head",
                    "l2": f"inputs rotate over {NSETS} distinct batches ({NSETS * B * 3 * IMG * IMG / 1e6:.0f} MB) and the "
                          f"backbone activations (> 1 GB per step) exceed the 126 MB L2",
                    "execution": ("stem eager, everything behind it one CUDA-graph replay per step" if graph_mode else "eager") +

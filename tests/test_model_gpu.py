@@ -123,6 +123,39 @@ def test_nway_batched_head_matches_oracle():
         assert matched / rb.shape[0] >= 0.97
 
 
+def test_highres_topk2000_head_matches_oracle():
+    """BASELINE.json configs[3]: 1333x800 queries (padded 800x1344, M = 22 050), PRE/POST_NMS_TOPK_TEST 2000, two
+    classes: top-k is exercised on all three levels, <= 6000 candidates per problem enter the NMS, <= 2000 ROIs per
+    problem the relation head, and the class-wise final NMS sees both classes."""
+    sd = head_state_dict()
+    model = _model("MODEL.CENTERNET.PRE_NMS_TOPK_TEST", 2000, "MODEL.CENTERNET.POST_NMS_TOPK_TEST", 2000)
+    cfg = O.HeadConfig(pre_nms_topk=2000, post_nms_topk=2000)
+    class_ids = [3, 8]
+    protos = synth.prototypes(class_ids, 5, 17)
+    model.set_prototypes(protos)
+    H, W = 800, 1344
+    feats = synth.features(1, H, W, 123)
+    (ob, os_, ocls, oc), tr = model.head({k: v.cuda() for k, v in feats.items()}, [(H, W)], [(H, W)], want_trace=True)
+    otr = {}
+    rb, rs, rc = O.detect_image(feats, protos, sd, (H, W), cfg, None, otr)
+    # proposals per class: same count (+- ties at the post-NMS threshold) and the same boxes / objectness
+    for c in range(2):
+        pc = otr["per_class"][c]
+        n = int(tr["proposals"].count[c])
+        assert pc["cand_boxes"].shape[0] > 4000            # every level contributed its top-k
+        assert abs(n - pc["proposals"].shape[0]) <= 2
+        assert _match(pc["proposals"], pc["objectness"], tr["proposals"].boxes[c, :n].cpu(), tr["proposals"].scores[c, :n].cpu()) >= 0.98
+    m = int(oc[0])
+    assert abs(m - rb.shape[0]) <= 2
+    gb, gs, gc = ob[0, :m].cpu(), os_[0, :m].cpu(), ocls[0, :m].cpu()
+    matched = 0.0
+    for c in range(2):
+        if int((rc == c).sum()) == 0:
+            continue
+        matched += _match(rb[rc == c], rs[rc == c], gb[gc == c], gs[gc == c]) * int((rc == c).sum())
+    assert matched / max(rb.shape[0], 1) >= 0.97
+
+
 def test_batched_call_equals_separate_calls():
     model = _model()
     model.set_prototypes(synth.prototypes([1], 5, 7))
