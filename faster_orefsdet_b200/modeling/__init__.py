@@ -3,7 +3,7 @@
 from ..compat import BACKBONE_REGISTRY, META_ARCH_REGISTRY, PROPOSAL_GENERATOR_REGISTRY
 from .backbone import build_backbone, build_fcos_vovnet_fpn_backbone
 from .centernet import CenterNet, CenterNetHead
-from .fsod_cen import CenterNet2Detector
+from .fsod_cen import CenterNet2Detector, PendingBatch
 from .fsod_rcnn import FsodRCNN
 from .prototypes import PrototypeBank, SM_Block
 from .roi_heads import ROI_HEADS_REGISTRY, CustomCascadeROIHeads, build_roi_heads

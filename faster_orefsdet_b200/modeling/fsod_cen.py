@@ -32,10 +32,25 @@ from .backbone import build_backbone
 from .centernet import CenterNet, RawProposals  # noqa: F401  (registers "CenterNet")
 from .prototypes import (LEVELS, PrototypeBank, SM_Block, SupportCache, bank_from_support_dict, broadcast_bank, load_bank,
                          save_bank)
-from .roi_heads import build_roi_heads, pack_instances
+from .roi_heads import build_roi_heads, instances_from_block, pack_block, pack_instances
 from ..compat import PROPOSAL_GENERATOR_REGISTRY
 
 __all__ = ["CenterNet2Detector"]
+
+
+class PendingBatch:
+    """A query batch that ``CenterNet2Detector.submit`` has put on the device: its host-to-device copies, the stem, the
+    graph replay and the device-to-host copy of the padded detections are all enqueued; ``model(pending)`` (or
+    ``collect``) waits for the one event and builds the ``Instances``.  Equivalent to calling ``model(inputs)``."""
+
+    __slots__ = ("inputs", "x_u8", "image_sizes", "out_sizes", "block", "host", "status_host", "done")
+
+    def __init__(self, inputs, x_u8, image_sizes, out_sizes, block, host, status_host, done):
+        self.inputs, self.x_u8, self.image_sizes, self.out_sizes = inputs, x_u8, image_sizes, out_sizes
+        self.block, self.host, self.status_host, self.done = block, host, status_host, done
+
+    def __len__(self):
+        return len(self.inputs)
 
 
 def build_proposal_generator(cfg, input_shape):
@@ -86,7 +101,56 @@ class CenterNet2Detector(nn.Module):
         return self.pixel_mean.device
 
     # ------------------------------------------------------------------ forward
-    def forward(self, batched_inputs: List[dict]):
+    def submit(self, batched_inputs: List[dict], do_postprocess: bool = True):
+        """Asynchronous half of ``forward`` (the role of the reference's DataLoader prefetch + ``.to(device)``,
+        fsod_cen.py:540-555, and of its evaluator's per-image ``.to(cpu)``, fewx/evaluation/coco_evaluation.py:119-126):
+        enqueue everything a batch needs - chunked host-to-device copies on the copy stream, the stem behind them, the
+        graph replay, one device-to-host copy of the padded detections and of the status word - and return at once.
+        A serving loop submits batch k+1 before it collects batch k (``model(pending_k)``), so the PCIe transfers and the
+        host-side construction of the ``Instances`` ride under the kernels of the neighbouring batches.  Returns a
+        ``PendingBatch``, or ``batched_inputs`` itself when the uint8 fast path or the CUDA graph does not apply (then
+        nothing is enqueued and ``model(...)`` runs the batch synchronously)."""
+        if self.training or not self.USE_CUDA_GRAPH:
+            return batched_inputs
+        self.init_model()
+        if self._bank is None:
+            raise _lib.FodError("no support prototypes installed: call init_model() / set_prototypes() first")
+        staged = self._stage_uint8(batched_inputs)
+        if staged is None:
+            return batched_inputs
+        x_u8, events, chunk = staged
+        n, _, h, w = x_u8.shape
+        image_sizes = [(int(h), int(w))] * n
+        out_sizes = [(int(inp.get("height", h)), int(inp.get("width", w))) if do_postprocess else (int(h), int(w))
+                     for inp in batched_inputs]
+        g = self._graph_for(n, h, w)
+        self._stem_from_uint8(x_u8, events, chunk, into=(g["buf"], g["first"], g["amax"]))
+        self._graph_launch(g, image_sizes, out_sizes)
+        (ob, os_, ocls, orow, oc), per_roi, props, attn, status = g["res"]
+        block = pack_block(ob, os_, ocls, oc)        # a fresh tensor per batch: the graph's buffers belong to the next replay
+        host = torch.empty(block.shape, dtype=torch.float32, pin_memory=True)
+        status_host = torch.empty((1,), dtype=status.dtype, pin_memory=True)
+        host.copy_(block, non_blocking=True)
+        status_host.copy_(status.view(-1)[:1], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        return PendingBatch(batched_inputs, x_u8, image_sizes, out_sizes, block, host, status_host, done)
+
+    def collect(self, pending: "PendingBatch", do_postprocess: bool = True):
+        """Wait for a submitted batch and build its results (what ``forward`` returns)."""
+        pending.done.synchronize()
+        st = int(pending.status_host[0]) & 0xFFFFFFFF
+        if st:
+            # ties above the reserved proposal slack (or an error): redo this batch eagerly with fresh buffers, stream
+            # ordered behind whatever has been submitted since
+            ob, os_, ocls, oc = self.head(self.features_from_uint8(pending.x_u8), pending.image_sizes, pending.out_sizes)
+            results = pack_instances(ob, os_, ocls, oc, pending.out_sizes)
+        else:
+            results = instances_from_block(pending.block, pending.host, pending.out_sizes)
+        return [{"instances": r} for r in results] if do_postprocess else results
+
+    def forward(self, batched_inputs):
+        """``batched_inputs``: list[dict] like the reference (fsod_cen.py:417), or a ``PendingBatch`` from ``submit``."""
         if not self.training:
             self.init_model()
             return self.inference(batched_inputs)
@@ -183,6 +247,8 @@ class CenterNet2Detector(nn.Module):
         assert not self.training
         if self._bank is None:
             raise _lib.FodError("no support prototypes installed: call init_model() / set_prototypes() first")
+        if isinstance(batched_inputs, PendingBatch):
+            return self.collect(batched_inputs, do_postprocess)
         staged = self._stage_uint8(batched_inputs)
         if staged is not None:
             x_u8, events, chunk = staged
@@ -202,6 +268,7 @@ class CenterNet2Detector(nn.Module):
 
     # ------------------------------------------------------------------ input staging
     PIPELINE_CHUNK = 16      # images per host-to-device chunk
+    U8_RING = 3              # device input buffers per batch shape (batches in flight + 1)
 
     def features_from_uint8(self, x_u8: torch.Tensor, events=None, chunk: int = 0) -> Dict[str, torch.Tensor]:
         """Raw uint8 image batch [N,3,H,W] already on the device (H, W multiples of the backbone's size divisibility)
@@ -226,6 +293,11 @@ class CenterNet2Detector(nn.Module):
             if events is not None:
                 main.wait_event(events[k])
             vov.tc_stem_u8(x_u8[c0:c1], mean, std, first[c0:c1], amax[0:1])
+        last = getattr(self, "_u8_last", None)
+        if last is not None and last[2] is x_u8:     # the ring slot may be refilled once this stem has read it
+            ev = torch.cuda.Event()
+            ev.record(main)
+            last[0]["consumed"][last[1]] = ev
         return buf, amax
 
     def detect_from_uint8(self, x_u8: torch.Tensor, image_sizes, out_sizes, events=None, chunk: int = 0):
@@ -269,11 +341,26 @@ class CenterNet2Detector(nn.Module):
             return None
         n, (c, h, w) = len(imgs), imgs[0].shape
         main = torch.cuda.current_stream(self.device)
-        x_u8 = torch.empty((n, c, h, w), dtype=torch.uint8, device=self.device)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         side = self._copy_stream
-        side.wait_stream(main)                 # x_u8 was allocated on the main stream
+        # The device batch comes from a ring of U8_RING persistent buffers per batch shape: the copy stream must not wait
+        # for the main stream as a whole (a submitted batch may still be running there), only for the stem that last
+        # read this slot (event recorded by _stem_from_uint8).
+        rings = self.__dict__.setdefault("_u8_rings", {})
+        ring = rings.get((n, c, h, w))
+        if ring is None:
+            ring = {"bufs": [torch.empty((n, c, h, w), dtype=torch.uint8, device=self.device) for _ in range(self.U8_RING)],
+                    "consumed": [None] * self.U8_RING, "next": 0}
+            rings.clear()                      # one batch shape at a time
+            rings[(n, c, h, w)] = ring
+            side.wait_stream(main)             # the buffers were allocated on the main stream
+        j = ring["next"]
+        ring["next"] = (j + 1) % self.U8_RING
+        x_u8 = ring["bufs"][j]
+        if ring["consumed"][j] is not None:
+            side.wait_event(ring["consumed"][j])
+        self._u8_last = (ring, j, x_u8)
         events, chunk = [], self.PIPELINE_CHUNK
         with torch.cuda.stream(side):
             for c0 in range(0, n, chunk):
@@ -354,8 +441,7 @@ class CenterNet2Detector(nn.Module):
         vov = self.backbone.bottom_up
         buf, first, amax = vov.tc_new_input_buffer(n, h, w, dev)
         g = {"key": key, "buf": buf, "first": first, "amax": amax,
-             "image_hw": torch.zeros((n, 2), dtype=torch.int32, device=dev), "out_hw": torch.zeros((n, 2), dtype=torch.int32, device=dev),
-             "sizes_host": torch.zeros((2, n, 2), dtype=torch.int32).pin_memory()}
+             "image_hw": torch.zeros((n, 2), dtype=torch.int32, device=dev), "out_hw": torch.zeros((n, 2), dtype=torch.int32, device=dev)}
         g["image_hw"][:] = torch.tensor([h, w], dtype=torch.int32, device=dev)
         g["out_hw"][:] = g["image_hw"]
         first.zero_()
@@ -379,13 +465,15 @@ class CenterNet2Detector(nn.Module):
         self._graph = g
         return g
 
-    def _graph_replay(self, g, image_sizes, out_sizes, want_trace: bool = False):
-        sh = g["sizes_host"]
-        sh[0] = torch.tensor([list(s) for s in image_sizes], dtype=torch.int32)
-        sh[1] = torch.tensor([list(s) for s in out_sizes], dtype=torch.int32)
+    def _graph_launch(self, g, image_sizes, out_sizes):
+        # a fresh pinned block per launch: an earlier submitted batch may not have read its sizes yet
+        sh = torch.tensor([[list(s) for s in image_sizes], [list(s) for s in out_sizes]], dtype=torch.int32).pin_memory()
         g["image_hw"].copy_(sh[0], non_blocking=True)
         g["out_hw"].copy_(sh[1], non_blocking=True)
         g["graph"].replay()
+
+    def _graph_replay(self, g, image_sizes, out_sizes, want_trace: bool = False):
+        self._graph_launch(g, image_sizes, out_sizes)
         return self._head_finish(g["res"], g["feats"], g["image_hw"], g["out_hw"], want_trace)
 
     def preprocess_image(self, batched_inputs: List[dict]) -> ImageList:

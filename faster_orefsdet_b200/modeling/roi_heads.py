@@ -159,25 +159,37 @@ class CustomCascadeROIHeads(nn.Module):
 LAST_D2H_BYTES = 0     # size of the last detections transfer (bench.py reports it)
 
 
+def pack_block(boxes, scores, classes, count) -> torch.Tensor:
+    """Padded device outputs -> one [B, K, 7] fp32 block (box, score, class, count) that leaves in ONE transfer."""
+    B, K = scores.shape
+    return torch.cat((boxes, scores.unsqueeze(-1), classes.to(torch.float32).unsqueeze(-1),
+                      count.to(torch.float32).view(B, 1, 1).expand(B, K, 1)), -1)
+
+
 def pack_instances(boxes, scores, classes, count, image_sizes) -> List[Instances]:
     """Padded device outputs -> list[Instances] on the device, with ONE device-to-host transfer of the whole
     padded block ([B, K, 7] fp32) whose views ride along as the host mirror of every Instances
     (compat Instances.to("cpu") returns them; the reference's evaluator copies field by field, image by image:
     fewx/evaluation/coco_evaluation.py:119-126).  The valid rows are compacted once and split per image with
     split_with_sizes, so the per-image Python cost is the construction of the containers only."""
-    B, K = scores.shape
-    block = torch.cat((boxes, scores.unsqueeze(-1), classes.to(torch.float32).unsqueeze(-1),
-                       count.to(torch.float32).view(B, 1, 1).expand(B, K, 1)), -1)
+    block = pack_block(boxes, scores, classes, count)
     host = torch.empty(block.shape, dtype=torch.float32, pin_memory=True)
     host.copy_(block, non_blocking=True)
     torch.cuda.current_stream(scores.device).synchronize()
+    return instances_from_block(block, host, image_sizes)
+
+
+def instances_from_block(block: torch.Tensor, host: torch.Tensor, image_sizes) -> List[Instances]:
+    """``block``: the device block of pack_block, ``host``: its (completed) pinned host copy."""
+    B, K = host.shape[0], host.shape[1]
     global LAST_D2H_BYTES
     LAST_D2H_BYTES = host.numel() * 4
     counts_t = host[:, 0, 6].to(torch.int64)
     counts = counts_t.tolist()
     idx = torch.nonzero((torch.arange(K)[None, :] < counts_t[:, None]).flatten()).squeeze(1)
     flat_h = host.view(B * K, 7).index_select(0, idx)
-    flat_d = block.view(B * K, 7).index_select(0, idx.to(scores.device, non_blocking=True))
+    # (pinned: the copy of the index list must not wait for whatever the stream is running - a later batch, say)
+    flat_d = block.view(B * K, 7).index_select(0, idx.pin_memory().to(block.device, non_blocking=True))
     parts = []
     for flat in (flat_d, flat_h):
         parts.append((torch.split(flat[:, :4], counts), torch.split(flat[:, 4], counts),

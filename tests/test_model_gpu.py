@@ -291,6 +291,49 @@ def test_pipelined_uint8_input_path_equals_generic_path():
     assert model._features_pipelined([{"image": synth.ore_image(100, 160, 1)}])[0] is None
 
 
+def test_submitted_batches_equal_plain_calls():
+    """model.submit(next) before model(pending current): a batch enqueued behind the one in flight must not disturb it,
+    and a PendingBatch must give the detections of the plain call bit for bit (host mirror and device fields)."""
+    model = _model()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    model.set_prototypes(synth.prototypes([1], 5, 7))
+    model.PIPELINE_CHUNK = 2
+    batches = [[{"image": synth.ore_image(128, 160, 4000 + 10 * b + i).pin_memory(), "height": 100 + b, "width": 150} for i in range(3)]
+               for b in range(3)]
+    plain = [model(b) for b in batches]
+    nxt = model.submit(batches[0])
+    staged = []
+    for k in range(3):
+        cur = nxt
+        if k + 1 < 3:
+            nxt = model.submit(batches[k + 1])
+        assert type(cur).__name__ == "PendingBatch" and len(cur) == 3
+        staged.append(model(cur))
+    for rp, rs in zip(plain, staged):
+        for a, b in zip(rp, rs):
+            ia, ib = a["instances"], b["instances"]
+            assert ia.image_size == ib.image_size
+            assert torch.equal(ia.pred_boxes.tensor, ib.pred_boxes.tensor) and torch.equal(ia.scores, ib.scores)
+            assert torch.equal(ia.pred_classes, ib.pred_classes)
+            ha, hb = ia.to("cpu"), ib.to("cpu")
+            assert torch.equal(ha.pred_boxes.tensor, hb.pred_boxes.tensor) and torch.equal(ha.scores, ib.scores.cpu())
+    # inputs outside the uint8 fast path come back unchanged (nothing to prefetch) and still run
+    odd = [{"image": synth.ore_image(100, 160, 1)}]
+    assert model.submit(odd) is odd
+    assert len(model(model.submit(odd))) == 1
+    # up to three batches in flight through the ring of three input buffers
+    pend = [model.submit(batches[k % 3]) for k in range(2)]
+    outs = []
+    for k in range(2, 6):
+        pend.append(model.submit(batches[k % 3]))
+        outs.append(model(pend.pop(0)))
+    outs += [model(p) for p in pend]
+    for k, r in enumerate(outs):
+        for a, b in zip(plain[k % 3], r):
+            assert torch.equal(a["instances"].scores, b["instances"].scores)
+
+
 def test_cuda_graph_replay_equals_eager_launches():
     """detect_from_uint8: stem eager + one graph replay must equal the eager path bit for bit, also when the requested
     output sizes change between replays and when the batch content changes."""
