@@ -171,6 +171,48 @@ def test_batched_call_equals_separate_calls():
         assert_close(ss[0, :m], os_[b, :m], rtol=1e-5, atol=1e-6, what="scores")
 
 
+def test_full_size_batch64_properties():
+    """BASELINE.json configs[1] at its full size (batch 64 x 640x640, 1-way 25-shot) through the whole detector, checked
+    by size-independent properties: per-image results do not depend on the batch they ran in (sampled images re-run
+    alone from the same features), detections are sorted by score, at most DETECTIONS_PER_IMAGE of them, inside the
+    image, no surviving pair overlaps above NMS_THRESH_TEST, and the final NMS is idempotent on its own output."""
+    from torchvision.ops import box_iou
+    model = _model()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    model.set_prototypes(synth.prototypes([1], 25, 7))
+    B, H, W = 64, 640, 640
+    base = [synth.ore_image(H, W, 1000 + i) for i in range(8)]
+    imgs = torch.stack([torch.roll(base[i % 8], shifts=(7 * (i // 8), 13 * (i // 8)), dims=(1, 2)) for i in range(B)]).cuda()
+    with torch.no_grad():
+        feats = model.features_from_uint8(imgs)
+        ob, os_, ocls, oc = model.head(feats, [(H, W)] * B, [(H, W)] * B)
+        status = ops.new_status("cuda")
+        total = 0
+        for b in range(B):
+            m = int(oc[b])
+            total += m
+            assert 0 < m <= 100
+            bx, sc = ob[b, :m], os_[b, :m]
+            assert torch.all(sc[:-1] >= sc[1:]) and torch.all(ocls[b, :m] == 0)
+            assert float(bx[:, 0::2].min()) >= 0 and float(bx[:, 0::2].max()) <= W and float(bx[:, 1::2].min()) >= 0 and float(bx[:, 1::2].max()) <= H
+            iou = box_iou(bx, bx).triu(1)
+            assert float(iou.max()) <= CFG.nms_thresh_test + 1e-5
+            if b % 16 == 0:      # idempotence: the same NMS over its own output keeps every box, in the same order
+                keep = ops.batched_nms(bx.contiguous(), sc.contiguous(), torch.zeros(m, dtype=torch.int64, device="cuda"),
+                                       CFG.nms_thresh_test)
+                assert keep.tolist() == list(range(m))
+        assert total > B          # the synthetic scene produces detections everywhere
+        for b in (0, 37, 63):     # the same image alone, from the same features: same detections
+            fb = {k: v[b:b + 1].contiguous(memory_format=torch.channels_last) for k, v in feats.items()}
+            sb, ss, _, scount = model.head(fb, [(H, W)], [(H, W)])
+            m = int(oc[b])
+            assert int(scount[0]) == m
+            assert_close(sb[0, :m], ob[b, :m], rtol=1e-5, atol=1e-3, what="boxes")
+            assert_close(ss[0, :m], os_[b, :m], rtol=1e-5, atol=1e-6, what="scores")
+    ops.check_status(status)
+
+
 def test_full_detector_forward_with_pkl_side_channel(tmp_path, monkeypatch):
     """model(batched_inputs) through the real backbone, prototypes from ./support_dir/support_feature.pkl."""
     monkeypatch.chdir(tmp_path)
