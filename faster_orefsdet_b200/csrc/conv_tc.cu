@@ -77,6 +77,7 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAStageCols = 32;                // [hi: 16 columns of packed fp16 pairs | lo: 16]
 constexpr uint32_t kColA = 0;                       // 6 stages x 32
 constexpr uint32_t kColAcc = kStages * kAStageCols; // 2 stages x 128
+constexpr uint32_t kColRun = kColAcc + kAccStages * 128;  // 64 columns: running partial sums of layers with <= 64 output channels
 
 // 2^e with amax * 2^e in [2^13, 2^14) (and its inverse); 1 for zero / denormal-range / non-finite bounds
 __device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
@@ -135,6 +136,7 @@ struct Params {
   int cin_chunks, chunks, parts, chunks_per_part;
   int n_groups, n_group, nhalf, ncol32, cout;
   int relu, num_pairs, pair_units, n_amax, ho, wo, cin;
+  int run_tmem;   // running partial sums live in tensor memory (n_group <= 64, more than one part) instead of shared memory
   uint32_t q_stage_bytes, q_stage_stride;
 };
 
@@ -386,6 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(acc_full(as_), aph);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + col_acc + as_ * acc_w;
+        const uint32_t trun = tmem_base + ((uint32_t)(qd * 32) << 16) + kColRun;
         const int part_chunks = min(P.chunks_per_part, P.chunks - part * P.chunks_per_part);
         const float comp = 1.f + P.rz_kappa * 0.5f * (float)(part_chunks * mma_per_chunk);
 #pragma unroll 1
@@ -398,13 +401,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * as_);
           }
+          if (P.run_tmem) {
+            // Narrow layers: the running sum of the parts stays in 64 spare columns of tensor memory (this warp's own
+            // lanes) - no shared-memory read-modify-write per part; the IEEE fp32 additions are the same as below.
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * comp);
+            if (part > 0) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t r[16];
+                tmem_ld16(trun + j * 32 + hh * 16, r);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[hh * 16 + i] = __float_as_uint(__uint_as_float(v[hh * 16 + i]) + __uint_as_float(r[i]));
+              }
+            }
+            if (part < parts - 1) {
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                uint32_t w16[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w16[i] = v[hh * 16 + i];
+                tmem_st16(trun + j * 32 + hh * 16, w16);
+              }
+              if (j == ncol32 - 1) tmem_wait_st();   // visible to this thread's loads of the next part
+              continue;
+            }
+          }
           const uint32_t slab = row_s + (uint32_t)j * kSlabBytes;
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const uint32_t sa = slab + (uint32_t)((c4 ^ (m & 7)) << 4);
-            float4 x = make_float4(__uint_as_float(v[c4 * 4 + 0]) * comp, __uint_as_float(v[c4 * 4 + 1]) * comp,
-                                   __uint_as_float(v[c4 * 4 + 2]) * comp, __uint_as_float(v[c4 * 4 + 3]) * comp);
-            if (part > 0) {
+            float4 x;
+            if (P.run_tmem)   // already scaled and added to the running sum above
+              x = make_float4(__uint_as_float(v[c4 * 4 + 0]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]),
+                              __uint_as_float(v[c4 * 4 + 3]));
+            else
+              x = make_float4(__uint_as_float(v[c4 * 4 + 0]) * comp, __uint_as_float(v[c4 * 4 + 1]) * comp,
+                              __uint_as_float(v[c4 * 4 + 2]) * comp, __uint_as_float(v[c4 * 4 + 3]) * comp);
+            if (part > 0 && !P.run_tmem) {
               const float4 r = lds4s(sa);
               x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
             }
@@ -856,6 +891,8 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.nhalf = prm.n_group / 2;
   prm.ncol32 = (prm.n_group + 31) / 32;
   prm.cout = cout;
+  prm.run_tmem = (prm.n_group <= 64 && prm.parts > 1) ? 1 : 0;
+  if (const char* e = getenv("FOD_CONV_RUN_TMEM")) prm.run_tmem = prm.run_tmem && atoi(e) != 0;   // development knob (A/B)
   prm.relu = relu;
   prm.bias = bias;
   prm.x_amax = x_amax;
