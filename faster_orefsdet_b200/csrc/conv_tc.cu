@@ -32,8 +32,8 @@
 //   * weights: pre-split fp16 hi / lo planes [Cout][taps][Cin_pad] (fod_conv2d_pack_weights), TMA-streamed per chunk
 //     into a 6-stage ring (they are L2 resident: <= 0.6 MB per layer).
 //   * the tensor core accumulates with round-toward-zero (tools/tc_probe.cu), so the K loop is cut into partial sums
-//     of <= 16 chunks (96 MMAs) that the 4 epilogue warps add in IEEE fp32 into a running tile in shared memory; the
-//     last part rescales, adds the bias, applies ReLU and the tile leaves through TMA stores (clipped at the image
+//     of <= 16 chunks (96 MMAs) that the 4 epilogue warps add in IEEE fp32 into a running tile - in 64 spare columns of
+//     tensor memory for layers with <= 64 output channels, in shared memory otherwise; the last part rescales, adds the bias, applies ReLU and the tile leaves through TMA stores (clipped at the image
 //     border and at Cout by the tensor map, so the output may be a channel slice of a wider NHWC buffer: concatenation
 //     is free).
 #include <cuda_fp16.h>

@@ -252,7 +252,8 @@ int fod_group_norm_affine(const float* colsum, const float* colsumsq, int maps, 
 /* eSE attention of the OSA stages (d2!/modeling/backbone/vovnet.py eSEModule: x * hsigmoid(fc(avg_pool(x)))) without a
  * pass over x: the convolution that produces x writes per-tile channel sums (colsum), fod_ese_gate turns them into
  * gate [N][C] = relu6(fc(mean) + 3) / 6, and the consumers multiply it in (fod_conv2d_nhwc a_gate, fod_maxpool3x3s2_nhwc gate).
- *   colsum : [N][fod_conv2d_tiles_per_image(Ho, Wo)][C]   fc_weight [C][C], fc_bias [C]   hw = Ho * Wo */
+ *   colsum : [N][fod_conv2d_tiles_per_image(Ho, Wo)][C]   fc_weight [C][C], fc_bias [C]   hw = Ho * Wo
+ *   C a multiple of 4 (<= 1024), colsum 16-byte aligned; the summation order is fixed, gates do not depend on the grid */
 int fod_conv2d_tiles_per_image(int ho, int wo);
 int fod_ese_gate(const float* colsum, int n, int tiles_per_img, int channels, long hw, const float* fc_weight,
                  const float* fc_bias, float* gate, fod_stream_t stream);
