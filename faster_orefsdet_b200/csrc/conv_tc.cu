@@ -50,7 +50,7 @@ namespace cvt {
 
 constexpr int kTileH = 8, kTileW = 16;
 constexpr int kChunk = 32;
-constexpr int kQStages = 3, kStages = 6, kAccStages = 2;
+constexpr int kQStages = 3, kQStagesMax = 4, kStages = 6, kAccStages = 2;   // input ring: 3 halo tiles, or 4 tiles of 8 x 16 pixels (1x1 / stride 2)
 constexpr int kPartChunks = 16;
 constexpr float kRzKappa = 0.f;  // a scalar compensation of the truncation bias (8.8e-8 per MMA for same-sign sums, tools/rz_calib.py) over-corrects real, mixed-sign layers: off
 constexpr uint32_t kQStageStrideS1 = ((kTileH + 2) * (kTileW + 2) * 128 + 1023) / 1024 * 1024;   // 23552
@@ -63,7 +63,7 @@ constexpr uint32_t kOffB = kOffQ + kQStages * kQStageStrideS1;              // 7
 constexpr uint32_t kOffSum = kOffB + kStages * kBStageBytes;                // running tile / store staging, 4 slabs
 constexpr uint32_t kOffBias = kOffSum + 4 * kSlabBytes;
 constexpr uint32_t kOffBars = kOffBias + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kQStages + 3 * kStages + 2 * kAccStages;
+constexpr uint32_t kNumBars = 2 * kQStagesMax + 3 * kStages + 2 * kAccStages;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr uint32_t kOffFlag = kOffTmemPtr + 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
@@ -138,6 +138,7 @@ struct Params {
   int relu, num_pairs, pair_units, n_amax, ho, wo, cin;
   int run_tmem;   // running partial sums live in tensor memory (n_group <= 64, more than one part) instead of shared memory
   uint32_t q_stage_bytes, q_stage_stride;
+  int q_stages;   // depth of the input ring: as many tiles as fit (3 halo tiles, 4 single-tap tiles)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ Params P) {
@@ -153,12 +154,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #endif
   const uint32_t bar0 = sbase + kOffBars;
   auto q_full = [&](int s) { return bar0 + 8u * s; };                                  // TMA -> converters
-  auto q_empty = [&](int s) { return bar0 + 8u * (kQStages + s); };                    // converters -> TMA
-  auto b_full = [&](int s) { return bar0 + 8u * (2 * kQStages + s); };                 // TMA of both CTAs -> MMA (leader)
-  auto ready = [&](int s) { return bar0 + 8u * (2 * kQStages + kStages + s); };        // converters + weight bytes -> MMA
-  auto st_free = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kStages + s); };  // MMA commit -> A + B stage free
-  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + s); };
-  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + kAccStages + s); };
+  auto q_empty = [&](int s) { return bar0 + 8u * (kQStagesMax + s); };                 // converters -> TMA
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + s); };                 // TMA of both CTAs -> MMA (leader)
+  auto ready = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + kStages + s); };        // converters + weight bytes -> MMA
+  auto st_free = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + 2 * kStages + s); };  // MMA commit -> A + B stage free
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + 3 * kStages + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + 3 * kStages + kAccStages + s); };
   constexpr int stages = kStages;
   constexpr uint32_t acc_w = 128u, col_acc = kColAcc, b_stage = kBStageBytes;
   float xs = 1.f, xs_inv = 1.f;   // input scale 2^e (converters) and its inverse (epilogue)
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 
   if (tid == 0) {
-    for (int s = 0; s < kQStages; ++s) {
+    for (int s = 0; s < kQStagesMax; ++s) {
       mbar_init(q_full(s), 1);
       mbar_init(q_empty(s), kConvWarps);
     }
@@ -220,8 +221,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int loads = P.per_tap ? taps : 1;
         for (int cc = 0; cc < cin_chunks; ++cc)
           for (int tap = 0; tap < loads; ++tap, ++g) {
-            const int s = g % kQStages;
-            const uint32_t ph = (g / kQStages) & 1;
+            const int s = (int)(g % (uint32_t)P.q_stages);
+            const uint32_t ph = (g / (uint32_t)P.q_stages) & 1;
             const int dy = tap / P.ksize, dx = tap - dy * P.ksize;   // (0, 0) when the halo tile serves every tap
             mbar_wait(q_empty(s), ph ^ 1);
             mbar_arrive_expect_tx(q_full(s), P.q_stage_bytes);
@@ -600,18 +601,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int cc = 0; cc < cin_chunks; ++cc) {
         if (P.a_gate) gate_row = P.a_gate + (size_t)unit_n * P.cin + cc * kChunk;
         if (P.a_shift) shift_row = P.a_shift + (size_t)unit_n * P.cin + cc * kChunk;
-        int qs = gq % kQStages;
+        int qs = (int)(gq % (uint32_t)P.q_stages);
         uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
         if (!per_tap) {
-          mbar_wait(q_full(qs), (gq / kQStages) & 1);
+          mbar_wait(q_full(qs), (gq / (uint32_t)P.q_stages) & 1);
           if (!direct) convert_stage(qt);
         }
         int dy = 0, dx = 0;
         for (int tap = 0; tap < taps; ++tap, ++g) {
           if (per_tap) {  // this tap's own 8 x 16 tile
-            qs = gq % kQStages;
+            qs = (int)(gq % (uint32_t)P.q_stages);
             qt = sbase + kOffQ + qs * P.q_stage_stride;
-            mbar_wait(q_full(qs), (gq / kQStages) & 1);
+            mbar_wait(q_full(qs), (gq / (uint32_t)P.q_stages) & 1);
           }
           if ((int)(g & 1) == set) {
             if (cw == 0 || cw == 8) DBG_STAMP(3, g, 0);
@@ -870,6 +871,10 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.q_stage_bytes = per_tap ? (uint32_t)(cvt::kTileW * cvt::kTileH * 128) : (uint32_t)(halo_w * halo_h * 128);
   prm.q_stage_stride = (prm.q_stage_bytes + 1023) / 1024 * 1024;
   FOD_REQUIRE(cvt::kQStages * prm.q_stage_stride <= cvt::kOffB, "fod_conv2d_nhwc: halo tile does not fit the input ring");
+  // memory-bound layers (1x1, stride 2) stage 16 KB tiles: a fourth tile in flight per SM raises what Little's law allows
+  prm.q_stages = (int)(cvt::kOffB / prm.q_stage_stride);
+  if (prm.q_stages > cvt::kQStagesMax) prm.q_stages = cvt::kQStagesMax;
+  if (const char* e = getenv("FOD_CONV_Q_STAGES")) prm.q_stages = atoi(e) >= 2 && atoi(e) <= prm.q_stages ? atoi(e) : prm.q_stages;   // development knob (A/B)
   const int cin_pad = (cin + 31) / 32 * 32;
   prm.ksize = ksize;
   prm.taps = ksize * ksize;

@@ -9,8 +9,8 @@ torch.backends.cuda.matmul.allow_tf32 = False
 torch.backends.cudnn.benchmark = True
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dev = "cuda"
-shapes = [  # name, H, W, Cin, Cout, k
-    ("stem2", 320, 320, 64, 64, 3), ("osa2_0", 160, 160, 128, 64, 3), ("osa2_1", 160, 160, 64, 64, 3),
+shapes = [  # name, H, W, Cin, Cout, k (a name ending in "_s2": stride 2)
+    ("stem3_s2", 320, 320, 64, 128, 3), ("stem2", 320, 320, 64, 64, 3), ("osa2_0", 160, 160, 128, 64, 3), ("osa2_1", 160, 160, 64, 64, 3),
     ("osa2_cat", 160, 160, 320, 112, 1), ("osa3_0", 80, 80, 112, 80, 3), ("osa3_1", 80, 80, 80, 80, 3),
     ("osa3_cat", 80, 80, 352, 256, 1), ("osa4_0", 40, 40, 256, 96, 3), ("osa4_1", 40, 40, 96, 96, 3),
     ("osa4_cat", 40, 40, 544, 384, 1), ("osa5_0", 20, 20, 384, 112, 3), ("osa5_cat", 20, 20, 720, 512, 1),
@@ -42,12 +42,13 @@ for name, H, W, cin, cout, k in shapes:
     b = torch.randn(cout, device=dev)
     packed = ops.conv2d_pack(w)
     ax = ops.absmax(x)
-    y = ops.conv2d_nhwc(x, packed, b, cout, k, True, x_amax=ax)
-    ref = F.relu(F.conv2d(x, wc, b, padding=k // 2))
+    st = 2 if name.endswith("_s2") else 1
+    y = ops.conv2d_nhwc(x, packed, b, cout, k, True, x_amax=ax, stride=st)
+    ref = F.relu(F.conv2d(x, wc, b, padding=k // 2, stride=st))
     err = float((y - ref).abs().max()) / float(ref.abs().max())
-    t_a = timeit(lambda: ops.conv2d_nhwc(x, packed, b, cout, k, True, out=y, x_amax=ax))
-    t_b = timeit(lambda: F.relu_(F.conv2d(x, wc, b, padding=k // 2)))
-    fl = 2.0 * B * H * W * cin * cout * k * k
+    t_a = timeit(lambda: ops.conv2d_nhwc(x, packed, b, cout, k, True, out=y, x_amax=ax, stride=st))
+    t_b = timeit(lambda: F.relu_(F.conv2d(x, wc, b, padding=k // 2, stride=st)))
+    fl = 2.0 * B * (H // st) * (W // st) * cin * cout * k * k
     tot_a += t_a
     tot_b += t_b
     print(f"{name:9s} {H}x{W} {cin}->{cout} k{k}: tc {t_a:7.3f} ms ({fl/t_a/1e9:6.1f} TFLOP/s fp32-equiv)   cudnn {t_b:7.3f} ms "
