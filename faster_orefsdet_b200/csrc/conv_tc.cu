@@ -50,7 +50,7 @@ namespace cvt {
 
 constexpr int kTileH = 8, kTileW = 16;
 constexpr int kChunk = 32;
-constexpr int kQStages = 3, kQStagesMax = 4, kStages = 6, kAccStages = 2;   // input ring: 3 halo tiles, or 4 tiles of 8 x 16 pixels (1x1 / stride 2)
+constexpr int kQStagesMax = 6, kStages = 6, kAccStages = 2;   // input ring: 4 halo tiles, or 6 tiles of 8 x 16 pixels (1x1 / stride 2)
 constexpr int kPartChunks = 16;
 constexpr float kRzKappa = 0.f;  // a scalar compensation of the truncation bias (8.8e-8 per MMA for same-sign sums, tools/rz_calib.py) over-corrects real, mixed-sign layers: off
 constexpr uint32_t kQStageStrideS1 = ((kTileH + 2) * (kTileW + 2) * 128 + 1023) / 1024 * 1024;   // 23552
@@ -59,7 +59,9 @@ constexpr uint32_t kBStageBytes = 2 * kBPlaneMax;                           // h
 constexpr uint32_t kSlabBytes = 128 * 128;                                  // 128 pixels x 32 channels
 
 constexpr uint32_t kOffQ = 0;
-constexpr uint32_t kOffB = kOffQ + kQStages * kQStageStrideS1;              // 70656
+constexpr uint32_t kQBytes = 6 * 16384;                                     // 98304
+static_assert(4 * kQStageStrideS1 <= kQBytes, "four halo tiles fit the input ring");
+constexpr uint32_t kOffB = kOffQ + kQBytes;
 constexpr uint32_t kOffSum = kOffB + kStages * kBStageBytes;                // running tile / store staging, 4 slabs
 constexpr uint32_t kOffBias = kOffSum + 4 * kSlabBytes;
 constexpr uint32_t kOffBars = kOffBias + 128 * 4;
@@ -870,9 +872,10 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.halo_w = per_tap ? cvt::kTileW : halo_w;
   prm.q_stage_bytes = per_tap ? (uint32_t)(cvt::kTileW * cvt::kTileH * 128) : (uint32_t)(halo_w * halo_h * 128);
   prm.q_stage_stride = (prm.q_stage_bytes + 1023) / 1024 * 1024;
-  FOD_REQUIRE(cvt::kQStages * prm.q_stage_stride <= cvt::kOffB, "fod_conv2d_nhwc: halo tile does not fit the input ring");
-  // memory-bound layers (1x1, stride 2) stage 16 KB tiles: a fourth tile in flight per SM raises what Little's law allows
-  prm.q_stages = (int)(cvt::kOffB / prm.q_stage_stride);
+  FOD_REQUIRE(2 * prm.q_stage_stride <= cvt::kQBytes, "fod_conv2d_nhwc: halo tile does not fit the input ring");
+  // as many tiles in flight per SM as the ring holds (4 halo tiles, 6 of the 16 KB single-tap tiles of the memory-bound
+  // 1x1 / stride-2 layers): more bytes in flight is what Little's law asks for
+  prm.q_stages = (int)(cvt::kQBytes / prm.q_stage_stride);
   if (prm.q_stages > cvt::kQStagesMax) prm.q_stages = cvt::kQStagesMax;
   if (const char* e = getenv("FOD_CONV_Q_STAGES")) prm.q_stages = atoi(e) >= 2 && atoi(e) <= prm.q_stages ? atoi(e) : prm.q_stages;   // development knob (A/B)
   const int cin_pad = (cin + 31) / 32 * 32;
