@@ -32,8 +32,8 @@
 //   * weights: pre-split fp16 hi / lo planes [Cout][taps][Cin_pad] (fod_conv2d_pack_weights), TMA-streamed per chunk
 //     into a 6-stage ring (they are L2 resident: <= 0.6 MB per layer).
 //   * the tensor core accumulates with round-toward-zero (tools/tc_probe.cu), so the K loop is cut into partial sums
-//     of <= 16 chunks (96 MMAs) that the 4 epilogue warps add in IEEE fp32 into a running tile - in 64 spare columns of
-//     tensor memory for layers with <= 64 output channels, in shared memory otherwise; the last part rescales, adds the bias, applies ReLU and the tile leaves through TMA stores (clipped at the image
+//     of <= 16 chunks (96 MMAs) that the 4 epilogue warps add in IEEE fp32 into a running tile in shared memory; the
+//     last part rescales, adds the bias, applies ReLU and the tile leaves through TMA stores (clipped at the image
 //     border and at Cout by the tensor map, so the output may be a channel slice of a wider NHWC buffer: concatenation
 //     is free).
 #include <cuda_fp16.h>
@@ -50,7 +50,7 @@ namespace cvt {
 
 constexpr int kTileH = 8, kTileW = 16;
 constexpr int kChunk = 32;
-constexpr int kQStagesMax = 6, kStages = 6, kAccStages = 2;   // input ring: 4 halo tiles, or 6 tiles of 8 x 16 pixels (1x1 / stride 2)
+constexpr int kQStages = 3, kStages = 6, kAccStages = 2;
 constexpr int kPartChunks = 16;
 constexpr float kRzKappa = 0.f;  // a scalar compensation of the truncation bias (8.8e-8 per MMA for same-sign sums, tools/rz_calib.py) over-corrects real, mixed-sign layers: off
 constexpr uint32_t kQStageStrideS1 = ((kTileH + 2) * (kTileW + 2) * 128 + 1023) / 1024 * 1024;   // 23552
@@ -59,13 +59,11 @@ constexpr uint32_t kBStageBytes = 2 * kBPlaneMax;                           // h
 constexpr uint32_t kSlabBytes = 128 * 128;                                  // 128 pixels x 32 channels
 
 constexpr uint32_t kOffQ = 0;
-constexpr uint32_t kQBytes = 6 * 16384;                                     // 98304
-static_assert(4 * kQStageStrideS1 <= kQBytes, "four halo tiles fit the input ring");
-constexpr uint32_t kOffB = kOffQ + kQBytes;
+constexpr uint32_t kOffB = kOffQ + kQStages * kQStageStrideS1;              // 70656
 constexpr uint32_t kOffSum = kOffB + kStages * kBStageBytes;                // running tile / store staging, 4 slabs
 constexpr uint32_t kOffBias = kOffSum + 4 * kSlabBytes;
 constexpr uint32_t kOffBars = kOffBias + 128 * 4;
-constexpr uint32_t kNumBars = 2 * kQStagesMax + 3 * kStages + 2 * kAccStages;
+constexpr uint32_t kNumBars = 2 * kQStages + 3 * kStages + 2 * kAccStages;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr uint32_t kOffFlag = kOffTmemPtr + 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
@@ -79,7 +77,6 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAStageCols = 32;                // [hi: 16 columns of packed fp16 pairs | lo: 16]
 constexpr uint32_t kColA = 0;                       // 6 stages x 32
 constexpr uint32_t kColAcc = kStages * kAStageCols; // 2 stages x 128
-constexpr uint32_t kColRun = kColAcc + kAccStages * 128;  // 64 columns: running partial sums of layers with <= 64 output channels
 
 // 2^e with amax * 2^e in [2^13, 2^14) (and its inverse); 1 for zero / denormal-range / non-finite bounds
 __device__ __forceinline__ void pow2_scale(float amax, float& scale, float& inv) {
@@ -138,9 +135,7 @@ struct Params {
   int cin_chunks, chunks, parts, chunks_per_part;
   int n_groups, n_group, nhalf, ncol32, cout;
   int relu, num_pairs, pair_units, n_amax, ho, wo, cin;
-  int run_tmem;   // running partial sums live in tensor memory (n_group <= 64, more than one part) instead of shared memory
   uint32_t q_stage_bytes, q_stage_stride;
-  int q_stages;   // depth of the input ring: as many tiles as fit (3 halo tiles, 4 single-tap tiles)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ Params P) {
@@ -156,12 +151,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #endif
   const uint32_t bar0 = sbase + kOffBars;
   auto q_full = [&](int s) { return bar0 + 8u * s; };                                  // TMA -> converters
-  auto q_empty = [&](int s) { return bar0 + 8u * (kQStagesMax + s); };                 // converters -> TMA
-  auto b_full = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + s); };                 // TMA of both CTAs -> MMA (leader)
-  auto ready = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + kStages + s); };        // converters + weight bytes -> MMA
-  auto st_free = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + 2 * kStages + s); };  // MMA commit -> A + B stage free
-  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + 3 * kStages + s); };
-  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStagesMax + 3 * kStages + kAccStages + s); };
+  auto q_empty = [&](int s) { return bar0 + 8u * (kQStages + s); };                    // converters -> TMA
+  auto b_full = [&](int s) { return bar0 + 8u * (2 * kQStages + s); };                 // TMA of both CTAs -> MMA (leader)
+  auto ready = [&](int s) { return bar0 + 8u * (2 * kQStages + kStages + s); };        // converters + weight bytes -> MMA
+  auto st_free = [&](int s) { return bar0 + 8u * (2 * kQStages + 2 * kStages + s); };  // MMA commit -> A + B stage free
+  auto acc_full = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + s); };
+  auto acc_empty = [&](int s) { return bar0 + 8u * (2 * kQStages + 3 * kStages + kAccStages + s); };
   constexpr int stages = kStages;
   constexpr uint32_t acc_w = 128u, col_acc = kColAcc, b_stage = kBStageBytes;
   float xs = 1.f, xs_inv = 1.f;   // input scale 2^e (converters) and its inverse (epilogue)
@@ -172,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
 
   if (tid == 0) {
-    for (int s = 0; s < kQStagesMax; ++s) {
+    for (int s = 0; s < kQStages; ++s) {
       mbar_init(q_full(s), 1);
       mbar_init(q_empty(s), kConvWarps);
     }
@@ -223,8 +218,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int loads = P.per_tap ? taps : 1;
         for (int cc = 0; cc < cin_chunks; ++cc)
           for (int tap = 0; tap < loads; ++tap, ++g) {
-            const int s = (int)(g % (uint32_t)P.q_stages);
-            const uint32_t ph = (g / (uint32_t)P.q_stages) & 1;
+            const int s = g % kQStages;
+            const uint32_t ph = (g / kQStages) & 1;
             const int dy = tap / P.ksize, dx = tap - dy * P.ksize;   // (0, 0) when the halo tile serves every tap
             mbar_wait(q_empty(s), ph ^ 1);
             mbar_arrive_expect_tx(q_full(s), P.q_stage_bytes);
@@ -391,7 +386,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(acc_full(as_), aph);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + col_acc + as_ * acc_w;
-        const uint32_t trun = tmem_base + ((uint32_t)(qd * 32) << 16) + kColRun;
         const int part_chunks = min(P.chunks_per_part, P.chunks - part * P.chunks_per_part);
         const float comp = 1.f + P.rz_kappa * 0.5f * (float)(part_chunks * mma_per_chunk);
 #pragma unroll 1
@@ -404,45 +398,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * as_);
           }
-          if (P.run_tmem) {
-            // Narrow layers: the running sum of the parts stays in 64 spare columns of tensor memory (this warp's own
-            // lanes) - no shared-memory read-modify-write per part; the IEEE fp32 additions are the same as below.
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * comp);
-            if (part > 0) {
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                uint32_t r[16];
-                tmem_ld16(trun + j * 32 + hh * 16, r);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[hh * 16 + i] = __float_as_uint(__uint_as_float(v[hh * 16 + i]) + __uint_as_float(r[i]));
-              }
-            }
-            if (part < parts - 1) {
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                uint32_t w16[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) w16[i] = v[hh * 16 + i];
-                tmem_st16(trun + j * 32 + hh * 16, w16);
-              }
-              if (j == ncol32 - 1) tmem_wait_st();   // visible to this thread's loads of the next part
-              continue;
-            }
-          }
           const uint32_t slab = row_s + (uint32_t)j * kSlabBytes;
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const uint32_t sa = slab + (uint32_t)((c4 ^ (m & 7)) << 4);
-            float4 x;
-            if (P.run_tmem)   // already scaled and added to the running sum above
-              x = make_float4(__uint_as_float(v[c4 * 4 + 0]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]),
-                              __uint_as_float(v[c4 * 4 + 3]));
-            else
-              x = make_float4(__uint_as_float(v[c4 * 4 + 0]) * comp, __uint_as_float(v[c4 * 4 + 1]) * comp,
-                              __uint_as_float(v[c4 * 4 + 2]) * comp, __uint_as_float(v[c4 * 4 + 3]) * comp);
-            if (part > 0 && !P.run_tmem) {
+            float4 x = make_float4(__uint_as_float(v[c4 * 4 + 0]) * comp, __uint_as_float(v[c4 * 4 + 1]) * comp,
+                                   __uint_as_float(v[c4 * 4 + 2]) * comp, __uint_as_float(v[c4 * 4 + 3]) * comp);
+            if (part > 0) {
               const float4 r = lds4s(sa);
               x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
             }
@@ -603,18 +565,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int cc = 0; cc < cin_chunks; ++cc) {
         if (P.a_gate) gate_row = P.a_gate + (size_t)unit_n * P.cin + cc * kChunk;
         if (P.a_shift) shift_row = P.a_shift + (size_t)unit_n * P.cin + cc * kChunk;
-        int qs = (int)(gq % (uint32_t)P.q_stages);
+        int qs = gq % kQStages;
         uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
         if (!per_tap) {
-          mbar_wait(q_full(qs), (gq / (uint32_t)P.q_stages) & 1);
+          mbar_wait(q_full(qs), (gq / kQStages) & 1);
           if (!direct) convert_stage(qt);
         }
         int dy = 0, dx = 0;
         for (int tap = 0; tap < taps; ++tap, ++g) {
           if (per_tap) {  // this tap's own 8 x 16 tile
-            qs = (int)(gq % (uint32_t)P.q_stages);
+            qs = gq % kQStages;
             qt = sbase + kOffQ + qs * P.q_stage_stride;
-            mbar_wait(q_full(qs), (gq / (uint32_t)P.q_stages) & 1);
+            mbar_wait(q_full(qs), (gq / kQStages) & 1);
           }
           if ((int)(g & 1) == set) {
             if (cw == 0 || cw == 8) DBG_STAMP(3, g, 0);
@@ -872,12 +834,7 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.halo_w = per_tap ? cvt::kTileW : halo_w;
   prm.q_stage_bytes = per_tap ? (uint32_t)(cvt::kTileW * cvt::kTileH * 128) : (uint32_t)(halo_w * halo_h * 128);
   prm.q_stage_stride = (prm.q_stage_bytes + 1023) / 1024 * 1024;
-  FOD_REQUIRE(2 * prm.q_stage_stride <= cvt::kQBytes, "fod_conv2d_nhwc: halo tile does not fit the input ring");
-  // as many tiles in flight per SM as the ring holds (4 halo tiles, 6 of the 16 KB single-tap tiles of the memory-bound
-  // 1x1 / stride-2 layers): more bytes in flight is what Little's law asks for
-  prm.q_stages = (int)(cvt::kQBytes / prm.q_stage_stride);
-  if (prm.q_stages > cvt::kQStagesMax) prm.q_stages = cvt::kQStagesMax;
-  if (const char* e = getenv("FOD_CONV_Q_STAGES")) prm.q_stages = atoi(e) >= 2 && atoi(e) <= prm.q_stages ? atoi(e) : prm.q_stages;   // development knob (A/B)
+  FOD_REQUIRE(cvt::kQStages * prm.q_stage_stride <= cvt::kOffB, "fod_conv2d_nhwc: halo tile does not fit the input ring");
   const int cin_pad = (cin + 31) / 32 * 32;
   prm.ksize = ksize;
   prm.taps = ksize * ksize;
@@ -899,8 +856,6 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.nhalf = prm.n_group / 2;
   prm.ncol32 = (prm.n_group + 31) / 32;
   prm.cout = cout;
-  prm.run_tmem = (prm.n_group <= 64 && prm.parts > 1) ? 1 : 0;
-  if (const char* e = getenv("FOD_CONV_RUN_TMEM")) prm.run_tmem = prm.run_tmem && atoi(e) != 0;   // development knob (A/B)
   prm.relu = relu;
   prm.bias = bias;
   prm.x_amax = x_amax;
