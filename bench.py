@@ -266,7 +266,10 @@ def run_gpu_arm(args):
 
     with torch.no_grad():
         for i in range(args.warmup):
-            step_resident(i)
+            out = step_resident(i)
+        if world > 1:     # the job's final gather once untimed as well: NCCL sets its channels up lazily on the first call
+            packed = torch.cat((out[0], out[1].unsqueeze(-1), out[2].unsqueeze(-1).float()), -1)
+            dist.all_gather([torch.empty_like(packed) for _ in range(world)], packed)
         barrier()
         clocks = ClockSampler(local)
         if rank == 0:
