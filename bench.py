@@ -253,7 +253,7 @@ def run_gpu_arm(args):
     sizes = [(IMG, IMG)] * B
     timer = KernelTimer()
     timer.wrap(ops, ["correlate_levels", "decode_topk", "nms_proposals", "roi_align", "relation_head", "final_detect",
-                     "conv2d_nhwc", "group_norm_nhwc", "stem_patches", "stem_patches_u8", "stem1_u8", "maxpool3x3s2_nhwc"])
+                     "conv2d_nhwc", "group_norm_nhwc", "stem_patches", "stem_patches_u8", "stem1_u8", "maxpool3x3s2_nhwc", "ese_gate"])
 
     def step_resident(i):      # raw uint8 images resident in HBM -> padded detections on the device
         return model.detect_from_uint8(dev_sets[i % NSETS], sizes, sizes)
