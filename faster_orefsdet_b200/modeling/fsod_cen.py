@@ -115,9 +115,13 @@ class CenterNet2Detector(nn.Module):
         self.init_model()
         if self._bank is None:
             raise _lib.FodError("no support prototypes installed: call init_model() / set_prototypes() first")
+        if getattr(self, "_in_flight", 0) >= self.U8_RING - 1:
+            raise _lib.FodError(f"submit: {self._in_flight} batches are already in flight; collect one first "
+                                f"(the input ring holds {self.U8_RING} buffers)")
         staged = self._stage_uint8(batched_inputs)
         if staged is None:
             return batched_inputs
+        self._in_flight = getattr(self, "_in_flight", 0) + 1
         x_u8, events, chunk = staged
         n, _, h, w = x_u8.shape
         image_sizes = [(int(h), int(w))] * n
@@ -139,6 +143,7 @@ class CenterNet2Detector(nn.Module):
     def collect(self, pending: "PendingBatch", do_postprocess: bool = True):
         """Wait for a submitted batch and build its results (what ``forward`` returns)."""
         pending.done.synchronize()
+        self._in_flight = max(getattr(self, "_in_flight", 0) - 1, 0)
         st = int(pending.status_host[0]) & 0xFFFFFFFF
         if st:
             # ties above the reserved proposal slack (or an error): redo this batch eagerly with fresh buffers, stream

@@ -365,12 +365,14 @@ def test_submitted_batches_equal_plain_calls():
     odd = [{"image": synth.ore_image(100, 160, 1)}]
     assert model.submit(odd) is odd
     assert len(model(model.submit(odd))) == 1
-    # up to three batches in flight through the ring of three input buffers
+    # two batches in flight through the ring of three input buffers; a third submit is refused until one is collected
     pend = [model.submit(batches[k % 3]) for k in range(2)]
+    with pytest.raises(Exception, match="in flight"):
+        model.submit(batches[2])
     outs = []
     for k in range(2, 6):
-        pend.append(model.submit(batches[k % 3]))
         outs.append(model(pend.pop(0)))
+        pend.append(model.submit(batches[k % 3]))
     outs += [model(p) for p in pend]
     for k, r in enumerate(outs):
         for a, b in zip(plain[k % 3], r):
