@@ -125,14 +125,6 @@ class Instances:
         return self._fields
 
     def to(self, *args: Any, **kwargs: Any) -> "Instances":
-        # The detector copies all detections of a batch to the host in ONE transfer and attaches the host views
-        # (``_host_mirror``); ``.to("cpu")`` - what COCOEvaluator.process does per image - then costs no device sync.
-        mirror = self.__dict__.get("_host_mirror")
-        if mirror is not None and not kwargs and len(args) == 1 and str(args[0]) == "cpu":
-            ret = Instances(self._image_size)
-            for k, v in mirror.items():
-                ret.set(k, v)
-            return ret
         ret = Instances(self._image_size)
         for k, v in self._fields.items():
             if hasattr(v, "to"):

@@ -72,6 +72,15 @@ constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColA = 0;      // 4 stages x [s_hi 16 | s_lo 16 | q_hi 16 | q_lo 16]
 constexpr uint32_t kColAcc = 256;  // 2 stages x 128
 
+// Support taps of every (level, class) set of one launch travel INSIDE THE LAUNCH PARAMETERS (constant bank 0): a tap is
+// warp-uniform, so it reaches the FMA as a uniform / constant operand instead of costing shared-memory bandwidth per
+// lane, and - unlike a __constant__ symbol - the values belong to the launch, not to the device: concurrent calls on
+// different streams (or a graph replay next to an eager call) cannot overwrite each other's taps.
+constexpr int kMaxTapSets = 6;     // 6 x 4 KB of the 32 764-byte parameter space (CUDA >= 12.1)
+constexpr int kStencilUnroll = 1;  // measured: 1, 2 and 4 run at the same speed; 1 keeps the body inside the L0 I-cache
+// rows 0..6: k11, k13 (left, centre, right), k31 (up, centre, down); row 7: c11 = k11 > 0 ? k11*k11 : 0
+constexpr int kTapRows = 8;
+
 struct Level {
   int H, W, tiles_x, tiles_per_problem, tiles_per_class, tile_begin;  // tiles_per_class = batch * tiles_per_problem
 };
@@ -85,6 +94,8 @@ struct Params {
   float* attn_amax[FOD_MAX_LEVELS];   // null or device scalar per level (zeroed by the caller): raised to max(attn)
   // problems of this launch: images x classes [class_begin, class_begin + class_count) of num_classes
   int num_levels, num_classes, class_begin, class_count, total_tiles, num_pairs;
+  // tap sets of this launch, set = level * class_count + class (filled on the host from the caller's HOST taps)
+  alignas(16) float taps[kMaxTapSets][kTapRows][kC];
 };
 
 // Tile order: level-major, then class, then image, then tile (all tiles that share one tap set are contiguous).
@@ -126,31 +137,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// Support taps of every (level, class) set of the launch, in the constant bank: a tap is warp-uniform, so it
-// reaches the FMA as a uniform / constant operand instead of costing shared-memory bandwidth per lane.
-constexpr int kMaxTapSets = 15;
-constexpr int kStencilUnroll = 1;  // measured: 1, 2 and 4 run at the same speed; 1 keeps the body inside the L0 I-cache
-// rows 0..6: k11, k13 (left, centre, right), k31 (up, centre, down); row 7: c11 = k11 > 0 ? k11*k11 : 0
-constexpr int kTapRows = 8;
-__constant__ __align__(16) float c_taps[kMaxTapSets][kTapRows][kC];
-
-// Fills the constant-bank tap sets of one launch (set = level * class_count + class) from the [C][7][128] taps of
-// fod_support_taps and appends row 7.  Runs stream-ordered before the persistent kernel (the constant cache is
-// coherent at kernel boundaries).
-struct TapPack {
-  const float* src[FOD_MAX_LEVELS];
-  int class_count;
-};
-__global__ void pack_taps_kernel(const TapPack pk, float* __restrict__ dst) {
-  const int set = blockIdx.x, l = set / pk.class_count, cc = set - l * pk.class_count, ch = threadIdx.x;
-  const float* s = pk.src[l] + (size_t)cc * 7 * kC;
-  float* d = dst + (size_t)set * kTapRows * kC;
-#pragma unroll
-  for (int k = 0; k < 7; ++k) d[k * kC + ch] = s[k * kC + ch];
-  const float k11 = s[ch];
-  d[7 * kC + ch] = k11 > 0.f ? k11 * k11 : 0.f;
-}
 
 struct StencilCtx {
   uint8_t* smem;
@@ -213,7 +199,7 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
           for (int j4 = 0; j4 < 4; ++j4) {  // 4 channels per step
             {
               const int jj = (sub & 1) * 4 + j4;  // 16-byte channel group inside the q box
-              const float* tp = &c_taps[set][0][sub * kSub + j4 * 4];
+              const float* tp = &P.taps[set][0][sub * kSub + j4 * 4];
               const uint32_t jx = (uint32_t)jj << 4;
               const float4 k13l = *reinterpret_cast<const float4*>(tp + 1 * kC);
               const float4 k13c = *reinterpret_cast<const float4*>(tp + 2 * kC);
@@ -529,7 +515,7 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* t
     const int H = levels[l].height, W = levels[l].width;
     FOD_REQUIRE(H > 0 && W > 0 && q[l] && attn[l] && taps[l], "fod_correlate_levels: level %d invalid", l);
     prm.attn_amax[l] = attn_amax ? attn_amax[l] : nullptr;
-    FOD_REQUIRE((((uintptr_t)q[l] | (uintptr_t)attn[l] | (uintptr_t)taps[l]) & 15) == 0,
+    FOD_REQUIRE((((uintptr_t)q[l] | (uintptr_t)attn[l]) & 15) == 0,
                 "fod_correlate_levels: level %d pointers must be 16-byte aligned", l);
     int rc = make_nhwc_map(&prm.in_map[l], q[l], batch, H, W, kC, ctc::kChunk, ctc::kHaloW, ctc::kHaloH);
     if (rc != FOD_OK) return rc;
@@ -546,13 +532,9 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* t
   const int max_pairs = sms / 2 > 0 ? sms / 2 : 1;
   FOD_CUDA_CALL(cudaFuncSetAttribute(ctc::correlate_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)ctc::kSmemAlloc));
-  // The taps live in the constant bank (ctc::c_taps, kMaxTapSets sets): classes are processed in groups that fit,
-  // each group = one stream-ordered symbol update + one persistent launch.
+  // The taps ride in the launch parameters (ctc::Params::taps, kMaxTapSets sets): classes are processed in groups that
+  // fit, one persistent launch per group.  Nothing outside the launch is written: the call is re-entrant.
   const int group = ctc::kMaxTapSets / num_levels;
-  float* ctaps_dev = nullptr;
-  FOD_CUDA_CALL(cudaGetSymbolAddress(reinterpret_cast<void**>(&ctaps_dev), ctc::c_taps));
-  ctc::TapPack pk;
-  memset(&pk, 0, sizeof(pk));
   for (int c0 = 0; c0 < num_classes; c0 += group) {
     const int cn = num_classes - c0 < group ? num_classes - c0 : group;
     long tiles = 0;
@@ -566,11 +548,13 @@ extern "C" int fod_correlate_levels(const float* const* q, const float* const* t
       L.tile_begin = (int)tiles;
       tiles += (long)cn * L.tiles_per_class;
       FOD_REQUIRE(tiles < (1L << 30), "fod_correlate_levels: too many tiles");
-      pk.src[l] = taps[l] + (size_t)c0 * 7 * kC;
+      for (int cc = 0; cc < cn; ++cc) {   // set = l * cn + cc
+        const float* src = taps[l] + (size_t)(c0 + cc) * 7 * kC;
+        float(*dst)[kC] = prm.taps[l * cn + cc];
+        memcpy(dst, src, sizeof(float) * 7 * kC);
+        for (int ch = 0; ch < kC; ++ch) dst[7][ch] = src[ch] > 0.f ? src[ch] * src[ch] : 0.f;
+      }
     }
-    pk.class_count = cn;
-    ctc::pack_taps_kernel<<<num_levels * cn, kC, 0, as_stream(stream)>>>(pk, ctaps_dev);
-    FOD_CUDA_LAUNCH_CHECK("fod_correlate_levels (pack taps)");
     prm.class_begin = c0;
     prm.class_count = cn;
     prm.total_tiles = (int)tiles;

@@ -109,7 +109,11 @@ class CenterNet2Detector(nn.Module):
         A serving loop submits batch k+1 before it collects batch k (``model(pending_k)``), so the PCIe transfers and the
         host-side construction of the ``Instances`` ride under the kernels of the neighbouring batches.  Returns a
         ``PendingBatch``, or ``batched_inputs`` itself when the uint8 fast path or the CUDA graph does not apply (then
-        nothing is enqueued and ``model(...)`` runs the batch synchronously)."""
+        nothing is enqueued and ``model(...)`` runs the batch synchronously).
+
+        Contract for the caller: pinned host images are read by the copy engine AFTER this call returns - do not
+        modify or free them until the batch has been collected (``model(pending)``) or abandoned (``abandon``).  Every
+        PendingBatch must be collected or abandoned: the input ring holds ``U8_RING`` device buffers."""
         if self.training or not self.USE_CUDA_GRAPH:
             return batched_inputs
         self.init_model()
@@ -121,7 +125,6 @@ class CenterNet2Detector(nn.Module):
         staged = self._stage_uint8(batched_inputs)
         if staged is None:
             return batched_inputs
-        self._in_flight = getattr(self, "_in_flight", 0) + 1
         x_u8, events, chunk = staged
         n, _, h, w = x_u8.shape
         image_sizes = [(int(h), int(w))] * n
@@ -138,11 +141,23 @@ class CenterNet2Detector(nn.Module):
         status_host.copy_(status.view(-1)[:1], non_blocking=True)
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(self.device))
+        # counted only once everything is enqueued: an exception above leaves the counter untouched
+        self._in_flight = getattr(self, "_in_flight", 0) + 1
         return PendingBatch(batched_inputs, x_u8, image_sizes, out_sizes, block, host, status_host, done)
+
+    def abandon(self, pending: "PendingBatch") -> None:
+        """Give up a submitted batch without building its results (its kernels still run to completion)."""
+        if isinstance(pending, PendingBatch) and pending.done is not None:
+            pending.done.synchronize()
+            pending.done = None
+            self._in_flight = max(getattr(self, "_in_flight", 0) - 1, 0)
 
     def collect(self, pending: "PendingBatch", do_postprocess: bool = True):
         """Wait for a submitted batch and build its results (what ``forward`` returns)."""
+        if pending.done is None:
+            raise _lib.FodError("collect: this PendingBatch was already collected or abandoned")
         pending.done.synchronize()
+        pending.done = None
         self._in_flight = max(getattr(self, "_in_flight", 0) - 1, 0)
         st = int(pending.status_host[0]) & 0xFFFFFFFF
         if st:
@@ -176,11 +191,24 @@ class CenterNet2Detector(nn.Module):
         self.set_bank(broadcast_bank(self._bank, self.device, src))
         return self._bank
 
+    def _refresh_bank_bias(self):
+        """The folded per-class bias depends on the relation-head weights: recompute it when they changed (any path:
+        load_state_dict on the model or on a sub-module, in-place edits, .to()), also for banks installed through
+        set_prototypes / set_bank / sync_prototypes."""
+        bank = self._bank
+        if bank is None:
+            return
+        fk = self.roi_heads.fold_key()
+        if bank.__dict__.get("_bias_key") != fk:
+            bank.bias_cls = self.roi_heads.class_bias(bank.support_mean)
+            bank.__dict__["_bias_key"] = fk
+
     def init_model(self):
         """fsod_cen.py:313-415.  Cache present: load it (once per file version).  Cache missing:
         build it from ./datasets/coco/10_shot_support_df.pkl, write it, and ``sys.exit(0)`` exactly
         like the reference (README.md:74 tells users to delete the cache before fine-tuning)."""
         if self._bank is not None and self._bank_key is not None and self._bank_key[0] in ("memory", "bank"):
+            self._refresh_bank_bias()
             return
         os.makedirs(os.path.dirname(self._support.path) or ".", exist_ok=True)
         if not self._support.exists():
@@ -192,8 +220,9 @@ class CenterNet2Detector(nn.Module):
         # changed: its (mtime, size) is checked per call, and the reduced episode (taps, support mean, folded bias) is kept
         # next to it as a binary, mmap-able file that a fresh process uploads with one copy.
         src = self._support.stat_key()
-        key = (os.path.abspath(self._support.path),) + tuple(src) + (getattr(self, "_weights_epoch", 0),)
+        key = (os.path.abspath(self._support.path),) + tuple(src)
         if self._bank is not None and self._bank_key == key:
+            self._refresh_bank_bias()
             return
         bank = None
         if os.environ.get("FOD_BINARY_PROTOTYPES", "1") == "1":
@@ -207,6 +236,7 @@ class CenterNet2Detector(nn.Module):
             except OSError:
                 pass
         self._bank, self._bank_key = bank, key
+        self._refresh_bank_bias()
 
     @torch.no_grad()
     def build_support_dict(self, images_per_class: Dict[int, List[torch.Tensor]],
@@ -360,6 +390,8 @@ class CenterNet2Detector(nn.Module):
             rings.clear()                      # one batch shape at a time
             rings[(n, c, h, w)] = ring
             side.wait_stream(main)             # the buffers were allocated on the main stream
+        if any(im.is_cuda for im in imgs):
+            side.wait_stream(main)             # device-resident inputs: whatever produced them on the current stream first
         j = ring["next"]
         ring["next"] = (j + 1) % self.U8_RING
         x_u8 = ring["bufs"][j]
@@ -392,7 +424,7 @@ class CenterNet2Detector(nn.Module):
         bank = self._bank
         raw = [features[f] for f in self.in_features]
         status = ops.new_status(raw[0].device)
-        attn, attn_amax = ops.correlate_levels(raw, bank.taps, self.conv3.weight, self.conv3.bias, want_amax=True)
+        attn, attn_amax = ops.correlate_levels(raw, bank.taps_host, self.conv3.weight, self.conv3.bias, want_amax=True)
         props = self.proposal_generator.propose_raw(attn, status, cap, bounds=attn_amax)
         out, per_roi = self.roi_heads.detect_raw(raw, bank.bias_cls, props.boxes, props.count, bank.num_classes, image_hw, out_hw,
                                                  status)
@@ -416,10 +448,21 @@ class CenterNet2Detector(nn.Module):
     # ------------------------------------------------------------------ CUDA graph of everything behind the stem
     USE_CUDA_GRAPH = os.environ.get("FOD_CUDA_GRAPH", "1") == "1"
 
+    def _weights_fingerprint(self):
+        """(data_ptr, version) of every parameter and buffer: changes on load_state_dict (of the model or of any
+        sub-module), in-place edits, .to() / .float().  The tensor list is cached per epoch (``_apply`` and
+        ``load_state_dict`` bump it; code that REPLACES Parameter objects must call ``_bump_weights_epoch``)."""
+        ep = getattr(self, "_weights_epoch", 0)
+        hit = self.__dict__.get("_fp_tensors")
+        if hit is None or hit[0] != ep:
+            hit = (ep, list(self.parameters()) + list(self.buffers()))
+            self.__dict__["_fp_tensors"] = hit
+        return tuple((t.data_ptr(), t._version) for t in hit[1])
+
     def _graph_key(self, n, h, w):
-        # weights enter the captured graph as packed copies: any path that replaces or rewrites them bumps the epoch
-        # (load_state_dict, .to() / .cuda() / .float() through _apply)
-        return (n, h, w, self._bank_key, id(self._bank), getattr(self, "_weights_epoch", 0), str(self.device))
+        # weights enter the captured graph as packed copies (tcconv cache, folded relation matrix, folded bias): the key
+        # carries the identity and version of every parameter, so no path that changes a weight can leave a stale graph
+        return (n, h, w, self._bank_key, id(self._bank), self._weights_fingerprint(), str(self.device))
 
     def _bump_weights_epoch(self, *args, **kwargs):
         self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
@@ -467,6 +510,11 @@ class CenterNet2Detector(nn.Module):
         with torch.cuda.graph(graph):
             g["feats"], g["res"] = run()
         g["graph"] = graph
+        # the graph's kernel nodes hold raw pointers into the packed weight copies and the episode tensors: keep those
+        # alive for as long as the graph, whatever an eager call re-packs in the meantime
+        from . import tcconv
+        g["keepalive"] = ([v for v in tcconv._cache.values()], self.roi_heads._fold_cache, self._bank,
+                          self._bank.bias_cls, list(self._bank.taps))
         self._graph = g
         return g
 

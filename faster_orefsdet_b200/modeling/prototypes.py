@@ -79,6 +79,16 @@ class PrototypeBank:
     def num_classes(self) -> int:
         return len(self.class_ids)
 
+    @property
+    def taps_host(self) -> List[torch.Tensor]:
+        """Host copies of the taps (one transfer per episode): fod_correlate_levels takes them as launch parameters."""
+        hit = self.__dict__.get("_taps_host")
+        if hit is None or hit[0] != tuple((t.data_ptr(), t._version) for t in self.taps):
+            hit = (tuple((t.data_ptr(), t._version) for t in self.taps),
+                   [t.detach().to("cpu", torch.float32).contiguous() for t in self.taps])
+            self.__dict__["_taps_host"] = hit
+        return hit[1]
+
     # ---- one flat fp32 buffer for the NCCL broadcast (SURVEY section 8e)
     def pack(self) -> torch.Tensor:
         return torch.cat([t.reshape(-1) for t in self.taps] + [self.support_mean.reshape(-1), self.bias_cls.reshape(-1)])

@@ -100,8 +100,12 @@ class CustomCascadeROIHeads(nn.Module):
     def _state(self) -> Dict[str, torch.Tensor]:
         return {"roi_heads." + k: v.detach() for k, v in self.state_dict().items()}
 
+    def fold_key(self):
+        """Identity + version of every parameter the folded matrix and the per-class bias depend on."""
+        return tuple((p.data_ptr(), p._version, p.device) for p in self._fold_params())
+
     def folded(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        key = tuple((p.data_ptr(), p._version, p.device) for p in self._fold_params())
+        key = self.fold_key()
         if self._fold_cache is None or self._fold_cache[0] != key:
             w_fold, w_out, b_out = fold.fold_relation_weights(self._state())
             if w_fold.is_cuda:       # tf32 hi / lo planes for the tensor-core kernel, once per weight load
@@ -166,10 +170,42 @@ def pack_block(boxes, scores, classes, count) -> torch.Tensor:
                       count.to(torch.float32).view(B, 1, 1).expand(B, K, 1)), -1)
 
 
+def _targets_cpu(args, kwargs) -> bool:
+    dev = kwargs.get("device", args[0] if args else None)
+    if set(kwargs) - {"device", "non_blocking"} or len(args) > 1 or dev is None:
+        return False
+    return (isinstance(dev, str) and dev == "cpu") or (isinstance(dev, torch.device) and dev.type == "cpu")
+
+
+def _field_stamp(v):
+    t = v.tensor if isinstance(v, Boxes) else v
+    return (v, t._version if isinstance(t, torch.Tensor) else None)
+
+
+class DetectionInstances(Instances):
+    """``Instances`` (detectron2's own class when it is installed, the compat stand-in otherwise) whose fields also exist
+    on the host: the detector moves all detections of a batch with ONE device-to-host transfer and attaches the host
+    views.  ``.to("cpu")`` - what COCOEvaluator.process does per image (fewx/evaluation/coco_evaluation.py:119-126) -
+    returns them without touching the device, as long as no field was added, removed, replaced or modified in place
+    since construction; otherwise (and for every other target) it is the base class's field-by-field ``to``."""
+
+    def to(self, *args, **kwargs):
+        mirror = self.__dict__.get("_host_mirror")
+        if mirror is not None and _targets_cpu(args, kwargs):
+            stamps, fields = self.__dict__["_mirror_stamps"], self._fields
+            if len(fields) == len(stamps) and all(k in fields and fields[k] is st[0] and _field_stamp(fields[k])[1] == st[1]
+                                                  for k, st in stamps.items()):
+                ret = Instances(self._image_size)
+                for k, v in mirror.items():
+                    ret.set(k, v)
+                return ret
+        return super().to(*args, **kwargs)
+
+
 def pack_instances(boxes, scores, classes, count, image_sizes) -> List[Instances]:
     """Padded device outputs -> list[Instances] on the device, with ONE device-to-host transfer of the whole
-    padded block ([B, K, 7] fp32) whose views ride along as the host mirror of every Instances
-    (compat Instances.to("cpu") returns them; the reference's evaluator copies field by field, image by image:
+    padded block ([B, K, 7] fp32) whose views ride along as the host mirror of every DetectionInstances
+    (its .to("cpu") returns them; the reference's evaluator copies field by field, image by image:
     fewx/evaluation/coco_evaluation.py:119-126).  The valid rows are compacted once and split per image with
     split_with_sizes, so the per-image Python cost is the construction of the containers only."""
     block = pack_block(boxes, scores, classes, count)
@@ -202,9 +238,11 @@ def instances_from_block(block: torch.Tensor, host: torch.Tensor, image_sizes) -
 
     out = []
     for b in range(B):
-        inst = Instances.__new__(Instances)           # the three fields have equal lengths by construction
+        inst = DetectionInstances.__new__(DetectionInstances)     # the three fields have equal lengths by construction
         inst.__dict__["_image_size"] = (int(image_sizes[b][0]), int(image_sizes[b][1]))
-        inst.__dict__["_fields"] = {"pred_boxes": boxes_of(db[b]), "scores": ds[b], "pred_classes": dc[b]}
+        fields = {"pred_boxes": boxes_of(db[b]), "scores": ds[b], "pred_classes": dc[b]}
+        inst.__dict__["_fields"] = fields
         inst.__dict__["_host_mirror"] = {"pred_boxes": boxes_of(hb[b]), "scores": hs[b], "pred_classes": hc[b]}
+        inst.__dict__["_mirror_stamps"] = {k: _field_stamp(v) for k, v in fields.items()}
         out.append(inst)
     return out

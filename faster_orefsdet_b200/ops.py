@@ -102,14 +102,17 @@ def _empty_nhwc(n: int, h: int, w: int, device) -> Tensor:
 def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3: Tensor, want_amax: bool = False):
     """All FPN levels in one persistent tensor-core launch.
     q[l] [B,128,H_l,W_l], taps[l] [C,7,128] -> attn[l] [B*C,128,H_l,W_l] (NHWC memory), problem-major
-    (fsod_cen.py:463-470, 482-491, 502-509).  With ``want_amax`` also returns max(attn[l]) per level as device floats
-    (the operand bounds of the tower convolutions), tracked in the kernel's epilogue."""
+    (fsod_cen.py:463-470, 482-491, 502-509).  ``taps`` are episode constants and travel to the kernel as launch
+    parameters: pass HOST tensors (``PrototypeBank.taps_host``); CUDA tensors are copied to the host first, which
+    synchronises (tests / interop only - not allowed inside a graph capture).  With ``want_amax`` also returns
+    max(attn[l]) per level as device floats (the operand bounds of the tower convolutions), tracked in the kernel's
+    epilogue."""
     L = len(q)
     if L < 1 or L > 3 or len(taps) != L:
         raise _lib.FodError("correlate_levels: 1..3 levels with one taps tensor each")
     q = [nhwc(t, f"q[{i}]") for i, t in enumerate(q)]
     B, C = q[0].shape[0], taps[0].shape[0]
-    taps = [_chk(t, torch.float32, "taps").contiguous() for t in taps]
+    taps = [t.detach().to("cpu", torch.float32).contiguous() for t in taps]
     for t, qq in zip(taps, q):
         if tuple(t.shape) != (C, 7, 128) or qq.shape[0] != B or qq.shape[1] != 128:
             raise _lib.FodError("correlate_levels: bad shapes")

@@ -16,8 +16,10 @@
  *     torch.channels_last memory format has exactly this layout.
  *   - a "problem" is one (query image b, support class c) pair, p = b*C + c.
  *   - the caller owns every buffer; the library allocates nothing, keeps no
- *     global state, never synchronises, never touches the default stream;
- *     every call is stream-ordered and CUDA-graph capturable.
+ *     global state (no device symbols are written: episode constants such as the
+ *     support taps travel inside the launch parameters), never synchronises,
+ *     never touches the default stream; every call is stream-ordered, re-entrant
+ *     across streams and CUDA-graph capturable.
  *   - return value: FOD_OK or a negative FOD_ERR_* (fod_last_error() gives text).
  *     Data-dependent overflow of a fixed-capacity output is reported on the
  *     device in the caller's `status` word (FOD_STATUS_* bits) and must be
@@ -76,7 +78,7 @@ int fod_support_taps(const float* proto, int num_classes, int h, int w, float* t
  * Replaces fsod_cen.py:463-470 (p3), :482-491 (p4), :502-509 (p5): four depthwise
  * F.conv2d + ReLUs + adds + torch.cat + self.conv3 + ReLU.
  *   q     : [B][H][W][128]            query map of this level
- *   taps  : [C][7][128]               from fod_support_taps
+ *   taps  : [C][7][128]  HOST memory  from fod_support_taps, copied to the host once per episode (see below)
  *   w3    : [128][256]                conv3.weight (out, in) ; in = [attn-sum | q]
  *   b3    : [128]
  *   attn  : [B*C][H][W][128]          problem-major output
@@ -86,10 +88,14 @@ int fod_correlate(const float* q, const float* taps, const float* w3, const floa
 
 /* Q2+Q3 for ALL FPN levels and all (image, class) problems in one persistent launch
  * (tcgen05 tensor cores, 3xTF32 operand splitting = fp32 accuracy, TMA in/out).
- * Same arithmetic contract as fod_correlate.  q, taps, attn are HOST arrays of
- * num_levels DEVICE pointers:
+ * Same arithmetic contract as fod_correlate.  q and attn are HOST arrays of
+ * num_levels DEVICE pointers; taps is a HOST array of num_levels HOST pointers:
  *   q[l]    : [B][H_l][W_l][128]
- *   taps[l] : [C][7][128]              from fod_support_taps on the level-l prototype
+ *   taps[l] : [C][7][128]  HOST        the output of fod_support_taps on the level-l prototype, read back once per
+ *                                      episode.  The taps are warp-uniform operands of the stencil: they are copied
+ *                                      into the launch parameters (constant bank 0, 6 sets = 24 KB per launch; classes
+ *                                      are processed in groups of 6 / num_levels), so no device state outlives or is
+ *                                      shared between calls, and a captured graph bakes in the episode's taps.
  *   attn[l] : [B*C][H_l][W_l][128]     problem-major output
  *   attn_amax : NULL, or per level NULL / a DEVICE float (zeroed by the caller) that is raised to max(attn[l]): the
  *               operand bound of the convolution that consumes the map (fod_conv2d_nhwc x_amax), without a pass over it

@@ -156,6 +156,81 @@ def test_highres_topk2000_head_matches_oracle():
     assert matched / max(rb.shape[0], 1) >= 0.97
 
 
+def _match_by_class(rb, rs, rc, gb, gs, gc, num_classes):
+    """Fraction of oracle detections reproduced, matched class by class (different classes may propose the same box)."""
+    if rb.shape[0] == 0:
+        return 1.0
+    matched = 0.0
+    for c in range(num_classes):
+        k = int((rc == c).sum())
+        if k == 0:
+            continue
+        if int((gc == c).sum()) == 0:
+            continue
+        matched += _match(rb[rc == c], rs[rc == c], gb[gc == c], gs[gc == c]) * k
+    return matched / rb.shape[0]
+
+
+def test_config3_ten_way_ten_shot_head_matches_oracle():
+    """BASELINE.json configs[2]: 10 support classes x 10 shots against a batch of 640x640 queries (B = 4 here so that
+    the CPU oracle stays within seconds; the batch-32 run is timed by bench.py).  10 classes x 3 levels = 30 tap sets,
+    i.e. five launches of the correlation kernel with class_begin > 0, ten per-class relation biases, and up to
+    10 x 320 rows per image in the class-wise final NMS.  Every (image, class) proposal list and the final detections
+    of two images are compared with the oracle."""
+    sd = head_state_dict()
+    model = _model()
+    class_ids = [11, 3, 7, 2, 19, 5, 13, 17, 23, 29]
+    C = len(class_ids)
+    protos = synth.prototypes(class_ids, 10, 19)
+    model.set_prototypes(protos)
+    B, H, W = 4, 640, 640
+    feats = synth.features(B, H, W, 191)
+    (ob, os_, ocls, oc), tr = model.head({k: v.cuda() for k, v in feats.items()}, [(H, W)] * B, [(H, W)] * B, want_trace=True)
+    assert tr["proposals"].count.shape[0] == B * C
+    for b in (0, 3):
+        fb = {k: v[b:b + 1] for k, v in feats.items()}
+        otr = {}
+        rb, rs, rc = O.detect_image(fb, protos, sd, (H, W), CFG, None, otr)
+        for c in range(C):
+            pc = otr["per_class"][c]
+            p = b * C + c
+            n = int(tr["proposals"].count[p])
+            assert abs(n - pc["proposals"].shape[0]) <= 2, (b, c, n, pc["proposals"].shape[0])
+            assert _match(pc["proposals"], pc["objectness"], tr["proposals"].boxes[p, :n].cpu(),
+                          tr["proposals"].scores[p, :n].cpu()) >= 0.98, (b, c)
+            # per-ROI scores of this class: the class's own folded bias was used
+            assert _match(pc["det_boxes"], pc["det_scores"], tr["det_boxes"][p, :n].cpu(), tr["det_scores"][p, :n].cpu()) >= 0.97, (b, c)
+        m = int(oc[b])
+        assert abs(m - rb.shape[0]) <= 2
+        gb, gs, gc = ob[b, :m].cpu(), os_[b, :m].cpu(), ocls[b, :m].cpu()
+        assert set(gc.tolist()) <= set(range(C))
+        assert _match_by_class(rb, rs, rc, gb, gs, gc, C) >= 0.97
+
+
+def test_config4_highres_batch16_topk2000_matches_oracle():
+    """BASELINE.json configs[3] at its batch size: 16 queries of 1333x800 (padded 800x1344, M = 22 050),
+    PRE/POST_NMS_TOPK_TEST 2000; images 0 and 15 against the oracle."""
+    sd = head_state_dict()
+    model = _model("MODEL.CENTERNET.PRE_NMS_TOPK_TEST", 2000, "MODEL.CENTERNET.POST_NMS_TOPK_TEST", 2000)
+    cfg = O.HeadConfig(pre_nms_topk=2000, post_nms_topk=2000)
+    protos = synth.prototypes([5], 5, 23)
+    model.set_prototypes(protos)
+    B, H, W = 16, 800, 1344
+    feats = synth.features(B, H, W, 223)
+    (ob, os_, ocls, oc), tr = model.head({k: v.cuda() for k, v in feats.items()}, [(H, W)] * B, [(H, W)] * B, want_trace=True)
+    for b in (0, 15):
+        otr = {}
+        rb, rs, rc = O.detect_image({k: v[b:b + 1] for k, v in feats.items()}, protos, sd, (H, W), cfg, None, otr)
+        pc = otr["per_class"][0]
+        n = int(tr["proposals"].count[b])
+        assert pc["cand_boxes"].shape[0] > 4000
+        assert abs(n - pc["proposals"].shape[0]) <= 2
+        assert _match(pc["proposals"], pc["objectness"], tr["proposals"].boxes[b, :n].cpu(), tr["proposals"].scores[b, :n].cpu()) >= 0.98
+        m = int(oc[b])
+        assert abs(m - rb.shape[0]) <= 2
+        assert _match(rb, rs, ob[b, :m].cpu(), os_[b, :m].cpu()) >= 0.97
+
+
 def test_batched_call_equals_separate_calls():
     model = _model()
     model.set_prototypes(synth.prototypes([1], 5, 7))
@@ -203,6 +278,14 @@ def test_full_size_batch64_properties():
                                        CFG.nms_thresh_test)
                 assert keep.tolist() == list(range(m))
         assert total > B          # the synthetic scene produces detections everywhere
+        sd_cpu = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        protos25 = synth.prototypes([1], 25, 7)
+        for b in (0, 37, 63):     # the oracle on the features the model's own extractor produced for this image
+            fb = {k: v[b:b + 1].cpu().contiguous() for k, v in feats.items()}
+            rb, rs, rc = O.detect_image(fb, protos25, sd_cpu, (H, W), CFG)
+            m = int(oc[b])
+            assert abs(m - rb.shape[0]) <= 2, (b, m, rb.shape[0])
+            assert _match(rb, rs, ob[b, :m].cpu(), os_[b, :m].cpu()) >= 0.97, b
         for b in (0, 37, 63):     # the same image alone, from the same features: same detections
             fb = {k: v[b:b + 1].contiguous(memory_format=torch.channels_last) for k, v in feats.items()}
             sb, ss, _, scount = model.head(fb, [(H, W)], [(H, W)])

@@ -219,6 +219,55 @@ def test_correlate_levels_tensor_core_matches_oracle(sizes, B, C):
                 assert_close(got[b * C + c], ref[0], what=f"attn level{l} b{b} c{c}")
 
 
+@pytest.mark.parametrize("C", [7, 10])
+def test_correlate_levels_many_classes_matches_oracle(C):
+    """BASELINE.json configs[2] is 10-way: the taps ride in the launch parameters six sets at a time, so C > 2 takes
+    several launches with class_begin > 0 (three levels) - every (image, class) map against the oracle."""
+    sd = head_state_dict()
+    sizes, B = ((20, 24), (10, 12), (5, 6)), 2
+    qs = [synth.tensor((B, 128, h, w), 350 + h + 3 * i, -1.5, 1.5) for i, (h, w) in enumerate(sizes)]
+    protos = [synth.tensor((C, 128, 8 // (i + 1) + 1, 8 // (i + 1) + 2), 360 + i, -0.6, 0.8) for i in range(len(sizes))]
+    taps = [ops.support_taps(p.to(DEV)).cpu() for p in protos]
+    outs = ops.correlate_levels([q.to(DEV) for q in qs], taps, sd["conv3.weight"].to(DEV), sd["conv3.bias"].to(DEV))
+    torch.cuda.synchronize()
+    for l, (q, proto) in enumerate(zip(qs, protos)):
+        got = outs[l].cpu()
+        assert got.shape == (B * C, 128) + tuple(sizes[l])
+        for b in range(B):
+            for c in range(C):
+                k11, k13, k31 = O.support_taps(proto[c:c + 1])
+                ref = O.correlate_level(q[b:b + 1], k11, k13, k31, sd["conv3.weight"], sd["conv3.bias"])
+                assert_close(got[b * C + c], ref[0], what=f"attn level{l} b{b} c{c}")
+    # a single level takes six classes per launch: same maps
+    one = ops.correlate_levels([qs[0].to(DEV)], taps[:1], sd["conv3.weight"].to(DEV), sd["conv3.bias"].to(DEV))[0]
+    assert torch.equal(one, outs[0])
+
+
+def test_correlate_levels_is_reentrant_across_streams():
+    """Two episodes correlated concurrently on two streams must not see each other's taps (the taps are launch
+    parameters, not a device symbol)."""
+    sd = head_state_dict()
+    w3, b3 = sd["conv3.weight"].to(DEV), sd["conv3.bias"].to(DEV)
+    B, C = 8, 2
+    qs = [synth.tensor((B, 128, 80, 80), 370, -1.5, 1.5).to(DEV), synth.tensor((B, 128, 40, 40), 371, -1.5, 1.5).to(DEV)]
+    tap_sets = []
+    for e in range(2):
+        protos = [synth.tensor((C, 128, 9, 10), 380 + 10 * e + i, -0.6, 0.8) for i in range(2)]
+        tap_sets.append([ops.support_taps(p.to(DEV)).cpu() for p in protos])
+    ref = [[t.clone() for t in ops.correlate_levels(qs, tp, w3, b3)] for tp in tap_sets]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    for rnd in range(4):
+        got = [None, None]
+        for e in range(2):
+            with torch.cuda.stream(streams[e]):
+                got[e] = ops.correlate_levels(qs, tap_sets[e], w3, b3)
+        torch.cuda.synchronize()
+        for e in range(2):
+            for a, b in zip(got[e], ref[e]):
+                assert torch.equal(a, b), (rnd, e)
+
+
 def test_correlate_golden_reference_maps():
     g = golden("full_small")
     sd = head_state_dict()
@@ -320,10 +369,38 @@ def test_relation_head_tensor_core_multi_class_ragged_counts():
             assert float(ds[p, n:].abs().max()) == 0.0
 
 
+def test_relation_head_ten_classes_per_class_bias():
+    """C = 10 (BASELINE.json configs[2]): every problem must pick its own class's folded bias."""
+    sd = head_state_dict()
+    B, C, cap = 2, 10, 130
+    P = B * C
+    counts = torch.tensor([(37 * p + 5) % (cap + 1) for p in range(P)], dtype=torch.int32)
+    pooled = synth.tensor((P, cap, 64, 128), 171, -1.0, 1.5)
+    bx = _boxes(P * cap, 172, 30.0, 280.0, 8.0, 150.0).reshape(P, cap, 4)
+    sup = synth.tensor((C, 128, 8, 8), 173, -1.0, 1.0)
+    w_fold, w_out, b_out = fold.fold_relation_weights(sd)
+    bias = fold.fold_class_bias(sd, sup)
+    db, ds, logits, deltas = ops.relation_head(pooled.to(DEV), ops.split_tf32(w_fold.to(DEV)), bias.to(DEV), w_out.to(DEV),
+                                               b_out.to(DEV), bx.to(DEV), counts.to(DEV), C, CFG.bbox_reg_weights,
+                                               want_raw=True)
+    torch.cuda.synchronize()
+    for p in range(P):
+        n = int(counts[p])
+        if n == 0:
+            continue
+        x = pooled[p, :n].reshape(n, 8, 8, 128).permute(0, 3, 1, 2).contiguous()
+        ref_logits, ref_deltas = O.relation_head(x, sup[p % C:p % C + 1], sd)
+        assert_close(logits[p, :n].cpu(), ref_logits, what=f"logits p{p}")
+        assert_close(deltas[p, :n].cpu(), ref_deltas, atol=2e-5, what=f"deltas p{p}")
+        sc, bb = O.score_and_decode(ref_logits, ref_deltas, bx[p, :n], CFG)
+        assert_close(ds[p, :n].cpu(), sc, what=f"scores p{p}")
+        assert_close(db[p, :n].cpu(), bb, atol=2e-3, what=f"boxes p{p}")
+
+
 # ----------------------------------------------------------------------------------------- final detect
-@pytest.mark.parametrize("C", [1, 3])
-def test_final_detect_bit_exact(C):
-    B, cap = 3, 64
+@pytest.mark.parametrize("C,cap", [(1, 64), (3, 64), (10, 320)])
+def test_final_detect_bit_exact(C, cap):
+    B = 3
     P = B * C
     boxes = _boxes(P * cap, 300, 10.0, 300.0, 10.0, 120.0).reshape(P, cap, 4)      # some stick out of the image
     scores = synth.tensor((P, cap), 301, 0.0, 1.0)
@@ -332,6 +409,8 @@ def test_final_detect_bit_exact(C):
     boxes[0, 4, 2] = float("inf")
     scores[1 % P, 5] = float("inf")
     counts = torch.tensor([(cap - 7 * p) % (cap + 1) for p in range(P)], dtype=torch.int32)
+    if C == 10:
+        counts[::3] = cap      # 10-way: full problems too (up to 3 200 rows per image enter the class-wise NMS)
     image_hw = torch.tensor([[256, 320]] * B, dtype=torch.int32)
     out_hw = torch.tensor([[256, 320], [300, 500], [128, 160]], dtype=torch.int32)
     for sthr, nthr, topk in ((0.0, 0.9, 100), (0.3, 0.5, 10)):
