@@ -1,6 +1,6 @@
 """Host-side mirror of the reference's modeling interface for the hot path
 (fewx/modeling/__init__.py:2, fewx/modeling/fsod/__init__.py:1-6)."""
-from ..compat import BACKBONE_REGISTRY, META_ARCH_REGISTRY, PROPOSAL_GENERATOR_REGISTRY
+from ..compat import BACKBONE_REGISTRY, META_ARCH_REGISTRY, PROPOSAL_GENERATOR_REGISTRY, resolve
 from .backbone import build_backbone, build_fcos_vovnet_fpn_backbone
 from .centernet import CenterNet, CenterNetHead
 from .fsod_cen import CenterNet2Detector, PendingBatch
@@ -12,7 +12,7 @@ from .roi_heads import ROI_HEADS_REGISTRY, CustomCascadeROIHeads, build_roi_head
 def build_model(cfg):
     """d2!/modeling/meta_arch/build.py:16-25."""
     import torch
-    model = META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)
+    model = resolve(META_ARCH_REGISTRY, cfg.MODEL.META_ARCHITECTURE)(cfg)
     model.to(torch.device(cfg.MODEL.DEVICE))
     return model
 

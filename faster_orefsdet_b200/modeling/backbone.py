@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import ops
-from ..compat import BACKBONE_REGISTRY, ShapeSpec
+from ..compat import Backbone, register, resolve, BACKBONE_REGISTRY, ShapeSpec
 from . import tcconv
 
 _STAGE_SPECS = {
@@ -188,7 +188,7 @@ class _OSAStage(nn.Sequential):
             self.add_module(n, _OSAModule(concat_ch, stage_ch, concat_ch, layers, n, identity=True))
 
 
-class VoVNet(nn.Module):
+class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(backbone, Backbone) (d2!/modeling/backbone/build.py:32)
     def __init__(self, cfg, input_ch: int, out_features: List[str]):
         super().__init__()
         stem_ch, conv_ch, out_ch, layers, blocks = _STAGE_SPECS[cfg.MODEL.VOVNET.CONV_BODY]
@@ -329,7 +329,7 @@ class VoVNet(nn.Module):
                 for n in self._out_features}
 
 
-class FPN(nn.Module):
+class FPN(Backbone):
     """Top-down pathway with lateral 1x1 and output 3x3 convs, "sum" fusion, no top block
     (MODEL.FCOS.TOP_LEVELS = 0, log:264)."""
 
@@ -411,7 +411,7 @@ class FPN(nn.Module):
                 for n in self._out_features}
 
 
-@BACKBONE_REGISTRY.register()
+@register(BACKBONE_REGISTRY)
 def build_fcos_vovnet_fpn_backbone(cfg, input_shape: ShapeSpec):
     if cfg.MODEL.FCOS.TOP_LEVELS != 0:
         raise NotImplementedError("MODEL.FCOS.TOP_LEVELS != 0 (P6/P7) is not used by finetune_vovnet.yaml")
@@ -422,4 +422,4 @@ def build_fcos_vovnet_fpn_backbone(cfg, input_shape: ShapeSpec):
 def build_backbone(cfg, input_shape: ShapeSpec = None):
     if input_shape is None:
         input_shape = ShapeSpec(channels=len(cfg.MODEL.PIXEL_MEAN))
-    return BACKBONE_REGISTRY.get(cfg.MODEL.BACKBONE.NAME)(cfg, input_shape)
+    return resolve(BACKBONE_REGISTRY, cfg.MODEL.BACKBONE.NAME)(cfg, input_shape)

@@ -21,7 +21,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .. import ops
-from ..compat import PROPOSAL_GENERATOR_REGISTRY, Boxes, Instances, ShapeSpec
+from ..compat import register, resolve, PROPOSAL_GENERATOR_REGISTRY, Boxes, Instances, ShapeSpec
 from . import tcconv
 
 
@@ -138,7 +138,7 @@ class RawProposals:
     cand_count: torch.Tensor   # [P] int32
 
 
-@PROPOSAL_GENERATOR_REGISTRY.register()
+@register(PROPOSAL_GENERATOR_REGISTRY)
 class CenterNet(nn.Module):
     def __init__(self, cfg, input_shape: Dict[str, ShapeSpec]):
         super().__init__()

@@ -27,7 +27,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from .. import _lib, ops
-from ..compat import META_ARCH_REGISTRY, Boxes, ImageList, Instances
+from ..compat import register, resolve, META_ARCH_REGISTRY, Boxes, ImageList, Instances
 from .backbone import build_backbone
 from .centernet import CenterNet, RawProposals  # noqa: F401  (registers "CenterNet")
 from .prototypes import (LEVELS, PrototypeBank, SM_Block, SupportCache, bank_from_support_dict, broadcast_bank, load_bank,
@@ -54,10 +54,10 @@ class PendingBatch:
 
 
 def build_proposal_generator(cfg, input_shape):
-    return PROPOSAL_GENERATOR_REGISTRY.get(cfg.MODEL.PROPOSAL_GENERATOR.NAME)(cfg, input_shape)
+    return resolve(PROPOSAL_GENERATOR_REGISTRY, cfg.MODEL.PROPOSAL_GENERATOR.NAME)(cfg, input_shape)
 
 
-@META_ARCH_REGISTRY.register()
+@register(META_ARCH_REGISTRY)
 class CenterNet2Detector(nn.Module):
     def __init__(self, cfg, pos_encoding=True):
         super().__init__()
@@ -116,6 +116,10 @@ class CenterNet2Detector(nn.Module):
         PendingBatch must be collected or abandoned: the input ring holds ``U8_RING`` device buffers."""
         if self.training or not self.USE_CUDA_GRAPH:
             return batched_inputs
+        with torch.cuda.device(self.device):
+            return self._submit(batched_inputs, do_postprocess)
+
+    def _submit(self, batched_inputs, do_postprocess):
         self.init_model()
         if self._bank is None:
             raise _lib.FodError("no support prototypes installed: call init_model() / set_prototypes() first")
@@ -172,8 +176,9 @@ class CenterNet2Detector(nn.Module):
     def forward(self, batched_inputs):
         """``batched_inputs``: list[dict] like the reference (fsod_cen.py:417), or a ``PendingBatch`` from ``submit``."""
         if not self.training:
-            self.init_model()
-            return self.inference(batched_inputs)
+            with torch.cuda.device(self.device):      # launches go to the model's device whatever the caller's current one
+                self.init_model()
+                return self.inference(batched_inputs)
         raise NotImplementedError("CenterNet2Detector: training (fsod_cen.py:156-308) is outside the inference hot path")
 
     # ------------------------------------------------------------------ prototypes

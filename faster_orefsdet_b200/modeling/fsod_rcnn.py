@@ -11,10 +11,10 @@ from __future__ import annotations
 
 from torch import nn
 
-from ..compat import META_ARCH_REGISTRY
+from ..compat import register, resolve, META_ARCH_REGISTRY
 
 
-@META_ARCH_REGISTRY.register()
+@register(META_ARCH_REGISTRY)
 class FsodRCNN(nn.Module):
     def __init__(self, cfg):
         super().__init__()

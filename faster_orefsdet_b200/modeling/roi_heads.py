@@ -21,13 +21,13 @@ import torch
 from torch import nn
 
 from .. import fold, ops
-from ..compat import Boxes, Instances, Registry, ShapeSpec
+from ..compat import register, resolve, Boxes, Instances, Registry, ShapeSpec
 
 ROI_HEADS_REGISTRY = Registry("ROI_HEADS")  # module-local, like fsod_roi_heads.py:33
 
 
 def build_roi_heads(cfg, input_shape):
-    return ROI_HEADS_REGISTRY.get(cfg.MODEL.ROI_HEADS.NAME)(cfg, input_shape)
+    return resolve(ROI_HEADS_REGISTRY, cfg.MODEL.ROI_HEADS.NAME)(cfg, input_shape)
 
 
 class FastRCNNConvFCHead(nn.Sequential):
@@ -63,7 +63,7 @@ class FastRCNNOutputLayers(nn.Module):
         self.test_topk_per_image = cfg.TEST.DETECTIONS_PER_IMAGE
 
 
-@ROI_HEADS_REGISTRY.register()
+@register(ROI_HEADS_REGISTRY)
 class CustomCascadeROIHeads(nn.Module):
     def __init__(self, cfg, input_shape: Dict[str, ShapeSpec]):
         super().__init__()
@@ -202,6 +202,17 @@ class DetectionInstances(Instances):
         return super().to(*args, **kwargs)
 
 
+def mirrored_instances(image_size, fields, host_fields) -> "DetectionInstances":
+    """DetectionInstances over ``fields`` (device) with ``host_fields`` as their completed host copies; the fields must
+    have equal lengths (not re-checked: the hot path builds one of these per image)."""
+    inst = DetectionInstances.__new__(DetectionInstances)
+    inst.__dict__["_image_size"] = image_size
+    inst.__dict__["_fields"] = fields
+    inst.__dict__["_host_mirror"] = host_fields
+    inst.__dict__["_mirror_stamps"] = {k: _field_stamp(v) for k, v in fields.items()}
+    return inst
+
+
 def pack_instances(boxes, scores, classes, count, image_sizes) -> List[Instances]:
     """Padded device outputs -> list[Instances] on the device, with ONE device-to-host transfer of the whole
     padded block ([B, K, 7] fp32) whose views ride along as the host mirror of every DetectionInstances
@@ -238,11 +249,7 @@ def instances_from_block(block: torch.Tensor, host: torch.Tensor, image_sizes) -
 
     out = []
     for b in range(B):
-        inst = DetectionInstances.__new__(DetectionInstances)     # the three fields have equal lengths by construction
-        inst.__dict__["_image_size"] = (int(image_sizes[b][0]), int(image_sizes[b][1]))
-        fields = {"pred_boxes": boxes_of(db[b]), "scores": ds[b], "pred_classes": dc[b]}
-        inst.__dict__["_fields"] = fields
-        inst.__dict__["_host_mirror"] = {"pred_boxes": boxes_of(hb[b]), "scores": hs[b], "pred_classes": hc[b]}
-        inst.__dict__["_mirror_stamps"] = {k: _field_stamp(v) for k, v in fields.items()}
-        out.append(inst)
+        out.append(mirrored_instances((int(image_sizes[b][0]), int(image_sizes[b][1])),
+                                      {"pred_boxes": boxes_of(db[b]), "scores": ds[b], "pred_classes": dc[b]},
+                                      {"pred_boxes": boxes_of(hb[b]), "scores": hs[b], "pred_classes": hc[b]}))
     return out

@@ -23,6 +23,7 @@ _vp = ctypes.c_void_p
 
 
 def _stream() -> _vp:
+    """torch's current stream of the CURRENT device; ``_chk`` makes sure the tensors live there."""
     return _vp(torch.cuda.current_stream().cuda_stream)
 
 
@@ -35,6 +36,10 @@ def _chk(t: Tensor, dtype, name: str) -> Tensor:
         raise _lib.FodError(f"{name}: expected a CUDA tensor (the detection head has no CPU path)")
     if t.dtype != dtype:
         raise _lib.FodError(f"{name}: expected {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # the launch goes to the current device's stream and the library sizes its grids from the current device
+        raise _lib.FodError(f"{name}: tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}; "
+                            f"wrap the call in torch.cuda.device({t.device.index})")
     return t
 
 

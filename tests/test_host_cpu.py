@@ -130,3 +130,37 @@ def test_binary_prototype_file_round_trip(tmp_path):
     with open(path, "r+b") as f:                                       # truncated file is refused
         f.truncate(1000)
     assert load_bank(path, "cpu") is None
+
+
+def test_detection_instances_host_mirror_is_used_only_while_the_fields_are_untouched():
+    """Instances.to("cpu") may return the host copy made by the detector's single transfer only while the
+    fields are the ones it was built with."""
+    from faster_orefsdet_b200.compat import Boxes, Instances
+    from faster_orefsdet_b200.modeling.roi_heads import DetectionInstances, mirrored_instances
+
+    def make():
+        dev = {"pred_boxes": Boxes(torch.arange(8.0).reshape(2, 4)), "scores": torch.tensor([0.9, 0.8]),
+               "pred_classes": torch.zeros(2, dtype=torch.int64)}
+        host = {"pred_boxes": Boxes(torch.arange(8.0).reshape(2, 4) + 100), "scores": torch.tensor([0.9, 0.8]) + 100,
+                "pred_classes": torch.zeros(2, dtype=torch.int64)}
+        return mirrored_instances((10, 12), dev, host)
+
+    inst = make()
+    assert isinstance(inst, Instances) and isinstance(inst, DetectionInstances) and len(inst) == 2
+    for target in ("cpu", torch.device("cpu")):
+        h = inst.to(target)
+        assert float(h.scores[0]) == pytest.approx(100.9) and h.image_size == (10, 12) and type(h) is Instances
+    assert float(inst.to(device="cpu", non_blocking=True).scores[0]) == pytest.approx(100.9)
+    # any other target, a replaced / added / removed field or an in-place edit: the plain field-by-field path
+    assert float(inst.to(torch.float64 if False else "cpu", ).scores[0]) == pytest.approx(100.9)
+    inst.scores = torch.tensor([0.5, 0.4])
+    assert float(inst.to("cpu").scores[0]) == pytest.approx(0.5)
+    inst = make()
+    inst.pred_masks = torch.zeros(2, 3)
+    assert inst.to("cpu").has("pred_masks") and float(inst.to("cpu").scores[0]) == pytest.approx(0.9)
+    inst = make()
+    inst.pred_boxes.tensor.mul_(2.0)          # Boxes.scale() edits in place
+    assert float(inst.to("cpu").pred_boxes.tensor[1, 3]) == pytest.approx(14.0)
+    inst = make()
+    inst.remove("pred_classes")
+    assert not inst.to("cpu").has("pred_classes")
