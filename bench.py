@@ -25,11 +25,19 @@ import torch  # noqa: E402
 
 from faster_orefsdet_b200 import synth  # noqa: E402
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one conv_tc_kernel launch (ncu --set full, batch 64), keyed by
-# (H, W, Cin, Cout, ksize, stride); profiles/r1_ncu_v3_summary.md
-NCU_CONV_TRAFFIC = {(320, 320, 64, 64, 3, 1): 1.678e9 + 1.633e9,      # stem_2: algorithmic 2 x 1.678 GB (read x, write y)
-                    (80, 80, 128, 128, 3, 1): 210.4e6 + 162.2e6}
+def _ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels, from the committed summary
+    of the `ncu --set full` captures (profiles/traffic.json, written by tools/ncu_summary.py next to the capture it
+    came from): {"kernels": {name: bytes}, "conv_layers": {"H,W,Cin,Cout,k,s": bytes}, "batch": 64, "source": ...}."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return {"kernels": {}, "conv_layers": {}, "batch": None, "source": None}
+    with open(p) as f:
+        return json.load(f)
 
+
+HEAD_KERNELS = ("correlate_levels", "decode_topk", "nms_proposals", "roi_align", "relation_head", "roi_relation_head",
+                "final_detect")
 METRIC = "query_images_per_sec"
 UNIT = "images/s"
 IMG = 640
@@ -300,6 +308,7 @@ def run_gpu_arm(args):
         model.USE_CUDA_GRAPH = graph_mode
         ksum = timer.summary()
         launches = timer.launches
+        layers = timer.conv_layers()
 
         # ---- end-to-end through the public API: host images in, host detections out.  Every step copies its 64 pinned
         # host images to the device and reads its detections back, all inside the timed region.  `pipelined`: the serving
@@ -340,16 +349,100 @@ def run_gpu_arm(args):
             e2e[mode] = time.perf_counter() - t0
         e2e_s = e2e["pipelined"]
 
-    t = torch.tensor([ms, e2e_s * 1e3, e2e["serial"] * 1e3], dtype=torch.float64, device=dev)
+        # ---- the other BASELINE.json configurations as sub-records (N = 1 only; outside the headline region; parity for
+        # the same shapes is pinned by tests/test_model_gpu.py::test_config3_* / test_config4_*)
+        cfg_records = {}
+        if world == 1 and not args.no_configs:
+            pg = model.proposal_generator
+            keep = (pg.pre_nms_topk_test, pg.post_nms_topk_test)
+            for name, (cb, ch, cw, ways, shots, pre, post) in (
+                    ("C3", (32, IMG, IMG, 10, 10, keep[0], keep[1])),      # 10 ways x 10 shots, batch 32, 640x640
+                    ("C4", (16, 800, 1344, 1, SHOTS, 2000, 2000))):        # 1333x800 (padded 800x1344), top-k 2000, batch 16
+                pg.pre_nms_topk_test, pg.post_nms_topk_test = pre, post
+                model.set_prototypes(synth.prototypes(list(range(1, ways + 1)), shots, 7))
+                xs = [torch.stack([synth.ore_image(ch, cw, 5000 + 31 * k + i) for i in range(4)]).repeat(cb // 4, 1, 1, 1).to(dev)
+                      for k in range(2)]
+                for k in range(2):          # distinct content per slot
+                    for i in range(cb):
+                        xs[k][i] = torch.roll(xs[k][i], shifts=(5 * (i // 4), 11 * (i // 4)), dims=(1, 2))
+                szs = [(ch, cw)] * cb
+                for k in range(3):
+                    model.detect_from_uint8(xs[k % 2], szs, szs)
+                torch.cuda.synchronize()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_cfg = max(args.steps // 2, 3)
+                c0.record()
+                for k in range(n_cfg):
+                    res = model.detect_from_uint8(xs[k % 2], szs, szs)
+                c1.record()
+                torch.cuda.synchronize()
+                cms = c0.elapsed_time(c1) / n_cfg
+                # head kernels of this configuration, eagerly with events (same method as the headline's per-kernel table)
+                model.USE_CUDA_GRAPH = False
+                model.detect_from_uint8(xs[0], szs, szs)
+                timer.records, timer.enabled = {}, True
+                for k in range(3):
+                    model.detect_from_uint8(xs[k % 2], szs, szs)
+                torch.cuda.synchronize()
+                timer.enabled = False
+                model.USE_CUDA_GRAPH = graph_mode
+                hk = {n: tot / 3 for n, (tot, cnt) in timer.summary().items() if n in HEAD_KERNELS}
+                cfg_records[name] = {"workload": f"{ways}-way {shots}-shot, batch {cb} x {ch}x{cw}, PRE/POST_NMS_TOPK {pre}/{post}",
+                                     "ms_per_step": cms, "images_per_s": cb / (cms * 1e-3), "steps": n_cfg,
+                                     "detections": int(res[3].sum()), "head_ms_per_step": sum(hk.values()), "head_kernels_ms": hk}
+                del xs
+            pg.pre_nms_topk_test, pg.post_nms_topk_test = keep
+            model.set_prototypes(synth.prototypes([1], SHOTS, 7))
+
+        # ---- BASELINE.json configs[4] as written (strong scaling): ONE global batch of 256 queries sharded 256 / G with the
+        # InferenceSampler formula (d2!/data/samplers/distributed_sampler.py:191-194), prototypes broadcast by rank 0 and the
+        # padded detections of all ranks gathered (fewx/evaluation/coco_evaluation.py:131-137) INSIDE the timed region
+        strong = None
+        if not args.no_strong:
+            from faster_orefsdet_b200 import dist_utils
+            G = 256
+            lo, hi = dist_utils.shard_range(G, rank, world)
+            nb = hi - lo
+            shard_sets = [torch.stack(_images(G, 7000 + 100 * k)[lo:hi]).to(dev) for k in range(2)]
+            ssz = [(IMG, IMG)] * nb
+
+            def strong_job(n_steps):
+                if world > 1:
+                    model.sync_prototypes(0)
+                tot = None
+                for k in range(n_steps):
+                    ob, os_, ocls, oc = model.detect_from_uint8(shard_sets[k % 2], ssz, ssz)
+                    if world > 1:
+                        ob, os_, ocls, oc = dist_utils.gather_detections(ob, os_, ocls, oc, G)
+                    tot = oc
+                return tot
+
+            strong_job(3)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_strong = max(args.steps // 2, 3)
+            s0.record()
+            tot = strong_job(n_strong)
+            s1.record()
+            barrier()
+            strong_ms = s0.elapsed_time(s1)
+            strong = {"n_det": int(tot.sum()), "n_img": int(tot.numel()), "batch_per_gpu": nb, "steps": n_strong, "ms": strong_ms}
+            del shard_sets
+
+    vals = [ms, e2e_s * 1e3, e2e["serial"] * 1e3, strong["ms"] if strong else 0.0]
+    t = torch.tensor(vals, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms, e2e_serial_ms = float(t[0]), float(t[1]), float(t[2])
+    if strong:
+        strong["ms"] = float(t[3])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peak, tensor_peak, peak_src = _peaks()
+    traffic = _ncu_traffic()
     # algorithmic bytes per launch (DESIGN.md "Measurement"), 1-way, B images of 640x640
     lvl_px = [6400, 1600, 400]
     alg = {
@@ -370,7 +463,6 @@ def run_gpu_arm(args):
         kernels[n] = {"ms_per_step": tot_ms / args.steps, "launches_per_step": cnt / args.steps,
                       "achieved_gbs": gbs, "frac": gbs / peak}
     # the convolution kernel: per layer shape, and the launch with the largest share of the step
-    layers = timer.conv_layers()
     conv_ms = sum(v[0] for v in layers.values()) / args.steps
     conv_flops = sum(v[2] * v[1] for v in layers.values()) / args.steps
     top = max(layers, key=lambda t: layers[t][0]) if layers else None
@@ -382,7 +474,8 @@ def run_gpu_arm(args):
         # bf16 rate: the ceiling of this arithmetic is peak / 3
         conv_roof = {"bound": "tensor", "kernel": "conv_tc_kernel (fod_conv2d_nhwc)",
                      "launch": "N%d %dx%d %d->%d k%d s%d" % top, "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s",
-                     "frac": ach / tensor_peak, "traffic": NCU_CONV_TRAFFIC.get(top[1:]) if B == BATCH else None,
+                     "frac": ach / tensor_peak,
+                     "traffic": traffic["conv_layers"].get(",".join(str(v) for v in top[1:])) if B == traffic["batch"] else None,
                      "algorithmic_flops": fl, "issued_f16_tflops": 3 * ach, "frac_of_split_ceiling": ach / (tensor_peak / 3),
                      "all_layers": {"ms_per_step": conv_ms, "launches_per_step": sum(v[1] for v in layers.values()) / args.steps,
                                     "achieved": conv_flops / (conv_ms * 1e-3) / 1e12, "frac": conv_flops / (conv_ms * 1e-3) / 1e12 / tensor_peak},
@@ -390,7 +483,7 @@ def run_gpu_arm(args):
         extractor["conv2d_nhwc"]["fp32_tflops"] = conv_flops / (conv_ms * 1e-3) / 1e12
     # DRAM traffic per launch of the same kernels from the committed `ncu --set full` captures
     # (dram__bytes_read.sum + dram__bytes_write.sum, batch 64, 1-way; profiles/r1_ncu_v2_summary.md)
-    ncu_traffic = {"correlate_levels": 504.9e6, "relation_head": 550.6e6, "roi_align": 686.9e6} if B == BATCH else {}
+    ncu_traffic = traffic["kernels"] if B == traffic["batch"] else {}
     dom = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
     head_ms = sum(k["ms_per_step"] for k in kernels.values())
     head_alg_bytes = 13.2e6 * B
@@ -419,12 +512,15 @@ def run_gpu_arm(args):
                 "serial": {"value": total_images / (e2e_serial_ms * 1e-3), "unit": UNIT,
                            "api": "model(batched_inputs) alone: copies, kernels, transfer and Instances of one batch in series"}},
         "gpu_launches": launches,
-        # dominant kernel of the step: the tensor-core convolution (its largest launch); the head's memory-bound
-        # kernels follow under "head" with their own HBM roofline fractions
-        "roofline": conv_roof if conv_roof is not None and conv_ms > kernels[dom]["ms_per_step"] else
-                    {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+        # The path north_star names is the HEAD: `roofline` is its dominant kernel (largest share of the head's time)
+        # against the HBM roof; the step-dominant kernel overall is the feature extractor's tensor-core convolution
+        # (an "(f)" row of SURVEY section 8), reported under `step_dominant` against the tensor roof.
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                      "frac": kernels[dom]["frac"], "traffic": ncu_traffic.get(dom), "algorithmic_bytes": alg[dom],
-                     "peak_source": peak_src},
+                     "ms_per_launch": kernels[dom]["ms_per_step"] / max(kernels[dom]["launches_per_step"], 1),
+                     "scope": "dominant kernel of the support-guided head (the hot path)", "peak_source": peak_src,
+                     "traffic_source": traffic.get("source")},
+        "step_dominant": conv_roof,
         "head": {"ms_per_step": head_ms, "images_per_s": B / (head_ms * 1e-3),
                  "achieved_gbs": head_alg_bytes / (head_ms * 1e-3) / 1e9, "frac": head_alg_bytes / (head_ms * 1e-3) / 1e9 / peak,
                  "share_of_step": head_ms / (ms / args.steps), "kernels": kernels,
@@ -434,6 +530,16 @@ def run_gpu_arm(args):
         "feature_extractor": extractor,
         "clocks": clk,
     }
+    if cfg_records:
+        line["configs"] = cfg_records
+    if strong:
+        sm = strong["ms"] / strong["steps"]
+        line["strong"] = {"workload": "BASELINE.json configs[4]: one global batch of 256 synthetic 640x640 queries sharded 256/G "
+                                      "(InferenceSampler formula), NCCL prototype broadcast + all-gather of the padded "
+                                      "detections inside the timed region",
+                          "global_batch": 256, "batch_per_gpu": strong["batch_per_gpu"], "steps": strong["steps"],
+                          "ms_per_step": sm, "images_per_s": 256 / (sm * 1e-3), "scaling": "strong",
+                          "images_gathered": strong["n_img"], "detections": strong["n_det"]}
     if cpu_rate is not None:
         line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                                 "sample": f"{args.cpu_images} images 640x640 after 2 warm-up, batch-1 loop, oracle head + "
@@ -452,6 +558,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--cpu-images", type=int, default=200)      # ~12 s of host work on 16 cores
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 sub-records")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (global batch 256) sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -491,6 +491,66 @@ def test_cuda_graph_replay_equals_eager_launches():
         assert torch.equal(a, b)
 
 
+def test_submodule_weight_reload_refreshes_bias_and_graph():
+    """weights replaced through a SUB-module (model.roi_heads.load_state_dict) or edited in place must
+    invalidate the captured graph and the folded per-class bias of a bank installed with set_prototypes."""
+    model = _model()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    model.set_prototypes(synth.prototypes([1, 2], 5, 7))
+    sizes = [(128, 160)] * 2
+    x = torch.stack([synth.ore_image(128, 160, 4100 + i) for i in range(2)]).cuda()
+    model.USE_CUDA_GRAPH = True
+    first = [t.clone() for t in model.detect_from_uint8(x, sizes, sizes)]
+    g0, bias0 = model._graph["graph"], model._bank.bias_cls.clone()
+    sd = {k: v * 1.5 if k in ("conv2.weight", "conv2.bias", "box_head.0.fc1.bias") else v for k, v in model.roi_heads.state_dict().items()}
+    model.roi_heads.load_state_dict(sd)                       # sub-module path: the model's own load_state_dict is not involved
+    model.init_model()
+    got = [t.clone() for t in model.detect_from_uint8(x, sizes, sizes)]
+    assert model._graph["graph"] is not g0
+    assert not torch.equal(model._bank.bias_cls, bias0)
+    assert_close(model._bank.bias_cls, model.roi_heads.class_bias(model._bank.support_mean), rtol=0, atol=0, what="bias")
+    model.USE_CUDA_GRAPH = False
+    for a, b in zip(got, model.detect_from_uint8(x, sizes, sizes)):
+        assert torch.equal(a, b)
+    assert not torch.equal(got[1], first[1])                  # the scores moved with the weights
+    # in-place edit of a tower weight: new graph as well
+    model.USE_CUDA_GRAPH = True
+    g1 = model._graph["graph"] if model._graph["key"] == model._graph_key(2, 128, 160) else None
+    model.detect_from_uint8(x, sizes, sizes)
+    g1 = model._graph["graph"]
+    with torch.no_grad():
+        model.proposal_generator.centernet_head.agn_hm.bias.add_(0.25)
+    got = [t.clone() for t in model.detect_from_uint8(x, sizes, sizes)]
+    assert model._graph["graph"] is not g1
+    model.USE_CUDA_GRAPH = False
+    for a, b in zip(got, model.detect_from_uint8(x, sizes, sizes)):
+        assert torch.equal(a, b)
+
+
+def test_abandoned_batch_frees_its_ring_slot():
+    model = _model()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    model.set_prototypes(synth.prototypes([1], 5, 7))
+    batch = [{"image": synth.ore_image(128, 160, 4200 + i).pin_memory()} for i in range(2)]
+    ref = model(batch)
+    a, b = model.submit(batch), model.submit(batch)
+    with pytest.raises(Exception, match="in flight"):
+        model.submit(batch)
+    model.abandon(a)
+    c = model.submit(batch)
+    with pytest.raises(Exception, match="collected or abandoned"):
+        model(a)
+    for pend in (b, c):
+        for x, y in zip(ref, model(pend)):
+            assert torch.equal(x["instances"].scores, y["instances"].scores)
+    # device-resident uint8 inputs go through the same staging path, ordered behind their producer on the current stream
+    dev_batch = [{"image": (d["image"].cuda() + 0)} for d in batch]
+    for x, y in zip(ref, model(dev_batch)):
+        assert torch.equal(x["instances"].scores, y["instances"].scores)
+
+
 def test_tensor_core_backbone_matches_reference_vovnet_fpn():
     """The feature extractor on the tensor-core path against the outputs recorded from the reference's own
     VoVNet-19-slim-eSE + FPN (tests/golden/backbone.npz; the CPU test_host_cpu.py checks the same vectors through ATen).
