@@ -1,6 +1,8 @@
 // D1+D2+D3: heat-map sigmoid -> candidate threshold -> per-level radix-select top-k ->
-// box decode -> dense level-major candidate list.  One CTA per problem; the keys of
-// one level live in shared memory, so the heat-map is read from HBM exactly once.
+// box decode -> dense level-major candidate list.  One CTA per (problem, level): the keys of
+// the level live in shared memory; the CTA's offset into the level-major list is the number of
+// survivors of the lower levels, which it recounts from their heat-maps (a read of <= 4 bytes
+// per pixel, no cross-CTA dependency), so the levels of a problem run on different SMs.
 //
 // Selection: key = fp32 bits of p (positive floats order like their bit patterns),
 // 0 for non-candidates.  An MSB-first 8-bit radix select (warp-aggregated shared
@@ -33,20 +35,10 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
   __shared__ int hist[kDecWarps][256];
   __shared__ int warp_sums[kDecWarps];
   __shared__ int sh[8];
-  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int out_base = 0;
-  for (int l = 0; l < prm.num_levels; ++l) {
-    const int H = prm.H[l], W = prm.W[l], n = H * W, stride = prm.stride[l];
-    const float* hm = prm.hm[l] + (size_t)p * n;
-    // ---- pass 0: keys + candidate count
-    int local = 0;
-    for (int i = tid; i < n; i += kDecThreads) {
-      float v = __ldg(hm + i);
-      float pr = prm.hm_is_logit ? 1.0f / (1.0f + expf(-v)) : v;
-      uint32_t k = (pr > prm.thresh) ? __float_as_uint(pr) : 0u;
-      keys[i] = k;
-      local += (k != 0u);
-    }
+  const int p = blockIdx.x / prm.num_levels, l = blockIdx.x - p * prm.num_levels;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // block-wide sum of one int per thread (result in every thread)
+  auto block_sum = [&](int local) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
     if (lane == 0) warp_sums[warp] = local;
@@ -58,7 +50,36 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
       if (lane == 0) sh[0] = v;
     }
     __syncthreads();
-    const int cnt = sh[0];
+    const int r = sh[0];
+    __syncthreads();
+    return r;
+  };
+  // survivors of the lower levels (the predicate their own CTAs evaluate)
+  int out_base = 0;
+  for (int ll = 0; ll < l; ++ll) {
+    const int nn = prm.H[ll] * prm.W[ll];
+    const float* hml = prm.hm[ll] + (size_t)p * nn;
+    int local = 0;
+    for (int i = tid; i < nn; i += kDecThreads) {
+      const float v = __ldg(hml + i);
+      const float pr = prm.hm_is_logit ? 1.0f / (1.0f + expf(-v)) : v;
+      local += (pr > prm.thresh);
+    }
+    out_base += min(block_sum(local), prm.pre_topk);
+  }
+  {
+    const int H = prm.H[l], W = prm.W[l], n = H * W, stride = prm.stride[l];
+    const float* hm = prm.hm[l] + (size_t)p * n;
+    // ---- pass 0: keys + candidate count
+    int local = 0;
+    for (int i = tid; i < n; i += kDecThreads) {
+      float v = __ldg(hm + i);
+      float pr = prm.hm_is_logit ? 1.0f / (1.0f + expf(-v)) : v;
+      uint32_t k = (pr > prm.thresh) ? __float_as_uint(pr) : 0u;
+      keys[i] = k;
+      local += (k != 0u);
+    }
+    const int cnt = block_sum(local);
     uint32_t T = 0u;   // select keys > T plus the first `need` keys == T
     int need = 0;
     if (cnt > prm.pre_topk) {
@@ -198,10 +219,8 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
       __syncthreads();
     }
     if (tid == 0) level_count[p * prm.num_levels + l] = nsel;
-    out_base += nsel;
-    __syncthreads();
+    if (tid == 0 && l == prm.num_levels - 1) cand_count[p] = min(out_base + nsel, prm.cand_cap);
   }
-  if (tid == 0) cand_count[p] = min(out_base, prm.cand_cap);
 }
 
 }  // namespace fod
@@ -243,9 +262,10 @@ extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, 
   prm.thresh = score_thresh;
   prm.pre_topk = pre_topk;
   prm.cand_cap = cand_cap;
+  FOD_REQUIRE((long)num_problems * num_levels < (1L << 30), "fod_decode_topk: too many problems");
   size_t smem = (size_t)maxpix * sizeof(uint32_t);
   FOD_CUDA_CALL(cudaFuncSetAttribute(decode_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  decode_topk_kernel<<<num_problems, kDecThreads, smem, as_stream(stream)>>>(prm, boxes, scores, loc, level_count,
+  decode_topk_kernel<<<num_problems * num_levels, kDecThreads, smem, as_stream(stream)>>>(prm, boxes, scores, loc, level_count,
                                                                              cand_count, status);
   FOD_CUDA_LAUNCH_CHECK("fod_decode_topk");
   return FOD_OK;

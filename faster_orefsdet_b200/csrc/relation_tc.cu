@@ -5,13 +5,19 @@
 // Design (B200, sm_100a) - the same skeleton as correlate_tc.cu:
 //   * work unit = 128 consecutive ROI rows of one problem; CTA pairs (cluster of 2, cta_group::2) cover two units
 //     per MMA (M = 256) and split the 128 rows of the folded weight matrix between them (N = 2 x 64).
-//   * K = 8192 is streamed in 32-wide chunks by TMA: the pooled rows (A, fp32) and the pre-split tf32 hi / lo
-//     planes of the folded weights (B) land in 128-byte-swizzled shared-memory rings (4 stages each).
+//   * K = 8192 is streamed in 32-wide chunks by TMA: the pooled rows (A, fp32, 128-byte swizzle) and the pre-split
+//     fp16 hi / lo planes of the folded weights (B, 64-byte swizzle) land in shared-memory rings (6 stages each).
+//   * fp32 accuracy on 16-bit tensor-core inputs, the arithmetic of conv_tc.cu: every operand is scaled by a power of
+//     two that puts its tensor's largest magnitude into [2^13, 2^14) and split, x * 2^e = hi + lo (two fp16, 22
+//     significant bits); a product is hi.hi + lo.hi + hi.lo on kind::f16 MMAs (K = 16 per instruction: half the
+//     tensor time of the 3xTF32 scheme this kernel used in round 1), the exact scales are undone in the epilogue.
 //   * 8 converter warps (one ROI row per lane = TMEM lane) read their row of the A chunk (conflict-free LDS.128),
-//     split it into tf32 hi / lo and write it into TENSOR MEMORY; the MMA (3xTF32: Ahi.Bhi + Alo.Bhi + Ahi.Blo)
-//     then reads A from tensor memory and only the weights from shared memory.
+//     scale and split it and write the packed fp16 pairs into TENSOR MEMORY; the MMA reads A from tensor memory and
+//     only the weights from shared memory.
 //   * accumulators (2 x 128 columns) are double buffered; the 4 epilogue warps own one ROI row per lane, so the
 //     six output dot products, the softmax and the box decoding need no cross-lane traffic.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -27,18 +33,18 @@ namespace rtc {
 constexpr int kK = 64 * kC;          // 8192
 constexpr int kChunk = 32;           // K per pipeline stage
 constexpr int kNumChunks = kK / kChunk;  // 256
-constexpr int kStages = 4;           // A ring, B ring and TMEM A ring
+constexpr int kStages = 6;           // A ring, B ring and TMEM A ring
 constexpr int kAccStages = 2;
 // The tensor core adds into its fp32 accumulator with round-toward-zero (measured, tools/tc_probe.cu acc: the
-// relative bias grows by ~1.7e-8 per accumulated MMA).  3072 MMAs per output (K = 8192, 3 products) would leave a
-// 5e-5 bias, so the K loop is cut into kParts partial sums of 96 MMAs each (bias ~1.6e-6, the chain length of the
+// relative bias grows by ~1.7e-8 per accumulated MMA).  1536 MMAs per output (K = 8192 / 16, 3 products) would leave
+// a 2.6e-5 bias, so the K loop is cut into kParts partial sums of 96 MMAs each (bias ~1.6e-6, the chain length of the
 // correlation kernel); the partials are added in IEEE fp32 by the epilogue warps into a running sum held in
 // shared memory.
-constexpr int kParts = 32;
-constexpr int kChunksPerPart = kNumChunks / kParts;  // 8
+constexpr int kParts = 16;
+constexpr int kChunksPerPart = kNumChunks / kParts;  // 16 chunks x 6 MMAs
 constexpr uint32_t kABytes = 128 * 128;       // 128 rows x 32 fp32
 constexpr uint32_t kBHalfRows = 64;
-constexpr uint32_t kBPlaneBytes = kBHalfRows * 128;  // 8192: hi or lo plane of one chunk
+constexpr uint32_t kBPlaneBytes = kBHalfRows * 64;   // 4096: hi or lo fp16 plane of one chunk (64-byte rows)
 constexpr uint32_t kBBytes = 2 * kBPlaneBytes;
 
 constexpr uint32_t kOffA = 0;
@@ -46,7 +52,7 @@ constexpr uint32_t kOffB = kOffA + kStages * kABytes;
 constexpr uint32_t kOffSum = kOffB + kStages * kBBytes;     // running sum [32 col groups][128 rows] x 16 B
 constexpr uint32_t kOffBias = kOffSum + 128 * kC * 4;       // 2 x [128] fp32
 constexpr uint32_t kOffWout = kOffBias + 2 * kC * 4;        // [6][128] + [6] (+pad) fp32
-constexpr int kMaxProblems = 4095;
+constexpr int kMaxProblems = 2047;
 constexpr uint32_t kOffPref = kOffWout + (6 * kC + 8) * 4;  // int32[P + 1]: exclusive prefix of units per problem
 constexpr uint32_t kOffBars = kOffPref + (kMaxProblems + 1) * 4;
 constexpr uint32_t kNumBars = 5 * kStages + 2 * kAccStages;
@@ -60,15 +66,19 @@ constexpr int kWarpTma = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpTmaB = 3, kWarpEp
 constexpr int kThreads = (kWarpConv0 + kConvWarps) * 32;  // 512
 
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColA = 0;        // 4 stages x [hi 32 | lo 32]
+constexpr uint32_t kAStageCols = 32; // [hi: 16 columns of packed fp16 pairs | lo: 16]
+constexpr uint32_t kColA = 0;        // 6 stages x 32
 constexpr uint32_t kColAcc = 256;    // 2 stages x 128
 
 constexpr float kScaleClamp = 4.135166556742356f;  // log(1000/16), d2 box_regression.py:13
 
 struct Params {
   CUtensorMap a_map;    // pooled, tiled [P*units*256*128][32], box 32 x 128 (one contiguous 16 KB A tile)
-  CUtensorMap whi_map;  // w_fold hi plane [128][8192], box 32 x 64
-  CUtensorMap wlo_map;  // w_fold lo plane
+  CUtensorMap whi_map;  // w_fold fp16 hi plane [128][8192], box 32 x 64
+  CUtensorMap wlo_map;  // w_fold fp16 lo plane
+  const float* x_amax;    // [n_amax] bounds of max|pooled| (= of the feature maps); their maximum fixes the A scale
+  const float* w_inv;     // 1 / weight scale (tail of the packed weights)
+  int n_amax;
   const float* bias_cls;  // [C][128]
   const float* rois;      // [P][roi_cap][4]
   const int32_t* roi_count;
@@ -81,6 +91,15 @@ struct Params {
   float reg_w[4];
   int num_problems, classes, roi_cap, tiles_per_problem, total_slots, num_pairs;
 };
+
+// (a, b) -> packed fp16 pair of the rounded values (a in the low half) and of the exact remainders
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 struct Slot {
   int p, r0, rows;  // rows = valid ROI rows in this unit (0 = padding unit of the last pair)
@@ -114,6 +133,16 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = blockIdx.x & 1;  // == %cluster_ctarank for cluster dims (2,1,1)
   const int pair = blockIdx.x >> 1;
+  float xs = 1.f, xs_inv = 1.f;   // operand scale 2^e of the pooled rows (converters) and its inverse (epilogue)
+  {
+    float amax = 0.f;
+    for (int i = 0; i < P.n_amax; ++i) amax = fmaxf(amax, __ldg(P.x_amax + i));
+    const int E = (int)((__float_as_uint(amax) >> 23) & 0xFF);
+    if (E >= 32 && E <= 240) {     // amax * 2^e in [2^13, 2^14); 1 for zero / denormal-range / non-finite bounds
+      xs = __uint_as_float((uint32_t)(267 - E) << 23);
+      xs_inv = __uint_as_float((uint32_t)(E - 13) << 23);
+    }
+  }
 
   const uint32_t bar0 = sbase + kOffBars;
   auto a_full = [&](int s) { return bar0 + 8u * s; };                       // TMA -> converters (A chunk landed)
@@ -224,7 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
     }
   } else if (warp == kWarpMma) {
     if (rank == 0) {
-      const uint32_t idesc = idesc_tf32(256, 128);
+      const uint32_t idesc = idesc_f16(256, 128);
       // A helper thread (warp kWarpAlloc) does all the barrier waiting and publishes the number of chunks whose
       // operands are in place through one shared-memory word; this warp only polls that word.  The whole warp runs
       // the loop converged and one elected lane issues, so that every tcgen05.mma operand is a warp-uniform value
@@ -247,17 +276,17 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
         const int as_ = gp % kAccStages;
         const bool first = (g % kChunksPerPart) == 0, last = (g % kChunksPerPart) == kChunksPerPart - 1;
         const uint32_t d = tmem_base + kColAcc + as_ * 128;
-        const uint32_t a0 = tmem_base + kColA + s * 64;
-        const uint64_t bhi = smem_desc_k_sw128(sbase + kOffB + s * kBBytes);
-        const uint64_t blo = smem_desc_k_sw128(sbase + kOffB + s * kBBytes + kBPlaneBytes);
+        const uint32_t a0 = tmem_base + kColA + s * kAStageCols;
+        const uint64_t bhi = smem_desc_k_sw64(sbase + kOffB + s * kBBytes);
+        const uint64_t blo = smem_desc_k_sw64(sbase + kOffB + s * kBBytes + kBPlaneBytes);
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint32_t ah = a0 + ks * 8, al = ah + 32;
+          for (int ks = 0; ks < 2; ++ks) {  // K = 16 fp16 per MMA: 8 packed columns of A, 32 bytes of a B row
+            const uint32_t ah = a0 + ks * 8, al = ah + 16;
             const uint64_t boff = (uint64_t)((ks * 32) >> 4);
-            mma_tf32_ts<2>(d, ah, bhi + boff, idesc, (!first || ks) ? 1u : 0u);
-            mma_tf32_ts<2>(d, al, bhi + boff, idesc, 1u);
-            mma_tf32_ts<2>(d, ah, blo + boff, idesc, 1u);
+            mma_f16_ts<2>(d, ah, bhi + boff, idesc, (!first || ks) ? 1u : 0u);
+            mma_f16_ts<2>(d, al, bhi + boff, idesc, 1u);
+            mma_f16_ts<2>(d, ah, blo + boff, idesc, 1u);
           }
           mma_commit_pair(st_free(s), 3);
           if (last) mma_commit_pair(acc_full(as_), 3);
@@ -290,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
     const int m = qd * 32 + lane;
     const uint32_t acc_empty_leader = map_to_cta(acc_empty(0), 0);
     uint32_t gp = 0;
+    const float rescale = xs_inv * __ldg(P.w_inv);   // undoes the two power-of-two operand scales (exact)
     const uint32_t sum_s = sbase + kOffSum + (uint32_t)m * 16;  // + col_group * 2048: lanes = consecutive 16 B
     for (int i = 0; in_range(i); ++i) {
       const Slot me = decode_unit(P, pref, slot_of(i, rank));
@@ -333,8 +363,8 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
               sts4s(sa, x);
             } else {
               const float4 bb = lds4s(bias_s + (j * 32 + c4 * 4) * 4);
-              const float f0 = fmaxf(x.x + bb.x, 0.f), f1 = fmaxf(x.y + bb.y, 0.f);
-              const float f2 = fmaxf(x.z + bb.z, 0.f), f3 = fmaxf(x.w + bb.w, 0.f);
+              const float f0 = fmaxf(fmaf(x.x, rescale, bb.x), 0.f), f1 = fmaxf(fmaf(x.y, rescale, bb.y), 0.f);
+              const float f2 = fmaxf(fmaf(x.z, rescale, bb.z), 0.f), f3 = fmaxf(fmaf(x.w, rescale, bb.w), 0.f);
 #pragma unroll
               for (int o = 0; o < 6; ++o) {
                 const float4 w = lds4s(sbase + kOffWout + (o * kC + j * 32 + c4 * 4) * 4);
@@ -377,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
     const int qd = wc & 3, half = wc >> 2;
     const int m = qd * 32 + lane;
     const uint32_t ready_leader = map_to_cta(ready(0), 0);
-    const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColA + half * 16;
+    const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16) + kColA + half * 8;
     const uint32_t arow = (uint32_t)(m * 128);
     uint32_t g = 0;
     for (int i = 0; in_range(i); ++i) {
@@ -389,18 +419,16 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
         float4 x[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = lds4s(at + ((((half * 4 + j) ^ (m & 7)) & 7) << 4));
-        uint32_t hi[16], lo[16];
+        uint32_t hi[8], lo[8];   // this warp's 16 K values of the chunk as packed fp16 pairs
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          split_tf32(x[j].x, hi[4 * j + 0], lo[4 * j + 0]);
-          split_tf32(x[j].y, hi[4 * j + 1], lo[4 * j + 1]);
-          split_tf32(x[j].z, hi[4 * j + 2], lo[4 * j + 2]);
-          split_tf32(x[j].w, hi[4 * j + 3], lo[4 * j + 3]);
+          split_f16x2(x[j].x * xs, x[j].y * xs, hi[2 * j + 0], lo[2 * j + 0]);
+          split_f16x2(x[j].z * xs, x[j].w * xs, hi[2 * j + 1], lo[2 * j + 1]);
         }
         mbar_wait(st_free(s), ph ^ 1);  // the MMAs that read this TMEM stage have completed
         tc_fence_after();
-        tmem_st16(trow + s * 64, hi);
-        tmem_st16(trow + s * 64 + 32, lo);
+        tmem_st8(trow + s * kAStageCols, hi);
+        tmem_st8(trow + s * kAStageCols + 16, lo);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -442,16 +470,18 @@ extern "C" int fod_split_tf32(const float* src, float* hi_lo, size_t n, fod_stre
   return FOD_OK;
 }
 
-extern "C" int fod_relation_head(const float* pooled, const float* w_fold_split, const float* bias_cls, const float* w_out,
-                                 const float* b_out, const float* rois, const int32_t* roi_count, int num_problems,
-                                 int problems_per_image, int roi_cap, const float* reg_weights, float* det_boxes,
-                                 float* det_scores, float* logits, float* deltas, fod_stream_t stream) {
-  FOD_REQUIRE(pooled && w_fold_split && bias_cls && w_out && b_out && rois && reg_weights && det_boxes && det_scores,
+extern "C" int fod_relation_head(const float* pooled, const float* x_amax, int n_amax, const float* w_fold_packed,
+                                 const float* bias_cls, const float* w_out, const float* b_out, const float* rois,
+                                 const int32_t* roi_count, int num_problems, int problems_per_image, int roi_cap,
+                                 const float* reg_weights, float* det_boxes, float* det_scores, float* logits, float* deltas,
+                                 fod_stream_t stream) {
+  FOD_REQUIRE(pooled && x_amax && w_fold_packed && bias_cls && w_out && b_out && rois && reg_weights && det_boxes && det_scores,
               "fod_relation_head: null pointer");
+  FOD_REQUIRE(n_amax >= 1 && n_amax <= 8, "fod_relation_head: 1..8 operand bounds");
   FOD_REQUIRE(num_problems >= 0 && problems_per_image > 0 && roi_cap > 0, "fod_relation_head: bad sizes");
   FOD_REQUIRE(num_problems % problems_per_image == 0, "fod_relation_head: num_problems not a multiple of classes");
   FOD_REQUIRE(num_problems <= rtc::kMaxProblems, "fod_relation_head: more than %d problems per call", rtc::kMaxProblems);
-  FOD_REQUIRE((((uintptr_t)pooled | (uintptr_t)w_fold_split | (uintptr_t)bias_cls | (uintptr_t)rois | (uintptr_t)det_boxes |
+  FOD_REQUIRE((((uintptr_t)pooled | (uintptr_t)w_fold_packed | (uintptr_t)bias_cls | (uintptr_t)rois | (uintptr_t)det_boxes |
                 (uintptr_t)deltas) & 15) == 0, "fod_relation_head: pointers must be 16-byte aligned");
   if (num_problems == 0) return FOD_OK;
   rtc::Params prm;
@@ -460,10 +490,16 @@ extern "C" int fod_relation_head(const float* pooled, const float* w_fold_split,
   FOD_REQUIRE(units * rtc::kNumChunks * 128 < (1L << 31), "fod_relation_head: pooled buffer too large for one call");
   int rc = make_matrix_map(&prm.a_map, pooled, units * rtc::kNumChunks * 128, rtc::kChunk, rtc::kChunk, 128);
   if (rc != FOD_OK) return rc;
-  rc = make_matrix_map(&prm.whi_map, w_fold_split, kC, rtc::kK, rtc::kChunk, rtc::kBHalfRows);
+  // packed weights = fod_conv2d_pack_weights of the folded matrix seen as a 1x1 convolution [128][8192][1][1]:
+  // fp16 hi plane [128][8192], lo plane, then {1/scale, scale, max|w|, 0}
+  const __half* whi = reinterpret_cast<const __half*>(w_fold_packed);
+  rc = make_matrix_map_f16(&prm.whi_map, whi, kC, rtc::kK, rtc::kChunk, rtc::kBHalfRows);
   if (rc != FOD_OK) return rc;
-  rc = make_matrix_map(&prm.wlo_map, w_fold_split + (size_t)kC * rtc::kK, kC, rtc::kK, rtc::kChunk, rtc::kBHalfRows);
+  rc = make_matrix_map_f16(&prm.wlo_map, whi + (size_t)kC * rtc::kK, kC, rtc::kK, rtc::kChunk, rtc::kBHalfRows);
   if (rc != FOD_OK) return rc;
+  prm.w_inv = w_fold_packed + (size_t)kC * rtc::kK;   // two fp16 planes = kC * kK floats
+  prm.x_amax = x_amax;
+  prm.n_amax = n_amax;
   prm.bias_cls = bias_cls;
   prm.rois = rois;
   prm.roi_count = roi_count;

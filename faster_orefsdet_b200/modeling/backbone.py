@@ -375,7 +375,10 @@ class FPN(Backbone):
         def run(m, t, a_in=None, a_out=None, gate=None):
             if tcconv.supported(m, t) and (gate is None or m.in_channels % 32 == 0):
                 return tcconv.conv(t, m, x_amax=a_in, y_amax=a_out, a_gate=gate)
-            return m(t if gate is None else t * gate)
+            y = m(t if gate is None else t * gate)
+            if a_out is not None:
+                a_out.copy_(y.detach().abs().max().reshape(1))
+            return y
 
         def bound(t):
             return ops.new_amax(t.device) if t.is_cuda else None
@@ -383,7 +386,14 @@ class FPN(Backbone):
         top = self.in_features[-1]
         a_prev = bound(feats[top])
         prev = run(self._laterals[0], feats[top], bounds.get(top), a_prev, gates.get(top))
-        results = [run(self._outputs[0], prev, a_prev)]
+        out_bounds = []      # max|output map| per level (device scalars), reported by the output convolutions' epilogues
+
+        def out_bound(t):
+            b = bound(t)
+            out_bounds.insert(0, b)
+            return b
+
+        results = [run(self._outputs[0], prev, a_prev, out_bound(prev))]
         for idx in range(1, len(self._laterals)):
             name = self.in_features[-idx - 1]
             f, lat = feats[name], self._laterals[idx]
@@ -403,7 +413,8 @@ class FPN(Backbone):
                     a_prev = a_lat + a_prev            # |lateral + upsampled| <= bound + bound
                 if self._fuse_type == "avg":
                     prev = prev / 2
-            results.insert(0, run(self._outputs[idx], prev, a_prev))
+            results.insert(0, run(self._outputs[idx], prev, a_prev, out_bound(prev)))
+        self.last_output_bounds = dict(zip(self._out_features, out_bounds))
         return dict(zip(self._out_features, results))
 
     def output_shape(self):

@@ -424,15 +424,17 @@ class CenterNet2Detector(nn.Module):
         res = self._head_launch(features, image_hw, out_hw, None)
         return self._head_finish(res, features, image_hw, out_hw, want_trace)
 
-    def _head_launch(self, features, image_hw, out_hw, cap):
-        """Kernel launches of the head only (stream-ordered, no host sync: CUDA-graph capturable)."""
+    def _head_launch(self, features, image_hw, out_hw, cap, feature_bounds=None):
+        """Kernel launches of the head only (stream-ordered, no host sync: CUDA-graph capturable).  ``feature_bounds``:
+        {level: device scalar >= max|features[level]|} when the feature extractor reported them."""
         bank = self._bank
         raw = [features[f] for f in self.in_features]
         status = ops.new_status(raw[0].device)
         attn, attn_amax = ops.correlate_levels(raw, bank.taps_host, self.conv3.weight, self.conv3.bias, want_amax=True)
         props = self.proposal_generator.propose_raw(attn, status, cap, bounds=attn_amax)
+        fb = None if feature_bounds is None else [feature_bounds.get(f) for f in self.in_features]
         out, per_roi = self.roi_heads.detect_raw(raw, bank.bias_cls, props.boxes, props.count, bank.num_classes, image_hw, out_hw,
-                                                 status)
+                                                 status, feature_bounds=fb)
         return out, per_roi, props, attn, status
 
     def _head_finish(self, res, features, image_hw, out_hw, want_trace: bool = False):
@@ -501,7 +503,7 @@ class CenterNet2Detector(nn.Module):
 
         def run():
             feats = self.backbone.top_down(*vov.tc_body(buf, amax, fuse_gates=True))
-            return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None)
+            return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None, self.backbone.last_output_bounds)
 
         main = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)

@@ -108,8 +108,8 @@ class CustomCascadeROIHeads(nn.Module):
         key = self.fold_key()
         if self._fold_cache is None or self._fold_cache[0] != key:
             w_fold, w_out, b_out = fold.fold_relation_weights(self._state())
-            if w_fold.is_cuda:       # tf32 hi / lo planes for the tensor-core kernel, once per weight load
-                w_fold = ops.split_tf32(w_fold)
+            if w_fold.is_cuda:       # scaled fp16 hi / lo planes for the tensor-core kernel, once per weight load
+                w_fold = ops.relation_pack(w_fold)
             self._fold_cache = (key, (w_fold, w_out, b_out))
         return self._fold_cache[1]
 
@@ -121,13 +121,17 @@ class CustomCascadeROIHeads(nn.Module):
     @torch.no_grad()
     def detect_raw(self, features: Sequence[torch.Tensor], bias_cls: torch.Tensor, rois: torch.Tensor,
                    roi_count: torch.Tensor, num_classes: int, image_hw: torch.Tensor, out_hw: Optional[torch.Tensor],
-                   status: torch.Tensor):
+                   status: torch.Tensor, feature_bounds: Optional[Sequence[torch.Tensor]] = None):
         """features[l] [B,128,H,W] raw backbone maps; rois [B*C,cap,4]; returns the padded
-        outputs of ops.final_detect plus the per-ROI (boxes, scores)."""
+        outputs of ops.final_detect plus the per-ROI (boxes, scores).  ``feature_bounds[l]``: device scalar bounding
+        max|features[l]| when the producer reported it (the FPN output convolutions do); computed otherwise."""
         w_fold, w_out, b_out = self.folded()
         pooled = ops.roi_align(features, self.strides, rois, roi_count, num_classes, self.pooler_resolution, tiled=True)
+        if feature_bounds is None or any(b is None for b in feature_bounds):
+            feature_bounds = [ops.absmax(ops.nhwc(f)) for f in features]
+        x_amax = torch.cat([b.reshape(1) for b in feature_bounds])
         det_boxes, det_scores = ops.relation_head(pooled, w_fold, bias_cls, w_out, b_out, rois, roi_count, num_classes,
-                                                  self.bbox_reg_weights)
+                                                  self.bbox_reg_weights, x_amax=x_amax)
         p = self.box_predictor[0]
         out = ops.final_detect(det_boxes, det_scores, roi_count, num_classes, p.test_score_thresh, p.test_nms_thresh,
                                p.test_topk_per_image, image_hw, out_hw, status)

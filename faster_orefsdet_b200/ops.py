@@ -241,36 +241,53 @@ def split_tf32(w: Tensor) -> Tensor:
     return out
 
 
+def relation_pack(w_fold: Tensor) -> Tensor:
+    """Folded relation matrix [128, 8192] -> the packed operand of relation_head: scaled fp16 hi / lo planes + the scale
+    (fod_conv2d_pack_weights of the matrix seen as a 1x1 convolution weight; once per weight load)."""
+    w = _chk(w_fold, torch.float32, "w_fold")
+    if tuple(w.shape) != (128, 8192):
+        raise _lib.FodError("relation_pack: folded matrix [128, 8192] expected")
+    return conv2d_pack(w.reshape(128, 8192, 1, 1))
+
+
 def relation_head(pooled: Tensor, w_fold: Tensor, bias_cls: Tensor, w_out: Tensor, b_out: Tensor, rois: Tensor,
                   roi_count: Optional[Tensor], problems_per_image: int, reg_weights: Sequence[float],
-                  want_raw: bool = False):
+                  want_raw: bool = False, x_amax: Optional[Tensor] = None):
     """-> (det_boxes [P,cap,4] unclipped, det_scores [P,cap][, logits [P,cap,2], deltas [P,cap,4]])
     (fsod_roi_heads.py:482-520, custom_fast_rcnn.py:160-170, d2 box_regression.py:77-115).
     pooled: the tiled layout [P,U,256,128,32] written by roi_align(tiled=True) (a [P,cap,64,128] tensor is
-    re-tiled with torch ops first - tests only).  w_fold: the folded matrix [128,8192] or, preferably, its pre-split planes [2,128,8192] (split_tf32)."""
+    re-tiled with torch ops first - tests only).  w_fold: the folded matrix [128,8192] or, preferably, its packed form
+    (relation_pack).  x_amax: device floats (1..8) bounding max|pooled| = the bounds of the feature maps the ROIAlign
+    read; computed from ``pooled`` when omitted, which needs the dense [P,cap,64,128] form."""
     P, cap = rois.shape[0], rois.shape[1]
     dev = rois.device
     if w_fold.dim() == 2:
-        w_fold = split_tf32(w_fold)
+        w_fold = relation_pack(w_fold)
+    if x_amax is None:
+        if pooled.dim() != 4:
+            raise _lib.FodError("relation_head: x_amax (bounds of the pooled features) is required with the tiled layout")
+        x_amax = absmax(pooled.contiguous())
     if pooled.dim() == 4:
         pooled = tile_pooled(pooled)
     if tuple(pooled.shape) != (P, (cap + 127) // 128, 256, 128, 32):
         raise _lib.FodError("relation_head: pooled must be [P,U,256,128,32]")
     for t, n in ((pooled, "pooled"), (w_fold, "w_fold"), (bias_cls, "bias_cls"), (w_out, "w_out"), (b_out, "b_out"),
-                 (rois, "rois")):
+                 (rois, "rois"), (x_amax, "x_amax")):
         _chk(t, torch.float32, n)
         if not t.is_contiguous():
             raise _lib.FodError(f"relation_head: {n} must be contiguous")
-    if tuple(w_fold.shape) != (2, 128, 8192) or tuple(w_out.shape) != (6, 128) or bias_cls.shape[-1] != 128:
+    if w_fold.numel() != _lib.lib().fod_conv2d_packed_floats(128, 8192, 1) or tuple(w_out.shape) != (6, 128) or bias_cls.shape[-1] != 128:
         raise _lib.FodError("relation_head: bad weight shapes")
+    if not 1 <= x_amax.numel() <= 8:
+        raise _lib.FodError("relation_head: 1..8 operand bounds")
     det_boxes = torch.zeros((P, cap, 4), dtype=torch.float32, device=dev)
     det_scores = torch.zeros((P, cap), dtype=torch.float32, device=dev)
     logits = torch.zeros((P, cap, 2), dtype=torch.float32, device=dev) if want_raw else None
     deltas = torch.zeros((P, cap, 4), dtype=torch.float32, device=dev) if want_raw else None
     rw = (ctypes.c_float * 4)(*[float(x) for x in reg_weights])
-    _lib.check(_lib.lib().fod_relation_head(_ptr(pooled), _ptr(w_fold), _ptr(bias_cls), _ptr(w_out), _ptr(b_out),
-                                            _ptr(rois), _ptr(roi_count), P, int(problems_per_image), cap, rw,
-                                            _ptr(det_boxes), _ptr(det_scores), _ptr(logits), _ptr(deltas), _stream()),
+    _lib.check(_lib.lib().fod_relation_head(_ptr(pooled), _ptr(x_amax), int(x_amax.numel()), _ptr(w_fold), _ptr(bias_cls),
+                                            _ptr(w_out), _ptr(b_out), _ptr(rois), _ptr(roi_count), P, int(problems_per_image),
+                                            cap, rw, _ptr(det_boxes), _ptr(det_scores), _ptr(logits), _ptr(deltas), _stream()),
                "fod_relation_head")
     return (det_boxes, det_scores, logits, deltas) if want_raw else (det_boxes, det_scores)
 

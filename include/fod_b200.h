@@ -168,21 +168,27 @@ int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_l
  * Box2BoxTransform.apply_deltas d2!/modeling/box_regression.py:77-115.
  * The three 1x1 convs and fc1 have no non-linearity between them and are folded
  * on the host into one [128][8192] matrix plus a per-class bias.
- * Tensor cores (tcgen05, 3xTF32 operand splitting = fp32 accuracy), TMA-fed.
+ * Tensor cores (tcgen05 kind::f16) with fp32 accuracy: both operands are scaled by a power of two and split into two
+ * fp16 values, three MMAs per product (the arithmetic of fod_conv2d_nhwc), TMA-fed.
  *   pooled   : [P][U][256][128][32], the tiled layout of fod_roi_align (tiled = 1)
- *   w_fold_split : [2][128][8192]   k index = bin*128 + channel; plane 0 = tf32-rounded folded weights, plane 1 =
- *                  exact remainder, as written by fod_split_tf32 (once per weight load)
+ *   x_amax   : n_amax (1..8) DEVICE floats bounding max|pooled|; ROIAlign averages bilinear samples, so the bounds of
+ *              the feature maps it read (fod_conv2d_nhwc y_amax of the FPN output convolutions, or fod_absmax) hold.
+ *              Any bound >= the true maximum gives the same result up to 2^-38 of the bound.
+ *   w_fold_packed : fod_conv2d_pack_weights(w_fold as a [128][8192][1][1] convolution weight, ksize 1):
+ *                  fod_conv2d_packed_floats(128, 8192, 1) floats; k index = bin*128 + channel (once per weight load)
  *   bias_cls : [C][128]      per-class folded bias (support term + fc1 bias)
  *   w_out    : [6][128], b_out [6] : rows 0-1 cls_score, rows 2-5 bbox_pred
  *   reg_weights : HOST pointer, 4 floats (wx, wy, ww, wh) = ROI_BOX_CASCADE_HEAD.BBOX_REG_WEIGHTS[0]
  *   det_boxes: [P][roi_cap][4] (unclipped), det_scores [P][roi_cap] (foreground probability)
  *   logits/deltas (optional, may be NULL): [P][roi_cap][2] / [P][roi_cap][4]
+ * At most 2047 problems per call.
  */
 int fod_split_tf32(const float* src, float* hi_lo /* [2][n] */, size_t n, fod_stream_t stream);
-int fod_relation_head(const float* pooled, const float* w_fold_split, const float* bias_cls, const float* w_out,
-                      const float* b_out, const float* rois, const int32_t* roi_count, int num_problems,
-                      int problems_per_image, int roi_cap, const float* reg_weights, float* det_boxes,
-                      float* det_scores, float* logits, float* deltas, fod_stream_t stream);
+int fod_relation_head(const float* pooled, const float* x_amax, int n_amax, const float* w_fold_packed,
+                      const float* bias_cls, const float* w_out, const float* b_out, const float* rois,
+                      const int32_t* roi_count, int num_problems, int problems_per_image, int roi_cap,
+                      const float* reg_weights, float* det_boxes, float* det_scores, float* logits, float* deltas,
+                      fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * R4 / N1 / O1  final class-wise NMS, top-k, rescale to the output resolution.

@@ -340,7 +340,7 @@ def test_relation_head_matches_reference_and_oracle():
 
 
 def test_relation_head_tensor_core_multi_class_ragged_counts():
-    """tcgen05 3xTF32 contraction: several classes, roi_cap not a multiple of 128, empty / 1-row / full problems."""
+    """tcgen05 fp16-split contraction: several classes, roi_cap not a multiple of 128, empty / 1-row / full problems."""
     sd = head_state_dict()
     B, C, cap = 3, 2, 320
     P = B * C
@@ -350,7 +350,7 @@ def test_relation_head_tensor_core_multi_class_ragged_counts():
     sup = synth.tensor((C, 128, 8, 8), 73, -1.0, 1.0)
     w_fold, w_out, b_out = fold.fold_relation_weights(sd)
     bias = fold.fold_class_bias(sd, sup)
-    db, ds, logits, deltas = ops.relation_head(pooled.to(DEV), ops.split_tf32(w_fold.to(DEV)), bias.to(DEV), w_out.to(DEV),
+    db, ds, logits, deltas = ops.relation_head(pooled.to(DEV), ops.relation_pack(w_fold.to(DEV)), bias.to(DEV), w_out.to(DEV),
                                                b_out.to(DEV), bx.to(DEV), counts.to(DEV), C, CFG.bbox_reg_weights,
                                                want_raw=True)
     torch.cuda.synchronize()
@@ -380,7 +380,7 @@ def test_relation_head_ten_classes_per_class_bias():
     sup = synth.tensor((C, 128, 8, 8), 173, -1.0, 1.0)
     w_fold, w_out, b_out = fold.fold_relation_weights(sd)
     bias = fold.fold_class_bias(sd, sup)
-    db, ds, logits, deltas = ops.relation_head(pooled.to(DEV), ops.split_tf32(w_fold.to(DEV)), bias.to(DEV), w_out.to(DEV),
+    db, ds, logits, deltas = ops.relation_head(pooled.to(DEV), ops.relation_pack(w_fold.to(DEV)), bias.to(DEV), w_out.to(DEV),
                                                b_out.to(DEV), bx.to(DEV), counts.to(DEV), C, CFG.bbox_reg_weights,
                                                want_raw=True)
     torch.cuda.synchronize()

@@ -14,7 +14,7 @@ ctr = torch.rand(P, cap, 2, device=dev) * 500 + 70
 wh = torch.rand(P, cap, 2, device=dev) * 100 + 60
 rois = torch.cat((ctr - wh / 2, ctr + wh / 2), -1).contiguous()
 counts = torch.full((P,), n, dtype=torch.int32, device=dev)
-w_fold = ops.split_tf32(torch.randn(128, 8192, device=dev) * 0.01)
+w_fold = ops.relation_pack(torch.randn(128, 8192, device=dev) * 0.01)
 bias = torch.randn(C, 128, device=dev) * 0.1
 w_out = torch.randn(6, 128, device=dev) * 0.05
 b_out = torch.zeros(6, device=dev)
@@ -35,7 +35,8 @@ def timeit(fn, iters=10, warm=3):
 
 pooled = ops.roi_align(feats, (8, 16, 32), rois, counts, C, 8, tiled=True)
 t_roi = timeit(lambda: ops.roi_align(feats, (8, 16, 32), rois, counts, C, 8, tiled=True))
-t_rel = timeit(lambda: ops.relation_head(pooled, w_fold, bias, w_out, b_out, rois, counts, C, (10., 10., 5., 5.)))
+xa = torch.cat([ops.absmax(f.contiguous(memory_format=torch.channels_last)) for f in feats])
+t_rel = timeit(lambda: ops.relation_head(pooled, w_fold, bias, w_out, b_out, rois, counts, C, (10., 10., 5., 5.), x_amax=xa))
 flops = 2.0 * P * n * 8192 * 128
 print(f"B={B} C={C}: roi_align {t_roi*1e3:.1f} us   relation_head {t_rel*1e3:.1f} us ({flops/t_rel/1e9:.1f} fp32-equivalent TFLOP/s, "
       f"pooled read {P*n*32768/t_rel/1e6:.0f} GB/s)")

@@ -10,7 +10,7 @@ ctr = torch.rand(P, cap, 2, device=dev) * 500 + 70
 wh = torch.rand(P, cap, 2, device=dev) * 100 + 60
 rois = torch.cat((ctr - wh / 2, ctr + wh / 2), -1).contiguous()
 counts = torch.full((P,), n, dtype=torch.int32, device=dev)
-w_fold = ops.split_tf32(torch.randn(128, 8192, device=dev) * 0.01)
+w_fold = ops.relation_pack(torch.randn(128, 8192, device=dev) * 0.01)
 bias = torch.randn(C, 128, device=dev) * 0.1
 w_out = torch.randn(6, 128, device=dev) * 0.05
 b_out = torch.zeros(6, device=dev)
