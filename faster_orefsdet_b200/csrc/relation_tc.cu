@@ -61,9 +61,15 @@ constexpr uint32_t kOffFlag = kOffTmemPtr + 8;   // chunks released to the MMA t
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
 constexpr uint32_t kSmemAlloc = kSmemBytes + 1024;
 
-constexpr int kConvWarps = 8;
+constexpr int kConvWarps = 8;        // converter warps per chunk: 4 TMEM quadrants x 2 halves of the 32-wide K chunk
+#ifndef FOD_REL_SETS
+#define FOD_REL_SETS 1
+#endif
+constexpr int kConvSets = FOD_REL_SETS;   // sets of converter warps that take alternate chunks: one chunk costs a warp
+                                          // ~900 cycles (two mbarrier waits of ~250 cycles each, the split, tcgen05.st),
+                                          // the 6 MMAs of a chunk 384
 constexpr int kWarpTma = 0, kWarpMma = 1, kWarpAlloc = 2, kWarpTmaB = 3, kWarpEpi0 = 4, kWarpConv0 = 8;
-constexpr int kThreads = (kWarpConv0 + kConvWarps) * 32;  // 512
+constexpr int kThreads = (kWarpConv0 + kConvWarps * kConvSets) * 32;  // 512 (768 with two sets: measured neutral, 119 vs 120 us)
 
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAStageCols = 32; // [hi: 16 columns of packed fp16 pairs | lo: 16]
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
       mbar_init(a_full(s), 1);
       mbar_init(a_empty(s), kConvWarps);
       mbar_init(b_full(s), 1);  // leader only: armed by the leader's producer for the bytes of both CTAs
-      mbar_init(ready(s), 2 * kConvWarps);
+      mbar_init(ready(s), 2 * kConvWarps + 1);  // converter warps of both CTAs + the weight producer's expect_tx
       mbar_init(st_free(s), 1);
     }
     for (int s = 0; s < kAccStages; ++s) {
@@ -233,7 +239,10 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
     // ------------------------------------------------------------------ TMA producer, B operand (weights); its own
     // thread so that a late st_free never delays the A stream and vice versa
     if (lane == 0) {
-      const uint32_t b_full_leader = map_to_cta(b_full(0), 0);
+      // An mbarrier wait costs ~250 cycles even when its phase completed long ago, and the MMA warp's watcher is the
+      // only thread that waits once per chunk: the weight bytes of both CTAs therefore complete the SAME barrier as
+      // the converter warps' arrivals (ready), one wait per chunk instead of two.
+      const uint32_t b_full_leader = map_to_cta(ready(0), 0);
       uint32_t g = 0;
       for (int i = 0; in_range(i); ++i) {
         for (int kc = 0; kc < kNumChunks; ++kc, ++g) {
@@ -242,9 +251,9 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
           // each CTA loads its 64 rows; both CTAs' bytes complete on the LEADER's barrier
           mbar_wait(st_free(s), ph ^ 1);
 #if FOD_EXP == 2
-          if (g >= (uint32_t)kStages) { if (rank == 0) mbar_arrive(b_full(s)); continue; }
+          if (g >= (uint32_t)kStages) { if (rank == 0) mbar_arrive(ready(s)); continue; }
 #endif
-          if (rank == 0) mbar_arrive_expect_tx(b_full(s), 2 * kBBytes);
+          if (rank == 0) mbar_arrive_expect_tx(ready(s), 2 * kBBytes);
           tma_load_2d_2sm(sbase + kOffB + s * kBBytes, &P.whi_map, b_full_leader + 8u * s, kc * kChunk, rank * kBHalfRows);
           tma_load_2d_2sm(sbase + kOffB + s * kBBytes + kBPlaneBytes, &P.wlo_map, b_full_leader + 8u * s, kc * kChunk,
                           rank * kBHalfRows);
@@ -304,8 +313,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
       for (uint32_t g = 0; g < total; ++g) {
         const int s = g % kStages;
         const uint32_t ph = (g / kStages) & 1;
-        mbar_wait(b_full(s), ph);   // weight chunks of both CTAs have landed
-        mbar_wait(ready(s), ph);    // A chunk of both CTAs is in tensor memory
+        mbar_wait(ready(s), ph);    // A chunk of both CTAs is in tensor memory and the weight chunks have landed
         if (g % kChunksPerPart == 0) {  // first chunk of a partial sum: its accumulator must have been drained
           const uint32_t gp = g / kChunksPerPart;
           mbar_wait(acc_empty(gp % kAccStages), ((gp / kAccStages) & 1) ^ 1);
@@ -403,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
     }
   } else if (warp >= kWarpConv0) {
     // ------------------------------------------------------------------ converters: A chunk smem -> tf32 hi/lo in TMEM
-    const int wc = warp - kWarpConv0;
+    const int wc = (warp - kWarpConv0) % kConvWarps, set = (warp - kWarpConv0) / kConvWarps;
     const int qd = wc & 3, half = wc >> 2;
     const int m = qd * 32 + lane;
     const uint32_t ready_leader = map_to_cta(ready(0), 0);
@@ -412,6 +420,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
     uint32_t g = 0;
     for (int i = 0; in_range(i); ++i) {
       for (int kc = 0; kc < kNumChunks; ++kc, ++g) {
+        if ((int)(g % kConvSets) != set) continue;
         const int s = g % kStages;
         const uint32_t ph = (g / kStages) & 1;
         mbar_wait(a_full(s), ph);
