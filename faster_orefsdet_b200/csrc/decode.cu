@@ -22,7 +22,8 @@ struct DecodeParams {
   const float* reg[FOD_MAX_LEVELS];
   int H[FOD_MAX_LEVELS], W[FOD_MAX_LEVELS], stride[FOD_MAX_LEVELS];
   int num_levels;
-  int hm_is_logit, reg_channels_last;
+  int hm_is_logit, reg_channels_last, reg_activate;
+  float reg_scale[FOD_MAX_LEVELS];   // reg_activate: reg = relu(reg_scale[l] * raw) (Scale + ReLU of CenterNetHead)
   float thresh;
   int pre_topk, cand_cap;
 };
@@ -202,6 +203,13 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
             const float* rp = prm.reg[l] + (size_t)p * 4 * n + i;
             r0 = __ldg(rp); r1 = __ldg(rp + n); r2 = __ldg(rp + 2 * (size_t)n); r3 = __ldg(rp + 3 * (size_t)n);
           }
+          if (prm.reg_activate) {   // F.relu(scale * x), centernet_head.py:157-160 (one rounded product, then max)
+            const float sc = prm.reg_scale[l];
+            r0 = fmaxf(__fmul_rn(r0, sc), 0.f);
+            r1 = fmaxf(__fmul_rn(r1, sc), 0.f);
+            r2 = fmaxf(__fmul_rn(r2, sc), 0.f);
+            r3 = fmaxf(__fmul_rn(r3, sc), 0.f);
+          }
           float x1 = __fsub_rn(gx, __fmul_rn(r0, fstride));
           float y1 = __fsub_rn(gy, __fmul_rn(r1, fstride));
           float x2 = __fadd_rn(gx, __fmul_rn(r2, fstride));
@@ -229,7 +237,7 @@ using namespace fod;
 
 extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_level_t* levels,
                                int num_levels, int num_problems, int hm_is_logit, int reg_channels_last,
-                               float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores,
+                               const float* reg_scale, float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores,
                                int64_t* loc, int32_t* level_count, int32_t* cand_count, uint32_t* status,
                                fod_stream_t stream) {
   FOD_REQUIRE(hm && reg && levels && boxes && scores && loc && level_count && cand_count && status,
@@ -259,6 +267,8 @@ extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, 
   prm.num_levels = num_levels;
   prm.hm_is_logit = hm_is_logit;
   prm.reg_channels_last = reg_channels_last;
+  prm.reg_activate = reg_scale ? 1 : 0;
+  for (int l = 0; l < FOD_MAX_LEVELS; ++l) prm.reg_scale[l] = (reg_scale && l < num_levels) ? reg_scale[l] : 1.f;
   prm.thresh = score_thresh;
   prm.pre_topk = pre_topk;
   prm.cand_cap = cand_cap;

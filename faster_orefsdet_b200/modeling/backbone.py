@@ -1,4 +1,7 @@
-"""VoVNet-19-slim-eSE + FPN backbone (side input of the hot path; stays PyTorch/cuDNN).
+"""VoVNet-19-slim-eSE + FPN feature extractor (the caller side of the hot path).
+
+On CUDA every convolution runs on the tensor-core kernel (csrc/conv_tc.cu via modeling/tcconv.py), pooling, eSE gate
+and stem on csrc/glue.cu; on CPU tensors the same module runs through ATen - that is the CPU baseline of bench.py.
 
 Restates d2!/modeling/backbone/vovnet.py:50-58,205-489,527-555 and
 d2!/modeling/backbone/fpn.py:17-155 with the same module / state_dict key names
@@ -77,8 +80,9 @@ class ConvNormReLUSeq(nn.Sequential):
             if tcconv.supported(conv, x):          # tcgen05 3xTF32 kernel (csrc/conv_tc.cu)
                 x = tcconv.conv(x, conv, norm, relu=True)
                 continue
-            w, b = self._folded(i, conv, norm)     # stride-2 / 3-channel stem convolutions, CPU tensors: cuDNN / ATen
-            x = F.relu_(F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups))
+            w, b = self._folded(i, conv, norm)     # CPU tensors (the CPU baseline), shapes outside the kernel: ATen
+            with torch.backends.cudnn.flags(allow_tf32=False):      # the reference computes in fp32 (log:490-491)
+                x = F.relu_(F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups))
         return x
 
 
@@ -214,7 +218,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
                 self._out_feature_strides[name] = stride
 
     def _tc_path(self, x) -> bool:
-        return (tcconv.ENABLED and x.is_cuda and x.dtype == torch.float32 and not self.training and x.shape[1] == 3
+        return (x.is_cuda and x.dtype == torch.float32 and not self.training and x.shape[1] == 3
                 and all(len([m for m in getattr(self, n) if isinstance(m, _OSAModule)]) == 1 for n in self.stage_names))
 
     def _stem1_packed(self):

@@ -2,8 +2,8 @@
 
 Mirrors the reference interface:
   * ``CenterNetHead`` - CenterNet2/centernet/modeling/dense_heads/centernet_head.py:21-161
-    (conv tower + GroupNorm + agn_hm + bbox_pred + Scale).  Boundary row H0: the 3x3
-    convolutions stay PyTorch/cuDNN.
+    (conv tower + GroupNorm + agn_hm + bbox_pred + Scale).  Row H0 / 8f#1: the 3x3 convolutions
+    run on the tensor-core kernel (csrc/conv_tc.cu), GroupNorm on csrc/gn.cu; there is no cuDNN path.
   * ``CenterNet`` - fewx/modeling/fsod/fsod_rpn.py:491-655, 1068-1210, registered in
     PROPOSAL_GENERATOR_REGISTRY under the same name, built as ``cls(cfg, input_shape)``,
     ``forward(images, features_dict, gt_instances) -> (list[Instances], {})``.
@@ -66,19 +66,28 @@ class CenterNetHead(nn.Module):
         nn.init.constant_(self.agn_hm.bias, -math.log((1 - c.PRIOR_PROB) / c.PRIOR_PROB))
         nn.init.normal_(self.agn_hm.weight, std=0.01)
 
-    def forward(self, x: Sequence[torch.Tensor], bounds: Optional[Sequence[torch.Tensor]] = None):
-        """``bounds[l]``: device scalar bounding max|x[l]| when the producer reported it (ops.correlate_levels)."""
+    def forward(self, x: Sequence[torch.Tensor], bounds: Optional[Sequence[torch.Tensor]] = None, raw_reg: bool = False):
+        """``bounds[l]``: device scalar bounding max|x[l]| when the producer reported it (ops.correlate_levels).
+        ``raw_reg``: return bbox_pred's output as it is; the caller applies relu(scale_l * x) (fod_decode_topk does it
+        while it reads the map, centernet_head.py:157-160), which saves one elementwise pass per level."""
         clss, bbox_reg, agn_hms = [], [], []
         for l, feature in enumerate(x):
-            if tcconv.supported(self.agn_hm, feature):
-                hm, reg = self._level_tc(feature, bounds[l] if bounds is not None else None)
-            else:
-                t = self.bbox_tower(feature)
-                hm, reg = self.agn_hm(t), self.bbox_pred(t)
+            if not tcconv.supported(self.agn_hm, feature):
+                raise ops._lib.FodError("CenterNetHead: fp32 CUDA maps in NHWC memory expected (the head has no cuDNN / CPU path)")
+            hm, reg = self._level_tc(feature, bounds[l] if bounds is not None else None)
             clss.append(None)
             agn_hms.append(hm)
-            bbox_reg.append(F.relu(self.scales[l](reg)))
+            bbox_reg.append(reg if raw_reg else F.relu(self.scales[l](reg)))
         return clss, bbox_reg, agn_hms
+
+    def scales_host(self) -> List[float]:
+        """The per-level Scale factors as host floats (read back once per weight version)."""
+        key = tuple((m.scale.data_ptr(), m.scale._version) for m in self.scales)
+        hit = self.__dict__.get("_scales_host")
+        if hit is None or hit[0] != key:
+            hit = (key, [float(m.scale.detach().reshape(-1)[0].item()) for m in self.scales])
+            self.__dict__["_scales_host"] = hit
+        return hit[1]
 
     # conv -> GroupNorm -> ReLU -> conv without writing the normalised map (statistics from the first convolution's
     # epilogue, affine + ReLU on the second one's operand): correct (tests/test_conv_gpu.py) but 0.37 ms per step SLOWER
@@ -178,9 +187,10 @@ class CenterNet(nn.Module):
     def propose_raw(self, features: Sequence[torch.Tensor], status: torch.Tensor, roi_cap: Optional[int] = None,
                     bounds: Optional[Sequence[torch.Tensor]] = None) -> RawProposals:
         """features[l]: [P,128,H_l,W_l] correlated maps, one row per (image, class) problem."""
-        _, reg, hm = self.centernet_head(features, bounds)
+        _, reg, hm = self.centernet_head(features, bounds, raw_reg=True)
         boxes, scores, loc, level_count, cand_count = ops.decode_topk(
-            hm, reg, self.strides, self.score_thresh, self.pre_nms_topk_test, status, hm_is_logit=True)
+            hm, reg, self.strides, self.score_thresh, self.pre_nms_topk_test, status, hm_is_logit=True,
+            reg_scale=self.centernet_head.scales_host())
         keep, pb, ps, pc = ops.nms_proposals(boxes, scores, cand_count, self.nms_thresh_test, self.post_nms_topk_test,
                                              roi_cap or self.roi_cap, status)
         return RawProposals(pb, ps, pc, keep, boxes, scores, loc, level_count, cand_count)

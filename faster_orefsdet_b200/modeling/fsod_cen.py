@@ -61,15 +61,6 @@ def build_proposal_generator(cfg, input_shape):
 class CenterNet2Detector(nn.Module):
     def __init__(self, cfg, pos_encoding=True):
         super().__init__()
-        # The reference computes in fp32 (SOLVER.AMP off, log:490-491; sm_75 has no TF32).  PyTorch lets cuDNN
-        # use TF32 for convolutions by default, which would put the heat-map 1e-3 away from the reference.
-        if os.environ.get("FOD_ALLOW_TF32", "0") != "1":
-            torch.backends.cudnn.allow_tf32 = False
-            torch.backends.cuda.matmul.allow_tf32 = False
-        # cuDNN's heuristic picks FFT / legacy SIMT engines for the fp32 convolutions of the backbone on sm_100;
-        # letting it time the candidates once per shape is worth ~20 % of a step (profiles/r1_step_breakdown.md).
-        if os.environ.get("FOD_CUDNN_BENCHMARK", "1") == "1":
-            torch.backends.cudnn.benchmark = True
         self.backbone = build_backbone(cfg)
         self.proposal_generator = build_proposal_generator(cfg, self.backbone.output_shape())
         self.roi_heads = build_roi_heads(cfg, self.backbone.output_shape())
@@ -374,7 +365,7 @@ class CenterNet2Detector(nn.Module):
         imgs = [x["image"] for x in batched_inputs]
         d = self.backbone.size_divisibility
         vov = getattr(self.backbone, "bottom_up", None)
-        if (not tcconv.ENABLED or vov is None or not imgs or any(im.dtype != torch.uint8 or im.dim() != 3 or im.shape != imgs[0].shape
+        if (vov is None or not imgs or any(im.dtype != torch.uint8 or im.dim() != 3 or im.shape != imgs[0].shape
                                                                  for im in imgs)
                 or imgs[0].shape[0] != 3 or imgs[0].shape[1] % d or imgs[0].shape[2] % d or self.device.type != "cuda"
                 or not vov._tc_path(torch.empty((1, 3, 1, 1), device=self.device))):

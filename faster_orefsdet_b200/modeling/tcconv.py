@@ -3,12 +3,12 @@
 A ``torch.nn.Conv2d`` (optionally followed by a frozen BatchNorm that is folded into it) is
 run on CUDA tensors through the C-ABI kernel: fp16-split operands on tcgen05 = fp32 accuracy, bias and
 ReLU fused, NHWC in and out, input and output allowed to be channel slices of wider NHWC
-buffers (so an OSA concat is written in place).  CPU tensors take PyTorch's own convolution:
-the backbone module is also what the CPU baseline of bench.py runs on the host cores.
+buffers (so an OSA concat is written in place).  There is no switch back to cuDNN.  CPU tensors take
+PyTorch's own convolution: the backbone module is also what the CPU baseline of bench.py runs on the
+host cores.
 """
 from __future__ import annotations
 
-import os
 import weakref
 from typing import Optional
 
@@ -18,13 +18,12 @@ from torch.nn import functional as F
 
 from .. import ops
 
-ENABLED = os.environ.get("FOD_TC_CONV", "1") == "1"      # 0: cuDNN convolutions (A/B timing only)
 _cache: "weakref.WeakKeyDictionary[nn.Module, tuple]" = weakref.WeakKeyDictionary()
 
 
 def supported(conv: nn.Conv2d, x: torch.Tensor) -> bool:
     k = conv.kernel_size[0]
-    return (ENABLED and x.is_cuda and x.dtype == torch.float32 and conv.kernel_size in ((1, 1), (3, 3))
+    return (x.is_cuda and x.dtype == torch.float32 and conv.kernel_size in ((1, 1), (3, 3))
             and (conv.stride == (1, 1) or (conv.stride == (2, 2) and k == 3))
             and conv.padding == (k // 2, k // 2) and conv.dilation == (1, 1)
             and conv.groups == 1 and conv.in_channels % 4 == 0)

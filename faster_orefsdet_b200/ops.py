@@ -136,8 +136,10 @@ def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3
 
 # --------------------------------------------------------------------------- D1-D3
 def decode_topk(hm: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[int], score_thresh: float,
-                pre_topk: int, status: Tensor, hm_is_logit: bool = True, cand_cap: Optional[int] = None):
-    """hm[l] [P,1,H,W], reg[l] [P,4,H,W] (either memory format) ->
+                pre_topk: int, status: Tensor, hm_is_logit: bool = True, cand_cap: Optional[int] = None,
+                reg_scale: Optional[Sequence[float]] = None):
+    """hm[l] [P,1,H,W], reg[l] [P,4,H,W] (either memory format; with ``reg_scale`` the raw bbox_pred output, the
+    kernel applies relu(reg_scale[l] * x) = the Scale + ReLU of centernet_head.py:157-160 as it reads it) ->
     (boxes [P,cap,4], scores [P,cap], loc [P,cap] i64, level_count [P,L] i32, cand_count [P] i32)
     (fsod_rpn.py:1071-1181)."""
     L = len(hm)
@@ -163,7 +165,8 @@ def decode_topk(hm: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[i
     level_count = torch.empty((P, L), dtype=torch.int32, device=dev)
     cand_count = torch.empty((P,), dtype=torch.int32, device=dev)
     lv = _levels(hm, strides)
-    _lib.check(_lib.lib().fod_decode_topk(_ptr_array(hm), _ptr_array(regs), lv, L, P, int(hm_is_logit), int(bool(cl)),
+    rs = None if reg_scale is None else (ctypes.c_float * L)(*[float(v) for v in reg_scale])
+    _lib.check(_lib.lib().fod_decode_topk(_ptr_array(hm), _ptr_array(regs), lv, L, P, int(hm_is_logit), int(bool(cl)), rs,
                                           float(score_thresh), int(pre_topk), cap, _ptr(boxes), _ptr(scores), _ptr(loc),
                                           _ptr(level_count), _ptr(cand_count), _ptr(status), _stream()),
                "fod_decode_topk")

@@ -111,6 +111,8 @@ int fod_correlate_levels(const float* const* q, const float* const* taps, const 
  * 1116-1181 and compute_grids :782-800.
  *   hm[l]   : [P][H_l][W_l]           agn_hm output (logits if hm_is_logit, else sigmoid already applied)
  *   reg[l]  : [P][H_l][W_l][4] if reg_channels_last else [P][4][H_l][W_l]; relu(scale*bbox_pred), NOT yet x stride
+ *   reg_scale : NULL, or a HOST array of num_levels floats (the CenterNetHead Scale factors, centernet_head.py:157-160):
+ *               reg[l] then is the RAW bbox_pred output and the kernel applies relu(reg_scale[l] * x) as it reads it
  *   boxes   : [P][cand_cap][4]        candidates, level-major, ascending location inside a level
  *   scores  : [P][cand_cap]           sqrt(p)
  *   loc     : [P][cand_cap] int64     location index y*W+x inside its level
@@ -120,7 +122,8 @@ int fod_correlate_levels(const float* const* q, const float* const* taps, const 
  * cand_cap must be >= num_levels * pre_topk.
  */
 int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_level_t* levels, int num_levels,
-                    int num_problems, int hm_is_logit, int reg_channels_last, float score_thresh, int pre_topk,
+                    int num_problems, int hm_is_logit, int reg_channels_last, const float* reg_scale, float score_thresh,
+                    int pre_topk,
                     int cand_cap, float* boxes, float* scores, int64_t* loc, int32_t* level_count,
                     int32_t* cand_count, uint32_t* status, fod_stream_t stream);
 
