@@ -40,7 +40,7 @@ _PROTOTYPES = {
     "fod_correlate_levels": ([ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _vp, _vp,
                               ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _vp], _i),
     "fod_decode_topk": ([ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _i,
-                         ctypes.POINTER(_f), _f, _i,
+                         ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_f), _f, _i,
                          _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_nms_proposals": ([_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_roi_align": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],

@@ -21,6 +21,7 @@ struct DecodeParams {
   const float* hm[FOD_MAX_LEVELS];
   const float* reg[FOD_MAX_LEVELS];
   int H[FOD_MAX_LEVELS], W[FOD_MAX_LEVELS], stride[FOD_MAX_LEVELS];
+  int hm_ps[FOD_MAX_LEVELS], reg_ps[FOD_MAX_LEVELS];   // pixel strides in floats (1 / 4 = dense)
   int num_levels;
   int hm_is_logit, reg_channels_last, reg_activate;
   float reg_scale[FOD_MAX_LEVELS];   // reg_activate: reg = relu(reg_scale[l] * raw) (Scale + ReLU of CenterNetHead)
@@ -59,10 +60,11 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
   int out_base = 0;
   for (int ll = 0; ll < l; ++ll) {
     const int nn = prm.H[ll] * prm.W[ll];
-    const float* hml = prm.hm[ll] + (size_t)p * nn;
+    const int hps = prm.hm_ps[ll];
+    const float* hml = prm.hm[ll] + (size_t)p * nn * hps;
     int local = 0;
     for (int i = tid; i < nn; i += kDecThreads) {
-      const float v = __ldg(hml + i);
+      const float v = __ldg(hml + (size_t)i * hps);
       const float pr = prm.hm_is_logit ? 1.0f / (1.0f + expf(-v)) : v;
       local += (pr > prm.thresh);
     }
@@ -70,11 +72,12 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
   }
   {
     const int H = prm.H[l], W = prm.W[l], n = H * W, stride = prm.stride[l];
-    const float* hm = prm.hm[l] + (size_t)p * n;
+    const int hps = prm.hm_ps[l], rps = prm.reg_ps[l];
+    const float* hm = prm.hm[l] + (size_t)p * n * hps;
     // ---- pass 0: keys + candidate count
     int local = 0;
     for (int i = tid; i < n; i += kDecThreads) {
-      float v = __ldg(hm + i);
+      float v = __ldg(hm + (size_t)i * hps);
       float pr = prm.hm_is_logit ? 1.0f / (1.0f + expf(-v)) : v;
       uint32_t k = (pr > prm.thresh) ? __float_as_uint(pr) : 0u;
       keys[i] = k;
@@ -197,8 +200,13 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
           float gy = __fadd_rn((float)(y * stride), half);
           float r0, r1, r2, r3;
           if (prm.reg_channels_last) {
-            float4 r = ldg4(prm.reg[l] + ((size_t)p * n + i) * 4);
-            r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
+            const float* rp = prm.reg[l] + ((size_t)p * n + i) * rps;
+            if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+              float4 r = ldg4(rp);
+              r0 = r.x; r1 = r.y; r2 = r.z; r3 = r.w;
+            } else {       // a channel slice of a wider NHWC buffer (the fused agn_hm | bbox_pred convolution output)
+              r0 = __ldg(rp); r1 = __ldg(rp + 1); r2 = __ldg(rp + 2); r3 = __ldg(rp + 3);
+            }
           } else {
             const float* rp = prm.reg[l] + (size_t)p * 4 * n + i;
             r0 = __ldg(rp); r1 = __ldg(rp + n); r2 = __ldg(rp + 2 * (size_t)n); r3 = __ldg(rp + 3 * (size_t)n);
@@ -237,7 +245,8 @@ using namespace fod;
 
 extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_level_t* levels,
                                int num_levels, int num_problems, int hm_is_logit, int reg_channels_last,
-                               const float* reg_scale, float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores,
+                               const int* hm_pixel_stride, const int* reg_pixel_stride, const float* reg_scale,
+                               float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores,
                                int64_t* loc, int32_t* level_count, int32_t* cand_count, uint32_t* status,
                                fod_stream_t stream) {
   FOD_REQUIRE(hm && reg && levels && boxes && scores && loc && level_count && cand_count && status,
@@ -257,6 +266,10 @@ extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, 
     prm.H[l] = levels[l].height;
     prm.W[l] = levels[l].width;
     prm.stride[l] = levels[l].stride;
+    prm.hm_ps[l] = hm_pixel_stride ? hm_pixel_stride[l] : 1;
+    prm.reg_ps[l] = reg_pixel_stride ? reg_pixel_stride[l] : 4;
+    FOD_REQUIRE(prm.hm_ps[l] >= 1 && prm.reg_ps[l] >= 4, "fod_decode_topk: bad pixel stride at level %d", l);
+    FOD_REQUIRE(!reg_pixel_stride || reg_channels_last, "fod_decode_topk: reg_pixel_stride needs the channels-last layout");
     int px = levels[l].height * levels[l].width;
     if (px > maxpix) maxpix = px;
   }

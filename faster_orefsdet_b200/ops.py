@@ -145,19 +145,36 @@ def decode_topk(hm: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[i
     L = len(hm)
     P = hm[0].shape[0]
     dev = hm[0].device
-    hm = [_chk(h, torch.float32, "hm").reshape(P, h.shape[-2], h.shape[-1]).contiguous() for h in hm]
-    regs, cl = [], None
+    # heat-maps: dense [P,H,W], or channel 0 of a wider NHWC buffer read in place through its pixel stride
+    hms, hm_ps = [], []
+    for h in hm:
+        _chk(h, torch.float32, "hm")
+        _, _, H, W = h.shape
+        s = h.stride()
+        ps = s[3] if W > 1 else (s[2] if H > 1 else 1)
+        if not ((W == 1 or s[3] == ps) and (H == 1 or s[2] == W * ps) and (P == 1 or s[0] == H * W * ps) and ps >= 1):
+            h, ps = h.reshape(P, H, W).contiguous(), 1
+        hms.append(h)
+        hm_ps.append(int(ps))
+    hm = hms
+    regs, cl, reg_ps = [], None, []
     for r in reg:
         _chk(r, torch.float32, "reg")
         n, c, h, w = r.shape
-        is_cl = r.stride() == (h * w * c, 1, w * c, c)
+        try:
+            ps = _pixel_stride(r, "reg")          # NHWC view, possibly a channel slice of a wider buffer
+            is_cl = c > 1 and ps >= 4
+        except _lib.FodError:
+            ps, is_cl = 4, False
         if cl is None:
             cl = is_cl
         if is_cl != cl:
             r = nhwc(r) if cl else r.contiguous()
+            ps = 4
         elif not is_cl:
             r = r.contiguous()
         regs.append(r)
+        reg_ps.append(int(ps))
     cap = cand_cap if cand_cap is not None else L * pre_topk
     boxes = torch.empty((P, cap, 4), dtype=torch.float32, device=dev)
     scores = torch.empty((P, cap), dtype=torch.float32, device=dev)
@@ -166,7 +183,9 @@ def decode_topk(hm: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[i
     cand_count = torch.empty((P,), dtype=torch.int32, device=dev)
     lv = _levels(hm, strides)
     rs = None if reg_scale is None else (ctypes.c_float * L)(*[float(v) for v in reg_scale])
-    _lib.check(_lib.lib().fod_decode_topk(_ptr_array(hm), _ptr_array(regs), lv, L, P, int(hm_is_logit), int(bool(cl)), rs,
+    hps = (ctypes.c_int * L)(*hm_ps)
+    rps = (ctypes.c_int * L)(*reg_ps) if cl else None
+    _lib.check(_lib.lib().fod_decode_topk(_ptr_array(hm), _ptr_array(regs), lv, L, P, int(hm_is_logit), int(bool(cl)), hps, rps, rs,
                                           float(score_thresh), int(pre_topk), cap, _ptr(boxes), _ptr(scores), _ptr(loc),
                                           _ptr(level_count), _ptr(cand_count), _ptr(status), _stream()),
                "fod_decode_topk")

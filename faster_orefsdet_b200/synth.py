@@ -73,6 +73,10 @@ def state_dict(shapes: Dict[str, Tuple[int, ...]], base_seed: int = 0) -> Dict[s
             out[name] = tensor(shape, seed, -0.06, 0.06)
         elif name.endswith("centernet_head.bbox_pred.weight"):
             out[name] = tensor(shape, seed, -0.12, 0.12)
+        elif any(t in name for t in ("cls_score_cor.weight", "cls_score_fc.weight", "cls_score_pr.weight")):
+            out[name] = tensor(shape, seed, -0.0004, 0.0004)     # FsodFastRCNNOutputLayers: logits stay unsaturated
+        elif "bbox_pred_cor.weight" in name:
+            out[name] = tensor(shape, seed, -0.0004, 0.0004)
         elif "cls_score.weight" in name:
             out[name] = tensor(shape, seed, -0.25, 0.25)
         elif "box_predictor.0.bbox_pred.weight" in name:

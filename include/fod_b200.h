@@ -111,6 +111,9 @@ int fod_correlate_levels(const float* const* q, const float* const* taps, const 
  * 1116-1181 and compute_grids :782-800.
  *   hm[l]   : [P][H_l][W_l]           agn_hm output (logits if hm_is_logit, else sigmoid already applied)
  *   reg[l]  : [P][H_l][W_l][4] if reg_channels_last else [P][4][H_l][W_l]; relu(scale*bbox_pred), NOT yet x stride
+ *   hm_pixel_stride / reg_pixel_stride : NULL (dense: 1 and 4), or HOST arrays of num_levels pixel strides in floats:
+ *               hm[l] / reg[l] then point at their first channel inside a wider NHWC buffer (the fused agn_hm | bbox_pred
+ *               convolution writes [P][H][W][8] = hm, l, t, r, b, 0, 0, 0); reg_pixel_stride needs reg_channels_last
  *   reg_scale : NULL, or a HOST array of num_levels floats (the CenterNetHead Scale factors, centernet_head.py:157-160):
  *               reg[l] then is the RAW bbox_pred output and the kernel applies relu(reg_scale[l] * x) as it reads it
  *   boxes   : [P][cand_cap][4]        candidates, level-major, ascending location inside a level
@@ -122,9 +125,8 @@ int fod_correlate_levels(const float* const* q, const float* const* taps, const 
  * cand_cap must be >= num_levels * pre_topk.
  */
 int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_level_t* levels, int num_levels,
-                    int num_problems, int hm_is_logit, int reg_channels_last, const float* reg_scale, float score_thresh,
-                    int pre_topk,
-                    int cand_cap, float* boxes, float* scores, int64_t* loc, int32_t* level_count,
+                    int num_problems, int hm_is_logit, int reg_channels_last, const int* hm_pixel_stride,
+                    const int* reg_pixel_stride, const float* reg_scale, float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores, int64_t* loc, int32_t* level_count,
                     int32_t* cand_count, uint32_t* status, fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
