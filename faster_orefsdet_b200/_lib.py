@@ -45,13 +45,15 @@ _PROTOTYPES = {
     "fod_nms_proposals": ([_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_roi_align": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
                       _i),
-    "fod_relation_head": ([_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.POINTER(_f), _vp, _vp, _vp, _vp,
+    "fod_roi_align_wide": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+                           _i),
+    "fod_relation_head": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.POINTER(_f), _vp, _vp, _vp, _vp,
                            _vp], _i),
     "fod_split_tf32": ([_vp, _vp, ctypes.c_size_t, _vp], _i),
     "fod_final_detect": ([_vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_batched_nms": ([_vp, _vp, _vp, _i, _d, _vp, _vp, _vp], _i),
     "fod_group_norm_workspace_bytes": ([_i, _i], ctypes.c_size_t),
-    "fod_group_norm_nhwc": ([_vp, _i, ctypes.c_long, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp], _i),
+    "fod_group_norm_nhwc": ([_vp, _i, ctypes.c_long, _i, _i, _vp, _vp, _f, _i, _vp, _vp, _i, _vp, _vp], _i),
     "fod_absmax": ([_vp, ctypes.c_size_t, _vp, _vp], _i),
     "fod_stem_patches": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "fod_stem_patches_u8": ([_vp, _i, _i, _i, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _vp], _i),
@@ -59,7 +61,7 @@ _PROTOTYPES = {
     "fod_maxpool3x3s2_nhwc": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _vp, ctypes.c_long, _vp], _i),
     "fod_conv2d_packed_floats": ([_i, _i, _i], ctypes.c_size_t),
     "fod_conv2d_pack_weights": ([_vp, _i, _i, _i, _vp, _vp], _i),
-    "fod_conv2d_nhwc": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_long, _vp, _vp,
+    "fod_conv2d_nhwc": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_long, _vp, _vp,
                          _i, _vp, _vp, _i, _vp, _vp, _vp], _i),
     "fod_group_norm_affine": ([_vp, _vp, _i, _i, _i, _i, ctypes.c_long, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_conv2d_tiles_per_image": ([_i, _i], _i),

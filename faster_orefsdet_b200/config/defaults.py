@@ -35,7 +35,7 @@ def get_cfg() -> CN:
     _C.MODEL.LOAD_PROPOSALS = False
 
     _C.MODEL.BACKBONE = CN()
-    _C.MODEL.BACKBONE.NAME = "build_fcos_vovnet_fpn_backbone"
+    _C.MODEL.BACKBONE.NAME = "build_resnet_backbone"      # detectron2's default; finetune_vovnet.yaml selects the VoVNet
     _C.MODEL.BACKBONE.FREEZE_AT = 2
 
     _C.MODEL.VOVNET = CN()
@@ -62,9 +62,35 @@ def get_cfg() -> CN:
     _C.MODEL.PROPOSAL_GENERATOR.MIN_SIZE = 0
 
     _C.MODEL.RPN = CN()
+    _C.MODEL.RPN.HEAD_NAME = "StandardRPNHead"
+    _C.MODEL.RPN.IN_FEATURES = ["res4"]
+    _C.MODEL.RPN.BBOX_REG_WEIGHTS = (1.0, 1.0, 1.0, 1.0)
+    _C.MODEL.RPN.PRE_NMS_TOPK_TRAIN = 12000
+    _C.MODEL.RPN.POST_NMS_TOPK_TRAIN = 2000
     _C.MODEL.RPN.PRE_NMS_TOPK_TEST = 1000
     _C.MODEL.RPN.POST_NMS_TOPK_TEST = 1000
     _C.MODEL.RPN.NMS_THRESH = 0.7
+
+    _C.MODEL.ANCHOR_GENERATOR = CN()
+    _C.MODEL.ANCHOR_GENERATOR.NAME = "DefaultAnchorGenerator"
+    _C.MODEL.ANCHOR_GENERATOR.SIZES = [[32, 64, 128, 256, 512]]
+    _C.MODEL.ANCHOR_GENERATOR.ASPECT_RATIOS = [[0.5, 1.0, 2.0]]
+    _C.MODEL.ANCHOR_GENERATOR.ANGLES = [[-90, 0, 90]]
+    _C.MODEL.ANCHOR_GENERATOR.OFFSET = 0.0
+
+    _C.MODEL.RESNETS = CN()
+    _C.MODEL.RESNETS.DEPTH = 50
+    _C.MODEL.RESNETS.OUT_FEATURES = ["res4"]
+    _C.MODEL.RESNETS.NUM_GROUPS = 1
+    _C.MODEL.RESNETS.NORM = "FrozenBN"
+    _C.MODEL.RESNETS.WIDTH_PER_GROUP = 64
+    _C.MODEL.RESNETS.STRIDE_IN_1X1 = True
+    _C.MODEL.RESNETS.RES5_DILATION = 1
+    _C.MODEL.RESNETS.RES2_OUT_CHANNELS = 256
+    _C.MODEL.RESNETS.STEM_OUT_CHANNELS = 64
+    _C.MODEL.RESNETS.DEFORM_ON_PER_STAGE = [False, False, False, False]
+    _C.MODEL.RESNETS.DEFORM_MODULATED = False
+    _C.MODEL.RESNETS.DEFORM_NUM_GROUPS = 1
 
     c = _C.MODEL.CENTERNET = CN()
     c.NUM_CLASSES = 1

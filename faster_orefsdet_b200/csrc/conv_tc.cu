@@ -135,6 +135,9 @@ struct Params {
   int cin_chunks, chunks, parts, chunks_per_part;
   int n_groups, n_group, nhalf, ncol32, cout;
   int relu, num_pairs, pair_units, n_amax, ho, wo, cin;
+  int x_amax_stride;    // 0: x_amax holds n_amax scalars (one scale for the whole batch); N: x_amax is [n_amax][N], the scale
+                        // of image n comes from column n, so an image's result does not depend on its batch mates
+  int y_amax_per_image; // y_amax is [N]: max|y| per image
   uint32_t q_stage_bytes, q_stage_stride;
 };
 
@@ -160,11 +163,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   constexpr int stages = kStages;
   constexpr uint32_t acc_w = 128u, col_acc = kColAcc, b_stage = kBStageBytes;
   float xs = 1.f, xs_inv = 1.f;   // input scale 2^e (converters) and its inverse (epilogue)
-  {
+  auto image_scale = [&](int n) {   // (re)computes xs / xs_inv for image n (any n in the batch-wide mode)
     float amax = 0.f;
-    for (int i = 0; i < P.n_amax; ++i) amax = fmaxf(amax, __ldg(P.x_amax + i));
+    const float* col = P.x_amax + (P.x_amax_stride ? n : 0);
+    const int step = P.x_amax_stride ? P.x_amax_stride : 1;
+    for (int i = 0; i < P.n_amax; ++i) amax = fmaxf(amax, __ldg(col + (size_t)i * step));
     pow2_scale(amax, xs, xs_inv);
-  }
+  };
+  image_scale(0);
 
   if (tid == 0) {
     for (int s = 0; s < kQStages; ++s) {
@@ -353,7 +359,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t row_s = sbase + kOffSum + (uint32_t)((m >> 3) * 1024 + (m & 7) * 128);
     const uint32_t bias_s = sbase + kOffBias;
     const int ncol32 = P.ncol32, parts = P.parts;
-    const float rescale = xs_inv * __ldg(P.w_inv);   // undoes the two power-of-two operand scales (exact)
+    const float w_inv = __ldg(P.w_inv);
+    float rescale = xs_inv * w_inv;   // undoes the two power-of-two operand scales (exact)
     // The tensor core truncates its fp32 accumulator toward zero after every MMA: a part that accumulated n MMAs
     // comes out smaller by ~kappa * n / 2 of its value in expectation (calibrated on the hardware, tools/rz_calib.py).
     // Each part is scaled back by that factor before it is added; what remains is the unbiased part of the rounding.
@@ -367,6 +374,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int n = tc_ / P.tiles_per_img, tt = tc_ - n * P.tiles_per_img;
       const int ty = tt / P.tiles_x, tx = tt - ty * P.tiles_x;
       const int ch0 = unit_grp(i) * P.n_group;
+      if (P.x_amax_stride) {
+        image_scale(n);
+        rescale = xs_inv * w_inv;
+      }
       const int oy = ty * kTileH + (m >> 4), ox = tx * kTileW + (m & 15);
       const bool px_valid = do_store && oy < P.ho && ox < P.wo;
       const float* res_px = nullptr;   // this pixel's row of the residual map
@@ -431,6 +442,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
       }
+      if (P.y_amax && P.y_amax_per_image) {   // this unit's image: one atomic per warp and unit
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+        if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(P.y_amax + n), wmax);
+        vmax = 0.f;
+      }
       fence_proxy_async_smem();
       named_bar_sync(1, 128);
       if (issuer && do_store) {
@@ -472,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
     if (issuer) tma_store_wait<0>();
-    if (P.y_amax) {   // non-negative floats order like their bit patterns; a NaN becomes a huge bound (scale 1 downstream)
+    if (P.y_amax && !P.y_amax_per_image) {   // non-negative floats order like their bit patterns; a NaN becomes a huge bound (scale 1 downstream)
       const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
       if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(P.y_amax), wmax);
     }
@@ -557,6 +573,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int i = 0; in_range(i); ++i) {
       const int unit_t = min(unit_tile(i), P.tiles_total - 1);
       const int unit_n = unit_t / P.tiles_per_img;
+      if (P.x_amax_stride) image_scale(unit_n);
       {
         const int tt = unit_t - unit_n * P.tiles_per_img, ty = tt / P.tiles_x, tx = tt - ty * P.tiles_x;
         in_y0 = ty * kTileH * P.stride - (ksz >> 1);
@@ -803,7 +820,7 @@ extern "C" int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, i
 }
 
 extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax,
-                               int n_amax, const float* packed, const float* bias, int cout, int ksize, int stride,
+                               int n_amax, int amax_per_image, const float* packed, const float* bias, int cout, int ksize, int stride,
                                int relu, float* y, long y_pixel_stride, float* y_amax, const float* residual,
                                int residual_upsample2, const float* a_gate, const float* a_shift, int a_relu, float* colsum,
                                float* colsumsq, fod_stream_t stream) {
@@ -861,6 +878,8 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.x_amax = x_amax;
   prm.n_amax = n_amax;
   prm.y_amax = y_amax;
+  prm.x_amax_stride = (amax_per_image & 1) ? n : 0;
+  prm.y_amax_per_image = (amax_per_image & 2) ? 1 : 0;
   prm.ho = ho;
   prm.wo = wo;
   prm.a_gate = a_gate;

@@ -91,7 +91,9 @@ struct Params {
   Level lv[FOD_MAX_LEVELS];
   const float* w3;
   const float* b3;
-  float* attn_amax[FOD_MAX_LEVELS];   // null or device scalar per level (zeroed by the caller): raised to max(attn)
+  float* attn_amax[FOD_MAX_LEVELS];   // null or, per level, [B*C] device floats (zeroed by the caller): entry p is raised to
+                                      // max(attn of problem p) - per problem, so that the operand scale of the convolution
+                                      // that consumes a map does not depend on the other problems of the batch
   // problems of this launch: images x classes [class_begin, class_begin + class_count) of num_classes
   int num_levels, num_classes, class_begin, class_count, total_tiles, num_pairs;
   // tap sets of this launch, set = level * class_count + class (filled on the host from the caller's HOST taps)
@@ -419,7 +421,6 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
     const int m = qd * 32 + lane;  // pixel row of the tile == TMEM lane
     const uint32_t acc_empty_leader = map_to_cta(acc_empty(0), 0);
     const bool issuer = (warp == kWarpEpi0 && lane == 0);
-    float lmax0 = 0.f, lmax1 = 0.f, lmax2 = 0.f;   // running max of each level's output over this lane's pixels
     for (int i = 0; iter_valid(i); ++i) {
       int t = tile_of(i);
       bool do_store = t < T;
@@ -462,21 +463,14 @@ __global__ void __launch_bounds__(kThreads, 1) correlate_tc_kernel(const __grid_
           tma_store_commit();
         }
       }
-      if (px_valid) {
-        if (tcd.level == 0) lmax0 = fmaxf(lmax0, vmax);
-        else if (tcd.level == 1) lmax1 = fmaxf(lmax1, vmax);
-        else lmax2 = fmaxf(lmax2, vmax);
+      // max of this problem's output (>= 0 after the ReLU) = the operand bound the tower convolution needs
+      // (fod_conv2d_nhwc x_amax, per image): one atomic per warp and tile, no extra pass over the maps
+      if (P.attn_amax[tcd.level]) {
+        const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(px_valid ? vmax : 0.f));
+        if (lane == 0 && wmax) atomicMax(reinterpret_cast<unsigned int*>(P.attn_amax[tcd.level] + pg), wmax);
       }
     }
     if (issuer) tma_store_wait<0>();
-    // max of each level's output (>= 0 after the ReLU) = the operand bound the tower convolution needs (fod_conv2d_nhwc
-    // x_amax): one atomic per warp and level for the whole launch, no extra pass over the maps
-#pragma unroll
-    for (int l = 0; l < FOD_MAX_LEVELS; ++l) {
-      const float lm = l == 0 ? lmax0 : (l == 1 ? lmax1 : lmax2);
-      const uint32_t wmax = __reduce_max_sync(0xffffffffu, __float_as_uint(lm));
-      if (lane == 0 && wmax && l < P.num_levels && P.attn_amax[l]) atomicMax(reinterpret_cast<unsigned int*>(P.attn_amax[l]), wmax);
-    }
   } else if (warp >= kWarpSten0) {
     // ------------------------------------------------------------------ stencil: build A in tensor memory
     StencilCtx cx;

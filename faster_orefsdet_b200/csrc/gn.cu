@@ -43,13 +43,16 @@ __global__ void __launch_bounds__(kThreads) stats_kernel(const float* __restrict
 __global__ void __launch_bounds__(kThreads) apply_kernel(const float* __restrict__ x, float* __restrict__ y, long hw,
                                                          int channels, int cpg, int groups, const double* __restrict__ stats,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                         float eps, int relu, size_t total4, float* __restrict__ y_amax) {
+                                                         float eps, int relu, size_t total4, float* __restrict__ y_amax,
+                                                         int amax_per_map) {
+  // grid = (CTAs per map, maps); total4 = float4 elements of ONE map
   const int c4n = channels >> 2;
   float vmax = 0.f;
   const double inv_n = 1.0 / ((double)hw * cpg);
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total4; i += (size_t)gridDim.x * kThreads) {
-    const int c4 = (int)(i % c4n);
-    const size_t map = i / ((size_t)c4n * hw);
+  const size_t map = blockIdx.y;
+  for (size_t il = (size_t)blockIdx.x * kThreads + threadIdx.x; il < total4; il += (size_t)gridDim.x * kThreads) {
+    const size_t i = map * total4 + il;
+    const int c4 = (int)(il % c4n);
     const int g = (c4 * 4) / cpg;
     const double* st = stats + (map * groups + g) * 2;
     const double mean = st[0] * inv_n;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(kThreads) apply_kernel(const float* __restrict
   }
   if (y_amax) {
     const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
-    if ((threadIdx.x & 31) == 0 && w) atomicMax(reinterpret_cast<unsigned int*>(y_amax), w);
+    if ((threadIdx.x & 31) == 0 && w) atomicMax(reinterpret_cast<unsigned int*>(y_amax + (amax_per_map ? map : 0)), w);
   }
 }
 
@@ -133,8 +136,8 @@ using namespace fod;
 extern "C" size_t fod_group_norm_workspace_bytes(int maps, int groups) { return (size_t)maps * groups * 2 * sizeof(double); }
 
 extern "C" int fod_group_norm_nhwc(const float* x, int maps, long hw, int channels, int groups, const float* gamma,
-                                   const float* beta, float eps, int relu, float* y, float* y_amax, void* workspace,
-                                   fod_stream_t stream) {
+                                   const float* beta, float eps, int relu, float* y, float* y_amax, int amax_per_map,
+                                   void* workspace, fod_stream_t stream) {
   FOD_REQUIRE(x && y && workspace, "fod_group_norm_nhwc: null pointer");
   FOD_REQUIRE(maps >= 0 && hw > 0 && channels > 0 && groups > 0 && channels % groups == 0, "fod_group_norm_nhwc: bad sizes");
   const int cpg = channels / groups;
@@ -144,21 +147,22 @@ extern "C" int fod_group_norm_nhwc(const float* x, int maps, long hw, int channe
               "fod_group_norm_nhwc: pointers must be 16-byte aligned");
   if (maps == 0) return FOD_OK;
   FOD_CUDA_CALL(cudaMemsetAsync(workspace, 0, fod_group_norm_workspace_bytes(maps, groups), as_stream(stream)));
-  // ~8 CTAs per SM worth of slabs over all maps (the pass is bound by the latency of its loads: 2 CTAs per SM reached
-  // 2.4 TB/s)
-  long slabs = (148 * 8 + maps - 1) / maps;
-  const long max_slabs = (hw + 63) / 64;
-  if (slabs > max_slabs) slabs = max_slabs;
+  // Slabs of 64 pixels, whatever the number of maps: the per-thread fp32 partial sums of a map are then the same in
+  // every batch (the statistics of a map must not depend on its batch mates); 100 slabs per 80 x 80 map keep the pass at
+  // several CTAs per SM (it is bound by the latency of its loads).
+  long slabs = (hw + 63) / 64;
   if (slabs < 1) slabs = 1;
   gn::stats_kernel<<<dim3((unsigned)slabs, (unsigned)maps), gn::kThreads, 2 * groups * sizeof(double), as_stream(stream)>>>(
       x, hw, channels, cpg, groups, static_cast<double*>(workspace));
   FOD_CUDA_LAUNCH_CHECK("fod_group_norm_nhwc (stats)");
-  const size_t total4 = (size_t)maps * hw * (channels / 4);
+  const size_t total4 = (size_t)hw * (channels / 4);      // per map
   size_t blocks = (total4 + gn::kThreads - 1) / gn::kThreads;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  gn::apply_kernel<<<(unsigned)blocks, gn::kThreads, 0, as_stream(stream)>>>(x, y, hw, channels, cpg, groups,
-                                                                            static_cast<const double*>(workspace), gamma, beta,
-                                                                            eps, relu, total4, y_amax);
+  const size_t want = (size_t)(148 * 16 + maps - 1) / maps;
+  if (blocks > want) blocks = want;
+  if (blocks < 1) blocks = 1;
+  gn::apply_kernel<<<dim3((unsigned)blocks, (unsigned)maps), gn::kThreads, 0, as_stream(stream)>>>(
+      x, y, hw, channels, cpg, groups, static_cast<const double*>(workspace), gamma, beta, eps, relu, total4, y_amax,
+      amax_per_map);
   FOD_CUDA_LAUNCH_CHECK("fod_group_norm_nhwc (apply)");
   return FOD_OK;
 }

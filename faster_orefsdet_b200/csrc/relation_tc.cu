@@ -85,6 +85,8 @@ struct Params {
   const float* x_amax;    // [n_amax] bounds of max|pooled| (= of the feature maps); their maximum fixes the A scale
   const float* w_inv;     // 1 / weight scale (tail of the packed weights)
   int n_amax;
+  int amax_stride;        // 0: n_amax scalars (one scale per call); B: x_amax is [n_amax][B], a unit is scaled with column
+                          // (problem / classes) - the bounds of ITS image, so batch mates do not influence a result
   const float* bias_cls;  // [C][128]
   const float* rois;      // [P][roi_cap][4]
   const int32_t* roi_count;
@@ -140,15 +142,20 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
   const uint32_t rank = blockIdx.x & 1;  // == %cluster_ctarank for cluster dims (2,1,1)
   const int pair = blockIdx.x >> 1;
   float xs = 1.f, xs_inv = 1.f;   // operand scale 2^e of the pooled rows (converters) and its inverse (epilogue)
-  {
+  auto image_scale = [&](int img) {
     float amax = 0.f;
-    for (int i = 0; i < P.n_amax; ++i) amax = fmaxf(amax, __ldg(P.x_amax + i));
+    const float* col = P.x_amax + (P.amax_stride ? img : 0);
+    const int step = P.amax_stride ? P.amax_stride : 1;
+    for (int i = 0; i < P.n_amax; ++i) amax = fmaxf(amax, __ldg(col + (size_t)i * step));
     const int E = (int)((__float_as_uint(amax) >> 23) & 0xFF);
+    xs = 1.f;
+    xs_inv = 1.f;
     if (E >= 32 && E <= 240) {     // amax * 2^e in [2^13, 2^14); 1 for zero / denormal-range / non-finite bounds
       xs = __uint_as_float((uint32_t)(267 - E) << 23);
       xs_inv = __uint_as_float((uint32_t)(E - 13) << 23);
     }
-  }
+  };
+  image_scale(0);
 
   const uint32_t bar0 = sbase + kOffBars;
   auto a_full = [&](int s) { return bar0 + 8u * s; };                       // TMA -> converters (A chunk landed)
@@ -327,10 +334,15 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
     const int m = qd * 32 + lane;
     const uint32_t acc_empty_leader = map_to_cta(acc_empty(0), 0);
     uint32_t gp = 0;
-    const float rescale = xs_inv * __ldg(P.w_inv);   // undoes the two power-of-two operand scales (exact)
+    const float w_inv = __ldg(P.w_inv);
+    float rescale = xs_inv * w_inv;   // undoes the two power-of-two operand scales (exact)
     const uint32_t sum_s = sbase + kOffSum + (uint32_t)m * 16;  // + col_group * 2048: lanes = consecutive 16 B
     for (int i = 0; in_range(i); ++i) {
       const Slot me = decode_unit(P, pref, slot_of(i, rank));
+      if (P.amax_stride) {
+        image_scale(me.p / P.classes);
+        rescale = xs_inv * w_inv;
+      }
       // per-class folded bias of this unit -> shared memory (read back as broadcast)
       const int c = me.p % P.classes;
       const uint32_t bias_s = sbase + kOffBias;
@@ -419,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) relation_tc_kernel(const __grid_c
     const uint32_t arow = (uint32_t)(m * 128);
     uint32_t g = 0;
     for (int i = 0; in_range(i); ++i) {
+      if (P.amax_stride) image_scale(decode_unit(P, pref, slot_of(i, rank)).p / P.classes);
       for (int kc = 0; kc < kNumChunks; ++kc, ++g) {
         if ((int)(g % kConvSets) != set) continue;
         const int s = g % kStages;
@@ -479,7 +492,8 @@ extern "C" int fod_split_tf32(const float* src, float* hi_lo, size_t n, fod_stre
   return FOD_OK;
 }
 
-extern "C" int fod_relation_head(const float* pooled, const float* x_amax, int n_amax, const float* w_fold_packed,
+extern "C" int fod_relation_head(const float* pooled, const float* x_amax, int n_amax, int amax_per_image,
+                                 const float* w_fold_packed,
                                  const float* bias_cls, const float* w_out, const float* b_out, const float* rois,
                                  const int32_t* roi_count, int num_problems, int problems_per_image, int roi_cap,
                                  const float* reg_weights, float* det_boxes, float* det_scores, float* logits, float* deltas,
@@ -509,6 +523,7 @@ extern "C" int fod_relation_head(const float* pooled, const float* x_amax, int n
   prm.w_inv = w_fold_packed + (size_t)kC * rtc::kK;   // two fp16 planes = kC * kK floats
   prm.x_amax = x_amax;
   prm.n_amax = n_amax;
+  prm.amax_stride = amax_per_image ? num_problems / problems_per_image : 0;
   prm.bias_cls = bias_cls;
   prm.rois = rois;
   prm.roi_count = roi_count;

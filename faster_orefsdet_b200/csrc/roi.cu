@@ -17,6 +17,7 @@ struct RoiParams {
   int roi_cap;
   int R;        // output resolution
   int tiled;    // output layout, see roi_align_kernel
+  int pix;      // floats per pixel of the maps = channels (a multiple of 128; blockIdx.z selects the 128-channel block)
 };
 
 // d2 poolers.py:50-58, fp32 like torch: floor(4 + log2(sqrt(area)/224 + 1e-8)) clamped to the
@@ -69,10 +70,11 @@ constexpr int kMaxTaps = 8;             // distinct rows / columns one bin can t
 // interpolation weight of each.  Consecutive samples of a bin share a row (the upper neighbour of one is the lower
 // neighbour of the next), so a bin with a g x g grid reads (g+1)^2 pixels instead of 4 g^2 taps.  Lists are padded
 // to the ROI-wide maximum length with zero-weight entries so that the hot loop has a compile-time trip count.
+constexpr int kMaxBins = 16;            // per axis (resolution 4, 8 or 14)
 struct AxisTaps {
-  int off[8][kMaxTaps];   // element offset of the row / column inside the map (index * row pitch or * 128)
-  float w[8][kMaxTaps];
-  int n[8];
+  int off[kMaxBins][kMaxTaps];   // element offset of the row / column inside the map (index * row pitch or * channels)
+  float w[kMaxBins][kMaxTaps];
+  int n[kMaxBins];
 };
 
 __device__ __forceinline__ void build_axis_taps(AxisTaps& t, int bin, float start, float bin_size, int grid, int size,
@@ -152,7 +154,7 @@ __device__ __forceinline__ void roi_accumulate(const AxisTaps& xt, const AxisTap
 // One CTA per ROI; warp = (bin row, half of the bin columns), lane = 4 channels: every tap is one fully coalesced
 // 512-byte row of the NHWC map, 4 accumulators per lane keep the register count low enough for full occupancy.
 template <int R>
-__global__ void __launch_bounds__(R * 64, 2)
+__global__ void __launch_bounds__(R * 64, R > 8 ? 1 : 2)
 roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* __restrict__ roi_count,
                  float* __restrict__ pooled, int32_t* __restrict__ out_level) {
   __shared__ __align__(16) AxisTaps xt, yt;
@@ -179,7 +181,7 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
     const float roi_w = __fsub_rn(end_w, start_w), roi_h = __fsub_rn(end_h, start_h);
     const int grid_h = (int)ceilf(__fdiv_rn(roi_h, (float)R));
     const int grid_w = (int)ceilf(__fdiv_rn(roi_w, (float)R));
-    geom.f = fbase + (size_t)(p / prm.C) * H * W * kC;
+    geom.f = fbase + (size_t)(p / prm.C) * H * W * prm.pix;
     geom.W = W;
     geom.inv_count = 1.0f / fmaxf((float)(grid_h * grid_w), 1.0f);
     geom.tables = grid_h <= kMaxGrid && grid_w <= kMaxGrid;
@@ -197,11 +199,11 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
   const int W = __float_as_int(gbox[6]), H = __float_as_int(gbox[7]);
   const int grid_w = __float_as_int(gbox[4]), grid_h = __float_as_int(gbox[5]);
   if (tables) {
-    if (threadIdx.x < R) build_axis_taps(xt, threadIdx.x, gbox[0], gbox[2], grid_w, W, kC);
-    else if (threadIdx.x >= 32 && threadIdx.x < 32 + R) build_axis_taps(yt, threadIdx.x - 32, gbox[1], gbox[3], grid_h, H, W * kC);
+    if (threadIdx.x < R) build_axis_taps(xt, threadIdx.x, gbox[0], gbox[2], grid_w, W, prm.pix);
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + R) build_axis_taps(yt, threadIdx.x - 32, gbox[1], gbox[3], grid_h, H, W * prm.pix);
   }
   __syncthreads();
-  const float* f = geom.f + lane * 4;
+  const float* f = geom.f + blockIdx.z * kC + lane * 4;   // this CTA's 128-channel block of the pixel
   const int ph = warp >> 1, pw0 = (warp & 1) * (R / 2);
   float4 acc[R / 2];
 #pragma unroll
@@ -223,14 +225,14 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
     for (int iy = 0; iy < grid_h; ++iy) {
       const AxisSample ys = axis_sample(gbox[1], gbox[3], ph, iy, grid_h, H);
       if (ys.w_lo == 0.f && ys.w_hi == 0.f) continue;
-      const float* row_lo = f + (size_t)ys.lo * W * kC;
-      const float* row_hi = f + (size_t)ys.hi * W * kC;
+      const float* row_lo = f + (size_t)ys.lo * W * prm.pix;
+      const float* row_hi = f + (size_t)ys.hi * W * prm.pix;
 #pragma unroll
       for (int j = 0; j < R / 2; ++j) {
         for (int ix = 0; ix < grid_w; ++ix) {
           const AxisSample xs = axis_sample(gbox[0], gbox[2], pw0 + j, ix, grid_w, W);
-          const float4 v1 = ldg4(row_lo + (size_t)xs.lo * kC), v2 = ldg4(row_lo + (size_t)xs.hi * kC);
-          const float4 v3 = ldg4(row_hi + (size_t)xs.lo * kC), v4 = ldg4(row_hi + (size_t)xs.hi * kC);
+          const float4 v1 = ldg4(row_lo + (size_t)xs.lo * prm.pix), v2 = ldg4(row_lo + (size_t)xs.hi * prm.pix);
+          const float4 v3 = ldg4(row_hi + (size_t)xs.lo * prm.pix), v4 = ldg4(row_hi + (size_t)xs.hi * prm.pix);
           const float w1 = ys.w_lo * xs.w_lo, w2 = ys.w_lo * xs.w_hi, w3 = ys.w_hi * xs.w_lo, w4 = ys.w_hi * xs.w_hi;
           acc[j].x += w1 * v1.x + w2 * v2.x + w3 * v3.x + w4 * v4.x;
           acc[j].y += w1 * v1.y + w2 * v2.y + w3 * v3.y + w4 * v4.y;
@@ -250,8 +252,8 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
     out = pooled + ((((size_t)p * units + (r >> 7)) * 256 + (lane >> 3)) * 128 + (r & 127)) * 32 + (lane & 7) * 4;
     bin_stride = (size_t)4 * 128 * 32;  // next bin = 4 k-chunks further
   } else {
-    out = pooled + ((size_t)p * prm.roi_cap + r) * R * R * kC + lane * 4;
-    bin_stride = kC;
+    out = pooled + ((size_t)p * prm.roi_cap + r) * R * R * prm.pix + blockIdx.z * kC + lane * 4;
+    bin_stride = prm.pix;
   }
   const float inv_count = geom.inv_count;
 #pragma unroll
@@ -265,13 +267,16 @@ roi_align_kernel(RoiParams prm, const float* __restrict__ rois, const int32_t* _
 
 using namespace fod;
 
-extern "C" int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
-                             int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap,
-                             int resolution, int tiled, float* pooled, int32_t* out_level, fod_stream_t stream) {
+extern "C" int fod_roi_align_wide(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
+                                  int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap,
+                                  int resolution, int channels, int tiled, float* pooled, int32_t* out_level,
+                                  fod_stream_t stream) {
   FOD_REQUIRE(feat && levels && rois && pooled, "fod_roi_align: null pointer");
   FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_roi_align: num_levels %d out of range", num_levels);
   FOD_REQUIRE(batch >= 0 && problems_per_image > 0 && roi_cap > 0, "fod_roi_align: bad sizes");
-  FOD_REQUIRE(resolution == 8 || resolution == 4, "fod_roi_align: pooler resolution must be 8 or 4 (POOLER_RESOLUTION / _2)");
+  FOD_REQUIRE(resolution == 8 || resolution == 4 || resolution == 14,
+              "fod_roi_align: pooler resolution must be 8, 4 (POOLER_RESOLUTION / _2) or 14 (the C4 heads)");
+  FOD_REQUIRE(channels >= kC && channels % kC == 0 && channels / kC <= 65535, "fod_roi_align: channels must be a multiple of 128");
   long P = (long)batch * problems_per_image;
   if (P == 0) return FOD_OK;
   FOD_REQUIRE(P <= 65535, "fod_roi_align: batch*classes %ld > 65535", P);
@@ -290,14 +295,23 @@ extern "C" int fod_roi_align(const float* const* feat, const fod_level_t* levels
   prm.C = problems_per_image;
   prm.roi_cap = roi_cap;
   prm.R = resolution;
-  FOD_REQUIRE(!tiled || resolution == 8, "fod_roi_align: the tiled layout needs resolution 8");
+  prm.pix = channels;
+  FOD_REQUIRE(!tiled || (resolution == 8 && channels == kC), "fod_roi_align: the tiled layout needs resolution 8 and 128 channels");
   prm.tiled = tiled ? 1 : 0;
-  dim3 grid(roi_cap, (unsigned)P);
+  dim3 grid(roi_cap, (unsigned)P, (unsigned)(channels / kC));
   if (resolution == 8)
     roi_align_kernel<8><<<grid, 512, 0, as_stream(stream)>>>(prm, rois, roi_count, pooled, out_level);
-  else
+  else if (resolution == 4)
     roi_align_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(prm, rois, roi_count, pooled, out_level);
+  else
+    roi_align_kernel<14><<<grid, 896, 0, as_stream(stream)>>>(prm, rois, roi_count, pooled, out_level);
   FOD_CUDA_LAUNCH_CHECK("fod_roi_align");
   return FOD_OK;
 }
 
+extern "C" int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
+                             int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap,
+                             int resolution, int tiled, float* pooled, int32_t* out_level, fod_stream_t stream) {
+  return fod_roi_align_wide(feat, levels, num_levels, batch, problems_per_image, rois, roi_count, roi_cap, resolution, kC,
+                            tiled, pooled, out_level, stream);
+}

@@ -4,7 +4,10 @@ from ..compat import BACKBONE_REGISTRY, META_ARCH_REGISTRY, PROPOSAL_GENERATOR_R
 from .backbone import build_backbone, build_fcos_vovnet_fpn_backbone
 from .centernet import CenterNet, CenterNetHead
 from .fsod_cen import CenterNet2Detector, PendingBatch
+from .fsod_heads import FsodFastRCNNOutputLayers, FsodRes5ROIHeads
 from .fsod_rcnn import FsodRCNN
+from .resnet import build_resnet_backbone
+from .rpn import FsodRPN
 from .prototypes import PrototypeBank, SM_Block
 from .roi_heads import ROI_HEADS_REGISTRY, CustomCascadeROIHeads, build_roi_heads
 
@@ -18,5 +21,5 @@ def build_model(cfg):
 
 
 __all__ = ["build_model", "build_backbone", "build_roi_heads", "CenterNet", "CenterNetHead", "CenterNet2Detector",
-           "FsodRCNN", "CustomCascadeROIHeads", "PrototypeBank", "SM_Block", "META_ARCH_REGISTRY",
+           "FsodRCNN", "FsodRPN", "FsodRes5ROIHeads", "FsodFastRCNNOutputLayers", "build_resnet_backbone", "CustomCascadeROIHeads", "PrototypeBank", "SM_Block", "META_ARCH_REGISTRY",
            "PROPOSAL_GENERATOR_REGISTRY", "BACKBONE_REGISTRY", "ROI_HEADS_REGISTRY"]

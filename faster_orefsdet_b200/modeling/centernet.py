@@ -118,10 +118,10 @@ class CenterNetHead(nn.Module):
         while i < len(mods):
             m = mods[i]
             if isinstance(m, nn.Conv2d):
-                t, bound = tcconv.conv(t, m, x_amax=bound), None
+                t, bound = tcconv.conv(t, m, x_amax=None if bound is None else bound.reshape(1, -1) if bound.numel() == t.shape[0] and t.shape[0] > 1 else bound), None
             elif isinstance(m, nn.GroupNorm) and m.num_channels % (4 * m.num_groups) == 0:
                 fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)      # GN + ReLU in one pass, in place
-                bound = ops.new_amax(t.device)
+                bound = ops.new_amax(t.device, t.shape[0])      # one bound per problem: batch mates do not set a map's scale
                 t = ops.group_norm_nhwc(t, m.num_groups, m.weight, m.bias, m.eps, relu=fuse, inplace=True, y_amax=bound)
                 i += int(fuse)
             elif isinstance(m, nn.ReLU):
@@ -129,6 +129,8 @@ class CenterNetHead(nn.Module):
             else:
                 t, bound = m(t).contiguous(memory_format=torch.channels_last), None
             i += 1
+        if bound is not None and bound.numel() == t.shape[0] and t.shape[0] > 1:
+            bound = bound.reshape(1, -1)                                          # [1, P]: per-image operand scales
         y = tcconv.conv(t, self.agn_hm, extra=self.bbox_pred, x_amax=bound)      # [P, 8, H, W]: hm | l t r b | 0 0 0
         return y[:, 0:1], y[:, 1:5]
 

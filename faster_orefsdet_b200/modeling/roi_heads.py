@@ -124,12 +124,15 @@ class CustomCascadeROIHeads(nn.Module):
                    status: torch.Tensor, feature_bounds: Optional[Sequence[torch.Tensor]] = None):
         """features[l] [B,128,H,W] raw backbone maps; rois [B*C,cap,4]; returns the padded
         outputs of ops.final_detect plus the per-ROI (boxes, scores).  ``feature_bounds[l]``: device scalar bounding
-        max|features[l]| when the producer reported it (the FPN output convolutions do); computed otherwise."""
+        max|features[l]|, or [B] floats with one bound per image, when the producer reported it (the FPN output
+        convolutions do); computed otherwise."""
         w_fold, w_out, b_out = self.folded()
         pooled = ops.roi_align(features, self.strides, rois, roi_count, num_classes, self.pooler_resolution, tiled=True)
+        B = features[0].shape[0]
         if feature_bounds is None or any(b is None for b in feature_bounds):
-            feature_bounds = [ops.absmax(ops.nhwc(f)) for f in features]
-        x_amax = torch.cat([b.reshape(1) for b in feature_bounds])
+            feature_bounds = [f.abs().amax((1, 2, 3)) for f in features]          # generic path: per-image max|map|
+        # [levels, B]: the rows of image b are scaled by ITS maps' bounds (a [1]-shaped bound is shared by the batch)
+        x_amax = torch.stack([b.reshape(-1).expand(B) for b in feature_bounds]).contiguous()
         det_boxes, det_scores = ops.relation_head(pooled, w_fold, bias_cls, w_out, b_out, rois, roi_count, num_classes,
                                                   self.bbox_reg_weights, x_amax=x_amax)
         p = self.box_predictor[0]

@@ -109,9 +109,9 @@ def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3
     q[l] [B,128,H_l,W_l], taps[l] [C,7,128] -> attn[l] [B*C,128,H_l,W_l] (NHWC memory), problem-major
     (fsod_cen.py:463-470, 482-491, 502-509).  ``taps`` are episode constants and travel to the kernel as launch
     parameters: pass HOST tensors (``PrototypeBank.taps_host``); CUDA tensors are copied to the host first, which
-    synchronises (tests / interop only - not allowed inside a graph capture).  With ``want_amax`` also returns
-    max(attn[l]) per level as device floats (the operand bounds of the tower convolutions), tracked in the kernel's
-    epilogue."""
+    synchronises (tests / interop only - not allowed inside a graph capture).  With ``want_amax`` also returns, per
+    level, max(attn[l][p]) for every problem p as device floats [B*C] (the per-image operand bounds of the tower
+    convolutions), tracked in the kernel's epilogue."""
     L = len(q)
     if L < 1 or L > 3 or len(taps) != L:
         raise _lib.FodError("correlate_levels: 1..3 levels with one taps tensor each")
@@ -125,12 +125,12 @@ def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3
     b3 = _chk(b3, torch.float32, "b3").contiguous()
     attn = [_empty_nhwc(B * C, t.shape[2], t.shape[3], t.device) for t in q]
     lv = _levels(q, [0] * L)
-    out_amax = torch.zeros((L,), dtype=torch.float32, device=q[0].device) if want_amax else None
-    am_ptrs = (_vp * L)(*[out_amax[i:i + 1].data_ptr() for i in range(L)]) if want_amax else None
+    out_amax = torch.zeros((L, B * C), dtype=torch.float32, device=q[0].device) if want_amax else None
+    am_ptrs = (_vp * L)(*[out_amax[i].data_ptr() for i in range(L)]) if want_amax else None
     _lib.check(_lib.lib().fod_correlate_levels(_ptr_array(q), _ptr_array(taps), lv, L, _ptr(w3), _ptr(b3),
                                                _ptr_array(attn), am_ptrs, B, C, _stream()), "fod_correlate_levels")
     if want_amax:
-        return attn, [out_amax[i:i + 1] for i in range(L)]
+        return attn, [out_amax[i] for i in range(L)]       # per level: [B*C] bounds, one per problem
     return attn
 
 
@@ -231,25 +231,27 @@ def untile_pooled(t: Tensor, cap: int) -> Tensor:
 def roi_align(feats: Sequence[Tensor], strides: Sequence[int], rois: Tensor, roi_count: Optional[Tensor],
               problems_per_image: int, resolution: int, out: Optional[Tensor] = None, want_levels: bool = False,
               tiled: bool = False):
-    """feats[l] [B,128,H,W]; rois [P,cap,4] -> pooled [P,cap,R*R,128] (bin-major, channel innermost), or with
-    tiled=True (R == 8) the relation-head operand layout [P,U,256,128,32] (see tile_pooled)
-    (d2 poolers.py:190-250)."""
+    """feats[l] [B,C,H,W] (C a multiple of 128); rois [P,cap,4] -> pooled [P,cap,R*R,C] (bin-major, channel innermost;
+    R = 4, 8 or 14), or with tiled=True (R == 8, C == 128) the relation-head operand layout [P,U,256,128,32] (see
+    tile_pooled) (d2 poolers.py:190-250)."""
     feats = [nhwc(f, "feat") for f in feats]
-    B = feats[0].shape[0]
+    B, ch = feats[0].shape[0], feats[0].shape[1]
     _chk(rois, torch.float32, "rois")
     rois = rois.contiguous()
     P, cap = rois.shape[0], rois.shape[1]
     if P != B * problems_per_image:
         raise _lib.FodError("roi_align: rois.shape[0] must be batch * problems_per_image")
+    if ch % 128 or any(f.shape[1] != ch for f in feats):
+        raise _lib.FodError("roi_align: maps with a multiple of 128 channels expected")
     dev = rois.device
     if out is None:
-        shape = (P, (cap + 127) // 128, 256, 128, 32) if tiled else (P, cap, resolution * resolution, 128)
+        shape = (P, (cap + 127) // 128, 256, 128, 32) if tiled else (P, cap, resolution * resolution, ch)
         out = torch.empty(shape, dtype=torch.float32, device=dev)
     lvl = torch.zeros((P, cap), dtype=torch.int32, device=dev) if want_levels else None
     lv = _levels(feats, strides)
-    _lib.check(_lib.lib().fod_roi_align(_ptr_array(feats), lv, len(feats), B, int(problems_per_image), _ptr(rois),
-                                        _ptr(roi_count), cap, int(resolution), int(bool(tiled)), _ptr(out), _ptr(lvl),
-                                        _stream()), "fod_roi_align")
+    _lib.check(_lib.lib().fod_roi_align_wide(_ptr_array(feats), lv, len(feats), B, int(problems_per_image), _ptr(rois),
+                                             _ptr(roi_count), cap, int(resolution), int(ch), int(bool(tiled)), _ptr(out),
+                                             _ptr(lvl), _stream()), "fod_roi_align")
     return (out, lvl) if want_levels else out
 
 
@@ -279,8 +281,10 @@ def relation_head(pooled: Tensor, w_fold: Tensor, bias_cls: Tensor, w_out: Tenso
     (fsod_roi_heads.py:482-520, custom_fast_rcnn.py:160-170, d2 box_regression.py:77-115).
     pooled: the tiled layout [P,U,256,128,32] written by roi_align(tiled=True) (a [P,cap,64,128] tensor is
     re-tiled with torch ops first - tests only).  w_fold: the folded matrix [128,8192] or, preferably, its packed form
-    (relation_pack).  x_amax: device floats (1..8) bounding max|pooled| = the bounds of the feature maps the ROIAlign
-    read; computed from ``pooled`` when omitted, which needs the dense [P,cap,64,128] form."""
+    (relation_pack).  x_amax: device floats bounding max|pooled| = the bounds of the feature maps the ROIAlign read:
+    [k] (k = 1..8, one scale for the call) or [k, B] (per image: the rows of image b are scaled by column b, so its
+    scores do not depend on its batch mates); computed from ``pooled`` when omitted, which needs the dense
+    [P,cap,64,128] form."""
     P, cap = rois.shape[0], rois.shape[1]
     dev = rois.device
     if w_fold.dim() == 2:
@@ -300,14 +304,16 @@ def relation_head(pooled: Tensor, w_fold: Tensor, bias_cls: Tensor, w_out: Tenso
             raise _lib.FodError(f"relation_head: {n} must be contiguous")
     if w_fold.numel() != _lib.lib().fod_conv2d_packed_floats(128, 8192, 1) or tuple(w_out.shape) != (6, 128) or bias_cls.shape[-1] != 128:
         raise _lib.FodError("relation_head: bad weight shapes")
-    if not 1 <= x_amax.numel() <= 8:
-        raise _lib.FodError("relation_head: 1..8 operand bounds")
+    per_image = x_amax.dim() == 2
+    n_amax = x_amax.shape[0] if per_image else x_amax.numel()
+    if not 1 <= n_amax <= 8 or (per_image and x_amax.shape[1] * problems_per_image != P):
+        raise _lib.FodError("relation_head: x_amax must be [k] or [k, B] with k = 1..8")
     det_boxes = torch.zeros((P, cap, 4), dtype=torch.float32, device=dev)
     det_scores = torch.zeros((P, cap), dtype=torch.float32, device=dev)
     logits = torch.zeros((P, cap, 2), dtype=torch.float32, device=dev) if want_raw else None
     deltas = torch.zeros((P, cap, 4), dtype=torch.float32, device=dev) if want_raw else None
     rw = (ctypes.c_float * 4)(*[float(x) for x in reg_weights])
-    _lib.check(_lib.lib().fod_relation_head(_ptr(pooled), _ptr(x_amax), int(x_amax.numel()), _ptr(w_fold), _ptr(bias_cls),
+    _lib.check(_lib.lib().fod_relation_head(_ptr(pooled), _ptr(x_amax), int(n_amax), int(per_image), _ptr(w_fold), _ptr(bias_cls),
                                             _ptr(w_out), _ptr(b_out), _ptr(rois), _ptr(roi_count), P, int(problems_per_image),
                                             cap, rw, _ptr(det_boxes), _ptr(det_scores), _ptr(logits), _ptr(deltas), _stream()),
                "fod_relation_head")
@@ -402,8 +408,9 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
                 a_relu: bool = False, colsumsq: Optional[Tensor] = None) -> Tensor:
     """Convolution with padding ksize//2 on the tensor cores (fp16-split operands, fp32 accuracy), bias + optional
     ReLU fused.  x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise.
-    ``x_amax``: device float tensor (1..8 values) bounding max|x| (computed with ``absmax`` when omitted, which needs a
-    dense x); ``y_amax``: zeroed device float[1] that receives max|y|."""
+    ``x_amax``: device floats bounding max|x|: [k] (k = 1..8 values, one scale for the batch; computed with ``absmax`` when
+    omitted, which needs a dense x) or [k, N] (image n is scaled by the maximum of column n: its result does not depend
+    on its batch mates); ``y_amax``: zeroed device floats that receive max|y|: [1], or [N] for one bound per image."""
     ps_x = _pixel_stride(x, "x")
     n, cin, h, w = x.shape
     pad = ksize // 2
@@ -420,8 +427,16 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
             raise _lib.FodError("conv2d_nhwc: x_amax is required for a channel-slice input")
         x_amax = absmax(x)
     _chk(x_amax, torch.float32, "x_amax")
+    x_pi = x_amax.dim() == 2
+    if x_pi and (x_amax.shape[1] != n or not x_amax.is_contiguous()):
+        raise _lib.FodError("conv2d_nhwc: per-image x_amax must be a contiguous [k, N] tensor")
+    n_amax = x_amax.shape[0] if x_pi else x_amax.numel()
+    y_pi = False
     if y_amax is not None:
         _chk(y_amax, torch.float32, "y_amax")
+        if y_amax.numel() not in (1, n):
+            raise _lib.FodError("conv2d_nhwc: y_amax must hold 1 or N floats")
+        y_pi = y_amax.numel() == n and n > 1
     if residual is not None:     # added before the activation; with residual_upsample2 read at (oy // 2, ox // 2)
         residual = nhwc(residual, "residual")
         rh, rw = ((ho + 1) // 2, (wo + 1) // 2) if residual_upsample2 else (ho, wo)
@@ -436,7 +451,8 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
             _chk(cs, torch.float32, name)
             if tuple(cs.shape) != (n, conv2d_tiles_per_image(ho, wo), cout) or not cs.is_contiguous():
                 raise _lib.FodError(f"conv2d_nhwc: bad {name} buffer")
-    _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(x_amax), int(x_amax.numel()), _ptr(packed), _ptr(bias),
+    _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(x_amax), int(n_amax), int(x_pi) | (int(y_pi) << 1),
+                                          _ptr(packed), _ptr(bias),
                                           cout, ksize, int(stride), int(relu), _ptr(out), ps_y, _ptr(y_amax), _ptr(residual),
                                           int(residual_upsample2), _ptr(a_gate), _ptr(a_shift), int(a_relu), _ptr(colsum),
                                           _ptr(colsumsq), _stream()), "fod_conv2d_nhwc")
@@ -486,8 +502,11 @@ def group_norm_nhwc(x: Tensor, groups: int, gamma: Optional[Tensor], beta: Optio
     ws = torch.empty((L.fod_group_norm_workspace_bytes(n, groups) // 8,), dtype=torch.float64, device=x.device)
     g = None if gamma is None else _chk(gamma, torch.float32, "gamma").contiguous()
     b = None if beta is None else _chk(beta, torch.float32, "beta").contiguous()
+    per_map = y_amax is not None and y_amax.numel() == n and n > 1       # [N]: one bound per map
+    if y_amax is not None and y_amax.numel() not in (1, n):
+        raise _lib.FodError("group_norm_nhwc: y_amax must hold 1 or N floats")
     _lib.check(L.fod_group_norm_nhwc(_ptr(x), n, h * w, c, groups, _ptr(g), _ptr(b), float(eps), int(relu), _ptr(y),
-                                     _ptr(y_amax), _ptr(ws), _stream()), "fod_group_norm_nhwc")
+                                     _ptr(y_amax), int(per_map), _ptr(ws), _stream()), "fod_group_norm_nhwc")
     return y
 
 

@@ -97,8 +97,9 @@ int fod_correlate(const float* q, const float* taps, const float* w3, const floa
  *                                      are processed in groups of 6 / num_levels), so no device state outlives or is
  *                                      shared between calls, and a captured graph bakes in the episode's taps.
  *   attn[l] : [B*C][H_l][W_l][128]     problem-major output
- *   attn_amax : NULL, or per level NULL / a DEVICE float (zeroed by the caller) that is raised to max(attn[l]): the
- *               operand bound of the convolution that consumes the map (fod_conv2d_nhwc x_amax), without a pass over it
+ *   attn_amax : NULL, or per level NULL / B*C DEVICE floats (zeroed by the caller): entry p is raised to max(attn[l] of
+ *               problem p) - the per-image operand bound of the convolution that consumes the maps (fod_conv2d_nhwc
+ *               x_amax with amax_per_image), without a pass over them
  */
 int fod_correlate_levels(const float* const* q, const float* const* taps, const fod_level_t* levels, int num_levels,
                          const float* w3, const float* b3, float* const* attn, float* const* attn_amax, int batch,
@@ -164,6 +165,13 @@ int fod_nms_proposals(const float* boxes, const float* scores, const int32_t* co
 int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
                   int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap, int resolution,
                   int tiled, float* pooled, int32_t* out_level, fod_stream_t stream);
+/* The same pooling over maps with `channels` = a multiple of 128 channels per pixel (feat[l] : [B][H_l][W_l][channels]) and
+ * resolution 4, 8 or 14: the ROIPooler of the R50-C4 heads (FsodRes5ROIHeads, fewx/modeling/fsod/fsod_roi_heads.py:69-74,
+ * 119-126: 1024-channel res4, 14 x 14, one level).  pooled : [P][roi_cap][R*R][channels] (tiled must be 0 unless
+ * channels == 128 and R == 8). */
+int fod_roi_align_wide(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
+                       int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap, int resolution,
+                       int channels, int tiled, float* pooled, int32_t* out_level, fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * R2+R3  relation head on pooled ROI features, softmax, box decoding.
@@ -179,6 +187,8 @@ int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_l
  *   x_amax   : n_amax (1..8) DEVICE floats bounding max|pooled|; ROIAlign averages bilinear samples, so the bounds of
  *              the feature maps it read (fod_conv2d_nhwc y_amax of the FPN output convolutions, or fod_absmax) hold.
  *              Any bound >= the true maximum gives the same result up to 2^-38 of the bound.
+ *   amax_per_image : x_amax is [n_amax][B] (B = num_problems / problems_per_image) and the rows of image b are scaled
+ *              with the maximum of column b: an image's scores do not depend on the other images of the batch
  *   w_fold_packed : fod_conv2d_pack_weights(w_fold as a [128][8192][1][1] convolution weight, ksize 1):
  *                  fod_conv2d_packed_floats(128, 8192, 1) floats; k index = bin*128 + channel (once per weight load)
  *   bias_cls : [C][128]      per-class folded bias (support term + fc1 bias)
@@ -189,7 +199,7 @@ int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_l
  * At most 2047 problems per call.
  */
 int fod_split_tf32(const float* src, float* hi_lo /* [2][n] */, size_t n, fod_stream_t stream);
-int fod_relation_head(const float* pooled, const float* x_amax, int n_amax, const float* w_fold_packed,
+int fod_relation_head(const float* pooled, const float* x_amax, int n_amax, int amax_per_image, const float* w_fold_packed,
                       const float* bias_cls, const float* w_out, const float* b_out, const float* rois,
                       const int32_t* roi_count, int num_problems, int problems_per_image, int roi_cap,
                       const float* reg_weights, float* det_boxes, float* det_scores, float* logits, float* deltas,
@@ -238,6 +248,8 @@ int fod_batched_nms(const float* boxes, const float* scores, const int64_t* idxs
  *             fixes the power-of-two operand scale.  Any bound >= the true maximum gives the same result up to 2^-38 of
  *             the bound; a bound below the true maximum may overflow fp16.  fod_absmax computes it; the kernel that
  *             produced x normally reports it (y_amax below).
+ *   amax_per_image : bit 0: x_amax is [n_amax][N] and image n is scaled by the maximum of column n, so that the result of
+ *             an image does not depend on which other images share the batch; bit 1: y_amax is [N], max|y| per image
  *   packed  : fod_conv2d_pack_weights output (fod_conv2d_packed_floats floats)
  *   bias    : [cout] or NULL
  *   y       : [N][Ho][Wo] pixels of y_pixel_stride floats, the first cout are written
@@ -256,7 +268,7 @@ size_t fod_conv2d_packed_floats(int cout, int cin, int ksize);
 /* w_oihw : [cout][cin][ksize][ksize] (PyTorch conv weight) -> scaled fp16 hi / lo planes [cout][ky][kx][cin_pad] + scale */
 int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, int ksize, float* packed, fod_stream_t stream);
 int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax, int n_amax,
-                    const float* packed, const float* bias, int cout, int ksize, int stride, int relu, float* y,
+                    int amax_per_image, const float* packed, const float* bias, int cout, int ksize, int stride, int relu, float* y,
                     long y_pixel_stride, float* y_amax, const float* residual, int residual_upsample2, const float* a_gate,
                     const float* a_shift, int a_relu, float* colsum, float* colsumsq, fod_stream_t stream);
 /* GroupNorm (+ ReLU) between two convolutions without materialising the normalised map (CenterNetHead tower,
@@ -284,13 +296,14 @@ int fod_absmax(const float* x, size_t n, float* out, fod_stream_t stream);
  * group's channels, biased variance, fp64 accumulation across threads.
  *   x, y      : [maps][hw][channels] (y may alias x)
  *   gamma/beta: [channels] or NULL
- *   y_amax    : NULL, or a DEVICE float (zeroed by the caller) raised to max|y| (the bound fod_conv2d_nhwc needs)
+ *   y_amax    : NULL, or a DEVICE float (zeroed by the caller) raised to max|y| (the bound fod_conv2d_nhwc needs); with
+ *               amax_per_map [maps] floats, one bound per map
  *   workspace : fod_group_norm_workspace_bytes(maps, groups) bytes, 16-byte aligned
  * channels / groups must be a multiple of 4.
  */
 size_t fod_group_norm_workspace_bytes(int maps, int groups);
 int fod_group_norm_nhwc(const float* x, int maps, long hw, int channels, int groups, const float* gamma,
-                        const float* beta, float eps, int relu, float* y, float* y_amax, void* workspace,
+                        const float* beta, float eps, int relu, float* y, float* y_amax, int amax_per_map, void* workspace,
                         fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
