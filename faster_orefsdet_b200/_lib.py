@@ -43,10 +43,11 @@ _PROTOTYPES = {
                          ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_f), _f, _i,
                          _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_nms_proposals": ([_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
-    "fod_roi_align": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "fod_roi_align_workspace_bytes": ([_i, _i, _i], ctypes.c_size_t),
+    "fod_roi_align": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
                       _i),
-    "fod_roi_align_wide": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
-                           _i),
+    "fod_roi_align_wide": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp,
+                            _vp], _i),
     "fod_relation_head": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.POINTER(_f), _vp, _vp, _vp, _vp,
                            _vp], _i),
     "fod_split_tf32": ([_vp, _vp, ctypes.c_size_t, _vp], _i),

@@ -249,9 +249,11 @@ def roi_align(feats: Sequence[Tensor], strides: Sequence[int], rois: Tensor, roi
         out = torch.empty(shape, dtype=torch.float32, device=dev)
     lvl = torch.zeros((P, cap), dtype=torch.int32, device=dev) if want_levels else None
     lv = _levels(feats, strides)
-    _lib.check(_lib.lib().fod_roi_align_wide(_ptr_array(feats), lv, len(feats), B, int(problems_per_image), _ptr(rois),
-                                             _ptr(roi_count), cap, int(resolution), int(ch), int(bool(tiled)), _ptr(out),
-                                             _ptr(lvl), _stream()), "fod_roi_align")
+    L = _lib.lib()
+    ws = torch.empty((L.fod_roi_align_workspace_bytes(P, cap, int(resolution)) // 16, 4), dtype=torch.int32, device=dev)
+    _lib.check(L.fod_roi_align_wide(_ptr_array(feats), lv, len(feats), B, int(problems_per_image), _ptr(rois),
+                                    _ptr(roi_count), cap, int(resolution), int(ch), int(bool(tiled)), _ptr(out),
+                                    _ptr(lvl), _ptr(ws), _stream()), "fod_roi_align")
     return (out, lvl) if want_levels else out
 
 

@@ -162,16 +162,20 @@ int fod_nms_proposals(const float* boxes, const float* scores, const int32_t* co
  *              [128 rows x 32 k] operand tile is 16 KB of contiguous memory (one linear TMA box).
  *   out_level: [P][roi_cap] int32 assigned level (may be NULL)
  */
+/*   workspace : fod_roi_align_workspace_bytes(P, roi_cap, resolution) bytes, 16-byte aligned: per ROI the box geometry
+ *              and the per-bin lists of distinct rows / columns with their interpolation weights, written by a
+ *              pre-pass over all ROIs (one thread per axis and bin) and read by the pooling CTAs */
+size_t fod_roi_align_workspace_bytes(int num_problems, int roi_cap, int resolution);
 int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
                   int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap, int resolution,
-                  int tiled, float* pooled, int32_t* out_level, fod_stream_t stream);
+                  int tiled, float* pooled, int32_t* out_level, void* workspace, fod_stream_t stream);
 /* The same pooling over maps with `channels` = a multiple of 128 channels per pixel (feat[l] : [B][H_l][W_l][channels]) and
  * resolution 4, 8 or 14: the ROIPooler of the R50-C4 heads (FsodRes5ROIHeads, fewx/modeling/fsod/fsod_roi_heads.py:69-74,
  * 119-126: 1024-channel res4, 14 x 14, one level).  pooled : [P][roi_cap][R*R][channels] (tiled must be 0 unless
  * channels == 128 and R == 8). */
 int fod_roi_align_wide(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
                        int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap, int resolution,
-                       int channels, int tiled, float* pooled, int32_t* out_level, fod_stream_t stream);
+                       int channels, int tiled, float* pooled, int32_t* out_level, void* workspace, fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * R2+R3  relation head on pooled ROI features, softmax, box decoding.
