@@ -205,7 +205,7 @@ class KernelTimer:
                 if __n == "conv2d_nhwc":      # (N, H, W, Cin, Cout, ksize, stride) of this layer
                     x = a[0]
                     tag = (x.shape[0], x.shape[2], x.shape[3], x.shape[1], int(a[3]), int(a[4]), int(k.get("stride", 1)))
-                self.records.setdefault(__n, []).append((s, e, tag))
+                self.records.setdefault({"decode_topk_taps": "decode_topk"}.get(__n, __n), []).append((s, e, tag))
                 self.launches += self.kernels_per_call.get(__n, 1)
                 return r
             setattr(ops_mod, n, timed)
@@ -260,7 +260,7 @@ def run_gpu_arm(args):
     dev_sets = [torch.stack(hs).to(dev) for hs in host_sets]
     sizes = [(IMG, IMG)] * B
     timer = KernelTimer()
-    timer.wrap(ops, ["correlate_levels", "decode_topk", "nms_proposals", "roi_align", "relation_head", "final_detect",
+    timer.wrap(ops, ["correlate_levels", "decode_topk", "decode_topk_taps", "group_norm_affine", "nms_proposals", "roi_align", "relation_head", "final_detect",
                      "conv2d_nhwc", "group_norm_nhwc", "stem_patches", "stem_patches_u8", "stem1_u8", "maxpool3x3s2_nhwc", "ese_gate"])
 
     def step_resident(i):      # raw uint8 images resident in HBM -> padded detections on the device
@@ -485,6 +485,11 @@ def run_gpu_arm(args):
                                     "achieved": conv_flops / (conv_ms * 1e-3) / 1e12, "frac": conv_flops / (conv_ms * 1e-3) / 1e12 / tensor_peak},
                      "peak_source": peak_src + ", dense bf16 sustained"}
         extractor["conv2d_nhwc"]["fp32_tflops"] = conv_flops / (conv_ms * 1e-3) / 1e12
+        # the layers by their share of the step (shape, launches per step, ms per step, fp32-equivalent TFLOP/s)
+        extractor["conv2d_nhwc"]["layers"] = [
+            {"shape": "N%d %dx%d %d->%d k%d s%d" % tag, "launches": v[1] / args.steps, "ms_per_step": v[0] / args.steps,
+             "tflops": v[2] / (v[0] / v[1] * 1e-3) / 1e12}
+            for tag, v in sorted(layers.items(), key=lambda kv: -kv[1][0])]
     # DRAM traffic per launch of the same kernels from the committed `ncu --set full` captures
     # (dram__bytes_read.sum + dram__bytes_write.sum, batch 64, 1-way; profiles/r1_ncu_v2_summary.md)
     ncu_traffic = traffic["kernels"] if B == traffic["batch"] else {}

@@ -42,6 +42,8 @@ _PROTOTYPES = {
     "fod_decode_topk": ([ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _i,
                          ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_f), _f, _i,
                          _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
+    "fod_decode_topk_taps": ([ctypes.POINTER(_vp), ctypes.POINTER(_i), ctypes.POINTER(_f), ctypes.POINTER(fod_level_t), _i, _i,
+                              ctypes.POINTER(_f), _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_nms_proposals": ([_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp], _i),
     "fod_roi_align_workspace_bytes": ([_i, _i, _i], ctypes.c_size_t),
     "fod_roi_align": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -64,7 +66,7 @@ _PROTOTYPES = {
     "fod_conv2d_pack_weights": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "fod_conv2d_nhwc": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_long, _vp, _vp,
                          _i, _vp, _vp, _i, _vp, _vp, _vp], _i),
-    "fod_group_norm_affine": ([_vp, _vp, _i, _i, _i, _i, ctypes.c_long, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp], _i),
+    "fod_group_norm_affine": ([_vp, _vp, _i, _i, _i, _i, ctypes.c_long, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _vp], _i),
     "fod_conv2d_tiles_per_image": ([_i, _i], _i),
     "fod_ese_gate": ([_vp, _i, _i, _i, ctypes.c_long, _vp, _vp, _vp, _vp], _i),
 }

@@ -22,12 +22,34 @@ struct DecodeParams {
   const float* reg[FOD_MAX_LEVELS];
   int H[FOD_MAX_LEVELS], W[FOD_MAX_LEVELS], stride[FOD_MAX_LEVELS];
   int hm_ps[FOD_MAX_LEVELS], reg_ps[FOD_MAX_LEVELS];   // pixel strides in floats (1 / 4 = dense)
+  // tap mode (fod_decode_topk_taps): hm[l] points at G[P][H][W][tap_ps] with G[p][tap*8 + o] = the product of the
+  // 3x3 output convolution's tap `tap` (ky*3 + kx) for output channel o (0 = heat-map, 1..4 = l, t, r, b) with the
+  // tower output at pixel p; the convolution at pixel (y, x) is bias + sum over taps of G[(y+ky-1, x+kx-1)][tap*8 + o]
+  int taps;            // 0: hm / reg maps, 9: tap products
+  float bias[5];       // agn_hm.bias, bbox_pred.bias (tap mode)
   int num_levels;
   int hm_is_logit, reg_channels_last, reg_activate;
   float reg_scale[FOD_MAX_LEVELS];   // reg_activate: reg = relu(reg_scale[l] * raw) (Scale + ReLU of CenterNetHead)
   float thresh;
   int pre_topk, cand_cap;
 };
+
+// value of output channel o of the 3x3 output convolution at pixel (y, x) from the per-tap products (zero padding)
+__device__ __forceinline__ float tap_sum(const float* __restrict__ G, int ps, int H, int W, int y, int x, int o, float bias) {
+  float acc = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = y + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = x + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      acc += __ldg(G + ((size_t)yy * W + xx) * ps + (ky * 3 + kx) * 8 + o);
+    }
+  }
+  return acc + bias;
+}
 
 __global__ void __launch_bounds__(kDecThreads, 1)
 decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restrict__ scores, int64_t* __restrict__ loc,
@@ -64,7 +86,8 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
     const float* hml = prm.hm[ll] + (size_t)p * nn * hps;
     int local = 0;
     for (int i = tid; i < nn; i += kDecThreads) {
-      const float v = __ldg(hml + (size_t)i * hps);
+      const float v = prm.taps ? tap_sum(hml, hps, prm.H[ll], prm.W[ll], i / prm.W[ll], i % prm.W[ll], 0, prm.bias[0])
+                               : __ldg(hml + (size_t)i * hps);
       const float pr = prm.hm_is_logit ? 1.0f / (1.0f + expf(-v)) : v;
       local += (pr > prm.thresh);
     }
@@ -77,7 +100,7 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
     // ---- pass 0: keys + candidate count
     int local = 0;
     for (int i = tid; i < n; i += kDecThreads) {
-      float v = __ldg(hm + (size_t)i * hps);
+      float v = prm.taps ? tap_sum(hm, hps, H, W, i / W, i % W, 0, prm.bias[0]) : __ldg(hm + (size_t)i * hps);
       float pr = prm.hm_is_logit ? 1.0f / (1.0f + expf(-v)) : v;
       uint32_t k = (pr > prm.thresh) ? __float_as_uint(pr) : 0u;
       keys[i] = k;
@@ -199,7 +222,12 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
           float gx = __fadd_rn((float)(xx * stride), half);
           float gy = __fadd_rn((float)(y * stride), half);
           float r0, r1, r2, r3;
-          if (prm.reg_channels_last) {
+          if (prm.taps) {
+            r0 = tap_sum(hm, hps, H, W, y, xx, 1, prm.bias[1]);
+            r1 = tap_sum(hm, hps, H, W, y, xx, 2, prm.bias[2]);
+            r2 = tap_sum(hm, hps, H, W, y, xx, 3, prm.bias[3]);
+            r3 = tap_sum(hm, hps, H, W, y, xx, 4, prm.bias[4]);
+          } else if (prm.reg_channels_last) {
             const float* rp = prm.reg[l] + ((size_t)p * n + i) * rps;
             if ((reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
               float4 r = ldg4(rp);
@@ -243,13 +271,12 @@ decode_topk_kernel(DecodeParams prm, float* __restrict__ boxes, float* __restric
 
 using namespace fod;
 
-extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_level_t* levels,
-                               int num_levels, int num_problems, int hm_is_logit, int reg_channels_last,
-                               const int* hm_pixel_stride, const int* reg_pixel_stride, const float* reg_scale,
-                               float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores,
-                               int64_t* loc, int32_t* level_count, int32_t* cand_count, uint32_t* status,
-                               fod_stream_t stream) {
-  FOD_REQUIRE(hm && reg && levels && boxes && scores && loc && level_count && cand_count && status,
+static int decode_launch(const float* const* hm, const float* const* reg, const fod_level_t* levels, int num_levels,
+                         int num_problems, int hm_is_logit, int reg_channels_last, const int* hm_pixel_stride,
+                         const int* reg_pixel_stride, const float* reg_scale, int taps, const float* bias5,
+                         float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores, int64_t* loc,
+                         int32_t* level_count, int32_t* cand_count, uint32_t* status, fod_stream_t stream) {
+  FOD_REQUIRE(hm && levels && boxes && scores && loc && level_count && cand_count && status && (taps || reg),
               "fod_decode_topk: null pointer");
   FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_decode_topk: num_levels %d out of range", num_levels);
   FOD_REQUIRE(num_problems >= 0 && pre_topk > 0 && cand_cap >= num_levels * pre_topk,
@@ -259,16 +286,16 @@ extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, 
   DecodeParams prm;
   int maxpix = 0;
   for (int l = 0; l < num_levels; ++l) {
-    FOD_REQUIRE(hm[l] && reg[l], "fod_decode_topk: null level pointer");
+    FOD_REQUIRE(hm[l] && (taps || reg[l]), "fod_decode_topk: null level pointer");
     FOD_REQUIRE(levels[l].height > 0 && levels[l].width > 0 && levels[l].stride > 0, "fod_decode_topk: bad level %d", l);
     prm.hm[l] = hm[l];
-    prm.reg[l] = reg[l];
+    prm.reg[l] = taps ? nullptr : reg[l];
     prm.H[l] = levels[l].height;
     prm.W[l] = levels[l].width;
     prm.stride[l] = levels[l].stride;
-    prm.hm_ps[l] = hm_pixel_stride ? hm_pixel_stride[l] : 1;
+    prm.hm_ps[l] = hm_pixel_stride ? hm_pixel_stride[l] : (taps ? 72 : 1);
     prm.reg_ps[l] = reg_pixel_stride ? reg_pixel_stride[l] : 4;
-    FOD_REQUIRE(prm.hm_ps[l] >= 1 && prm.reg_ps[l] >= 4, "fod_decode_topk: bad pixel stride at level %d", l);
+    FOD_REQUIRE(prm.hm_ps[l] >= (taps ? 72 : 1) && prm.reg_ps[l] >= 4, "fod_decode_topk: bad pixel stride at level %d", l);
     FOD_REQUIRE(!reg_pixel_stride || reg_channels_last, "fod_decode_topk: reg_pixel_stride needs the channels-last layout");
     int px = levels[l].height * levels[l].width;
     if (px > maxpix) maxpix = px;
@@ -282,6 +309,8 @@ extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, 
   prm.reg_channels_last = reg_channels_last;
   prm.reg_activate = reg_scale ? 1 : 0;
   for (int l = 0; l < FOD_MAX_LEVELS; ++l) prm.reg_scale[l] = (reg_scale && l < num_levels) ? reg_scale[l] : 1.f;
+  prm.taps = taps;
+  for (int i = 0; i < 5; ++i) prm.bias[i] = bias5 ? bias5[i] : 0.f;
   prm.thresh = score_thresh;
   prm.pre_topk = pre_topk;
   prm.cand_cap = cand_cap;
@@ -292,4 +321,25 @@ extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, 
                                                                              cand_count, status);
   FOD_CUDA_LAUNCH_CHECK("fod_decode_topk");
   return FOD_OK;
+}
+
+extern "C" int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_level_t* levels,
+                               int num_levels, int num_problems, int hm_is_logit, int reg_channels_last,
+                               const int* hm_pixel_stride, const int* reg_pixel_stride, const float* reg_scale,
+                               float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores,
+                               int64_t* loc, int32_t* level_count, int32_t* cand_count, uint32_t* status,
+                               fod_stream_t stream) {
+  return decode_launch(hm, reg, levels, num_levels, num_problems, hm_is_logit, reg_channels_last, hm_pixel_stride,
+                       reg_pixel_stride, reg_scale, 0, nullptr, score_thresh, pre_topk, cand_cap, boxes, scores, loc,
+                       level_count, cand_count, status, stream);
+}
+
+extern "C" int fod_decode_topk_taps(const float* const* taps, const int* tap_pixel_stride, const float* bias5,
+                                    const fod_level_t* levels, int num_levels, int num_problems, const float* reg_scale,
+                                    float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores,
+                                    int64_t* loc, int32_t* level_count, int32_t* cand_count, uint32_t* status,
+                                    fod_stream_t stream) {
+  FOD_REQUIRE(bias5, "fod_decode_topk_taps: null bias");
+  return decode_launch(taps, nullptr, levels, num_levels, num_problems, 1, 1, tap_pixel_stride, nullptr, reg_scale, 9, bias5,
+                       score_thresh, pre_topk, cand_cap, boxes, scores, loc, level_count, cand_count, status, stream);
 }

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ c
                                                      int tiles, int channels, int cpg, double inv_n,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                      const float* __restrict__ x_amax, float* __restrict__ scale,
-                                                     float* __restrict__ shift, float* __restrict__ y_amax) {
+                                                     float* __restrict__ shift, float* __restrict__ y_amax, int amax_per_map) {
   extern __shared__ double sm[];   // [channels] sums, [channels] sums of squares
   double* s1 = sm;
   double* s2 = sm + channels;
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ c
   }
   __syncthreads();
   float vmax = 0.f;
-  const float xa = x_amax ? __ldg(x_amax) : 0.f;
+  const float xa = x_amax ? __ldg(x_amax + (amax_per_map ? blockIdx.x : 0)) : 0.f;
   for (int c = threadIdx.x; c < channels; c += blockDim.x) {
     const int g0 = (c / cpg) * cpg;
     double a = 0.0, b = 0.0;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256) affine_kernel(const float* __restrict__ c
   }
   if (y_amax) {
     const uint32_t w = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
-    if ((threadIdx.x & 31) == 0 && w) atomicMax(reinterpret_cast<unsigned int*>(y_amax), w);
+    if ((threadIdx.x & 31) == 0 && w) atomicMax(reinterpret_cast<unsigned int*>(y_amax + (amax_per_map ? blockIdx.x : 0)), w);
   }
 }
 
@@ -169,14 +169,15 @@ extern "C" int fod_group_norm_nhwc(const float* x, int maps, long hw, int channe
 
 extern "C" int fod_group_norm_affine(const float* colsum, const float* colsumsq, int maps, int tiles_per_map, int channels,
                                      int groups, long hw, const float* gamma, const float* beta, float eps,
-                                     const float* x_amax, float* scale, float* shift, float* y_amax, fod_stream_t stream) {
+                                     const float* x_amax, float* scale, float* shift, float* y_amax, int amax_per_map,
+                                     fod_stream_t stream) {
   FOD_REQUIRE(colsum && colsumsq && scale && shift, "fod_group_norm_affine: null pointer");
   FOD_REQUIRE(maps >= 0 && tiles_per_map > 0 && channels > 0 && groups > 0 && channels % groups == 0 && hw > 0 &&
                   channels <= 2048, "fod_group_norm_affine: bad sizes");
   if (maps == 0) return FOD_OK;
   const int cpg = channels / groups;
   gn::affine_kernel<<<maps, 256, 2 * channels * sizeof(double), as_stream(stream)>>>(
-      colsum, colsumsq, tiles_per_map, channels, cpg, 1.0 / ((double)hw * cpg), gamma, beta, eps, x_amax, scale, shift, y_amax);
+      colsum, colsumsq, tiles_per_map, channels, cpg, 1.0 / ((double)hw * cpg), gamma, beta, eps, x_amax, scale, shift, y_amax, amax_per_map);
   FOD_CUDA_LAUNCH_CHECK("fod_group_norm_affine");
   return FOD_OK;
 }

@@ -80,6 +80,57 @@ class CenterNetHead(nn.Module):
             bbox_reg.append(reg if raw_reg else F.relu(self.scales[l](reg)))
         return clss, bbox_reg, agn_hms
 
+    # ---- hot path: tower convolution with GroupNorm statistics in its epilogue -> GroupNorm + ReLU applied to the operand
+    # of ONE 1x1 contraction that produces the nine tap products of agn_hm | bbox_pred (72 columns); the nine shifted sums,
+    # the biases and Scale + ReLU happen inside fod_decode_topk_taps.  The normalised map, hm and reg never exist.
+    def tap_products(self, x: Sequence[torch.Tensor], bounds: Optional[Sequence[torch.Tensor]] = None):
+        mods = list(self.bbox_tower)
+        if not (len(mods) == 3 and isinstance(mods[0], nn.Conv2d) and isinstance(mods[1], nn.GroupNorm)
+                and isinstance(mods[2], nn.ReLU) and mods[1].num_channels % 32 == 0):
+            return None
+        conv, gn = mods[0], mods[1]
+        pk9 = self._packed_taps()
+        out = []
+        for l, t in enumerate(x):
+            if not tcconv.supported(conv, t):
+                raise ops._lib.FodError("CenterNetHead: fp32 CUDA maps in NHWC memory expected (the head has no cuDNN / CPU path)")
+            n, _, h, w = t.shape
+            tiles = ops.conv2d_tiles_per_image(h, w)
+            cs = torch.empty((n, tiles, conv.out_channels), dtype=torch.float32, device=t.device)
+            cq = torch.empty_like(cs)
+            a_t = ops.new_amax(t.device, n)                        # per problem
+            b = bounds[l] if bounds is not None else None
+            if b is not None and b.numel() == n and n > 1:
+                b = b.reshape(1, -1)
+            t = tcconv.conv(t, conv, x_amax=b, y_amax=a_t, colsum=cs, colsumsq=cq)
+            scale, shift, a_g = ops.group_norm_affine(cs, cq, h * w, gn.num_groups, gn.weight, gn.bias, gn.eps, x_amax=a_t)
+            if a_g.numel() == n and n > 1:
+                a_g = a_g.reshape(1, -1)
+            out.append(ops.conv2d_nhwc(t, pk9, None, 72, 1, x_amax=a_g, a_gate=scale, a_shift=shift, a_relu=True))
+        return out
+
+    def _packed_taps(self) -> torch.Tensor:
+        """[72, 128, 1, 1]: row tap*8 + o = filter tap (ky, kx) of output o (0 = agn_hm, 1..4 = bbox_pred, 5..7 zero)."""
+        ws = (self.agn_hm.weight, self.bbox_pred.weight)
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        hit = self.__dict__.get("_taps_cache")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                w = torch.cat((ws[0], ws[1], ws[0].new_zeros((3,) + tuple(ws[0].shape[1:]))), 0)       # [8, C, 3, 3]
+                w9 = w.permute(2, 3, 0, 1).reshape(72, w.shape[1], 1, 1).contiguous()                  # (ky, kx, o) major
+                hit = (key, ops.conv2d_pack(w9.float()))
+            self.__dict__["_taps_cache"] = hit
+        return hit[1]
+
+    def bias5_host(self) -> List[float]:
+        ps = (self.agn_hm.bias, self.bbox_pred.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        hit = self.__dict__.get("_bias5_host")
+        if hit is None or hit[0] != key:
+            hit = (key, [float(v) for v in torch.cat([p.detach().reshape(-1) for p in ps]).tolist()])
+            self.__dict__["_bias5_host"] = hit
+        return hit[1]
+
     def scales_host(self) -> List[float]:
         """The per-level Scale factors as host floats (read back once per weight version)."""
         key = tuple((m.scale.data_ptr(), m.scale._version) for m in self.scales)
@@ -170,6 +221,8 @@ class CenterNet(nn.Module):
         # extra proposal rows reserved for ties at the post-NMS threshold (fsod_rpn.py:1204 keeps them all)
         self.tie_slack = 64
 
+    FOLD_OUTPUT_CONV = True      # tower -> tap products -> decode (see CenterNetHead.tap_products); False: hm / reg maps
+
     @property
     def roi_cap(self) -> int:
         return (self.post_nms_topk_test + self.tie_slack + 63) // 64 * 64
@@ -189,10 +242,17 @@ class CenterNet(nn.Module):
     def propose_raw(self, features: Sequence[torch.Tensor], status: torch.Tensor, roi_cap: Optional[int] = None,
                     bounds: Optional[Sequence[torch.Tensor]] = None) -> RawProposals:
         """features[l]: [P,128,H_l,W_l] correlated maps, one row per (image, class) problem."""
-        _, reg, hm = self.centernet_head(features, bounds, raw_reg=True)
-        boxes, scores, loc, level_count, cand_count = ops.decode_topk(
-            hm, reg, self.strides, self.score_thresh, self.pre_nms_topk_test, status, hm_is_logit=True,
-            reg_scale=self.centernet_head.scales_host())
+        head = self.centernet_head
+        taps = head.tap_products(features, bounds) if self.FOLD_OUTPUT_CONV else None
+        if taps is not None:
+            boxes, scores, loc, level_count, cand_count = ops.decode_topk_taps(
+                taps, head.bias5_host(), self.strides, self.score_thresh, self.pre_nms_topk_test, status,
+                reg_scale=head.scales_host())
+        else:
+            _, reg, hm = head(features, bounds, raw_reg=True)
+            boxes, scores, loc, level_count, cand_count = ops.decode_topk(
+                hm, reg, self.strides, self.score_thresh, self.pre_nms_topk_test, status, hm_is_logit=True,
+                reg_scale=head.scales_host())
         keep, pb, ps, pc = ops.nms_proposals(boxes, scores, cand_count, self.nms_thresh_test, self.post_nms_topk_test,
                                              roi_cap or self.roi_cap, status)
         return RawProposals(pb, ps, pc, keep, boxes, scores, loc, level_count, cand_count)

@@ -192,6 +192,36 @@ def decode_topk(hm: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[i
     return boxes, scores, loc, level_count, cand_count
 
 
+def decode_topk_taps(taps: Sequence[Tensor], bias5: Sequence[float], strides: Sequence[int], score_thresh: float,
+                     pre_topk: int, status: Tensor, reg_scale: Optional[Sequence[float]] = None,
+                     cand_cap: Optional[int] = None):
+    """decode_topk with the 3x3 output convolutions folded in: taps[l] [P,72(+),H,W] NHWC = the per-tap products of the
+    stacked agn_hm | bbox_pred filter with the tower output (one 1x1 contraction, column tap*8 + o); the kernel forms
+    bias + the nine shifted sums as it reads (centernet_head.py:152-160, fsod_rpn.py:1071-1181).  Same outputs as
+    decode_topk."""
+    L = len(taps)
+    P, dev = taps[0].shape[0], taps[0].device
+    ps = []
+    for t in taps:
+        s_ = _pixel_stride(t, "taps")
+        if t.shape[1] < 72:
+            raise _lib.FodError("decode_topk_taps: 72 tap columns per pixel expected")
+        ps.append(int(s_))
+    cap = cand_cap if cand_cap is not None else L * pre_topk
+    boxes = torch.empty((P, cap, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((P, cap), dtype=torch.float32, device=dev)
+    loc = torch.empty((P, cap), dtype=torch.int64, device=dev)
+    level_count = torch.empty((P, L), dtype=torch.int32, device=dev)
+    cand_count = torch.empty((P,), dtype=torch.int32, device=dev)
+    lv = _levels(taps, strides)
+    rs = None if reg_scale is None else (ctypes.c_float * L)(*[float(v) for v in reg_scale])
+    b5 = (ctypes.c_float * 5)(*[float(v) for v in bias5])
+    _lib.check(_lib.lib().fod_decode_topk_taps(_ptr_array(taps), (ctypes.c_int * L)(*ps), b5, lv, L, P, rs, float(score_thresh),
+                                               int(pre_topk), cap, _ptr(boxes), _ptr(scores), _ptr(loc), _ptr(level_count),
+                                               _ptr(cand_count), _ptr(status), _stream()), "fod_decode_topk_taps")
+    return boxes, scores, loc, level_count, cand_count
+
+
 # --------------------------------------------------------------------------- N0
 def nms_proposals(boxes: Tensor, scores: Tensor, count: Optional[Tensor], iou_thresh: float, post_topk: int,
                   roi_cap: int, status: Tensor):
@@ -485,11 +515,13 @@ def group_norm_affine(colsum: Tensor, colsumsq: Tensor, hw: int, groups: int, ga
     dev = colsum.device
     scale = torch.empty((n, c), dtype=torch.float32, device=dev)
     shift = torch.empty((n, c), dtype=torch.float32, device=dev)
-    bound = torch.zeros((1,), dtype=torch.float32, device=dev)
+    per_map = x_amax is not None and x_amax.numel() == n and n > 1      # one bound per map in, one per map out
+    bound = torch.zeros((n if per_map else 1,), dtype=torch.float32, device=dev)
     g = None if gamma is None else _chk(gamma, torch.float32, "gamma").contiguous()
     b = None if beta is None else _chk(beta, torch.float32, "beta").contiguous()
     _lib.check(_lib.lib().fod_group_norm_affine(_ptr(colsum), _ptr(colsumsq), n, tiles, c, groups, int(hw), _ptr(g), _ptr(b),
-                                                float(eps), _ptr(x_amax), _ptr(scale), _ptr(shift), _ptr(bound), _stream()),
+                                                float(eps), _ptr(x_amax), _ptr(scale), _ptr(shift), _ptr(bound), int(per_map),
+                                                _stream()),
                "fod_group_norm_affine")
     return scale, shift, bound
 

@@ -130,6 +130,20 @@ int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_l
                     const int* reg_pixel_stride, const float* reg_scale, float score_thresh, int pre_topk, int cand_cap, float* boxes, float* scores, int64_t* loc, int32_t* level_count,
                     int32_t* cand_count, uint32_t* status, fod_stream_t stream);
 
+/* The same selection with the 3x3 output convolutions (agn_hm 128 -> 1, bbox_pred 128 -> 4,
+ * CenterNet2/centernet/modeling/dense_heads/centernet_head.py:152-160) folded in.  A 3x3 convolution with 5 outputs keeps the
+ * tensor cores busy for 36 K-chunks per tile whatever its width; computed instead as ONE 1x1 contraction
+ *   G[p][tap*8 + o] = sum_c W[o][c][ky][kx] * t[p][c]      (tap = ky*3 + kx, o = 0: heat-map, 1..4: l t r b; 72 columns)
+ * (fod_conv2d_nhwc, ksize 1, 4 K-chunks per tile) it leaves nine shifted additions per output, which this kernel does
+ * while it reads:  out(y, x)[o] = bias5[o] + sum_tap G[(y + ky - 1, x + kx - 1)][tap*8 + o]  (zero outside the map).
+ *   taps[l] : [P][H_l][W_l][tap_pixel_stride[l] >= 72] fp32 (tap_pixel_stride NULL = 72)
+ *   bias5   : HOST, agn_hm.bias then bbox_pred.bias;  reg_scale as in fod_decode_topk (HOST, may be NULL)
+ * The heat-map is taken as a logit. */
+int fod_decode_topk_taps(const float* const* taps, const int* tap_pixel_stride, const float* bias5, const fod_level_t* levels,
+                         int num_levels, int num_problems, const float* reg_scale, float score_thresh, int pre_topk,
+                         int cand_cap, float* boxes, float* scores, int64_t* loc, int32_t* level_count, int32_t* cand_count,
+                         uint32_t* status, fod_stream_t stream);
+
 /* ---------------------------------------------------------------------------
  * N0  class-agnostic NMS + post-NMS top-k.  Replaces nms_and_topK -> ml_nms ->
  * batched_nms -> torchvision nms and the CPU kthvalue, fsod_rpn.py:1184-1210,
@@ -278,10 +292,11 @@ int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_s
 /* GroupNorm (+ ReLU) between two convolutions without materialising the normalised map (CenterNetHead tower,
  * centernet_head.py:61-72, 145-150): the first convolution writes colsum / colsumsq, fod_group_norm_affine turns them
  * into scale / shift [maps][channels] (and the bound max|normalised map| from the bound x_amax of the raw map), the
- * second convolution applies act(x * a_gate + a_shift) to its input operand (a_gate = scale, a_shift = shift, a_relu). */
+ * second convolution applies act(x * a_gate + a_shift) to its input operand (a_gate = scale, a_shift = shift, a_relu).
+ * amax_per_map: x_amax and y_amax hold one bound per map ([maps]) instead of one for the batch. */
 int fod_group_norm_affine(const float* colsum, const float* colsumsq, int maps, int tiles_per_map, int channels, int groups,
                           long hw, const float* gamma, const float* beta, float eps, const float* x_amax, float* scale,
-                          float* shift, float* y_amax, fod_stream_t stream);
+                          float* shift, float* y_amax, int amax_per_map, fod_stream_t stream);
 /* eSE attention of the OSA stages (d2!/modeling/backbone/vovnet.py eSEModule: x * hsigmoid(fc(avg_pool(x)))) without a
  * pass over x: the convolution that produces x writes per-tile channel sums (colsum), fod_ese_gate turns them into
  * gate [N][C] = relu6(fc(mean) + 3) / 6, and the consumers multiply it in (fod_conv2d_nhwc a_gate, fod_maxpool3x3s2_nhwc gate).

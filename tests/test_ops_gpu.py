@@ -170,6 +170,45 @@ def test_decode_topk_from_logits_matches_oracle_set():
             off += n
 
 
+def test_decode_topk_taps_equals_conv_then_decode():
+    """The 3x3 output convolutions folded into the decode (nine shifted sums of per-tap products from one 1x1 contraction)
+    against F.conv2d + decode_level of the oracle: same candidate set, boxes and scores."""
+    sd = head_state_dict()
+    P = 3
+    wh, bh = sd["proposal_generator.centernet_head.agn_hm.weight"], sd["proposal_generator.centernet_head.agn_hm.bias"]
+    wr, br = sd["proposal_generator.centernet_head.bbox_pred.weight"], sd["proposal_generator.centernet_head.bbox_pred.bias"]
+    w8 = torch.cat((wh, wr, torch.zeros((3, 128, 3, 3))), 0)
+    w9 = w8.permute(2, 3, 0, 1).reshape(72, 128, 1, 1).contiguous()
+    pk = ops.conv2d_pack(w9.to(DEV))
+    sizes, strides, scales = [(40, 48), (20, 24), (7, 9)], (8, 16, 32), (1.0, 0.9, 1.1)
+    taps, ts = [], []
+    for l, (h, w) in enumerate(sizes):
+        t_ = synth.tensor((P, 128, h, w), 400 + l, 0.0, 1.2)            # tower output (post ReLU)
+        ts.append(t_)
+        taps.append(ops.conv2d_nhwc(t_.to(DEV).contiguous(memory_format=torch.channels_last), pk, None, 72, 1))
+    status = ops.new_status(DEV)
+    bias5 = torch.cat((bh, br)).tolist()
+    boxes, scores, loc, lc, cc = ops.decode_topk_taps(taps, bias5, strides, CFG.inference_th, 1000, status, reg_scale=scales)
+    ops.check_status(status)
+    for p in range(P):
+        off = 0
+        for l in range(3):
+            hm = torch.nn.functional.conv2d(ts[l][p:p + 1], wh, bh, padding=1)[0, 0]
+            reg = torch.relu(torch.nn.functional.conv2d(ts[l][p:p + 1], wr, br, padding=1)[0] * scales[l])
+            ref_loc, ref_boxes, ref_scores = O.decode_level(hm, reg, strides[l], CFG)
+            n = int(lc[p, l])
+            got, want = set(loc[p, off:off + n].cpu().tolist()), set(ref_loc.tolist())
+            assert abs(n - ref_loc.numel()) <= 2 and len(got ^ want) <= 4        # summation order at the k-th value
+            gi = {v: i for i, v in enumerate(loc[p, off:off + n].cpu().tolist())}
+            ri = {v: i for i, v in enumerate(ref_loc.tolist())}
+            common = sorted(got & want)
+            gsel, rsel = torch.tensor([gi[v] for v in common]), torch.tensor([ri[v] for v in common])
+            assert_close(scores[p, off:off + n].cpu()[gsel], ref_scores[rsel], what="scores")
+            assert_close(boxes[p, off:off + n].cpu()[gsel], ref_boxes[rsel], atol=2e-3, what="boxes")
+            off += n
+        assert int(cc[p]) == off
+
+
 # ----------------------------------------------------------------------------------------- correlation
 def test_support_taps_match_oracle():
     for size in (32, 16, 8, 7, 5):
