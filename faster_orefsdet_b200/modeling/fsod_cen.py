@@ -412,8 +412,13 @@ class CenterNet2Detector(nn.Module):
         dev = features[self.in_features[0]].device
         image_hw = torch.tensor([list(s) for s in image_sizes], dtype=torch.int32).to(dev, non_blocking=True)
         out_hw = torch.tensor([list(s) for s in out_sizes], dtype=torch.int32).to(dev, non_blocking=True)
-        res = self._head_launch(features, image_hw, out_hw, None)
+        with ops.zero_arena(dev, self._arena_bytes(len(image_sizes))):
+            res = self._head_launch(features, image_hw, out_hw, None)
         return self._head_finish(res, features, image_hw, out_hw, want_trace)
+
+    def _arena_bytes(self, n_images: int) -> int:
+        P = n_images * max(self._bank.num_classes if self._bank is not None else 1, 1)
+        return P * self.proposal_generator.roi_cap * 64 + n_images * 100 * 64 + (1 << 20)
 
     def _head_launch(self, features, image_hw, out_hw, cap, feature_bounds=None):
         """Kernel launches of the head only (stream-ordered, no host sync: CUDA-graph capturable).  ``feature_bounds``:
@@ -493,8 +498,9 @@ class CenterNet2Detector(nn.Module):
         first.zero_()
 
         def run():
-            feats = self.backbone.top_down(*vov.tc_body(buf, amax, fuse_gates=True))
-            return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None, self.backbone.last_output_bounds)
+            with ops.zero_arena(dev, self._arena_bytes(n)):      # every counter / bound / padded output: one fill
+                feats = self.backbone.top_down(*vov.tc_body(buf, amax, fuse_gates=True))
+                return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None, self.backbone.last_output_bounds)
 
         main = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)

@@ -68,8 +68,46 @@ def _ptr_array(ts: Sequence[Tensor]):
     return (_vp * len(ts))(*[t.data_ptr() for t in ts])
 
 
+# ---- zero-initialised scratch: counters, bounds and padded outputs of one pass come out of ONE pre-zeroed buffer (one
+# fill kernel instead of ~30 small ones per step; profiles/r2_ncu_summary.md)
+_ARENA = None
+
+
+class zero_arena:
+    """``with ops.zero_arena(device, nbytes):`` - inside, every zero-filled buffer the wrappers need is a 256-byte-aligned
+    view of one zeroed allocation (falling back to ``torch.zeros`` when it is used up)."""
+
+    def __init__(self, device, nbytes: int):
+        self.device, self.nbytes = torch.device(device), int(nbytes)
+
+    def __enter__(self):
+        global _ARENA
+        self.prev = _ARENA
+        _ARENA = [torch.zeros((self.nbytes,), dtype=torch.uint8, device=self.device), 0]
+        return self
+
+    def __exit__(self, *exc):
+        global _ARENA
+        _ARENA = self.prev
+        return False
+
+
+def _zeros(shape, dtype, device) -> Tensor:
+    a = _ARENA
+    if a is not None and a[0].device == torch.device(device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        if a[1] + nbytes <= a[0].numel():
+            off = a[1]
+            a[1] = (off + nbytes + 255) // 256 * 256
+            return a[0][off:off + nbytes].view(dtype).view(tuple(shape))
+    return torch.zeros(tuple(shape), dtype=dtype, device=device)
+
+
 def new_status(device) -> Tensor:
-    return torch.zeros(1, dtype=torch.int32, device=device)
+    return _zeros((1,), torch.int32, device)
 
 
 def check_status(status: Tensor) -> None:
@@ -125,7 +163,7 @@ def correlate_levels(q: Sequence[Tensor], taps: Sequence[Tensor], w3: Tensor, b3
     b3 = _chk(b3, torch.float32, "b3").contiguous()
     attn = [_empty_nhwc(B * C, t.shape[2], t.shape[3], t.device) for t in q]
     lv = _levels(q, [0] * L)
-    out_amax = torch.zeros((L, B * C), dtype=torch.float32, device=q[0].device) if want_amax else None
+    out_amax = _zeros((L, B * C), torch.float32, q[0].device) if want_amax else None
     am_ptrs = (_vp * L)(*[out_amax[i].data_ptr() for i in range(L)]) if want_amax else None
     _lib.check(_lib.lib().fod_correlate_levels(_ptr_array(q), _ptr_array(taps), lv, L, _ptr(w3), _ptr(b3),
                                                _ptr_array(attn), am_ptrs, B, C, _stream()), "fod_correlate_levels")
@@ -231,9 +269,9 @@ def nms_proposals(boxes: Tensor, scores: Tensor, count: Optional[Tensor], iou_th
     P, cap = scores.shape
     dev = boxes.device
     boxes, scores = boxes.contiguous(), scores.contiguous()
-    keep = torch.zeros((P, roi_cap), dtype=torch.int64, device=dev)
-    ob = torch.zeros((P, roi_cap, 4), dtype=torch.float32, device=dev)
-    os_ = torch.zeros((P, roi_cap), dtype=torch.float32, device=dev)
+    keep = _zeros((P, roi_cap), torch.int64, dev)
+    ob = _zeros((P, roi_cap, 4), torch.float32, dev)
+    os_ = _zeros((P, roi_cap), torch.float32, dev)
     oc = torch.empty((P,), dtype=torch.int32, device=dev)
     _lib.check(_lib.lib().fod_nms_proposals(_ptr(boxes), _ptr(scores), _ptr(count), P, cap, float(iou_thresh),
                                             int(post_topk), int(roi_cap), _ptr(keep), _ptr(ob), _ptr(os_), _ptr(oc),
@@ -340,8 +378,8 @@ def relation_head(pooled: Tensor, w_fold: Tensor, bias_cls: Tensor, w_out: Tenso
     n_amax = x_amax.shape[0] if per_image else x_amax.numel()
     if not 1 <= n_amax <= 8 or (per_image and x_amax.shape[1] * problems_per_image != P):
         raise _lib.FodError("relation_head: x_amax must be [k] or [k, B] with k = 1..8")
-    det_boxes = torch.zeros((P, cap, 4), dtype=torch.float32, device=dev)
-    det_scores = torch.zeros((P, cap), dtype=torch.float32, device=dev)
+    det_boxes = _zeros((P, cap, 4), torch.float32, dev)
+    det_scores = _zeros((P, cap), torch.float32, dev)
     logits = torch.zeros((P, cap, 2), dtype=torch.float32, device=dev) if want_raw else None
     deltas = torch.zeros((P, cap, 4), dtype=torch.float32, device=dev) if want_raw else None
     rw = (ctypes.c_float * 4)(*[float(x) for x in reg_weights])
@@ -363,10 +401,10 @@ def final_detect(det_boxes: Tensor, det_scores: Tensor, roi_count: Optional[Tens
     dev = det_boxes.device
     _chk(det_boxes, torch.float32, "det_boxes"), _chk(det_scores, torch.float32, "det_scores")
     det_boxes, det_scores = det_boxes.contiguous(), det_scores.contiguous()
-    ob = torch.zeros((B, max_det, 4), dtype=torch.float32, device=dev)
-    os_ = torch.zeros((B, max_det), dtype=torch.float32, device=dev)
-    ocls = torch.zeros((B, max_det), dtype=torch.int64, device=dev)
-    orow = torch.zeros((B, max_det), dtype=torch.int64, device=dev)
+    ob = _zeros((B, max_det, 4), torch.float32, dev)
+    os_ = _zeros((B, max_det), torch.float32, dev)
+    ocls = _zeros((B, max_det), torch.int64, dev)
+    orow = _zeros((B, max_det), torch.int64, dev)
     oc = torch.empty((B,), dtype=torch.int32, device=dev)
     _lib.check(_lib.lib().fod_final_detect(_ptr(det_boxes), _ptr(det_scores), _ptr(roi_count), B,
                                            int(problems_per_image), cap, float(score_thresh), float(iou_thresh),
@@ -430,7 +468,7 @@ def absmax(x: Tensor) -> Tensor:
 
 
 def new_amax(device, n: int = 1) -> Tensor:
-    return torch.zeros((n,), dtype=torch.float32, device=device)
+    return _zeros((n,), torch.float32, device)
 
 
 def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ksize: int, relu: bool = False,
@@ -516,7 +554,7 @@ def group_norm_affine(colsum: Tensor, colsumsq: Tensor, hw: int, groups: int, ga
     scale = torch.empty((n, c), dtype=torch.float32, device=dev)
     shift = torch.empty((n, c), dtype=torch.float32, device=dev)
     per_map = x_amax is not None and x_amax.numel() == n and n > 1      # one bound per map in, one per map out
-    bound = torch.zeros((n if per_map else 1,), dtype=torch.float32, device=dev)
+    bound = _zeros((n if per_map else 1,), torch.float32, dev)
     g = None if gamma is None else _chk(gamma, torch.float32, "gamma").contiguous()
     b = None if beta is None else _chk(beta, torch.float32, "beta").contiguous()
     _lib.check(_lib.lib().fod_group_norm_affine(_ptr(colsum), _ptr(colsumsq), n, tiles, c, groups, int(hw), _ptr(g), _ptr(b),
