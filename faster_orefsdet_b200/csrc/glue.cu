@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(kThreads, 2) stem1_u8_tile_kernel(const uint8_
                                                                     float m0, float m1, float m2, float s0, float s1, float s2,
                                                                     const float* __restrict__ w /*[64][27] = OIHW*/,
                                                                     const float* __restrict__ bias, float* __restrict__ y,
-                                                                    float* __restrict__ y_amax, int tiles_x, int tiles_y,
-                                                                    long total_tiles) {
+                                                                    float* __restrict__ y_amax, int amax_per_image,
+                                                                    int tiles_x, int tiles_y, long total_tiles) {
   __shared__ __align__(16) float vs[kS1Rows][3][3 * kS1TileX];   // [input row][channel][kx][pixel]
   __shared__ __align__(16) float ws[27][kStemC];
   __shared__ __align__(16) float bs[kStemC];
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem1_u8_tile_kernel(const uint8_
     __syncthreads();
     if (tile + (int)gridDim.x < total) fetch(tile + (int)gridDim.x);
     const int oy = oy0 + wr;
-    if (oy >= Ho) continue;   // (uniform per warp; the barriers are at the top of the loop and every warp reaches them)
+    if (oy < Ho) {   // (uniform per warp; the barriers are at the top of the loop and every warp reaches them)
     float2 acc[4][8];         // [pixel pair m: pixels 8q + 2m, + 1][channel j]
     {
       const float4 b0 = *reinterpret_cast<const float4*>(&bs[4 * cl]), b1 = *reinterpret_cast<const float4*>(&bs[32 + 4 * cl]);
@@ -334,8 +334,14 @@ __global__ void __launch_bounds__(kThreads, 2) stem1_u8_tile_kernel(const uint8_
         *reinterpret_cast<float4*>(o + 32) = hi;
       }
     }
+    }
+    if (y_amax && amax_per_image) {   // this tile's image: max|y| per image, so that no image's scale depends on its batch mates
+      const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
+      if ((threadIdx.x & 31) == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(y_amax + n), wm);
+      vmax = 0.f;
+    }
   }
-  if (y_amax) {
+  if (y_amax && !amax_per_image) {
     const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax));
     if ((threadIdx.x & 31) == 0 && wm) atomicMax(reinterpret_cast<unsigned int*>(y_amax), wm);
   }
@@ -408,7 +414,7 @@ extern "C" int fod_stem_patches_u8(const uint8_t* x, int n, int h, int w, const 
 }
 
 extern "C" int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, const float* weight,
-                            const float* bias, float* y, float* y_amax, fod_stream_t stream) {
+                            const float* bias, float* y, float* y_amax, int amax_per_image, fod_stream_t stream) {
   FOD_REQUIRE(x && y && mean3 && std3 && weight, "fod_stem1_u8: null pointer");
   FOD_REQUIRE(n >= 0 && h > 0 && w > 0, "fod_stem1_u8: bad sizes");
   FOD_REQUIRE(((uintptr_t)y & 15) == 0, "fod_stem1_u8: output must be 16-byte aligned");
@@ -422,7 +428,7 @@ extern "C" int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* 
   FOD_CUDA_CALL(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long resident = 2L * (sms > 0 ? sms : 148);   // two CTAs per SM (__launch_bounds__), each loops over tiles
   glue::stem1_u8_tile_kernel<<<(unsigned)(total_tiles < resident ? total_tiles : resident), glue::kThreads, 0, as_stream(stream)>>>(
-      x, h, w, ho, wo, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], weight, bias, y, y_amax, tiles_x, tiles_y,
+      x, h, w, ho, wo, mean3[0], mean3[1], mean3[2], std3[0], std3[1], std3[2], weight, bias, y, y_amax, amax_per_image, tiles_x, tiles_y,
       total_tiles);
   FOD_CUDA_LAUNCH_CHECK("fod_stem1_u8");
   return FOD_OK;

@@ -143,10 +143,11 @@ class _OSAModule(nn.Module):
         return self.layers[0][0].in_channels + sum(layer[0].out_channels for layer in self.layers)
 
     def new_buffer(self, n, h, w, device):
-        """NHWC buffer [x | y0 | y1 | y2] of this module, its first slice (written by the producer of x) and one
-        max|.| scalar per slice (the operand bounds of the tensor-core convolutions, ops.conv2d_nhwc)."""
+        """NHWC buffer [x | y0 | y1 | y2] of this module, its first slice (written by the producer of x) and the bounds
+        max|.| per slice AND image, [slices, N] (the operand bounds of the tensor-core convolutions, ops.conv2d_nhwc: every
+        image is scaled by its own bounds, so its result does not depend on its batch mates)."""
         buf = torch.empty((n, h, w, self.concat_channels), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
-        return buf, buf[:, :self.layers[0][0].in_channels], ops.new_amax(device, len(self.layers) + 1)
+        return buf, buf[:, :self.layers[0][0].in_channels], ops.new_amax(device, (len(self.layers) + 1) * n).view(len(self.layers) + 1, n)
 
     def _layers_in_place(self, x, buf=None, amax=None):
         """The 3x3 layers write their outputs straight into channel slices of one NHWC buffer
@@ -155,12 +156,12 @@ class _OSAModule(nn.Module):
         if buf is None:
             buf, first, amax = self.new_buffer(n, h, w, x.device)
             first.copy_(x)
-            amax[0:1].copy_(ops.absmax(x if x.is_contiguous(memory_format=torch.channels_last) else first.contiguous(memory_format=torch.channels_last)))
+            amax[0].copy_(x.detach().abs().amax((1, 2, 3)))
         src, off = buf[:, :c], c
         for i, layer in enumerate(self.layers):
             cw = layer[0].out_channels
             dst = buf[:, off:off + cw]
-            tcconv.conv(src, layer[0], layer[1], relu=True, out=dst, x_amax=amax[i:i + 1], y_amax=amax[i + 1:i + 2])
+            tcconv.conv(src, layer[0], layer[1], relu=True, out=dst, x_amax=amax[i:i + 1], y_amax=amax[i + 1])
             src, off = dst, off + cw
         return buf, amax
 
@@ -171,8 +172,8 @@ class _OSAModule(nn.Module):
         c = self.layers[0][0].in_channels
         amax[1:].zero_()
         self._layers_in_place(buf[:, :c], buf, amax)
-        a_y = ops.new_amax(buf.device)
         n, _, h, w = buf.shape
+        a_y = ops.new_amax(buf.device, n)
         cout = self.concat[0].out_channels
         # the eSE average comes out of the concat convolution's epilogue as per-tile channel sums: no pass over y
         colsum = torch.empty((n, ops.conv2d_tiles_per_image(h, w), cout), dtype=torch.float32, device=buf.device)
@@ -262,22 +263,24 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
         if self.stem[0].out_channels != 64 or tuple(self.stem[0].weight.shape[1:]) != (3, 3, 3):
             return self.tc_stem(ops.stem_patches_u8(x_u8, mean, std), None, out, out_amax)
         w, b = self._stem1_folded()
-        a1, a2 = ops.new_amax(x_u8.device), ops.new_amax(x_u8.device)
+        n = x_u8.shape[0]
+        a1, a2 = ops.new_amax(x_u8.device, n), ops.new_amax(x_u8.device, n)          # per image
         y = ops.stem1_u8(x_u8, mean, std, w, b, y_amax=a1)
-        y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1, y_amax=a2)
-        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2, y_amax=out_amax)
+        y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1.view(1, n), y_amax=a2)
+        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2.view(1, n), y_amax=out_amax)
 
     def tc_stem(self, patches, patches_amax, out, out_amax):
         """stem_1 (as a 1x1 convolution over im2col rows) -> stem_2 -> stem_3 into ``out`` (a batch slice of the first
         slice of the stage-2 concat buffer; ``out_amax`` is only ever raised).  Works on any sub-batch, so a caller can
         overlap host-to-device copies of later images with the stem of earlier ones."""
         pk, b = self._stem1_packed()
+        n = patches.shape[0]
         if patches_amax is None:
-            patches_amax = ops.absmax(patches)
-        a1, a2 = ops.new_amax(patches.device), ops.new_amax(patches.device)
+            patches_amax = patches.detach().abs().amax((1, 2, 3)).view(1, n)           # per image
+        a1, a2 = ops.new_amax(patches.device, n), ops.new_amax(patches.device, n)
         y = ops.conv2d_nhwc(patches, pk, b, self.stem[0].out_channels, 1, relu=True, x_amax=patches_amax, y_amax=a1)
-        y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1, y_amax=a2)
-        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2, y_amax=out_amax)
+        y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1.view(1, n), y_amax=a2)
+        tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2.view(1, n), y_amax=out_amax)
 
     def tc_body(self, buf, amax, want_amax: bool = False, fuse_gates: bool = False):
         """OSA stages from a filled stage-2 concat buffer.  The stage poolings write straight into the first slice of
@@ -289,7 +292,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
         mods = self._tc_modules()
         n = buf.shape[0]
         if "stem" in self._out_features:
-            outputs["stem"], bounds["stem"] = buf[:, :mods[0].layers[0][0].in_channels], amax[0:1]
+            outputs["stem"], bounds["stem"] = buf[:, :mods[0].layers[0][0].in_channels], amax[0]
         for i, (name, mod) in enumerate(zip(self.stage_names, mods)):
             y, gate, a_y = mod.forward_buffer(buf, amax)
             if name in self._out_features:
@@ -303,7 +306,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
                 h, w = (y.shape[2] - 2) // 2 + 1, (y.shape[3] - 2) // 2 + 1
                 buf, first, amax = mods[i + 1].new_buffer(n, h, w, y.device)
                 ops.maxpool3x3s2_nhwc(y, gate, out=first)
-                amax[0:1].copy_(a_y)
+                amax[0].copy_(a_y)
         if fuse_gates:
             return outputs, bounds, gates
         return (outputs, bounds) if want_amax else outputs
@@ -312,7 +315,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
         """Inference on CUDA: every convolution on the tensor cores (csrc/conv_tc.cu), no torch.cat, no layout copies."""
         buf, first, amax = self.tc_new_input_buffer(x.shape[0], x.shape[2], x.shape[3], x.device)
         patches = ops.stem_patches(x)
-        self.tc_stem(patches, ops.absmax(patches), first, amax[0:1])
+        self.tc_stem(patches, None, first, amax[0])
         return self.tc_body(buf, amax)
 
     def forward(self, x):
@@ -376,16 +379,19 @@ class FPN(Backbone):
         ``gates[name]``: [N,C,1,1] factor still to be multiplied into feats[name] (the eSE gate, VoVNet.tc_body)."""
         bounds, gates = bounds or {}, gates or {}
 
+        def per_image(a, t):      # a bound per image [N] -> the [1, N] operand-bound layout of ops.conv2d_nhwc
+            return a.reshape(1, -1) if a is not None and a.dim() == 1 and a.numel() == t.shape[0] and t.shape[0] > 1 else a
+
         def run(m, t, a_in=None, a_out=None, gate=None):
             if tcconv.supported(m, t) and (gate is None or m.in_channels % 32 == 0):
-                return tcconv.conv(t, m, x_amax=a_in, y_amax=a_out, a_gate=gate)
+                return tcconv.conv(t, m, x_amax=per_image(a_in, t), y_amax=a_out, a_gate=gate)
             y = m(t if gate is None else t * gate)
             if a_out is not None:
                 a_out.copy_(y.detach().abs().max().reshape(1))
             return y
 
         def bound(t):
-            return ops.new_amax(t.device) if t.is_cuda else None
+            return ops.new_amax(t.device, t.shape[0]) if t.is_cuda else None      # [N]: one bound per image
 
         top = self.in_features[-1]
         a_prev = bound(feats[top])
@@ -407,8 +413,8 @@ class FPN(Backbone):
                     and tuple(prev.shape[2:]) == ((f.shape[2] + 1) // 2, (f.shape[3] + 1) // 2)):
                 # nearest 2x upsampling + sum inside the lateral convolution's epilogue; its bound is that of the sum
                 a_prev = bound(f)
-                prev = tcconv.conv(f, lat, x_amax=bounds.get(name), y_amax=a_prev, residual=prev, residual_upsample2=True,
-                                   a_gate=gate)
+                prev = tcconv.conv(f, lat, x_amax=per_image(bounds.get(name), f), y_amax=a_prev, residual=prev,
+                                   residual_upsample2=True, a_gate=gate)
             else:
                 top_down = F.interpolate(prev, scale_factor=2.0, mode="nearest")
                 a_lat = bound(f)

@@ -316,14 +316,14 @@ class CenterNet2Detector(nn.Module):
         n, _, h, w = x_u8.shape
         buf, first, amax = into if into is not None else vov.tc_new_input_buffer(n, h, w, x_u8.device)
         mean, std = self._mean_std_host()
-        amax[0:1].zero_()
+        amax[0].zero_()
         chunk = chunk or n
         main = torch.cuda.current_stream(x_u8.device)
         for k, c0 in enumerate(range(0, n, chunk)):
             c1 = min(c0 + chunk, n)
             if events is not None:
                 main.wait_event(events[k])
-            vov.tc_stem_u8(x_u8[c0:c1], mean, std, first[c0:c1], amax[0:1])
+            vov.tc_stem_u8(x_u8[c0:c1], mean, std, first[c0:c1], amax[0, c0:c1])
         last = getattr(self, "_u8_last", None)
         if last is not None and last[2] is x_u8:     # the ring slot may be refilled once this stem has read it
             ev = torch.cuda.Event()

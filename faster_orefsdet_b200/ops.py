@@ -628,8 +628,11 @@ def stem1_u8(x: Tensor, mean: Sequence[float], std: Sequence[float], weight: Ten
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     out = torch.empty((n, ho, wo, 64), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
     m3, s3 = (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std])
-    _lib.check(_lib.lib().fod_stem1_u8(_ptr(x), n, h, w, m3, s3, _ptr(weight), _ptr(bias), _ptr(out), _ptr(y_amax), _stream()),
-               "fod_stem1_u8")
+    per_image = y_amax is not None and y_amax.numel() == n and n > 1
+    if y_amax is not None and y_amax.numel() not in (1, n):
+        raise _lib.FodError("stem1_u8: y_amax must hold 1 or N floats")
+    _lib.check(_lib.lib().fod_stem1_u8(_ptr(x), n, h, w, m3, s3, _ptr(weight), _ptr(bias), _ptr(out), _ptr(y_amax),
+                                       int(per_image), _stream()), "fod_stem1_u8")
     return out
 
 

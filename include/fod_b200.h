@@ -341,10 +341,10 @@ int fod_stem_patches_u8(const uint8_t* x, int n, int h, int w, const float* mean
                         fod_stream_t stream);
 /* stem_1 in one pass (CUDA cores, fp32 FMA): raw uint8 planar batch x [N][3][H][W] -> (x - mean)/std -> 3x3 / stride 2 /
  * pad 1 convolution, 64 output channels, weight [64][3][3][3] (OIHW, FrozenBN folded), bias [64] or NULL -> ReLU ->
- * y [N][ceil(H/2)][ceil(W/2)][64] NHWC; y_amax as in fod_conv2d_nhwc.  (d2!/modeling/backbone/vovnet.py stem_1 +
+ * y [N][ceil(H/2)][ceil(W/2)][64] NHWC; y_amax as in fod_conv2d_nhwc ([N] floats with amax_per_image).  (d2!/modeling/backbone/vovnet.py stem_1 +
  * fsod_cen.py:540-555) */
 int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, const float* weight,
-                 const float* bias, float* y, float* y_amax, fod_stream_t stream);
+                 const float* bias, float* y, float* y_amax, int amax_per_image, fod_stream_t stream);
 int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate, float* y,
                           long y_pixel_stride, fod_stream_t stream);
 

@@ -299,6 +299,25 @@ def test_full_size_batch64_properties():
     ops.check_status(status)
 
 
+def test_whole_detector_batch_equals_single_image_calls():
+    """model(batched_inputs) with B images == B calls with one image each, bit for bit, through the whole detector
+    (feature extractor included): every power-of-two operand scale of the tensor-core kernels is per image."""
+    model = _model()
+    shapes = {k: tuple(v.shape) for k, v in model.state_dict().items() if k.startswith("backbone.")}
+    model.load_state_dict(synth.state_dict(shapes), strict=False)
+    model.set_prototypes(synth.prototypes([1, 6], 5, 7))
+    imgs = [synth.ore_image(192, 256, 4300 + i) for i in range(3)]
+    imgs[1] = (imgs[1].float() * 0.25).to(torch.uint8)          # a much darker image: its own scales must be used
+    batch = [{"image": im} for im in imgs]
+    both = model(batch)
+    for i in range(3):
+        single = model([batch[i]])[0]["instances"]
+        inst = both[i]["instances"]
+        assert len(single) == len(inst) and len(inst) > 0
+        assert torch.equal(single.pred_boxes.tensor, inst.pred_boxes.tensor)
+        assert torch.equal(single.scores, inst.scores) and torch.equal(single.pred_classes, inst.pred_classes)
+
+
 def test_full_detector_forward_with_pkl_side_channel(tmp_path, monkeypatch):
     """model(batched_inputs) through the real backbone, prototypes from ./support_dir/support_feature.pkl."""
     monkeypatch.chdir(tmp_path)
