@@ -81,7 +81,7 @@ class CenterNetHead(nn.Module):
         return clss, bbox_reg, agn_hms
 
     # ---- hot path: tower convolution with GroupNorm statistics in its epilogue -> GroupNorm + ReLU applied to the operand
-    # of ONE 1x1 contraction that produces the nine tap products of agn_hm | bbox_pred (72 columns); the nine shifted sums,
+    # of ONE 1x1 contraction that produces the nine tap products of agn_hm | bbox_pred (45 columns, padded to 48); the nine shifted sums,
     # the biases and Scale + ReLU happen inside fod_decode_topk_taps.  The normalised map, hm and reg never exist.
     def tap_products(self, x: Sequence[torch.Tensor], bounds: Optional[Sequence[torch.Tensor]] = None):
         mods = list(self.bbox_tower)
@@ -106,18 +106,21 @@ class CenterNetHead(nn.Module):
             scale, shift, a_g = ops.group_norm_affine(cs, cq, h * w, gn.num_groups, gn.weight, gn.bias, gn.eps, x_amax=a_t)
             if a_g.numel() == n and n > 1:
                 a_g = a_g.reshape(1, -1)
-            out.append(ops.conv2d_nhwc(t, pk9, None, 72, 1, x_amax=a_g, a_gate=scale, a_shift=shift, a_relu=True))
+            out.append(ops.conv2d_nhwc(t, pk9, None, 48, 1, x_amax=a_g, a_gate=scale, a_shift=shift, a_relu=True))
         return out
 
     def _packed_taps(self) -> torch.Tensor:
-        """[72, 128, 1, 1]: row tap*8 + o = filter tap (ky, kx) of output o (0 = agn_hm, 1..4 = bbox_pred, 5..7 zero)."""
+        """[48, 128, 1, 1]: row tap = filter tap (ky, kx) of agn_hm, row 12 + tap*4 + j = that tap of bbox_pred output j;
+        rows 9..11 zero (the layout fod_decode_topk_taps reads)."""
         ws = (self.agn_hm.weight, self.bbox_pred.weight)
         key = tuple((w.data_ptr(), w._version) for w in ws)
         hit = self.__dict__.get("_taps_cache")
         if hit is None or hit[0] != key:
             with torch.no_grad():
-                w = torch.cat((ws[0], ws[1], ws[0].new_zeros((3,) + tuple(ws[0].shape[1:]))), 0)       # [8, C, 3, 3]
-                w9 = w.permute(2, 3, 0, 1).reshape(72, w.shape[1], 1, 1).contiguous()                  # (ky, kx, o) major
+                c_in = ws[0].shape[1]
+                hm9 = ws[0].permute(0, 2, 3, 1).reshape(9, c_in)                                       # (ky, kx) major
+                reg36 = ws[1].permute(2, 3, 0, 1).reshape(36, c_in)                                    # (ky, kx, j) major
+                w9 = torch.cat((hm9, hm9.new_zeros((3, c_in)), reg36), 0).reshape(48, c_in, 1, 1).contiguous()
                 hit = (key, ops.conv2d_pack(w9.float()))
             self.__dict__["_taps_cache"] = hit
         return hit[1]

@@ -233,8 +233,9 @@ def decode_topk(hm: Sequence[Tensor], reg: Sequence[Tensor], strides: Sequence[i
 def decode_topk_taps(taps: Sequence[Tensor], bias5: Sequence[float], strides: Sequence[int], score_thresh: float,
                      pre_topk: int, status: Tensor, reg_scale: Optional[Sequence[float]] = None,
                      cand_cap: Optional[int] = None):
-    """decode_topk with the 3x3 output convolutions folded in: taps[l] [P,72(+),H,W] NHWC = the per-tap products of the
-    stacked agn_hm | bbox_pred filter with the tower output (one 1x1 contraction, column tap*8 + o); the kernel forms
+    """decode_topk with the 3x3 output convolutions folded in: taps[l] [P,48,H,W] NHWC = the per-tap products of the
+    stacked agn_hm | bbox_pred filter with the tower output (one 1x1 contraction; column tap = heat-map, 12 + tap*4 + j =
+    regression output j); the kernel forms
     bias + the nine shifted sums as it reads (centernet_head.py:152-160, fsod_rpn.py:1071-1181).  Same outputs as
     decode_topk."""
     L = len(taps)
@@ -242,8 +243,8 @@ def decode_topk_taps(taps: Sequence[Tensor], bias5: Sequence[float], strides: Se
     ps = []
     for t in taps:
         s_ = _pixel_stride(t, "taps")
-        if t.shape[1] < 72:
-            raise _lib.FodError("decode_topk_taps: 72 tap columns per pixel expected")
+        if t.shape[1] < 48 or s_ % 4:
+            raise _lib.FodError("decode_topk_taps: 48 tap columns per pixel expected")
         ps.append(int(s_))
     cap = cand_cap if cand_cap is not None else L * pre_topk
     boxes = torch.empty((P, cap, 4), dtype=torch.float32, device=dev)
@@ -254,9 +255,10 @@ def decode_topk_taps(taps: Sequence[Tensor], bias5: Sequence[float], strides: Se
     lv = _levels(taps, strides)
     rs = None if reg_scale is None else (ctypes.c_float * L)(*[float(v) for v in reg_scale])
     b5 = (ctypes.c_float * 5)(*[float(v) for v in bias5])
+    ws = torch.empty((max(int(_lib.lib().fod_decode_topk_taps_workspace_bytes(lv, L, P)), 4),), dtype=torch.uint8, device=dev)
     _lib.check(_lib.lib().fod_decode_topk_taps(_ptr_array(taps), (ctypes.c_int * L)(*ps), b5, lv, L, P, rs, float(score_thresh),
                                                int(pre_topk), cap, _ptr(boxes), _ptr(scores), _ptr(loc), _ptr(level_count),
-                                               _ptr(cand_count), _ptr(status), _stream()), "fod_decode_topk_taps")
+                                               _ptr(cand_count), _ptr(status), _ptr(ws), _stream()), "fod_decode_topk_taps")
     return boxes, scores, loc, level_count, cand_count
 
 

@@ -133,16 +133,20 @@ int fod_decode_topk(const float* const* hm, const float* const* reg, const fod_l
 /* The same selection with the 3x3 output convolutions (agn_hm 128 -> 1, bbox_pred 128 -> 4,
  * CenterNet2/centernet/modeling/dense_heads/centernet_head.py:152-160) folded in.  A 3x3 convolution with 5 outputs keeps the
  * tensor cores busy for 36 K-chunks per tile whatever its width; computed instead as ONE 1x1 contraction
- *   G[p][tap*8 + o] = sum_c W[o][c][ky][kx] * t[p][c]      (tap = ky*3 + kx, o = 0: heat-map, 1..4: l t r b; 72 columns)
- * (fod_conv2d_nhwc, ksize 1, 4 K-chunks per tile) it leaves nine shifted additions per output, which this kernel does
- * while it reads:  out(y, x)[o] = bias5[o] + sum_tap G[(y + ky - 1, x + kx - 1)][tap*8 + o]  (zero outside the map).
- *   taps[l] : [P][H_l][W_l][tap_pixel_stride[l] >= 72] fp32 (tap_pixel_stride NULL = 72)
+ *   G[p][tap]            = sum_c W_hm[c][ky][kx]     * t[p][c]     (tap = ky*3 + kx; columns 9..11 unused)
+ *   G[p][12 + tap*4 + j] = sum_c W_reg[j][c][ky][kx] * t[p][c]     (j = l, t, r, b; 48 columns in all)
+ * (fod_conv2d_nhwc, ksize 1, 4 K-chunks per tile) it leaves nine shifted additions per output, which this op does while
+ * it reads:  out(y, x)[o] = bias5[o] + sum_tap G[(y + ky - 1, x + kx - 1)][column(o, tap)]  (zero outside the map).
+ *   taps[l] : [P][H_l][W_l][tap_pixel_stride[l] >= 48, multiple of 4] fp32, 16-byte aligned (tap_pixel_stride NULL = 48)
  *   bias5   : HOST, agn_hm.bias then bbox_pred.bias;  reg_scale as in fod_decode_topk (HOST, may be NULL)
+ *   workspace : fod_decode_topk_taps_workspace_bytes(levels, num_levels, num_problems) bytes of device memory (the keys
+ *               of every pixel, formed by a wide first kernel; the selecting CTAs read them)
  * The heat-map is taken as a logit. */
+size_t fod_decode_topk_taps_workspace_bytes(const fod_level_t* levels, int num_levels, int num_problems);
 int fod_decode_topk_taps(const float* const* taps, const int* tap_pixel_stride, const float* bias5, const fod_level_t* levels,
                          int num_levels, int num_problems, const float* reg_scale, float score_thresh, int pre_topk,
                          int cand_cap, float* boxes, float* scores, int64_t* loc, int32_t* level_count, int32_t* cand_count,
-                         uint32_t* status, fod_stream_t stream);
+                         uint32_t* status, void* workspace, fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * N0  class-agnostic NMS + post-NMS top-k.  Replaces nms_and_topK -> ml_nms ->

@@ -177,15 +177,15 @@ def test_decode_topk_taps_equals_conv_then_decode():
     P = 3
     wh, bh = sd["proposal_generator.centernet_head.agn_hm.weight"], sd["proposal_generator.centernet_head.agn_hm.bias"]
     wr, br = sd["proposal_generator.centernet_head.bbox_pred.weight"], sd["proposal_generator.centernet_head.bbox_pred.bias"]
-    w8 = torch.cat((wh, wr, torch.zeros((3, 128, 3, 3))), 0)
-    w9 = w8.permute(2, 3, 0, 1).reshape(72, 128, 1, 1).contiguous()
+    w9 = torch.cat((wh.permute(0, 2, 3, 1).reshape(9, 128), torch.zeros((3, 128)),   # row tap | 12 + tap*4 + j
+                    wr.permute(2, 3, 0, 1).reshape(36, 128)), 0).reshape(48, 128, 1, 1).contiguous()
     pk = ops.conv2d_pack(w9.to(DEV))
     sizes, strides, scales = [(40, 48), (20, 24), (7, 9)], (8, 16, 32), (1.0, 0.9, 1.1)
     taps, ts = [], []
     for l, (h, w) in enumerate(sizes):
         t_ = synth.tensor((P, 128, h, w), 400 + l, 0.0, 1.2)            # tower output (post ReLU)
         ts.append(t_)
-        taps.append(ops.conv2d_nhwc(t_.to(DEV).contiguous(memory_format=torch.channels_last), pk, None, 72, 1))
+        taps.append(ops.conv2d_nhwc(t_.to(DEV).contiguous(memory_format=torch.channels_last), pk, None, 48, 1))
     status = ops.new_status(DEV)
     bias5 = torch.cat((bh, br)).tolist()
     boxes, scores, loc, lc, cc = ops.decode_topk_taps(taps, bias5, strides, CFG.inference_th, 1000, status, reg_scale=scales)
