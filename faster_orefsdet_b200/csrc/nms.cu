@@ -40,6 +40,7 @@ __device__ long long g_nms_prof[16];
 
 constexpr int kNmsThreads = 1024;
 constexpr int kChunk = 64;
+constexpr int kPreRead = 3;      // list passes a thread may hold in registers (suppression pass of greedy_sweep)
 constexpr int kMaxCluster = 4;   // measured: 8 CTAs per problem are slower than 4 (cluster barrier + the redundant sort / resolve)
 
 struct NmsSmem {
@@ -340,22 +341,22 @@ __device__ inline int greedy_sweep(const NmsSmem& s, int n, float thr_f, int lim
     const int nk = s.scalars[2];
     // 1'. the next chunk's bit matrix (independent of the suppression state, so it shares this all-warps phase)
     build_colmask(c + 1);
+    PROF_ADD(14, t3);
     // 3. survivors of this chunk suppress later boxes.  This CTA owns the words w with w % S == rank and keeps a list
     //    of its boxes that are alive and beyond the resolved chunks; one pass tests every listed box against the
     //    chunk's survivors (G lanes share a box and split the survivor list) and compacts the list in place, so the
     //    work follows the number of boxes still alive, not the number of candidates.
-    {   // (also when the chunk has no survivor: the pass drops the resolved chunk from the list)
+    if (nk > 0) {   // (a chunk without survivors changes nothing; its own entries are dropped by the next pass)
       const int lim = base + kChunk;
       const int nal = s.scalars[3];
-      int G = 4;
-      while (G < 32 && nal * G * 2 <= kNmsThreads) G <<= 1;
-      const int per_pass = kNmsThreads / G;
-      const int sub = tid & (G - 1), grp = tid / G;
+      int lg = 0;
+      while (lg < 5 && (nal << (lg + 1)) <= kNmsThreads) ++lg;
+      const int G = 1 << lg, per_pass = kNmsThreads >> lg;
+      const int sub = tid & (G - 1), grp = tid >> lg;
       const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-      for (int e0 = 0; e0 < nal; e0 += per_pass) {
-        const int e = e0 + grp;
-        const int j = e < nal ? (int)s.alist_top[-e] : -1;
-        const bool live = j >= lim;
+      // suppression test of list entry j against the chunk's survivors (the G lanes of a group split them)
+      // suppression test of list entry j against the chunk's survivors (the G lanes of a group split them)
+      auto test = [&](int j, bool live) {
         bool hit = false;
         if (live) {
           const float4 bj = s.box[j];
@@ -367,7 +368,52 @@ __device__ inline int greedy_sweep(const NmsSmem& s, int n, float thr_f, int lim
             }
           }
         }
-        const bool dead = (__ballot_sync(0xffffffffu, hit) & gmask) != 0u;
+        return (__ballot_sync(0xffffffffu, hit) & gmask) != 0u;
+      };
+      if (nal <= kPreRead * per_pass) {
+        // The usual case: every thread fetches its entries of all passes first, so after ONE barrier the compaction may
+        // write anywhere in the list; a warp then runs its passes back to back and claims its output slots with one
+        // atomic (the order of the list is irrelevant: it is a set).
+        int js[kPreRead];
+#pragma unroll
+        for (int q = 0; q < kPreRead; ++q) {
+          const int e = q * per_pass + grp;
+          js[q] = e < nal ? (int)s.alist_top[-e] : -1;
+        }
+        __syncthreads();
+        unsigned survbits = 0;   // bit q: entry q of this thread survives (set in the group's first lane only)
+        int wtot = 0;
+        const int wfirst = (warp * 32) >> lg;   // this warp's first entry of pass 0: a warp without entries skips the pass
+#pragma unroll
+        for (int q = 0; q < kPreRead; ++q) {
+          if (q * per_pass + wfirst < nal) {   // uniform over the warp
+            const int j = js[q];
+            const bool live = j >= lim;
+            const bool dead = test(j, live);
+            if (live && dead && sub == 0) atomicOr(&s.suppressed[j >> 5], 1u << (j & 31));
+            const bool surv = live && !dead && sub == 0;
+            survbits |= (surv ? 1u : 0u) << q;
+            wtot += __popc(__ballot_sync(0xffffffffu, surv));
+          }
+        }
+        int wbase = 0;
+        if (lane == 0 && wtot) wbase = atomicAdd(&s.scalars[4], wtot);
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+#pragma unroll
+        for (int q = 0; q < kPreRead; ++q) {
+          if (q * per_pass + wfirst < nal) {
+            const bool surv = (survbits >> q) & 1u;
+            const unsigned sm = __ballot_sync(0xffffffffu, surv);
+            if (surv) s.alist_top[-(wbase + __popc(sm & ((1u << lane) - 1u)))] = (uint16_t)js[q];
+            wbase += __popc(sm);
+          }
+        }
+      } else {
+      for (int e0 = 0; e0 < nal; e0 += per_pass) {
+        const int e = e0 + grp;
+        const int j = e < nal ? (int)s.alist_top[-e] : -1;
+        const bool live = j >= lim;
+        const bool dead = test(j, live);
         if (live && dead && sub == 0) atomicOr(&s.suppressed[j >> 5], 1u << (j & 31));
         const bool surv = live && !dead && sub == 0;
         const unsigned sm = __ballot_sync(0xffffffffu, surv);
@@ -377,11 +423,13 @@ __device__ inline int greedy_sweep(const NmsSmem& s, int n, float thr_f, int lim
         __syncthreads();  // every entry of this pass has been read; the writes stay below the next pass's entries
         if (surv) s.alist_top[-(wbase + __popc(sm & ((1u << lane) - 1u)))] = (uint16_t)j;
       }
+      }
     }
+    PROF_ADD(15, t3);
     __syncthreads();
     PROF_ADD(3, t3);
     PROF_T(t4);
-    if (tid == 0) s.scalars[3] = s.scalars[4];
+    if (tid == 0 && nk > 0) s.scalars[3] = s.scalars[4];
     if (S > 1) {
       // hand the next chunk's two suppression words to every CTA (parity-alternating slots: the peers may still be
       // reading this chunk's slot)
@@ -400,7 +448,7 @@ __device__ inline int greedy_sweep(const NmsSmem& s, int n, float thr_f, int lim
   }
   __syncthreads();
   PROF_FLUSH(0, 6);
-  PROF_FLUSH(9, 14);
+  PROF_FLUSH(9, 16);
   return s.scalars[0];
 }
 

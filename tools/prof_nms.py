@@ -42,7 +42,9 @@ for _ in range(3):
     ops.nms_proposals(boxes, scores, count, 0.6, post, roi_cap, status)
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 16)()
-L.fod_nms_prof(buf, 1)
+has_prof = hasattr(L, 'fod_nms_prof')      # only in a -DFOD_NMS_PROF build
+if has_prof:
+    L.fod_nms_prof(buf, 1)
 iters = 10
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
@@ -50,8 +52,10 @@ for _ in range(iters):
     keep, ob, os_, oc = ops.nms_proposals(boxes, scores, count, 0.6, post, roi_cap, status)
 e1.record()
 torch.cuda.synchronize()
-L.fod_nms_prof(buf, 0)
+if has_prof:
+    L.fod_nms_prof(buf, 0)
 v = [x / iters for x in buf]
 print(f"P={P} n={n} post={post}: {e0.elapsed_time(e1)/iters*1e3:.1f} us/call; kept(sweep) {v[8]:.0f}, out {int(oc[0])}")
 print(f"  chunks {v[9]:.0f}  fixed-point rounds {v[10]:.0f}  step2 cumulative: after fixed point {v[11]:.0f}, after kept writes {v[12]:.0f}, after lane-0 tail {v[13]:.0f}")
 print(f"  cycles: load+sort+gather {v[6]:.0f}  sweep {v[7]:.0f}  [step1 {v[1]:.0f} step2 {v[2]:.0f} step3 {v[3]:.0f} push+sync {v[4]:.0f} loop-total {v[5]:.0f}]")
+print(f"  step3 of thread 0 (cumulative): after colmask {v[14]:.0f}, after its suppression passes {v[15]:.0f}")
