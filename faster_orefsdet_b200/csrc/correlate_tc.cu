@@ -167,15 +167,19 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
   const uint32_t bar0 = cx.bar0;
   const uint32_t a_full_leader = map_to_cta(bar0 + 8u * (2 * kQStages), 0);
   const uint32_t trow = cx.tmem_base + ((uint32_t)(qd * 32) << 16) + kColA;
-  // byte offset of 16-byte chunk 0 of each neighbour's 128-byte row (swizzled); chunk jj is this ^ (jj << 4)
-  uint32_t off[3][3];
+  // A warp holds two tile rows (lanes 0..15: row 2 qd, lanes 16..31: row 2 qd + 1).  The 1x3 row pass of a halo row is
+  // shared by the three 3x1 taps that read it, so a lane evaluates it for its own row and for the row on the far side
+  // (above for the upper half warp, below for the lower one) and takes the third from lane ^ 16, whose own row it is:
+  // 6 LDS.128 and 4 SHFL per four channels instead of 9 LDS.128 - the kernel's limiter is the shared-memory pipe.
+  // byte offset of 16-byte chunk 0 of a neighbour's 128-byte row (swizzled); chunk jj is this ^ (jj << 4)
+  const bool upper = lane < 16;
+  uint32_t off_own[3], off_out[3];
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      int r = (ty + dy) * kHaloW + tx + dx;
-      off[dy][dx] = (uint32_t)(r * 128 + ((r & 7) << 4));
-    }
+  for (int dx = 0; dx < 3; ++dx) {
+    const int r1 = (ty + 1) * kHaloW + tx + dx, r2 = (ty + (upper ? 0 : 2)) * kHaloW + tx + dx;
+    off_own[dx] = (uint32_t)(r1 * 128 + ((r1 & 7) << 4));
+    off_out[dx] = (uint32_t)(r2 * 128 + ((r2 & 7) << 4));
+  }
   const int T = P.total_tiles;
   int i = 0;
   // Outer loops over the tap sets (level, class): `set` is a loop counter (uniform); this CTA's tiles arrive in
@@ -209,18 +213,33 @@ __device__ __forceinline__ void stencil_role(const Params& P, const StencilCtx& 
               uint32_t shi[4], slo[4], qhi[4], qlo[4];
               float4 qc4;
               float2 t3[3][2];
+              float2 t_own[2], t_out[2];
 #pragma unroll
-              for (int dy = 0; dy < 3; ++dy) {
-                const float4 ql = lds4s(qt + (off[dy][0] ^ jx));
-                const float4 qm = lds4s(qt + (off[dy][1] ^ jx));
-                const float4 qr = lds4s(qt + (off[dy][2] ^ jx));
-                if (dy == 1) qc4 = qm;
-                t3[dy][0] = relu2(__ffma2_rn(make_float2(k13r.x, k13r.y), make_float2(qr.x, qr.y),
-                                             __ffma2_rn(make_float2(k13l.x, k13l.y), make_float2(ql.x, ql.y),
-                                                        __fmul2_rn(make_float2(k13c.x, k13c.y), make_float2(qm.x, qm.y)))));
-                t3[dy][1] = relu2(__ffma2_rn(make_float2(k13r.z, k13r.w), make_float2(qr.z, qr.w),
-                                             __ffma2_rn(make_float2(k13l.z, k13l.w), make_float2(ql.z, ql.w),
-                                                        __fmul2_rn(make_float2(k13c.z, k13c.w), make_float2(qm.z, qm.w)))));
+              for (int rr = 0; rr < 2; ++rr) {   // rr = 0: the lane's own row, 1: the row on the far side
+                const float4 ql = lds4s(qt + ((rr ? off_out[0] : off_own[0]) ^ jx));
+                const float4 qm = lds4s(qt + ((rr ? off_out[1] : off_own[1]) ^ jx));
+                const float4 qr = lds4s(qt + ((rr ? off_out[2] : off_own[2]) ^ jx));
+                if (rr == 0) qc4 = qm;
+                const float2 v0 = relu2(__ffma2_rn(make_float2(k13r.x, k13r.y), make_float2(qr.x, qr.y),
+                                                   __ffma2_rn(make_float2(k13l.x, k13l.y), make_float2(ql.x, ql.y),
+                                                              __fmul2_rn(make_float2(k13c.x, k13c.y), make_float2(qm.x, qm.y)))));
+                const float2 v1 = relu2(__ffma2_rn(make_float2(k13r.z, k13r.w), make_float2(qr.z, qr.w),
+                                                   __ffma2_rn(make_float2(k13l.z, k13l.w), make_float2(ql.z, ql.w),
+                                                              __fmul2_rn(make_float2(k13c.z, k13c.w), make_float2(qm.z, qm.w)))));
+                if (rr == 0) {
+                  t_own[0] = v0;
+                  t_own[1] = v1;
+                } else {
+                  t_out[0] = v0;
+                  t_out[1] = v1;
+                }
+              }
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float2 t_x = make_float2(__shfl_xor_sync(0xffffffffu, t_own[h].x, 16), __shfl_xor_sync(0xffffffffu, t_own[h].y, 16));
+                t3[0][h] = upper ? t_out[h] : t_x;
+                t3[1][h] = t_own[h];
+                t3[2][h] = upper ? t_x : t_out[h];
               }
               const float4 c11 = *reinterpret_cast<const float4*>(tp + 7 * kC);
               const float4 k31u = *reinterpret_cast<const float4*>(tp + 4 * kC);
