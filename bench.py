@@ -225,6 +225,41 @@ class KernelTimer:
         return out
 
 
+def fsodrcnn_record(dev, steps):
+    """SURVEY 8f#3, the R50-C4 FsodRCNN path (Base-FSOD-C4.yaml: attention RPN, 1000 -> 100 proposals, relation head):
+    model(batched_inputs) on 16 synthetic 640x640 images already on the device, 2-way episode, timed with CUDA events
+    after three warm-up calls; parity of this path is pinned by tests/test_fsodrcnn_gpu.py."""
+    from faster_orefsdet_b200.compat import META_ARCH_REGISTRY
+    from faster_orefsdet_b200.config import get_cfg
+    import faster_orefsdet_b200.modeling  # noqa: F401
+    cfg = get_cfg()
+    cfg.merge_from_file(os.path.join(ROOT, "configs/fsod/Base-FSOD-C4.yaml"))
+    cfg.merge_from_list(["MODEL.DEVICE", str(dev)])
+    m = META_ARCH_REGISTRY.get("FsodRCNN")(cfg).to(dev).eval()      # (detectron2's build_model does the .to())
+    m.load_state_dict(synth.state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}))
+    sup = {"res4_avg": {}, "res5_avg": {}}
+    for j, c in enumerate((3, 9)):
+        sup["res4_avg"][c] = synth.tensor((1, 1024, 14, 14), 341 + 2 * j, 0.0, 1.2)
+        sup["res5_avg"][c] = synth.tensor((1, 2048, 7, 7), 342 + 2 * j, 0.0, 1.0)
+    m.set_prototypes(sup)
+    nb = 16
+    batches = [[{"image": synth.ore_image(IMG, IMG, 7000 + 17 * k + i).to(dev)} for i in range(nb)] for k in range(2)]
+    with torch.no_grad():
+        for k in range(3):
+            out = m(batches[k % 2])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            out = m(batches[k % 2])
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"workload": f"FsodRCNN R50-C4 (Base-FSOD-C4.yaml), 2-way episode, batch {nb} x {IMG}x{IMG}, through model(batched_inputs)",
+            "ms_per_step": ms, "images_per_s": nb / (ms * 1e-3), "steps": steps,
+            "detections": int(sum(len(o["instances"]) for o in out))}
+
+
 def run_gpu_arm(args):
     import torch.distributed as dist
     from faster_orefsdet_b200 import ops
@@ -393,6 +428,7 @@ def run_gpu_arm(args):
                 del xs
             pg.pre_nms_topk_test, pg.post_nms_topk_test = keep
             model.set_prototypes(synth.prototypes([1], SHOTS, 7))
+            cfg_records["FsodRCNN"] = fsodrcnn_record(dev, max(args.steps // 2, 3))
 
         # ---- BASELINE.json configs[4] as written (strong scaling): ONE global batch of 256 queries sharded 256 / G with the
         # InferenceSampler formula (d2!/data/samplers/distributed_sampler.py:191-194), prototypes broadcast by rank 0 and the
