@@ -46,17 +46,18 @@ constexpr int kMaxCluster = 4;   // measured: 8 CTAs per problem are slower than
 struct NmsSmem {
   unsigned long long* keys;     // [npad]
   float4* box;                  // [ncap] sorted boxes (possibly class-offset)
-  float4* kbox;                 // [64] survivors of the chunk being applied
+  float4* kbox;                 // [128] survivors of the chunk pair being applied
   uint32_t* colmask;            // [2 buffers][lo 64 | hi 64]: bit i of word j: chunk box i (i < j) overlaps chunk box j
-  float* karea;                 // [64]
+  float* karea;                 // [128]
   uint32_t* suppressed;         // [ncap/32 + 2]; a CTA of a cluster keeps only its own words up to date
-  uint32_t* chunk_sup;          // [2 parities][2]: suppression words of the chunk being resolved (pushed by their owners)
+  uint32_t* chunk_sup;          // [2 parities][4 + 2]: suppression words of the chunk pair being resolved (pushed by their
+                                // owners), then the pair's two cross words (second chunk suppressed by the first one's survivors)
   int* scalars;                 // [8]
   uint16_t* kept;               // [ncap] sorted ranks of survivors, growing from the front ...
   uint16_t* alist_top;          // ... and, from the END of the same array downwards (entry e at alist_top[-e]), this CTA's
-                                // boxes that are still alive and not yet resolved (any order).  While chunk c is being
-                                // resolved the list still holds the chunk's own <= 64 boxes: survivors + listed <= n + 64,
-                                // which is the size of the array.
+                                // boxes that are still alive and not yet resolved (any order).  While a pair of chunks is
+                                // being resolved the list still holds the pair's own <= 128 boxes: survivors + listed
+                                // <= n + 128, which is the size of the array.
 };
 
 __host__ __device__ inline int next_pow2(int n) {
@@ -65,11 +66,11 @@ __host__ __device__ inline int next_pow2(int n) {
   return p;
 }
 
-__host__ __device__ inline size_t nms_words(int ncap) { return (size_t)(ncap + 31) / 32 + 2; }
+__host__ __device__ inline size_t nms_words(int ncap) { return (size_t)(ncap + 31) / 32 + 4; }   // 4 spare (zero) words
 
 __host__ inline size_t nms_smem_bytes(int ncap) {
   int npad = next_pow2(ncap < 64 ? 64 : ncap);
-  return (size_t)npad * 8 + (size_t)ncap * 16 + 64 * 16 + 2 * 128 * 4 + 64 * 4 + nms_words(ncap) * 4 + 16 + 32 + (size_t)(ncap + kChunk) * 2 + 64;
+  return (size_t)npad * 8 + (size_t)ncap * 16 + 128 * 16 + 2 * 128 * 4 + 128 * 4 + nms_words(ncap) * 4 + 48 + 32 + (size_t)(ncap + 2 * kChunk) * 2 + 64;
 }
 
 __device__ inline NmsSmem carve(unsigned char* base, int ncap) {
@@ -80,19 +81,19 @@ __device__ inline NmsSmem carve(unsigned char* base, int ncap) {
   s.box = reinterpret_cast<float4*>(base);
   base += (size_t)ncap * 16;
   s.kbox = reinterpret_cast<float4*>(base);
-  base += 64 * 16;
+  base += 128 * 16;
   s.colmask = reinterpret_cast<uint32_t*>(base);
   base += 2 * 128 * 4;
   s.karea = reinterpret_cast<float*>(base);
-  base += 64 * 4;
+  base += 128 * 4;
   s.suppressed = reinterpret_cast<uint32_t*>(base);
   base += nms_words(ncap) * 4;
   s.chunk_sup = reinterpret_cast<uint32_t*>(base);
-  base += 16;
+  base += 48;
   s.scalars = reinterpret_cast<int*>(base);
   base += 32;
   s.kept = reinterpret_cast<uint16_t*>(base);
-  s.alist_top = s.kept + (ncap + kChunk - 1);
+  s.alist_top = s.kept + (ncap + 2 * kChunk - 1);
   return s;
 }
 
@@ -200,8 +201,9 @@ __device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v
 // S = CTAs per problem (cluster size), rank = this CTA's rank in the cluster: every CTA calls with identical data and
 // gets the same survivor list in s.kept; the return value is its length.
 //
-// Per chunk: [resolve: one warp] sync [bit matrix of the NEXT chunk + suppression of later boxes: all warps] sync
-// [exchange of the next chunk's suppression words: cluster only].  A warp that runs alone is latency bound (~5 cycles
+// Per pair of chunks: [resolve the first: one warp] sync [bit matrix of the second + its boxes against the first one's
+// survivors: all warps] sync [resolve the second: one warp] sync [bit matrix of the next pair's first chunk + suppression
+// of later boxes by the pair's survivors: all warps] sync [exchange of the next pair's suppression words: cluster only].  A warp that runs alone is latency bound (~5 cycles
 // per dependent instruction), so the resolve step works on 32-bit halves and everything that does not depend on it is
 // moved into the all-warps phase.
 template <typename ScoreFn>
@@ -211,8 +213,8 @@ __device__ inline int greedy_sweep(const NmsSmem& s, int n, float thr_f, int lim
   const int nwords = (n + 31) >> 5;
   const int nchunks = (n + kChunk - 1) / kChunk;
   PROF_DECL;
-  for (int w = tid; w < nwords + 2; w += blockDim.x) s.suppressed[w] = 0;
-  if (tid < 2) s.chunk_sup[tid] = 0;  // chunk 0 (parity 0) starts with nothing suppressed; parity 1 is always pushed
+  for (int w = tid; w < nwords + 4; w += blockDim.x) s.suppressed[w] = 0;
+  if (tid < 4) s.chunk_sup[tid] = 0;  // pair 0 (parity 0) starts with nothing suppressed; parity 1 is always pushed
   // this CTA's boxes: ranks j whose word (j >> 5) is congruent to `rank` modulo S; all alive at the start
   for (int q = tid;; q += blockDim.x) {
     const int j = (rank + (q >> 5) * S) * 32 + (q & 31);
@@ -264,98 +266,123 @@ __device__ inline int greedy_sweep(const NmsSmem& s, int n, float thr_f, int lim
   __syncthreads();
   build_colmask(0);
   sync_group(S);  // also: every CTA of the cluster is running before anyone writes into a peer's shared memory
-  for (int c = 0; c < nchunks; ++c) {
+  // 2. resolution of chunk c by one warp: fixed point of kept_j = alive_j && !(colmask_j & kept), 32-bit halves.  The
+  //    chunk's survivors are appended to s.kept and to the pair's survivor boxes from slot `kofs` on.  (warp 0 only)
+  auto resolve = [&](int c, uint32_t suplo, uint32_t suphi, int kofs) {
     const int base = c * kChunk;
     const int m = min(kChunk, n - base);
-    const int par = c & 1;
-    PROF_T(t2);
-    // 2. resolution of the chunk by one warp: fixed point of kept_j = alive_j && !(colmask_j & kept), 32-bit halves
-    if (warp == 0) {
-      uint32_t suplo, suphi;
-      if (S > 1) {
-        suplo = s.chunk_sup[par * 2];
-        suphi = s.chunk_sup[par * 2 + 1];
-      } else {
-        suplo = s.suppressed[base >> 5];
-        suphi = s.suppressed[(base >> 5) + 1];
-      }
-      const uint32_t validlo = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
-      const uint32_t validhi = m == 64 ? 0xffffffffu : (m > 32 ? ((1u << (m - 32)) - 1u) : 0u);
-      const uint32_t alo = validlo & ~suplo, ahi = validhi & ~suphi;
-      const uint32_t* clo = s.colmask + par * 128;
-      const uint32_t c0 = clo[lane], c1l = clo[lane + 32], c1h = clo[64 + lane + 32];
-      const bool a0 = (alo >> lane) & 1u, a1 = (ahi >> lane) & 1u;
-      uint32_t klo = alo, khi = ahi;
-      for (int it = 0; it < kChunk; ++it) {
-        const uint32_t nlo = __ballot_sync(0xffffffffu, a0 && !(c0 & klo));
-        const uint32_t nhi = __ballot_sync(0xffffffffu, a1 && !((c1l & klo) | (c1h & khi)));
-        PROF_CNT(10, 1);
-        if (nlo == klo && nhi == khi) break;
-        klo = nlo;
-        khi = nhi;
-      }
-      PROF_ADD(11, t2);
-      int cnt = s.scalars[0];
-      const uint32_t lt = (1u << lane) - 1u;
-      const int nklo = __popc(klo);
-      if ((klo >> lane) & 1u) {
-        const int pos = __popc(klo & lt);
-        const float4 b = s.box[base + lane];
-        s.kept[cnt + pos] = (uint16_t)(base + lane);
-        s.kbox[pos] = b;
-        s.karea[pos] = box_area(b);
-      }
-      if ((khi >> lane) & 1u) {
-        const int pos = nklo + __popc(khi & lt);
-        const float4 b = s.box[base + lane + 32];
-        s.kept[cnt + pos] = (uint16_t)(base + lane + 32);
-        s.kbox[pos] = b;
-        s.karea[pos] = box_area(b);
-      }
-      const int nk = nklo + __popc(khi);
-      cnt += nk;
-      __syncwarp();
-      PROF_ADD(12, t2);
-      if (lane == 0) {
-        s.scalars[0] = cnt;
-        s.scalars[2] = nk;
-        s.scalars[4] = 0;   // survivor counter of this chunk's compaction pass
-        // early stop: the top-`limit` survivors are decided
-        int stop = 0;
-        if (limit > 0 && cnt >= limit && base + kChunk < n) {
-          if (!keep_ties) {
-            stop = 1;
-          } else {
-            float sl = score_of_rank(s.kept[limit - 1]);
-            if (score_of_rank(base + kChunk) < sl) stop = 1;
-          }
+    const uint32_t validlo = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+    const uint32_t validhi = m == 64 ? 0xffffffffu : (m > 32 ? ((1u << (m - 32)) - 1u) : 0u);
+    const uint32_t alo = validlo & ~suplo, ahi = validhi & ~suphi;
+    const uint32_t* clo = s.colmask + (c & 1) * 128;
+    const uint32_t c0 = clo[lane], c1l = clo[lane + 32], c1h = clo[64 + lane + 32];
+    const bool a0 = (alo >> lane) & 1u, a1 = (ahi >> lane) & 1u;
+    uint32_t klo = alo, khi = ahi;
+    for (int it = 0; it < kChunk; ++it) {
+      const uint32_t nlo = __ballot_sync(0xffffffffu, a0 && !(c0 & klo));
+      const uint32_t nhi = __ballot_sync(0xffffffffu, a1 && !((c1l & klo) | (c1h & khi)));
+      PROF_CNT(10, 1);
+      if (nlo == klo && nhi == khi) break;
+      klo = nlo;
+      khi = nhi;
+    }
+    int cnt = s.scalars[0];
+    const uint32_t lt = (1u << lane) - 1u;
+    const int nklo = __popc(klo);
+    if ((klo >> lane) & 1u) {
+      const int pos = __popc(klo & lt);
+      const float4 b = s.box[base + lane];
+      s.kept[cnt + pos] = (uint16_t)(base + lane);
+      s.kbox[kofs + pos] = b;
+      s.karea[kofs + pos] = box_area(b);
+    }
+    if ((khi >> lane) & 1u) {
+      const int pos = nklo + __popc(khi & lt);
+      const float4 b = s.box[base + lane + 32];
+      s.kept[cnt + pos] = (uint16_t)(base + lane + 32);
+      s.kbox[kofs + pos] = b;
+      s.karea[kofs + pos] = box_area(b);
+    }
+    const int nk = nklo + __popc(khi);
+    cnt += nk;
+    __syncwarp();
+    if (lane == 0) {
+      s.scalars[0] = cnt;
+      s.scalars[2] = kofs + nk;   // survivors of the pair so far
+      // early stop: the top-`limit` survivors are decided
+      int stop = 0;
+      if (limit > 0 && cnt >= limit && base + kChunk < n) {
+        if (!keep_ties) {
+          stop = 1;
+        } else {
+          float sl = score_of_rank(s.kept[limit - 1]);
+          if (score_of_rank(base + kChunk) < sl) stop = 1;
         }
-        s.scalars[1] = stop;
       }
-      PROF_ADD(13, t2);
+      s.scalars[1] = stop;
+    }
+  };
+  // Chunks are taken in PAIRS: the second chunk of a pair gets the first one's suppression from a direct 64 x nk test
+  // (two boxes per warp, redundantly in every CTA of a cluster), so the expensive pass over all later boxes - whose cost
+  // is mostly its fixed per-warp skeleton, see profiles/r2_ncu_summary.md - runs once per 128 candidates.
+  for (int c = 0; c < nchunks; c += 2) {
+    const int base = c * kChunk;
+    const int par = (c >> 1) & 1;
+    uint32_t* csup = s.chunk_sup + par * 6;   // [0..1] chunk c, [2..3] chunk c + 1, [4..5] cross words of chunk c + 1
+    PROF_T(t2);
+    if (warp == 0) {
+      if (lane < 2) csup[4 + lane] = 0;
+      resolve(c, S > 1 ? csup[0] : s.suppressed[base >> 5], S > 1 ? csup[1] : s.suppressed[(base >> 5) + 1], 0);
+      if (lane == 0) s.scalars[4] = 0;   // survivor counter of the pair's compaction pass
+    }
+    __syncthreads();
+    if (s.scalars[1] || c + 1 == nchunks) break;  // same decision in every CTA of the cluster (identical data)
+    {
+      // 1'. bit matrix of the pair's second chunk, and its boxes against the first chunk's survivors
+      build_colmask(c + 1);
+      const int nk0 = s.scalars[2];
+      const int base1 = base + kChunk, m1 = min(kChunk, n - base1);
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int j = warp * 2 + rr;
+        bool hit = false;
+        if (j < m1) {
+          const float4 bj = s.box[base1 + j];
+          const float aj = box_area(bj);
+          for (int k = lane; k < nk0; k += 32) hit = hit || iou_exceeds(s.kbox[k], s.karea[k], bj, aj, thr_f);
+        }
+        if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(&csup[4 + (j >> 5)], 1u << (j & 31));
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int w1 = (base + kChunk) >> 5;
+      resolve(c + 1, (S > 1 ? csup[2] : s.suppressed[w1]) | csup[4], (S > 1 ? csup[3] : s.suppressed[w1 + 1]) | csup[5], s.scalars[2]);
     }
     __syncthreads();
     PROF_ADD(2, t2);
     PROF_T(t3);
-    if (s.scalars[1] || c + 1 == nchunks) break;  // same decision in every CTA of the cluster (identical data)
+    if (s.scalars[1] || c + 2 >= nchunks) break;
     const int nk = s.scalars[2];
-    // 1'. the next chunk's bit matrix (independent of the suppression state, so it shares this all-warps phase)
-    build_colmask(c + 1);
+#ifdef FOD_NMS_DBG
+    if (tid == 0 && blockIdx.x == 0) printf("pair c=%d base=%d nk=%d nal=%d kept=%d cross=%08x %08x\n", c, base, nk, s.scalars[3], s.scalars[0], csup[4], csup[5]);
+#endif
+    // 1'. the next pair's first bit matrix (independent of the suppression state, so it shares this all-warps phase)
+    build_colmask(c + 2);
     PROF_ADD(14, t3);
-    // 3. survivors of this chunk suppress later boxes.  This CTA owns the words w with w % S == rank and keeps a list
+    // 3. survivors of this pair suppress later boxes.  This CTA owns the words w with w % S == rank and keeps a list
     //    of its boxes that are alive and beyond the resolved chunks; one pass tests every listed box against the
-    //    chunk's survivors (G lanes share a box and split the survivor list) and compacts the list in place, so the
+    //    pair's survivors (G lanes share a box and split the survivor list) and compacts the list in place, so the
     //    work follows the number of boxes still alive, not the number of candidates.
-    if (nk > 0) {   // (a chunk without survivors changes nothing; its own entries are dropped by the next pass)
-      const int lim = base + kChunk;
+    if (nk > 0) {   // (a pair without survivors changes nothing; its own entries are dropped by the next pass)
+      const int lim = base + 2 * kChunk;
       const int nal = s.scalars[3];
       int lg = 0;
       while (lg < 5 && (nal << (lg + 1)) <= kNmsThreads) ++lg;
       const int G = 1 << lg, per_pass = kNmsThreads >> lg;
       const int sub = tid & (G - 1), grp = tid >> lg;
       const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
-      // suppression test of list entry j against the chunk's survivors (the G lanes of a group split them)
-      // suppression test of list entry j against the chunk's survivors (the G lanes of a group split them)
+      // suppression test of list entry j against the pair's survivors (the G lanes of a group split them)
       auto test = [&](int j, bool live) {
         bool hit = false;
         if (live) {
@@ -409,20 +436,20 @@ __device__ inline int greedy_sweep(const NmsSmem& s, int n, float thr_f, int lim
           }
         }
       } else {
-      for (int e0 = 0; e0 < nal; e0 += per_pass) {
-        const int e = e0 + grp;
-        const int j = e < nal ? (int)s.alist_top[-e] : -1;
-        const bool live = j >= lim;
-        const bool dead = test(j, live);
-        if (live && dead && sub == 0) atomicOr(&s.suppressed[j >> 5], 1u << (j & 31));
-        const bool surv = live && !dead && sub == 0;
-        const unsigned sm = __ballot_sync(0xffffffffu, surv);
-        int wbase = 0;
-        if (lane == 0 && sm) wbase = atomicAdd(&s.scalars[4], __popc(sm));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        __syncthreads();  // every entry of this pass has been read; the writes stay below the next pass's entries
-        if (surv) s.alist_top[-(wbase + __popc(sm & ((1u << lane) - 1u)))] = (uint16_t)j;
-      }
+        for (int e0 = 0; e0 < nal; e0 += per_pass) {
+          const int e = e0 + grp;
+          const int j = e < nal ? (int)s.alist_top[-e] : -1;
+          const bool live = j >= lim;
+          const bool dead = test(j, live);
+          if (live && dead && sub == 0) atomicOr(&s.suppressed[j >> 5], 1u << (j & 31));
+          const bool surv = live && !dead && sub == 0;
+          const unsigned sm = __ballot_sync(0xffffffffu, surv);
+          int wbase = 0;
+          if (lane == 0 && sm) wbase = atomicAdd(&s.scalars[4], __popc(sm));
+          wbase = __shfl_sync(0xffffffffu, wbase, 0);
+          __syncthreads();  // every entry of this pass has been read; the writes stay below the next pass's entries
+          if (surv) s.alist_top[-(wbase + __popc(sm & ((1u << lane) - 1u)))] = (uint16_t)j;
+        }
       }
     }
     PROF_ADD(15, t3);
@@ -431,14 +458,14 @@ __device__ inline int greedy_sweep(const NmsSmem& s, int n, float thr_f, int lim
     PROF_T(t4);
     if (tid == 0 && nk > 0) s.scalars[3] = s.scalars[4];
     if (S > 1) {
-      // hand the next chunk's two suppression words to every CTA (parity-alternating slots: the peers may still be
-      // reading this chunk's slot)
-      const int first_word = (base + kChunk) >> 5;
-      if (tid < 2 * S) {
+      // hand the next pair's four suppression words to every CTA (parity-alternating slots: the peers may still be
+      // reading this pair's slots)
+      const int first_word = (base + 2 * kChunk) >> 5;
+      if (tid < 4 * S) {
         const int wsel = tid / S, dst = tid - wsel * S;
         const int w = first_word + wsel;
-        if (w % S == rank)   // (zero beyond the list: the array has two spare words)
-          st_cluster_u32(tc::map_to_cta(tc::smem_u32(&s.chunk_sup[(par ^ 1) * 2 + wsel]), (uint32_t)dst), s.suppressed[w]);
+        if (w % S == rank)   // (zero beyond the list: the array has spare words)
+          st_cluster_u32(tc::map_to_cta(tc::smem_u32(&s.chunk_sup[(par ^ 1) * 6 + wsel]), (uint32_t)dst), s.suppressed[w]);
       }
       tc::cluster_sync();
     }
@@ -763,8 +790,9 @@ static int set_smem(K kernel, size_t bytes, const char* name) {
 static int pick_cluster(long problems) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int S = 1;
-  while (S * 2 <= kMaxCluster && problems * (S * 2) <= sms) S *= 2;
+  int S = 1, smax = kMaxCluster;
+  if (const char* e = getenv("FOD_NMS_MAX_CLUSTER")) smax = atoi(e) > 0 ? atoi(e) : smax;   // development knob
+  while (S * 2 <= smax && problems * (S * 2) <= sms) S *= 2;
   return S;
 }
 

@@ -59,6 +59,31 @@ def test_batched_nms_all_equal_scores_and_identical_boxes():
     assert np.array_equal(got.cpu().numpy(), ref.numpy())
 
 
+@pytest.mark.parametrize("max_cluster", [1, 2, 4])
+def test_nms_every_cluster_size(max_cluster, monkeypatch):
+    """One, two and four CTAs per problem run the same sweep on differently split data (own suppression words, exchanged
+    chunk pairs, shared survivor / alive-list array): each must reproduce the oracle on a full sweep without early stop
+    (3000 candidates, almost nothing suppressed at first) and on the duplicated-box list."""
+    monkeypatch.setenv("FOD_NMS_MAX_CLUSTER", str(max_cluster))
+    n = 500
+    boxes = _boxes(n, 77)
+    boxes[250:] = boxes[:250]
+    scores = torch.full((n,), 0.5)
+    ref = O.batched_nms_coordinate_trick(boxes, scores, torch.zeros(n, dtype=torch.long), 0.6)
+    got = ops.batched_nms(boxes.to(DEV), scores.to(DEV), None, 0.6)
+    assert np.array_equal(got.cpu().numpy(), ref.numpy())
+    cap = 3000
+    pb = _boxes(cap, 300, 30.0, 600.0, 20.0, 60.0).unsqueeze(0)
+    ps = synth.tensor((cap,), 301, 0.01, 1.0).unsqueeze(0)
+    status = ops.new_status(DEV)
+    keep, ob, os_, oc = ops.nms_proposals(pb.to(DEV), ps.to(DEV), torch.tensor([cap], dtype=torch.int32, device=DEV), 0.6, -1, cap,
+                                          status)
+    ops.check_status(status)
+    ref = O.proposal_nms_topk(pb[0], ps[0], O.HeadConfig(post_nms_topk=10 ** 9))
+    m = int(oc[0])
+    assert m == ref.numel() and np.array_equal(keep[0, :m].cpu().numpy(), ref.numpy())
+
+
 @pytest.mark.parametrize("post_topk,ties", [(256, False), (256, True), (2000, False), (-1, False)])
 def test_nms_proposals_bit_exact(post_topk, ties):
     P, cap = 5, 3000
