@@ -296,7 +296,7 @@ def run_gpu_arm(args):
     sizes = [(IMG, IMG)] * B
     timer = KernelTimer()
     timer.wrap(ops, ["correlate_levels", "decode_topk", "decode_topk_taps", "group_norm_affine", "nms_proposals", "roi_align", "relation_head", "final_detect",
-                     "conv2d_nhwc", "group_norm_nhwc", "stem_patches", "stem_patches_u8", "stem1_u8", "maxpool3x3s2_nhwc", "ese_gate"])
+                     "conv2d_nhwc", "group_norm_nhwc", "stem_patches", "stem_patches_u8", "stem1_u8", "stem1_u8_tc", "maxpool3x3s2_nhwc", "ese_gate"])
 
     def step_resident(i):      # raw uint8 images resident in HBM -> padded detections on the device
         return model.detect_from_uint8(dev_sets[i % NSETS], sizes, sizes)

@@ -257,15 +257,21 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
             self._stem1_folded_cache = hit
         return hit[1], hit[2]
 
+    STEM1_TENSOR_CORES = True     # stem_1 of uint8 input: csrc/stem1_tc.cu (False: the FP32 FMA kernel, ops.stem1_u8)
+
     def tc_stem_u8(self, x_u8, mean, std, out, out_amax):
-        """Raw uint8 images -> stem_1 on the CUDA cores (normalisation fused, ops.stem1_u8) -> stem_2 -> stem_3 into
-        ``out``; same contract as tc_stem."""
+        """Raw uint8 images -> stem_1 (normalisation fused; tensor-core kernel ops.stem1_u8_tc, the im2col gathered into
+        tensor memory) -> stem_2 -> stem_3 into ``out``; same contract as tc_stem."""
         if self.stem[0].out_channels != 64 or tuple(self.stem[0].weight.shape[1:]) != (3, 3, 3):
             return self.tc_stem(ops.stem_patches_u8(x_u8, mean, std), None, out, out_amax)
-        w, b = self._stem1_folded()
         n = x_u8.shape[0]
         a1, a2 = ops.new_amax(x_u8.device, n), ops.new_amax(x_u8.device, n)          # per image
-        y = ops.stem1_u8(x_u8, mean, std, w, b, y_amax=a1)
+        if self.STEM1_TENSOR_CORES:
+            pk, b = self._stem1_packed()
+            y = ops.stem1_u8_tc(x_u8, mean, std, pk, b, y_amax=a1)
+        else:
+            w, b = self._stem1_folded()
+            y = ops.stem1_u8(x_u8, mean, std, w, b, y_amax=a1)
         y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1.view(1, n), y_amax=a2)
         tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2.view(1, n), y_amax=out_amax)
 

@@ -638,6 +638,32 @@ def stem1_u8(x: Tensor, mean: Sequence[float], std: Sequence[float], weight: Ten
     return out
 
 
+def stem1_u8_tc(x: Tensor, mean: Sequence[float], std: Sequence[float], packed: Tensor, bias: Optional[Tensor],
+                y_amax: Optional[Tensor] = None) -> Tensor:
+    """stem1_u8 on the tensor cores (fod_stem1_u8_tc): ``packed`` = conv2d_pack of the [64,32,1,1] im2col matrix with
+    columns (ky*3 + kx)*3 + c (27..31 zero)."""
+    _chk(x, torch.uint8, "x")
+    if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+        raise _lib.FodError("stem1_u8_tc: contiguous [N,3,H,W] uint8 expected")
+    _chk(packed, torch.float32, "packed")
+    if packed.numel() != 64 * 32 + 4:
+        raise _lib.FodError("stem1_u8_tc: packed weights of a [64,32,1,1] matrix expected")
+    if bias is not None:
+        bias = _chk(bias, torch.float32, "bias").contiguous()
+        if bias.numel() != 64:
+            raise _lib.FodError("stem1_u8_tc: 64 bias values expected")
+    n, _, h, w = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty((n, ho, wo, 64), dtype=torch.float32, device=x.device).permute(0, 3, 1, 2)
+    m3, s3 = (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std])
+    if y_amax is not None and y_amax.numel() not in (1, n):
+        raise _lib.FodError("stem1_u8_tc: y_amax must hold 1 or N floats")
+    per_image = y_amax is not None and y_amax.numel() == n and n > 1
+    _lib.check(_lib.lib().fod_stem1_u8_tc(_ptr(x), n, h, w, m3, s3, _ptr(packed), _ptr(bias), _ptr(out), 64, _ptr(y_amax),
+                                          int(per_image), _stream()), "fod_stem1_u8_tc")
+    return out
+
+
 def maxpool3x3s2_nhwc(x: Tensor, gate: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
     """nn.MaxPool2d(3, 2, ceil_mode=True) of an NHWC view, times an optional per-(image, channel) gate [N,C];
     ``out`` may be a channel slice of a wider NHWC buffer."""

@@ -349,6 +349,15 @@ int fod_stem_patches_u8(const uint8_t* x, int n, int h, int w, const float* mean
  * fsod_cen.py:540-555) */
 int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, const float* weight,
                  const float* bias, float* y, float* y_amax, int amax_per_image, fod_stream_t stream);
+/* the same layer on the tensor cores (csrc/stem1_tc.cu): a GEMM with ONE 32-wide K chunk per 128-pixel tile whose A
+ * operand - the 27 im2col columns k = (ky*3 + kx)*3 + c of an output pixel, normalised, zero outside the image - is gathered
+ * from the uint8 planes straight into tensor memory, so the layer is bound by its 256-byte-per-pixel output write
+ * instead of by FP32 FMAs.  Same arithmetic as fod_conv2d_nhwc (fp16 hi / lo split, fp32 accumulation); the operand scale
+ * is fixed by mean3 / std3, so an image's result does not depend on the batch.
+ *   packed : fod_conv2d_pack_weights of the [64][32][1][1] matrix (columns in the order above, 27..31 zero; BN folded)
+ *   y      : [N][ceil(H/2)][ceil(W/2)][y_pixel_stride >= 64] NHWC; y_amax as in fod_stem1_u8 */
+int fod_stem1_u8_tc(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, const float* packed,
+                    const float* bias, float* y, long y_pixel_stride, float* y_amax, int amax_per_image, fod_stream_t stream);
 int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate, float* y,
                           long y_pixel_stride, fod_stream_t stream);
 

@@ -154,6 +154,34 @@ def test_stem1_u8_matches_normalise_then_conv():
     assert abs(float(bound) - float(ref.max())) <= 1e-5 * float(ref.max())
 
 
+@pytest.mark.parametrize("std", [[1.0, 1.0, 1.0], [1.0, 57.4, 58.4]])
+@pytest.mark.parametrize("hw", [(38, 52), (37, 51), (640, 640)])
+def test_stem1_u8_tensor_cores_match_normalise_then_conv(std, hw):
+    """The same layer through the tensor-core stem kernel (uint8 gather into tensor memory), odd sizes included (the last
+    output row / column reads one pixel of padding), more tiles than SMs at 640x640, per-image output bounds."""
+    h, w_ = hw
+    n = 2 if h < 100 else 3
+    x = (synth.tensor((n, 3, h, w_), 81, 0.0, 255.99)).to(torch.uint8)
+    mean = [103.53, 116.28, 123.675]
+    w = synth.tensor((64, 3, 3, 3), 82, -0.3, 0.3)
+    b = synth.tensor((64,), 83, -1.0, 1.0)
+    xn = (x.double() - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    ref = F.conv2d(xn, w.double(), b.double(), stride=2, padding=1).relu().float()
+    w32 = torch.cat((w.permute(0, 2, 3, 1).reshape(64, 27), torch.zeros(64, 5)), 1).reshape(64, 32, 1, 1).contiguous()
+    pk = ops.conv2d_pack(w32.to(DEV))
+    bound = ops.new_amax(DEV, n)
+    y = ops.stem1_u8_tc(x.to(DEV), mean, std, pk, b.to(DEV), y_amax=bound)
+    assert tuple(y.shape) == (n, 64, (h - 1) // 2 + 1, (w_ - 1) // 2 + 1) and y.stride(1) == 1
+    _check(y, ref, "stem_1 (tensor cores)")
+    for i in range(n):
+        assert abs(float(bound.view(-1)[i]) - float(ref[i].max())) <= 1e-5 * float(ref[i].max())
+    # and against the FP32 FMA kernel of the same layer
+    y2 = ops.stem1_u8(x.to(DEV), mean, std, w.to(DEV), b.to(DEV))
+    assert float((y - y2).abs().max()) <= 2e-6 * float(y2.abs().max())
+    # a second launch on the same data gives the same bits (no state survives a launch)
+    assert torch.equal(y, ops.stem1_u8_tc(x.to(DEV), mean, std, pk, b.to(DEV)))
+
+
 @pytest.mark.parametrize("up2", [False, True])
 def test_conv2d_nhwc_residual_in_epilogue(up2):
     """FPN top-down step: lateral 1x1 + (nearest 2x upsampled) coarser map, fused into the convolution's epilogue."""

@@ -186,3 +186,23 @@ def test_conv_and_group_norm_stay_inside_their_buffers(monkeypatch, shape):
         return out
 
     run_guarded(monkeypatch, fn, lambda o: o)
+
+
+@pytest.mark.parametrize("hw", [(37, 51), (320, 416)])
+def test_stem_kernels_stay_inside_their_buffers(monkeypatch, hw):
+    """stem_1 from uint8 images, FMA and tensor-core kernel: odd sizes (the last tile row / column is clipped by the TMA
+    store) and more tiles than SMs; the two runs of each pattern double as a run-to-run check of the tensor-core hand-offs."""
+    h, w_ = hw
+    n = 3
+    x = synth.tensor((n, 3, h, w_), 810, 0.0, 255.99).to(torch.uint8).to(DEV)
+    mean, std = [103.53, 116.28, 123.675], [1.0, 1.0, 1.0]
+    w = synth.tensor((64, 3, 3, 3), 811, -0.3, 0.3).to(DEV)
+    b = synth.tensor((64,), 812, -1.0, 1.0).to(DEV)
+    w32 = torch.cat((w.permute(0, 2, 3, 1).reshape(64, 27), torch.zeros(64, 5, device=DEV)), 1).reshape(64, 32, 1, 1).contiguous()
+
+    def fn():
+        pk = ops.conv2d_pack(w32)
+        a1, a2 = ops.new_amax(DEV, n), ops.new_amax(DEV, n)
+        return [ops.stem1_u8_tc(x, mean, std, pk, b, y_amax=a1), a1, ops.stem1_u8(x, mean, std, w, b, y_amax=a2), a2]
+
+    run_guarded(monkeypatch, fn, lambda o: o)

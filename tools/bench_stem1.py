@@ -54,3 +54,43 @@ for name, fn in (("stem1", lambda: ops.stem1_u8(x, mean, std, w, b)), ("conv", l
     out = p.stdout.read().strip().splitlines()
     print(f"{name}: {dt / n * 1e3:.3f} ms per launch over {dt:.1f} s; nvidia-smi samples (sm MHz, W, power cap, hw slowdown, sw thermal, temp):")
     print("   " + " | ".join(out[2:10]))
+
+# the same layer through the tensor-core stem kernel (csrc/stem1_tc.cu)
+w32 = torch.cat((w.permute(0, 2, 3, 1).reshape(64, 27), torch.zeros(64, 5, device="cuda")), 1).reshape(64, 32, 1, 1).contiguous()
+pk1 = ops.conv2d_pack(w32)
+print("stem1 on tensor cores, back to back: %.3f ms" % t(lambda: ops.stem1_u8_tc(x, mean, std, pk1, b)))
+ya, yb = ops.stem1_u8(x, mean, std, w, b), ops.stem1_u8_tc(x, mean, std, pk1, b)
+print("max |fma - tc| = %.3e of %.3e" % (float((ya - yb).abs().max()), float(ya.abs().max())))
+xs4 = [(torch.rand(64, 3, 640, 640, device="cuda") * 255).to(torch.uint8) for _ in range(4)]
+am = ops.new_amax("cuda", 64)
+k = [0]
+def rot():
+    k[0] += 1
+    ops.stem1_u8_tc(xs4[k[0] % 4], mean, std, pk1, b, y_amax=am)
+print("stem1 on tensor cores, rotating inputs + per-image bounds: %.3f ms" % t(rot))
+def rot_fma():
+    k[0] += 1
+    ops.stem1_u8(xs4[k[0] % 4], mean, std, w, b, y_amax=am)
+print("stem1 FMA kernel, rotating inputs + per-image bounds: %.3f ms" % t(rot_fma))
+
+
+def mixed_tc():
+    for _ in range(8):
+        ops.conv2d_nhwc(xc, pk, None, 64, 3, True, x_amax=ax)
+    rot()
+
+
+tc8 = t(lambda: [ops.conv2d_nhwc(xc, pk, None, 64, 3, True, x_amax=ax) for _ in range(8)])
+tm = t(mixed_tc)
+print("8 convs + tensor-core stem1: %.3f ms -> stem1 share if convs unchanged (%.3f): %.3f ms" % (tm, tc8, tm - tc8))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+tot = 0.0
+for _ in range(10):
+    for _ in range(8):
+        ops.conv2d_nhwc(xc, pk, None, 64, 3, True, x_amax=ax)
+    e0.record()
+    rot()
+    e1.record()
+    torch.cuda.synchronize()
+    tot += e0.elapsed_time(e1)
+print("tensor-core stem1 right after 8 convs, by its own events: %.3f ms" % (tot / 10))

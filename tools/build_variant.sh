@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/../faster_orefsdet_b200/csrc"
 mkdir -p ../../build/$1
-for f in api tmap nms decode correlate correlate_tc roi relation_tc conv_tc gn glue; do
+for f in api tmap nms decode correlate correlate_tc roi relation_tc conv_tc stem1_tc gn glue; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --fmad=true $2 -c $f.cu -o ../../build/$1/$f.o &
 done
 wait
