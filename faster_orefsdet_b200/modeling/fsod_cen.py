@@ -298,7 +298,7 @@ class CenterNet2Detector(nn.Module):
         return [{"instances": r} for r in results] if do_postprocess else results
 
     # ------------------------------------------------------------------ input staging
-    PIPELINE_CHUNK = 16      # images per host-to-device chunk
+    PIPELINE_CHUNK = 16      # images per host-to-device chunk (measured against 32: +4 % on the synchronous path, -1 % pipelined)
     U8_RING = 3              # device input buffers per batch shape (batches in flight + 1)
 
     def features_from_uint8(self, x_u8: torch.Tensor, events=None, chunk: int = 0) -> Dict[str, torch.Tensor]:
