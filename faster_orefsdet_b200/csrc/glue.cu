@@ -347,32 +347,44 @@ __global__ void __launch_bounds__(kThreads, 2) stem1_u8_tile_kernel(const uint8_
   }
 }
 
-// x: [N][H][W] pixels of xs floats (first C used), gate: [N][C] or null -> y: [N][Ho][Wo] pixels of ys floats
+// x: [N][H][W] pixels of xs floats (first C used), gate: [N][C] or null -> y: [N][Ho][Wo] pixels of ys floats.
+// Grid (x: blocks over one output row's (pixel, 4-channel group) items, y: output row, z: image): the only division left
+// per thread is one 32-bit one (a flat 64-bit index cost three 64-bit div / mod pairs per output, more instructions than
+// the nine loads and the maxima).  Consecutive threads take consecutive channel groups of one pixel: 16-byte loads,
+// fully coalesced; the 3x3 windows of neighbouring outputs overlap by one column / row, which the L1 serves.
 __global__ void __launch_bounds__(kThreads) maxpool_kernel(const float* __restrict__ x, long xs, int H, int W, int C,
                                                            const float* __restrict__ gate, float* __restrict__ y, long ys,
-                                                           int Ho, int Wo, size_t total) {
+                                                           int Ho, int Wo) {
   const int c4n = C >> 2;
-  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (size_t)gridDim.x * kThreads) {
-    const int c4 = (int)(i % c4n);
-    const size_t pix = i / c4n;
-    const int ox = (int)(pix % Wo);
-    const size_t r = pix / Wo;
-    const int oy = (int)(r % Ho);
-    const size_t n = r / Ho;
-    const int y0 = 2 * oy, x0 = 2 * ox;
-    const int y1 = min(y0 + 3, H), x1 = min(x0 + 3, W);
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    for (int iy = y0; iy < y1; ++iy)
-      for (int ix = x0; ix < x1; ++ix) {
-        const float4 v = ldg4(x + ((n * H + iy) * (size_t)W + ix) * xs + c4 * 4);
+  const int item = (int)(blockIdx.x * kThreads + threadIdx.x);
+  if (item >= Wo * c4n) return;
+  const int ox = item / c4n, c4 = item - ox * c4n;
+  const int oy = (int)blockIdx.y;
+  const size_t n = blockIdx.z;
+  const int y0 = 2 * oy, x0 = 2 * ox;
+  const int y1 = min(y0 + 3, H), x1 = min(x0 + 3, W);
+  const float* px = x + ((n * H + y0) * (size_t)W + x0) * xs + c4 * 4;
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  if (y1 - y0 == 3 && x1 - x0 == 3) {   // the full window: nine independent loads
+    float4 v[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v[k] = ldg4(px + ((size_t)(k / 3) * W + (k % 3)) * xs);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      m.x = fmaxf(m.x, v[k].x); m.y = fmaxf(m.y, v[k].y); m.z = fmaxf(m.z, v[k].z); m.w = fmaxf(m.w, v[k].w);
+    }
+  } else {
+    for (int iy = 0; iy < y1 - y0; ++iy)
+      for (int ix = 0; ix < x1 - x0; ++ix) {
+        const float4 v = ldg4(px + ((size_t)iy * W + ix) * xs);
         m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
       }
-    if (gate) {
-      const float4 g = ldg4(gate + n * C + c4 * 4);
-      m.x *= g.x; m.y *= g.y; m.z *= g.z; m.w *= g.w;
-    }
-    *reinterpret_cast<float4*>(y + pix * ys + c4 * 4) = m;
   }
+  if (gate) {
+    const float4 g = ldg4(gate + n * C + c4 * 4);
+    m.x *= g.x; m.y *= g.y; m.z *= g.z; m.w *= g.w;
+  }
+  *reinterpret_cast<float4*>(y + ((n * Ho + oy) * (size_t)Wo + ox) * ys + c4 * 4) = m;
 }
 
 }  // namespace glue
@@ -443,9 +455,9 @@ extern "C" int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c,
   if (n == 0) return FOD_OK;
   // ceil_mode output size of nn.MaxPool2d(3, 2): ceil((H - 3) / 2) + 1 (the last window always starts inside the map)
   const int ho = (h - 3 + 1) / 2 + 1, wo = (w - 3 + 1) / 2 + 1;
-  const size_t total = (size_t)n * ho * wo * (c / 4);
-  glue::maxpool_kernel<<<grid_for(total, glue::kThreads), glue::kThreads, 0, as_stream(stream)>>>(
-      x, x_pixel_stride, h, w, c, gate, y, y_pixel_stride, ho, wo, total);
+  FOD_REQUIRE(ho <= 65535 && n <= 65535, "fod_maxpool3x3s2_nhwc: more than 65535 output rows or images");
+  const dim3 grid((unsigned)(((long)wo * (c / 4) + glue::kThreads - 1) / glue::kThreads), (unsigned)ho, (unsigned)n);
+  glue::maxpool_kernel<<<grid, glue::kThreads, 0, as_stream(stream)>>>(x, x_pixel_stride, h, w, c, gate, y, y_pixel_stride, ho, wo);
   FOD_CUDA_LAUNCH_CHECK("fod_maxpool3x3s2_nhwc");
   return FOD_OK;
 }
