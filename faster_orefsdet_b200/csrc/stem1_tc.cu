@@ -44,7 +44,8 @@ constexpr uint32_t kPlaneBytes = kCout * kK * 2;          // 4096: one fp16 weig
 constexpr uint32_t kOffB = 0;                             // hi plane, lo plane
 constexpr uint32_t kBoxBytes = 32 * 128;                   // 32 pixels x 32 channels fp32
 constexpr uint32_t kOffStage = 8192;                      // [epilogue warp][buffer] boxes
-constexpr uint32_t kOffBars = kOffStage + kEpiWarps * 2 * kBoxBytes;
+constexpr uint32_t kOffLut = kOffStage + kEpiWarps * 2 * kBoxBytes;   // [3][256] normalised, scaled pixel values
+constexpr uint32_t kOffBars = kOffLut + 3 * 256 * 4;
 constexpr uint32_t kNumBars = 3 * kSlots + 1;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr uint32_t kSmemBytes = kOffTmemPtr + 16;
@@ -136,6 +137,13 @@ __global__ void __launch_bounds__(kThreads, 1) stem1_tc_kernel(const __grid_cons
     tma_prefetch_desc(&P.whi_map);
     tma_prefetch_desc(&P.wlo_map);
   }
+  {   // ((v - mean) / std) * 2^e for every byte value and channel: the reference's two roundings, then an exact scaling
+    float* lut = reinterpret_cast<float*>(smem + kOffLut);
+    for (int i = tid; i < 3 * 256; i += kThreads) {
+      const int c = i >> 8;
+      lut[i] = __fdiv_rn(__fsub_rn((float)(i & 255), P.mean[c]), P.std[c]) * P.xs;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -180,6 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem1_tc_kernel(const __grid_cons
     const size_t plane = (size_t)H * W;
     const float xs = P.xs;
     const float nm0 = -P.mean[0] * xs, nm1 = -P.mean[1] * xs, nm2 = -P.mean[2] * xs;   // exact: xs is a power of two
+    const float* lut = reinterpret_cast<const float*>(smem + kOffLut);
     const int tiles_y = P.tiles_per_img / P.tiles_x;
     TileWalk tw;
     tw.init((int)blockIdx.x, step, P.tiles_x, tiles_y);
@@ -192,25 +201,19 @@ __global__ void __launch_bounds__(kThreads, 1) stem1_tc_kernel(const __grid_cons
       // a tile whose 17 x 33 input window lies inside the image needs neither clamps nor padding (uniform per warp)
       const bool interior = ty > 0 && tx > 0 && 2 * (ty * kTileH + kTileH - 1) + 1 < H && 2 * (tx * kTileW + kTileW - 1) + 1 < W;
       float v[kK];
-      if (interior && P.std_one) {
+      uint32_t raw[kKUsed];
+      bool rok[3] = {true, true, true}, cok[3] = {true, true, true};
+      if (interior) {
         const uint8_t* p0 = img + (size_t)(2 * oy - 1) * W + (2 * ox - 1);
-        uint32_t raw[kKUsed];
 #pragma unroll
         for (int k = 0; k < kKUsed; ++k) {   // k = (ky*3 + kx)*3 + c
           const int tap = k / 3, c = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
           raw[k] = __ldg(p0 + c * plane + ky * W + kx);
         }
-#pragma unroll
-        for (int k = 0; k < kKUsed; ++k) {
-          const int c = k % 3;
-          // (raw - mean) * xs in one rounding: raw * xs and mean * xs are exact, so this is the rounded difference scaled
-          v[k] = fmaf((float)raw[k], xs, c == 0 ? nm0 : (c == 1 ? nm1 : nm2));
-        }
       } else {
         // every load is issued unconditionally from a clamped address (27 independent loads in flight); the padding is
         // applied to the value
         int rowoff[3], col[3];
-        bool rok[3], cok[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int iy = 2 * oy - 1 + k, ix = 2 * ox - 1 + k;
@@ -219,18 +222,28 @@ __global__ void __launch_bounds__(kThreads, 1) stem1_tc_kernel(const __grid_cons
           rowoff[k] = min(max(iy, 0), H - 1) * W;
           col[k] = min(max(ix, 0), W - 1);
         }
-        uint32_t raw[kKUsed];
 #pragma unroll
         for (int k = 0; k < kKUsed; ++k) {
           const int tap = k / 3, c = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
           raw[k] = __ldg(img + c * plane + rowoff[ky] + col[kx]);
         }
+      }
+      if (P.std_one) {
 #pragma unroll
         for (int k = 0; k < kKUsed; ++k) {
-          const int tap = k / 3, c = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
-          const float d = __fsub_rn((float)raw[k], P.mean[c]);
-          const float nv = (P.std_one ? d : __fdiv_rn(d, P.std[c])) * xs;
-          v[k] = (rok[ky] && cok[kx]) ? nv : 0.f;
+          const int c = k % 3;
+          // (raw - mean) * xs in one rounding: raw * xs and mean * xs are exact, so this is the rounded difference scaled
+          v[k] = fmaf((float)raw[k], xs, c == 0 ? nm0 : (c == 1 ? nm1 : nm2));
+        }
+      } else {   // a division per value would dominate the converter: table look-up (same bits)
+#pragma unroll
+        for (int k = 0; k < kKUsed; ++k) v[k] = lut[(k % 3) * 256 + raw[k]];
+      }
+      if (!interior) {
+#pragma unroll
+        for (int k = 0; k < kKUsed; ++k) {
+          const int tap = k / 3, ky = tap / 3, kx = tap - ky * 3;
+          v[k] = (rok[ky] && cok[kx]) ? v[k] : 0.f;
         }
       }
 #pragma unroll

@@ -7,6 +7,7 @@ x = (torch.rand(64, 3, 640, 640, device="cuda") * 255).to(torch.uint8)
 w = torch.randn(64, 3, 3, 3, device="cuda") * 0.1
 b = torch.zeros(64, device="cuda")
 mean, std = [103.53, 116.28, 123.675], [1.0, 1.0, 1.0]
+std2 = [1.0, 57.4, 58.4]
 xc = torch.randn(64, 160, 160, 128, device="cuda").permute(0, 3, 1, 2)
 pk = ops.conv2d_pack(torch.randn(64, 128, 3, 3, device="cuda") * 0.05)
 ax = ops.absmax(xc)
@@ -94,3 +95,4 @@ for _ in range(10):
     torch.cuda.synchronize()
     tot += e0.elapsed_time(e1)
 print("tensor-core stem1 right after 8 convs, by its own events: %.3f ms" % (tot / 10))
+print("stem1 on tensor cores, non-unit pixel_std (table look-up path): %.3f ms" % t(lambda: ops.stem1_u8_tc(x, mean, std2, pk1, b)))
