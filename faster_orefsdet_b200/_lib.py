@@ -51,6 +51,8 @@ _PROTOTYPES = {
                       _i),
     "fod_roi_align_wide": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp,
                             _vp], _i),
+    "fod_roi_align_per_roi": ([ctypes.POINTER(_vp), ctypes.POINTER(fod_level_t), _i, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
+                               _vp, _vp], _i),
     "fod_relation_head": ([_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, ctypes.POINTER(_f), _vp, _vp, _vp, _vp,
                            _vp], _i),
     "fod_split_tf32": ([_vp, _vp, ctypes.c_size_t, _vp], _i),

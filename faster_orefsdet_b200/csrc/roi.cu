@@ -1,5 +1,6 @@
 // R1/P1: multi-level ROIAlign (NHWC).  R2+R3 (relation head) live in relation_tc.cu.
 #include "common.cuh"
+#include "tc05.cuh"
 
 namespace fod {
 
@@ -123,6 +124,35 @@ __device__ __forceinline__ BoxGeom box_geometry(const RoiParams& prm, const floa
   return g;
 }
 
+// The list of DISTINCT map rows (columns) the samples of one bin touch along one axis, with the summed interpolation
+// weight of each (at most grid + 1 <= kMaxTaps entries, ascending).
+__device__ __forceinline__ int build_axis_taps(const BoxGeom& g, bool is_x, int bin, int (&idx)[kMaxTaps], float (&w)[kMaxTaps]) {
+  int n = 0;
+  const int grid = is_x ? g.grid_w : g.grid_h, size = is_x ? g.W : g.H;
+  const float start = is_x ? g.start_w : g.start_h, bsz = is_x ? g.bin_w : g.bin_h;
+  for (int i = 0; i < grid; ++i) {
+    const AxisSample s = axis_sample(start, bsz, bin, i, grid, size);
+    if (s.w_lo == 0.f && s.w_hi == 0.f) continue;
+    if (n > 0 && idx[n - 1] == s.lo) {
+      w[n - 1] += s.w_lo;
+    } else if (n > 1 && idx[n - 2] == s.lo) {
+      w[n - 2] += s.w_lo;
+    } else {
+      idx[n] = s.lo;
+      w[n] = s.w_lo;
+      ++n;
+    }
+    if (idx[n - 1] == s.hi) {
+      w[n - 1] += s.w_hi;
+    } else {
+      idx[n] = s.hi;
+      w[n] = s.w_hi;
+      ++n;
+    }
+  }
+  return n;
+}
+
 // One thread per (ROI, axis, bin): grid.x covers roi_cap * 2R threads of a problem, grid.y = problem.
 template <int R>
 __global__ void __launch_bounds__(256) roi_tables_kernel(RoiParams prm, const float* __restrict__ rois,
@@ -149,32 +179,10 @@ __global__ void __launch_bounds__(256) roi_tables_kernel(RoiParams prm, const fl
   if (!tables) return;
   const bool is_x = k < R;
   const int bin = is_x ? k : k - R;
-  // the list of DISTINCT rows / columns the bin's samples touch with their summed weights (see build_axis_taps)
+  // the list of DISTINCT rows / columns the bin's samples touch with their summed weights
   int idx[kMaxTaps];
   float w[kMaxTaps];
-  int n = 0;
-  const int grid = is_x ? g.grid_w : g.grid_h, size = is_x ? g.W : g.H;
-  const float start = is_x ? g.start_w : g.start_h, bsz = is_x ? g.bin_w : g.bin_h;
-  for (int i = 0; i < grid; ++i) {
-    const AxisSample s = axis_sample(start, bsz, bin, i, grid, size);
-    if (s.w_lo == 0.f && s.w_hi == 0.f) continue;
-    if (n > 0 && idx[n - 1] == s.lo) {
-      w[n - 1] += s.w_lo;
-    } else if (n > 1 && idx[n - 2] == s.lo) {
-      w[n - 2] += s.w_lo;
-    } else {
-      idx[n] = s.lo;
-      w[n] = s.w_lo;
-      ++n;
-    }
-    if (idx[n - 1] == s.hi) {
-      w[n - 1] += s.w_hi;
-    } else {
-      idx[n] = s.hi;
-      w[n] = s.w_hi;
-      ++n;
-    }
-  }
+  const int n = build_axis_taps(g, is_x, bin, idx, w);
   const int pitch = is_x ? prm.pix : g.W * prm.pix;
   int* po = is_x ? B.xoff[bin] : B.yoff[bin];
   float* pw = is_x ? B.xw[bin] : B.yw[bin];
@@ -223,16 +231,11 @@ __device__ __forceinline__ void roi_accumulate(const RoiBlob<R>& B, const float*
 // one fully coalesced 512-byte row of the NHWC map, 4 accumulators per lane keep the register count low enough for
 // full occupancy.  The ROI's geometry and tap lists come from roi_tables_kernel.
 template <int R>
-__global__ void __launch_bounds__(R * 64, R > 8 ? 1 : 2)
-roi_align_kernel(RoiParams prm, const int32_t* __restrict__ roi_count, const RoiBlob<R>* __restrict__ blobs,
-                 float* __restrict__ pooled) {
-  __shared__ RoiBlob<R> B;
-  const int r = blockIdx.x, p = blockIdx.y;
+__device__ __forceinline__ void pool_one_roi(const RoiParams& prm, const RoiBlob<R>* __restrict__ blobs,
+                                             float* __restrict__ pooled, const int p, const int r, RoiBlob<R>& B) {
 #ifdef FOD_ROI_PROF
   const long long t_start = clock64();
 #endif
-  const int cnt = roi_count ? min(roi_count[p], prm.roi_cap) : prm.roi_cap;
-  if (r >= cnt) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {
     const int4* src = reinterpret_cast<const int4*>(blobs + ((size_t)p * prm.roi_cap + r));
@@ -308,6 +311,355 @@ roi_align_kernel(RoiParams prm, const int32_t* __restrict__ roi_count, const Roi
   RPROF(3);
 }
 
+
+template <int R>
+__global__ void __launch_bounds__(R * 64, R > 8 ? 1 : 2)
+roi_align_kernel(RoiParams prm, const int32_t* __restrict__ roi_count, const RoiBlob<R>* __restrict__ blobs,
+                 float* __restrict__ pooled) {
+  __shared__ RoiBlob<R> B;
+  const int r = blockIdx.x, p = blockIdx.y;
+  const int cnt = roi_count ? min(roi_count[p], prm.roi_cap) : prm.roi_cap;
+  if (r >= cnt) return;
+  pool_one_roi<R>(prm, blobs, pooled, p, r, B);
+}
+
+// The same pooling for a LIST of ROIs (list[0] = number of entries, list[1 + i] = p * roi_cap + r): the ROIs whose
+// sampling grid is beyond the tap tables, which the tile-stationary kernel below leaves out.  Usually the list is empty.
+__global__ void __launch_bounds__(512, 2)
+roi_align_list_kernel(RoiParams prm, const int32_t* __restrict__ list, const RoiBlob<8>* __restrict__ blobs,
+                      float* __restrict__ pooled) {
+  __shared__ RoiBlob<8> B;
+  const int n = list[0];
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const int e = list[1 + i];
+    pool_one_roi<8>(prm, blobs, pooled, e / prm.roi_cap, e % prm.roi_cap, B);
+    __syncthreads();   // B is rewritten by the next entry
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile-stationary pooling (R = 8, 128 channels: the query path R1).
+//
+// The per-ROI kernel above gathers a ROI's ~17 x 17-pixel window out of L2 once per ROI; the windows of one image
+// overlap ~9 times, and it is the L2 -> SM path (9.5 TB/s) plus the L1 data pipe that bound it, not HBM.  Here the MAP
+// is stationary: a CTA owns an 8 x 8-pixel tile of one pyramid level of one image, TMA-stages the tile plus a 4-pixel
+// halo to the right / below into shared memory ONCE (12 x 12 pixels x 512 B = 72 KB, three CTAs per SM) and pools
+// every bin whose first tap lies inside its 8 x 8 pixels, whatever ROI (and class) the bin belongs to.  A bin reaches
+// at most ceil(bin size) + 1 rows / columns, so everything up to 4-pixel bins - the whole range FPN level assignment
+// produces - is served from shared memory; a longer bin (elongated boxes) reads the map directly, same arithmetic.
+// Work is found by a scan: one thread per ROI compares the ROI's 8 + 8 first taps (RoiSum, written by the table
+// pre-pass) with the tile; candidates go to a shared list and warp w takes bin row (w + i) & 7 of candidate i.
+// Inside a (ROI, bin row) task the tap lists live in registers, lane-distributed (lane = (bin & 3) * 8 + tap) and
+// broadcast with SHFL; a lane owns 4 channels, a tap is one conflict-free LDS.128 per lane.  The summation order of a
+// bin is the per-ROI kernel's (rows outer, columns inner, one FMA per tap and channel): results are bit-identical.
+// ------------------------------------------------------------------------------------------------
+struct alignas(16) RoiTile {       // tap lists of one ROI, indices instead of offsets, padded with the LAST valid index
+  int xi[8][kMaxTaps];             // (weight 0), so that entry [..][7] is the bin's largest column / row
+  float xw[8][kMaxTaps];
+  int yi[8][kMaxTaps];
+  float yw[8][kMaxTaps];
+};
+struct alignas(16) RoiSum {        // what the scan and a task's prologue need (48 bytes)
+  short x0[8], y0[8];              // first column / row of every bin (0 for a bin without samples inside the map)
+  short level, nx, tables, pad;    // nx = largest number of distinct columns over the ROI's bins
+  uint32_t yn;                     // number of distinct rows of bin row i in bits 4i .. 4i+3
+  float inv_count;
+};
+
+namespace rt {
+constexpr int kOwn = 8;                       // a CTA owns kOwn x kOwn pixels ...
+constexpr int kEdge = 12;                     // ... and stages kEdge x kEdge
+constexpr int kThreads = 256;
+constexpr int kScan = 128;                    // ROIs per scan pass (one per thread of the first four warps)
+constexpr uint32_t kTileBytes = kEdge * kEdge * kC * 4;
+constexpr uint32_t kOffCand = kTileBytes;                    // uint32[kScan]: ROI | column mask of the bins that start here
+constexpr uint32_t kOffTask = kOffCand + kScan * 4;          // uint16[kScan * 8]: candidate | bin row << 8
+constexpr uint32_t kOffBar = kOffTask + kScan * 8 * 2;       // mbarrier
+constexpr uint32_t kOffCount = kOffBar + 8;                  // counters: candidates, tasks, next task
+constexpr uint32_t kSmemBytes = kOffCount + 16;
+constexpr uint32_t kSmemAlloc = kSmemBytes + 128;            // slack for the 128-byte alignment of the TMA destination
+struct Params {
+  CUtensorMap map[FOD_MAX_LEVELS];
+  const float* feat[FOD_MAX_LEVELS];
+  int H[FOD_MAX_LEVELS], W[FOD_MAX_LEVELS], tiles_x[FOD_MAX_LEVELS], tile_end[FOD_MAX_LEVELS];
+  int num_levels, C, roi_cap, tiled;
+};
+}  // namespace rt
+
+// One thread per (ROI, axis, bin), 16 threads per ROI.  Tabled ROIs get a RoiTile; a ROI whose sampling grid is beyond
+// the tables gets the per-ROI kernel's blob header and an entry in the slow list.  Every ROI gets a RoiSum.
+__global__ void __launch_bounds__(256) roi_tile_tables_kernel(RoiParams prm, const float* __restrict__ rois,
+                                                              const int32_t* __restrict__ roi_count,
+                                                              RoiTile* __restrict__ tiles, RoiSum* __restrict__ sums,
+                                                              RoiBlob<8>* __restrict__ blobs, int32_t* __restrict__ slow_list,
+                                                              int32_t* __restrict__ out_level) {
+  constexpr int R = 8;
+  const int p = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = t >> 4, k = t & 15;                  // k < 8: x bin k, else y bin k - 8
+  const int cnt = roi_count ? min(roi_count[p], prm.roi_cap) : prm.roi_cap;
+  const bool valid = r < cnt;                        // no early exit: the shuffles below are warp-wide
+  const size_t row = (size_t)p * prm.roi_cap + (valid ? r : 0);
+  const float4 box = *reinterpret_cast<const float4*>(rois + row * 4);
+  const BoxGeom g = box_geometry<R>(prm, box);
+  const bool tables = g.grid_h <= kMaxGrid && g.grid_w <= kMaxGrid;
+  const bool is_x = k < R;
+  const int bin = k & 7;
+  int idx[kMaxTaps];
+  float w[kMaxTaps];
+  int n = 0;
+  if (valid && tables) n = build_axis_taps(g, is_x, bin, idx, w);
+  int nx = is_x ? n : 0;
+  uint32_t yn = is_x ? 0u : ((uint32_t)n << (4 * bin));
+#pragma unroll
+  for (int d = 8; d >= 1; d >>= 1) {
+    nx = max(nx, __shfl_xor_sync(0xffffffffu, nx, d));
+    yn |= __shfl_xor_sync(0xffffffffu, yn, d);
+  }
+  if (!valid) return;
+  RoiSum& S = sums[row];
+  if (k == 0) {
+    if (out_level) out_level[row] = g.lvl;
+    S.level = (short)g.lvl;
+    S.nx = (short)nx;
+    S.tables = tables ? 1 : 0;
+    S.pad = 0;
+    S.yn = yn;
+    S.inv_count = 1.0f / fmaxf((float)(g.grid_h * g.grid_w), 1.0f);
+    if (!tables) {
+      RoiBlob<R>& B = blobs[row];
+      B.gbox[0] = g.start_w; B.gbox[1] = g.start_h; B.gbox[2] = g.bin_w; B.gbox[3] = g.bin_h;
+      B.grid_w = g.grid_w; B.grid_h = g.grid_h; B.W = g.W; B.H = g.H;
+      B.level = g.lvl;
+      B.tables = 0;
+      B.inv_count = 1.0f / fmaxf((float)(g.grid_h * g.grid_w), 1.0f);
+      B.pad = 0;
+      slow_list[1 + atomicAdd(slow_list, 1)] = (int32_t)row;
+    }
+  }
+  (is_x ? S.x0 : S.y0)[bin] = (short)(n ? idx[0] : 0);
+  if (!tables) return;
+  RoiTile& T = tiles[row];
+  int* pi = is_x ? T.xi[bin] : T.yi[bin];
+  float* pw = is_x ? T.xw[bin] : T.yw[bin];
+  const int last = n ? idx[n - 1] : 0;
+#pragma unroll
+  for (int q = 0; q < kMaxTaps; ++q) {
+    pi[q] = q < n ? idx[q] : last;
+    pw[q] = q < n ? w[q] : 0.f;
+  }
+}
+
+// One bin out of the staged tile with compile-time tap counts: NX column taps (fetched from the lanes that hold the
+// ROI's lists) x NY rows (addresses and weights prepared once per task); the NY * NX loads are independent.
+template <int NY, int NX>
+__device__ __forceinline__ float4 tile_bin_fixed(const uint32_t (&rowa)[4], const float (&wy)[4], const int xb, const float xw,
+                                                 const int src) {
+  uint32_t off[NX];
+  float w[NX];
+#pragma unroll
+  for (int k = 0; k < NX; ++k) {
+    off[k] = (uint32_t)__shfl_sync(0xffffffffu, xb, src + k);
+    w[k] = __shfl_sync(0xffffffffu, xw, src + k);
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int kr = 0; kr < NY; ++kr) {
+    float4 v[NX];
+#pragma unroll
+    for (int k = 0; k < NX; ++k) v[k] = tc::lds4s(rowa[kr] + off[k]);
+#pragma unroll
+    for (int k = 0; k < NX; ++k) {
+      const float ww = wy[kr] * w[k];
+      acc.x = fmaf(ww, v[k].x, acc.x);
+      acc.y = fmaf(ww, v[k].y, acc.y);
+      acc.z = fmaf(ww, v[k].z, acc.z);
+      acc.w = fmaf(ww, v[k].w, acc.w);
+    }
+  }
+  return acc;
+}
+
+// Any tap counts (bins wider / taller than 3 pixels, taps beyond the staged pixels): taps fetched inside the loops.
+// xb = byte offset of the column inside the tile (relative column * 512), yr = relative row.
+template <bool SM>
+__device__ __forceinline__ float4 tile_bin_any(const int nx, const int xb, const float xw, const int src, const int yr,
+                                               const float yw, const int ny, const uint32_t tile_lane,
+                                               const float* __restrict__ f_lane, const int tx0, const int ty0, const int W) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int kr = 0; kr < ny; ++kr) {
+    const int yrel = __shfl_sync(0xffffffffu, yr, kr);
+    const float wy = __shfl_sync(0xffffffffu, yw, kr);
+    for (int k = 0; k < nx; ++k) {
+      const int xo = __shfl_sync(0xffffffffu, xb, src + k);
+      const float ww = wy * __shfl_sync(0xffffffffu, xw, src + k);
+      float4 v;
+      if (SM) v = tc::lds4s(tile_lane + (uint32_t)(yrel * (rt::kEdge * kC * 4) + xo));
+      else v = ldg4(f_lane + ((size_t)(yrel + ty0) * W + ((xo >> 9) + tx0)) * kC);
+      acc.x = fmaf(ww, v.x, acc.x);
+      acc.y = fmaf(ww, v.y, acc.y);
+      acc.z = fmaf(ww, v.z, acc.z);
+      acc.w = fmaf(ww, v.w, acc.w);
+    }
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(rt::kThreads, 3)
+roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __restrict__ roi_count,
+                       const RoiTile* __restrict__ tiles, const RoiSum* __restrict__ sums, float* __restrict__ pooled) {
+  using namespace rt;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* sgen = smem_raw + (sbase - tc::smem_u32(smem_raw));
+  uint32_t* cand = reinterpret_cast<uint32_t*>(sgen + kOffCand);
+  uint16_t* task = reinterpret_cast<uint16_t*>(sgen + kOffTask);
+  int* s_count = reinterpret_cast<int*>(sgen + kOffCount);    // [0] candidates, [1] tasks, [2] next task
+  const uint32_t bar = sbase + kOffBar;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y;
+  // which tile of which level
+  int lvl = 0, id = blockIdx.x;
+  if (P.num_levels > 1 && id >= P.tile_end[0]) { lvl = 1; }
+  if (P.num_levels > 2 && id >= P.tile_end[1]) { lvl = 2; }
+  if (lvl) id -= P.tile_end[lvl - 1];
+  int W = P.W[0], H = P.H[0], tiles_x = P.tiles_x[0];
+  const float* fmap = P.feat[0];
+  if (lvl == 1) { W = P.W[1]; H = P.H[1]; tiles_x = P.tiles_x[1]; fmap = P.feat[1]; }
+  if (lvl == 2) { W = P.W[2]; H = P.H[2]; tiles_x = P.tiles_x[2]; fmap = P.feat[2]; }
+  const int ty = id / tiles_x, tx = id - ty * tiles_x;
+  const int tx0 = tx * kOwn, ty0 = ty * kOwn;
+  const float* f_lane = fmap + (size_t)b * H * W * kC + lane * 4;
+  const uint32_t tile_lane = sbase + lane * 16;
+  if (tid == 0) {                            // the tile is on its way while the ROIs are scanned
+    tc::mbar_init(bar, 1);
+    tc::fence_barrier_init();
+    tc::mbar_arrive_expect_tx(bar, kTileBytes);
+    tc::tma_load_4d(sbase, &P.map[lvl], bar, 0, tx0, ty0, b);
+  }
+  bool waited = false;
+  const int units = (P.roi_cap + 127) >> 7;
+  for (int c = 0; c < P.C; ++c) {
+    const int p = b * P.C + c;
+    const int cnt = roi_count ? min(roi_count[p], P.roi_cap) : P.roi_cap;
+    for (int base = 0; base < cnt; base += kScan) {
+      if (tid < 3) s_count[tid] = 0;
+      __syncthreads();                       // also orders the barrier initialisation before its first use
+      {                                      // scan: which bins of ROI base + tid start inside this tile
+        const int r = base + tid;
+        if (tid < kScan && r < cnt) {
+          const int4* sp = reinterpret_cast<const int4*>(sums + ((size_t)p * P.roi_cap + r));
+          const int4 m = __ldg(sp + 2);      // level | nx, tables | pad, yn, inv_count
+          const int level = (short)(m.x & 0xffff), tabled = (short)(m.y & 0xffff);
+          if (level == lvl && tabled) {
+            const int4 xa = __ldg(sp), ya = __ldg(sp + 1);
+            const int xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w};
+            uint32_t xm = 0, ym = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int x_even = (short)(xs[j] & 0xffff), x_odd = xs[j] >> 16;
+              const int y_even = (short)(ys[j] & 0xffff), y_odd = ys[j] >> 16;
+              xm |= ((uint32_t)(x_even - tx0) < (uint32_t)kOwn ? 1u : 0u) << (2 * j);
+              xm |= ((uint32_t)(x_odd - tx0) < (uint32_t)kOwn ? 1u : 0u) << (2 * j + 1);
+              ym |= ((uint32_t)(y_even - ty0) < (uint32_t)kOwn ? 1u : 0u) << (2 * j);
+              ym |= ((uint32_t)(y_odd - ty0) < (uint32_t)kOwn ? 1u : 0u) << (2 * j + 1);
+            }
+            if (xm && ym) {                  // one task per bin row that starts here
+              const int ci = atomicAdd(&s_count[0], 1);
+              cand[ci] = (uint32_t)tid | (xm << 8);
+              int slot = atomicAdd(&s_count[1], __popc(ym));
+              for (uint32_t mrow = ym; mrow; mrow &= mrow - 1) task[slot++] = (uint16_t)(ci | ((__ffs(mrow) - 1) << 8));
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const int ntask = s_count[1];
+      if (ntask > 0) {
+        tc::mbar_wait(bar, 0);
+        waited = true;
+        for (;;) {                           // warps draw (ROI, bin row) tasks from a shared counter
+          int ti = 0;
+          if (lane == 0) ti = atomicAdd(&s_count[2], 1);
+          ti = __shfl_sync(0xffffffffu, ti, 0);
+          if (ti >= ntask) break;
+          const uint32_t tk = task[ti];
+          const uint32_t e = cand[tk & 255u];
+          const int by = (int)(tk >> 8);
+          const int r = base + (int)(e & 255u);
+          const uint32_t xm = (e >> 8) & 255u;
+          const size_t row = (size_t)p * P.roi_cap + r;
+          const RoiTile& T = tiles[row];
+          // lane = (bin & 3) * 8 + tap holds the column taps of bins 0-3 (a) and 4-7 (b); lanes 0-7 the row taps
+          const int* xi = &T.xi[0][0];
+          const float* xw = &T.xw[0][0];
+          const int xa_r = __ldg(xi + lane) - tx0, xb_r = __ldg(xi + 32 + lane) - tx0;
+          const float xa_w = __ldg(xw + lane), xb_w = __ldg(xw + 32 + lane);
+          const int yr = __ldg(&T.yi[by][lane & 7]) - ty0;
+          const float yw = __ldg(&T.yw[by][lane & 7]);
+          const int4 m = __ldg(reinterpret_cast<const int4*>(sums + row) + 2);
+          const int ny = (int)(((uint32_t)m.z >> (4 * by)) & 15u);
+          const float inv_count = __int_as_float(m.w);
+          // a tap beyond the staged 12 x 12 pixels sends its bin (or the whole bin row) to the map
+          const uint32_t far_a = __ballot_sync(0xffffffffu, (uint32_t)xa_r >= (uint32_t)kEdge);
+          const uint32_t far_b = __ballot_sync(0xffffffffu, (uint32_t)xb_r >= (uint32_t)kEdge);
+          const uint32_t nz_a = __ballot_sync(0xffffffffu, xa_w != 0.f);
+          const uint32_t nz_b = __ballot_sync(0xffffffffu, xb_w != 0.f);
+          const bool rows_near = (__ballot_sync(0xffffffffu, (uint32_t)yr >= (uint32_t)kEdge) & 0xffu) == 0u;
+          const int xa_b = xa_r * (kC * 4), xb_b = xb_r * (kC * 4);      // byte offsets inside the tile
+          uint32_t rowa[4];
+          float wy[4];
+#pragma unroll
+          for (int kr = 0; kr < 4; ++kr) {
+            rowa[kr] = tile_lane + (uint32_t)(__shfl_sync(0xffffffffu, yr, kr) * (kEdge * kC * 4));
+            wy[kr] = __shfl_sync(0xffffffffu, yw, kr);
+          }
+          float* out = P.tiled ? pooled + ((((size_t)p * units + (r >> 7)) * 256 + (lane >> 3)) * 128 + (r & 127)) * 32 + (lane & 7) * 4
+                               : pooled + row * 64 * kC + lane * 4;
+          const uint32_t bin_stride = P.tiled ? 4u * 128u * 32u : (uint32_t)kC;
+          out += (size_t)(by * 8) * bin_stride;
+          for (uint32_t mm = xm; mm; mm &= mm - 1) {
+            const int bx = __ffs(mm) - 1;
+            const bool hi = bx >= 4;
+            const int src = (bx & 3) * 8;
+            const bool near = rows_near && (((hi ? far_b : far_a) >> src) & 255u) == 0u;
+            const int n = 32 - __clz(((hi ? nz_b : nz_a) >> src) & 255u);      // taps up to the last non-zero weight
+            const int xb = hi ? xb_b : xa_b;
+            const float xwv = hi ? xb_w : xa_w;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n == 0 || ny == 0) {
+            } else if (near && n <= 4 && ny <= 4) {
+              switch ((ny - 1) * 3 + max(n, 2) - 2) {        // zero-weight padding taps lie inside the tile as well
+                case 0: a = tile_bin_fixed<1, 2>(rowa, wy, xb, xwv, src); break;
+                case 1: a = tile_bin_fixed<1, 3>(rowa, wy, xb, xwv, src); break;
+                case 2: a = tile_bin_fixed<1, 4>(rowa, wy, xb, xwv, src); break;
+                case 3: a = tile_bin_fixed<2, 2>(rowa, wy, xb, xwv, src); break;
+                case 4: a = tile_bin_fixed<2, 3>(rowa, wy, xb, xwv, src); break;
+                case 5: a = tile_bin_fixed<2, 4>(rowa, wy, xb, xwv, src); break;
+                case 6: a = tile_bin_fixed<3, 2>(rowa, wy, xb, xwv, src); break;
+                case 7: a = tile_bin_fixed<3, 3>(rowa, wy, xb, xwv, src); break;
+                case 8: a = tile_bin_fixed<3, 4>(rowa, wy, xb, xwv, src); break;
+                case 9: a = tile_bin_fixed<4, 2>(rowa, wy, xb, xwv, src); break;
+                case 10: a = tile_bin_fixed<4, 3>(rowa, wy, xb, xwv, src); break;
+                default: a = tile_bin_fixed<4, 4>(rowa, wy, xb, xwv, src); break;
+              }
+            } else if (near) {
+              a = tile_bin_any<true>(n, xb, xwv, src, yr, yw, ny, tile_lane, f_lane, tx0, ty0, W);
+            } else {
+              a = tile_bin_any<false>(n, xb, xwv, src, yr, yw, ny, tile_lane, f_lane, tx0, ty0, W);
+            }
+            const float4 o = make_float4(a.x * inv_count, a.y * inv_count, a.z * inv_count, a.w * inv_count);
+            *reinterpret_cast<float4*>(out + (size_t)bx * bin_stride) = o;
+          }
+        }
+      }
+      __syncthreads();                       // the candidate list is rewritten by the next pass
+    }
+  }
+  if (!waited) tc::mbar_wait(bar, 0);        // nothing started here: the copy must still land before the CTA's memory is released
+}
+
+
 }  // namespace fod
 
 #ifdef FOD_ROI_PROF
@@ -324,10 +676,11 @@ extern "C" int fod_roi_prof(long long* out8, int reset) {
 
 using namespace fod;
 
-extern "C" int fod_roi_align_wide(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
-                                  int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap,
-                                  int resolution, int channels, int tiled, float* pooled, int32_t* out_level,
-                                  void* workspace, fod_stream_t stream) {
+// tile_stationary: 1 = the tile-stationary kernel where it applies (resolution 8, 128 channels), 0 = one CTA per ROI
+static int roi_align_impl(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
+                          int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap,
+                          int resolution, int channels, int tiled, float* pooled, int32_t* out_level,
+                          void* workspace, fod_stream_t stream, int tile_stationary) {
   FOD_REQUIRE(feat && levels && rois && pooled && workspace, "fod_roi_align: null pointer");
   FOD_REQUIRE(((uintptr_t)workspace & 15) == 0, "fod_roi_align: workspace must be 16-byte aligned");
   FOD_REQUIRE(num_levels >= 1 && num_levels <= FOD_MAX_LEVELS, "fod_roi_align: num_levels %d out of range", num_levels);
@@ -359,7 +712,44 @@ extern "C" int fod_roi_align_wide(const float* const* feat, const fod_level_t* l
   dim3 grid(roi_cap, (unsigned)P, (unsigned)(channels / kC));
   const dim3 tgrid((unsigned)((roi_cap * 2 * resolution + 255) / 256), (unsigned)P);
   cudaStream_t st = as_stream(stream);
-  if (resolution == 8) {
+  if (tile_stationary && resolution == 8 && channels == kC) {
+    const size_t n = (size_t)P * roi_cap;
+    auto* blobs = static_cast<RoiBlob<8>*>(workspace);
+    auto* tiles = reinterpret_cast<RoiTile*>(blobs + n);
+    auto* sums = reinterpret_cast<RoiSum*>(tiles + n);
+    auto* slow = reinterpret_cast<int32_t*>(sums + n);
+    static_assert(sizeof(RoiBlob<8>) % 16 == 0 && sizeof(RoiTile) == 1024 && sizeof(RoiSum) == 48, "workspace layout");
+    rt::Params tp;
+    int total = 0;
+    for (int l = 0; l < num_levels; ++l) {
+      const int rc = make_nhwc_map_plain(&tp.map[l], feat[l], batch, prm.H[l], prm.W[l], kC, kC, rt::kEdge, rt::kEdge);
+      if (rc != FOD_OK) return rc;
+      tp.feat[l] = feat[l];
+      tp.H[l] = prm.H[l];
+      tp.W[l] = prm.W[l];
+      tp.tiles_x[l] = (prm.W[l] + rt::kOwn - 1) / rt::kOwn;
+      total += tp.tiles_x[l] * ((prm.H[l] + rt::kOwn - 1) / rt::kOwn);
+      tp.tile_end[l] = total;
+    }
+    for (int l = num_levels; l < FOD_MAX_LEVELS; ++l) {
+      tp.map[l] = tp.map[0];
+      tp.feat[l] = feat[0];
+      tp.H[l] = prm.H[0]; tp.W[l] = prm.W[0]; tp.tiles_x[l] = tp.tiles_x[0]; tp.tile_end[l] = total;
+    }
+    tp.num_levels = num_levels;
+    tp.C = problems_per_image;
+    tp.roi_cap = roi_cap;
+    tp.tiled = tiled ? 1 : 0;
+    FOD_CUDA_CALL(cudaFuncSetAttribute(roi_align_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt::kSmemAlloc));
+    FOD_CUDA_CALL(cudaFuncSetAttribute(roi_align_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       (int)cudaSharedmemCarveoutMaxShared));
+    FOD_CUDA_CALL(cudaMemsetAsync(slow, 0, sizeof(int32_t), st));
+    const dim3 tgrid8((unsigned)((roi_cap * 16 + 255) / 256), (unsigned)P);
+    roi_tile_tables_kernel<<<tgrid8, 256, 0, st>>>(prm, rois, roi_count, tiles, sums, blobs, slow, out_level);
+    roi_align_tiles_kernel<<<dim3((unsigned)total, (unsigned)batch), rt::kThreads, rt::kSmemAlloc, st>>>(tp, roi_count, tiles,
+                                                                                                     sums, pooled);
+    roi_align_list_kernel<<<74, 512, 0, st>>>(prm, slow, blobs, pooled);
+  } else if (resolution == 8) {
     auto* blobs = static_cast<RoiBlob<8>*>(workspace);
     roi_tables_kernel<8><<<tgrid, 256, 0, st>>>(prm, rois, roi_count, blobs, out_level);
     roi_align_kernel<8><<<grid, 512, 0, st>>>(prm, roi_count, blobs, pooled);
@@ -376,9 +766,27 @@ extern "C" int fod_roi_align_wide(const float* const* feat, const fod_level_t* l
   return FOD_OK;
 }
 
+extern "C" int fod_roi_align_wide(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
+                                  int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap,
+                                  int resolution, int channels, int tiled, float* pooled, int32_t* out_level,
+                                  void* workspace, fod_stream_t stream) {
+  return roi_align_impl(feat, levels, num_levels, batch, problems_per_image, rois, roi_count, roi_cap, resolution, channels,
+                        tiled, pooled, out_level, workspace, stream, 1);
+}
+
+extern "C" int fod_roi_align_per_roi(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
+                                     int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap,
+                                     int resolution, int channels, int tiled, float* pooled, int32_t* out_level,
+                                     void* workspace, fod_stream_t stream) {
+  return roi_align_impl(feat, levels, num_levels, batch, problems_per_image, rois, roi_count, roi_cap, resolution, channels,
+                        tiled, pooled, out_level, workspace, stream, 0);
+}
+
 extern "C" size_t fod_roi_align_workspace_bytes(int num_problems, int roi_cap, int resolution) {
-  const size_t per = resolution == 8 ? sizeof(RoiBlob<8>) : (resolution == 4 ? sizeof(RoiBlob<4>) : sizeof(RoiBlob<14>));
-  return (size_t)num_problems * roi_cap * per;
+  const size_t n = (size_t)num_problems * roi_cap;
+  if (resolution == 8)   // blobs | tile tap lists | scan summaries | slow list (count + entries)
+    return n * (sizeof(RoiBlob<8>) + sizeof(RoiTile) + sizeof(RoiSum)) + ((n + 1) * sizeof(int32_t) + 15) / 16 * 16;
+  return n * (resolution == 4 ? sizeof(RoiBlob<4>) : sizeof(RoiBlob<14>));
 }
 
 extern "C" int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,

@@ -300,10 +300,11 @@ def untile_pooled(t: Tensor, cap: int) -> Tensor:
 
 def roi_align(feats: Sequence[Tensor], strides: Sequence[int], rois: Tensor, roi_count: Optional[Tensor],
               problems_per_image: int, resolution: int, out: Optional[Tensor] = None, want_levels: bool = False,
-              tiled: bool = False):
+              tiled: bool = False, per_roi: bool = False):
     """feats[l] [B,C,H,W] (C a multiple of 128); rois [P,cap,4] -> pooled [P,cap,R*R,C] (bin-major, channel innermost;
     R = 4, 8 or 14), or with tiled=True (R == 8, C == 128) the relation-head operand layout [P,U,256,128,32] (see
-    tile_pooled) (d2 poolers.py:190-250)."""
+    tile_pooled) (d2 poolers.py:190-250).  R == 8 over 128-channel maps runs the tile-stationary kernel; per_roi=True
+    forces the one-CTA-per-ROI kernel (fod_roi_align_per_roi: bit-identical results, kept for comparison)."""
     feats = [nhwc(f, "feat") for f in feats]
     B, ch = feats[0].shape[0], feats[0].shape[1]
     _chk(rois, torch.float32, "rois")
@@ -321,9 +322,9 @@ def roi_align(feats: Sequence[Tensor], strides: Sequence[int], rois: Tensor, roi
     lv = _levels(feats, strides)
     L = _lib.lib()
     ws = torch.empty((L.fod_roi_align_workspace_bytes(P, cap, int(resolution)) // 16, 4), dtype=torch.int32, device=dev)
-    _lib.check(L.fod_roi_align_wide(_ptr_array(feats), lv, len(feats), B, int(problems_per_image), _ptr(rois),
-                                    _ptr(roi_count), cap, int(resolution), int(ch), int(bool(tiled)), _ptr(out),
-                                    _ptr(lvl), _ptr(ws), _stream()), "fod_roi_align")
+    fn = L.fod_roi_align_per_roi if per_roi else L.fod_roi_align_wide
+    _lib.check(fn(_ptr_array(feats), lv, len(feats), B, int(problems_per_image), _ptr(rois), _ptr(roi_count), cap,
+                  int(resolution), int(ch), int(bool(tiled)), _ptr(out), _ptr(lvl), _ptr(ws), _stream()), "fod_roi_align")
     return (out, lvl) if want_levels else out
 
 

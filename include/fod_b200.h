@@ -182,7 +182,8 @@ int fod_nms_proposals(const float* boxes, const float* scores, const int32_t* co
  */
 /*   workspace : fod_roi_align_workspace_bytes(P, roi_cap, resolution) bytes, 16-byte aligned: per ROI the box geometry
  *              and the per-bin lists of distinct rows / columns with their interpolation weights, written by a
- *              pre-pass over all ROIs (one thread per axis and bin) and read by the pooling CTAs */
+ *              pre-pass over all ROIs (one thread per axis and bin) and read by the pooling CTAs; for resolution 8
+ *              also the per-ROI scan summaries and the list of ROIs the tile-stationary kernel hands to the per-ROI one */
 size_t fod_roi_align_workspace_bytes(int num_problems, int roi_cap, int resolution);
 int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
                   int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap, int resolution,
@@ -194,6 +195,17 @@ int fod_roi_align(const float* const* feat, const fod_level_t* levels, int num_l
 int fod_roi_align_wide(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
                        int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap, int resolution,
                        int channels, int tiled, float* pooled, int32_t* out_level, void* workspace, fod_stream_t stream);
+
+/* fod_roi_align / fod_roi_align_wide pool resolution 8 over 128-channel maps (the query path R1) with the
+ * tile-stationary kernel: a CTA TMA-stages a 12 x 12-pixel piece of one map into shared memory and pools every bin
+ * that starts inside its 8 x 8 owned pixels, so that a map pixel leaves L2 about twice per call instead of once per
+ * ROI window that covers it.  Other shapes (resolution 4 / 14, wider maps) run one CTA per ROI.  This entry point
+ * forces the one-CTA-per-ROI kernel for every shape: same arguments, same workspace, bit-identical results (the
+ * summation order of a bin is the same) - kept as the comparison operator of the parity tests and the A/B timing. */
+int fod_roi_align_per_roi(const float* const* feat, const fod_level_t* levels, int num_levels, int batch,
+                          int problems_per_image, const float* rois, const int32_t* roi_count, int roi_cap,
+                          int resolution, int channels, int tiled, float* pooled, int32_t* out_level, void* workspace,
+                          fod_stream_t stream);
 
 /* ---------------------------------------------------------------------------
  * R2+R3  relation head on pooled ROI features, softmax, box decoding.

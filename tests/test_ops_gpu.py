@@ -380,6 +380,54 @@ def test_roi_align_respects_counts_and_classes():
         assert torch.equal(back[p, :n], pooled[p, :n])
 
 
+def _roi_stress_boxes(n, seed, height, width):
+    """Boxes of every kind the pooling has a separate path for: ordinary proposals, slivers and elongated boxes (bins
+    longer than the tile halo: taps read from the map), boxes larger than their level expects (sampling grid beyond the
+    tap tables: per-ROI list kernel), boxes partly / entirely outside the image, zero-area and inverted boxes."""
+    base = _boxes(n, seed, 0.0, float(max(height, width)), 6.0, 260.0)
+    kind = (synth.tensor((n,), seed + 7, 0.0, 1.0) * 10).floor()
+    ctr = (base[:, :2] + base[:, 2:]) / 2
+    wh = base[:, 2:] - base[:, :2]
+    wh = torch.where((kind == 1)[:, None], wh * torch.tensor([6.0, 0.15]), wh)       # long and flat
+    wh = torch.where((kind == 2)[:, None], wh * torch.tensor([0.1, 5.0]), wh)        # tall and thin
+    wh = torch.where((kind == 3)[:, None], wh * 8.0, wh)                             # far beyond the image
+    wh = torch.where((kind == 4)[:, None], wh * 0.0, wh)                             # zero area
+    wh = torch.where((kind == 5)[:, None], wh * torch.tensor([-1.0, 1.0]), wh)       # inverted in x
+    ctr = torch.where((kind == 6)[:, None], ctr - float(max(height, width)), ctr)    # left of / above the image
+    ctr = torch.where((kind == 7)[:, None], ctr + float(max(height, width)), ctr)    # right of / below the image
+    return torch.cat((ctr - wh / 2, ctr + wh / 2), 1)
+
+
+@pytest.mark.parametrize("height,width,C", [(256, 320, 1), (200, 312, 3), (640, 640, 2)])
+def test_roi_align_tile_stationary_is_bit_identical_to_per_roi(height, width, C):
+    """The tile-stationary kernel (fod_roi_align, resolution 8) against the one-CTA-per-ROI kernel on the same inputs:
+    every valid row bit-identical, rows beyond the count untouched, both output layouts; and against the oracle."""
+    B, cap = 3, 300                                          # 300 > 256: two scan passes per problem
+    feats = synth.features(B, height, width, 71 + C)
+    fl = [feats["p3"], feats["p4"], feats["p5"]]
+    bx = _roi_stress_boxes(B * C * cap, 300 + C, height, width).reshape(B * C, cap, 4)
+    counts = torch.tensor([cap, 257, 0, 1, 256, 129, 40, cap, 7][:B * C], dtype=torch.int32)
+    fd = [f.to(DEV) for f in fl]
+    for tiled in (False, True):
+        shape = (B * C, 3, 256, 128, 32) if tiled else (B * C, cap, 64, 128)
+        out_t = torch.full(shape, -7.0, device=DEV)
+        out_r = torch.full(shape, -7.0, device=DEV)
+        _, lv_t = ops.roi_align(fd, (8, 16, 32), bx.to(DEV), counts.to(DEV), C, 8, out=out_t, tiled=tiled, want_levels=True)
+        _, lv_r = ops.roi_align(fd, (8, 16, 32), bx.to(DEV), counts.to(DEV), C, 8, out=out_r, tiled=tiled, want_levels=True,
+                                per_roi=True)
+        assert torch.equal(lv_t, lv_r)
+        assert torch.equal(out_t, out_r), f"tiled={tiled}: {(out_t != out_r).sum().item()} elements differ"
+        if not tiled:
+            got = out_t.cpu()
+            for p in range(B * C):
+                n = int(counts[p])
+                assert torch.all(got[p, n:] == -7.0)
+                if n and p % 2 == 0:
+                    ok = (bx[p, :n, 2] > bx[p, :n, 0]) & (bx[p, :n, 3] > bx[p, :n, 1])     # the oracle's level rule needs a positive area
+                    ref = O.roi_pool([f[p // C:p // C + 1] for f in fl], [bx[p, :n][ok]], 8)
+                    assert_close(got[p, :n].reshape(n, 8, 8, 128).permute(0, 3, 1, 2)[ok], ref, what=f"problem {p} vs oracle")
+
+
 def test_relation_head_matches_reference_and_oracle():
     g = golden("ops")
     sd = head_state_dict()

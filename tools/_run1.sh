@@ -1,0 +1,3 @@
+set -x
+python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k "roi_align or relation_head" 2>&1 | tail -15
+python tools/bench_roi.py 2>&1 | tail -8
