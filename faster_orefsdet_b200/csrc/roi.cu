@@ -370,13 +370,15 @@ namespace rt {
 constexpr int kOwn = 8;                       // a CTA owns kOwn x kOwn pixels ...
 constexpr int kEdge = 12;                     // ... and stages kEdge x kEdge
 constexpr int kThreads = 256;
-constexpr int kScan = 128;                    // ROIs per scan pass (one per thread of the first four warps)
+constexpr int kScan = 256;                    // ROIs per scan pass (one per thread)
+constexpr int kTaskCap = 1280;                // tasks per pass; a pass ends early (and the next one resumes) beyond that
 constexpr uint32_t kTileBytes = kEdge * kEdge * kC * 4;
-constexpr uint32_t kOffCand = kTileBytes;                    // uint32[kScan]: ROI | column mask of the bins that start here
-constexpr uint32_t kOffTask = kOffCand + kScan * 4;          // uint16[kScan * 8]: candidate | bin row << 8
-constexpr uint32_t kOffBar = kOffTask + kScan * 8 * 2;       // mbarrier
-constexpr uint32_t kOffCount = kOffBar + 8;                  // counters: candidates, tasks, next task
-constexpr uint32_t kSmemBytes = kOffCount + 16;
+constexpr uint32_t kOffCand = kTileBytes;                    // uint8[kScan]: column mask of the ROI's bins that start here
+constexpr uint32_t kOffTask = kOffCand + kScan;              // uint16[kTaskCap]: ROI of the pass | bin row << 8
+constexpr uint32_t kOffBar = kOffTask + kTaskCap * 2;        // mbarrier
+constexpr uint32_t kOffCount = kOffBar + 8;                  // int[12]: task count of each warp's ROIs, next task, resume point, tasks
+constexpr uint32_t kSmemBytes = kOffCount + 48;
+static_assert(3 * (kSmemBytes + 128 + 1024) <= 233472, "three CTAs per SM");
 constexpr uint32_t kSmemAlloc = kSmemBytes + 128;            // slack for the 128-byte alignment of the TMA destination
 struct Params {
   CUtensorMap map[FOD_MAX_LEVELS];
@@ -512,9 +514,9 @@ roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __re
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* sgen = smem_raw + (sbase - tc::smem_u32(smem_raw));
-  uint32_t* cand = reinterpret_cast<uint32_t*>(sgen + kOffCand);
+  uint8_t* cand = sgen + kOffCand;
   uint16_t* task = reinterpret_cast<uint16_t*>(sgen + kOffTask);
-  int* s_count = reinterpret_cast<int*>(sgen + kOffCount);    // [0] candidates, [1] tasks, [2] next task
+  int* s_count = reinterpret_cast<int*>(sgen + kOffCount);    // [0..7] tasks of each warp's ROIs, [8] next task, [9] resume, [10] tasks
   const uint32_t bar = sbase + kOffBar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y;
@@ -542,19 +544,19 @@ roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __re
   for (int c = 0; c < P.C; ++c) {
     const int p = b * P.C + c;
     const int cnt = roi_count ? min(roi_count[p], P.roi_cap) : P.roi_cap;
-    for (int base = 0; base < cnt; base += kScan) {
-      if (tid < 3) s_count[tid] = 0;
-      __syncthreads();                       // also orders the barrier initialisation before its first use
-      {                                      // scan: which bins of ROI base + tid start inside this tile
+    for (int base = 0; base < cnt;) {
+      // Scan: which bins of ROI base + tid start inside this tile.  Tasks (one per bin row) are laid out in ROI order
+      // by a prefix sum over the CTA; if they exceed the list the pass stops at the first ROI that does not fit.
+      uint32_t xm = 0, ym = 0;
+      {
         const int r = base + tid;
-        if (tid < kScan && r < cnt) {
+        if (r < cnt) {
           const int4* sp = reinterpret_cast<const int4*>(sums + ((size_t)p * P.roi_cap + r));
           const int4 m = __ldg(sp + 2);      // level | nx, tables | pad, yn, inv_count
           const int level = (short)(m.x & 0xffff), tabled = (short)(m.y & 0xffff);
           if (level == lvl && tabled) {
             const int4 xa = __ldg(sp), ya = __ldg(sp + 1);
             const int xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w};
-            uint32_t xm = 0, ym = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int x_even = (short)(xs[j] & 0xffff), x_odd = xs[j] >> 16;
@@ -564,30 +566,54 @@ roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __re
               ym |= ((uint32_t)(y_even - ty0) < (uint32_t)kOwn ? 1u : 0u) << (2 * j);
               ym |= ((uint32_t)(y_odd - ty0) < (uint32_t)kOwn ? 1u : 0u) << (2 * j + 1);
             }
-            if (xm && ym) {                  // one task per bin row that starts here
-              const int ci = atomicAdd(&s_count[0], 1);
-              cand[ci] = (uint32_t)tid | (xm << 8);
-              int slot = atomicAdd(&s_count[1], __popc(ym));
-              for (uint32_t mrow = ym; mrow; mrow &= mrow - 1) task[slot++] = (uint16_t)(ci | ((__ffs(mrow) - 1) << 8));
-            }
+            if (!xm) ym = 0;
           }
         }
       }
+      const int nrow = __popc(ym);
+      int incl = nrow;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      if (lane == 31) s_count[warp] = incl;
+      if (tid == 0) s_count[8] = 0;
+      __syncthreads();                       // also orders the barrier initialisation before its first use
+      int woff = 0, total = 0;
+#pragma unroll
+      for (int w8 = 0; w8 < kThreads / 32; ++w8) {
+        const int v = s_count[w8];
+        if (w8 < warp) woff += v;
+        total += v;
+      }
+      {
+        const int end = woff + incl, start = end - nrow;
+        if (nrow && end <= kTaskCap) {
+          cand[tid] = (uint8_t)xm;
+          int slot = start;
+          for (uint32_t mrow = ym; mrow; mrow &= mrow - 1) task[slot++] = (uint16_t)(tid | ((__ffs(mrow) - 1) << 8));
+        }
+        if (end > kTaskCap && start <= kTaskCap) {       // the first ROI that does not fit (its predecessors end <= the cap)
+          s_count[9] = base + tid;
+          s_count[10] = start;
+        }
+      }
       __syncthreads();
-      const int ntask = s_count[1];
+      const int ntask = total > kTaskCap ? s_count[10] : total;
+      const int next_base = total > kTaskCap ? s_count[9] : base + kScan;
       if (ntask > 0) {
         tc::mbar_wait(bar, 0);
         waited = true;
         for (;;) {                           // warps draw (ROI, bin row) tasks from a shared counter
           int ti = 0;
-          if (lane == 0) ti = atomicAdd(&s_count[2], 1);
+          if (lane == 0) ti = atomicAdd(&s_count[8], 1);
           ti = __shfl_sync(0xffffffffu, ti, 0);
           if (ti >= ntask) break;
           const uint32_t tk = task[ti];
-          const uint32_t e = cand[tk & 255u];
           const int by = (int)(tk >> 8);
-          const int r = base + (int)(e & 255u);
-          const uint32_t xm = (e >> 8) & 255u;
+          const int r = base + (int)(tk & 255u);
+          const uint32_t xm = cand[tk & 255u];
           const size_t row = (size_t)p * P.roi_cap + r;
           const RoiTile& T = tiles[row];
           // lane = (bin & 3) * 8 + tap holds the column taps of bins 0-3 (a) and 4-7 (b); lanes 0-7 the row taps
@@ -653,7 +679,8 @@ roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __re
           }
         }
       }
-      __syncthreads();                       // the candidate list is rewritten by the next pass
+      base = next_base;
+      if (base < cnt || c + 1 < P.C) __syncthreads();      // the lists are rewritten by the next pass
     }
   }
   if (!waited) tc::mbar_wait(bar, 0);        // nothing started here: the copy must still land before the CTA's memory is released

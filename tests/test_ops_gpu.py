@@ -428,6 +428,22 @@ def test_roi_align_tile_stationary_is_bit_identical_to_per_roi(height, width, C)
                     assert_close(got[p, :n].reshape(n, 8, 8, 128).permute(0, 3, 1, 2)[ok], ref, what=f"problem {p} vs oracle")
 
 
+def test_roi_align_tile_stationary_resumes_after_a_full_task_list():
+    """300 small boxes crowded into one corner: every ROI's eight bin rows start inside the same 8 x 8-pixel tile, more
+    tasks than one pass of the tile-stationary kernel holds (it stops at the first ROI that does not fit and resumes)."""
+    feats = synth.features(2, 256, 320, 77)
+    fl = [feats["p3"], feats["p4"], feats["p5"]]
+    bx = _boxes(2 * 300, 91, 12.0, 44.0, 6.0, 30.0).reshape(2, 300, 4)
+    counts = torch.tensor([300, 290], dtype=torch.int32, device=DEV)
+    fd = [f.to(DEV) for f in fl]
+    out_t = ops.roi_align(fd, (8, 16, 32), bx.to(DEV), counts, 1, 8)
+    out_r = ops.roi_align(fd, (8, 16, 32), bx.to(DEV), counts, 1, 8, per_roi=True)
+    for p, n in enumerate((300, 290)):
+        assert torch.equal(out_t[p, :n], out_r[p, :n])
+    ref = O.roi_pool([f[:1] for f in fl], [bx[0]], 8)
+    assert_close(out_t[0].cpu().reshape(300, 8, 8, 128).permute(0, 3, 1, 2), ref, what="crowded boxes vs oracle")
+
+
 def test_relation_head_matches_reference_and_oracle():
     g = golden("ops")
     sd = head_state_dict()
