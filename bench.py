@@ -185,7 +185,7 @@ class KernelTimer:
         self.enabled = False
 
     # kernels of this library per C-ABI call (memsets are not counted)
-    kernels_per_call = {"group_norm_nhwc": 2, "roi_align": 2, "decode_topk_taps": 2}   # statistics + apply; tap tables + pooling; keys + select
+    kernels_per_call = {"group_norm_nhwc": 2, "roi_align": 3, "decode_topk_taps": 2}   # statistics + apply; tap tables + tile pooling + per-ROI list; keys + select
 
     def wrap(self, ops_mod, names):
         for n in names:
