@@ -371,15 +371,13 @@ constexpr int kOwn = 8;                       // a CTA owns kOwn x kOwn pixels .
 constexpr int kEdge = 12;                     // ... and stages kEdge x kEdge
 constexpr int kThreads = 256;
 constexpr int kScan = 256;                    // ROIs per scan pass (one per thread)
-constexpr int kTaskCap = 1280;                // tasks per pass; a pass ends early (and the next one resumes) beyond that
 constexpr uint32_t kTileBytes = kEdge * kEdge * kC * 4;
-constexpr uint32_t kOffCand = kTileBytes;                    // uint8[kScan]: column mask of the ROI's bins that start here
-constexpr uint32_t kOffTask = kOffCand + kScan;              // uint16[kTaskCap]: ROI of the pass | bin row << 8
-constexpr uint32_t kOffBar = kOffTask + kTaskCap * 2;        // mbarrier
-constexpr uint32_t kOffCount = kOffBar + 8;                  // int[12]: task count of each warp's ROIs, next task, resume point, tasks
-constexpr uint32_t kSmemBytes = kOffCount + 48;
-static_assert(3 * (kSmemBytes + 128 + 1024) <= 233472, "three CTAs per SM");
+constexpr uint32_t kOffCand = kTileBytes;                    // uint32[kScan]: ROI of the pass | column mask << 8 | row mask << 16
+constexpr uint32_t kOffBar = kOffCand + kScan * 4;           // mbarrier
+constexpr uint32_t kOffCount = kOffBar + 8;                  // int[2]: candidates, next task
+constexpr uint32_t kSmemBytes = kOffCount + 8;
 constexpr uint32_t kSmemAlloc = kSmemBytes + 128;            // slack for the 128-byte alignment of the TMA destination
+static_assert(3 * (kSmemAlloc + 1024) <= 233472, "three CTAs per SM");
 struct Params {
   CUtensorMap map[FOD_MAX_LEVELS];
   const float* feat[FOD_MAX_LEVELS];
@@ -486,12 +484,12 @@ __device__ __forceinline__ float4 tile_bin_fixed(const uint32_t (&rowa)[4], cons
 // xb = byte offset of the column inside the tile (relative column * 512), yr = relative row.
 template <bool SM>
 __device__ __forceinline__ float4 tile_bin_any(const int nx, const int xb, const float xw, const int src, const int yr,
-                                               const float yw, const int ny, const uint32_t tile_lane,
+                                               const float yw, const int ysrc, const int ny, const uint32_t tile_lane,
                                                const float* __restrict__ f_lane, const int tx0, const int ty0, const int W) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int kr = 0; kr < ny; ++kr) {
-    const int yrel = __shfl_sync(0xffffffffu, yr, kr);
-    const float wy = __shfl_sync(0xffffffffu, yw, kr);
+    const int yrel = __shfl_sync(0xffffffffu, yr, ysrc + kr);
+    const float wy = __shfl_sync(0xffffffffu, yw, ysrc + kr);
     for (int k = 0; k < nx; ++k) {
       const int xo = __shfl_sync(0xffffffffu, xb, src + k);
       const float ww = wy * __shfl_sync(0xffffffffu, xw, src + k);
@@ -514,11 +512,10 @@ roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __re
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (tc::smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* sgen = smem_raw + (sbase - tc::smem_u32(smem_raw));
-  uint8_t* cand = sgen + kOffCand;
-  uint16_t* task = reinterpret_cast<uint16_t*>(sgen + kOffTask);
-  int* s_count = reinterpret_cast<int*>(sgen + kOffCount);    // [0..7] tasks of each warp's ROIs, [8] next task, [9] resume, [10] tasks
+  uint32_t* cand = reinterpret_cast<uint32_t*>(sgen + kOffCand);
+  int* s_count = reinterpret_cast<int*>(sgen + kOffCount);    // [0] candidates, [1] next task
   const uint32_t bar = sbase + kOffBar;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int b = blockIdx.y;
   // which tile of which level
   int lvl = 0, id = blockIdx.x;
@@ -544,11 +541,10 @@ roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __re
   for (int c = 0; c < P.C; ++c) {
     const int p = b * P.C + c;
     const int cnt = roi_count ? min(roi_count[p], P.roi_cap) : P.roi_cap;
-    for (int base = 0; base < cnt;) {
-      // Scan: which bins of ROI base + tid start inside this tile.  Tasks (one per bin row) are laid out in ROI order
-      // by a prefix sum over the CTA; if they exceed the list the pass stops at the first ROI that does not fit.
-      uint32_t xm = 0, ym = 0;
-      {
+    for (int base = 0; base < cnt; base += kScan) {
+      if (tid < 2) s_count[tid] = 0;
+      __syncthreads();                       // also orders the barrier initialisation before its first use
+      {                                      // scan: which bins of ROI base + tid start inside this tile
         const int r = base + tid;
         if (r < cnt) {
           const int4* sp = reinterpret_cast<const int4*>(sums + ((size_t)p * P.roi_cap + r));
@@ -557,6 +553,7 @@ roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __re
           if (level == lvl && tabled) {
             const int4 xa = __ldg(sp), ya = __ldg(sp + 1);
             const int xs[4] = {xa.x, xa.y, xa.z, xa.w}, ys[4] = {ya.x, ya.y, ya.z, ya.w};
+            uint32_t xm = 0, ym = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int x_even = (short)(xs[j] & 0xffff), x_odd = xs[j] >> 16;
@@ -566,121 +563,97 @@ roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __re
               ym |= ((uint32_t)(y_even - ty0) < (uint32_t)kOwn ? 1u : 0u) << (2 * j);
               ym |= ((uint32_t)(y_odd - ty0) < (uint32_t)kOwn ? 1u : 0u) << (2 * j + 1);
             }
-            if (!xm) ym = 0;
+            if (xm && ym) cand[atomicAdd(&s_count[0], 1)] = (uint32_t)tid | (xm << 8) | (ym << 16);
           }
-        }
-      }
-      const int nrow = __popc(ym);
-      int incl = nrow;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      if (lane == 31) s_count[warp] = incl;
-      if (tid == 0) s_count[8] = 0;
-      __syncthreads();                       // also orders the barrier initialisation before its first use
-      int woff = 0, total = 0;
-#pragma unroll
-      for (int w8 = 0; w8 < kThreads / 32; ++w8) {
-        const int v = s_count[w8];
-        if (w8 < warp) woff += v;
-        total += v;
-      }
-      {
-        const int end = woff + incl, start = end - nrow;
-        if (nrow && end <= kTaskCap) {
-          cand[tid] = (uint8_t)xm;
-          int slot = start;
-          for (uint32_t mrow = ym; mrow; mrow &= mrow - 1) task[slot++] = (uint16_t)(tid | ((__ffs(mrow) - 1) << 8));
-        }
-        if (end > kTaskCap && start <= kTaskCap) {       // the first ROI that does not fit (its predecessors end <= the cap)
-          s_count[9] = base + tid;
-          s_count[10] = start;
         }
       }
       __syncthreads();
-      const int ntask = total > kTaskCap ? s_count[10] : total;
-      const int next_base = total > kTaskCap ? s_count[9] : base + kScan;
+      const int ntask = s_count[0];
       if (ntask > 0) {
         tc::mbar_wait(bar, 0);
         waited = true;
-        for (;;) {                           // warps draw (ROI, bin row) tasks from a shared counter
+        for (;;) {                           // warps draw ROIs from a shared counter
           int ti = 0;
-          if (lane == 0) ti = atomicAdd(&s_count[8], 1);
+          if (lane == 0) ti = atomicAdd(&s_count[1], 1);
           ti = __shfl_sync(0xffffffffu, ti, 0);
           if (ti >= ntask) break;
-          const uint32_t tk = task[ti];
-          const int by = (int)(tk >> 8);
-          const int r = base + (int)(tk & 255u);
-          const uint32_t xm = cand[tk & 255u];
+          const uint32_t e = cand[ti];
+          const int r = base + (int)(e & 255u);
+          const uint32_t xm = (e >> 8) & 255u, ym = e >> 16;
           const size_t row = (size_t)p * P.roi_cap + r;
           const RoiTile& T = tiles[row];
-          // lane = (bin & 3) * 8 + tap holds the column taps of bins 0-3 (a) and 4-7 (b); lanes 0-7 the row taps
-          const int* xi = &T.xi[0][0];
-          const float* xw = &T.xw[0][0];
-          const int xa_r = __ldg(xi + lane) - tx0, xb_r = __ldg(xi + 32 + lane) - tx0;
-          const float xa_w = __ldg(xw + lane), xb_w = __ldg(xw + 32 + lane);
-          const int yr = __ldg(&T.yi[by][lane & 7]) - ty0;
-          const float yw = __ldg(&T.yw[by][lane & 7]);
-          const int4 m = __ldg(reinterpret_cast<const int4*>(sums + row) + 2);
-          const int ny = (int)(((uint32_t)m.z >> (4 * by)) & 15u);
-          const float inv_count = __int_as_float(m.w);
+          // lane = (bin & 3) * 8 + tap holds the taps of bins / bin rows 0-3 (a) and 4-7 (b)
+          const int xa_r = __ldg(&T.xi[0][0] + lane) - tx0, xb_r = __ldg(&T.xi[0][0] + 32 + lane) - tx0;
+          const float xa_w = __ldg(&T.xw[0][0] + lane), xb_w = __ldg(&T.xw[0][0] + 32 + lane);
+          const int ya_r = __ldg(&T.yi[0][0] + lane) - ty0, yb_r = __ldg(&T.yi[0][0] + 32 + lane) - ty0;
+          const float ya_w = __ldg(&T.yw[0][0] + lane), yb_w = __ldg(&T.yw[0][0] + 32 + lane);
+          const uint32_t yn = __ldg(&sums[row].yn);
+          const float inv_count = __ldg(&sums[row].inv_count);
           // a tap beyond the staged 12 x 12 pixels sends its bin (or the whole bin row) to the map
-          const uint32_t far_a = __ballot_sync(0xffffffffu, (uint32_t)xa_r >= (uint32_t)kEdge);
-          const uint32_t far_b = __ballot_sync(0xffffffffu, (uint32_t)xb_r >= (uint32_t)kEdge);
+          const uint32_t xfar_a = __ballot_sync(0xffffffffu, (uint32_t)xa_r >= (uint32_t)kEdge);
+          const uint32_t xfar_b = __ballot_sync(0xffffffffu, (uint32_t)xb_r >= (uint32_t)kEdge);
+          const uint32_t yfar_a = __ballot_sync(0xffffffffu, (uint32_t)ya_r >= (uint32_t)kEdge);
+          const uint32_t yfar_b = __ballot_sync(0xffffffffu, (uint32_t)yb_r >= (uint32_t)kEdge);
           const uint32_t nz_a = __ballot_sync(0xffffffffu, xa_w != 0.f);
           const uint32_t nz_b = __ballot_sync(0xffffffffu, xb_w != 0.f);
-          const bool rows_near = (__ballot_sync(0xffffffffu, (uint32_t)yr >= (uint32_t)kEdge) & 0xffu) == 0u;
-          const int xa_b = xa_r * (kC * 4), xb_b = xb_r * (kC * 4);      // byte offsets inside the tile
-          uint32_t rowa[4];
-          float wy[4];
-#pragma unroll
-          for (int kr = 0; kr < 4; ++kr) {
-            rowa[kr] = tile_lane + (uint32_t)(__shfl_sync(0xffffffffu, yr, kr) * (kEdge * kC * 4));
-            wy[kr] = __shfl_sync(0xffffffffu, yw, kr);
-          }
-          float* out = P.tiled ? pooled + ((((size_t)p * units + (r >> 7)) * 256 + (lane >> 3)) * 128 + (r & 127)) * 32 + (lane & 7) * 4
-                               : pooled + row * 64 * kC + lane * 4;
+          const int xa_b = xa_r * (kC * 4), xb_b = xb_r * (kC * 4);                    // byte offsets inside the tile
+          const int ya_b = ya_r * (kEdge * kC * 4), yb_b = yb_r * (kEdge * kC * 4);
+          float* out_roi = P.tiled ? pooled + ((((size_t)p * units + (r >> 7)) * 256 + (lane >> 3)) * 128 + (r & 127)) * 32 + (lane & 7) * 4
+                                   : pooled + row * 64 * kC + lane * 4;
           const uint32_t bin_stride = P.tiled ? 4u * 128u * 32u : (uint32_t)kC;
-          out += (size_t)(by * 8) * bin_stride;
-          for (uint32_t mm = xm; mm; mm &= mm - 1) {
-            const int bx = __ffs(mm) - 1;
-            const bool hi = bx >= 4;
-            const int src = (bx & 3) * 8;
-            const bool near = rows_near && (((hi ? far_b : far_a) >> src) & 255u) == 0u;
-            const int n = 32 - __clz(((hi ? nz_b : nz_a) >> src) & 255u);      // taps up to the last non-zero weight
-            const int xb = hi ? xb_b : xa_b;
-            const float xwv = hi ? xb_w : xa_w;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n == 0 || ny == 0) {
-            } else if (near && n <= 4 && ny <= 4) {
-              switch ((ny - 1) * 3 + max(n, 2) - 2) {        // zero-weight padding taps lie inside the tile as well
-                case 0: a = tile_bin_fixed<1, 2>(rowa, wy, xb, xwv, src); break;
-                case 1: a = tile_bin_fixed<1, 3>(rowa, wy, xb, xwv, src); break;
-                case 2: a = tile_bin_fixed<1, 4>(rowa, wy, xb, xwv, src); break;
-                case 3: a = tile_bin_fixed<2, 2>(rowa, wy, xb, xwv, src); break;
-                case 4: a = tile_bin_fixed<2, 3>(rowa, wy, xb, xwv, src); break;
-                case 5: a = tile_bin_fixed<2, 4>(rowa, wy, xb, xwv, src); break;
-                case 6: a = tile_bin_fixed<3, 2>(rowa, wy, xb, xwv, src); break;
-                case 7: a = tile_bin_fixed<3, 3>(rowa, wy, xb, xwv, src); break;
-                case 8: a = tile_bin_fixed<3, 4>(rowa, wy, xb, xwv, src); break;
-                case 9: a = tile_bin_fixed<4, 2>(rowa, wy, xb, xwv, src); break;
-                case 10: a = tile_bin_fixed<4, 3>(rowa, wy, xb, xwv, src); break;
-                default: a = tile_bin_fixed<4, 4>(rowa, wy, xb, xwv, src); break;
-              }
-            } else if (near) {
-              a = tile_bin_any<true>(n, xb, xwv, src, yr, yw, ny, tile_lane, f_lane, tx0, ty0, W);
-            } else {
-              a = tile_bin_any<false>(n, xb, xwv, src, yr, yw, ny, tile_lane, f_lane, tx0, ty0, W);
+          for (uint32_t rows = ym; rows; rows &= rows - 1) {
+            const int by = __ffs(rows) - 1;
+            const bool yhi = by >= 4;
+            const int ysrc = (by & 3) * 8;
+            const int ny = (int)((yn >> (4 * by)) & 15u);
+            const bool rows_near = (((yhi ? yfar_b : yfar_a) >> ysrc) & 255u) == 0u;
+            const int yb = yhi ? yb_b : ya_b, yr = yhi ? yb_r : ya_r;
+            const float yw = yhi ? yb_w : ya_w;
+            uint32_t rowa[4];
+            float wy[4];
+#pragma unroll
+            for (int kr = 0; kr < 4; ++kr) {
+              rowa[kr] = tile_lane + (uint32_t)__shfl_sync(0xffffffffu, yb, ysrc + kr);
+              wy[kr] = __shfl_sync(0xffffffffu, yw, ysrc + kr);
             }
-            const float4 o = make_float4(a.x * inv_count, a.y * inv_count, a.z * inv_count, a.w * inv_count);
-            *reinterpret_cast<float4*>(out + (size_t)bx * bin_stride) = o;
+            float* out = out_roi + (size_t)(by * 8) * bin_stride;
+            for (uint32_t mm = xm; mm; mm &= mm - 1) {
+              const int bx = __ffs(mm) - 1;
+              const bool hi = bx >= 4;
+              const int src = (bx & 3) * 8;
+              const bool near = rows_near && (((hi ? xfar_b : xfar_a) >> src) & 255u) == 0u;
+              const int n = 32 - __clz(((hi ? nz_b : nz_a) >> src) & 255u);      // taps up to the last non-zero weight
+              const int xb = hi ? xb_b : xa_b;
+              const float xwv = hi ? xb_w : xa_w;
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (n == 0 || ny == 0) {
+              } else if (near && n <= 4 && ny <= 4) {
+                switch ((ny - 1) * 3 + max(n, 2) - 2) {        // zero-weight padding taps lie inside the tile as well
+                  case 0: a = tile_bin_fixed<1, 2>(rowa, wy, xb, xwv, src); break;
+                  case 1: a = tile_bin_fixed<1, 3>(rowa, wy, xb, xwv, src); break;
+                  case 2: a = tile_bin_fixed<1, 4>(rowa, wy, xb, xwv, src); break;
+                  case 3: a = tile_bin_fixed<2, 2>(rowa, wy, xb, xwv, src); break;
+                  case 4: a = tile_bin_fixed<2, 3>(rowa, wy, xb, xwv, src); break;
+                  case 5: a = tile_bin_fixed<2, 4>(rowa, wy, xb, xwv, src); break;
+                  case 6: a = tile_bin_fixed<3, 2>(rowa, wy, xb, xwv, src); break;
+                  case 7: a = tile_bin_fixed<3, 3>(rowa, wy, xb, xwv, src); break;
+                  case 8: a = tile_bin_fixed<3, 4>(rowa, wy, xb, xwv, src); break;
+                  case 9: a = tile_bin_fixed<4, 2>(rowa, wy, xb, xwv, src); break;
+                  case 10: a = tile_bin_fixed<4, 3>(rowa, wy, xb, xwv, src); break;
+                  default: a = tile_bin_fixed<4, 4>(rowa, wy, xb, xwv, src); break;
+                }
+              } else if (near) {
+                a = tile_bin_any<true>(n, xb, xwv, src, yr, yw, ysrc, ny, tile_lane, f_lane, tx0, ty0, W);
+              } else {
+                a = tile_bin_any<false>(n, xb, xwv, src, yr, yw, ysrc, ny, tile_lane, f_lane, tx0, ty0, W);
+              }
+              const float4 o = make_float4(a.x * inv_count, a.y * inv_count, a.z * inv_count, a.w * inv_count);
+              *reinterpret_cast<float4*>(out + (size_t)bx * bin_stride) = o;
+            }
           }
         }
       }
-      base = next_base;
-      if (base < cnt || c + 1 < P.C) __syncthreads();      // the lists are rewritten by the next pass
+      if (base + kScan < cnt || c + 1 < P.C) __syncthreads();      // the list is rewritten by the next pass
     }
   }
   if (!waited) tc::mbar_wait(bar, 0);        // nothing started here: the copy must still land before the CTA's memory is released
