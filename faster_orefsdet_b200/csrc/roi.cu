@@ -386,6 +386,33 @@ struct Params {
 };
 }  // namespace rt
 
+// The same list without indexed local arrays: a bin's distinct rows / columns are CONSECUTIVE (the sampling step
+// bin / grid is at most one pixel and the clamped ends repeat the border index), so entry q is index first + q and a
+// sample adds its two weights to the slots lo - first and hi - first - the same additions in the same order as
+// build_axis_taps (the pooling tests compare the two bit for bit), but w[] stays in registers.
+__device__ __forceinline__ int build_axis_taps_reg(const BoxGeom& g, bool is_x, int bin, int& first, float (&w)[kMaxTaps]) {
+  int n = 0;
+  first = 0;
+#pragma unroll
+  for (int q = 0; q < kMaxTaps; ++q) w[q] = 0.f;
+  const int grid = is_x ? g.grid_w : g.grid_h, size = is_x ? g.W : g.H;
+  const float start = is_x ? g.start_w : g.start_h, bsz = is_x ? g.bin_w : g.bin_h;
+  for (int i = 0; i < grid; ++i) {
+    const AxisSample s = axis_sample(start, bsz, bin, i, grid, size);
+    if (s.w_lo == 0.f && s.w_hi == 0.f) continue;
+    if (n == 0) first = s.lo;
+    const int dlo = s.lo - first, dhi = s.hi - first;
+#pragma unroll
+    for (int q = 0; q < kMaxTaps; ++q)
+      if (q == dlo) w[q] += s.w_lo;
+#pragma unroll
+    for (int q = 0; q < kMaxTaps; ++q)
+      if (q == dhi) w[q] += s.w_hi;
+    n = max(n, dhi + 1);
+  }
+  return n;
+}
+
 // One thread per (ROI, axis, bin), 16 threads per ROI.  Tabled ROIs get a RoiTile; a ROI whose sampling grid is beyond
 // the tables gets the per-ROI kernel's blob header and an entry in the slow list.  Every ROI gets a RoiSum.
 __global__ void __launch_bounds__(256) roi_tile_tables_kernel(RoiParams prm, const float* __restrict__ rois,
@@ -405,10 +432,10 @@ __global__ void __launch_bounds__(256) roi_tile_tables_kernel(RoiParams prm, con
   const bool tables = g.grid_h <= kMaxGrid && g.grid_w <= kMaxGrid;
   const bool is_x = k < R;
   const int bin = k & 7;
-  int idx[kMaxTaps];
+  int first = 0;
   float w[kMaxTaps];
   int n = 0;
-  if (valid && tables) n = build_axis_taps(g, is_x, bin, idx, w);
+  if (valid && tables) n = build_axis_taps_reg(g, is_x, bin, first, w);
   int nx = is_x ? n : 0;
   uint32_t yn = is_x ? 0u : ((uint32_t)n << (4 * bin));
 #pragma unroll
@@ -437,17 +464,19 @@ __global__ void __launch_bounds__(256) roi_tile_tables_kernel(RoiParams prm, con
       slow_list[1 + atomicAdd(slow_list, 1)] = (int32_t)row;
     }
   }
-  (is_x ? S.x0 : S.y0)[bin] = (short)(n ? idx[0] : 0);
+  (is_x ? S.x0 : S.y0)[bin] = (short)first;
   if (!tables) return;
   RoiTile& T = tiles[row];
-  int* pi = is_x ? T.xi[bin] : T.yi[bin];
-  float* pw = is_x ? T.xw[bin] : T.yw[bin];
-  const int last = n ? idx[n - 1] : 0;
+  int4* pi = reinterpret_cast<int4*>(is_x ? T.xi[bin] : T.yi[bin]);
+  float4* pw = reinterpret_cast<float4*>(is_x ? T.xw[bin] : T.yw[bin]);
+  const int last = n ? first + n - 1 : 0;
+  int iv[kMaxTaps];
 #pragma unroll
-  for (int q = 0; q < kMaxTaps; ++q) {
-    pi[q] = q < n ? idx[q] : last;
-    pw[q] = q < n ? w[q] : 0.f;
-  }
+  for (int q = 0; q < kMaxTaps; ++q) iv[q] = min(first + q, last);      // w[q] is 0 for q >= n by construction
+  pi[0] = make_int4(iv[0], iv[1], iv[2], iv[3]);
+  pi[1] = make_int4(iv[4], iv[5], iv[6], iv[7]);
+  pw[0] = make_float4(w[0], w[1], w[2], w[3]);
+  pw[1] = make_float4(w[4], w[5], w[6], w[7]);
 }
 
 // One bin out of the staged tile with compile-time tap counts: NX column taps (fetched from the lanes that hold the

@@ -1,5 +1,3 @@
 set -x
-python bench.py > gpurun_out/r3_bench.json 2> gpurun_out/r3_bench.err; echo rc=$?
-tail -c 400 gpurun_out/r3_bench.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r3_bench_ref.json 2> gpurun_out/r3_bench_ref.err; echo rc=$?
-tail -c 300 gpurun_out/r3_bench_ref.json
+python -m pytest tests/test_ops_gpu.py tests/test_guards_gpu.py -x -q -m gpu -k "roi_align or relation_head or guard" 2>&1 | tail -5
+python tools/bench_roi.py 2>&1 | tail -5
