@@ -575,7 +575,7 @@ roi_align_tiles_kernel(const __grid_constant__ rt::Params P, const int32_t* __re
       __syncthreads();                       // also orders the barrier initialisation before its first use
       {                                      // scan: which bins of ROI base + tid start inside this tile
         const int r = base + tid;
-        if (r < cnt) {
+        if (tid < kScan && r < cnt) {
           const int4* sp = reinterpret_cast<const int4*>(sums + ((size_t)p * P.roi_cap + r));
           const int4 m = __ldg(sp + 2);      // level | nx, tables | pad, yn, inv_count
           const int level = (short)(m.x & 0xffff), tabled = (short)(m.y & 0xffff);
