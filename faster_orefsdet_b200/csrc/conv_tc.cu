@@ -136,6 +136,7 @@ struct Params {
   int n_groups, n_group, nhalf, ncol32, cout;
   int relu, num_pairs, pair_units, n_amax, ho, wo, cin;
   int x_amax_stride;    // 0: x_amax holds n_amax scalars (one scale for the whole batch); N: x_amax is [n_amax][N], the scale
+  int x_presplit;       // x already holds [32 x fp16 hi | 32 x fp16 lo] of x * 2^e per 32 channels (e from x_amax): no conversion pass
                         // of image n comes from column n, so an image's result does not depend on its batch mates
   int y_amax_per_image; // y_amax is [N]: max|y| per image
   uint32_t q_stage_bytes, q_stage_stride;
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
         if (!per_tap) {
           mbar_wait(q_full(qs), (gq / kQStages) & 1);
-          if (!direct) convert_stage(qt);
+          if (!direct && !P.x_presplit) convert_stage(qt);
         }
         int dy = 0, dx = 0;
         for (int tap = 0; tap < taps; ++tap, ++g) {
@@ -879,6 +880,9 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   prm.n_amax = n_amax;
   prm.y_amax = y_amax;
   prm.x_amax_stride = (amax_per_image & 1) ? n : 0;
+  prm.x_presplit = (amax_per_image & 4) ? 1 : 0;
+  FOD_REQUIRE(!prm.x_presplit || (ksize == 3 && stride == 1 && !a_gate && !a_shift && cin % 32 == 0 && x_pixel_stride % 32 == 0),
+              "fod_conv2d_nhwc: a pre-split input needs a 3x3 stride-1 convolution over whole 32-channel groups without a_gate / a_shift");
   prm.y_amax_per_image = (amax_per_image & 2) ? 1 : 0;
   prm.ho = ho;
   prm.wo = wo;

@@ -64,6 +64,7 @@ struct Params {
   const float* w_inv;    // 1 / weight scale (tail of the packed buffer)
   float* y_amax;         // null, [1] or [N]
   int y_amax_per_image;
+  const float* y_bound;   // split output: device float >= max(y); y is written as [32 x fp16 hi | 32 x fp16 lo] of y * 2^e per 32 channels
   int H, W, ho, wo;
   int tiles_x, tiles_per_img, tiles_total;
   int std_one;
@@ -72,6 +73,12 @@ struct Params {
 };
 
 // (a, b) -> packed fp16 pair of the rounded values (a in the low half) and of the exact remainders
+// conv_tc.cu's pow2_scale: 2^e with amax * 2^e in [2^13, 2^14); the consumer derives the same scale from the same bound
+__device__ __forceinline__ float pow2_scale_of(float amax) {
+  const int E = (int)((__float_as_uint(amax) >> 23) & 0xFF);
+  return (E < 32 || E > 240) ? 1.f : __uint_as_float((uint32_t)(267 - E) << 23);
+}
+
 __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
@@ -269,6 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) stem1_tc_kernel(const __grid_cons
     const uint32_t box0 = sbase + kOffStage + (uint32_t)ew * 2u * kBoxBytes;            // this warp's two staging boxes
     const uint32_t row0 = box0 + (uint32_t)((lane >> 3) * 1024 + (lane & 7) * 128);   // this lane's pixel row
     const float rescale = P.xs_inv * __ldg(P.w_inv);   // undoes the two power-of-two operand scales (exact)
+    const float ysplit = P.y_bound ? pow2_scale_of(__ldg(P.y_bound)) : 0.f;
     float bias[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) bias[j] = P.bias ? __ldg(P.bias + half * 32 + j) : 0.f;
@@ -305,15 +313,36 @@ __global__ void __launch_bounds__(kThreads, 1) stem1_tc_kernel(const __grid_cons
       __syncwarp();
       const uint32_t row_s = row0 + (uint32_t)(i & 1) * kBoxBytes;
       float lmax = 0.f;
+      if (ysplit != 0.f) {
+        // the consumer's operand format (conv_tc.cu, converters phase A): chunk c = fp16 hi of channels [8c, 8c + 8),
+        // chunk 4 + c = the exact remainders, of y * 2^e
 #pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        float4 o;
-        o.x = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 0]), rescale, bias[c4 * 4 + 0]), 0.f);
-        o.y = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 1]), rescale, bias[c4 * 4 + 1]), 0.f);
-        o.z = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 2]), rescale, bias[c4 * 4 + 2]), 0.f);
-        o.w = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 3]), rescale, bias[c4 * 4 + 3]), 0.f);
-        lmax = fmaxf(fmaxf(lmax, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
-        sts4s(row_s + (uint32_t)((c4 ^ (lane & 7)) << 4), o);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = c * 8 + q * 2;
+            const float a = fmaxf(fmaf(__uint_as_float(v[j]), rescale, bias[j]), 0.f);
+            const float b = fmaxf(fmaf(__uint_as_float(v[j + 1]), rescale, bias[j + 1]), 0.f);
+            lmax = fmaxf(lmax, fmaxf(a, b));
+            split_f16x2(a * ysplit, b * ysplit, hi[q], lo[q]);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_s + (uint32_t)((c ^ (lane & 7)) << 4)), "r"(hi[0]),
+                       "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_s + (uint32_t)(((4 + c) ^ (lane & 7)) << 4)), "r"(lo[0]),
+                       "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          float4 o;
+          o.x = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 0]), rescale, bias[c4 * 4 + 0]), 0.f);
+          o.y = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 1]), rescale, bias[c4 * 4 + 1]), 0.f);
+          o.z = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 2]), rescale, bias[c4 * 4 + 2]), 0.f);
+          o.w = fmaxf(fmaf(__uint_as_float(v[c4 * 4 + 3]), rescale, bias[c4 * 4 + 3]), 0.f);
+          lmax = fmaxf(fmaxf(lmax, fmaxf(o.x, o.y)), fmaxf(o.z, o.w));
+          sts4s(row_s + (uint32_t)((c4 ^ (lane & 7)) << 4), o);
+        }
       }
       if (px_valid) vmax = fmaxf(vmax, lmax);
       fence_proxy_async_smem();
@@ -338,9 +367,9 @@ __global__ void __launch_bounds__(kThreads, 1) stem1_tc_kernel(const __grid_cons
 
 using namespace fod;
 
-extern "C" int fod_stem1_u8_tc(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3,
-                               const float* packed, const float* bias, float* y, long y_pixel_stride, float* y_amax,
-                               int amax_per_image, fod_stream_t stream) {
+static int stem1_u8_tc_impl(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3,
+                            const float* packed, const float* bias, float* y, long y_pixel_stride, float* y_amax,
+                            int amax_per_image, const float* y_bound, fod_stream_t stream) {
   FOD_REQUIRE(x && mean3 && std3 && packed && y, "fod_stem1_u8_tc: null pointer");
   FOD_REQUIRE(n >= 0 && h > 0 && w > 0, "fod_stem1_u8_tc: bad sizes");
   FOD_REQUIRE(y_pixel_stride >= s1tc::kCout && y_pixel_stride % 4 == 0, "fod_stem1_u8_tc: bad output pixel stride");
@@ -370,6 +399,7 @@ extern "C" int fod_stem1_u8_tc(const uint8_t* x, int n, int h, int w, const floa
   prm.bias = bias;
   prm.y_amax = y_amax;
   prm.y_amax_per_image = amax_per_image ? 1 : 0;
+  prm.y_bound = y_bound;
   prm.H = h;
   prm.W = w;
   prm.ho = (h - 1) / 2 + 1;
@@ -395,4 +425,17 @@ extern "C" int fod_stem1_u8_tc(const uint8_t* x, int n, int h, int w, const floa
   s1tc::stem1_tc_kernel<<<grid, s1tc::kThreads, s1tc::kSmemAlloc, as_stream(stream)>>>(prm);
   FOD_CUDA_LAUNCH_CHECK("fod_stem1_u8_tc");
   return FOD_OK;
+}
+
+extern "C" int fod_stem1_u8_tc(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3,
+                               const float* packed, const float* bias, float* y, long y_pixel_stride, float* y_amax,
+                               int amax_per_image, fod_stream_t stream) {
+  return stem1_u8_tc_impl(x, n, h, w, mean3, std3, packed, bias, y, y_pixel_stride, y_amax, amax_per_image, nullptr, stream);
+}
+
+extern "C" int fod_stem1_u8_tc_split(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3,
+                                     const float* packed, const float* bias, float* y, long y_pixel_stride, float* y_amax,
+                                     int amax_per_image, const float* y_bound, fod_stream_t stream) {
+  FOD_REQUIRE(y_bound, "fod_stem1_u8_tc_split: y_bound is required");
+  return stem1_u8_tc_impl(x, n, h, w, mean3, std3, packed, bias, y, y_pixel_stride, y_amax, amax_per_image, y_bound, stream);
 }

@@ -258,6 +258,24 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
         return hit[1], hit[2]
 
     STEM1_TENSOR_CORES = True     # stem_1 of uint8 input: csrc/stem1_tc.cu (False: the FP32 FMA kernel, ops.stem1_u8)
+    STEM1_SPLIT_OUTPUT = True     # ... writing stem_2's operand format (fod_stem1_u8_tc_split) instead of fp32
+
+    def _stem1_bound(self, mean, std):
+        """One device float >= every output of stem_1 (ReLU of the folded convolution) for ANY uint8 image: the absolute
+        row sums of the folded weight times the largest normalised pixel magnitude per colour plane, plus |bias|."""
+        conv, norm = self.stem[0], self.stem[1]
+        key = (tcconv._versions(conv.weight, *norm.buffers()), tuple(mean), tuple(std))
+        hit = getattr(self, "_stem1_bound_cache", None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                w, b = self._stem1_folded()
+                xmax = torch.tensor([max(abs(0.0 - m), abs(255.0 - m)) / abs(sd) for m, sd in zip(mean, std)],
+                                    dtype=torch.float64, device=w.device)
+                rows = (w.double().abs().sum((2, 3)) * xmax.view(1, 3)).sum(1) + (b.double().abs() if b is not None else 0.0)
+                bound = (rows.max() * 1.001).clamp_min(1e-30).float().reshape(1).contiguous()
+            hit = (key, bound)
+            self._stem1_bound_cache = hit
+        return hit[1]
 
     def tc_stem_u8(self, x_u8, mean, std, out, out_amax):
         """Raw uint8 images -> stem_1 (normalisation fused; tensor-core kernel ops.stem1_u8_tc, the im2col gathered into
@@ -266,6 +284,16 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
             return self.tc_stem(ops.stem_patches_u8(x_u8, mean, std), None, out, out_amax)
         n = x_u8.shape[0]
         a1, a2 = ops.new_amax(x_u8.device, n), ops.new_amax(x_u8.device, n)          # per image
+        if self.STEM1_TENSOR_CORES and self.STEM1_SPLIT_OUTPUT:
+            # stem_1 writes the operand format of stem_2 (fp16 hi / lo of y * 2^e) instead of fp32: its output bound follows
+            # from the weights and the pixel range alone, so the scale is known before the layer runs and stem_2 skips
+            # the conversion pass of every staged tile
+            pk, b = self._stem1_packed()
+            bound = self._stem1_bound(mean, std)
+            y = ops.stem1_u8_tc(x_u8, mean, std, pk, b, y_bound=bound)
+            y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=bound, y_amax=a2, x_presplit=True)
+            tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2.view(1, n), y_amax=out_amax)
+            return
         if self.STEM1_TENSOR_CORES:
             pk, b = self._stem1_packed()
             y = ops.stem1_u8_tc(x_u8, mean, std, pk, b, y_amax=a1)

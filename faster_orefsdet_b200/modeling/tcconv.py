@@ -76,13 +76,13 @@ def conv(x: torch.Tensor, m: nn.Conv2d, norm: Optional[nn.Module] = None, relu: 
          y_amax: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          residual_upsample2: bool = False, a_gate: Optional[torch.Tensor] = None,
          colsum: Optional[torch.Tensor] = None, a_shift: Optional[torch.Tensor] = None, a_relu: bool = False,
-         colsumsq: Optional[torch.Tensor] = None) -> torch.Tensor:
+         colsumsq: Optional[torch.Tensor] = None, x_presplit: bool = False) -> torch.Tensor:
     """conv (+ folded frozen BN) (+ ReLU) of an NHWC CUDA view; returns [N, Cout_padded_to_4, H, W] (NHWC memory).
     ``x_amax`` / ``y_amax``: device scalars bounding max|x| (computed when omitted) / receiving max|y| (ops.conv2d_nhwc)."""
     pk, b, cout = packed(m, norm, extra)
     return ops.conv2d_nhwc(x, pk, b, cout, m.kernel_size[0], relu, out=out, stride=m.stride[0], x_amax=x_amax, y_amax=y_amax,
                            residual=residual, residual_upsample2=residual_upsample2, a_gate=a_gate, colsum=colsum,
-                           a_shift=a_shift, a_relu=a_relu, colsumsq=colsumsq)
+                           a_shift=a_shift, a_relu=a_relu, colsumsq=colsumsq, x_presplit=x_presplit)
 
 
 def conv_reference(x: torch.Tensor, m: nn.Conv2d, norm: Optional[nn.Module] = None, relu: bool = False) -> torch.Tensor:

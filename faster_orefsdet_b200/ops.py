@@ -478,9 +478,11 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
                 out: Optional[Tensor] = None, stride: int = 1, x_amax: Optional[Tensor] = None,
                 y_amax: Optional[Tensor] = None, residual: Optional[Tensor] = None, residual_upsample2: bool = False,
                 a_gate: Optional[Tensor] = None, colsum: Optional[Tensor] = None, a_shift: Optional[Tensor] = None,
-                a_relu: bool = False, colsumsq: Optional[Tensor] = None) -> Tensor:
+                a_relu: bool = False, colsumsq: Optional[Tensor] = None, x_presplit: bool = False) -> Tensor:
     """Convolution with padding ksize//2 on the tensor cores (fp16-split operands, fp32 accuracy), bias + optional
-    ReLU fused.  x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise.
+    ReLU fused.  ``x_presplit``: x is not fp32 but the kernel's own operand format, written by a producer that was given
+    the bound in ``x_amax`` (stem1_u8_tc(y_bound=...)): per pixel and 32 channels [32 x fp16 hi | 32 x fp16 lo] of
+    x * 2^e - the 3x3 layer then skips its conversion pass.  x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise.
     ``x_amax``: device floats bounding max|x|: [k] (k = 1..8 values, one scale for the batch; computed with ``absmax`` when
     omitted, which needs a dense x) or [k, N] (image n is scaled by the maximum of column n: its result does not depend
     on its batch mates); ``y_amax``: zeroed device floats that receive max|y|: [1], or [N] for one bound per image."""
@@ -524,7 +526,7 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
             _chk(cs, torch.float32, name)
             if tuple(cs.shape) != (n, conv2d_tiles_per_image(ho, wo), cout) or not cs.is_contiguous():
                 raise _lib.FodError(f"conv2d_nhwc: bad {name} buffer")
-    _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(x_amax), int(n_amax), int(x_pi) | (int(y_pi) << 1),
+    _lib.check(_lib.lib().fod_conv2d_nhwc(_ptr(x), n, h, w, cin, ps_x, _ptr(x_amax), int(n_amax), int(x_pi) | (int(y_pi) << 1) | (int(bool(x_presplit)) << 2),
                                           _ptr(packed), _ptr(bias),
                                           cout, ksize, int(stride), int(relu), _ptr(out), ps_y, _ptr(y_amax), _ptr(residual),
                                           int(residual_upsample2), _ptr(a_gate), _ptr(a_shift), int(a_relu), _ptr(colsum),
@@ -640,9 +642,11 @@ def stem1_u8(x: Tensor, mean: Sequence[float], std: Sequence[float], weight: Ten
 
 
 def stem1_u8_tc(x: Tensor, mean: Sequence[float], std: Sequence[float], packed: Tensor, bias: Optional[Tensor],
-                y_amax: Optional[Tensor] = None) -> Tensor:
+                y_amax: Optional[Tensor] = None, y_bound: Optional[Tensor] = None) -> Tensor:
     """stem1_u8 on the tensor cores (fod_stem1_u8_tc): ``packed`` = conv2d_pack of the [64,32,1,1] im2col matrix with
-    columns (ky*3 + kx)*3 + c (27..31 zero)."""
+    columns (ky*3 + kx)*3 + c (27..31 zero).  With ``y_bound`` (one device float >= every output, e.g. from the weights'
+    absolute row sums and the pixel range) the output is written in the operand format of the next 3x3 convolution
+    (conv2d_nhwc(..., x_amax=y_bound, x_presplit=True)) instead of fp32: same bytes, no conversion pass downstream."""
     _chk(x, torch.uint8, "x")
     if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
         raise _lib.FodError("stem1_u8_tc: contiguous [N,3,H,W] uint8 expected")
@@ -660,6 +664,13 @@ def stem1_u8_tc(x: Tensor, mean: Sequence[float], std: Sequence[float], packed: 
     if y_amax is not None and y_amax.numel() not in (1, n):
         raise _lib.FodError("stem1_u8_tc: y_amax must hold 1 or N floats")
     per_image = y_amax is not None and y_amax.numel() == n and n > 1
+    if y_bound is not None:
+        _chk(y_bound, torch.float32, "y_bound")
+        if y_bound.numel() != 1:
+            raise _lib.FodError("stem1_u8_tc: y_bound must hold one float")
+        _lib.check(_lib.lib().fod_stem1_u8_tc_split(_ptr(x), n, h, w, m3, s3, _ptr(packed), _ptr(bias), _ptr(out), 64, _ptr(y_amax),
+                                                    int(per_image), _ptr(y_bound), _stream()), "fod_stem1_u8_tc_split")
+        return out
     _lib.check(_lib.lib().fod_stem1_u8_tc(_ptr(x), n, h, w, m3, s3, _ptr(packed), _ptr(bias), _ptr(out), 64, _ptr(y_amax),
                                           int(per_image), _stream()), "fod_stem1_u8_tc")
     return out

@@ -284,6 +284,8 @@ int fod_batched_nms(const float* boxes, const float* scores, const int64_t* idxs
  *             produced x normally reports it (y_amax below).
  *   amax_per_image : bit 0: x_amax is [n_amax][N] and image n is scaled by the maximum of column n, so that the result of
  *             an image does not depend on which other images share the batch; bit 1: y_amax is [N], max|y| per image
+ *               bit 2: x is PRE-SPLIT (written by fod_stem1_u8_tc_split with y_bound = this x_amax): per pixel and 32 channels
+ *               [32 x fp16 hi | 32 x fp16 lo] of x * 2^e; 3x3 stride-1 layers only, no a_gate / a_shift; the conversion pass is skipped
  *   packed  : fod_conv2d_pack_weights output (fod_conv2d_packed_floats floats)
  *   bias    : [cout] or NULL
  *   y       : [N][Ho][Wo] pixels of y_pixel_stride floats, the first cout are written
@@ -370,6 +372,19 @@ int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* mean3, cons
  *   y      : [N][ceil(H/2)][ceil(W/2)][y_pixel_stride >= 64] NHWC; y_amax as in fod_stem1_u8 */
 int fod_stem1_u8_tc(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, const float* packed,
                     const float* bias, float* y, long y_pixel_stride, float* y_amax, int amax_per_image, fod_stream_t stream);
+/* fod_stem1_u8_tc with the output written in the OPERAND FORMAT of the 3x3 convolution that reads it instead of fp32:
+ * per pixel and group of 32 channels 128 bytes = [32 x fp16 hi | 32 x fp16 lo] of y * 2^e (hi = fp16(y * 2^e), lo the
+ * exact remainder rounded to fp16), 2^e = the scale fod_conv2d_nhwc derives from a bound on max|y|.
+ *   y_bound : ONE device float >= every output value; it is known before the layer runs: the pixel range is
+ *             [0, 255], so max_c (sum_k |w[c][k]| * max(|0 - mean|, |255 - mean|) / std + |bias[c]|) holds for every image.
+ * The consumer is fod_conv2d_nhwc(x = y, x_amax = y_bound, n_amax = 1, amax_per_image bit 2 set): it skips the in-place
+ * conversion pass of every staged tile (and the barrier behind it).  Same bytes in HBM, same accuracy class (22
+ * significant bits relative to the bound), results independent of the batch (the scale depends on weights only).
+ * y_amax still receives max(y) of the fp32 values. */
+int fod_stem1_u8_tc_split(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, const float* packed,
+                          const float* bias, float* y, long y_pixel_stride, float* y_amax, int amax_per_image,
+                          const float* y_bound, fod_stream_t stream);
+
 int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate, float* y,
                           long y_pixel_stride, fod_stream_t stream);
 

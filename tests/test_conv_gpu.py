@@ -182,6 +182,42 @@ def test_stem1_u8_tensor_cores_match_normalise_then_conv(std, hw):
     assert torch.equal(y, ops.stem1_u8_tc(x.to(DEV), mean, std, pk, b.to(DEV)))
 
 
+@pytest.mark.parametrize("std,hw", [([1.0, 1.0, 1.0], (70, 90)), ([57.375, 57.12, 58.395], (129, 93)), ([57.375, 57.12, 58.395], (320, 320))])
+def test_stem1_split_output_feeds_the_next_convolution_without_conversion(std, hw):
+    """stem_1 writing the operand format of stem_2 (fp16 hi / lo of y * 2^e, the scale from a weights-only bound) and
+    stem_2 reading it pre-split: against float64 of the two layers, against the fp32 hand-off, per-image max(y) kept."""
+    h, w_ = hw
+    n = 2
+    x = (synth.tensor((n, 3, h, w_), 181, 0.0, 255.99)).to(torch.uint8)
+    mean = [103.53, 116.28, 123.675]
+    w1 = synth.tensor((64, 3, 3, 3), 182, -0.3, 0.3)
+    b1 = synth.tensor((64,), 183, -1.0, 1.0)
+    w2 = synth.tensor((64, 64, 3, 3), 184, -0.08, 0.08)
+    b2 = synth.tensor((64,), 185, -0.5, 0.5)
+    xn = (x.double() - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    r1 = F.conv2d(xn, w1.double(), b1.double(), stride=2, padding=1).relu()
+    ref = F.conv2d(r1, w2.double(), b2.double(), padding=1).relu().float()
+    w32 = torch.cat((w1.permute(0, 2, 3, 1).reshape(64, 27), torch.zeros(64, 5)), 1).reshape(64, 32, 1, 1).contiguous()
+    pk1, pk2 = ops.conv2d_pack(w32.to(DEV)), ops.conv2d_pack(w2.to(DEV))
+    xmax = torch.tensor([max(abs(0.0 - m), abs(255.0 - m)) / sd for m, sd in zip(mean, std)], dtype=torch.float64)
+    bound = (((w1.double().abs().sum((2, 3)) * xmax.view(1, 3)).sum(1) + b1.double().abs()).max() * 1.001).float().reshape(1).to(DEV)
+    assert float(bound) >= float(r1.max())
+    a1 = ops.new_amax(DEV, n)
+    y1 = ops.stem1_u8_tc(x.to(DEV), mean, std, pk1, b1.to(DEV), y_amax=a1, y_bound=bound)
+    for i in range(n):
+        assert abs(float(a1.view(-1)[i]) - float(r1[i].max())) <= 1e-5 * float(r1[i].max())
+    y2 = ops.conv2d_nhwc(y1, pk2, b2.to(DEV), 64, 3, True, x_amax=bound, x_presplit=True)
+    _check(y2, ref, "stem_2 on a pre-split stem_1")
+    # the fp32 hand-off of the same two layers
+    a1f = ops.new_amax(DEV, n)
+    y1f = ops.stem1_u8_tc(x.to(DEV), mean, std, pk1, b1.to(DEV), y_amax=a1f)
+    y2f = ops.conv2d_nhwc(y1f, pk2, b2.to(DEV), 64, 3, True, x_amax=a1f.view(1, n))
+    assert float((y2 - y2f).abs().max()) <= 2e-6 * float(y2f.abs().max())
+    # every image alone gives the same bits (the scale does not depend on the data)
+    y1s = ops.stem1_u8_tc(x[1:].to(DEV), mean, std, pk1, b1.to(DEV), y_bound=bound)
+    assert torch.equal(ops.conv2d_nhwc(y1s, pk2, b2.to(DEV), 64, 3, True, x_amax=bound, x_presplit=True)[0], y2[1])
+
+
 @pytest.mark.parametrize("up2", [False, True])
 def test_conv2d_nhwc_residual_in_epilogue(up2):
     """FPN top-down step: lateral 1x1 + (nearest 2x upsampled) coarser map, fused into the convolution's epilogue."""
