@@ -202,10 +202,10 @@ class KernelTimer:
                 r = __fn(*a, **k)
                 e.record()
                 tag = None
-                if __n == "conv2d_nhwc":      # (N, H, W, Cin, Cout, ksize, stride) of this layer
+                if __n in ("conv2d_nhwc", "conv2d_nhwc_split"):      # (N, H, W, Cin, Cout, ksize, stride) of this layer
                     x = a[0]
                     tag = (x.shape[0], x.shape[2], x.shape[3], x.shape[1], int(a[3]), int(a[4]), int(k.get("stride", 1)))
-                self.records.setdefault({"decode_topk_taps": "decode_topk"}.get(__n, __n), []).append((s, e, tag))
+                self.records.setdefault({"decode_topk_taps": "decode_topk", "conv2d_nhwc_split": "conv2d_nhwc"}.get(__n, __n), []).append((s, e, tag))
                 self.launches += self.kernels_per_call.get(__n, 1)
                 return r
             setattr(ops_mod, n, timed)
@@ -296,7 +296,7 @@ def run_gpu_arm(args):
     sizes = [(IMG, IMG)] * B
     timer = KernelTimer()
     timer.wrap(ops, ["correlate_levels", "decode_topk", "decode_topk_taps", "group_norm_affine", "nms_proposals", "roi_align", "relation_head", "final_detect",
-                     "conv2d_nhwc", "group_norm_nhwc", "stem_patches", "stem_patches_u8", "stem1_u8", "stem1_u8_tc", "maxpool3x3s2_nhwc", "ese_gate"])
+                     "conv2d_nhwc", "conv2d_nhwc_split", "group_norm_nhwc", "stem_patches", "stem_patches_u8", "stem1_u8", "stem1_u8_tc", "maxpool3x3s2_nhwc", "ese_gate"])
 
     def step_resident(i):      # raw uint8 images resident in HBM -> padded detections on the device
         return model.detect_from_uint8(dev_sets[i % NSETS], sizes, sizes)

@@ -64,6 +64,8 @@ _PROTOTYPES = {
     "fod_stem_patches": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "fod_stem_patches_u8": ([_vp, _i, _i, _i, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _vp], _i),
     "fod_stem1_u8_tc": ([_vp, _i, _i, _i, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _vp, _vp, ctypes.c_long, _vp, _i, _vp], _i),
+    "fod_conv2d_nhwc_split": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_long, _vp, _vp,
+                               _vp, _vp, _f, _f, _i, ctypes.POINTER(_i), _vp], _i),
     "fod_stem1_u8_tc_split": ([_vp, _i, _i, _i, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _vp, _vp, ctypes.c_long, _vp, _i, _vp,
                                _vp], _i),
     "fod_stem1_u8": ([_vp, _i, _i, _i, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _vp, _vp, _vp, _i, _vp], _i),

@@ -139,6 +139,14 @@ struct Params {
   int x_presplit;       // x already holds [32 x fp16 hi | 32 x fp16 lo] of x * 2^e per 32 channels (e from x_amax): no conversion pass
                         // of image n comes from column n, so an image's result does not depend on its batch mates
   int y_amax_per_image; // y_amax is [N]: max|y| per image
+  // Split hand-off between convolutions (the producer writes the consumer's operand format; same bytes as fp32):
+  const float* x_actual;   // null or [N] / [1] like x_amax: the ACTUAL max|x| (x_amax may be the looser bound that fixed the scale
+                           // of a pre-split x); only used for the output bound below
+  float* y_bound;          // null or [N] / [1]: y is written as [32 x fp16 hi | 32 x fp16 lo] of y * 2^e per pixel and 32 channels,
+                           // 2^e = pow2_scale(y_l1 * max|x| + y_beta); that bound is published here for the consumer
+  float y_l1, y_beta;      // max_c sum|w[c]| and max|bias| (host constants of the layer)
+  int x_presplit_from;     // single-tap path: input channels >= this are pre-split, each slice at the scale of ITS x_amax row
+  int slice_ch[8];         // first channel of the slice that x_amax row k bounds
   uint32_t q_stage_bytes, q_stage_stride;
 };
 
@@ -164,11 +172,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   constexpr int stages = kStages;
   constexpr uint32_t acc_w = 128u, col_acc = kColAcc, b_stage = kBStageBytes;
   float xs = 1.f, xs_inv = 1.f;   // input scale 2^e (converters) and its inverse (epilogue)
+  float x_bound = 0.f;            // the bound xs was derived from
   auto image_scale = [&](int n) {   // (re)computes xs / xs_inv for image n (any n in the batch-wide mode)
     float amax = 0.f;
     const float* col = P.x_amax + (P.x_amax_stride ? n : 0);
     const int step = P.x_amax_stride ? P.x_amax_stride : 1;
     for (int i = 0; i < P.n_amax; ++i) amax = fmaxf(amax, __ldg(col + (size_t)i * step));
+    x_bound = amax;
     pow2_scale(amax, xs, xs_inv);
   };
   image_scale(0);
@@ -379,6 +389,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         image_scale(n);
         rescale = xs_inv * w_inv;
       }
+      float ysplit = 0.f;   // != 0: the final part leaves as fp16 hi / lo of y * ysplit
+      if (P.y_bound) {
+        const int bi = P.x_amax_stride ? n : 0;
+        const float yb = fmaf(P.y_l1, P.x_actual ? __ldg(P.x_actual + bi) : x_bound, P.y_beta);
+        float unused;
+        pow2_scale(yb, ysplit, unused);
+        if (issuer) P.y_bound[bi] = yb;   // every CTA that works on image n writes the same value
+      }
       const int oy = ty * kTileH + (m >> 4), ox = tx * kTileW + (m & 15);
       const bool px_valid = do_store && oy < P.ho && ox < P.wo;
       const float* res_px = nullptr;   // this pixel's row of the residual map
@@ -411,6 +429,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if (lane == 0) mbar_arrive_remote(acc_empty_leader + 8u * as_);
           }
           const uint32_t slab = row_s + (uint32_t)j * kSlabBytes;
+          if (ysplit != 0.f && part == parts - 1) {
+            // the consumer's operand format: all 32 channels of the row are formed first (the running sums sit where the
+            // packed chunks go), then chunk c = fp16 hi of channels [8c, 8c + 8), chunk 4 + c = the exact remainders
+            float4 xv[8];
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+              const uint32_t sa = slab + (uint32_t)((c4 ^ (m & 7)) << 4);
+              float4 x = make_float4(__uint_as_float(v[c4 * 4 + 0]) * comp, __uint_as_float(v[c4 * 4 + 1]) * comp,
+                                     __uint_as_float(v[c4 * 4 + 2]) * comp, __uint_as_float(v[c4 * 4 + 3]) * comp);
+              if (part > 0) {
+                const float4 r = lds4s(sa);
+                x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+              }
+              const float4 bb = lds4s(bias_s + (j * 32 + c4 * 4) * 4);
+              x.x = fmaf(x.x, rescale, bb.x); x.y = fmaf(x.y, rescale, bb.y);
+              x.z = fmaf(x.z, rescale, bb.z); x.w = fmaf(x.w, rescale, bb.w);
+              if (P.relu) {
+                x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+              }
+              if (P.y_amax && px_valid) {
+                const int cb = ch0 + j * 32 + c4 * 4;
+                if (cb + 0 < P.cout) vmax = fmaxf(vmax, fabsf(x.x));
+                if (cb + 1 < P.cout) vmax = fmaxf(vmax, fabsf(x.y));
+                if (cb + 2 < P.cout) vmax = fmaxf(vmax, fabsf(x.z));
+                if (cb + 3 < P.cout) vmax = fmaxf(vmax, fabsf(x.w));
+              }
+              xv[c4] = x;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t hi[4], lo[4];
+              split_f16x2(xv[2 * c].x * ysplit, xv[2 * c].y * ysplit, hi[0], lo[0]);
+              split_f16x2(xv[2 * c].z * ysplit, xv[2 * c].w * ysplit, hi[1], lo[1]);
+              split_f16x2(xv[2 * c + 1].x * ysplit, xv[2 * c + 1].y * ysplit, hi[2], lo[2]);
+              split_f16x2(xv[2 * c + 1].z * ysplit, xv[2 * c + 1].w * ysplit, hi[3], lo[3]);
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(slab + (uint32_t)((c ^ (m & 7)) << 4)), "r"(hi[0]), "r"(hi[1]),
+                           "r"(hi[2]), "r"(hi[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(slab + (uint32_t)(((4 + c) ^ (m & 7)) << 4)), "r"(lo[0]),
+                           "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+            }
+            continue;
+          }
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
             const uint32_t sa = slab + (uint32_t)((c4 ^ (m & 7)) << 4);
@@ -583,6 +643,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int cc = 0; cc < cin_chunks; ++cc) {
         if (P.a_gate) gate_row = P.a_gate + (size_t)unit_n * P.cin + cc * kChunk;
         if (P.a_shift) shift_row = P.a_shift + (size_t)unit_n * P.cin + cc * kChunk;
+        // single-tap path over a concat buffer whose later slices were written pre-split by their producers, each at the
+        // scale of its own bound: the stored halves are brought to this launch's common scale by an exact power of two
+        const bool pre = direct && cc * kChunk >= P.x_presplit_from;
+        __half2 pre_mult = __float2half2_rn(1.f);
+        if (pre) {
+          int k = P.n_amax - 1;
+          while (k > 0 && cc * kChunk < P.slice_ch[k]) --k;
+          const int step = P.x_amax_stride ? P.x_amax_stride : 1;
+          float sk, sk_inv;
+          pow2_scale(__ldg(P.x_amax + (size_t)k * step + (P.x_amax_stride ? unit_n : 0)), sk, sk_inv);
+          pre_mult = __float2half2_rn(xs * sk_inv);
+        }
         int qs = gq % kQStages;
         uint32_t qt = sbase + kOffQ + qs * P.q_stage_stride;
         if (!per_tap) {
@@ -602,7 +674,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t at = qt + (uint32_t)r * 128u;
             const uint32_t key = (uint32_t)(r & 7);
             uint32_t hi[8], lo[8];
-            if (direct) {
+            if (pre) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(hi[4 * j]), "=r"(hi[4 * j + 1]), "=r"(hi[4 * j + 2]), "=r"(hi[4 * j + 3])
+                             : "r"(at + ((((uint32_t)(2 * half + j)) ^ key) << 4)));
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(lo[4 * j]), "=r"(lo[4 * j + 1]), "=r"(lo[4 * j + 2]), "=r"(lo[4 * j + 3])
+                             : "r"(at + ((((uint32_t)(4 + 2 * half + j)) ^ key) << 4)));
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&hi[j]), pre_mult);
+                const __half2 l = __hmul2(*reinterpret_cast<const __half2*>(&lo[j]), pre_mult);
+                hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+            } else if (direct) {
               {   // image position of this pixel's input for this tap (a per-tap tile holds every stride-th pixel)
                 const int iy = in_y0 + (per_tap ? py * P.stride + dy : py), ix = in_x0 + (per_tap ? px * P.stride + dx : px);
                 row_in = iy >= 0 && iy < P.in_h && ix >= 0 && ix < P.in_w;
@@ -820,11 +909,12 @@ extern "C" int fod_conv2d_pack_weights(const float* w_oihw, int cout, int cin, i
   return FOD_OK;
 }
 
-extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax,
-                               int n_amax, int amax_per_image, const float* packed, const float* bias, int cout, int ksize, int stride,
-                               int relu, float* y, long y_pixel_stride, float* y_amax, const float* residual,
-                               int residual_upsample2, const float* a_gate, const float* a_shift, int a_relu, float* colsum,
-                               float* colsumsq, fod_stream_t stream) {
+static int conv2d_nhwc_impl(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax,
+                            int n_amax, int amax_per_image, const float* packed, const float* bias, int cout, int ksize, int stride,
+                            int relu, float* y, long y_pixel_stride, float* y_amax, const float* residual,
+                            int residual_upsample2, const float* a_gate, const float* a_shift, int a_relu, float* colsum,
+                            float* colsumsq, const float* x_actual, float* y_bound, float y_l1, float y_beta,
+                            int x_presplit_from, const int* slice_ch, fod_stream_t stream) {
   FOD_REQUIRE((((uintptr_t)a_gate | (uintptr_t)a_shift | (uintptr_t)colsum | (uintptr_t)colsumsq) & 15) == 0,
               "fod_conv2d_nhwc: a_gate / a_shift / colsum / colsumsq must be 16-byte aligned");
   FOD_REQUIRE((!a_gate && !a_shift) || cin % 32 == 0, "fod_conv2d_nhwc: a_gate / a_shift need cin to be a multiple of 32");
@@ -884,6 +974,17 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
   FOD_REQUIRE(!prm.x_presplit || (ksize == 3 && stride == 1 && !a_gate && !a_shift && cin % 32 == 0 && x_pixel_stride % 32 == 0),
               "fod_conv2d_nhwc: a pre-split input needs a 3x3 stride-1 convolution over whole 32-channel groups without a_gate / a_shift");
   prm.y_amax_per_image = (amax_per_image & 2) ? 1 : 0;
+  prm.x_actual = x_actual;
+  prm.y_bound = y_bound;
+  prm.y_l1 = y_l1;
+  prm.y_beta = y_beta;
+  prm.x_presplit_from = x_presplit_from >= 0 ? x_presplit_from : (1 << 30);
+  for (int k = 0; k < 8; ++k) prm.slice_ch[k] = (slice_ch && k < n_amax) ? slice_ch[k] : 0;
+  FOD_REQUIRE(!y_bound || (!residual && !colsum && cout % 32 == 0 && y_pixel_stride % 32 == 0 && relu),
+              "fod_conv2d_nhwc_split: a split output needs ReLU, whole 32-channel groups and no residual / colsum");
+  FOD_REQUIRE(x_presplit_from < 0 || (ksize == 1 && stride == 1 && slice_ch && x_presplit_from % 32 == 0 && cin % 32 == 0 &&
+                                      x_pixel_stride % 32 == 0 && !a_gate && !a_shift),
+              "fod_conv2d_nhwc_split: pre-split slices need a 1x1 convolution over whole 32-channel groups without a_gate / a_shift");
   prm.ho = ho;
   prm.wo = wo;
   prm.a_gate = a_gate;
@@ -939,4 +1040,24 @@ extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, lon
     return FOD_ERR_CUDA;
   }
   return FOD_OK;
+}
+
+extern "C" int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax,
+                               int n_amax, int amax_per_image, const float* packed, const float* bias, int cout, int ksize, int stride,
+                               int relu, float* y, long y_pixel_stride, float* y_amax, const float* residual,
+                               int residual_upsample2, const float* a_gate, const float* a_shift, int a_relu, float* colsum,
+                               float* colsumsq, fod_stream_t stream) {
+  return conv2d_nhwc_impl(x, n, h, w, cin, x_pixel_stride, x_amax, n_amax, amax_per_image, packed, bias, cout, ksize, stride, relu, y,
+                          y_pixel_stride, y_amax, residual, residual_upsample2, a_gate, a_shift, a_relu, colsum, colsumsq, nullptr,
+                          nullptr, 0.f, 0.f, -1, nullptr, stream);
+}
+
+extern "C" int fod_conv2d_nhwc_split(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax,
+                                     int n_amax, int amax_per_image, const float* packed, const float* bias, int cout, int ksize,
+                                     int stride, int relu, float* y, long y_pixel_stride, float* y_amax, float* colsum,
+                                     const float* x_actual, float* y_bound, float y_l1, float y_beta, int x_presplit_from,
+                                     const int* slice_ch, fod_stream_t stream) {
+  return conv2d_nhwc_impl(x, n, h, w, cin, x_pixel_stride, x_amax, n_amax, amax_per_image, packed, bias, cout, ksize, stride, relu, y,
+                          y_pixel_stride, y_amax, nullptr, 0, nullptr, nullptr, 0, colsum, nullptr, x_actual, y_bound, y_l1, y_beta,
+                          x_presplit_from, slice_ch, stream);
 }

@@ -128,7 +128,7 @@ class _OSAModule(nn.Module):
     def forward(self, x):
         if not self.training and all(tcconv.supported(layer[0], x) for layer in self.layers):
             buf, amax = self._layers_in_place(x)
-            y = self.ese(tcconv.conv(buf, self.concat[0], self.concat[1], relu=True, x_amax=amax))
+            y = self.ese(tcconv.conv(buf, self.concat[0], self.concat[1], relu=True, x_amax=amax[:len(self.layers) + 1]))
             return y + x if self.identity else y
         outs = [x]
         y = x
@@ -147,7 +147,8 @@ class _OSAModule(nn.Module):
         max|.| per slice AND image, [slices, N] (the operand bounds of the tensor-core convolutions, ops.conv2d_nhwc: every
         image is scaled by its own bounds, so its result does not depend on its batch mates)."""
         buf = torch.empty((n, h, w, self.concat_channels), dtype=torch.float32, device=device).permute(0, 3, 1, 2)
-        return buf, buf[:, :self.layers[0][0].in_channels], ops.new_amax(device, (len(self.layers) + 1) * n).view(len(self.layers) + 1, n)
+        # one more row than slices: the actual max|x| of a first slice that arrives pre-split (row 0 then holds ITS bound)
+        return buf, buf[:, :self.layers[0][0].in_channels], ops.new_amax(device, (len(self.layers) + 2) * n).view(len(self.layers) + 2, n)
 
     def _layers_in_place(self, x, buf=None, amax=None):
         """The 3x3 layers write their outputs straight into channel slices of one NHWC buffer
@@ -165,19 +166,54 @@ class _OSAModule(nn.Module):
             src, off = dst, off + cw
         return buf, amax
 
-    def forward_buffer(self, buf, amax):
+    SPLIT_HANDOFF = True      # 3x3 layers write their slices in the operand format of their readers (fod_conv2d_nhwc_split)
+
+    def _split_eligible(self) -> bool:
+        """Whole 32-channel groups everywhere (the split format packs 32 channels into 128 bytes) and plain 3x3 layers."""
+        convs = [layer[0] for layer in self.layers]
+        return (all(cv.kernel_size == (3, 3) and cv.stride == (1, 1) and cv.out_channels % 32 == 0 for cv in convs)
+                and convs[0].in_channels % 32 == 0 and len({cv.out_channels for cv in convs}) == 1 and len(convs) + 1 <= 8
+                and self.concat[0].out_channels % 4 == 0)
+
+    def forward_buffer(self, buf, amax, in_presplit: bool = False):
         """Tensor-core path with x already sitting in the first slice of ``buf`` (and its bound in amax[0]): returns the
         concat-conv output BEFORE the eSE gate, the gate [N,C,1,1] (the consumer fuses the multiplication) and the
-        bound of the output."""
+        bound of the output.  ``in_presplit``: the producer wrote x in the split operand format at the scale of the bound
+        in amax[0]; the actual max|x| is in the last row of amax."""
         c = self.layers[0][0].in_channels
-        amax[1:].zero_()
-        self._layers_in_place(buf[:, :c], buf, amax)
         n, _, h, w = buf.shape
         a_y = ops.new_amax(buf.device, n)
         cout = self.concat[0].out_channels
         # the eSE average comes out of the concat convolution's epilogue as per-tile channel sums: no pass over y
         colsum = torch.empty((n, ops.conv2d_tiles_per_image(h, w), cout), dtype=torch.float32, device=buf.device)
-        y = tcconv.conv(buf, self.concat[0], self.concat[1], relu=True, x_amax=amax, y_amax=a_y, colsum=colsum)
+        nl = len(self.layers)
+        if in_presplit and not (self.SPLIT_HANDOFF and self._split_eligible()):
+            raise RuntimeError("a pre-split first slice needs the split hand-off of this module")
+        if self.SPLIT_HANDOFF and self._split_eligible():
+            # Split hand-off: every 3x3 layer writes its slice in the operand format of its readers (fp16 hi / lo of
+            # y * 2^e, e from the bound l1 * max|x| + beta that it publishes into amax[i + 1]); the next 3x3 layer reads it
+            # without its conversion pass, the concat convolution rescales each slice to its common scale by a power of
+            # two.  The actual maxima (``act``) only feed the next layer's bound, so the bounds do not compound.
+            act = ops.new_amax(buf.device, nl * n).view(nl, n)
+            src, off = buf[:, :c], c
+            for i, layer in enumerate(self.layers):
+                cw = layer[0].out_channels
+                dst = buf[:, off:off + cw]
+                pk, b, cw4 = tcconv.packed(layer[0], layer[1])
+                l1, beta = tcconv.bound_consts(layer[0], layer[1])
+                ops.conv2d_nhwc_split(src, pk, b, cw4, 3, dst, amax[i:i + 1], y_amax=act[i], x_presplit=i > 0 or in_presplit,
+                                      x_actual=act[i - 1] if i > 0 else (amax[nl + 1] if in_presplit else None),
+                                      y_bound=amax[i + 1], y_l1=l1, y_beta=beta)
+                src, off = dst, off + cw
+            pk, b, co4 = tcconv.packed(self.concat[0], self.concat[1])
+            starts = [0] + [c + i * self.layers[0][0].out_channels for i in range(nl)]
+            y = torch.empty((n, h, w, co4), dtype=torch.float32, device=buf.device).permute(0, 3, 1, 2)
+            ops.conv2d_nhwc_split(buf, pk, b, co4, 1, y, amax[:nl + 1], y_amax=a_y, x_presplit_from=0 if in_presplit else c,
+                                  slice_ch=starts, colsum=colsum)
+        else:
+            amax[1:nl + 1].zero_()
+            self._layers_in_place(buf[:, :c], buf, amax)
+            y = tcconv.conv(buf, self.concat[0], self.concat[1], relu=True, x_amax=amax[:nl + 1], y_amax=a_y, colsum=colsum)
         gate = ops.ese_gate(colsum, h * w, self.ese.fc.weight, self.ese.fc.bias)
         return y, gate.view(n, cout, 1, 1), a_y
 
@@ -277,7 +313,15 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
             self._stem1_bound_cache = hit
         return hit[1]
 
-    def tc_stem_u8(self, x_u8, mean, std, out, out_amax):
+    def stem_u8_writes_split(self) -> bool:
+        """tc_stem_u8 leaves its output (the first slice of the stage-2 concat buffer) in the split operand format."""
+        return (self.STEM1_TENSOR_CORES and self.STEM1_SPLIT_OUTPUT and self.STEM3_SPLIT_OUTPUT and "stem" not in self._out_features
+                and self.stem[0].out_channels == 64 and tuple(self.stem[0].weight.shape[1:]) == (3, 3, 3)
+                and self.stem[6].out_channels % 32 == 0 and self._tc_modules()[0].SPLIT_HANDOFF and self._tc_modules()[0]._split_eligible())
+
+    STEM3_SPLIT_OUTPUT = True     # stem_3 writes the operand format of the first OSA layer and of the concat convolution
+
+    def tc_stem_u8(self, x_u8, mean, std, out, out_amax, out_act=None):
         """Raw uint8 images -> stem_1 (normalisation fused; tensor-core kernel ops.stem1_u8_tc, the im2col gathered into
         tensor memory) -> stem_2 -> stem_3 into ``out``; same contract as tc_stem."""
         if self.stem[0].out_channels != 64 or tuple(self.stem[0].weight.shape[1:]) != (3, 3, 3):
@@ -292,6 +336,12 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
             bound = self._stem1_bound(mean, std)
             y = ops.stem1_u8_tc(x_u8, mean, std, pk, b, y_bound=bound)
             y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=bound, y_amax=a2, x_presplit=True)
+            if out_act is not None:     # split hand-off to the first OSA module: out_amax receives the bound, out_act max(y)
+                pk3, b3, c3 = tcconv.packed(self.stem[6], self.stem[7])
+                l1, beta = tcconv.bound_consts(self.stem[6], self.stem[7])
+                ops.conv2d_nhwc_split(y, pk3, b3, c3, 3, out, a2.view(1, n), y_amax=out_act, y_bound=out_amax, y_l1=l1, y_beta=beta,
+                                      stride=2)
+                return
             tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2.view(1, n), y_amax=out_amax)
             return
         if self.STEM1_TENSOR_CORES:
@@ -316,7 +366,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
         y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=a1.view(1, n), y_amax=a2)
         tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2.view(1, n), y_amax=out_amax)
 
-    def tc_body(self, buf, amax, want_amax: bool = False, fuse_gates: bool = False):
+    def tc_body(self, buf, amax, want_amax: bool = False, fuse_gates: bool = False, in_presplit: bool = False):
         """OSA stages from a filled stage-2 concat buffer.  The stage poolings write straight into the first slice of
         the next stage's buffer; the eSE gate of a stage (<= 1, so the bound of the ungated map still holds) is applied
         inside the pooling that consumes it.  For the stages that are FPN inputs the gated map is materialised, unless
@@ -328,7 +378,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
         if "stem" in self._out_features:
             outputs["stem"], bounds["stem"] = buf[:, :mods[0].layers[0][0].in_channels], amax[0]
         for i, (name, mod) in enumerate(zip(self.stage_names, mods)):
-            y, gate, a_y = mod.forward_buffer(buf, amax)
+            y, gate, a_y = mod.forward_buffer(buf, amax, in_presplit=in_presplit and i == 0)
             if name in self._out_features:
                 if fuse_gates:
                     outputs[name], bounds[name], gates[name] = y, a_y, gate

@@ -307,7 +307,8 @@ class CenterNet2Detector(nn.Module):
         chunk of ``chunk`` images, recorded by the stream that fills ``x_u8``) the stem of chunk k starts as soon as
         chunk k has landed, overlapping the copies of the later chunks."""
         buf, amax = self._stem_from_uint8(x_u8, events, chunk)
-        return self.backbone.top_down(*self.backbone.bottom_up.tc_body(buf, amax, fuse_gates=True))
+        vov = self.backbone.bottom_up
+        return self.backbone.top_down(*vov.tc_body(buf, amax, fuse_gates=True, in_presplit=vov.stem_u8_writes_split()))
 
     def _stem_from_uint8(self, x_u8, events=None, chunk: int = 0, into=None):
         """stem_1..3 of a raw uint8 batch into the first slice of a stage-2 concat buffer (``into`` = (buf, first) of a
@@ -316,14 +317,15 @@ class CenterNet2Detector(nn.Module):
         n, _, h, w = x_u8.shape
         buf, first, amax = into if into is not None else vov.tc_new_input_buffer(n, h, w, x_u8.device)
         mean, std = self._mean_std_host()
-        amax[0].zero_()
+        split = vov.stem_u8_writes_split()     # row 0 then receives stem_3's bound (a plain store), the last row max(y)
+        amax[-1 if split else 0].zero_()
         chunk = chunk or n
         main = torch.cuda.current_stream(x_u8.device)
         for k, c0 in enumerate(range(0, n, chunk)):
             c1 = min(c0 + chunk, n)
             if events is not None:
                 main.wait_event(events[k])
-            vov.tc_stem_u8(x_u8[c0:c1], mean, std, first[c0:c1], amax[0, c0:c1])
+            vov.tc_stem_u8(x_u8[c0:c1], mean, std, first[c0:c1], amax[0, c0:c1], amax[-1, c0:c1] if split else None)
         last = getattr(self, "_u8_last", None)
         if last is not None and last[2] is x_u8:     # the ring slot may be refilled once this stem has read it
             ev = torch.cuda.Event()
@@ -499,7 +501,7 @@ class CenterNet2Detector(nn.Module):
 
         def run():
             with ops.zero_arena(dev, self._arena_bytes(n)):      # every counter / bound / padded output: one fill
-                feats = self.backbone.top_down(*vov.tc_body(buf, amax, fuse_gates=True))
+                feats = self.backbone.top_down(*vov.tc_body(buf, amax, fuse_gates=True, in_presplit=vov.stem_u8_writes_split()))
                 return feats, self._head_launch(feats, g["image_hw"], g["out_hw"], None, self.backbone.last_output_bounds)
 
         main = torch.cuda.current_stream(dev)

@@ -85,6 +85,24 @@ def conv(x: torch.Tensor, m: nn.Conv2d, norm: Optional[nn.Module] = None, relu: 
                            a_shift=a_shift, a_relu=a_relu, colsumsq=colsumsq, x_presplit=x_presplit)
 
 
+_bound_cache: "weakref.WeakKeyDictionary[nn.Module, tuple]" = weakref.WeakKeyDictionary()
+
+
+def bound_consts(conv: nn.Conv2d, norm: Optional[nn.Module] = None):
+    """(l1, beta) with  max|relu(conv(x))| <= l1 * max|x| + beta  for any x: the largest absolute row sum of the folded
+    weight and the largest |bias| (+ 0.1 % for the rounding of the sums).  Cached per module until a parameter changes."""
+    key = _versions(conv.weight, conv.bias, *(list(norm.buffers()) if norm is not None else []))
+    hit = _bound_cache.get(conv)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            w, b = folded(conv, norm)
+            l1 = float(w.double().abs().sum((1, 2, 3)).max()) * 1.001
+            beta = float(b.double().abs().max()) * 1.001 if b is not None else 0.0
+        hit = (key, l1, beta)
+        _bound_cache[conv] = hit
+    return hit[1], hit[2]
+
+
 def conv_reference(x: torch.Tensor, m: nn.Conv2d, norm: Optional[nn.Module] = None, relu: bool = False) -> torch.Tensor:
     """The same operation with PyTorch's convolution (CPU tensors, unsupported shapes)."""
     w, b = folded(m, norm)

@@ -534,6 +534,41 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
     return out
 
 
+def conv2d_nhwc_split(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ksize: int, out: Tensor,
+                      x_amax: Tensor, y_amax: Optional[Tensor] = None, x_presplit: bool = False,
+                      x_actual: Optional[Tensor] = None, y_bound: Optional[Tensor] = None, y_l1: float = 0.0, y_beta: float = 0.0,
+                      x_presplit_from: int = -1, slice_ch: Optional[Sequence[int]] = None, colsum: Optional[Tensor] = None,
+                      stride: int = 1) -> Tensor:
+    """conv2d_nhwc (+ ReLU) with the split hand-off of fod_conv2d_nhwc_split: ``y_bound`` ([1, N] or [1]) makes the output
+    leave in the operand format of its consumer and receives the bound that fixes its scale; ``x_presplit`` (3x3) /
+    ``x_presplit_from`` + ``slice_ch`` (1x1 over a concat buffer) say which input channels arrive in that format;
+    ``x_actual``: the actual max|x| per image when ``x_amax`` is such a published bound."""
+    ps_x, ps_y = _pixel_stride(x, "x"), _pixel_stride(out, "out")
+    n, cin, h, w = x.shape
+    _chk(x_amax, torch.float32, "x_amax")
+    x_pi = x_amax.dim() == 2
+    if x_pi and (x_amax.shape[1] != n or not x_amax.is_contiguous()):
+        raise _lib.FodError("conv2d_nhwc_split: per-image x_amax must be a contiguous [k, N] tensor")
+    n_amax = x_amax.shape[0] if x_pi else x_amax.numel()
+    want = n if x_pi else 1
+    for name, t in (("x_actual", x_actual), ("y_bound", y_bound)):
+        if t is not None and (_chk(t, torch.float32, name).numel() != want or not t.is_contiguous()):
+            raise _lib.FodError(f"conv2d_nhwc_split: {name} must hold {want} float(s) like a row of x_amax")
+    y_pi = y_amax is not None and y_amax.numel() == n and n > 1
+    if bias is not None:
+        bias = _chk(bias, torch.float32, "bias").contiguous()
+    sl = None
+    if slice_ch is not None:
+        if len(slice_ch) != n_amax:
+            raise _lib.FodError("conv2d_nhwc_split: one slice start per x_amax row")
+        sl = (ctypes.c_int * len(slice_ch))(*[int(v) for v in slice_ch])
+    _lib.check(_lib.lib().fod_conv2d_nhwc_split(
+        _ptr(x), n, h, w, cin, ps_x, _ptr(x_amax), int(n_amax), int(x_pi) | (int(y_pi) << 1) | (int(bool(x_presplit)) << 2),
+        _ptr(packed), _ptr(bias), cout, ksize, int(stride), 1, _ptr(out), ps_y, _ptr(y_amax), _ptr(colsum), _ptr(x_actual),
+        _ptr(y_bound), float(y_l1), float(y_beta), int(x_presplit_from), sl, _stream()), "fod_conv2d_nhwc_split")
+    return out
+
+
 def conv2d_tiles_per_image(ho: int, wo: int) -> int:
     return int(_lib.lib().fod_conv2d_tiles_per_image(int(ho), int(wo)))
 

@@ -307,6 +307,24 @@ int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_s
                     int amax_per_image, const float* packed, const float* bias, int cout, int ksize, int stride, int relu, float* y,
                     long y_pixel_stride, float* y_amax, const float* residual, int residual_upsample2, const float* a_gate,
                     const float* a_shift, int a_relu, float* colsum, float* colsumsq, fod_stream_t stream);
+/* Split hand-off between convolutions: fod_conv2d_nhwc whose OUTPUT can be written in the operand format of the
+ * convolution that reads it (per pixel and 32 channels [32 x fp16 hi | 32 x fp16 lo] of y * 2^e, the format of
+ * fod_stem1_u8_tc_split) and whose 1x1 form can READ a concat buffer in which the later slices were written that way.
+ * The consumer of a pre-split map skips the fp32 -> fp16 hi / lo conversion of its input; bytes in HBM are unchanged.
+ *   y_bound  : NULL (fp32 output), or [N] / [1] device floats (like x_amax): the output is written split at the scale
+ *              derived from  y_l1 * max|x| + y_beta  >= max|y|  (y_l1 = max_c sum |w[c]|, y_beta = max |bias|; needs ReLU,
+ *              cout and y_pixel_stride multiples of 32), and that bound is stored to y_bound[n] for the consumer
+ *   x_actual : NULL, or the actual max|x| ([N] / [1]) to use in that product when x_amax is itself such a bound (pre-split
+ *              x: amax_per_image bit 2 for a 3x3 layer) - bounds then do not compound along a chain of layers
+ *   x_presplit_from / slice_ch : 1x1 convolution over a concat buffer: input channels >= x_presplit_from are pre-split;
+ *              x_amax row k bounds the slice that starts at channel slice_ch[k] (k < n_amax, ascending, multiples of 32),
+ *              each pre-split slice at the scale of its own row; -1 / NULL: none
+ * residual, a_gate, a_shift and colsumsq of fod_conv2d_nhwc are not available here. */
+int fod_conv2d_nhwc_split(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax, int n_amax,
+                          int amax_per_image, const float* packed, const float* bias, int cout, int ksize, int stride, int relu,
+                          float* y, long y_pixel_stride, float* y_amax, float* colsum, const float* x_actual, float* y_bound,
+                          float y_l1, float y_beta, int x_presplit_from, const int* slice_ch, fod_stream_t stream);
+
 /* GroupNorm (+ ReLU) between two convolutions without materialising the normalised map (CenterNetHead tower,
  * centernet_head.py:61-72, 145-150): the first convolution writes colsum / colsumsq, fod_group_norm_affine turns them
  * into scale / shift [maps][channels] (and the bound max|normalised map| from the bound x_amax of the raw map), the
