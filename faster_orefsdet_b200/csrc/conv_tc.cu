@@ -982,9 +982,10 @@ static int conv2d_nhwc_impl(const float* x, int n, int h, int w, int cin, long x
   for (int k = 0; k < 8; ++k) prm.slice_ch[k] = (slice_ch && k < n_amax) ? slice_ch[k] : 0;
   FOD_REQUIRE(!y_bound || (!residual && !colsum && cout % 32 == 0 && y_pixel_stride % 32 == 0 && relu),
               "fod_conv2d_nhwc_split: a split output needs ReLU, whole 32-channel groups and no residual / colsum");
-  FOD_REQUIRE(x_presplit_from < 0 || (ksize == 1 && stride == 1 && slice_ch && x_presplit_from % 32 == 0 && cin % 32 == 0 &&
+  FOD_REQUIRE(x_presplit_from < 0 || ((ksize == 1 || stride != 1) && slice_ch && x_presplit_from % 32 == 0 && cin % 32 == 0 &&
                                       x_pixel_stride % 32 == 0 && !a_gate && !a_shift),
-              "fod_conv2d_nhwc_split: pre-split slices need a 1x1 convolution over whole 32-channel groups without a_gate / a_shift");
+              "fod_conv2d_nhwc_split: pre-split slices need a single-tap-per-tile convolution (1x1 or stride 2) over whole "
+              "32-channel groups without a_gate / a_shift");
   prm.ho = ho;
   prm.wo = wo;
   prm.a_gate = a_gate;

@@ -309,9 +309,17 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
                                     dtype=torch.float64, device=w.device)
                 rows = (w.double().abs().sum((2, 3)) * xmax.view(1, 3)).sum(1) + (b.double().abs() if b is not None else 0.0)
                 bound = (rows.max() * 1.001).clamp_min(1e-30).float().reshape(1).contiguous()
-            hit = (key, bound)
+            hit = (key, bound, {})
             self._stem1_bound_cache = hit
         return hit[1]
+
+    def _stem1_bound_rows(self, mean, std, n):
+        """The same bound as a [1, n] row (one column per image), cached per batch size."""
+        bound = self._stem1_bound(mean, std)
+        rows = self._stem1_bound_cache[2]
+        if n not in rows:
+            rows[n] = bound.expand(n).contiguous().view(1, n)
+        return rows[n]
 
     def stem_u8_writes_split(self) -> bool:
         """tc_stem_u8 leaves its output (the first slice of the stage-2 concat buffer) in the split operand format."""
@@ -334,14 +342,23 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
             # the conversion pass of every staged tile
             pk, b = self._stem1_packed()
             bound = self._stem1_bound(mean, std)
-            y = ops.stem1_u8_tc(x_u8, mean, std, pk, b, y_bound=bound)
-            y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=bound, y_amax=a2, x_presplit=True)
-            if out_act is not None:     # split hand-off to the first OSA module: out_amax receives the bound, out_act max(y)
+            if out_act is None:
+                y = ops.stem1_u8_tc(x_u8, mean, std, pk, b, y_bound=bound)
+            if out_act is not None:     # split hand-off all the way: stem_2 -> stem_3 -> the first OSA module
+                y = ops.stem1_u8_tc(x_u8, mean, std, pk, b, y_amax=a1, y_bound=bound)
+                pk2, b2, c2 = tcconv.packed(self.stem[3], self.stem[4])
+                l1, beta = tcconv.bound_consts(self.stem[3], self.stem[4])
+                b2nd = ops.new_amax(x_u8.device, n)          # stem_2's published bound, per image
+                y2 = torch.empty((n, y.shape[2], y.shape[3], c2), dtype=torch.float32, device=y.device).permute(0, 3, 1, 2)
+                ops.conv2d_nhwc_split(y, pk2, b2, c2, 3, y2, self._stem1_bound_rows(mean, std, n),
+                                      y_amax=a2, x_presplit=True, x_actual=a1, y_bound=b2nd, y_l1=l1, y_beta=beta)
                 pk3, b3, c3 = tcconv.packed(self.stem[6], self.stem[7])
                 l1, beta = tcconv.bound_consts(self.stem[6], self.stem[7])
-                ops.conv2d_nhwc_split(y, pk3, b3, c3, 3, out, a2.view(1, n), y_amax=out_act, y_bound=out_amax, y_l1=l1, y_beta=beta,
-                                      stride=2)
+                # out_amax receives stem_3's bound, out_act its max(y)
+                ops.conv2d_nhwc_split(y2, pk3, b3, c3, 3, out, b2nd.view(1, n), y_amax=out_act, x_actual=a2, y_bound=out_amax,
+                                      y_l1=l1, y_beta=beta, x_presplit_from=0, slice_ch=[0], stride=2)
                 return
+            y = tcconv.conv(y, self.stem[3], self.stem[4], relu=True, x_amax=bound, y_amax=a2, x_presplit=True)
             tcconv.conv(y, self.stem[6], self.stem[7], relu=True, out=out, x_amax=a2.view(1, n), y_amax=out_amax)
             return
         if self.STEM1_TENSOR_CORES:

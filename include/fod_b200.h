@@ -316,7 +316,7 @@ int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_s
  *              cout and y_pixel_stride multiples of 32), and that bound is stored to y_bound[n] for the consumer
  *   x_actual : NULL, or the actual max|x| ([N] / [1]) to use in that product when x_amax is itself such a bound (pre-split
  *              x: amax_per_image bit 2 for a 3x3 layer) - bounds then do not compound along a chain of layers
- *   x_presplit_from / slice_ch : 1x1 convolution over a concat buffer: input channels >= x_presplit_from are pre-split;
+ *   x_presplit_from / slice_ch : 1x1 (or stride-2) convolution, e.g. over a concat buffer: input channels >= x_presplit_from are pre-split;
  *              x_amax row k bounds the slice that starts at channel slice_ch[k] (k < n_amax, ascending, multiples of 32),
  *              each pre-split slice at the scale of its own row; -1 / NULL: none
  * residual, a_gate, a_shift and colsumsq of fod_conv2d_nhwc are not available here. */
