@@ -218,6 +218,61 @@ def test_stem1_split_output_feeds_the_next_convolution_without_conversion(std, h
     assert torch.equal(ops.conv2d_nhwc(y1s, pk2, b2.to(DEV), 64, 3, True, x_amax=bound, x_presplit=True)[0], y2[1])
 
 
+@pytest.mark.parametrize("cin,sc,h,w", [(128, 64, 40, 56), (64, 96, 20, 28)])
+def test_split_handoff_through_an_osa_block(cin, sc, h, w):
+    """fod_conv2d_nhwc_split on an OSA-shaped block: three 3x3 layers write their slices of one concat buffer in the
+    split operand format (the first reads fp32), each reads its predecessor pre-split, the concat 1x1 reads the fp32
+    slice and the three pre-split slices (each at its own published scale); against float64 and against the fp32
+    hand-off of the same block; images whose magnitudes differ 1 000-fold keep their own scales."""
+    n, cc = 3, 112
+    x = synth.tensor((n, cin, h, w), 201, -1.0, 1.0) * torch.tensor([1.0, 1e-3, 30.0]).view(n, 1, 1, 1)
+    ws = [synth.tensor((sc, cin if i == 0 else sc, 3, 3), 202 + i, -0.05, 0.05) for i in range(3)]
+    bs = [synth.tensor((sc,), 206 + i, -0.2, 0.2) for i in range(3)]
+    wc = synth.tensor((cc, cin + 3 * sc, 1, 1), 210, -0.05, 0.05)
+    bc = synth.tensor((cc,), 211, -0.3, 0.3)
+    outs = [x.double()]
+    for i in range(3):
+        outs.append(F.conv2d(outs[-1], ws[i].double(), bs[i].double(), padding=1).relu())
+    ref = F.conv2d(torch.cat(outs, 1), wc.double(), bc.double()).relu().float()
+
+    def run(split, x=x, n=n):
+        full = n == 3
+        buf = torch.empty((n, h, w, cin + 3 * sc), dtype=torch.float32, device=DEV).permute(0, 3, 1, 2)
+        buf[:, :cin].copy_(x.to(DEV))
+        amax = torch.zeros((4, n), device=DEV)
+        amax[0] = x.abs().amax((1, 2, 3)).to(DEV)
+        act = torch.zeros((3, n), device=DEV)
+        src, off = buf[:, :cin], cin
+        for i in range(3):
+            dst = buf[:, off:off + sc]
+            pk = ops.conv2d_pack(ws[i].to(DEV))
+            if split:
+                l1 = float(ws[i].double().abs().sum((1, 2, 3)).max()) * 1.001
+                beta = float(bs[i].abs().max()) * 1.001
+                ops.conv2d_nhwc_split(src, pk, bs[i].to(DEV), sc, 3, dst, amax[i:i + 1], y_amax=act[i], x_presplit=i > 0,
+                                      x_actual=act[i - 1] if i > 0 else None, y_bound=amax[i + 1], y_l1=l1, y_beta=beta)
+            else:
+                ops.conv2d_nhwc(src, pk, bs[i].to(DEV), sc, 3, True, out=dst, x_amax=amax[i:i + 1], y_amax=amax[i + 1])
+            src, off = dst, off + sc
+        y = torch.empty((n, h, w, cc), dtype=torch.float32, device=DEV).permute(0, 3, 1, 2)
+        pkc = ops.conv2d_pack(wc.to(DEV))
+        if split:
+            ops.conv2d_nhwc_split(buf, pkc, bc.to(DEV), cc, 1, y, amax, x_presplit_from=cin, slice_ch=[0, cin, cin + sc, cin + 2 * sc])
+            for i in range(3 if full else 0):      # the published bounds hold, the actual maxima are the true ones
+                assert bool((amax[i + 1].cpu() >= outs[i + 1].amax((1, 2, 3)).float()).all())
+                assert torch.allclose(act[i].cpu(), outs[i + 1].amax((1, 2, 3)).float(), rtol=1e-5)
+        else:
+            ops.conv2d_nhwc(buf, pkc, bc.to(DEV), cc, 1, True, out=y, x_amax=amax)
+        return y
+
+    y_split, y_fp32 = run(True), run(False)
+    for i in range(n):          # per image: the magnitudes differ by orders
+        _check(y_split[i:i + 1], ref[i:i + 1], f"split hand-off, image {i}")
+        assert float((y_split[i] - y_fp32[i]).abs().max()) <= 4e-6 * float(y_fp32[i].abs().max())
+    # an image alone gives the same bits as inside the batch
+    assert torch.equal(run(True, x[2:3], 1)[0], y_split[2])
+
+
 @pytest.mark.parametrize("up2", [False, True])
 def test_conv2d_nhwc_residual_in_epilogue(up2):
     """FPN top-down step: lateral 1x1 + (nearest 2x upsampled) coarser map, fused into the convolution's epilogue."""
