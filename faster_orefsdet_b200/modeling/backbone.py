@@ -329,13 +329,16 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
 
     STEM3_SPLIT_OUTPUT = True     # stem_3 writes the operand format of the first OSA layer and of the concat convolution
 
-    def tc_stem_u8(self, x_u8, mean, std, out, out_amax, out_act=None):
+    def tc_stem_u8(self, x_u8, mean, std, out, out_amax, out_act=None, scratch=None):
         """Raw uint8 images -> stem_1 (normalisation fused; tensor-core kernel ops.stem1_u8_tc, the im2col gathered into
         tensor memory) -> stem_2 -> stem_3 into ``out``; same contract as tc_stem."""
         if self.stem[0].out_channels != 64 or tuple(self.stem[0].weight.shape[1:]) != (3, 3, 3):
             return self.tc_stem(ops.stem_patches_u8(x_u8, mean, std), None, out, out_amax)
         n = x_u8.shape[0]
-        a1, a2 = ops.new_amax(x_u8.device, n), ops.new_amax(x_u8.device, n)          # per image
+        if scratch is not None:      # [2, n] zeroed floats of the caller (one fill per batch instead of two per chunk)
+            a1, a2 = scratch[0], scratch[1]
+        else:
+            a1, a2 = ops.new_amax(x_u8.device, n), ops.new_amax(x_u8.device, n)          # per image
         if self.STEM1_TENSOR_CORES and self.STEM1_SPLIT_OUTPUT:
             # stem_1 writes the operand format of stem_2 (fp16 hi / lo of y * 2^e) instead of fp32: its output bound follows
             # from the weights and the pixel range alone, so the scale is known before the layer runs and stem_2 skips
@@ -348,7 +351,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
                 y = ops.stem1_u8_tc(x_u8, mean, std, pk, b, y_amax=a1, y_bound=bound)
                 pk2, b2, c2 = tcconv.packed(self.stem[3], self.stem[4])
                 l1, beta = tcconv.bound_consts(self.stem[3], self.stem[4])
-                b2nd = ops.new_amax(x_u8.device, n)          # stem_2's published bound, per image
+                b2nd = torch.empty((n,), dtype=torch.float32, device=x_u8.device)          # stem_2's published bound, per image (a plain store)
                 y2 = torch.empty((n, y.shape[2], y.shape[3], c2), dtype=torch.float32, device=y.device).permute(0, 3, 1, 2)
                 ops.conv2d_nhwc_split(y, pk2, b2, c2, 3, y2, self._stem1_bound_rows(mean, std, n),
                                       y_amax=a2, x_presplit=True, x_actual=a1, y_bound=b2nd, y_l1=l1, y_beta=beta)

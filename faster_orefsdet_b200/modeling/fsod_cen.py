@@ -320,12 +320,14 @@ class CenterNet2Detector(nn.Module):
         split = vov.stem_u8_writes_split()     # row 0 then receives stem_3's bound (a plain store), the last row max(y)
         amax[-1 if split else 0].zero_()
         chunk = chunk or n
+        scratch = torch.zeros((2, n), dtype=torch.float32, device=x_u8.device)     # max(y) of stem_1 / stem_2 per image
         main = torch.cuda.current_stream(x_u8.device)
         for k, c0 in enumerate(range(0, n, chunk)):
             c1 = min(c0 + chunk, n)
             if events is not None:
                 main.wait_event(events[k])
-            vov.tc_stem_u8(x_u8[c0:c1], mean, std, first[c0:c1], amax[0, c0:c1], amax[-1, c0:c1] if split else None)
+            vov.tc_stem_u8(x_u8[c0:c1], mean, std, first[c0:c1], amax[0, c0:c1], amax[-1, c0:c1] if split else None,
+                           scratch=scratch[:, c0:c1])
         last = getattr(self, "_u8_last", None)
         if last is not None and last[2] is x_u8:     # the ring slot may be refilled once this stem has read it
             ev = torch.cuda.Event()
