@@ -136,13 +136,13 @@ struct Params {
   int n_groups, n_group, nhalf, ncol32, cout;
   int relu, num_pairs, pair_units, n_amax, ho, wo, cin;
   int x_amax_stride;    // 0: x_amax holds n_amax scalars (one scale for the whole batch); N: x_amax is [n_amax][N], the scale
-  int x_presplit;       // x already holds [32 x fp16 hi | 32 x fp16 lo] of x * 2^e per 32 channels (e from x_amax): no conversion pass
+  int x_presplit;       // x already holds [16 x fp16 hi | 16 x fp16 lo] of x * 2^e per 16 channels (e from x_amax): no conversion pass
                         // of image n comes from column n, so an image's result does not depend on its batch mates
   int y_amax_per_image; // y_amax is [N]: max|y| per image
   // Split hand-off between convolutions (the producer writes the consumer's operand format; same bytes as fp32):
   const float* x_actual;   // null or [N] / [1] like x_amax: the ACTUAL max|x| (x_amax may be the looser bound that fixed the scale
                            // of a pre-split x); only used for the output bound below
-  float* y_bound;          // null or [N] / [1]: y is written as [32 x fp16 hi | 32 x fp16 lo] of y * 2^e per pixel and 32 channels,
+  float* y_bound;          // null or [N] / [1]: y is written as [16 x fp16 hi | 16 x fp16 lo] of y * 2^e per pixel and 16 channels,
                            // 2^e = pow2_scale(y_l1 * max|x| + y_beta); that bound is published here for the consumer
   float y_l1, y_beta;      // max_c sum|w[c]| and max|bias| (host constants of the layer)
   int x_presplit_from;     // single-tap path: input channels >= this are pre-split, each slice at the scale of ITS x_amax row
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint32_t slab = row_s + (uint32_t)j * kSlabBytes;
           if (ysplit != 0.f && part == parts - 1) {
             // the consumer's operand format: all 32 channels of the row are formed first (the running sums sit where the
-            // packed chunks go), then chunk c = fp16 hi of channels [8c, 8c + 8), chunk 4 + c = the exact remainders
+            // packed chunks go), then per 16 channels [16 x fp16 hi | 16 x the exact remainders]
             float4 xv[8];
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
@@ -464,9 +464,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               split_f16x2(xv[2 * c].z * ysplit, xv[2 * c].w * ysplit, hi[1], lo[1]);
               split_f16x2(xv[2 * c + 1].x * ysplit, xv[2 * c + 1].y * ysplit, hi[2], lo[2]);
               split_f16x2(xv[2 * c + 1].z * ysplit, xv[2 * c + 1].w * ysplit, hi[3], lo[3]);
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(slab + (uint32_t)((c ^ (m & 7)) << 4)), "r"(hi[0]), "r"(hi[1]),
+              const int hp = (c >> 1) * 4 + (c & 1);      // per 16 channels [16 x hi | 16 x lo]: channels [8c, 8c + 8) -> chunk hp, hp + 2
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(slab + (uint32_t)((hp ^ (m & 7)) << 4)), "r"(hi[0]), "r"(hi[1]),
                            "r"(hi[2]), "r"(hi[3]) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(slab + (uint32_t)(((4 + c) ^ (m & 7)) << 4)), "r"(lo[0]),
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(slab + (uint32_t)(((hp + 2) ^ (m & 7)) << 4)), "r"(lo[0]),
                            "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
             }
             continue;
@@ -645,11 +646,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (P.a_shift) shift_row = P.a_shift + (size_t)unit_n * P.cin + cc * kChunk;
         // single-tap path over a concat buffer whose later slices were written pre-split by their producers, each at the
         // scale of its own bound: the stored halves are brought to this launch's common scale by an exact power of two
-        const bool pre = direct && cc * kChunk >= P.x_presplit_from;
+        const int ch16 = cc * kChunk + half * 16;          // first channel of the 16-channel group this warp moves
+        const bool pre = direct && ch16 >= P.x_presplit_from;
         __half2 pre_mult = __float2half2_rn(1.f);
         if (pre) {
           int k = P.n_amax - 1;
-          while (k > 0 && cc * kChunk < P.slice_ch[k]) --k;
+          while (k > 0 && ch16 < P.slice_ch[k]) --k;
           const int step = P.x_amax_stride ? P.x_amax_stride : 1;
           float sk, sk_inv;
           pow2_scale(__ldg(P.x_amax + (size_t)k * step + (P.x_amax_stride ? unit_n : 0)), sk, sk_inv);
@@ -674,15 +676,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t at = qt + (uint32_t)r * 128u;
             const uint32_t key = (uint32_t)(r & 7);
             uint32_t hi[8], lo[8];
-            if (pre) {
+            if (pre) {     // split format: per 16 channels 64 bytes [16 x hi | 16 x lo] = chunks 4h, 4h+1 | 4h+2, 4h+3
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(hi[4 * j]), "=r"(hi[4 * j + 1]), "=r"(hi[4 * j + 2]), "=r"(hi[4 * j + 3])
-                             : "r"(at + ((((uint32_t)(2 * half + j)) ^ key) << 4)));
+                             : "r"(at + ((((uint32_t)(4 * half + j)) ^ key) << 4)));
                 asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(lo[4 * j]), "=r"(lo[4 * j + 1]), "=r"(lo[4 * j + 2]), "=r"(lo[4 * j + 3])
-                             : "r"(at + ((((uint32_t)(4 + 2 * half + j)) ^ key) << 4)));
+                             : "r"(at + ((((uint32_t)(4 * half + 2 + j)) ^ key) << 4)));
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -705,14 +707,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 split_f16x2(x[j].z * xs, x[j].w * xs, hi[2 * j + 1], lo[2 * j + 1]);
               }
             } else {
+              // the converted tile holds [32 x hi | 32 x lo] per row, a pre-split one (written by its producer) per 16 channels
+              // [16 x hi | 16 x lo]: 16-aligned slices of a concat buffer stay whole groups
+              const uint32_t hi0 = P.x_presplit ? (uint32_t)(4 * half) : (uint32_t)(2 * half);
+              const uint32_t lo0 = P.x_presplit ? (uint32_t)(4 * half + 2) : (uint32_t)(4 + 2 * half);
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
                 asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(hi[4 * j]), "=r"(hi[4 * j + 1]), "=r"(hi[4 * j + 2]), "=r"(hi[4 * j + 3])
-                             : "r"(at + ((((uint32_t)(2 * half + j)) ^ key) << 4)));
+                             : "r"(at + (((hi0 + j) ^ key) << 4)));
                 asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(lo[4 * j]), "=r"(lo[4 * j + 1]), "=r"(lo[4 * j + 2]), "=r"(lo[4 * j + 3])
-                             : "r"(at + ((((uint32_t)(4 + 2 * half + j)) ^ key) << 4)));
+                             : "r"(at + (((lo0 + j) ^ key) << 4)));
               }
             }
             const int s = (int)(g % stages);
@@ -971,8 +977,8 @@ static int conv2d_nhwc_impl(const float* x, int n, int h, int w, int cin, long x
   prm.y_amax = y_amax;
   prm.x_amax_stride = (amax_per_image & 1) ? n : 0;
   prm.x_presplit = (amax_per_image & 4) ? 1 : 0;
-  FOD_REQUIRE(!prm.x_presplit || (ksize == 3 && stride == 1 && !a_gate && !a_shift && cin % 32 == 0 && x_pixel_stride % 32 == 0),
-              "fod_conv2d_nhwc: a pre-split input needs a 3x3 stride-1 convolution over whole 32-channel groups without a_gate / a_shift");
+  FOD_REQUIRE(!prm.x_presplit || (ksize == 3 && stride == 1 && !a_gate && !a_shift && cin % 16 == 0 && x_pixel_stride % 16 == 0),
+              "fod_conv2d_nhwc: a pre-split input needs a 3x3 stride-1 convolution over whole 16-channel groups without a_gate / a_shift");
   prm.y_amax_per_image = (amax_per_image & 2) ? 1 : 0;
   prm.x_actual = x_actual;
   prm.y_bound = y_bound;
@@ -980,12 +986,12 @@ static int conv2d_nhwc_impl(const float* x, int n, int h, int w, int cin, long x
   prm.y_beta = y_beta;
   prm.x_presplit_from = x_presplit_from >= 0 ? x_presplit_from : (1 << 30);
   for (int k = 0; k < 8; ++k) prm.slice_ch[k] = (slice_ch && k < n_amax) ? slice_ch[k] : 0;
-  FOD_REQUIRE(!y_bound || (!residual && !colsum && cout % 32 == 0 && y_pixel_stride % 32 == 0 && relu),
-              "fod_conv2d_nhwc_split: a split output needs ReLU, whole 32-channel groups and no residual / colsum");
-  FOD_REQUIRE(x_presplit_from < 0 || ((ksize == 1 || stride != 1) && slice_ch && x_presplit_from % 32 == 0 && cin % 32 == 0 &&
-                                      x_pixel_stride % 32 == 0 && !a_gate && !a_shift),
+  FOD_REQUIRE(!y_bound || (!residual && !colsum && cout % 16 == 0 && y_pixel_stride % 16 == 0 && relu),
+              "fod_conv2d_nhwc_split: a split output needs ReLU, whole 16-channel groups and no residual / colsum");
+  FOD_REQUIRE(x_presplit_from < 0 || ((ksize == 1 || stride != 1) && slice_ch && x_presplit_from % 16 == 0 && cin % 16 == 0 &&
+                                      x_pixel_stride % 16 == 0 && !a_gate && !a_shift),
               "fod_conv2d_nhwc_split: pre-split slices need a single-tap-per-tile convolution (1x1 or stride 2) over whole "
-              "32-channel groups without a_gate / a_shift");
+              "16-channel groups without a_gate / a_shift");
   prm.ho = ho;
   prm.wo = wo;
   prm.a_gate = a_gate;

@@ -64,7 +64,7 @@ struct Params {
   const float* w_inv;    // 1 / weight scale (tail of the packed buffer)
   float* y_amax;         // null, [1] or [N]
   int y_amax_per_image;
-  const float* y_bound;   // split output: device float >= max(y); y is written as [32 x fp16 hi | 32 x fp16 lo] of y * 2^e per 32 channels
+  const float* y_bound;   // split output: device float >= max(y); y is written as [16 x fp16 hi | 16 x fp16 lo] of y * 2^e per 16 channels
   int H, W, ho, wo;
   int tiles_x, tiles_per_img, tiles_total;
   int std_one;
@@ -314,8 +314,8 @@ __global__ void __launch_bounds__(kThreads, 1) stem1_tc_kernel(const __grid_cons
       const uint32_t row_s = row0 + (uint32_t)(i & 1) * kBoxBytes;
       float lmax = 0.f;
       if (ysplit != 0.f) {
-        // the consumer's operand format (conv_tc.cu, converters phase A): chunk c = fp16 hi of channels [8c, 8c + 8),
-        // chunk 4 + c = the exact remainders, of y * 2^e
+        // the split hand-off format (conv_tc.cu): per 16 channels 64 bytes = [16 x fp16 hi | 16 x the exact remainders]
+        // of y * 2^e
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t hi[4], lo[4];
@@ -327,9 +327,10 @@ __global__ void __launch_bounds__(kThreads, 1) stem1_tc_kernel(const __grid_cons
             lmax = fmaxf(lmax, fmaxf(a, b));
             split_f16x2(a * ysplit, b * ysplit, hi[q], lo[q]);
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_s + (uint32_t)((c ^ (lane & 7)) << 4)), "r"(hi[0]),
+          const int hp = (c >> 1) * 4 + (c & 1);      // per 16 channels [16 x hi | 16 x lo]
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_s + (uint32_t)((hp ^ (lane & 7)) << 4)), "r"(hi[0]),
                        "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_s + (uint32_t)(((4 + c) ^ (lane & 7)) << 4)), "r"(lo[0]),
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_s + (uint32_t)(((hp + 2) ^ (lane & 7)) << 4)), "r"(lo[0]),
                        "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
         }
       } else {

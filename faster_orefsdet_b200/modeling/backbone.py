@@ -169,10 +169,10 @@ class _OSAModule(nn.Module):
     SPLIT_HANDOFF = True      # 3x3 layers write their slices in the operand format of their readers (fod_conv2d_nhwc_split)
 
     def _split_eligible(self) -> bool:
-        """Whole 32-channel groups everywhere (the split format packs 32 channels into 128 bytes) and plain 3x3 layers."""
+        """Whole 16-channel groups everywhere (the split format packs 16 channels into 64 bytes) and plain 3x3 layers."""
         convs = [layer[0] for layer in self.layers]
-        return (all(cv.kernel_size == (3, 3) and cv.stride == (1, 1) and cv.out_channels % 32 == 0 for cv in convs)
-                and convs[0].in_channels % 32 == 0 and len({cv.out_channels for cv in convs}) == 1 and len(convs) + 1 <= 8
+        return (all(cv.kernel_size == (3, 3) and cv.stride == (1, 1) and cv.out_channels % 16 == 0 for cv in convs)
+                and convs[0].in_channels % 16 == 0 and len({cv.out_channels for cv in convs}) == 1 and len(convs) + 1 <= 8
                 and self.concat[0].out_channels % 4 == 0)
 
     def forward_buffer(self, buf, amax, in_presplit: bool = False):
@@ -325,7 +325,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
         """tc_stem_u8 leaves its output (the first slice of the stage-2 concat buffer) in the split operand format."""
         return (self.STEM1_TENSOR_CORES and self.STEM1_SPLIT_OUTPUT and self.STEM3_SPLIT_OUTPUT and "stem" not in self._out_features
                 and self.stem[0].out_channels == 64 and tuple(self.stem[0].weight.shape[1:]) == (3, 3, 3)
-                and self.stem[6].out_channels % 32 == 0 and self._tc_modules()[0].SPLIT_HANDOFF and self._tc_modules()[0]._split_eligible())
+                and self.stem[6].out_channels % 16 == 0 and self._tc_modules()[0].SPLIT_HANDOFF and self._tc_modules()[0]._split_eligible())
 
     STEM3_SPLIT_OUTPUT = True     # stem_3 writes the operand format of the first OSA layer and of the concat convolution
 

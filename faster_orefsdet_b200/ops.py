@@ -481,7 +481,7 @@ def conv2d_nhwc(x: Tensor, packed: Tensor, bias: Optional[Tensor], cout: int, ks
                 a_relu: bool = False, colsumsq: Optional[Tensor] = None, x_presplit: bool = False) -> Tensor:
     """Convolution with padding ksize//2 on the tensor cores (fp16-split operands, fp32 accuracy), bias + optional
     ReLU fused.  ``x_presplit``: x is not fp32 but the kernel's own operand format, written by a producer that was given
-    the bound in ``x_amax`` (stem1_u8_tc(y_bound=...)): per pixel and 32 channels [32 x fp16 hi | 32 x fp16 lo] of
+    the bound in ``x_amax`` (stem1_u8_tc(y_bound=...)): per pixel and 16 channels [16 x fp16 hi | 16 x fp16 lo] of
     x * 2^e - the 3x3 layer then skips its conversion pass.  x [N,Cin,H,W] NHWC view (may be a channel slice of a wider channels_last buffer); ``out`` likewise.
     ``x_amax``: device floats bounding max|x|: [k] (k = 1..8 values, one scale for the batch; computed with ``absmax`` when
     omitted, which needs a dense x) or [k, N] (image n is scaled by the maximum of column n: its result does not depend

@@ -284,8 +284,9 @@ int fod_batched_nms(const float* boxes, const float* scores, const int64_t* idxs
  *             produced x normally reports it (y_amax below).
  *   amax_per_image : bit 0: x_amax is [n_amax][N] and image n is scaled by the maximum of column n, so that the result of
  *             an image does not depend on which other images share the batch; bit 1: y_amax is [N], max|y| per image
- *               bit 2: x is PRE-SPLIT (written by fod_stem1_u8_tc_split with y_bound = this x_amax): per pixel and 32 channels
- *               [32 x fp16 hi | 32 x fp16 lo] of x * 2^e; 3x3 stride-1 layers only, no a_gate / a_shift; the conversion pass is skipped
+ *               bit 2: x is PRE-SPLIT (written by fod_stem1_u8_tc_split / fod_conv2d_nhwc_split with y_bound = this x_amax): per
+ *               pixel and 16 channels [16 x fp16 hi | 16 x fp16 lo] of x * 2^e; 3x3 stride-1 layers only, cin a multiple of 16, no
+ *               a_gate / a_shift; the conversion pass is skipped
  *   packed  : fod_conv2d_pack_weights output (fod_conv2d_packed_floats floats)
  *   bias    : [cout] or NULL
  *   y       : [N][Ho][Wo] pixels of y_pixel_stride floats, the first cout are written
@@ -308,16 +309,16 @@ int fod_conv2d_nhwc(const float* x, int n, int h, int w, int cin, long x_pixel_s
                     long y_pixel_stride, float* y_amax, const float* residual, int residual_upsample2, const float* a_gate,
                     const float* a_shift, int a_relu, float* colsum, float* colsumsq, fod_stream_t stream);
 /* Split hand-off between convolutions: fod_conv2d_nhwc whose OUTPUT can be written in the operand format of the
- * convolution that reads it (per pixel and 32 channels [32 x fp16 hi | 32 x fp16 lo] of y * 2^e, the format of
+ * convolution that reads it (per pixel and 16 channels [16 x fp16 hi | 16 x fp16 lo] of y * 2^e, the format of
  * fod_stem1_u8_tc_split) and whose 1x1 form can READ a concat buffer in which the later slices were written that way.
  * The consumer of a pre-split map skips the fp32 -> fp16 hi / lo conversion of its input; bytes in HBM are unchanged.
  *   y_bound  : NULL (fp32 output), or [N] / [1] device floats (like x_amax): the output is written split at the scale
  *              derived from  y_l1 * max|x| + y_beta  >= max|y|  (y_l1 = max_c sum |w[c]|, y_beta = max |bias|; needs ReLU,
- *              cout and y_pixel_stride multiples of 32), and that bound is stored to y_bound[n] for the consumer
+ *              cout and y_pixel_stride multiples of 16), and that bound is stored to y_bound[n] for the consumer
  *   x_actual : NULL, or the actual max|x| ([N] / [1]) to use in that product when x_amax is itself such a bound (pre-split
  *              x: amax_per_image bit 2 for a 3x3 layer) - bounds then do not compound along a chain of layers
  *   x_presplit_from / slice_ch : 1x1 (or stride-2) convolution, e.g. over a concat buffer: input channels >= x_presplit_from are pre-split;
- *              x_amax row k bounds the slice that starts at channel slice_ch[k] (k < n_amax, ascending, multiples of 32),
+ *              x_amax row k bounds the slice that starts at channel slice_ch[k] (k < n_amax, ascending, multiples of 16),
  *              each pre-split slice at the scale of its own row; -1 / NULL: none
  * residual, a_gate, a_shift and colsumsq of fod_conv2d_nhwc are not available here. */
 int fod_conv2d_nhwc_split(const float* x, int n, int h, int w, int cin, long x_pixel_stride, const float* x_amax, int n_amax,
@@ -391,7 +392,7 @@ int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* mean3, cons
 int fod_stem1_u8_tc(const uint8_t* x, int n, int h, int w, const float* mean3, const float* std3, const float* packed,
                     const float* bias, float* y, long y_pixel_stride, float* y_amax, int amax_per_image, fod_stream_t stream);
 /* fod_stem1_u8_tc with the output written in the OPERAND FORMAT of the 3x3 convolution that reads it instead of fp32:
- * per pixel and group of 32 channels 128 bytes = [32 x fp16 hi | 32 x fp16 lo] of y * 2^e (hi = fp16(y * 2^e), lo the
+ * per pixel and group of 16 channels 64 bytes = [16 x fp16 hi | 16 x fp16 lo] of y * 2^e (hi = fp16(y * 2^e), lo the
  * exact remainder rounded to fp16), 2^e = the scale fod_conv2d_nhwc derives from a bound on max|y|.
  *   y_bound : ONE device float >= every output value; it is known before the layer runs: the pixel range is
  *             [0, 255], so max_c (sum_k |w[c][k]| * max(|0 - mean|, |255 - mean|) / std + |bias[c]|) holds for every image.

@@ -218,7 +218,7 @@ def test_stem1_split_output_feeds_the_next_convolution_without_conversion(std, h
     assert torch.equal(ops.conv2d_nhwc(y1s, pk2, b2.to(DEV), 64, 3, True, x_amax=bound, x_presplit=True)[0], y2[1])
 
 
-@pytest.mark.parametrize("cin,sc,h,w", [(128, 64, 40, 56), (64, 96, 20, 28)])
+@pytest.mark.parametrize("cin,sc,h,w", [(128, 64, 40, 56), (64, 96, 20, 28), (112, 80, 20, 28), (48, 112, 12, 20)])
 def test_split_handoff_through_an_osa_block(cin, sc, h, w):
     """fod_conv2d_nhwc_split on an OSA-shaped block: three 3x3 layers write their slices of one concat buffer in the
     split operand format (the first reads fp32), each reads its predecessor pre-split, the concat 1x1 reads the fp32
