@@ -70,6 +70,7 @@ _PROTOTYPES = {
                                _vp], _i),
     "fod_stem1_u8": ([_vp, _i, _i, _i, ctypes.POINTER(_f), ctypes.POINTER(_f), _vp, _vp, _vp, _vp, _i, _vp], _i),
     "fod_maxpool3x3s2_nhwc": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _vp, ctypes.c_long, _vp], _i),
+    "fod_maxpool3x3s2_nhwc_split": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _vp, ctypes.c_long, _vp, _vp], _i),
     "fod_conv2d_packed_floats": ([_i, _i, _i], ctypes.c_size_t),
     "fod_conv2d_pack_weights": ([_vp, _i, _i, _i, _vp, _vp], _i),
     "fod_conv2d_nhwc": ([_vp, _i, _i, _i, _i, ctypes.c_long, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp, ctypes.c_long, _vp, _vp,

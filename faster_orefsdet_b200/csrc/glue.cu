@@ -7,6 +7,7 @@
 //                          vovnet.py eSEModule; the gate is >= 0, so it commutes with the max), written straight into a
 //                          channel slice of the next stage's concat buffer.
 // One float4 (4 channels) per thread, coalesced 128-bit accesses; the 9-fold window overlap is served by L1/L2.
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace fod {
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 2) stem1_u8_tile_kernel(const uint8_
 // fully coalesced; the 3x3 windows of neighbouring outputs overlap by one column / row, which the L1 serves.
 __global__ void __launch_bounds__(kThreads) maxpool_kernel(const float* __restrict__ x, long xs, int H, int W, int C,
                                                            const float* __restrict__ gate, float* __restrict__ y, long ys,
-                                                           int Ho, int Wo) {
+                                                           int Ho, int Wo, const float* __restrict__ y_bound) {
   const int c4n = C >> 2;
   const int item = (int)(blockIdx.x * kThreads + threadIdx.x);
   if (item >= Wo * c4n) return;
@@ -384,7 +385,25 @@ __global__ void __launch_bounds__(kThreads) maxpool_kernel(const float* __restri
     const float4 g = ldg4(gate + n * C + c4 * 4);
     m.x *= g.x; m.y *= g.y; m.z *= g.z; m.w *= g.w;
   }
-  *reinterpret_cast<float4*>(y + ((n * Ho + oy) * (size_t)Wo + ox) * ys + c4 * 4) = m;
+  float* out = y + ((n * Ho + oy) * (size_t)Wo + ox) * ys;
+  if (y_bound) {
+    // split hand-off format of the convolutions that read this map (conv_tc.cu): per 16 channels 64 bytes =
+    // [16 x fp16 hi | 16 x fp16 lo] of y * 2^e, 2^e = pow2_scale(y_bound[n]) - the consumer derives the same scale
+    const uint32_t E = (__float_as_uint(__ldg(y_bound + n)) >> 23) & 0xFFu;
+    const float sc = (E < 32u || E > 240u) ? 1.f : __uint_as_float((267u - E) << 23);
+    const __half2 h0 = __floats2half2_rn(m.x * sc, m.y * sc), h1 = __floats2half2_rn(m.z * sc, m.w * sc);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(m.x * sc - f0.x, m.y * sc - f0.y), l1 = __floats2half2_rn(m.z * sc - f1.x, m.w * sc - f1.y);
+    const int ch = c4 * 4, grp = ch >> 4, q = ch & 15;       // 4 channels = 8 bytes of hi and 8 bytes of lo inside the group
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h0); hv.y = *reinterpret_cast<const uint32_t*>(&h1);
+    lv.x = *reinterpret_cast<const uint32_t*>(&l0); lv.y = *reinterpret_cast<const uint32_t*>(&l1);
+    uint8_t* gb = reinterpret_cast<uint8_t*>(out) + grp * 64;
+    *reinterpret_cast<uint2*>(gb + q * 2) = hv;
+    *reinterpret_cast<uint2*>(gb + 32 + q * 2) = lv;
+  } else {
+    *reinterpret_cast<float4*>(out + c4 * 4) = m;
+  }
 }
 
 }  // namespace glue
@@ -446,8 +465,8 @@ extern "C" int fod_stem1_u8(const uint8_t* x, int n, int h, int w, const float* 
   return FOD_OK;
 }
 
-extern "C" int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate,
-                                     float* y, long y_pixel_stride, fod_stream_t stream) {
+static int maxpool_impl(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate, float* y,
+                        long y_pixel_stride, const float* y_bound, fod_stream_t stream) {
   FOD_REQUIRE(x && y, "fod_maxpool3x3s2_nhwc: null pointer");
   FOD_REQUIRE(n >= 0 && h >= 3 && w >= 3 && c > 0 && c % 4 == 0 && x_pixel_stride % 4 == 0 && y_pixel_stride % 4 == 0 &&
                   x_pixel_stride >= c && y_pixel_stride >= c, "fod_maxpool3x3s2_nhwc: bad sizes (channels / strides multiples of 4)");
@@ -457,7 +476,20 @@ extern "C" int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c,
   const int ho = (h - 3 + 1) / 2 + 1, wo = (w - 3 + 1) / 2 + 1;
   FOD_REQUIRE(ho <= 65535 && n <= 65535, "fod_maxpool3x3s2_nhwc: more than 65535 output rows or images");
   const dim3 grid((unsigned)(((long)wo * (c / 4) + glue::kThreads - 1) / glue::kThreads), (unsigned)ho, (unsigned)n);
-  glue::maxpool_kernel<<<grid, glue::kThreads, 0, as_stream(stream)>>>(x, x_pixel_stride, h, w, c, gate, y, y_pixel_stride, ho, wo);
+  FOD_REQUIRE(!y_bound || (c % 16 == 0 && y_pixel_stride % 16 == 0), "fod_maxpool3x3s2_nhwc_split: whole 16-channel groups needed");
+  glue::maxpool_kernel<<<grid, glue::kThreads, 0, as_stream(stream)>>>(x, x_pixel_stride, h, w, c, gate, y, y_pixel_stride, ho, wo,
+                                                                       y_bound);
   FOD_CUDA_LAUNCH_CHECK("fod_maxpool3x3s2_nhwc");
   return FOD_OK;
+}
+
+extern "C" int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate,
+                                     float* y, long y_pixel_stride, fod_stream_t stream) {
+  return maxpool_impl(x, n, h, w, c, x_pixel_stride, gate, y, y_pixel_stride, nullptr, stream);
+}
+
+extern "C" int fod_maxpool3x3s2_nhwc_split(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate,
+                                           float* y, long y_pixel_stride, const float* y_bound, fod_stream_t stream) {
+  FOD_REQUIRE(y_bound, "fod_maxpool3x3s2_nhwc_split: y_bound is required");
+  return maxpool_impl(x, n, h, w, c, x_pixel_stride, gate, y, y_pixel_stride, y_bound, stream);
 }

@@ -175,11 +175,12 @@ class _OSAModule(nn.Module):
                 and convs[0].in_channels % 16 == 0 and len({cv.out_channels for cv in convs}) == 1 and len(convs) + 1 <= 8
                 and self.concat[0].out_channels % 4 == 0)
 
-    def forward_buffer(self, buf, amax, in_presplit: bool = False):
+    def forward_buffer(self, buf, amax, in_presplit: bool = False, in_bound_is_actual: bool = False):
         """Tensor-core path with x already sitting in the first slice of ``buf`` (and its bound in amax[0]): returns the
         concat-conv output BEFORE the eSE gate, the gate [N,C,1,1] (the consumer fuses the multiplication) and the
         bound of the output.  ``in_presplit``: the producer wrote x in the split operand format at the scale of the bound
-        in amax[0]; the actual max|x| is in the last row of amax."""
+        in amax[0]; the actual max|x| is in the last row of amax, unless ``in_bound_is_actual`` (amax[0] is it: the pooling's
+        bound is the maximum of its source)."""
         c = self.layers[0][0].in_channels
         n, _, h, w = buf.shape
         a_y = ops.new_amax(buf.device, n)
@@ -202,7 +203,7 @@ class _OSAModule(nn.Module):
                 pk, b, cw4 = tcconv.packed(layer[0], layer[1])
                 l1, beta = tcconv.bound_consts(layer[0], layer[1])
                 ops.conv2d_nhwc_split(src, pk, b, cw4, 3, dst, amax[i:i + 1], y_amax=act[i], x_presplit=i > 0 or in_presplit,
-                                      x_actual=act[i - 1] if i > 0 else (amax[nl + 1] if in_presplit else None),
+                                      x_actual=act[i - 1] if i > 0 else (amax[nl + 1] if in_presplit and not in_bound_is_actual else None),
                                       y_bound=amax[i + 1], y_l1=l1, y_beta=beta)
                 src, off = dst, off + cw
             pk, b, co4 = tcconv.packed(self.concat[0], self.concat[1])
@@ -327,6 +328,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
                 and self.stem[0].out_channels == 64 and tuple(self.stem[0].weight.shape[1:]) == (3, 3, 3)
                 and self.stem[6].out_channels % 16 == 0 and self._tc_modules()[0].SPLIT_HANDOFF and self._tc_modules()[0]._split_eligible())
 
+    POOL_SPLIT_OUTPUT = False     # (True once verified on the GPU) the stage poolings write the next stage's first slice in the split format
     STEM3_SPLIT_OUTPUT = True     # stem_3 writes the operand format of the first OSA layer and of the concat convolution
 
     def tc_stem_u8(self, x_u8, mean, std, out, out_amax, out_act=None, scratch=None):
@@ -398,7 +400,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
         if "stem" in self._out_features:
             outputs["stem"], bounds["stem"] = buf[:, :mods[0].layers[0][0].in_channels], amax[0]
         for i, (name, mod) in enumerate(zip(self.stage_names, mods)):
-            y, gate, a_y = mod.forward_buffer(buf, amax, in_presplit=in_presplit and i == 0)
+            y, gate, a_y = mod.forward_buffer(buf, amax, in_presplit=in_presplit, in_bound_is_actual=i > 0)
             if name in self._out_features:
                 if fuse_gates:
                     outputs[name], bounds[name], gates[name] = y, a_y, gate
@@ -409,7 +411,10 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
             if i + 1 < len(mods):
                 h, w = (y.shape[2] - 2) // 2 + 1, (y.shape[3] - 2) // 2 + 1
                 buf, first, amax = mods[i + 1].new_buffer(n, h, w, y.device)
-                ops.maxpool3x3s2_nhwc(y, gate, out=first)
+                # the pooling hands the next stage its first slice in the split format when that stage reads it that way:
+                # the bound is the actual maximum of the pooled map's source (the gate is <= 1)
+                in_presplit = self.POOL_SPLIT_OUTPUT and mods[i + 1].SPLIT_HANDOFF and mods[i + 1]._split_eligible() and a_y.numel() == n
+                ops.maxpool3x3s2_nhwc(y, gate, out=first, y_bound=a_y if in_presplit else None)
                 amax[0].copy_(a_y)
         if fuse_gates:
             return outputs, bounds, gates

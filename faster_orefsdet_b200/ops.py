@@ -711,9 +711,11 @@ def stem1_u8_tc(x: Tensor, mean: Sequence[float], std: Sequence[float], packed: 
     return out
 
 
-def maxpool3x3s2_nhwc(x: Tensor, gate: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
-    """nn.MaxPool2d(3, 2, ceil_mode=True) of an NHWC view, times an optional per-(image, channel) gate [N,C];
-    ``out`` may be a channel slice of a wider NHWC buffer."""
+def maxpool3x3s2_nhwc(x: Tensor, gate: Optional[Tensor] = None, out: Optional[Tensor] = None,
+                      y_bound: Optional[Tensor] = None) -> Tensor:
+    """nn.MaxPool2d(3, 2, ceil_mode=True) of an NHWC view, times an optional per-(image, channel) gate [N,C] (<= 1);
+    ``out`` may be a channel slice of a wider NHWC buffer.  ``y_bound`` [N] (>= max|x| per image): the output leaves in
+    the split hand-off format of conv2d_nhwc_split instead of fp32."""
     ps_x = _pixel_stride(x, "x")
     n, c, h, w = x.shape
     ho, wo = (h - 2) // 2 + 1, (w - 2) // 2 + 1
@@ -724,6 +726,12 @@ def maxpool3x3s2_nhwc(x: Tensor, gate: Optional[Tensor] = None, out: Optional[Te
     ps_y = _pixel_stride(out, "out")
     if gate is not None:
         gate = _chk(gate, torch.float32, "gate").reshape(n, c).contiguous()
+    if y_bound is not None:
+        if _chk(y_bound, torch.float32, "y_bound").numel() != n or not y_bound.is_contiguous():
+            raise _lib.FodError("maxpool3x3s2_nhwc: y_bound must hold N floats")
+        _lib.check(_lib.lib().fod_maxpool3x3s2_nhwc_split(_ptr(x), n, h, w, c, ps_x, _ptr(gate), _ptr(out), ps_y, _ptr(y_bound),
+                                                          _stream()), "fod_maxpool3x3s2_nhwc_split")
+        return out
     _lib.check(_lib.lib().fod_maxpool3x3s2_nhwc(_ptr(x), n, h, w, c, ps_x, _ptr(gate), _ptr(out), ps_y, _stream()),
                "fod_maxpool3x3s2_nhwc")
     return out

@@ -406,6 +406,13 @@ int fod_stem1_u8_tc_split(const uint8_t* x, int n, int h, int w, const float* me
 
 int fod_maxpool3x3s2_nhwc(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate, float* y,
                           long y_pixel_stride, fod_stream_t stream);
+/* the same pooling with the output in the split hand-off format of fod_conv2d_nhwc_split (per 16 channels [16 x fp16 hi |
+ * 16 x fp16 lo] of y * 2^e): y_bound [N] device floats >= max|x| of each image (the y_amax of the convolution that wrote x;
+ * the gate is <= 1, so it bounds the pooled map too); c and y_pixel_stride multiples of 16.  The readers are
+ * fod_conv2d_nhwc with x_amax = y_bound and amax_per_image bit 2 (3x3) or x_presplit_from (1x1). */
+int fod_maxpool3x3s2_nhwc_split(const float* x, int n, int h, int w, int c, long x_pixel_stride, const float* gate, float* y,
+                                long y_pixel_stride, const float* y_bound, fod_stream_t stream);
+
 
 #ifdef __cplusplus
 }

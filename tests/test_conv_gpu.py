@@ -273,6 +273,31 @@ def test_split_handoff_through_an_osa_block(cin, sc, h, w):
     assert torch.equal(run(True, x[2:3], 1)[0], y_split[2])
 
 
+@pytest.mark.parametrize("c,h,w", [(112, 41, 56), (256, 20, 27)])
+def test_maxpool_split_output_feeds_a_3x3_convolution(c, h, w):
+    """The stage pooling writing the split hand-off format (bound = the maximum of its source, gate <= 1) and the 3x3
+    layer that reads it pre-split, against float64 and against the fp32 hand-off; odd sizes (ceil mode)."""
+    n, co = 2, 80
+    x = synth.tensor((n, c, h, w), 221, 0.0, 3.0) * torch.tensor([1.0, 40.0]).view(n, 1, 1, 1)
+    gate = synth.tensor((n, c), 222, 0.0, 1.0)
+    wt = synth.tensor((co, c, 3, 3), 223, -0.05, 0.05)
+    b = synth.tensor((co,), 224, -0.3, 0.3)
+    pooled = F.max_pool2d(x.double(), 3, 2, ceil_mode=True) * gate.double().view(n, c, 1, 1)
+    ref = F.conv2d(pooled, wt.double(), b.double(), padding=1).relu().float()
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    bound = x.amax((1, 2, 3)).to(DEV).contiguous()
+    pk = ops.conv2d_pack(wt.to(DEV))
+    ps = ops.maxpool3x3s2_nhwc(xd, gate.to(DEV), y_bound=bound)
+    y = torch.empty((n, ref.shape[2], ref.shape[3], co), dtype=torch.float32, device=DEV).permute(0, 3, 1, 2)
+    ops.conv2d_nhwc_split(ps, pk, b.to(DEV), co, 3, y, bound.view(1, n), x_presplit=True)
+    _check(y, ref, "3x3 on a pre-split pooled map")
+    pf = ops.maxpool3x3s2_nhwc(xd, gate.to(DEV))
+    assert float((pf.cpu() - pooled.float()).abs().max()) <= 1e-6 * float(pooled.max())
+    yf = ops.conv2d_nhwc(pf, pk, b.to(DEV), co, 3, True, x_amax=bound.view(1, n))
+    for i in range(n):
+        assert float((y[i] - yf[i]).abs().max()) <= 4e-6 * float(yf[i].abs().max())
+
+
 @pytest.mark.parametrize("up2", [False, True])
 def test_conv2d_nhwc_residual_in_epilogue(up2):
     """FPN top-down step: lateral 1x1 + (nearest 2x upsampled) coarser map, fused into the convolution's epilogue."""
