@@ -328,7 +328,7 @@ class VoVNet(Backbone):     # detectron2's build_backbone asserts isinstance(bac
                 and self.stem[0].out_channels == 64 and tuple(self.stem[0].weight.shape[1:]) == (3, 3, 3)
                 and self.stem[6].out_channels % 16 == 0 and self._tc_modules()[0].SPLIT_HANDOFF and self._tc_modules()[0]._split_eligible())
 
-    POOL_SPLIT_OUTPUT = False     # (True once verified on the GPU) the stage poolings write the next stage's first slice in the split format
+    POOL_SPLIT_OUTPUT = True      # the stage poolings write the next stage's first slice in the split format
     STEM3_SPLIT_OUTPUT = True     # stem_3 writes the operand format of the first OSA layer and of the concat convolution
 
     def tc_stem_u8(self, x_u8, mean, std, out, out_amax, out_act=None, scratch=None):
